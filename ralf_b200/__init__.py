@@ -1,0 +1,2 @@
+"""ralf_b200 -- B200-native (sm_100a) implementation of the RALF retrieval + layout-generation hot path."""
+__version__ = "0.1.0"

@@ -1,0 +1,75 @@
+"""ctypes binding of the C ABI declared in include/ralf_b200.h.
+
+There is deliberately no fallback: if the CUDA library is missing, importing the product path
+raises.  (The library is built in-tree by ``ralf_b200.build`` / ``__graft_entry__.build``.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libralf_b200.so")
+
+STATUS = {
+    0: "RALF_OK", -1: "RALF_ERR_SHAPE", -2: "RALF_ERR_ALIGN", -3: "RALF_ERR_NULL", -4: "RALF_ERR_CUDA",
+    -5: "RALF_ERR_DRIVER", -6: "RALF_ERR_ARCH", -7: "RALF_ERR_WORKSPACE",
+}
+
+
+class RalfError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("a_plane", C.c_longlong), ("lda", C.c_int),
+        ("W", C.c_void_p), ("w_plane", C.c_longlong), ("ldw", C.c_int),
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+        ("npass", C.c_int), ("block_n", C.c_int),
+        ("bias", C.c_void_p), ("act", C.c_int), ("post_relu", C.c_int),
+        ("res", C.c_void_p), ("res_split", C.c_void_p), ("res_plane", C.c_longlong),
+        ("res_ld", C.c_int), ("res_row_mod", C.c_int),
+        ("out_f32", C.c_void_p), ("out_split", C.c_void_p), ("out_plane", C.c_longlong),
+        ("out_split_lo", C.c_int), ("out_ld", C.c_int), ("out_col0", C.c_int),
+        ("rows_per_group", C.c_int), ("group_stride", C.c_int), ("group_offset", C.c_int),
+    ]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RalfError(
+                f"{LIB_PATH} is missing: the sm_100a CUDA library has not been built "
+                "(run `python -m ralf_b200.build`); there is no CPU fallback."
+            )
+        L = C.CDLL(LIB_PATH)
+        L.ralf_last_cuda_error.restype = C.c_char_p
+        L.ralf_knn_workspace_bytes.restype = C.c_size_t
+        L.ralf_knn_workspace_bytes.argtypes = [C.c_int] * 4
+        L.ralf_knn_topk.argtypes = [
+            C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_float,
+            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+        ]
+        L.ralf_knn_topk_exact.argtypes = [
+            C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_longlong,
+            C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+        ]
+        L.ralf_knn_merge.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]
+        L.ralf_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
+        L.ralf_check_device.argtypes = [C.c_int]
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = STATUS.get(rc, str(rc))
+        if rc == -4:
+            msg += ": " + lib().ralf_last_cuda_error().decode()
+        raise RalfError(f"{what} failed: {msg}")

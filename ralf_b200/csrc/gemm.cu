@@ -1,0 +1,415 @@
+// tcgen05 GEMM for every dense contraction on the RALF hot path (linear layers, 1x1 convs,
+// im2col'd 3x3/7x7 convs, K/V projections, LM head):
+//
+//     D[M,N] = A[M,K] . W[N,K]^T   (+ bias[N]) (activation) (+ residual)   fp32 accumulate in TMEM
+//
+// Both operands are K-major bf16 ("split" format: plane 0 = hi = bf16(x), plane 1 = lo =
+// bf16(x - hi)).  NPASS = 3 issues hi*lo + lo*hi + hi*hi per k-step, which reproduces an fp32
+// product to ~2^-17 relative -- that is what lets the logits / token ids match the fp32
+// reference (common/common.py:84-135, nn.Linear / nn.Conv2d in fp32).  NPASS = 1 is plain bf16.
+//
+// One CTA per 128 x BN output tile.  Warp 0 = TMA producer (SWIZZLE_128B boxes of 64 bf16 along
+// K), warp 1 = TMEM allocator + single-thread tcgen05.mma issuer, warps 2-5 = epilogue
+// (tcgen05.ld 32x32b, one accumulator row per thread, fused bias / ReLU / GELU / residual /
+// bf16 split, direct vectorised global stores).  smem ring of STAGES stages, full/empty
+// mbarriers, tcgen05.commit releases stages and signals the epilogue.
+#include <math.h>
+#include <stdio.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "ralf_internal.h"
+
+namespace ralf {
+
+struct GemmEpi {
+  const float* bias;               // [N] or null
+  const float* res;                // fp32 residual or null
+  const __nv_bfloat16* res_split;  // split residual (hi plane; lo at + res_plane) or null
+  long long res_plane;
+  int res_ld;
+  int res_row_mod;  // > 0: residual row = row % res_row_mod (row-broadcast table)
+  float* out_f32;   // or null
+  __nv_bfloat16* out_split;  // hi plane; lo plane at + out_plane (or null)
+  long long out_plane;
+  int out_ld;
+  int out_col0;
+  int rows_per_group, group_stride, group_offset;  // out_row = (r/rpg)*gs + go + r%rpg
+  int act;                                         // 0 none, 1 relu, 2 gelu (erf)
+  int post_relu;                                   // relu after the residual add
+  int vec_ok;                                      // all strides/offsets allow 16-byte accesses
+  int split_lo;                                    // write the lo plane too
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == 1) return fmaxf(x, 0.f);
+  if (act == 2) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+  return x;
+}
+
+template <int BN, int NPASS>
+struct GemmCfg {
+  static constexpr int P = (NPASS == 3) ? 2 : 1;
+  static constexpr int A_BYTES = 128 * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = P * (A_BYTES + B_BYTES);
+  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+template <int BN, int NPASS>
+__global__ void __launch_bounds__(192, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmEpi ep, const int M, const int N, const int K) {
+  using Cfg = GemmCfg<BN, NPASS>;
+  constexpr int P = Cfg::P;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * 128;
+  const int n0 = blockIdx.x * BN;
+  const int nkb = (K + 63) / 64;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          tma_load_3d(&tmA, &full_bar[s], st + p * Cfg::A_BYTES, kb * 64, m0, p);
+          tma_load_3d(&tmB, &full_bar[s], st + P * Cfg::A_BYTES + p * Cfg::B_BYTES, kb * 64, n0, p);
+        }
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(1, 128, BN);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_hi = base_u32 + s * Cfg::STAGE_BYTES;
+        const uint32_t b_hi = a_hi + P * Cfg::A_BYTES;
+        const uint64_t da_hi = make_sw128_kmajor_desc(a_hi);
+        const uint64_t db_hi = make_sw128_kmajor_desc(b_hi);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t koff = static_cast<uint64_t>(2 * k);  // 32 bytes >> 4 per UMMA_K = 16
+          if (NPASS == 3) {
+            const uint64_t da_lo = make_sw128_kmajor_desc(a_hi + Cfg::A_BYTES);
+            const uint64_t db_lo = make_sw128_kmajor_desc(b_hi + Cfg::B_BYTES);
+            mma_bf16_ss(tmem_base, da_hi + koff, db_lo + koff, idesc, (kb | k) != 0);
+            mma_bf16_ss(tmem_base, da_lo + koff, db_hi + koff, idesc, 1);
+            mma_bf16_ss(tmem_base, da_hi + koff, db_hi + koff, idesc, 1);
+          } else {
+            mma_bf16_ss(tmem_base, da_hi + koff, db_hi + koff, idesc, (kb | k) != 0);
+          }
+        }
+        tc_commit(&empty_bar[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      tc_commit(accum_bar);
+    }
+  } else {
+    // ------------------------------- epilogue ---------------------------------------------
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int r = m0 + quad * 32 + lane;
+    const bool row_ok = r < M;
+    const long long out_row =
+        (long long)(r / ep.rows_per_group) * ep.group_stride + ep.group_offset + r % ep.rows_per_group;
+    const long long res_row = ep.res_row_mod > 0 ? (r % ep.res_row_mod) : r;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      if (n0 + c >= N) break;
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c, v);
+      tmem_ld_wait();
+      if (!row_ok) continue;
+      const int nbase = n0 + c;
+      float x[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+      const bool full = ep.vec_ok && (nbase + 32 <= N);
+      if (full) {
+        if (ep.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + nbase + j));
+            x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
+          }
+        }
+        if (ep.act) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = apply_act(x[j], ep.act);
+        }
+        if (ep.res) {
+          const float* rp = ep.res + res_row * ep.res_ld + nbase;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(rp + j);
+            x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
+          }
+        }
+        if (ep.res_split) {
+          const __nv_bfloat16* rh = ep.res_split + res_row * ep.res_ld + nbase;
+          const __nv_bfloat16* rl = rh + ep.res_plane;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const uint4 h = *reinterpret_cast<const uint4*>(rh + j);
+            const uint4 l = *reinterpret_cast<const uint4*>(rl + j);
+            const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+            const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              x[j + 2 * q] += __uint_as_float(hw[q] << 16) + __uint_as_float(lw[q] << 16);
+              x[j + 2 * q + 1] +=
+                  __uint_as_float(hw[q] & 0xffff0000u) + __uint_as_float(lw[q] & 0xffff0000u);
+            }
+          }
+        }
+        if (ep.post_relu) {  // ResNet bottleneck tail: relu(bn3(conv3) + identity)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+        }
+        if (ep.out_f32) {
+          float* op = ep.out_f32 + out_row * ep.out_ld + ep.out_col0 + nbase;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(op + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+        }
+        if (ep.out_split) {
+          __nv_bfloat16* oh = ep.out_split + out_row * ep.out_ld + ep.out_col0 + nbase;
+          __nv_bfloat16* ol = oh + ep.out_plane;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(x[j + 2 * q], h0, l0);
+              split_bf16(x[j + 2 * q + 1], h1, l1);
+              hw[q] = pack_bf16(h0, h1);
+              lw[q] = pack_bf16(l0, l1);
+            }
+            *reinterpret_cast<uint4*>(oh + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            if (ep.split_lo) *reinterpret_cast<uint4*>(ol + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int j = 0; j < 32; ++j) {
+          const int n = nbase + j;
+          if (n >= N) break;
+          float y = x[j];
+          if (ep.bias) y += __ldg(ep.bias + n);
+          if (ep.act) y = apply_act(y, ep.act);
+          if (ep.res) y += ep.res[res_row * ep.res_ld + n];
+          if (ep.res_split) {
+            y += __bfloat162float(ep.res_split[res_row * ep.res_ld + n]) +
+                 __bfloat162float(ep.res_split[ep.res_plane + res_row * ep.res_ld + n]);
+          }
+          if (ep.post_relu) y = fmaxf(y, 0.f);
+          if (ep.out_f32) ep.out_f32[out_row * ep.out_ld + ep.out_col0 + n] = y;
+          if (ep.out_split) {
+            __nv_bfloat16 h, l;
+            split_bf16(y, h, l);
+            ep.out_split[out_row * ep.out_ld + ep.out_col0 + n] = h;
+            if (ep.split_lo) ep.out_split[ep.out_plane + out_row * ep.out_ld + ep.out_col0 + n] = l;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor-map construction (driver entry point, cached) and launch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+struct TmapKey {
+  const void* ptr;
+  uint64_t d0, d1, d2, ld, plane_stride;
+  uint32_t b0, b1, esz;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && ld == o.ld && plane_stride == o.plane_stride &&
+           b0 == o.b0 && b1 == o.b1 && esz == o.esz;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    auto mix = [&h](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix(k.d0); mix(k.d1); mix(k.d2); mix(k.ld); mix(k.plane_stride); mix(k.b0); mix(k.b1); mix(k.esz);
+    return h;
+  }
+};
+
+// K-major operand [planes, rows, K] (K contiguous; row stride ld elements; plane stride given in
+// elements), box = 128 bytes along K x box_rows rows x 1 plane, SWIZZLE_128B, OOB -> zeros.
+int make_kmajor_tmap(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t K, uint64_t rows,
+                     uint64_t planes, uint64_t ld, uint64_t plane_stride, uint32_t box_rows) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey key{ptr, K, rows, planes, ld, plane_stride, (uint32_t)(128 / elem_bytes), box_rows,
+              (uint32_t)elem_bytes};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return 0; }
+  }
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return RALF_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * elem_bytes) & 15) || ((plane_stride * elem_bytes) & 15))
+    return RALF_ERR_ALIGN;
+  cuuint64_t gdim[3] = {K, rows, planes};
+  cuuint64_t gstr[2] = {ld * elem_bytes, (planes > 1 ? plane_stride : ld * rows) * elem_bytes};
+  cuuint32_t box[3] = {(cuuint32_t)(128 / elem_bytes), box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = fn(out, dt, 3, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "ralf_b200: cuTensorMapEncodeTiled failed (%d) K=%llu rows=%llu planes=%llu ld=%llu\n",
+            (int)r, (unsigned long long)K, (unsigned long long)rows, (unsigned long long)planes,
+            (unsigned long long)ld);
+    return RALF_ERR_DRIVER;
+  }
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, *out);
+  return 0;
+}
+
+template <int BN, int NPASS>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi& ep, int M, int N, int K,
+                       cudaStream_t st) {
+  using Cfg = GemmCfg<BN, NPASS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_cuda_error(e);
+    attr_set = true;
+  }
+  dim3 grid((N + BN - 1) / BN, (M + 127) / 128);
+  gemm_bf16_kernel<BN, NPASS><<<grid, 192, Cfg::SMEM_BYTES, st>>>(ta, tb, ep, M, N, K);
+  return set_cuda_error(cudaGetLastError());
+}
+
+}  // namespace ralf
+
+using namespace ralf;
+
+extern "C" int ralf_gemm(const RalfGemmArgs* a, void* stream) {
+  if (!a || a->M <= 0 || a->N <= 0 || a->K <= 0) return RALF_ERR_SHAPE;
+  if (a->npass != 1 && a->npass != 3) return RALF_ERR_SHAPE;
+  if (!a->A || !a->W) return RALF_ERR_NULL;
+  if ((a->lda % 8) || (a->ldw % 8)) return RALF_ERR_ALIGN;
+  const int planes = a->npass == 3 ? 2 : 1;
+  int bn = a->block_n;
+  if (bn == 0) {
+    const long long mt = (a->M + 127) / 128;
+    if (mt * ((a->N + 255) / 256) >= 120 && a->N >= 256 && a->npass == 1) bn = 256;
+    else if (mt * ((a->N + 127) / 128) >= 120 && a->N >= 128) bn = 128;
+    else bn = 64;
+  }
+  if (bn != 64 && bn != 128 && bn != 256) return RALF_ERR_SHAPE;
+  CUtensorMap ta, tb;
+  int rc = make_kmajor_tmap(&ta, a->A, 2, a->K, a->M, planes, a->lda, a->a_plane, 128);
+  if (rc) return rc;
+  rc = make_kmajor_tmap(&tb, a->W, 2, a->K, a->N, planes, a->ldw, a->w_plane, bn);
+  if (rc) return rc;
+  GemmEpi ep;
+  ep.bias = a->bias;
+  ep.res = a->res;
+  ep.res_split = reinterpret_cast<const __nv_bfloat16*>(a->res_split);
+  ep.res_plane = a->res_plane;
+  ep.res_ld = a->res_ld;
+  ep.res_row_mod = a->res_row_mod;
+  ep.out_f32 = a->out_f32;
+  ep.out_split = reinterpret_cast<__nv_bfloat16*>(a->out_split);
+  ep.out_plane = a->out_plane;
+  ep.out_ld = a->out_ld;
+  ep.out_col0 = a->out_col0;
+  ep.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : a->M;
+  ep.group_stride = a->rows_per_group > 0 ? a->group_stride : 0;
+  ep.group_offset = a->rows_per_group > 0 ? a->group_offset : 0;
+  ep.act = a->act;
+  ep.post_relu = a->post_relu;
+  ep.split_lo = a->out_split_lo;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  ep.vec_ok = (a->out_ld % 8 == 0) && (a->out_col0 % 8 == 0) && al16(a->out_f32) && al16(a->out_split) &&
+              (a->out_plane % 8 == 0) && al16(a->bias) && al16(a->res) && al16(a->res_split) &&
+              (a->res_ld % 8 == 0 || (!a->res && !a->res_split)) && (a->res_plane % 8 == 0);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int np = a->npass;
+#define RALF_GEMM_CASE(BN_, NP_) \
+  if (bn == BN_ && np == NP_) return launch_gemm<BN_, NP_>(ta, tb, ep, a->M, a->N, a->K, st);
+  RALF_GEMM_CASE(64, 3)
+  RALF_GEMM_CASE(128, 3)
+  RALF_GEMM_CASE(256, 3)
+  RALF_GEMM_CASE(64, 1)
+  RALF_GEMM_CASE(128, 1)
+  RALF_GEMM_CASE(256, 1)
+#undef RALF_GEMM_CASE
+  return RALF_ERR_SHAPE;
+}

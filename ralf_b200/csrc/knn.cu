@@ -1,0 +1,531 @@
+// K1: exact maximum-inner-product top-k over an fp32 embedding gallery.
+//
+// Replaces the FAISS IndexFlat(METRIC_INNER_PRODUCT) scan the reference runs one query at a time
+// on the CPU (image2layout/train/models/retrieval/retriever.py:79-84,193-213).
+//
+// Phase 1 (knn_scan_kernel): the gallery [n, d] fp32 is streamed ONCE from HBM by TMA
+// (SWIZZLE_128B boxes of 256 rows x 32 floats) and multiplied with a 128-query tile by
+// tcgen05.mma kind::tf32 (M = 128 queries, N = 256 gallery rows, fp32 accumulators, two TMEM
+// buffers of 256 columns so the epilogue of tile t overlaps the MMAs of tile t+1).  Epilogue
+// thread q owns query q: it reads its accumulator row from TMEM and keeps a running top-C
+// candidate list (C >= 2k) in shared memory -- one fp32 compare per score in the steady state,
+// append on success, warp-synchronous insertion-sort compaction when a list nears capacity.
+// TF32 scores only nominate candidates; they never decide the result.
+// Phase 2 (knn_rerank_kernel): per query, merge the per-CTA candidate lists, re-score the best
+// C candidates with the canonical fp32 dot product (bit-identical to oracle/knn_oracle.c),
+// order by (score desc, index asc), emit top-k, and certify exactness from the TF32 error bound.
+//
+// Algorithmic HBM bytes per call: n*d*4 (gallery once) + q*d*4 + q*k*12.
+#include <float.h>
+#include <stdio.h>
+
+#include "common.cuh"
+#include "ralf_internal.h"
+
+namespace ralf {
+
+// Order-preserving key: higher score first, then LOWER index first.
+__device__ __forceinline__ uint64_t knn_key(float s, uint32_t idx) {
+  uint32_t u = __float_as_uint(s);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return (static_cast<uint64_t>(u) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - idx);
+}
+__device__ __forceinline__ float knn_key_score(uint64_t key) {
+  uint32_t u = static_cast<uint32_t>(key >> 32);
+  u = (u & 0x80000000u) ? (u ^ 0x80000000u) : ~u;
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ uint32_t knn_key_index(uint64_t key) {
+  return 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull);
+}
+
+// Canonical fp32 inner product (see oracle/knn_oracle.c: knn_canonical_dot):
+//   lane l accumulates  acc_l = fmaf(a[i], b[i], acc_l)  for i = l, l+32, l+64, ... (ascending),
+//   then the 32 partials are combined by the xor butterfly 16, 8, 4, 2, 1 (p_l += p_{l^off}).
+// Every lane returns the same value.  Executed by one full warp.
+__device__ __forceinline__ float canonical_dot_warp(const float* __restrict__ a,
+                                                    const float* __restrict__ b, int d) {
+  float acc = 0.f;
+  for (int i = lane_id(); i < d; i += 32) acc = fmaf(a[i], b[i], acc);
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, off);
+  return acc;
+}
+
+template <int C>
+struct KnnCfg {
+  static constexpr int CAP = C + 16;
+  static constexpr int A_BYTES = 128 * 128;  // 128 queries x 32 fp32
+  static constexpr int B_BYTES = 256 * 128;  // 256 gallery rows x 32 fp32
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (C <= 32) ? 3 : 2;
+  static constexpr int CAND_BYTES = CAP * 128 * 8;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + CAND_BYTES + 1024 + 256;
+};
+
+// Insert the unsorted tail [m, cnt) of this thread's candidate column into its sorted (descending)
+// prefix [0, m), keeping at most C entries.  Columns are interleaved: entry e of thread t lives at
+// col[e * 128] (col already offset by t) -> conflict-free shared-memory access across a warp.
+template <int C>
+__device__ __forceinline__ void knn_compact(uint64_t* col, int& m, int& cnt, float& thr) {
+  for (int e = m; e < cnt; ++e) {
+    const uint64_t key = col[e * 128];
+    int j = m;
+    while (j > 0 && col[(j - 1) * 128] < key) {
+      if (j < C) col[j * 128] = col[(j - 1) * 128];
+      --j;
+    }
+    if (j < C) col[j * 128] = key;
+    if (m < C) ++m;
+  }
+  cnt = m;
+  thr = (m == C) ? knn_key_score(col[(C - 1) * 128]) : -INFINITY;
+}
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+template <int C>
+__global__ void __launch_bounds__(192, 1)
+knn_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmG,
+                const int n, const int d, const int nq, uint64_t* __restrict__ cand) {
+  using Cfg = KnnCfg<C>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
+  uint64_t* cand_s = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::CAND_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;  // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;      // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qtile = blockIdx.y;
+  const int total_tiles = (n + 255) / 256;
+  const int t_begin = static_cast<int>((static_cast<long long>(blockIdx.x) * total_tiles) / gridDim.x);
+  const int t_end = static_cast<int>((static_cast<long long>(blockIdx.x + 1) * total_tiles) / gridDim.x);
+  const int nkb = (d + 31) / 32;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmG);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+          tma_load_3d(&tmQ, &full_bar[s], st, kb * 32, qtile * 128, 0);
+          tma_load_3d(&tmG, &full_bar[s], st + Cfg::A_BYTES, kb * 32, t * 256, 0);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(2, 128, 256);  // tf32 x tf32 -> fp32
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int t = t_begin; t < t_end; ++t, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * 256;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = base_u32 + s * Cfg::STAGE_BYTES;
+          const uint64_t da = make_sw128_kmajor_desc(a_addr);
+          const uint64_t db = make_sw128_kmajor_desc(a_addr + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // UMMA_K = 8 tf32 = 32 bytes -> descriptor += 2
+            mma_tf32_ss(tacc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          tc_commit(&empty_bar[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        tc_commit(&tfull_bar[buf]);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int ql = quad * 32 + lane;  // query lane within the tile == TMEM lane
+    const bool active = (qtile * 128 + ql) < nq;
+    uint64_t* col = cand_s + ql;
+    int m = 0, cnt = 0;
+    float thr = -INFINITY;
+    int it = 0;
+    for (int t = t_begin; t < t_end; ++t, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const int g0 = t * 256;
+      const int ncols = min(256, n - g0);
+      const uint32_t tacc = tmem_base + buf * 256 + (static_cast<uint32_t>(quad * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < ncols; c0 += 16) {
+        if (__any_sync(0xffffffffu, cnt > Cfg::CAP - 16)) knn_compact<C>(col, m, cnt, thr);
+        uint32_t v[16];
+        tmem_ld_32x16(tacc + c0, v);
+        tmem_ld_wait();
+        if (active) {
+          const int lim = ncols - c0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float s = __uint_as_float(v[j]);
+            if (s > thr && j < lim) {
+              col[cnt * 128] = knn_key(s, static_cast<uint32_t>(g0 + c0 + j));
+              ++cnt;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[buf]);
+    }
+    knn_compact<C>(col, m, cnt, thr);
+    // candidate lists: [qtile][cta][query lane][C]
+    uint64_t* out = cand + ((static_cast<size_t>(qtile) * gridDim.x + blockIdx.x) * 128 + ql) * C;
+#pragma unroll 4
+    for (int e = 0; e < C; ++e) out[e] = (e < m) ? col[e * 128] : 0ull;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// Phase 2.  One CTA (256 threads) per query.  `parts` candidate lists of C keys each.
+template <int C>
+__global__ void __launch_bounds__(256)
+knn_rerank_kernel(const uint64_t* __restrict__ cand, const int parts, const float* __restrict__ gallery,
+                  const float* __restrict__ queries, const int n, const int d, const int k,
+                  const long long index_base, const float gmax_norm, long long* __restrict__ out_idx,
+                  float* __restrict__ out_score, int* __restrict__ certified) {
+  extern __shared__ uint64_t keys[];  // parts * C
+  __shared__ uint64_t sel[C];
+  __shared__ float exact[C];
+  __shared__ uint64_t red_key[8];
+  __shared__ int red_pos[8];
+  __shared__ float qnorm2_s[8];
+  const int q = blockIdx.x;
+  const int qtile = q >> 7, ql = q & 127;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int total = parts * C;
+  for (int i = tid; i < total; i += 256) {
+    const int p = i / C, e = i - p * C;
+    keys[i] = cand[((static_cast<size_t>(qtile) * parts + p) * 128 + ql) * C + e];
+  }
+  __syncthreads();
+  // top-C by approximate key: C rounds of block arg-max (keys are unique per gallery row).
+  for (int r = 0; r < C; ++r) {
+    uint64_t best = 0;
+    int pos = -1;
+    for (int i = tid; i < total; i += 256) {
+      const uint64_t kv = keys[i];
+      if (kv > best) { best = kv; pos = i; }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const uint64_t ob = __shfl_xor_sync(0xffffffffu, best, off);
+      const int op = __shfl_xor_sync(0xffffffffu, pos, off);
+      if (ob > best) { best = ob; pos = op; }
+    }
+    if (lane == 0) { red_key[warp] = best; red_pos[warp] = pos; }
+    __syncthreads();
+    if (tid == 0) {
+      uint64_t b = 0;
+      int p = -1;
+      for (int w = 0; w < 8; ++w)
+        if (red_key[w] > b) { b = red_key[w]; p = red_pos[w]; }
+      sel[r] = b;
+      if (p >= 0) keys[p] = 0;
+    }
+    __syncthreads();
+  }
+  // exact canonical re-score of the selected candidates (warp per candidate)
+  const float* qv = queries + static_cast<size_t>(q) * d;
+  for (int c = warp; c < C; c += 8) {
+    const uint64_t kv = sel[c];
+    float s = -INFINITY;
+    if (kv != 0) s = canonical_dot_warp(qv, gallery + static_cast<size_t>(knn_key_index(kv)) * d, d);
+    if (lane == 0) exact[c] = s;
+  }
+  {
+    float a = 0.f;
+    for (int i = tid; i < d; i += 256) a = fmaf(qv[i], qv[i], a);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+    if (lane == 0) qnorm2_s[warp] = a;
+  }
+  __syncthreads();
+  // final order: exact score descending, index ascending
+  if (tid < C) {
+    const uint64_t kv = sel[tid];
+    const uint64_t mine = (kv != 0) ? knn_key(exact[tid], knn_key_index(kv)) : 0ull;
+    int rank = 0;
+    for (int j = 0; j < C; ++j) {
+      const uint64_t kj = sel[j];
+      const uint64_t other = (kj != 0) ? knn_key(exact[j], knn_key_index(kj)) : 0ull;
+      rank += (other > mine) || (other == mine && j < tid);
+    }
+    if (rank < k) {
+      out_idx[static_cast<size_t>(q) * k + rank] =
+          (kv != 0) ? static_cast<long long>(knn_key_index(kv)) + index_base : -1ll;
+      out_score[static_cast<size_t>(q) * k + rank] = (kv != 0) ? exact[tid] : -INFINITY;
+    }
+    // stash the final key so thread 0 can find the k-th exact score
+    keys[tid] = mine;
+    keys[C + tid] = static_cast<uint64_t>(rank);
+  }
+  __syncthreads();
+  if (tid == 0 && certified) {
+    int ok = 1;
+    if (sel[C - 1] != 0 && gmax_norm > 0.f) {  // otherwise every gallery row was a candidate
+      float qn2 = 0.f;
+      for (int w = 0; w < 8; ++w) qn2 += qnorm2_s[w];
+      const float err = (1.953125e-3f + static_cast<float>(d) * 1.2e-7f) * sqrtf(qn2) * gmax_norm;
+      const float a_c = knn_key_score(sel[C - 1]);  // approx score of the weakest candidate
+      float s_k = -INFINITY;
+      for (int j = 0; j < C; ++j)
+        if (static_cast<int>(keys[C + j]) == k - 1) s_k = knn_key_score(keys[j]);
+      ok = (s_k > a_c + err) ? 1 : 0;
+    } else if (sel[C - 1] != 0) {
+      ok = 0;  // no norm bound supplied: cannot certify
+    }
+    certified[q] = ok;
+  }
+}
+
+// Exact CUDA-core scan (fallback + independent check).  grid = (slices, q); block = 256 (8 warps);
+// each warp scores rows with the canonical dot and keeps a sorted top-C list (lane 0 inserts).
+template <int C>
+__global__ void __launch_bounds__(256)
+knn_exact_scan_kernel(const float* __restrict__ gallery, const float* __restrict__ queries, const int n,
+                      const int d, uint64_t* __restrict__ cand) {
+  __shared__ uint64_t lists[8][C];
+  const int q = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* qv = queries + static_cast<size_t>(q) * d;
+  const long long r0 = (static_cast<long long>(blockIdx.x) * n) / gridDim.x;
+  const long long r1 = (static_cast<long long>(blockIdx.x + 1) * n) / gridDim.x;
+  uint64_t* lst = lists[warp];
+  for (int e = lane; e < C; e += 32) lst[e] = 0;
+  __syncwarp();
+  int m = 0;
+  float thr = -INFINITY;
+  for (long long r = r0 + warp; r < r1; r += 8) {
+    const float s = canonical_dot_warp(qv, gallery + static_cast<size_t>(r) * d, d);
+    if (s > thr || m < C) {
+      if (lane == 0) {
+        const uint64_t key = knn_key(s, static_cast<uint32_t>(r));
+        int j = m;
+        while (j > 0 && lst[j - 1] < key) {
+          if (j < C) lst[j] = lst[j - 1];
+          --j;
+        }
+        if (j < C) lst[j] = key;
+      }
+      if (m < C) ++m;
+      __syncwarp();
+      thr = (m == C) ? knn_key_score(lst[C - 1]) : -INFINITY;
+    }
+  }
+  __syncwarp();
+  // layout expected by knn_rerank_kernel with parts = slices * 8: [qtile][part][lane][C]
+  const int qtile = q >> 7, ql = q & 127;
+  const int parts = gridDim.x * 8;
+  const int part = blockIdx.x * 8 + warp;
+  uint64_t* out = cand + ((static_cast<size_t>(qtile) * parts + part) * 128 + ql) * C;
+  for (int e = lane; e < C; e += 32) out[e] = lst[e];
+}
+
+__global__ void knn_merge_kernel(const float* __restrict__ ps, const long long* __restrict__ pi, const int parts,
+                                 const int nq, const int k, long long* __restrict__ out_idx,
+                                 float* __restrict__ out_score) {
+  const int q = blockIdx.x;
+  const int total = parts * k;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int p = i / k, e = i - p * k;
+    const size_t src = (static_cast<size_t>(p) * nq + q) * k + e;
+    const float s = ps[src];
+    const long long id = pi[src];
+    if (id < 0) continue;
+    int rank = 0;
+    for (int j = 0; j < total; ++j) {
+      const int pj = j / k, ej = j - pj * k;
+      const size_t sj = (static_cast<size_t>(pj) * nq + q) * k + ej;
+      const float s2 = ps[sj];
+      const long long id2 = pi[sj];
+      if (id2 < 0) continue;
+      rank += (s2 > s) || (s2 == s && id2 < id);
+    }
+    if (rank < k) {
+      out_idx[static_cast<size_t>(q) * k + rank] = id;
+      out_score[static_cast<size_t>(q) * k + rank] = s;
+    }
+  }
+}
+__global__ void knn_fill_kernel(long long* idx, float* score, size_t count) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < count) { idx[i] = -1; score[i] = -INFINITY; }
+}
+
+static int knn_c_for_k(int k) { return k <= 24 ? 32 : (k <= 48 ? 64 : 0); }
+static int knn_grid_x(int n) {
+  const int tiles = (n + 255) / 256;
+  const int sms = num_sms();
+  return tiles < sms ? tiles : sms;
+}
+static int knn_exact_slices(int C) { return C <= 32 ? 64 : 32; }
+
+}  // namespace ralf
+
+using namespace ralf;
+
+extern "C" size_t ralf_knn_workspace_bytes(int n, int d, int q, int k) {
+  (void)d;
+  const int C = knn_c_for_k(k);
+  if (C == 0 || n <= 0 || q <= 0) return 0;
+  const size_t qtiles = (q + 127) / 128;
+  size_t parts = knn_grid_x(n);
+  if (parts < static_cast<size_t>(knn_exact_slices(C)) * 8) parts = static_cast<size_t>(knn_exact_slices(C)) * 8;
+  return qtiles * parts * 128 * C * sizeof(uint64_t);
+}
+
+// knn_rerank_kernel serves both the tensor-core path (<= 148 lists) and the exact path (<= 512 lists).
+template <int C>
+static int knn_rerank_attr() {
+  static bool attr_set = false;
+  if (!attr_set) {
+    size_t need = static_cast<size_t>(knn_exact_slices(C)) * 8 * C * 8;
+    if (need < static_cast<size_t>(160) * C * 8) need = static_cast<size_t>(160) * C * 8;
+    cudaError_t e = cudaFuncSetAttribute(knn_rerank_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(need));
+    if (e != cudaSuccess) return set_cuda_error(e);
+    attr_set = true;
+  }
+  return 0;
+}
+
+template <int C>
+static int knn_topk_impl(const float* gallery, int n, int d, const float* queries, int q, int k,
+                         long long index_base, float gmax, long long* out_idx, float* out_score, int* certified,
+                         uint64_t* cand, cudaStream_t st) {
+  using Cfg = KnnCfg<C>;
+  CUtensorMap tq, tg;
+  int rc = make_kmajor_tmap(&tq, queries, 4, d, q, 1, d, 0, 128);
+  if (rc) return rc;
+  rc = make_kmajor_tmap(&tg, gallery, 4, d, n, 1, d, 0, 256);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(knn_scan_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_cuda_error(e);
+    attr_set = true;
+  }
+  rc = knn_rerank_attr<C>();
+  if (rc) return rc;
+  const int gx = knn_grid_x(n);
+  dim3 grid(gx, (q + 127) / 128);
+  knn_scan_kernel<C><<<grid, 192, Cfg::SMEM_BYTES, st>>>(tq, tg, n, d, q, cand);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e);
+  const size_t rr_smem = static_cast<size_t>(gx) * C * 8 < 2 * C * 8 ? 2 * C * 8 : static_cast<size_t>(gx) * C * 8;
+  knn_rerank_kernel<C><<<q, 256, rr_smem, st>>>(cand, gx, gallery, queries, n, d, k, index_base, gmax, out_idx,
+                                                 out_score, certified);
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_knn_topk(const float* gallery, int n, int d, const float* queries, int q, int k,
+                             long long index_base, float gallery_max_norm, long long* out_idx,
+                             float* out_score, int* certified, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  if (!gallery || !queries || !out_idx || !out_score) return RALF_ERR_NULL;
+  if (n <= 0 || q <= 0 || d <= 0 || k <= 0) return RALF_ERR_SHAPE;
+  const int C = knn_c_for_k(k);
+  if (C == 0) return RALF_ERR_SHAPE;
+  if (d % 4) return RALF_ERR_ALIGN;  // TMA needs 16-byte row pitch
+  if (!workspace || workspace_bytes < ralf_knn_workspace_bytes(n, d, q, k)) return RALF_ERR_WORKSPACE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint64_t* cand = reinterpret_cast<uint64_t*>(workspace);
+  if (C == 32)
+    return knn_topk_impl<32>(gallery, n, d, queries, q, k, index_base, gallery_max_norm, out_idx, out_score,
+                             certified, cand, st);
+  return knn_topk_impl<64>(gallery, n, d, queries, q, k, index_base, gallery_max_norm, out_idx, out_score,
+                           certified, cand, st);
+}
+
+template <int C>
+static int knn_exact_impl(const float* gallery, int n, int d, const float* queries, int q, int k,
+                          long long index_base, long long* out_idx, float* out_score, uint64_t* cand,
+                          cudaStream_t st) {
+  const int parts = knn_exact_slices(C) * 8;
+  int rc = knn_rerank_attr<C>();
+  if (rc) return rc;
+  dim3 grid(knn_exact_slices(C), q);
+  knn_exact_scan_kernel<C><<<grid, 256, 0, st>>>(gallery, queries, n, d, cand);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e);
+  knn_rerank_kernel<C><<<q, 256, static_cast<size_t>(parts) * C * 8, st>>>(
+      cand, parts, gallery, queries, n, d, k, index_base, 0.f, out_idx, out_score, nullptr);
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_knn_topk_exact(const float* gallery, int n, int d, const float* queries, int q, int k,
+                                   long long index_base, long long* out_idx, float* out_score, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  if (!gallery || !queries || !out_idx || !out_score) return RALF_ERR_NULL;
+  if (n <= 0 || q <= 0 || d <= 0 || k <= 0) return RALF_ERR_SHAPE;
+  const int C = knn_c_for_k(k);
+  if (C == 0) return RALF_ERR_SHAPE;
+  if (!workspace || workspace_bytes < ralf_knn_workspace_bytes(n, d, q, k)) return RALF_ERR_WORKSPACE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint64_t* cand = reinterpret_cast<uint64_t*>(workspace);
+  if (C == 32) return knn_exact_impl<32>(gallery, n, d, queries, q, k, index_base, out_idx, out_score, cand, st);
+  return knn_exact_impl<64>(gallery, n, d, queries, q, k, index_base, out_idx, out_score, cand, st);
+}
+
+extern "C" int ralf_knn_merge(const float* part_score, const long long* part_idx, int parts, int q, int k,
+                              long long* out_idx, float* out_score, void* stream) {
+  if (!part_score || !part_idx || !out_idx || !out_score) return RALF_ERR_NULL;
+  if (parts <= 0 || q <= 0 || k <= 0) return RALF_ERR_SHAPE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t count = static_cast<size_t>(q) * k;
+  knn_fill_kernel<<<static_cast<unsigned>((count + 255) / 256), 256, 0, st>>>(out_idx, out_score, count);
+  knn_merge_kernel<<<q, 128, 0, st>>>(part_score, part_idx, parts, q, k, out_idx, out_score);
+  return set_cuda_error(cudaGetLastError());
+}

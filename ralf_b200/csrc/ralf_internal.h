@@ -1,0 +1,16 @@
+// Internal helpers shared by the .cu files (error plumbing, tensor-map builder).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/ralf_b200.h"
+
+namespace ralf {
+// Records the CUDA error string for ralf_last_cuda_error(); returns 0 or RALF_ERR_CUDA.
+int set_cuda_error(cudaError_t e);
+// K-major operand [planes, rows, K] -> 3-D tensor map with a (128 bytes x box_rows x 1) box,
+// SWIZZLE_128B, zero fill out of bounds.  Cached by (ptr, shape).
+int make_kmajor_tmap(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t K, uint64_t rows,
+                     uint64_t planes, uint64_t ld, uint64_t plane_stride, uint32_t box_rows);
+int num_sms();
+}  // namespace ralf

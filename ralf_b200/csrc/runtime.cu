@@ -1,0 +1,37 @@
+// Error plumbing and device queries shared by all entry points.
+#include <string.h>
+
+#include "ralf_internal.h"
+
+namespace ralf {
+static thread_local char g_last_error[256] = "";
+
+int set_cuda_error(cudaError_t e) {
+  if (e == cudaSuccess) return RALF_OK;
+  strncpy(g_last_error, cudaGetErrorString(e), sizeof(g_last_error) - 1);
+  g_last_error[sizeof(g_last_error) - 1] = 0;
+  return RALF_ERR_CUDA;
+}
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+}  // namespace ralf
+
+extern "C" const char* ralf_last_cuda_error(void) { return ralf::g_last_error; }
+
+extern "C" int ralf_check_device(int dev) {
+  int major = 0;
+  cudaError_t e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return ralf::set_cuda_error(e);
+  return major == 10 ? RALF_OK : RALF_ERR_ARCH;
+}
+
+extern "C" int ralf_version(void) { return 100; }

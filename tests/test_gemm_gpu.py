@@ -1,0 +1,94 @@
+"""GPU parity of the tcgen05 GEMM (ralf_gemm) against a float64 contraction of the same operands."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a, w, bias=None, act=None, res=None, post_relu=False):
+    y = a.double() @ w.double().t()
+    if bias is not None:
+        y = y + bias.double()
+    if act == "relu":
+        y = y.relu()
+    elif act == "gelu":
+        y = torch.nn.functional.gelu(y)
+    if res is not None:
+        y = y + res.double()
+    if post_relu:
+        y = y.relu()
+    return y
+
+
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 64, 64, 64), (128, 128, 256, 128), (300, 768, 256, 0), (1000, 1024, 256, 0), (77, 519, 256, 0),
+    (256, 256, 1024, 64), (4096, 256, 2304, 0), (130, 256, 200, 64), (4, 256, 256, 0), (513, 3072, 256, 256),
+])
+def test_gemm_bf16x3_matches_fp64(cuda_device, M, N, K, bn):
+    from ralf_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, generator=g).to(cuda_device)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda_device)
+    bias = torch.randn(N, generator=g).to(cuda_device)
+    out, _ = ops.gemm(ops.split_bf16(a), ops.split_bf16(w), bias=bias, block_n=bn)
+    torch.cuda.synchronize()
+    ref = _ref(a, w, bias)
+    err = (out.double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2e-5 * scale, (err, scale)
+
+
+def test_gemm_plain_bf16(cuda_device):
+    from ralf_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(1)
+    a = torch.randn(512, 512, generator=g).to(cuda_device)
+    w = (torch.randn(384, 512, generator=g) / 512 ** 0.5).to(cuda_device)
+    a_s, w_s = ops.split_bf16(a), ops.split_bf16(w)
+    out, _ = ops.gemm(a_s, w_s, npass=1)
+    ref = a_s[0].double() @ w_s[0].double().t()  # bf16-rounded operands, exact products
+    err = (out.double() - ref).abs().max().item()
+    assert err <= 1e-5 * ref.abs().max().item(), err
+
+
+@pytest.mark.parametrize("act", [None, "relu", "gelu"])
+def test_gemm_epilogue(cuda_device, act):
+    from ralf_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(5)
+    M, N, K = 333, 256, 256
+    a = torch.randn(M, K, generator=g).to(cuda_device)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda_device)
+    bias = torch.randn(N, generator=g).to(cuda_device)
+    res = torch.randn(M, N, generator=g).to(cuda_device)
+    out, outs = ops.gemm(ops.split_bf16(a), ops.split_bf16(w), bias=bias, act=act, res=res, want_split=True)
+    ref = _ref(a, w, bias, act, res)
+    scale = ref.abs().max().item()
+    assert (out.double() - ref).abs().max().item() <= 2e-5 * scale
+    assert (ops.unsplit(outs).double() - ref).abs().max().item() <= 4e-5 * scale
+    # split residual + relu after the residual (ResNet bottleneck tail), row-broadcast residual
+    res_s = ops.split_bf16(res)
+    out2, _ = ops.gemm(ops.split_bf16(a), ops.split_bf16(w), bias=bias, res_split=res_s, post_relu=True)
+    ref2 = _ref(a, w, bias, None, ops.unsplit(res_s), post_relu=True)
+    assert (out2.double() - ref2).abs().max().item() <= 2e-5 * scale
+    tab = torch.randn(37, N, generator=g).to(cuda_device)
+    out3, _ = ops.gemm(ops.split_bf16(a), ops.split_bf16(w), res=tab, res_row_mod=37)
+    ref3 = _ref(a, w) + tab.double()[torch.arange(M) % 37]
+    assert (out3.double() - ref3).abs().max().item() <= 2e-5 * scale
+
+
+def test_gemm_row_remap_and_col_offset(cuda_device):
+    from ralf_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(9)
+    B, T, N, K = 6, 10, 256, 512
+    a = torch.randn(B * T, K, generator=g).to(cuda_device)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda_device)
+    out = torch.zeros(B * (T + 1), 2 * N, device=cuda_device)
+    ops.gemm(ops.split_bf16(a), ops.split_bf16(w), out_f32=out, out_col0=N, rows_per_group=T,
+             group_stride=T + 1, group_offset=1)
+    ref = _ref(a, w).float().view(B, T, N)
+    got = out.view(B, T + 1, 2 * N)
+    assert (got[:, 1:, N:] - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    assert got[:, 0].abs().max().item() == 0 and got[:, :, :N].abs().max().item() == 0

@@ -1,0 +1,97 @@
+"""GPU parity of the k-NN kernels against the C oracle: bit-exact indices and scores."""
+import numpy as np
+import pytest
+import torch
+
+from tests import oracle_knn
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(n, d, q, seed, normalize=True):
+    rng = np.random.default_rng(seed)
+    G = rng.standard_normal((n, d)).astype(np.float32)
+    Q = rng.standard_normal((q, d)).astype(np.float32)
+    if normalize:
+        G /= np.linalg.norm(G, axis=1, keepdims=True)
+        Q /= np.linalg.norm(Q, axis=1, keepdims=True)
+    return G, Q
+
+
+@pytest.mark.parametrize("n,d,q,k", [
+    (10000, 512, 1, 16), (10000, 512, 32, 16), (7734, 512, 5, 33), (48544, 512, 128, 16), (3000, 256, 200, 16),
+    (1000, 100, 3, 8), (257, 512, 2, 16), (20, 512, 2, 16), (5, 64, 1, 16),
+])
+def test_knn_topk_matches_oracle(cuda_device, n, d, q, k):
+    from ralf_b200 import ops
+
+    G, Q = _data(n, d, q, seed=n + q)
+    oi, os_ = oracle_knn.topk(G, Q, k, index_base=1000)
+    gi, gs, cert = ops.knn_topk(torch.from_numpy(G).to(cuda_device), torch.from_numpy(Q).to(cuda_device), k,
+                                index_base=1000, gallery_max_norm=1.0001)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(gi.cpu().numpy(), oi)
+    np.testing.assert_array_equal(gs.cpu().numpy().view(np.uint32), os_.view(np.uint32))
+    assert cert.cpu().numpy().all()
+
+
+def test_knn_exact_kernel_matches_oracle(cuda_device):
+    from ralf_b200 import ops
+
+    G, Q = _data(20000, 512, 3, seed=3, normalize=False)
+    oi, os_ = oracle_knn.topk(G, Q, 16)
+    gi, gs, _ = ops.knn_topk(torch.from_numpy(G).to(cuda_device), torch.from_numpy(Q).to(cuda_device), 16, exact=True)
+    np.testing.assert_array_equal(gi.cpu().numpy(), oi)
+    np.testing.assert_array_equal(gs.cpu().numpy().view(np.uint32), os_.view(np.uint32))
+
+
+def test_knn_ties_and_duplicates(cuda_device):
+    """Exact duplicates in the gallery: ties must resolve to the lower index (oracle rule)."""
+    from ralf_b200 import ops
+
+    G, Q = _data(4096, 512, 4, seed=11)
+    G[100:140] = G[7]          # 41 identical rows
+    Q[0] = G[7]                # query hits the duplicate cluster
+    oi, os_ = oracle_knn.topk(G, Q, 16)
+    gi, gs, cert = ops.knn_topk(torch.from_numpy(G).to(cuda_device), torch.from_numpy(Q).to(cuda_device), 16,
+                                gallery_max_norm=1.0001)
+    np.testing.assert_array_equal(gi.cpu().numpy(), oi)
+    # 41 equal scores straddle the candidate cut, so the TF32 bound cannot certify query 0 ...
+    assert cert.cpu().numpy()[0] == 0 and cert.cpu().numpy()[1:].all()
+    # ... and the exact kernel is the certified fallback
+    ei, es, _ = ops.knn_topk(torch.from_numpy(G).to(cuda_device), torch.from_numpy(Q).to(cuda_device), 16, exact=True)
+    np.testing.assert_array_equal(ei.cpu().numpy(), oi)
+
+
+def test_knn_sharded_merge_equals_unsharded(cuda_device):
+    from ralf_b200 import ops
+
+    G, Q = _data(30000, 512, 16, seed=5)
+    oi, os_ = oracle_knn.topk(G, Q, 16)
+    Gd, Qd = torch.from_numpy(G).to(cuda_device), torch.from_numpy(Q).to(cuda_device)
+    parts_s, parts_i = [], []
+    bounds = [0, 7000, 15000, 22001, 30000]
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        i, s, _ = ops.knn_topk(Gd[a:b], Qd, 16, index_base=a)
+        parts_s.append(s)
+        parts_i.append(i)
+    mi, ms = ops.knn_merge(torch.stack(parts_s), torch.stack(parts_i))
+    np.testing.assert_array_equal(mi.cpu().numpy(), oi)
+    np.testing.assert_array_equal(ms.cpu().numpy().view(np.uint32), os_.view(np.uint32))
+
+
+def test_knn_large_roundtrip_property(cuda_device):
+    """Full-size property (1M x 512): every gallery row queried against the gallery finds itself first."""
+    from ralf_b200 import ops
+
+    n, d = 1_000_000, 512
+    g = torch.Generator(device=cuda_device).manual_seed(0)
+    G = torch.randn(n, d, device=cuda_device, generator=g)
+    G = G / G.norm(dim=1, keepdim=True)
+    rows = torch.arange(0, n, n // 128, device=cuda_device)[:128]
+    idx, score, cert = ops.knn_topk(G, G[rows].contiguous(), 16, gallery_max_norm=1.0001)
+    assert torch.equal(idx[:, 0], rows)
+    assert (score[:, :-1] >= score[:, 1:]).all()
+    assert cert.all()
+    ei, es, _ = ops.knn_topk(G, G[rows[:2]].contiguous(), 16, exact=True)
+    assert torch.equal(ei, idx[:2]) and torch.equal(es, score[:2])
