@@ -1,0 +1,653 @@
+// Non-GEMM kernels of the RALF forward / generate path: LayerNorm, multi-head attention (full and
+// KV-cached single-query), im2col for the ResNet convolutions, max-pool, FPN merge, embeddings,
+// row glue, masked arg-max.  All fp32 arithmetic on CUDA cores (these ops are HBM/latency bound;
+// the dense contractions around them run on tcgen05 in gemm.cu).  Activations that feed a GEMM are
+// emitted in the split-bf16 format (hi plane, lo plane) by the producing kernel.
+#include <float.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "ralf_internal.h"
+
+namespace ralf {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
+  return v;
+}
+__device__ __forceinline__ void store_split(__nv_bfloat16* hi_plane, long long plane, long long off, float x) {
+  __nv_bfloat16 h, l;
+  split_bf16(x, h, l);
+  hi_plane[off] = h;
+  hi_plane[plane + off] = l;
+}
+__device__ __forceinline__ float load_split(const __nv_bfloat16* hi_plane, long long plane, long long off) {
+  return __bfloat162float(hi_plane[off]) + __bfloat162float(hi_plane[plane + off]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over the last dim (nn.LayerNorm, eps 1e-5; common/attention.py:20, nn.Transformer*Layer
+// norms).  One warp per row; D <= 1024, D % 32 == 0.
+// ------------------------------------------------------------------------------------------------
+__global__ void layernorm_kernel(const float* __restrict__ x, long long in_ld, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps, int M, int D,
+                                 float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_split,
+                                 long long out_plane) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + static_cast<long long>(row) * in_ld;
+  float v[32];
+  const int per = D >> 5;
+  float s = 0.f;
+#pragma unroll 8
+  for (int i = 0; i < per; ++i) {
+    v[i] = xr[lane + 32 * i];
+    s += v[i];
+  }
+  const float mean = warp_sum(s) / static_cast<float>(D);
+  float sq = 0.f;
+#pragma unroll 8
+  for (int i = 0; i < per; ++i) {
+    const float dlt = v[i] - mean;
+    sq += dlt * dlt;
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(D) + eps);
+#pragma unroll 8
+  for (int i = 0; i < per; ++i) {
+    const int c = lane + 32 * i;
+    const float y = (v[i] - mean) * rstd * gamma[c] + beta[c];
+    const long long off = static_cast<long long>(row) * D + c;
+    if (out_f32) out_f32[off] = y;
+    if (out_split) store_split(out_split, out_plane, off, y);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Multi-head attention, fp32, online softmax.  One thread per query, K/V tiles of 64 keys staged in
+// shared memory (broadcast reads).  Covers nn.MultiheadAttention inside nn.TransformerEncoderLayer /
+// DecoderLayer (common/common.py:26-35, retrieval_augmented_autoreg.py:116-126, fid/model.py:26-33)
+// and the fusion Attention (common/attention.py:49-71).
+//   q row (b, t): q + (b*Tq + t)*ldq + h*DH ; k/v row (b, j): k + (b*Tk + j)*ldk + h*DH
+//   mask: uint8 [B, Tk], nonzero = key is padding (-inf);  causal: key j > query t masked.
+// ------------------------------------------------------------------------------------------------
+template <int DH>
+__global__ void __launch_bounds__(128)
+attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, const float* __restrict__ v,
+                 int ldk, const unsigned char* __restrict__ mask, int Tq, int Tk, int causal, float scale,
+                 __nv_bfloat16* __restrict__ out_split, long long out_plane, float* __restrict__ out_f32, int ldo) {
+  constexpr int KT = 64;
+  __shared__ __align__(16) float ks[KT][DH];
+  __shared__ __align__(16) float vs[KT][DH];
+  __shared__ unsigned char ms[KT];
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = t < Tq;
+  float qr[DH], o[DH];
+  if (active) {
+    const float* qp = q + (static_cast<long long>(b) * Tq + t) * ldq + h * DH;
+#pragma unroll
+    for (int i = 0; i < DH; i += 4) {
+      const float4 f = *reinterpret_cast<const float4*>(qp + i);
+      qr[i] = f.x * scale; qr[i + 1] = f.y * scale; qr[i + 2] = f.z * scale; qr[i + 3] = f.w * scale;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < DH; ++i) o[i] = 0.f;
+  float mrun = -INFINITY, lrun = 0.f;
+  const int kmax = causal ? min(Tk, (blockIdx.x + 1) * static_cast<int>(blockDim.x)) : Tk;
+  for (int j0 = 0; j0 < kmax; j0 += KT) {
+    __syncthreads();
+    const int nk = min(KT, Tk - j0);
+    for (int i = threadIdx.x; i < KT * (DH / 4); i += blockDim.x) {
+      const int r = i / (DH / 4), c = (i % (DH / 4)) * 4;
+      float4 fk = make_float4(0.f, 0.f, 0.f, 0.f), fv = fk;
+      if (r < nk) {
+        const long long off = (static_cast<long long>(b) * Tk + j0 + r) * ldk + h * DH + c;
+        fk = *reinterpret_cast<const float4*>(k + off);
+        fv = *reinterpret_cast<const float4*>(v + off);
+      }
+      *reinterpret_cast<float4*>(&ks[r][c]) = fk;
+      *reinterpret_cast<float4*>(&vs[r][c]) = fv;
+    }
+    for (int i = threadIdx.x; i < KT; i += blockDim.x)
+      ms[i] = (i < nk) ? (mask ? mask[static_cast<long long>(b) * Tk + j0 + i] : 0) : 1;
+    __syncthreads();
+    if (!active) continue;
+    for (int c0 = 0; c0 < nk; c0 += 8) {
+      float s[8];
+      float cmax = -INFINITY;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int j = c0 + jj;
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < DH; i += 4) {
+          const float4 f = *reinterpret_cast<const float4*>(&ks[j & (KT - 1)][i]);
+          acc = fmaf(qr[i], f.x, acc); acc = fmaf(qr[i + 1], f.y, acc);
+          acc = fmaf(qr[i + 2], f.z, acc); acc = fmaf(qr[i + 3], f.w, acc);
+        }
+        const bool dead = (j >= nk) || ms[j & (KT - 1)] || (causal && (j0 + j) > t);
+        s[jj] = dead ? -INFINITY : acc;
+        cmax = fmaxf(cmax, s[jj]);
+      }
+      if (cmax == -INFINITY) continue;
+      const float mnew = fmaxf(mrun, cmax);
+      const float corr = __expf(mrun - mnew);  // mrun = -inf -> 0
+      lrun *= corr;
+#pragma unroll
+      for (int i = 0; i < DH; ++i) o[i] *= corr;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const float p = __expf(s[jj] - mnew);  // -inf -> 0
+        lrun += p;
+        const int j = (c0 + jj) & (KT - 1);
+#pragma unroll
+        for (int i = 0; i < DH; i += 4) {
+          const float4 f = *reinterpret_cast<const float4*>(&vs[j][i]);
+          o[i] = fmaf(p, f.x, o[i]); o[i + 1] = fmaf(p, f.y, o[i + 1]);
+          o[i + 2] = fmaf(p, f.z, o[i + 2]); o[i + 3] = fmaf(p, f.w, o[i + 3]);
+        }
+      }
+      mrun = mnew;
+    }
+  }
+  if (!active) return;
+  const float inv = 1.f / lrun;
+  const long long orow = (static_cast<long long>(b) * Tq + t) * ldo + h * DH;
+#pragma unroll
+  for (int i = 0; i < DH; ++i) {
+    const float y = o[i] * inv;
+    if (out_f32) out_f32[orow + i] = y;
+    if (out_split) store_split(out_split, out_plane, orow + i, y);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Single-query attention against a K/V cache (greedy decode).  One warp per (batch, head).
+//   q: [B, ldq] fp32 (+ h*DH);  K/V row j of batch b: base + (b*kv_bstride + j)*ldk + h*DH
+//   mask: uint8 [B, mask_ld] or null; Tk keys.  Output: split bf16 [2, B, H*DH].
+// Replaces the full-prefix recompute of retrieval_augmented_autoreg.py:271-297.
+// ------------------------------------------------------------------------------------------------
+template <int DH>
+__global__ void __launch_bounds__(128)
+attention_decode_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k,
+                        const float* __restrict__ v, long long kv_bstride, int ldk,
+                        const unsigned char* __restrict__ mask, int mask_ld, int Tk, int B, int H, float scale,
+                        __nv_bfloat16* __restrict__ out_split, long long out_plane, int ldo) {
+  extern __shared__ float probs[];  // [warps][Tk_pad]
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.x * (blockDim.x >> 5) + wid;
+  if (bh >= B * H) return;
+  const int b = bh / H, h = bh - b * H;
+  const int tk_pad = (Tk + 31) & ~31;
+  float* pr = probs + wid * tk_pad;
+  float qr[DH];
+  const float* qp = q + static_cast<long long>(b) * ldq + h * DH;
+#pragma unroll
+  for (int i = 0; i < DH; i += 4) {
+    const float4 f = *reinterpret_cast<const float4*>(qp + i);
+    qr[i] = f.x * scale; qr[i + 1] = f.y * scale; qr[i + 2] = f.z * scale; qr[i + 3] = f.w * scale;
+  }
+  const float* kb = k + static_cast<long long>(b) * kv_bstride * ldk + h * DH;
+  const float* vb = v + static_cast<long long>(b) * kv_bstride * ldk + h * DH;
+  float lmax = -INFINITY;
+  for (int j = lane; j < Tk; j += 32) {
+    const float* kr = kb + static_cast<long long>(j) * ldk;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < DH; i += 4) {
+      const float4 f = *reinterpret_cast<const float4*>(kr + i);
+      acc = fmaf(qr[i], f.x, acc); acc = fmaf(qr[i + 1], f.y, acc);
+      acc = fmaf(qr[i + 2], f.z, acc); acc = fmaf(qr[i + 3], f.w, acc);
+    }
+    if (mask && mask[static_cast<long long>(b) * mask_ld + j]) acc = -INFINITY;
+    pr[j] = acc;
+    lmax = fmaxf(lmax, acc);
+  }
+  lmax = warp_max(lmax);
+  float lsum = 0.f;
+  for (int j = lane; j < Tk; j += 32) {
+    const float p = __expf(pr[j] - lmax);
+    pr[j] = p;
+    lsum += p;
+  }
+  lsum = warp_sum(lsum);
+  __syncwarp();
+  const float inv = 1.f / lsum;
+  // o[d] = sum_j p_j V[j][d]; lane owns dims lane (+32)
+  float o0 = 0.f, o1 = 0.f;
+  int j = 0;
+  for (; j + 4 <= Tk; j += 4) {
+    float a[4], c[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float* vr = vb + static_cast<long long>(j + u) * ldk;
+      a[u] = vr[lane];
+      c[u] = (DH == 64) ? vr[lane + 32] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float p = pr[j + u];
+      o0 = fmaf(p, a[u], o0);
+      o1 = fmaf(p, c[u], o1);
+    }
+  }
+  for (; j < Tk; ++j) {
+    const float* vr = vb + static_cast<long long>(j) * ldk;
+    const float p = pr[j];
+    o0 = fmaf(p, vr[lane], o0);
+    if (DH == 64) o1 = fmaf(p, vr[lane + 32], o1);
+  }
+  const long long orow = static_cast<long long>(b) * ldo + h * DH;
+  store_split(out_split, out_plane, orow + lane, o0 * inv);
+  if (DH == 64) store_split(out_split, out_plane, orow + lane + 32, o1 * inv);
+}
+
+// ------------------------------------------------------------------------------------------------
+// ResNet stem im2col: image fp32 NCHW [B, 4, H, W] -> split rows [B*Ho*Wo, KP] with k = (kh*7+kw)*4+c
+// for the 7x7 / stride 2 / pad 3 convolution (common/image.py:69-77), zero padded to KP columns.
+// ------------------------------------------------------------------------------------------------
+__global__ void stem_im2col_kernel(const float* __restrict__ img, int B, int H, int W, int Ho, int Wo, int KP,
+                                   __nv_bfloat16* __restrict__ out, long long plane) {
+  const long long total = static_cast<long long>(B) * Ho * Wo * 50;  // 49 taps + 1 pad group of 4
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int tap = static_cast<int>(i % 50);
+    const long long pix = i / 50;
+    const int ox = static_cast<int>(pix % Wo);
+    const int oy = static_cast<int>((pix / Wo) % Ho);
+    const int b = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+    float vals[4] = {0.f, 0.f, 0.f, 0.f};
+    if (tap < 49) {
+      const int kh = tap / 7, kw = tap % 7;
+      const int iy = oy * 2 - 3 + kh, ix = ox * 2 - 3 + kw;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) vals[c] = img[((static_cast<long long>(b) * 4 + c) * H + iy) * W + ix];
+      }
+    }
+    const long long off = pix * KP + tap * 4;
+    if (tap * 4 + 4 <= KP) {
+      __nv_bfloat16 h[4], l[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) split_bf16(vals[c], h[c], l[c]);
+      *reinterpret_cast<uint2*>(out + off) = make_uint2(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]));
+      *reinterpret_cast<uint2*>(out + plane + off) = make_uint2(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]));
+    }
+  }
+}
+
+// Generic NHWC im2col on split activations: in [2][B,H,W,C] -> out [2][B*Ho*Wo, KH*KW*C]
+// (k = (kh*KW + kw)*C + c), 8 channels (16 bytes) per thread.  Used for the 3x3 convolutions and
+// the strided 1x1 downsample convolutions of ResNet50 / the FPN 3x3.
+__global__ void im2col_kernel(const __nv_bfloat16* __restrict__ in, long long in_plane, int B, int H, int W, int C,
+                              int KH, int KW, int stride, int pad, int Ho, int Wo,
+                              __nv_bfloat16* __restrict__ out, long long out_plane) {
+  const int c8 = C >> 3;
+  const long long total = static_cast<long long>(B) * Ho * Wo * KH * KW * c8;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cc = static_cast<int>(i % c8);
+    long long r = i / c8;
+    const int kw = static_cast<int>(r % KW); r /= KW;
+    const int kh = static_cast<int>(r % KH); r /= KH;
+    const long long pix = r;
+    const int ox = static_cast<int>(pix % Wo);
+    const int oy = static_cast<int>((pix / Wo) % Ho);
+    const int b = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+    const int iy = oy * stride - pad + kh, ix = ox * stride - pad + kw;
+    uint4 h = make_uint4(0, 0, 0, 0), l = h;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      const long long src = ((static_cast<long long>(b) * H + iy) * W + ix) * C + cc * 8;
+      h = *reinterpret_cast<const uint4*>(in + src);
+      l = *reinterpret_cast<const uint4*>(in + in_plane + src);
+    }
+    const long long dst = pix * (static_cast<long long>(KH) * KW * C) + (static_cast<long long>(kh) * KW + kw) * C + cc * 8;
+    *reinterpret_cast<uint4*>(out + dst) = h;
+    *reinterpret_cast<uint4*>(out + out_plane + dst) = l;
+  }
+}
+
+// 3x3 / stride 2 / pad 1 max-pool on split NHWC (ResNet stem pool).  2 channels per thread.
+__global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ in, long long in_plane, int B, int H, int W, int C,
+                               int Ho, int Wo, __nv_bfloat16* __restrict__ out, long long out_plane) {
+  const int c2 = C >> 1;
+  const long long total = static_cast<long long>(B) * Ho * Wo * c2;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cc = static_cast<int>(i % c2);
+    const long long pix = i / c2;
+    const int ox = static_cast<int>(pix % Wo);
+    const int oy = static_cast<int>((pix / Wo) % Ho);
+    const int b = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int iy = oy * 2 - 1 + kh;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int ix = ox * 2 - 1 + kw;
+        if (ix < 0 || ix >= W) continue;
+        const long long src = ((static_cast<long long>(b) * H + iy) * W + ix) * C + cc * 2;
+        const uint32_t hw = *reinterpret_cast<const uint32_t*>(in + src);
+        const uint32_t lw = *reinterpret_cast<const uint32_t*>(in + in_plane + src);
+        m0 = fmaxf(m0, __uint_as_float(hw << 16) + __uint_as_float(lw << 16));
+        m1 = fmaxf(m1, __uint_as_float(hw & 0xffff0000u) + __uint_as_float(lw & 0xffff0000u));
+      }
+    }
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(m0, h0, l0);
+    split_bf16(m1, h1, l1);
+    const long long dst = pix * C + cc * 2;
+    *reinterpret_cast<uint32_t*>(out + dst) = pack_bf16(h0, h1);
+    *reinterpret_cast<uint32_t*>(out + out_plane + dst) = pack_bf16(l0, l1);
+  }
+}
+
+// FPN merge (common/image.py:103-111): up = nearest(c5 -> h4 x w4); fused[:, 0:C] = up;
+// sum = up + c4.  c5 [B,h5,w5,C] fp32, c4 [B,h4,w4,C] fp32; outputs split, fused row stride ldf.
+__global__ void fpn_merge_kernel(const float* __restrict__ c5, const float* __restrict__ c4, int B, int h5, int w5,
+                                 int h4, int w4, int C, __nv_bfloat16* __restrict__ fused, long long fused_plane,
+                                 int ldf, __nv_bfloat16* __restrict__ sum, long long sum_plane) {
+  const long long total = static_cast<long long>(B) * h4 * w4 * C;
+  const float sy = static_cast<float>(h5) / static_cast<float>(h4);
+  const float sx = static_cast<float>(w5) / static_cast<float>(w4);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const long long pix = i / C;
+    const int x = static_cast<int>(pix % w4);
+    const int y = static_cast<int>((pix / w4) % h4);
+    const int b = static_cast<int>(pix / (static_cast<long long>(w4) * h4));
+    // F.interpolate(mode="nearest"): src = min(floor(dst * in/out), in - 1)
+    const int yy = min(static_cast<int>(floorf(static_cast<float>(y) * sy)), h5 - 1);
+    const int xx = min(static_cast<int>(floorf(static_cast<float>(x) * sx)), w5 - 1);
+    const float up = c5[((static_cast<long long>(b) * h5 + yy) * w5 + xx) * C + c];
+    store_split(fused, fused_plane, pix * ldf + c, up);
+    store_split(sum, sum_plane, pix * C + c, up + c4[pix * C + c]);
+  }
+}
+
+// Row glue: out[map(r), :] = in[r*in_ld + :] * scale + add + table[(r % tab_mod), :]
+// (positional encodings, concatenations, CLS-token fill).  in may be null (zeros).
+__global__ void rows_affine_kernel(const float* __restrict__ in, long long in_ld, int M, int D, float scale,
+                                   float add, const float* __restrict__ table, int tab_mod, int rpg, int gs, int go,
+                                   float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_split,
+                                   long long out_plane, int out_ld) {
+  const long long total = static_cast<long long>(M) * D;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % D);
+    const int r = static_cast<int>(i / D);
+    float y = (in ? in[static_cast<long long>(r) * in_ld + c] : 0.f) * scale + add;
+    if (table) y += table[static_cast<long long>(r % tab_mod) * D + c];
+    const long long orow = static_cast<long long>(r / rpg) * gs + go + r % rpg;
+    if (out_f32) out_f32[orow * out_ld + c] = y;
+    if (out_split) store_split(out_split, out_plane, orow * out_ld + c, y);
+  }
+}
+
+// Token embedding (BaseDecoder / UserConstraintTransformerEncoder front end, common/common.py:99-100,
+// 243-245): out[r, :] = emb[tok[r], :] * scale + pe[(pos0 + r % S), :]
+__global__ void embed_kernel(const long long* __restrict__ tok, long long tok_ld, int tok_col, int Bn, int S,
+                             const float* __restrict__ emb, int D, float scale, const float* __restrict__ pe,
+                             int pos0, float* __restrict__ out) {
+  const long long total = static_cast<long long>(Bn) * S * D;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % D);
+    const long long r = i / D;
+    const int s = static_cast<int>(r % S);
+    const int b = static_cast<int>(r / S);
+    const long long t = tok[static_cast<long long>(b) * tok_ld + tok_col + s];
+    out[i] = emb[t * D + c] * scale + pe[static_cast<long long>(pos0 + s) * D + c];
+  }
+}
+
+// FIDNetV3 input (fid/model.py:95-101): row = cat[fc_bbox(cx,cy,w,h), emb_label[label]] -> split [rows, 2*D]
+__global__ void fid_embed_kernel(const float* __restrict__ cx, const float* __restrict__ cy, const float* __restrict__ w,
+                                 const float* __restrict__ h, const long long* __restrict__ label, int rows, int D,
+                                 const float* __restrict__ fc_w /*[D,4]*/, const float* __restrict__ fc_b,
+                                 const float* __restrict__ emb /*[L,D]*/, __nv_bfloat16* __restrict__ out,
+                                 long long plane) {
+  const long long total = static_cast<long long>(rows) * 2 * D;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % (2 * D));
+    const long long r = i / (2 * D);
+    float y;
+    if (c < D) {
+      // nn.Linear(4, D) on BBOX_KEYS order (center_x, center_y, width, height), fid/data.py
+      float acc = fc_b[c];
+      acc = fmaf(cx[r], fc_w[c * 4 + 0], acc);
+      acc = fmaf(cy[r], fc_w[c * 4 + 1], acc);
+      acc = fmaf(w[r], fc_w[c * 4 + 2], acc);
+      acc = fmaf(h[r], fc_w[c * 4 + 3], acc);
+      y = acc;
+    } else {
+      y = emb[label[r] * D + (c - D)];
+    }
+    store_split(out, plane, i, y);
+  }
+}
+
+// Greedy step tail (retrieval_augmented_autoreg.py:281-297, helpers/sampling.py:24-25):
+// logits[b, allowed == 0] = -inf; tok = argmax (first max wins, like torch.argmax); seq[b, pos] = tok;
+// pad_mask[b, pos] = (tok == pad); optionally x_next[b, :] = emb[tok]*scale + pe[pos].
+__global__ void argmax_next_kernel(const float* __restrict__ logits, int ldl, int V,
+                                   const unsigned char* __restrict__ allowed, long long* __restrict__ seq, int seq_ld,
+                                   int pos, unsigned char* __restrict__ pad_mask, int mask_ld, long long pad_id,
+                                   const float* __restrict__ emb, int D, float scale, const float* __restrict__ pe,
+                                   float* __restrict__ x_next) {
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __shared__ float bv[8];
+  __shared__ int bi[8];
+  __shared__ int win;
+  float best = -INFINITY;
+  int arg = 0x7fffffff;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) {
+    const float x = allowed[c] ? logits[static_cast<long long>(b) * ldl + c] : -INFINITY;
+    if (x > best || (x == best && c < arg)) { best = x; arg = c; }
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, off);
+    const int oi = __shfl_xor_sync(0xffffffffu, arg, off);
+    if (ov > best || (ov == best && oi < arg)) { best = ov; arg = oi; }
+  }
+  if (lane == 0) { bv[wid] = best; bi[wid] = arg; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = bv[0];
+    int a = bi[0];
+    for (int w = 1; w < static_cast<int>(blockDim.x >> 5); ++w)
+      if (bv[w] > v || (bv[w] == v && bi[w] < a)) { v = bv[w]; a = bi[w]; }
+    win = a;
+    seq[static_cast<long long>(b) * seq_ld + pos] = a;
+    if (pad_mask) pad_mask[static_cast<long long>(b) * mask_ld + pos] = (a == pad_id) ? 1 : 0;
+  }
+  __syncthreads();
+  if (x_next) {
+    const int t = win;
+    for (int c = threadIdx.x; c < D; c += blockDim.x)
+      x_next[static_cast<long long>(b) * D + c] = emb[static_cast<long long>(t) * D + c] * scale + pe[static_cast<long long>(pos) * D + c];
+  }
+}
+
+// Scatter this step's K and V (columns [D, 3D) of the fused QKV projection) into the self-attention cache.
+__global__ void kv_append_kernel(const float* __restrict__ qkv, int B, int D, float* __restrict__ kcache,
+                                 float* __restrict__ vcache, int S, int pos) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * D) return;
+  const int b = i / D, c = i - b * D;
+  kcache[(static_cast<long long>(b) * S + pos) * D + c] = qkv[static_cast<long long>(b) * 3 * D + D + c];
+  vcache[(static_cast<long long>(b) * S + pos) * D + c] = qkv[static_cast<long long>(b) * 3 * D + 2 * D + c];
+}
+
+static inline int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  return static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace ralf
+
+using namespace ralf;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
+#define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+
+extern "C" int ralf_layernorm(const float* x, long long in_ld, const float* gamma, const float* beta, float eps,
+                              int M, int D, float* out_f32, void* out_split, long long out_plane, void* stream) {
+  if (!x || !gamma || !beta) return RALF_ERR_NULL;
+  if (M <= 0 || D <= 0 || D > 1024 || (D & 31)) return RALF_ERR_SHAPE;
+  layernorm_kernel<<<(M + 7) / 8, 256, 0, ST(stream)>>>(x, in_ld, gamma, beta, eps, M, D, out_f32, BF(out_split),
+                                                       out_plane);
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_attention(const float* q, int ldq, const float* k, const float* v, int ldk,
+                              const unsigned char* key_padding_mask, int B, int H, int Tq, int Tk, int head_dim,
+                              int causal, float scale, void* out_split, long long out_plane, float* out_f32, int ldo,
+                              void* stream) {
+  if (!q || !k || !v) return RALF_ERR_NULL;
+  if (B <= 0 || H <= 0 || Tq <= 0 || Tk <= 0 || (head_dim != 32 && head_dim != 64)) return RALF_ERR_SHAPE;
+  if ((ldq & 3) || (ldk & 3)) return RALF_ERR_ALIGN;
+  const int threads = Tq >= 128 ? 128 : ((Tq + 31) / 32) * 32;
+  dim3 grid((Tq + threads - 1) / threads, H, B);
+  if (head_dim == 32)
+    attention_kernel<32><<<grid, threads, 0, ST(stream)>>>(q, ldq, k, v, ldk, key_padding_mask, Tq, Tk, causal, scale,
+                                                          BF(out_split), out_plane, out_f32, ldo);
+  else
+    attention_kernel<64><<<grid, threads, 0, ST(stream)>>>(q, ldq, k, v, ldk, key_padding_mask, Tq, Tk, causal, scale,
+                                                          BF(out_split), out_plane, out_f32, ldo);
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_attention_decode(const float* q, int ldq, const float* k, const float* v, long long kv_bstride,
+                                     int ldk, const unsigned char* key_padding_mask, int mask_ld, int Tk, int B, int H,
+                                     int head_dim, float scale, void* out_split, long long out_plane, int ldo,
+                                     void* stream) {
+  if (!q || !k || !v || !out_split) return RALF_ERR_NULL;
+  if (B <= 0 || H <= 0 || Tk <= 0 || Tk > 2048 || (head_dim != 32 && head_dim != 64)) return RALF_ERR_SHAPE;
+  if ((ldq & 3) || (ldk & 3)) return RALF_ERR_ALIGN;
+  const int warps = 4;
+  const size_t smem = static_cast<size_t>(warps) * ((Tk + 31) & ~31) * sizeof(float);
+  const int grid = (B * H + warps - 1) / warps;
+  if (head_dim == 32)
+    attention_decode_kernel<32><<<grid, warps * 32, smem, ST(stream)>>>(q, ldq, k, v, kv_bstride, ldk, key_padding_mask,
+                                                                       mask_ld, Tk, B, H, scale, BF(out_split),
+                                                                       out_plane, ldo);
+  else
+    attention_decode_kernel<64><<<grid, warps * 32, smem, ST(stream)>>>(q, ldq, k, v, kv_bstride, ldk, key_padding_mask,
+                                                                       mask_ld, Tk, B, H, scale, BF(out_split),
+                                                                       out_plane, ldo);
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_stem_im2col(const float* img, int B, int H, int W, int KP, void* out, long long out_plane,
+                                void* stream) {
+  if (!img || !out) return RALF_ERR_NULL;
+  if (B <= 0 || H <= 0 || W <= 0 || KP < 196 || KP > 200 || (KP & 7)) return RALF_ERR_SHAPE;
+  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+  const long long total = static_cast<long long>(B) * Ho * Wo * 50;
+  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(img, B, H, W, Ho, Wo, KP, BF(out), out_plane);
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_im2col(const void* in, long long in_plane, int B, int H, int W, int C, int KH, int KW, int stride,
+                           int pad, void* out, long long out_plane, void* stream) {
+  if (!in || !out) return RALF_ERR_NULL;
+  if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 7) || KH <= 0 || KW <= 0 || stride <= 0) return RALF_ERR_SHAPE;
+  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  const long long total = static_cast<long long>(B) * Ho * Wo * KH * KW * (C >> 3);
+  im2col_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(CBF(in), in_plane, B, H, W, C, KH, KW, stride, pad, Ho,
+                                                             Wo, BF(out), out_plane);
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_maxpool3x3s2(const void* in, long long in_plane, int B, int H, int W, int C, void* out,
+                                 long long out_plane, void* stream) {
+  if (!in || !out) return RALF_ERR_NULL;
+  if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 1)) return RALF_ERR_SHAPE;
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long total = static_cast<long long>(B) * Ho * Wo * (C >> 1);
+  maxpool_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(CBF(in), in_plane, B, H, W, C, Ho, Wo, BF(out),
+                                                              out_plane);
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_fpn_merge(const float* c5, const float* c4, int B, int h5, int w5, int h4, int w4, int C,
+                              void* fused, long long fused_plane, int ldf, void* sum, long long sum_plane,
+                              void* stream) {
+  if (!c5 || !c4 || !fused || !sum) return RALF_ERR_NULL;
+  if (B <= 0 || h5 <= 0 || w5 <= 0 || h4 <= 0 || w4 <= 0 || C <= 0) return RALF_ERR_SHAPE;
+  const long long total = static_cast<long long>(B) * h4 * w4 * C;
+  fpn_merge_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(c5, c4, B, h5, w5, h4, w4, C, BF(fused), fused_plane,
+                                                                ldf, BF(sum), sum_plane);
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_rows_affine(const float* in, long long in_ld, int M, int D, float scale, float add,
+                                const float* table, int tab_mod, int rows_per_group, int group_stride,
+                                int group_offset, float* out_f32, void* out_split, long long out_plane, int out_ld,
+                                void* stream) {
+  if (M <= 0 || D <= 0) return RALF_ERR_SHAPE;
+  if (!out_f32 && !out_split) return RALF_ERR_NULL;
+  const int rpg = rows_per_group > 0 ? rows_per_group : M;
+  const int gs = rows_per_group > 0 ? group_stride : 0;
+  const int go = rows_per_group > 0 ? group_offset : 0;
+  const long long total = static_cast<long long>(M) * D;
+  rows_affine_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(in, in_ld, M, D, scale, add, table,
+                                                                  tab_mod > 0 ? tab_mod : 1, rpg, gs, go, out_f32,
+                                                                  BF(out_split), out_plane, out_ld);
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_embed(const long long* tok, long long tok_ld, int tok_col, int B, int S, const float* emb, int D,
+                          float scale, const float* pe, int pos0, float* out, void* stream) {
+  if (!tok || !emb || !pe || !out) return RALF_ERR_NULL;
+  if (B <= 0 || S <= 0 || D <= 0) return RALF_ERR_SHAPE;
+  const long long total = static_cast<long long>(B) * S * D;
+  embed_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(tok, tok_ld, tok_col, B, S, emb, D, scale, pe, pos0, out);
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_fid_embed(const float* cx, const float* cy, const float* w, const float* h, const long long* label,
+                              int rows, int D, const float* fc_w, const float* fc_b, const float* emb, void* out,
+                              long long out_plane, void* stream) {
+  if (!cx || !cy || !w || !h || !label || !fc_w || !fc_b || !emb || !out) return RALF_ERR_NULL;
+  if (rows <= 0 || D <= 0) return RALF_ERR_SHAPE;
+  const long long total = static_cast<long long>(rows) * 2 * D;
+  fid_embed_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(cx, cy, w, h, label, rows, D, fc_w, fc_b, emb, BF(out),
+                                                                out_plane);
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_argmax_next(const float* logits, int ldl, int B, int V, const unsigned char* allowed,
+                                long long* seq, int seq_ld, int pos, unsigned char* pad_mask, int mask_ld,
+                                long long pad_id, const float* emb, int D, float scale, const float* pe, float* x_next,
+                                void* stream) {
+  if (!logits || !allowed || !seq) return RALF_ERR_NULL;
+  if (B <= 0 || V <= 0) return RALF_ERR_SHAPE;
+  argmax_next_kernel<<<B, 128, 0, ST(stream)>>>(logits, ldl, V, allowed, seq, seq_ld, pos, pad_mask, mask_ld, pad_id,
+                                               emb, D, scale, pe, x_next);
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_kv_append(const float* qkv, int B, int D, float* kcache, float* vcache, int S, int pos,
+                              void* stream) {
+  if (!qkv || !kcache || !vcache) return RALF_ERR_NULL;
+  if (B <= 0 || D <= 0 || pos < 0 || pos >= S) return RALF_ERR_SHAPE;
+  kv_append_kernel<<<(B * D + 255) / 256, 256, 0, ST(stream)>>>(qkv, B, D, kcache, vcache, S, pos);
+  return set_cuda_error(cudaGetLastError());
+}
