@@ -107,6 +107,61 @@ typedef struct RalfGemmArgs {
 } RalfGemmArgs;
 int ralf_gemm(const RalfGemmArgs* args, void* stream);
 
+
+/* ---------------------------------------------------------------------------------------------
+ * K3. Non-GEMM ops of the forward / generate path (fp32 CUDA-core kernels, csrc/nn_kernels.cu).
+ * "split" outputs feed the next GEMM directly.
+ * ------------------------------------------------------------------------------------------- */
+/* nn.LayerNorm(D) over rows of x (row stride in_ld); D % 32 == 0, D <= 1024. */
+int ralf_layernorm(const float* x, long long in_ld, const float* gamma, const float* beta, float eps,
+                   int M, int D, float* out_f32, void* out_split, long long out_plane, void* stream);
+/* softmax(q k^T * scale + masks) v per (batch, head); replaces nn.MultiheadAttention's core inside
+ * nn.TransformerEncoderLayer / DecoderLayer (common/common.py:26-35) and common/attention.py:64-69.
+ * q row (b,t) at q + (b*Tq+t)*ldq + h*head_dim; k/v row (b,j) at k + (b*Tk+j)*ldk + h*head_dim.
+ * key_padding_mask: uint8 [B,Tk], nonzero = padded key; causal: keys j > t masked. */
+int ralf_attention(const float* q, int ldq, const float* k, const float* v, int ldk,
+                   const unsigned char* key_padding_mask, int B, int H, int Tq, int Tk, int head_dim,
+                   int causal, float scale, void* out_split, long long out_plane, float* out_f32, int ldo,
+                   void* stream);
+/* One query per (batch, head) against a K/V cache: the KV-cached replacement of the reference's
+ * full-prefix recompute (retrieval_augmented_autoreg.py:271-297).  K/V row j of batch b at
+ * base + (b*kv_bstride + j)*ldk + h*head_dim. */
+int ralf_attention_decode(const float* q, int ldq, const float* k, const float* v, long long kv_bstride,
+                          int ldk, const unsigned char* key_padding_mask, int mask_ld, int Tk, int B, int H,
+                          int head_dim, float scale, void* out_split, long long out_plane, int ldo,
+                          void* stream);
+/* ResNet50 stem (common/image.py:69-77): image fp32 NCHW [B,4,H,W] -> split im2col rows
+ * [B*Ho*Wo, KP] for the 7x7/s2/p3 conv, k = (kh*7+kw)*4 + c, KP = 200 (zero padded). */
+int ralf_stem_im2col(const float* img, int B, int H, int W, int KP, void* out, long long out_plane,
+                     void* stream);
+/* NHWC split im2col: [B,H,W,C] -> [B*Ho*Wo, KH*KW*C], k = (kh*KW+kw)*C + c; C % 8 == 0. */
+int ralf_im2col(const void* in, long long in_plane, int B, int H, int W, int C, int KH, int KW, int stride,
+                int pad, void* out, long long out_plane, void* stream);
+int ralf_maxpool3x3s2(const void* in, long long in_plane, int B, int H, int W, int C, void* out,
+                      long long out_plane, void* stream);
+/* FPN merge (common/image.py:103-111): fused[:, 0:C] = nearest-upsampled c5; sum = up + c4. */
+int ralf_fpn_merge(const float* c5, const float* c4, int B, int h5, int w5, int h4, int w4, int C,
+                   void* fused, long long fused_plane, int ldf, void* sum, long long sum_plane, void* stream);
+/* out[map(r), :] = in[r, :] * scale + add + table[r % tab_mod, :]  (in/table may be NULL). */
+int ralf_rows_affine(const float* in, long long in_ld, int M, int D, float scale, float add,
+                     const float* table, int tab_mod, int rows_per_group, int group_stride, int group_offset,
+                     float* out_f32, void* out_split, long long out_plane, int out_ld, void* stream);
+/* out[b*S+s, :] = emb[tok[b*tok_ld + tok_col + s], :] * scale + pe[pos0 + s, :]
+ * (common/common.py:99-100, positional_encoding.py:94-107). */
+int ralf_embed(const long long* tok, long long tok_ld, int tok_col, int B, int S, const float* emb, int D,
+               float scale, const float* pe, int pos0, float* out, void* stream);
+/* FIDNetV3 input rows cat[fc_bbox(cx,cy,w,h), emb_label[label]] (fid/model.py:95-101). */
+int ralf_fid_embed(const float* cx, const float* cy, const float* w, const float* h, const long long* label,
+                   int rows, int D, const float* fc_w, const float* fc_b, const float* emb, void* out,
+                   long long out_plane, void* stream);
+/* Greedy step tail (retrieval_augmented_autoreg.py:281-297, helpers/sampling.py:24-25): mask the
+ * vocabulary, argmax (first maximum), append to seq[:, pos], update the pad mask, embed the token. */
+int ralf_argmax_next(const float* logits, int ldl, int B, int V, const unsigned char* allowed, long long* seq,
+                     int seq_ld, int pos, unsigned char* pad_mask, int mask_ld, long long pad_id,
+                     const float* emb, int D, float scale, const float* pe, float* x_next, void* stream);
+/* Append this step's K,V (columns [D,3D) of the fused QKV row) to the self-attention cache [B,S,D]. */
+int ralf_kv_append(const float* qkv, int B, int D, float* kcache, float* vcache, int S, int pos, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,6 +63,19 @@ def lib() -> C.CDLL:
                                      C.c_void_p]
         L.ralf_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
         L.ralf_check_device.argtypes = [C.c_int]
+        vp, i, ll, f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+        L.ralf_layernorm.argtypes = [vp, ll, vp, vp, f, i, i, vp, vp, ll, vp]
+        L.ralf_attention.argtypes = [vp, i, vp, vp, i, vp, i, i, i, i, i, i, f, vp, ll, vp, i, vp]
+        L.ralf_attention_decode.argtypes = [vp, i, vp, vp, ll, i, vp, i, i, i, i, i, f, vp, ll, i, vp]
+        L.ralf_stem_im2col.argtypes = [vp, i, i, i, i, vp, ll, vp]
+        L.ralf_im2col.argtypes = [vp, ll, i, i, i, i, i, i, i, i, vp, ll, vp]
+        L.ralf_maxpool3x3s2.argtypes = [vp, ll, i, i, i, i, vp, ll, vp]
+        L.ralf_fpn_merge.argtypes = [vp, vp, i, i, i, i, i, i, vp, ll, i, vp, ll, vp]
+        L.ralf_rows_affine.argtypes = [vp, ll, i, i, f, f, vp, i, i, i, i, vp, vp, ll, i, vp]
+        L.ralf_embed.argtypes = [vp, ll, i, i, i, vp, i, f, vp, i, vp, vp]
+        L.ralf_fid_embed.argtypes = [vp, vp, vp, vp, vp, i, i, vp, vp, vp, vp, ll, vp]
+        L.ralf_argmax_next.argtypes = [vp, i, i, i, vp, vp, i, i, vp, i, ll, vp, i, f, vp, vp, vp]
+        L.ralf_kv_append.argtypes = [vp, i, i, vp, vp, i, i, vp]
         _lib = L
     return _lib
 

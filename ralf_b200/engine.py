@@ -1,0 +1,424 @@
+"""B200 execution engine for the RALF / Autoreg forward and greedy-generation path.
+
+Takes a state dict with the REFERENCE's key names (strict-load contract) and runs
+the whole path as hand-written sm_100a kernels behind the C ABI (include/ralf_b200.h):
+
+  image --stem im2col / tcgen05 GEMM (BN folded) / max-pool / 16 bottlenecks / FPN-->  [B*hw, 256]
+        --6 pre-LN encoder layers-->  memory_img
+  retrieved layouts [B,16,E] --FIDNetV3 (4 post-LN layers, batched over B*16) / adapter / PE--> ref [B,16,256]
+  fusion attention(memory_img, ref), head FFN over cat[memory_img, memory_ca, ref], constraint encoder,
+  concat  -->  memory [B, M, 256];  decoder cross K/V for all 6 layers in ONE GEMM (N = 3072)
+  greedy decode with self-attention KV cache + precomputed cross K/V (the reference recomputes the full
+  prefix and the memory projections at every step: retrieval_augmented_autoreg.py:271-297).
+
+Torch is used for device memory, streams and CUDA graphs only; every arithmetic kernel on the path is ours.
+Reference citations are relative to image2layout/train/.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import ops
+
+NHEAD = 8
+NLAYER = 6
+D = 256
+
+
+def _sine_pe_1d(max_len: int, d_model: int) -> torch.Tensor:
+    """models/common/positional_encoding.py:71-81."""
+    position = torch.arange(max_len).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2) * (-math.log(10000.0) / d_model))
+    pe = torch.zeros(max_len, d_model)
+    pe[:, 0::2] = torch.sin(position * div_term)
+    pe[:, 1::2] = torch.cos(position * div_term)
+    return pe
+
+
+def _pos_emb_2d(h: int, w: int, d_model: int) -> torch.Tensor:
+    """PositionEmbeddingSine(normalize=True) as a [h*w, d] table (positional_encoding.py:182-210)."""
+    half = d_model // 2
+    y, x = torch.meshgrid(torch.arange(h).float(), torch.arange(w).float(), indexing="ij")
+    y = y / (h - 1) * (2 * math.pi)
+    x = x / (w - 1) * (2 * math.pi)
+    dim_t = torch.arange(half).float()
+    dim_t = 10000 ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / half)
+    px = x.flatten()[:, None] / dim_t
+    py = y.flatten()[:, None] / dim_t
+    px = torch.stack((px[:, 0::2].sin(), px[:, 1::2].cos()), dim=2).flatten(1)
+    py = torch.stack((py[:, 0::2].sin(), py[:, 1::2].cos()), dim=2).flatten(1)
+    return torch.cat((py, px), dim=1).contiguous()
+
+
+class Engine:
+    """Prepared weights + kernel orchestration.  ``is_ralf=False`` gives the Autoreg baseline (no retrieval)."""
+
+    def __init__(self, state_dict: dict, device: torch.device, *, is_ralf: bool = True, top_k: int = 16,
+                 npass: int = 3) -> None:
+        self.dev = device
+        self.is_ralf = is_ralf
+        self.top_k = top_k
+        self.npass = npass
+        self.w: dict[str, torch.Tensor] = {}
+        self._pos2d: dict[tuple[int, int], torch.Tensor] = {}
+        self._prepare({k: v.detach() for k, v in state_dict.items()})
+
+    # ------------------------------------------------------------------------------------------
+    # weight preparation (once per load_state_dict)
+    # ------------------------------------------------------------------------------------------
+    def _put(self, name: str, t: torch.Tensor) -> None:
+        self.w[name] = t.to(self.dev, torch.float32).contiguous()
+
+    def _put_w(self, name: str, w2d: torch.Tensor) -> None:
+        """Linear/conv weight [N, K] -> split bf16 [2, N, K] (K padded to a multiple of 8)."""
+        w2d = w2d.to(self.dev, torch.float32)
+        if w2d.shape[1] % 8:
+            w2d = torch.nn.functional.pad(w2d, (0, 8 - w2d.shape[1] % 8))
+        self.w[name] = ops.split_bf16(w2d.contiguous())
+
+    def _conv_bn(self, sd, conv: str, bn: Optional[str], name: str, bias_key: Optional[str] = None) -> None:
+        w = sd[conv + ".weight"].float()
+        cout = w.shape[0]
+        if bn is not None:  # eval-mode BatchNorm folded into the convolution
+            scale = sd[bn + ".weight"].float() / torch.sqrt(sd[bn + ".running_var"].float() + 1e-5)
+            bias = sd[bn + ".bias"].float() - sd[bn + ".running_mean"].float() * scale
+            w = w * scale[:, None, None, None]
+        else:
+            bias = sd[bias_key].float()
+        self._put_w(name + ".w", w.permute(0, 2, 3, 1).reshape(cout, -1))  # k = (kh*KW + kw)*Cin + c
+        self._put(name + ".b", bias)
+
+    def _lin(self, sd, key: str, name: Optional[str] = None, wscale: float = 1.0, badd: float = 0.0) -> None:
+        name = name or key
+        self._put_w(name + ".w", sd[key + ".weight"].float() * wscale)
+        if (key + ".bias") in sd:
+            self._put(name + ".b", sd[key + ".bias"].float() * wscale + badd)
+
+    def _norm(self, sd, key: str) -> None:
+        self._put(key + ".g", sd[key + ".weight"])
+        self._put(key + ".beta", sd[key + ".bias"])
+
+    def _enc_layer(self, sd, p: str, badd_last: float = 0.0) -> None:
+        self._put_w(p + ".qkv.w", sd[p + ".self_attn.in_proj_weight"])
+        self._put(p + ".qkv.b", sd[p + ".self_attn.in_proj_bias"])
+        self._lin(sd, p + ".self_attn.out_proj", p + ".o")
+        self._lin(sd, p + ".linear1")
+        self._lin(sd, p + ".linear2", badd=badd_last)
+        self._norm(sd, p + ".norm1")
+        self._norm(sd, p + ".norm2")
+
+    def _prepare(self, sd: dict) -> None:
+        b = "encoder.extractor.body"
+        self._conv_bn(sd, b + ".conv1", b + ".bn1", "stem")
+        self.blocks = []
+        for li, (nblk, stride, planes) in enumerate([(3, 1, 64), (4, 2, 128), (6, 2, 256), (3, 2, 512)], start=1):
+            for bi in range(nblk):
+                p = f"{b}.layer{li}.{bi}"
+                for c in (1, 2, 3):
+                    self._conv_bn(sd, f"{p}.conv{c}", f"{p}.bn{c}", f"{p}.c{c}")
+                has_ds = (p + ".downsample.0.weight") in sd
+                if has_ds:
+                    self._conv_bn(sd, p + ".downsample.0", p + ".downsample.1", p + ".ds")
+                self.blocks.append((p, li, stride if bi == 0 else 1, planes, has_ds))
+        e = "encoder.extractor"
+        for n in ("fpn_conv11_4", "fpn_conv11_5", "fpn_conv33", "proj"):
+            self._conv_bn(sd, f"{e}.{n}", None, f"{e}.{n}", bias_key=f"{e}.{n}.bias")
+        for i in range(NLAYER):
+            self._enc_layer(sd, f"transformer_encoder.layers.{i}")
+        t0 = float(sd["task_emb.weight"][int(sd["flag_img"][0]), 0])
+        t1 = float(sd["task_emb.weight"][int(sd["flag_user_const"][0]), 0])
+        self.t_img = t0
+        for i in range(NLAYER):  # flag embedding of the constraint branch folded into its last bias
+            self._enc_layer(sd, f"user_const_encoder.encoder.layers.{i}", badd_last=t1 if i == NLAYER - 1 else 0.0)
+        self._put("user_const_encoder.emb", sd["user_const_encoder.emb.weight"])
+        self._put("pe1d", _sine_pe_1d(5000, D))
+        if self.is_ralf:
+            f = "layout_encoer"
+            self._put(f + ".emb_label", sd[f + ".emb_label.weight"])
+            self._put(f + ".fc_bbox.w", sd[f + ".fc_bbox.weight"])
+            self._put(f + ".fc_bbox.b", sd[f + ".fc_bbox.bias"])
+            self._lin(sd, f + ".enc_fc_in")
+            self._put(f + ".token", sd[f + ".enc_transformer.token"].reshape(1, D))
+            for i in range(4):
+                self._enc_layer(sd, f"{f}.enc_transformer.core.layers.{i}")
+            self._norm(sd, "layout_adapter.net.0")
+            self._lin(sd, "layout_adapter.net.1")
+            # pos_emb_1d multiplies by sqrt(d) = 16 (an exact power of two): fold into the last linear
+            self._lin(sd, "layout_adapter.net.4", wscale=math.sqrt(D))
+            self._norm(sd, "attn.norm")
+            self._lin(sd, "attn.to_q")
+            self._lin(sd, "attn.to_kv")
+            self._lin(sd, "attn.to_out.0")
+            self._norm(sd, "head.net.0")
+            self._lin(sd, "head.net.1")
+            self._lin(sd, "head.net.4", badd=t0)  # + task_emb(flag_img)
+        # decoder
+        d = "decoder.transformer.layers"
+        wkv, bkv = [], []
+        for i in range(NLAYER):
+            p = f"{d}.{i}"
+            self._put_w(p + ".qkv.w", sd[p + ".self_attn.in_proj_weight"])
+            self._put(p + ".qkv.b", sd[p + ".self_attn.in_proj_bias"])
+            self._lin(sd, p + ".self_attn.out_proj", p + ".o")
+            cw, cb = sd[p + ".multihead_attn.in_proj_weight"].float(), sd[p + ".multihead_attn.in_proj_bias"].float()
+            self._put_w(p + ".cq.w", cw[:D])
+            self._put(p + ".cq.b", cb[:D])
+            wkv.append(cw[D:])
+            bkv.append(cb[D:])
+            self._lin(sd, p + ".multihead_attn.out_proj", p + ".co")
+            self._lin(sd, p + ".linear1")
+            self._lin(sd, p + ".linear2")
+            for n in ("norm1", "norm2", "norm3"):
+                self._norm(sd, f"{p}.{n}")
+        self._put_w("decoder.ckv.w", torch.cat(wkv, 0))  # [6*512, 256]: layer l -> K cols l*512.., V cols l*512+256..
+        self._put("decoder.ckv.b", torch.cat(bkv, 0))
+        self._put("decoder.emb", sd["decoder.emb.weight"])
+        self._norm(sd, "decoder.head.0")
+        self._put_w("decoder.head.1.w", sd["decoder.head.1.weight"])
+        self.vocab = sd["decoder.emb.weight"].shape[0]
+
+    # ------------------------------------------------------------------------------------------
+    # kernel helpers
+    # ------------------------------------------------------------------------------------------
+    def _gemm(self, a, name, **kw):
+        kw.setdefault("npass", self.npass)
+        return ops.gemm(a, self.w[name + ".w"], bias=self.w.get(name + ".b"), **kw)
+
+    def _ln(self, x, name, **kw):
+        return ops.layernorm(x, self.w[name + ".g"], self.w[name + ".beta"], **kw)
+
+    def pos2d(self, h: int, w: int) -> torch.Tensor:
+        if (h, w) not in self._pos2d:
+            self._pos2d[(h, w)] = _pos_emb_2d(h, w, D).to(self.dev)
+        return self._pos2d[(h, w)]
+
+    # ------------------------------------------------------------------------------------------
+    # image branch: ResNet50 + FPN (common/image.py:90-120), NHWC split activations
+    # ------------------------------------------------------------------------------------------
+    def resnet_fpn(self, img: torch.Tensor) -> tuple[torch.Tensor, int, int]:
+        """img fp32 [B,4,H,W] -> tokens fp32 [B*h*w, 256] with the 2-D sine PE already added."""
+        B = img.shape[0]
+        a, H, W = ops.stem_im2col(img.contiguous())
+        _, x = self._gemm(a, "stem", act="relu", want_f32=False, want_split=True)
+        del a
+        x, H, W = ops.maxpool3x3s2(x, B, H, W, 64)
+        C = 64
+        feats = {}
+        for (p, li, stride, planes, has_ds) in self.blocks:
+            _, t1 = self._gemm(x, p + ".c1", act="relu", want_f32=False, want_split=True)
+            a2, Ho, Wo = ops.im2col(t1, B, H, W, planes, 3, 3, stride, 1)
+            _, t2 = self._gemm(a2, p + ".c2", act="relu", want_f32=False, want_split=True)
+            del a2, t1
+            if has_ds:
+                xs = x if stride == 1 else ops.im2col(x, B, H, W, C, 1, 1, stride, 0)[0]
+                _, idt = self._gemm(xs, p + ".ds", want_f32=False, want_split=True)
+            else:
+                idt = x
+            _, x = self._gemm(t2, p + ".c3", res_split=idt, post_relu=True, want_f32=False, want_split=True)
+            H, W, C = Ho, Wo, planes * 4
+            feats[li] = (x, H, W)
+        e = "encoder.extractor"
+        l3, h4, w4 = feats[3]
+        l4, h5, w5 = feats[4]
+        c4, _ = self._gemm(l3, e + ".fpn_conv11_4")
+        c5, _ = self._gemm(l4, e + ".fpn_conv11_5")
+        fused, summ = ops.fpn_merge(c5, c4, B, h5, w5, h4, w4, D)
+        a33, _, _ = ops.im2col(summ, B, h4, w4, D, 3, 3, 1, 1)
+        self._gemm(a33, e + ".fpn_conv33", out_split=fused, out_col0=D, want_f32=False)
+        tokens, _ = self._gemm(fused, e + ".proj", res=self.pos2d(h4, w4), res_row_mod=h4 * w4)
+        return tokens, h4, w4
+
+    # ------------------------------------------------------------------------------------------
+    # transformer layers
+    # ------------------------------------------------------------------------------------------
+    def _prenorm_layer(self, x, p, B, T, mask=None, nhead=NHEAD, out=None, out_map=None, want_split=False):
+        """nn.TransformerEncoderLayer(norm_first=True, relu) in eval mode.  x fp32 [B*T, 256]."""
+        _, h = self._ln(x, p + ".norm1")
+        qkv, _ = self._gemm(h, p + ".qkv")
+        a = ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B, nhead, T, T, D // nhead, mask=mask)
+        x1, _ = self._gemm(a, p + ".o", res=x)
+        _, h = self._ln(x1, p + ".norm2")
+        _, f = self._gemm(h, p + ".linear1", act="relu", want_f32=False, want_split=True)
+        kw = {}
+        if out_map is not None:
+            kw = dict(rows_per_group=out_map[0], group_stride=out_map[1], group_offset=out_map[2])
+        if isinstance(out, tuple):
+            return self._gemm(f, p + ".linear2", res=x1, out_f32=out[0], out_split=out[1], **kw)
+        return self._gemm(f, p + ".linear2", res=x1, out_f32=out, want_split=want_split, **kw)
+
+    def _postnorm_layer(self, x, xs, p, B, T, mask, nhead):
+        """nn.TransformerEncoderLayer default (post-norm) -- FIDNetV3 (fid/model.py:26-33).
+        x fp32 [B*T,256] and its split copy xs."""
+        qkv, _ = self._gemm(xs, p + ".qkv")
+        a = ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B, nhead, T, T, D // nhead, mask=mask)
+        y, _ = self._gemm(a, p + ".o", res=x)
+        x1, x1s = self._ln(y, p + ".norm1", want_f32=True)
+        _, f = self._gemm(x1s, p + ".linear1", act="relu", want_f32=False, want_split=True)
+        y2, _ = self._gemm(f, p + ".linear2", res=x1)
+        return self._ln(y2, p + ".norm2", want_f32=True)
+
+    def encode_image(self, img: torch.Tensor):
+        tokens, h, w = self.resnet_fpn(img)
+        B, T = img.shape[0], h * w
+        x = tokens
+        for i in range(NLAYER):
+            x, _ = self._prenorm_layer(x, f"transformer_encoder.layers.{i}", B, T)
+        return x, T
+
+    # ------------------------------------------------------------------------------------------
+    # retrieved-layout branch (retrieval_augmented_autoreg.py:526-584; fid/model.py:95-103)
+    # ------------------------------------------------------------------------------------------
+    def retrieved_features(self, retrieved: dict, B: int):
+        """-> ref_layouts fp32 [B*K, 256] (already x16 + PE) and its split copy."""
+        K = self.top_k
+        E = retrieved["label"].shape[-1]
+        N = B * K
+        f = "layout_encoer"
+        fl = lambda t: t[:, :K].reshape(-1).to(self.dev, torch.float32).contiguous()
+        rows = ops.fid_embed(fl(retrieved["center_x"]), fl(retrieved["center_y"]), fl(retrieved["width"]),
+                             fl(retrieved["height"]),
+                             retrieved["label"][:, :K].reshape(-1).to(self.dev, torch.int64).contiguous(),
+                             self.w[f + ".fc_bbox.w"], self.w[f + ".fc_bbox.b"], self.w[f + ".emb_label"])
+        T = E + 1
+        x = torch.empty((N * T, D), dtype=torch.float32, device=self.dev)
+        xs = torch.empty((2, N * T, D), dtype=torch.bfloat16, device=self.dev)
+        # CLS token rows (TransformerWithToken, fid/model.py:42-43) then relu(enc_fc_in(...)) rows
+        ops.rows_affine(None, N, D, table=self.w[f + ".token"], tab_mod=1, rows_per_group=1, group_stride=T,
+                        group_offset=0, out_f32=x, out_split=xs)
+        self._gemm(rows, f + ".enc_fc_in", act="relu", out_f32=x, out_split=xs, rows_per_group=E, group_stride=T,
+                   group_offset=1)
+        pad = torch.zeros((N, T), dtype=torch.uint8, device=self.dev)
+        pad[:, 1:] = (~retrieved["mask"][:, :K].reshape(N, E).to(self.dev).bool()).to(torch.uint8)
+        for i in range(4):
+            x, xs = self._postnorm_layer(x, xs, f"{f}.enc_transformer.core.layers.{i}", N, T, pad, 4)
+        # layout_adapter FeedForward on the CLS rows (row stride T*256), then x16 + PE1d[k]
+        _, h = self._ln(x, "layout_adapter.net.0", rows=N, in_ld=T * D)
+        _, g = self._gemm(h, "layout_adapter.net.1", act="gelu", want_f32=False, want_split=True)
+        return self._gemm(g, "layout_adapter.net.4", res=self.w["pe1d"], res_row_mod=K, want_split=True)
+
+    # ------------------------------------------------------------------------------------------
+    # constraint encoder (common/common.py:238-252)
+    # ------------------------------------------------------------------------------------------
+    def constraint_encoder(self, seq_const: torch.Tensor, pad_mask: torch.Tensor, mem, mem_s, Mlen: int, off: int):
+        B, T = seq_const.shape
+        x = ops.embed(seq_const.to(self.dev).contiguous(), 0, T, self.w["user_const_encoder.emb"], math.sqrt(D),
+                      self.w["pe1d"], 0)
+        m = pad_mask.to(self.dev).to(torch.uint8).contiguous()
+        for i in range(NLAYER):
+            last = i == NLAYER - 1
+            x, _ = self._prenorm_layer(x, f"user_const_encoder.encoder.layers.{i}", B, T, mask=m,
+                                       out=(mem, mem_s) if last else None, out_map=(T, Mlen, off) if last else None)
+
+    # ------------------------------------------------------------------------------------------
+    # memory (retrieval_augmented_autoreg.py:963-994,1004-1033 / autoreg.py:590-622)
+    # ------------------------------------------------------------------------------------------
+    def encode(self, image: torch.Tensor, retrieved: Optional[dict], seq_const: torch.Tensor,
+               seq_const_pad: torch.Tensor):
+        """-> (memory fp32 [B, M, 256], split copy [2, B*M, 256])."""
+        B = image.shape[0]
+        Tc = seq_const.shape[1]
+        x_img, T = self.encode_image(image.to(self.dev, torch.float32))
+        if self.is_ralf:
+            K = self.top_k
+            Tcat = 2 * T + K
+            Mlen = Tcat + Tc
+            ref, ref_s = self.retrieved_features(retrieved, B)
+            cat = torch.empty((B * Tcat, D), dtype=torch.float32, device=self.dev)
+            ops.rows_affine(x_img, B * T, D, rows_per_group=T, group_stride=Tcat, group_offset=0, out_f32=cat)
+            ops.rows_affine(ref, B * K, D, rows_per_group=K, group_stride=Tcat, group_offset=2 * T, out_f32=cat)
+            # fusion Attention (common/attention.py:49-71): LN on x only, 8 heads x 64, no residual
+            _, h = self._ln(x_img, "attn.norm")
+            q, _ = self._gemm(h, "attn.to_q")
+            kv, _ = self._gemm(ref_s, "attn.to_kv")
+            a = ops.attention(q, kv[:, :512], kv[:, 512:], B, 8, T, K, 64)
+            self._gemm(a, "attn.to_out.0", out_f32=cat, rows_per_group=T, group_stride=Tcat, group_offset=T)
+            # head FeedForward over the concatenation, written straight into memory rows [0, Tcat)
+            mem = torch.empty((B * Mlen, D), dtype=torch.float32, device=self.dev)
+            mem_s = torch.empty((2, B * Mlen, D), dtype=torch.bfloat16, device=self.dev)
+            _, h = self._ln(cat, "head.net.0")
+            _, g = self._gemm(h, "head.net.1", act="gelu", want_f32=False, want_split=True)
+            self._gemm(g, "head.net.4", out_f32=mem, out_split=mem_s, rows_per_group=Tcat, group_stride=Mlen,
+                       group_offset=0)
+            off = Tcat
+        else:
+            Mlen = T + Tc
+            mem = torch.empty((B * Mlen, D), dtype=torch.float32, device=self.dev)
+            mem_s = torch.empty((2, B * Mlen, D), dtype=torch.bfloat16, device=self.dev)
+            ops.rows_affine(x_img, B * T, D, add=self.t_img, rows_per_group=T, group_stride=Mlen, group_offset=0,
+                            out_f32=mem, out_split=mem_s)
+            off = T
+        self.constraint_encoder(seq_const, seq_const_pad, mem, mem_s, Mlen, off)
+        return mem.view(B, Mlen, D), mem_s
+
+    # ------------------------------------------------------------------------------------------
+    # decoder
+    # ------------------------------------------------------------------------------------------
+    def cross_kv(self, mem_s: torch.Tensor) -> torch.Tensor:
+        """K/V of the memory for all 6 decoder layers in one GEMM: fp32 [B*M, 6*512]."""
+        return self._gemm(mem_s, "decoder.ckv")[0]
+
+    def decoder_logits(self, seq: torch.Tensor, pad_mask: torch.Tensor, mem_s: torch.Tensor, B: int, Mlen: int):
+        """Teacher-forced BaseDecoder.forward (common/common.py:84-135), causal + key padding masks."""
+        S = seq.shape[1]
+        kvm = self.cross_kv(mem_s)
+        x = ops.embed(seq.to(self.dev).contiguous(), 0, S, self.w["decoder.emb"], math.sqrt(D), self.w["pe1d"], 0)
+        m = pad_mask.to(self.dev).to(torch.uint8).contiguous()
+        for i in range(NLAYER):
+            p = f"decoder.transformer.layers.{i}"
+            _, h = self._ln(x, p + ".norm1")
+            qkv, _ = self._gemm(h, p + ".qkv")
+            a = ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B, NHEAD, S, S, 32, mask=m, causal=True)
+            x, _ = self._gemm(a, p + ".o", res=x)
+            _, h = self._ln(x, p + ".norm2")
+            q, _ = self._gemm(h, p + ".cq")
+            a = ops.attention(q, kvm[:, i * 512:i * 512 + D], kvm[:, i * 512 + D:(i + 1) * 512], B, NHEAD, S, Mlen, 32)
+            x, _ = self._gemm(a, p + ".co", res=x)
+            _, h = self._ln(x, p + ".norm3")
+            _, f = self._gemm(h, p + ".linear1", act="relu", want_f32=False, want_split=True)
+            x, _ = self._gemm(f, p + ".linear2", res=x)
+        _, h = self._ln(x, "decoder.head.0")
+        logits, _ = self._gemm(h, "decoder.head.1")
+        return logits.view(B, S, self.vocab)
+
+    def generate(self, mem_s: torch.Tensor, B: int, Mlen: int, token_mask: torch.Tensor, bos_id: int, pad_id: int,
+                 steps: int, return_logits: bool = False):
+        """Greedy decode (retrieval_augmented_autoreg.py:244-300, cond_type uncond) with KV caches.
+        token_mask: uint8 [steps, V] (tokenizer.token_mask).  Returns seq int64 [B, steps] (BOS dropped)."""
+        dev = self.dev
+        kvm = self.cross_kv(mem_s)
+        seq = torch.full((B, steps + 1), pad_id, dtype=torch.int64, device=dev)
+        seq[:, 0] = bos_id
+        pad_mask = torch.zeros((B, steps + 1), dtype=torch.uint8, device=dev)
+        kc = [torch.empty((B, steps, D), dtype=torch.float32, device=dev) for _ in range(NLAYER)]
+        vc = [torch.empty((B, steps, D), dtype=torch.float32, device=dev) for _ in range(NLAYER)]
+        x = ops.embed(seq, 0, 1, self.w["decoder.emb"], math.sqrt(D), self.w["pe1d"], 0)
+        tm = token_mask.to(dev).to(torch.uint8).contiguous()
+        all_logits = []
+        for t in range(steps):
+            for i in range(NLAYER):
+                p = f"decoder.transformer.layers.{i}"
+                _, h = self._ln(x, p + ".norm1")
+                qkv, _ = self._gemm(h, p + ".qkv")
+                ops.kv_append(qkv, kc[i], vc[i], t)
+                a = ops.attention_decode(qkv, kc[i].view(B * steps, D), vc[i].view(B * steps, D), steps, t + 1, B,
+                                         NHEAD, 32, mask=pad_mask)
+                self._gemm(a, p + ".o", res=x, out_f32=x)
+                _, h = self._ln(x, p + ".norm2")
+                q, _ = self._gemm(h, p + ".cq")
+                a = ops.attention_decode(q, kvm[:, i * 512:i * 512 + D], kvm[:, i * 512 + D:(i + 1) * 512], Mlen,
+                                         Mlen, B, NHEAD, 32)
+                self._gemm(a, p + ".co", res=x, out_f32=x)
+                _, h = self._ln(x, p + ".norm3")
+                _, f = self._gemm(h, p + ".linear1", act="relu", want_f32=False, want_split=True)
+                self._gemm(f, p + ".linear2", res=x, out_f32=x)
+            _, h = self._ln(x, "decoder.head.0")
+            logits, _ = self._gemm(h, "decoder.head.1")
+            if return_logits:
+                all_logits.append(logits)
+            ops.argmax_next(logits, tm[t], seq, t + 1, pad_mask, pad_id, self.w["decoder.emb"], math.sqrt(D),
+                            self.w["pe1d"], x)
+        out = seq[:, 1:]
+        return (out, torch.stack(all_logits, 1)) if return_logits else out

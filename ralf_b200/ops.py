@@ -142,3 +142,127 @@ def knn_merge(part_score: torch.Tensor, part_idx: torch.Tensor) -> tuple[torch.T
     check(_lib.lib().ralf_knn_merge(part_score.data_ptr(), part_idx.data_ptr(), parts, q, k, idx.data_ptr(),
                                     score.data_ptr(), _stream()), "ralf_knn_merge")
     return idx, score
+
+
+# --------------------------------------------------------------------------------------------------
+# non-GEMM kernels (csrc/nn_kernels.cu)
+# --------------------------------------------------------------------------------------------------
+def _split_out(M: int, D: int, device) -> torch.Tensor:
+    return torch.empty((2, M, D), dtype=torch.bfloat16, device=device)
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, rows: Optional[int] = None,
+              in_ld: Optional[int] = None, want_f32: bool = False, want_split: bool = True, eps: float = 1e-5):
+    """Rows of x (fp32, last dim D, row stride in_ld) -> (fp32 [M,D] | None, split [2,M,D] | None)."""
+    D = x.shape[-1]
+    M = rows if rows is not None else x.numel() // D
+    ld = in_ld if in_ld is not None else D
+    of = torch.empty((M, D), dtype=torch.float32, device=x.device) if want_f32 else None
+    os_ = _split_out(M, D, x.device) if want_split else None
+    check(_lib.lib().ralf_layernorm(x.data_ptr(), ld, gamma.data_ptr(), beta.data_ptr(), eps, M, D, _ptr(of),
+                                    _ptr(os_), os_.stride(0) if os_ is not None else 0, _stream()), "ralf_layernorm")
+    return of, os_
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, H: int, Tq: int, Tk: int, dh: int, *,
+              mask: Optional[torch.Tensor] = None, causal: bool = False, scale: Optional[float] = None):
+    """q [B*Tq, >=H*dh] / k, v [B*Tk, >=H*dh] fp32 views (row stride = stride(0)); returns split [2, B*Tq, H*dh]."""
+    out = _split_out(B * Tq, H * dh, q.device)
+    assert k.stride(0) == v.stride(0)
+    sc = scale if scale is not None else dh ** -0.5
+    check(_lib.lib().ralf_attention(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), _ptr(mask),
+                                    B, H, Tq, Tk, dh, int(causal), sc, out.data_ptr(), out.stride(0), None, H * dh,
+                                    _stream()), "ralf_attention")
+    return out
+
+
+def attention_decode(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, kv_bstride: int, Tk: int, B: int, H: int,
+                     dh: int, *, mask: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
+    """One query per (b, h) against cached K/V rows (b*kv_bstride + j); returns split [2, B, H*dh]."""
+    if out is None:
+        out = _split_out(B, H * dh, q.device)
+    check(_lib.lib().ralf_attention_decode(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), kv_bstride,
+                                           k.stride(0), _ptr(mask), mask.stride(0) if mask is not None else 0, Tk, B,
+                                           H, dh, dh ** -0.5, out.data_ptr(), out.stride(0), H * dh, _stream()),
+          "ralf_attention_decode")
+    return out
+
+
+def stem_im2col(img: torch.Tensor, KP: int = 200):
+    B, C, H, W = img.shape
+    assert C == 4 and img.is_contiguous() and img.dtype == torch.float32
+    Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+    out = _split_out(B * Ho * Wo, KP, img.device)
+    check(_lib.lib().ralf_stem_im2col(img.data_ptr(), B, H, W, KP, out.data_ptr(), out.stride(0), _stream()),
+          "ralf_stem_im2col")
+    return out, Ho, Wo
+
+
+def im2col(x: torch.Tensor, B: int, H: int, W: int, C: int, KH: int, KW: int, stride: int, pad: int):
+    """x split [2, B*H*W, C] (NHWC) -> split [2, B*Ho*Wo, KH*KW*C]."""
+    Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    out = _split_out(B * Ho * Wo, KH * KW * C, x.device)
+    check(_lib.lib().ralf_im2col(x.data_ptr(), x.stride(0), B, H, W, C, KH, KW, stride, pad, out.data_ptr(),
+                                 out.stride(0), _stream()), "ralf_im2col")
+    return out, Ho, Wo
+
+
+def maxpool3x3s2(x: torch.Tensor, B: int, H: int, W: int, C: int):
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    out = _split_out(B * Ho * Wo, C, x.device)
+    check(_lib.lib().ralf_maxpool3x3s2(x.data_ptr(), x.stride(0), B, H, W, C, out.data_ptr(), out.stride(0),
+                                       _stream()), "ralf_maxpool3x3s2")
+    return out, Ho, Wo
+
+
+def fpn_merge(c5: torch.Tensor, c4: torch.Tensor, B: int, h5: int, w5: int, h4: int, w4: int, C: int):
+    fused = _split_out(B * h4 * w4, 2 * C, c5.device)
+    summ = _split_out(B * h4 * w4, C, c5.device)
+    check(_lib.lib().ralf_fpn_merge(c5.data_ptr(), c4.data_ptr(), B, h5, w5, h4, w4, C, fused.data_ptr(),
+                                    fused.stride(0), 2 * C, summ.data_ptr(), summ.stride(0), _stream()),
+          "ralf_fpn_merge")
+    return fused, summ
+
+
+def rows_affine(inp: Optional[torch.Tensor], M: int, D: int, *, in_ld: Optional[int] = None, scale: float = 1.0,
+                add: float = 0.0, table: Optional[torch.Tensor] = None, tab_mod: int = 0, rows_per_group: int = 0,
+                group_stride: int = 0, group_offset: int = 0, out_f32: Optional[torch.Tensor] = None,
+                out_split: Optional[torch.Tensor] = None, out_ld: Optional[int] = None):
+    ld = in_ld if in_ld is not None else D
+    old = out_ld if out_ld is not None else D
+    check(_lib.lib().ralf_rows_affine(_ptr(inp), ld, M, D, scale, add, _ptr(table), tab_mod, rows_per_group,
+                                      group_stride, group_offset, _ptr(out_f32), _ptr(out_split),
+                                      out_split.stride(0) if out_split is not None else 0, old, _stream()),
+          "ralf_rows_affine")
+
+
+def embed(tok: torch.Tensor, tok_col: int, S: int, emb: torch.Tensor, scale: float, pe: torch.Tensor, pos0: int = 0):
+    """tok int64 [B, >=tok_col+S] -> fp32 [B*S, D] = emb[tok]*scale + pe[pos0+s]."""
+    B, D = tok.shape[0], emb.shape[1]
+    out = torch.empty((B * S, D), dtype=torch.float32, device=emb.device)
+    check(_lib.lib().ralf_embed(tok.data_ptr(), tok.stride(0), tok_col, B, S, emb.data_ptr(), D, scale, pe.data_ptr(),
+                                pos0, out.data_ptr(), _stream()), "ralf_embed")
+    return out
+
+
+def fid_embed(cx, cy, w, h, label, fc_w, fc_b, emb):
+    rows, D = cx.numel(), emb.shape[1]
+    out = _split_out(rows, 2 * D, emb.device)
+    check(_lib.lib().ralf_fid_embed(cx.data_ptr(), cy.data_ptr(), w.data_ptr(), h.data_ptr(), label.data_ptr(), rows,
+                                    D, fc_w.data_ptr(), fc_b.data_ptr(), emb.data_ptr(), out.data_ptr(),
+                                    out.stride(0), _stream()), "ralf_fid_embed")
+    return out
+
+
+def argmax_next(logits, allowed, seq, pos, pad_mask, pad_id, emb, scale, pe, x_next):
+    B, V = logits.shape
+    check(_lib.lib().ralf_argmax_next(logits.data_ptr(), logits.stride(0), B, V, allowed.data_ptr(), seq.data_ptr(),
+                                      seq.stride(0), pos, _ptr(pad_mask), pad_mask.stride(0) if pad_mask is not None else 0,
+                                      pad_id, _ptr(emb), emb.shape[1] if emb is not None else 0, scale, _ptr(pe),
+                                      _ptr(x_next), _stream()), "ralf_argmax_next")
+
+
+def kv_append(qkv, kcache, vcache, pos):
+    B, D = qkv.shape[0], qkv.shape[1] // 3
+    check(_lib.lib().ralf_kv_append(qkv.data_ptr(), B, D, kcache.data_ptr(), vcache.data_ptr(), kcache.shape[1], pos,
+                                    _stream()), "ralf_kv_append")

@@ -1,0 +1,103 @@
+"""GPU parity of the engine (ralf_b200/engine.py -> C ABI -> sm_100a kernels) against (a) the reference's own
+outputs in tests/golden/*.npz and (b) the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): token ids bit-exact; logits within 1e-3 relative.  "Relative" is measured
+against the logit scale max|logits| (element-wise relative error is ill-defined near zero --
+two fp32 PyTorch paths already differ by 4.8e-2 element-wise)."""
+import numpy as np
+import pytest
+import torch
+
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("ralf_cgl_256", "ralf_cgl", True), ("ralf_cgl_350x240", "ralf_cgl", True),
+         ("autoreg_cgl_350x240", "autoreg_cgl", False)]
+LOGIT_RTOL = 1e-3
+
+
+def _relerr(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+def _engine(schema, seed, is_ralf, dev):
+    from ralf_b200.engine import Engine
+
+    return Engine(helpers.synth_weights(schema, seed), dev, is_ralf=is_ralf)
+
+
+def test_resnet_fpn_matches_oracle(cuda_device):
+    from oracle import ralf_oracle as O
+
+    z, meta = helpers.load_golden("ralf_cgl_256")
+    sd = helpers.synth_weights("ralf_cgl", meta["seed"])
+    eng = _engine("ralf_cgl", meta["seed"], True, cuda_device)
+    img = helpers.image4(helpers.synth_batch(meta))
+    with torch.no_grad():
+        f = O.resnet_fpn(sd, img)
+        ref = f.flatten(2).transpose(1, 2) + O.pos_emb_2d(f.shape[2], f.shape[3], 256)[None]
+    tokens, h, w = eng.resnet_fpn(img.to(cuda_device))
+    assert (h, w) == tuple(f.shape[2:])
+    err = _relerr(tokens.view(ref.shape).cpu().numpy(), ref.numpy())
+    assert err < 1e-4, err
+
+
+@pytest.mark.parametrize("name,schema,is_ralf", CASES)
+def test_engine_matches_reference_golden(cuda_device, name, schema, is_ralf):
+    z, meta = helpers.load_golden(name)
+    eng = _engine(schema, meta["seed"], is_ralf, cuda_device)
+    batch = helpers.synth_batch(meta)
+    tok = helpers.make_tokenizer()
+    B = meta["B"]
+    mem, mem_s = eng.encode(helpers.image4(batch), batch.get("retrieved"), torch.from_numpy(z["seq_layout_const"]),
+                            torch.from_numpy(z["seq_layout_const_pad_mask"]))
+    assert tuple(mem.shape) == z["memory"].shape
+    e_mem = _relerr(mem.cpu().numpy(), z["memory"])
+    assert e_mem < LOGIT_RTOL, e_mem
+    Mlen = mem.shape[1]
+    logits = eng.decoder_logits(torch.from_numpy(z["seq_in"]), torch.from_numpy(z["tgt_key_padding_mask"]), mem_s, B, Mlen)
+    e_log = _relerr(logits.cpu().numpy(), z["logits"])
+    assert e_log < LOGIT_RTOL, e_log
+    sp = meta["special"]
+    seq, step_logits = eng.generate(mem_s, B, Mlen, tok.token_mask, sp["bos"], sp["pad"], tok.max_token_length,
+                                    return_logits=True)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(seq.cpu().numpy(), z["gen_seq"])  # bit-exact token ids
+    ref = z["gen_step_logits"]
+    fin = np.isfinite(ref)
+    e_step = _relerr(step_logits.cpu().numpy()[fin], ref[fin])
+    assert e_step < LOGIT_RTOL, e_step
+    print(f"{name}: memory {e_mem:.2e} logits {e_log:.2e} greedy-step logits {e_step:.2e}")
+
+
+def test_engine_batch_matches_oracle_with_margin(cuda_device):
+    """B=8 random canvases vs the CPU oracle: token ids equal; a divergence is tolerated only where the oracle's
+    own top-2 margin at that step is below the logit tolerance (first-divergence rule)."""
+    from oracle import ralf_oracle as O
+    from oracle import synth
+
+    sd = helpers.synth_weights("ralf_cgl", 7)
+    eng = _engine("ralf_cgl", 7, True, cuda_device)
+    tok = helpers.make_tokenizer()
+    batch = synth.synth_batch(8, 256, 256, 10, 16, 4, seed=123)
+    z, meta = helpers.load_golden("ralf_cgl_256")
+    sc = torch.from_numpy(z["seq_layout_const"])[:1].expand(8, -1).contiguous()
+    sp_ = torch.zeros_like(sc, dtype=torch.bool)
+    sp = meta["special"]
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        mem_o = O.encode_ralf_memory(sd, helpers.image4(batch), {k: v.float() for k, v in batch["retrieved"].items()}, sc, sp_)
+        seq_o, lg_o = O.greedy_sample(sd, mem_o, tok.token_mask, sp["bos"], sp["pad"], tok.max_token_length, return_logits=True)
+    mem, mem_s = eng.encode(helpers.image4(batch), batch["retrieved"], sc, sp_)
+    assert _relerr(mem.cpu().numpy(), mem_o.numpy()) < LOGIT_RTOL
+    seq = eng.generate(mem_s, 8, mem.shape[1], tok.token_mask, sp["bos"], sp["pad"], tok.max_token_length).cpu()
+    for b in range(8):
+        diff = (seq[b] != seq_o[b]).nonzero()
+        if len(diff) == 0:
+            continue
+        t = int(diff[0])
+        top2 = torch.topk(lg_o[b, t], 2).values
+        margin = float(top2[0] - top2[1]) / float(lg_o[b, t][torch.isfinite(lg_o[b, t])].abs().max())
+        assert margin < LOGIT_RTOL, f"canvas {b} diverges at step {t} with oracle margin {margin:.3e}"
