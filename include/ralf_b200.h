@@ -159,6 +159,10 @@ int ralf_fid_embed(const float* cx, const float* cy, const float* w, const float
 int ralf_argmax_next(const float* logits, int ldl, int B, int V, const unsigned char* allowed, long long* seq,
                      int seq_ld, int pos, unsigned char* pad_mask, int mask_ld, long long pad_id,
                      const float* emb, int D, float scale, const float* pe, float* x_next, void* stream);
+/* nn.CrossEntropyLoss(label_smoothing=eps, ignore_index) with mean reduction over logits [M, V]
+ * (retrieval_augmented_autoreg.py:140-142,213-214); workspace = 2*M floats; out_loss = 1 float. */
+int ralf_ce_label_smooth(const float* logits, int ldl, const long long* targets, int M, int V, float eps,
+                         long long ignore_index, float* workspace, float* out_loss, void* stream);
 /* Append this step's K,V (columns [D,3D) of the fused QKV row) to the self-attention cache [B,S,D]. */
 int ralf_kv_append(const float* qkv, int B, int D, float* kcache, float* vcache, int S, int pos, void* stream);
 

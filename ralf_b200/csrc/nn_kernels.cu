@@ -493,6 +493,53 @@ __global__ void kv_append_kernel(const float* __restrict__ qkv, int B, int D, fl
   vcache[(static_cast<long long>(b) * S + pos) * D + c] = qkv[static_cast<long long>(b) * 3 * D + 2 * D + c];
 }
 
+
+// Label-smoothed cross entropy (nn.CrossEntropyLoss(label_smoothing=eps, ignore_index=pad), mean over
+// non-ignored targets; retrieval_augmented_autoreg.py:140-142,213-214).  One warp per row:
+//   row_loss = (1-eps) * (lse - x[t]) + eps * (lse - mean_c x[c]);  rows with t == ignore contribute 0.
+__global__ void ce_rows_kernel(const float* __restrict__ logits, int ldl, const long long* __restrict__ tgt, int M, int V,
+                               float eps, long long ignore, float* __restrict__ row_loss, float* __restrict__ row_valid) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const float* x = logits + static_cast<long long>(row) * ldl;
+  float mx = -INFINITY;
+  for (int c = lane; c < V; c += 32) mx = fmaxf(mx, x[c]);
+  mx = warp_max(mx);
+  float se = 0.f, sx = 0.f;
+  for (int c = lane; c < V; c += 32) {
+    se += expf(x[c] - mx);
+    sx += x[c];
+  }
+  se = warp_sum(se);
+  sx = warp_sum(sx);
+  if (lane == 0) {
+    const long long t = tgt[row];
+    const float lse = mx + logf(se);
+    const bool ok = (t != ignore);
+    row_loss[row] = ok ? ((1.f - eps) * (lse - x[t]) + eps * (lse - sx / static_cast<float>(V))) : 0.f;
+    row_valid[row] = ok ? 1.f : 0.f;
+  }
+}
+// Deterministic final reduction: one block, fixed order.
+__global__ void ce_reduce_kernel(const float* __restrict__ row_loss, const float* __restrict__ row_valid, int M,
+                                 float* __restrict__ out) {
+  __shared__ float sl[32], sv[32];
+  float a = 0.f, b = 0.f;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) { a += row_loss[i]; b += row_valid[i]; }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if ((threadIdx.x & 31) == 0) { sl[threadIdx.x >> 5] = a; sv[threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    a = threadIdx.x < (blockDim.x >> 5) ? sl[threadIdx.x] : 0.f;
+    b = threadIdx.x < (blockDim.x >> 5) ? sv[threadIdx.x] : 0.f;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (threadIdx.x == 0) out[0] = a / b;
+  }
+}
+
 static inline int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = static_cast<long long>(num_sms()) * 16;
@@ -649,5 +696,16 @@ extern "C" int ralf_kv_append(const float* qkv, int B, int D, float* kcache, flo
   if (!qkv || !kcache || !vcache) return RALF_ERR_NULL;
   if (B <= 0 || D <= 0 || pos < 0 || pos >= S) return RALF_ERR_SHAPE;
   kv_append_kernel<<<(B * D + 255) / 256, 256, 0, ST(stream)>>>(qkv, B, D, kcache, vcache, S, pos);
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_ce_label_smooth(const float* logits, int ldl, const long long* targets, int M, int V, float eps,
+                                    long long ignore_index, float* workspace /* 2*M floats */, float* out_loss,
+                                    void* stream) {
+  if (!logits || !targets || !workspace || !out_loss) return RALF_ERR_NULL;
+  if (M <= 0 || V <= 0) return RALF_ERR_SHAPE;
+  ce_rows_kernel<<<(M + 7) / 8, 256, 0, ST(stream)>>>(logits, ldl, targets, M, V, eps, ignore_index, workspace,
+                                                     workspace + M);
+  ce_reduce_kernel<<<1, 256, 0, ST(stream)>>>(workspace, workspace + M, M, out_loss);
   return set_cuda_error(cudaGetLastError());
 }

@@ -266,3 +266,16 @@ def kv_append(qkv, kcache, vcache, pos):
     B, D = qkv.shape[0], qkv.shape[1] // 3
     check(_lib.lib().ralf_kv_append(qkv.data_ptr(), B, D, kcache.data_ptr(), vcache.data_ptr(), kcache.shape[1], pos,
                                     _stream()), "ralf_kv_append")
+
+
+def ce_label_smooth(logits: torch.Tensor, targets: torch.Tensor, eps: float, ignore_index: int) -> torch.Tensor:
+    """Mean label-smoothed CE over logits [..., V] / targets [...] (ralf_ce_label_smooth); 0-dim fp32 tensor."""
+    V = logits.shape[-1]
+    lg = logits.reshape(-1, V)
+    tg = targets.reshape(-1).to(torch.int64).contiguous()
+    M = lg.shape[0]
+    ws = torch.empty(2 * M, dtype=torch.float32, device=lg.device)
+    out = torch.empty(1, dtype=torch.float32, device=lg.device)
+    check(_lib.lib().ralf_ce_label_smooth(lg.data_ptr(), lg.stride(0), tg.data_ptr(), M, V, eps, ignore_index,
+                                          ws.data_ptr(), out.data_ptr(), _stream()), "ralf_ce_label_smooth")
+    return out[0]

@@ -1,0 +1,98 @@
+"""GPU retrieval: exact top-k inner-product search over an embedding gallery + exemplar-layout fetch.
+
+Host-side mirror of the reference's retrieval objects for the hot path:
+
+* ``Retriever`` (image2layout/train/models/retrieval/retriever.py:24-229) builds a FAISS
+  ``IndexFlat(d, METRIC_INNER_PRODUCT)`` over the training-split embeddings and, per query, searches
+  ``top_k + 1`` neighbours, drops the query itself on the train split and stores ``dict[id -> list[idx]]``
+  (``preprocess_retrieval_cache`` :134-229).  :class:`GpuRetriever.search` / :meth:`build_table` do the same
+  with the sm_100a kernel (csrc/knn.cu), batched over queries and optionally sharded over GPUs.
+* ``RetrievalDatasetWrapper.__getitem__`` + ``collate_fn`` (helpers/retrieval_dataset_wrapper.py:89-148,
+  data.py:78-88) turn the k indices into ``retrieved{label, mask, center_x, center_y, width, height: [B,K,E]}``.
+  :meth:`GpuRetriever.fetch` is an index gather from a GPU-resident packed layout table (exemplar images
+  are never read when ``use_reference_image=False``, retrieval_augmented_autoreg.py:74,542).
+
+Multi-GPU: the gallery and layout table are row-sharded; every rank searches its shard for ALL
+queries, the per-rank [Q,k] (score, global index) lists are all-gathered (NCCL) and merged with the same
+(score desc, index asc) rule -- the result is bit-identical to the unsharded search.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+
+LAYOUT_KEYS = ["label", "mask", "center_x", "center_y", "width", "height"]
+
+
+class GpuRetriever:
+    def __init__(self, embeddings: torch.Tensor, layouts: Optional[dict] = None, *, device=None, rank: int = 0,
+                 world_size: int = 1, index_base: Optional[int] = None, process_group=None) -> None:
+        """embeddings: this rank's shard [n_local, d] fp32 (the whole gallery when world_size == 1);
+        layouts: dict of [n_total, E] tensors (replicated: it is tiny next to the embeddings)."""
+        self.dev = torch.device(device) if device is not None else embeddings.device
+        self.emb = embeddings.to(self.dev, torch.float32).contiguous()
+        self.rank, self.world = rank, world_size
+        self.pg = process_group
+        self.index_base = index_base if index_base is not None else 0
+        # FAISS does not normalise; the TF32 certificate only needs an upper bound on the row norms
+        self.max_norm = float(self.emb.norm(dim=1).max().item()) * 1.0001 if self.emb.numel() else 0.0
+        self.layouts = None
+        if layouts is not None:
+            self.layouts = {k: layouts[k].to(self.dev).contiguous() for k in LAYOUT_KEYS}
+        self._ws: Optional[torch.Tensor] = None
+
+    # -- search ---------------------------------------------------------------------------------
+    def search_local(self, queries: torch.Tensor, k: int):
+        """Top-k of this rank's shard for every query: (idx int64 [Q,k] global ids, score fp32 [Q,k])."""
+        q = queries.to(self.dev, torch.float32).contiguous()
+        idx, score, cert = ops.knn_topk(self.emb, q, k, index_base=self.index_base, gallery_max_norm=self.max_norm,
+                                        workspace=self._ws)
+        self.last_certified = cert
+        return idx, score
+
+    def search(self, queries: torch.Tensor, k: int, *, certify: bool = False):
+        """Global top-k.  With ``certify`` uncertified queries (TF32 bound inconclusive: near-duplicate
+        clusters wider than the candidate list) are re-run through the exact CUDA-core kernel."""
+        idx, score = self.search_local(queries, k)
+        if certify:
+            bad = (self.last_certified == 0).nonzero().flatten()
+            if bad.numel():  # host sync only on this opt-in path
+                q = queries.to(self.dev, torch.float32)[bad].contiguous()
+                ei, es, _ = ops.knn_topk(self.emb, q, k, index_base=self.index_base, exact=True)
+                idx[bad], score[bad] = ei, es
+        if self.world > 1:
+            import torch.distributed as dist
+
+            all_s = torch.empty((self.world, *score.shape), dtype=score.dtype, device=self.dev)
+            all_i = torch.empty((self.world, *idx.shape), dtype=idx.dtype, device=self.dev)
+            dist.all_gather_into_tensor(all_s, score, group=self.pg)
+            dist.all_gather_into_tensor(all_i, idx, group=self.pg)
+            idx, score = ops.knn_merge(all_s, all_i)
+        return idx, score
+
+    # -- exemplar fetch -------------------------------------------------------------------------
+    def fetch(self, idx: torch.Tensor) -> dict:
+        """indices [B, K] -> retrieved{key: [B, K, E]} gathered from the resident layout table."""
+        assert self.layouts is not None, "no layout table attached"
+        flat = idx.reshape(-1).clamp_min(0)
+        out = {k: v.index_select(0, flat).view(*idx.shape, -1) for k, v in self.layouts.items()}
+        return out
+
+    # -- reference cache-table format -----------------------------------------------------------
+    def build_table(self, queries: torch.Tensor, query_ids: list, db_ids: list, k: int, drop_self: bool) -> dict:
+        """``dict[data_id -> list[db_index]]`` like preprocess_retrieval_cache (retriever.py:193-221):
+        search k+1, and on the train split drop the first hit (the query itself)."""
+        idx, _ = self.search(queries, k + 1)
+        idx = idx.cpu().tolist()
+        table = {}
+        for qid, row in zip(query_ids, idx):
+            row = row[1:] if drop_self else row[:k]
+            table[qid] = row
+        return table
+
+
+def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
+    return (n * rank) // world, (n * (rank + 1)) // world
