@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- layouts/sec (retrieve + encode + decode) of the RALF hot path on N B200s.
+
+One "step" = one batch of synthetic canvases through the whole path, per GPU:
+  top-16 inner-product search of the batch's 512-d query embeddings over the (row-sharded) gallery
+  -> gather the 16 exemplar layouts from the GPU-resident layout table -> ResNet50-FPN + 6-layer encoder
+  + FIDNet/fusion/head + constraint encoder -> memory -> KV-cached greedy decode of S tokens (token ids on device).
+
+Workload (BASELINE.json configs[4] shape, quoted per GPU so scaling is weak): 128 canvases/GPU, 256x256x4
+synthetic canvases, k = 16, gallery 1M x 512 fp32 sharded over the ranks, E = 12 elements -> S = 60 tokens (<= 64).
+Random-init weights of the reference architecture (no checkpoints offline), synthetic data.
+
+Contract: `python bench.py --gpus N --steps K --warmup W` (torchrun for N > 1) prints ONE JSON line on rank 0.
+`--impl reference` times the CPU restatement of the reference path (oracle/, kind "port") on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# ---- algorithmic cost model -------------------------------------------------------------
+GF_ENCODE_256 = 15.44e9   # FLOPs per canvas: ResNet50+FPN 11.35, image encoder 2.82, retrieved/fusion/head/constraint 1.27
+GF_DECODE_PER_TOKEN = 14.8e6
+GF_MEMKV = lambda M: 6 * M * 2 * 256 * 256 * 2.0  # cross-attention K/V projection of the memory, 6 layers
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=128, help="canvases per GPU per step")
+    ap.add_argument("--gallery", type=int, default=1_000_000, help="total gallery rows (sharded over ranks)")
+    ap.add_argument("--hw", type=int, default=256)
+    ap.add_argument("--elems", type=int, default=12)
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.stop_flag = [], False
+        self.index = index
+        self.th = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def start(self):
+        self.th.start()
+
+    def stop(self):
+        self.stop_flag = True
+        self.th.join(timeout=6)
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = max((int(r[1]) for r in self.rows if r[1].isdigit()), default=None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+def synth_world(args, rank, world, dev):
+    """Seeded synthetic gallery shard, layout table, weights, and per-step inputs."""
+    from oracle import synth  # data generator only (shared with the tests); no oracle arithmetic
+    from ralf_b200.retrieval import GpuRetriever, shard_bounds
+    from ralf_b200.tokenizer import LayoutSequenceTokenizer
+    from tests import helpers
+
+    E, K = args.elems, 16
+    lo, hi = shard_bounds(args.gallery, world, rank)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    emb = torch.randn(hi - lo, 512, device=dev, generator=g)
+    emb = emb / emb.norm(dim=1, keepdim=True)
+    gl = torch.Generator().manual_seed(99)
+    n = args.gallery
+    cnt = torch.randint(1, E + 1, (n,), generator=gl)
+    mask = torch.arange(E)[None] < cnt[:, None]
+    lay = {"mask": mask, "label": torch.randint(0, 4, (n, E), generator=gl) * mask}
+    for k in ["center_x", "center_y", "width", "height"]:
+        lay[k] = torch.rand(n, E, generator=gl) * mask
+    retr = GpuRetriever(emb, lay, device=dev, rank=rank, world_size=world, index_base=lo)
+    tok = LayoutSequenceTokenizer(["logo", "text", "underlay", "embellishment"], E)
+    schema = helpers.load_schema("ralf_cgl")
+    sd = synth.synth_state_dict(schema, seed=0)
+    return retr, tok, sd
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    from ralf_b200 import generator as G
+    from ralf_b200 import ops
+
+    retr, tok, sd = synth_world(args, rank, world, dev)
+    model = G.RALF(features=None, tokenizer=tok, dataset_name="cgl", max_seq_length=args.elems, db_dataset=None,
+                   retrieval_backbone="dreamsim", top_k=16, saliency_k="None", auxilary_task="uncond",
+                   precision=args.precision)
+    model.load_state_dict(sd, strict=True)
+    model.eval().to(dev)
+    eng = model.engine()
+    B, HW = args.batch, args.hw
+    S = tok.max_token_length
+    ids = model.special_token_ids
+    gq = torch.Generator().manual_seed(7 + rank)
+    # host (pinned) inputs for the end-to-end leg; device-resident copies for the kernel-only leg
+    img_h = torch.rand(B, 4, HW, HW, generator=gq).pin_memory()
+    qry_h = torch.nn.functional.normalize(torch.randn(B, 512, generator=gq), dim=1).pin_memory()
+    img_d, qry_d = img_h.to(dev), qry_h.to(dev)
+    const = model.preprocessor(G.ConditionalInputs(image=img_d))
+    tm = tok.token_mask.to(dev).to(torch.uint8)
+    l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    knn_ev = []
+
+    def step_device(record=False):
+        """inputs already resident in HBM; result (token ids) stays on the device."""
+        q_all = qry_d
+        if world > 1:
+            import torch.distributed as dist
+
+            q_all = torch.empty(world * B, 512, device=dev)
+            dist.all_gather_into_tensor(q_all, qry_d)
+        if record:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        idx, _ = retr.search_local(q_all, 16)
+        if record:
+            e1.record()
+            knn_ev.append((e0, e1))
+        if world > 1:
+            idx, _ = retr.search(q_all, 16)  # includes all-gather + merge (search_local above is timed alone)
+            idx = idx[rank * B:(rank + 1) * B]
+        retrieved = retr.fetch(idx)
+        mem, mem_s = eng.encode(img_d, retrieved, const["seq"], const["pad_mask"])
+        return eng.generate(mem_s, B, mem.shape[1], tm, ids["bos"], ids["pad"], S)
+
+    def step_e2e():
+        """public API with HOST buffers: H2D of the step's inputs and D2H of the result inside the region."""
+        img = img_h.to(dev, non_blocking=True)
+        q = qry_h.to(dev, non_blocking=True)
+        q_all = q
+        if world > 1:
+            import torch.distributed as dist
+
+            q_all = torch.empty(world * B, 512, device=dev)
+            dist.all_gather_into_tensor(q_all, q)
+        idx, _ = retr.search(q_all, 16)
+        if world > 1:
+            idx = idx[rank * B:(rank + 1) * B]
+        cond = G.ConditionalInputs(image=img, retrieved=retr.fetch(idx))
+        out = model.sample(cond=cond, cond_type="uncond", return_seq=True)  # decodes to boxes on the host (D2H inside)
+        return out["seq"]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, record=False):
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(steps):
+            l2_flush.zero_()  # flush L2 between iterations (the 2 GB gallery alone is >> L2 as well)
+            fn(record) if record is not None else fn()
+        t1.record()
+        barrier()
+        ms = t0.elapsed_time(t1)
+        if world > 1:
+            import torch.distributed as dist
+
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(args.warmup):
+        step_device()
+    launches0 = ops.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(step_device, args.steps, record=True)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ops.launch_count() - launches0
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    ms_e2e = timed(lambda: step_e2e(), args.steps, record=None)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        knn_ms = sum(a.elapsed_time(b) for a, b in knn_ev) / max(1, len(knn_ev))
+        n_local = retr.emb.shape[0]
+        q_tot = world * B
+        knn_bytes = n_local * 512 * 4 + q_tot * 512 * 4 + q_tot * 16 * 12
+        M = 2 * (HW // 16) ** 2 + 16 + 4
+        flops_layout = GF_ENCODE_256 * (HW / 256.0) ** 2 + GF_MEMKV(M) + S * GF_DECODE_PER_TOKEN
+        step_ms = ms / args.steps
+        value = world * B / (step_ms / 1e3)
+        line = {
+            "metric": "layouts/sec (retrieve+encode+decode)", "value": round(value, 2), "unit": "layouts/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(step_ms, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3 (split-bf16 tensor-core products, fp32 accumulate)" if args.precision == "bf16x3" else "bf16",
+            "data": "synthetic",
+            "config": {"workload": "BASELINE configs[4] per-GPU shard: batched inference, RALF CGL k=16, greedy decode",
+                       "canvases_per_gpu": B, "canvas": f"{HW}x{HW}x4", "gallery_rows_total": args.gallery,
+                       "gallery_dim": 512, "top_k": 16, "max_elements": args.elems, "decode_tokens": S,
+                       "memory_len": M, "weights": "random-init reference architecture (seeded)",
+                       "l2": "flushed between iterations (256 MiB write); gallery shard >> L2",
+                       "parallelism": f"dp{world} canvases, gallery row-sharded, all-gather merge" if world > 1 else "single GPU"},
+            "e2e": {"value": round(world * B / (ms_e2e / args.steps / 1e3), 2), "unit": "layouts/s",
+                    "h2d_bytes_per_step": int(img_h.numel() * 4 + qry_h.numel() * 4), "d2h_bytes_per_step": int(B * S * 8),
+                    "ms_per_step": round(ms_e2e / args.steps, 3)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "knn_scan_kernel<32> (TF32 tcgen05 gallery scan + fused top-C filter)", "bound": "hbm",
+                         "achieved": round(knn_bytes / (knn_ms / 1e3) / 1e9, 1), "peak": hbm_peak, "unit": "GB/s",
+                         "frac": round(knn_bytes / (knn_ms / 1e3) / 1e9 / hbm_peak, 4), "traffic": None,
+                         "algorithmic_bytes_per_launch": int(knn_bytes), "ms_per_launch": round(knn_ms, 4),
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
+            "model_flops": {"algorithmic_gflop_per_layout": round(flops_layout / 1e9, 2),
+                            "achieved_tflops": round(flops_layout * value / 1e12 / world, 2),
+                            "bf16_peak_tflops": peaks.get("bf16_tflops_sustained"),
+                            "note": "per-GPU algorithmic FLOP rate of the whole step (SURVEY.md 8d), x3 tensor passes in bf16x3"},
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, budget_canvases: int = 2):
+    """The reference algorithm's CPU restatement (oracle/, kind "port") on the host cores, bounded sample:
+    `budget_canvases` canvases through retrieve (numpy fp32 G@q + top-k over a 100k-row slice, scaled) ->
+    encode -> greedy decode WITHOUT KV cache (as the reference does)."""
+    import numpy as np
+
+    from oracle import ralf_oracle as O
+    from oracle import synth
+    from tests import helpers
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    E = args.elems
+    tok = helpers.make_tokenizer(max_seq_length=E)
+    sd = synth.synth_state_dict(helpers.load_schema("ralf_cgl"), seed=0)
+    b = synth.synth_batch(budget_canvases, args.hw, args.hw, E, 16, 4, seed=1)
+    sc = torch.tensor([[517, 525, 519, 518]]).expand(budget_canvases, -1).contiguous()
+    sp = torch.zeros_like(sc, dtype=torch.bool)
+    rows = min(args.gallery, 100_000)
+    rng = np.random.default_rng(0)
+    Gm = rng.standard_normal((rows, 512)).astype(np.float32)
+    Qm = rng.standard_normal((budget_canvases, 512)).astype(np.float32)
+    t0 = time.time()
+    s = Gm @ Qm.T
+    np.argpartition(-s, 16, axis=0)
+    t_knn = (time.time() - t0) * (args.gallery / rows)
+    t0 = time.time()
+    with torch.no_grad():
+        img = torch.cat([b["image"], b["saliency"]], 1)
+        mem = O.encode_ralf_memory(sd, img, {k: v.float() for k, v in b["retrieved"].items()}, sc, sp)
+        O.greedy_sample(sd, mem, tok.token_mask, 517, 516, tok.max_token_length)
+    t_model = time.time() - t0
+    total = t_knn + t_model
+    return {"value": round(budget_canvases / total, 3), "unit": "layouts/s", "cores": cores, "kind": "port",
+            "sample": f"{budget_canvases} canvases {args.hw}x{args.hw}: k-NN over {rows} rows scaled to {args.gallery} "
+                      f"({t_knn:.2f}s) + oracle encode + no-KV-cache greedy decode of {tok.max_token_length} tokens ({t_model:.2f}s)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    vals = []
+    for i in range(args.warmup + args.steps):
+        cb = cpu_baseline(args, budget_canvases=2)
+        if i >= args.warmup:
+            vals.append(cb)
+    v = sum(c["value"] for c in vals) / len(vals)
+    cb = vals[-1]
+    cb["value"] = round(v, 3)
+    line = {"impl": "reference", "metric": "layouts/sec (retrieve+encode+decode)", "value": round(v, 3),
+            "unit": "layouts/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(2 / v * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "same path on the host CPU: oracle port of the reference (no KV cache), 2 canvases per step",
+                       "canvas": f"{args.hw}x{args.hw}x4", "gallery_rows_total": args.gallery, "top_k": 16,
+                       "max_elements": args.elems},
+            "cpu_baseline": cb,
+            "e2e": {"value": round(v, 3), "unit": "layouts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

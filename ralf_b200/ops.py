@@ -7,9 +7,23 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import GemmArgs, check
+from ._lib import GemmArgs
 
 ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2}
+
+# Number of OUR kernels launched through the C ABI (bench.py reports the delta over the timed region).
+_LAUNCHES = 0
+_KERNELS_PER_CALL = {"ralf_knn_topk": 2, "ralf_knn_topk_exact": 2, "ralf_knn_merge": 2, "ralf_ce_label_smooth": 2}
+
+
+def launch_count() -> int:
+    return _LAUNCHES
+
+
+def check(rc: int, what: str) -> None:  # noqa: F811  (wraps _lib.check with launch accounting)
+    global _LAUNCHES
+    _lib.check(rc, what)
+    _LAUNCHES += _KERNELS_PER_CALL.get(what, 1)
 
 
 def _stream() -> C.c_void_p:
