@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--elems", type=int, default=12)
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of CUDA graphs")
     return ap.parse_args()
 
 
@@ -133,59 +134,28 @@ def run_ours(args):
                    precision=args.precision)
     model.load_state_dict(sd, strict=True)
     model.eval().to(dev)
-    eng = model.engine()
+    from ralf_b200.pipeline import LayoutPipeline
+
     B, HW = args.batch, args.hw
     S = tok.max_token_length
-    ids = model.special_token_ids
     gq = torch.Generator().manual_seed(7 + rank)
     # host (pinned) inputs for the end-to-end leg; device-resident copies for the kernel-only leg
     img_h = torch.rand(B, 4, HW, HW, generator=gq).pin_memory()
     qry_h = torch.nn.functional.normalize(torch.randn(B, 512, generator=gq), dim=1).pin_memory()
-    img_d, qry_d = img_h.to(dev), qry_h.to(dev)
-    const = model.preprocessor(G.ConditionalInputs(image=img_d))
-    tm = tok.token_mask.to(dev).to(torch.uint8)
+    pipe = LayoutPipeline(model, retr, B, HW, HW, top_k=16, use_graph=not args.no_graph)
+    pipe.img.copy_(img_h)
+    pipe.qry.copy_(qry_h)
     l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-
     knn_ev = []
 
     def step_device(record=False):
-        """inputs already resident in HBM; result (token ids) stays on the device."""
-        q_all = qry_d
-        if world > 1:
-            import torch.distributed as dist
-
-            q_all = torch.empty(world * B, 512, device=dev)
-            dist.all_gather_into_tensor(q_all, qry_d)
-        if record:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        idx, _ = retr.search_local(q_all, 16)
-        if record:
-            e1.record()
-            knn_ev.append((e0, e1))
-        if world > 1:
-            idx, _ = retr.search(q_all, 16)  # includes all-gather + merge (search_local above is timed alone)
-            idx = idx[rank * B:(rank + 1) * B]
-        retrieved = retr.fetch(idx)
-        mem, mem_s = eng.encode(img_d, retrieved, const["seq"], const["pad_mask"])
-        return eng.generate(mem_s, B, mem.shape[1], tm, ids["bos"], ids["pad"], S)
+        """inputs already resident in HBM (pipe.img / pipe.qry); result (token ids) stays on the device."""
+        return pipe.step(events=knn_ev if record else None)
 
     def step_e2e():
-        """public API with HOST buffers: H2D of the step's inputs and D2H of the result inside the region."""
-        img = img_h.to(dev, non_blocking=True)
-        q = qry_h.to(dev, non_blocking=True)
-        q_all = q
-        if world > 1:
-            import torch.distributed as dist
-
-            q_all = torch.empty(world * B, 512, device=dev)
-            dist.all_gather_into_tensor(q_all, q)
-        idx, _ = retr.search(q_all, 16)
-        if world > 1:
-            idx = idx[rank * B:(rank + 1) * B]
-        cond = G.ConditionalInputs(image=img, retrieved=retr.fetch(idx))
-        out = model.sample(cond=cond, cond_type="uncond", return_seq=True)  # decodes to boxes on the host (D2H inside)
-        return out["seq"]
+        """public API with HOST buffers: H2D of the step's inputs and D2H of the result inside the region;
+        also decodes the tokens to boxes on the host like model.sample() does."""
+        return pipe.generate_layouts(img_h, qry_h)["seq"]
 
     def barrier():
         torch.cuda.synchronize()
@@ -223,6 +193,8 @@ def run_ours(args):
     ms = timed(step_device, args.steps, record=True)
     clocks = sampler.stop() if rank == 0 else None
     launches = ops.launch_count() - launches0
+    if not args.no_graph:  # replayed graphs: kernels recorded per step x steps
+        launches = pipe.kernels_per_step * args.steps
     for _ in range(min(args.warmup, 2)):
         step_e2e()
     ms_e2e = timed(lambda: step_e2e(), args.steps, record=None)
@@ -236,6 +208,7 @@ def run_ours(args):
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         knn_ms = sum(a.elapsed_time(b) for a, b in knn_ev) / max(1, len(knn_ev))
         n_local = retr.emb.shape[0]
+        ids = model.special_token_ids  # noqa: F841
         q_tot = world * B
         knn_bytes = n_local * 512 * 4 + q_tot * 512 * 4 + q_tot * 16 * 12
         M = 2 * (HW // 16) ** 2 + 16 + 4
@@ -259,7 +232,7 @@ def run_ours(args):
                     "ms_per_step": round(ms_e2e / args.steps, 3)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "knn_scan_kernel<32> (TF32 tcgen05 gallery scan + fused top-C filter)", "bound": "hbm",
+            "roofline": {"kernel": "knn_scan_kernel<32> (TF32 tcgen05 gallery scan + fused top-C filter) + knn_rerank_kernel<32>", "bound": "hbm",
                          "achieved": round(knn_bytes / (knn_ms / 1e3) / 1e9, 1), "peak": hbm_peak, "unit": "GB/s",
                          "frac": round(knn_bytes / (knn_ms / 1e3) / 1e9 / hbm_peak, 4), "traffic": None,
                          "algorithmic_bytes_per_launch": int(knn_bytes), "ms_per_launch": round(knn_ms, 4),

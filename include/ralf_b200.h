@@ -154,6 +154,16 @@ int ralf_embed(const long long* tok, long long tok_ld, int tok_col, int B, int S
 int ralf_fid_embed(const float* cx, const float* cy, const float* w, const float* h, const long long* label,
                    int rows, int D, const float* fc_w, const float* fc_b, const float* emb, void* out,
                    long long out_plane, void* stream);
+/* Exemplar fetch as an index gather (replaces RetrievalDatasetWrapper.__getitem__'s 16 row reads,
+ * helpers/retrieval_dataset_wrapper.py:89-148): packed table [n_table, row_elems] fp32, row_elems = 6*E
+ * (label, mask, center_x, center_y, width, height), idx [rows] global ids (table holds ids
+ * [index_base, index_base + n_table)); missing (-1) -> empty layout. */
+int ralf_gather_layouts(const float* table, const long long* idx, int rows, int row_elems, long long n_table,
+                        long long index_base, float* out, void* stream);
+/* FIDNetV3 input rows + key-padding mask [nseq, E+1] straight from packed layouts [nseq, 6, E]. */
+int ralf_fid_embed_packed(const float* packed, int nseq, int E, int D, const float* fc_w, const float* fc_b,
+                          const float* emb, int num_labels, void* out, long long out_plane,
+                          unsigned char* pad_mask, void* stream);
 /* Greedy step tail (retrieval_augmented_autoreg.py:281-297, helpers/sampling.py:24-25): mask the
  * vocabulary, argmax (first maximum), append to seq[:, pos], update the pad mask, embed the token. */
 int ralf_argmax_next(const float* logits, int ldl, int B, int V, const unsigned char* allowed, long long* seq,

@@ -76,6 +76,8 @@ def lib() -> C.CDLL:
         L.ralf_fid_embed.argtypes = [vp, vp, vp, vp, vp, i, i, vp, vp, vp, vp, ll, vp]
         L.ralf_argmax_next.argtypes = [vp, i, i, i, vp, vp, i, i, vp, i, ll, vp, i, f, vp, vp, vp]
         L.ralf_kv_append.argtypes = [vp, i, i, vp, vp, i, i, vp]
+        L.ralf_gather_layouts.argtypes = [vp, vp, i, i, ll, ll, vp, vp]
+        L.ralf_fid_embed_packed.argtypes = [vp, i, i, i, vp, vp, vp, i, vp, ll, vp, vp]
         L.ralf_ce_label_smooth.argtypes = [vp, i, vp, i, i, f, ll, vp, vp, vp]
         _lib = L
     return _lib

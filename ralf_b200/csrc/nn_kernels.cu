@@ -439,6 +439,58 @@ __global__ void fid_embed_kernel(const float* __restrict__ cx, const float* __re
   }
 }
 
+
+// Exemplar fetch (helpers/retrieval_dataset_wrapper.py:89-148 as an index gather): packed layout table
+// [N, 6, E] fp32 (label, mask, center_x, center_y, width, height) -> out [rows, 6, E] for idx [rows]
+// (negative / missing index -> empty layout).
+__global__ void gather_layouts_kernel(const float* __restrict__ table, const long long* __restrict__ idx, int rows,
+                                      int row_elems, long long n_table, long long index_base, float* __restrict__ out) {
+  const long long total = static_cast<long long>(rows) * row_elems;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % row_elems);
+    const long long r = i / row_elems;
+    const long long src = idx[r] - index_base;
+    out[i] = (src >= 0 && src < n_table) ? table[src * row_elems + c] : 0.f;
+  }
+}
+
+// FIDNetV3 input from packed layouts [rows_seq, 6, E]: for element (n, e) emit
+// cat[fc_bbox(cx,cy,w,h), emb_label[label]] (split, [rows_seq*E, 2D]) and the key-padding mask row
+// [rows_seq, E+1] (column 0 = CLS, never padded; fid/model.py:34-50,88-103).
+__global__ void fid_embed_packed_kernel(const float* __restrict__ packed, int nseq, int E, int D,
+                                        const float* __restrict__ fc_w, const float* __restrict__ fc_b,
+                                        const float* __restrict__ emb, int num_labels, __nv_bfloat16* __restrict__ out,
+                                        long long plane, unsigned char* __restrict__ pad) {
+  const long long total = static_cast<long long>(nseq) * E * 2 * D;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % (2 * D));
+    const long long r = i / (2 * D);  // n * E + e
+    const int e = static_cast<int>(r % E);
+    const long long n = r / E;
+    const float* row = packed + n * 6 * E;
+    float y;
+    if (c < D) {
+      float acc = fc_b[c];
+      acc = fmaf(row[2 * E + e], fc_w[c * 4 + 0], acc);
+      acc = fmaf(row[3 * E + e], fc_w[c * 4 + 1], acc);
+      acc = fmaf(row[4 * E + e], fc_w[c * 4 + 2], acc);
+      acc = fmaf(row[5 * E + e], fc_w[c * 4 + 3], acc);
+      y = acc;
+    } else {
+      int lab = static_cast<int>(row[e]);
+      lab = lab < 0 ? 0 : (lab >= num_labels ? num_labels - 1 : lab);
+      y = emb[static_cast<long long>(lab) * D + (c - D)];
+    }
+    store_split(out, plane, i, y);
+    if (c == 0) {
+      pad[n * (E + 1) + 1 + e] = (row[E + e] != 0.f) ? 0 : 1;
+      if (e == 0) pad[n * (E + 1)] = 0;
+    }
+  }
+}
+
 // Greedy step tail (retrieval_augmented_autoreg.py:281-297, helpers/sampling.py:24-25):
 // logits[b, allowed == 0] = -inf; tok = argmax (first max wins, like torch.argmax); seq[b, pos] = tok;
 // pad_mask[b, pos] = (tok == pad); optionally x_next[b, :] = emb[tok]*scale + pe[pos].
@@ -707,5 +759,26 @@ extern "C" int ralf_ce_label_smooth(const float* logits, int ldl, const long lon
   ce_rows_kernel<<<(M + 7) / 8, 256, 0, ST(stream)>>>(logits, ldl, targets, M, V, eps, ignore_index, workspace,
                                                      workspace + M);
   ce_reduce_kernel<<<1, 256, 0, ST(stream)>>>(workspace, workspace + M, M, out_loss);
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_gather_layouts(const float* table, const long long* idx, int rows, int row_elems,
+                                   long long n_table, long long index_base, float* out, void* stream) {
+  if (!table || !idx || !out) return RALF_ERR_NULL;
+  if (rows <= 0 || row_elems <= 0) return RALF_ERR_SHAPE;
+  const long long total = static_cast<long long>(rows) * row_elems;
+  gather_layouts_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(table, idx, rows, row_elems, n_table, index_base,
+                                                                     out);
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_fid_embed_packed(const float* packed, int nseq, int E, int D, const float* fc_w, const float* fc_b,
+                                     const float* emb, int num_labels, void* out, long long out_plane,
+                                     unsigned char* pad_mask, void* stream) {
+  if (!packed || !fc_w || !fc_b || !emb || !out || !pad_mask) return RALF_ERR_NULL;
+  if (nseq <= 0 || E <= 0 || D <= 0 || num_labels <= 0) return RALF_ERR_SHAPE;
+  const long long total = static_cast<long long>(nseq) * E * 2 * D;
+  fid_embed_packed_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(packed, nseq, E, D, fc_w, fc_b, emb, num_labels,
+                                                                       BF(out), out_plane, pad_mask);
   return set_cuda_error(cudaGetLastError());
 }

@@ -271,17 +271,24 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # retrieved-layout branch (retrieval_augmented_autoreg.py:526-584; fid/model.py:95-103)
     # ------------------------------------------------------------------------------------------
-    def retrieved_features(self, retrieved: dict, B: int):
+    @staticmethod
+    def pack_retrieved(retrieved: dict, K: int, dev) -> torch.Tensor:
+        """retrieved{label, mask, center_x, center_y, width, height: [B, >=K, E]} -> packed fp32 [B, K, 6, E]
+        (API convenience for dict inputs; GpuRetriever.fetch produces the packed form directly on the GPU)."""
+        if "packed" in retrieved:
+            return retrieved["packed"][:, :K].to(dev, torch.float32).contiguous()
+        keys = ["label", "mask", "center_x", "center_y", "width", "height"]
+        return torch.stack([retrieved[k][:, :K].to(dev, torch.float32) for k in keys], dim=2).contiguous()
+
+    def retrieved_features(self, retrieved, B: int):
         """-> ref_layouts fp32 [B*K, 256] (already x16 + PE) and its split copy."""
         K = self.top_k
-        E = retrieved["label"].shape[-1]
+        packed = retrieved if torch.is_tensor(retrieved) else self.pack_retrieved(retrieved, K, self.dev)
+        E = packed.shape[-1]
         N = B * K
         f = "layout_encoer"
-        fl = lambda t: t[:, :K].reshape(-1).to(self.dev, torch.float32).contiguous()
-        rows = ops.fid_embed(fl(retrieved["center_x"]), fl(retrieved["center_y"]), fl(retrieved["width"]),
-                             fl(retrieved["height"]),
-                             retrieved["label"][:, :K].reshape(-1).to(self.dev, torch.int64).contiguous(),
-                             self.w[f + ".fc_bbox.w"], self.w[f + ".fc_bbox.b"], self.w[f + ".emb_label"])
+        rows, pad = ops.fid_embed_packed(packed.view(N, 6, E), self.w[f + ".fc_bbox.w"], self.w[f + ".fc_bbox.b"],
+                                         self.w[f + ".emb_label"])
         T = E + 1
         x = torch.empty((N * T, D), dtype=torch.float32, device=self.dev)
         xs = torch.empty((2, N * T, D), dtype=torch.bfloat16, device=self.dev)
@@ -290,8 +297,6 @@ class Engine:
                         group_offset=0, out_f32=x, out_split=xs)
         self._gemm(rows, f + ".enc_fc_in", act="relu", out_f32=x, out_split=xs, rows_per_group=E, group_stride=T,
                    group_offset=1)
-        pad = torch.zeros((N, T), dtype=torch.uint8, device=self.dev)
-        pad[:, 1:] = (~retrieved["mask"][:, :K].reshape(N, E).to(self.dev).bool()).to(torch.uint8)
         for i in range(4):
             x, xs = self._postnorm_layer(x, xs, f"{f}.enc_transformer.core.layers.{i}", N, T, pad, 4)
         # layout_adapter FeedForward on the CLS rows (row stride T*256), then x16 + PE1d[k]

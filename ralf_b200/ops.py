@@ -293,3 +293,25 @@ def ce_label_smooth(logits: torch.Tensor, targets: torch.Tensor, eps: float, ign
     check(_lib.lib().ralf_ce_label_smooth(lg.data_ptr(), lg.stride(0), tg.data_ptr(), M, V, eps, ignore_index,
                                           ws.data_ptr(), out.data_ptr(), _stream()), "ralf_ce_label_smooth")
     return out[0]
+
+
+def gather_layouts(table: torch.Tensor, idx: torch.Tensor, index_base: int = 0) -> torch.Tensor:
+    """table fp32 [N, 6, E]; idx int64 [...] -> fp32 [..., 6, E] (ralf_gather_layouts)."""
+    n, six, E = table.shape
+    flat = idx.reshape(-1).contiguous()
+    out = torch.empty((*idx.shape, six, E), dtype=torch.float32, device=table.device)
+    check(_lib.lib().ralf_gather_layouts(table.data_ptr(), flat.data_ptr(), flat.numel(), six * E, n, index_base,
+                                         out.data_ptr(), _stream()), "ralf_gather_layouts")
+    return out
+
+
+def fid_embed_packed(packed: torch.Tensor, fc_w, fc_b, emb):
+    """packed fp32 [nseq, 6, E] -> (split rows [2, nseq*E, 2D], pad mask uint8 [nseq, E+1])."""
+    nseq, _, E = packed.shape
+    D = emb.shape[1]
+    out = _split_out(nseq * E, 2 * D, emb.device)
+    pad = torch.empty((nseq, E + 1), dtype=torch.uint8, device=emb.device)
+    check(_lib.lib().ralf_fid_embed_packed(packed.data_ptr(), nseq, E, D, fc_w.data_ptr(), fc_b.data_ptr(),
+                                           emb.data_ptr(), emb.shape[0], out.data_ptr(), out.stride(0), pad.data_ptr(),
+                                           _stream()), "ralf_fid_embed_packed")
+    return out, pad

@@ -39,9 +39,9 @@ class GpuRetriever:
         self.index_base = index_base if index_base is not None else 0
         # FAISS does not normalise; the TF32 certificate only needs an upper bound on the row norms
         self.max_norm = float(self.emb.norm(dim=1).max().item()) * 1.0001 if self.emb.numel() else 0.0
-        self.layouts = None
+        self.table = None  # packed fp32 [n_total, 6, E]: label, mask, center_x, center_y, width, height
         if layouts is not None:
-            self.layouts = {k: layouts[k].to(self.dev).contiguous() for k in LAYOUT_KEYS}
+            self.table = torch.stack([layouts[k].to(self.dev, torch.float32) for k in LAYOUT_KEYS], dim=1).contiguous()
         self._ws: Optional[torch.Tensor] = None
 
     # -- search ---------------------------------------------------------------------------------
@@ -64,21 +64,18 @@ class GpuRetriever:
                 ei, es, _ = ops.knn_topk(self.emb, q, k, index_base=self.index_base, exact=True)
                 idx[bad], score[bad] = ei, es
         if self.world > 1:
-            import torch.distributed as dist
-
-            all_s = torch.empty((self.world, *score.shape), dtype=score.dtype, device=self.dev)
-            all_i = torch.empty((self.world, *idx.shape), dtype=idx.dtype, device=self.dev)
-            dist.all_gather_into_tensor(all_s, score, group=self.pg)
-            dist.all_gather_into_tensor(all_i, idx, group=self.pg)
-            idx, score = ops.knn_merge(all_s, all_i)
+            idx, score = exchange_and_merge(idx, score, self.world, self.pg, ops.knn_merge)
         return idx, score
 
     # -- exemplar fetch -------------------------------------------------------------------------
     def fetch(self, idx: torch.Tensor) -> dict:
-        """indices [B, K] -> retrieved{key: [B, K, E]} gathered from the resident layout table."""
-        assert self.layouts is not None, "no layout table attached"
-        flat = idx.reshape(-1).clamp_min(0)
-        out = {k: v.index_select(0, flat).view(*idx.shape, -1) for k, v in self.layouts.items()}
+        """indices [B, K] -> retrieved{"packed": [B, K, 6, E], label/mask/...: [B, K, E] views} gathered from the
+        resident layout table by ralf_gather_layouts (one kernel, no host round trip)."""
+        assert self.table is not None, "no layout table attached"
+        packed = ops.gather_layouts(self.table, idx)
+        out = {"packed": packed}
+        for i, k in enumerate(LAYOUT_KEYS):
+            out[k] = packed[:, :, i]
         return out
 
     # -- reference cache-table format -----------------------------------------------------------
@@ -92,6 +89,26 @@ class GpuRetriever:
             row = row[1:] if drop_self else row[:k]
             table[qid] = row
         return table
+
+
+def exchange_and_merge(idx: torch.Tensor, score: torch.Tensor, world: int, pg, merge_fn):
+    """The one exchange step of the sharded search: all-gather every rank's [Q,k]
+    (score, global index) lists and merge them with ``merge_fn(all_score [W,Q,k], all_idx [W,Q,k])``.
+    Backend-agnostic (NCCL on GPUs; gloo in the CPU tests)."""
+    import torch.distributed as dist
+
+    all_s = torch.empty((world, *score.shape), dtype=score.dtype, device=score.device)
+    all_i = torch.empty((world, *idx.shape), dtype=idx.dtype, device=idx.device)
+    if score.is_cuda:
+        dist.all_gather_into_tensor(all_s, score.contiguous(), group=pg)
+        dist.all_gather_into_tensor(all_i, idx.contiguous(), group=pg)
+    else:  # gloo has no all_gather_into_tensor for every dtype: use the list form
+        ls = [torch.empty_like(score) for _ in range(world)]
+        li = [torch.empty_like(idx) for _ in range(world)]
+        dist.all_gather(ls, score.contiguous(), group=pg)
+        dist.all_gather(li, idx.contiguous(), group=pg)
+        all_s, all_i = torch.stack(ls), torch.stack(li)
+    return merge_fn(all_s, all_i)
 
 
 def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
