@@ -95,9 +95,7 @@ def synth_world(args, rank, world, dev):
     from oracle import synth  # data generator only (shared with the tests); no oracle arithmetic
     from ralf_b200.retrieval import GpuRetriever, shard_bounds
     from ralf_b200.tokenizer import LayoutSequenceTokenizer
-    from tests import helpers
-
-    E, K = args.elems, 16
+    E = args.elems
     lo, hi = shard_bounds(args.gallery, world, rank)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     emb = torch.randn(hi - lo, 512, device=dev, generator=g)
@@ -111,9 +109,15 @@ def synth_world(args, rank, world, dev):
         lay[k] = torch.rand(n, E, generator=gl) * mask
     retr = GpuRetriever(emb, lay, device=dev, rank=rank, world_size=world, index_base=lo)
     tok = LayoutSequenceTokenizer(["logo", "text", "underlay", "embellishment"], E)
-    schema = helpers.load_schema("ralf_cgl")
-    sd = synth.synth_state_dict(schema, seed=0)
-    return retr, tok, sd
+    return retr, tok
+
+
+def synth_weights_for(model):
+    """Seeded random weights with the model's own state-dict schema (the constraint vocabulary depends on E)."""
+    from oracle import synth  # generator only
+
+    schema = {k: {"shape": list(v.shape), "dtype": str(v.dtype).replace("torch.", "")} for k, v in model.state_dict().items()}
+    return synth.synth_state_dict(schema, seed=0)
 
 
 def run_ours(args):
@@ -129,11 +133,11 @@ def run_ours(args):
     from ralf_b200 import generator as G
     from ralf_b200 import ops
 
-    retr, tok, sd = synth_world(args, rank, world, dev)
+    retr, tok = synth_world(args, rank, world, dev)
     model = G.RALF(features=None, tokenizer=tok, dataset_name="cgl", max_seq_length=args.elems, db_dataset=None,
                    retrieval_backbone="dreamsim", top_k=16, saliency_k="None", auxilary_task="uncond",
                    precision=args.precision)
-    model.load_state_dict(sd, strict=True)
+    model.load_state_dict(synth_weights_for(model), strict=True)
     model.eval().to(dev)
     from ralf_b200.pipeline import LayoutPipeline
 
@@ -268,9 +272,13 @@ def cpu_baseline(args, budget_canvases: int = 2):
     torch.set_num_threads(cores)
     E = args.elems
     tok = helpers.make_tokenizer(max_seq_length=E)
-    sd = synth.synth_state_dict(helpers.load_schema("ralf_cgl"), seed=0)
+    from ralf_b200 import generator as G
+
+    model = G.RALF(features=None, tokenizer=tok, dataset_name="cgl", max_seq_length=E, top_k=16, auxilary_task="uncond")
+    sd = synth_weights_for(model)
+    const_ids = model.preprocessor(G.ConditionalInputs(image=torch.zeros(1, 4, 8, 8)))["seq"][0].tolist()
     b = synth.synth_batch(budget_canvases, args.hw, args.hw, E, 16, 4, seed=1)
-    sc = torch.tensor([[517, 525, 519, 518]]).expand(budget_canvases, -1).contiguous()
+    sc = torch.tensor([const_ids]).expand(budget_canvases, -1).contiguous()
     sp = torch.zeros_like(sc, dtype=torch.bool)
     rows = min(args.gallery, 100_000)
     rng = np.random.default_rng(0)

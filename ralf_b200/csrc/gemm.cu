@@ -56,18 +56,19 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = P * (A_BYTES + B_BYTES);
   static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int MAX_STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  // The ring depth is a launch-time choice (min(MAX_STAGES, k-blocks)): short-K GEMMs then take little
+  // shared memory and several CTAs share an SM, hiding each other's prologue / epilogue.
+  static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/; }
   static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
 };
 
 template <int BN, int NPASS>
 __global__ void __launch_bounds__(192, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const GemmEpi ep, const int M, const int N, const int K) {
+                 const GemmEpi ep, const int M, const int N, const int K, const int STAGES) {
   using Cfg = GemmCfg<BN, NPASS>;
   constexpr int P = Cfg::P;
-  constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
@@ -346,12 +347,14 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
+                                         Cfg::smem_bytes(Cfg::MAX_STAGES));
     if (e != cudaSuccess) return set_cuda_error(e);
     attr_set = true;
   }
   dim3 grid((N + BN - 1) / BN, (M + 127) / 128);
-  gemm_bf16_kernel<BN, NPASS><<<grid, 192, Cfg::SMEM_BYTES, st>>>(ta, tb, ep, M, N, K);
+  const int nkb = (K + 63) / 64;
+  const int stages = nkb < Cfg::MAX_STAGES ? nkb : Cfg::MAX_STAGES;
+  gemm_bf16_kernel<BN, NPASS><<<grid, 192, Cfg::smem_bytes(stages), st>>>(ta, tb, ep, M, N, K, stages);
   return set_cuda_error(cudaGetLastError());
 }
 
