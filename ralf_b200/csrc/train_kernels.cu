@@ -1,0 +1,485 @@
+// Training-side kernels: operand transposes for the weight-gradient GEMMs,
+// bias-gradient reductions, LayerNorm / attention / cross-entropy / BatchNorm / pooling backward, dropout,
+// embedding scatter, global gradient norm and the fused clip + AdamW update.  The dense contractions of the
+// backward pass (dX = dY.W, dW = dY^T.X) reuse the tcgen05 GEMM in gemm.cu with K-major operands produced here.
+// fp32 arithmetic; GEMM operands are emitted as split bf16 (hi, lo planes).
+#include <float.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "ralf_internal.h"
+
+namespace ralf {
+
+__device__ __forceinline__ float t_warp_sum(float v) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+__device__ __forceinline__ void t_store_split(__nv_bfloat16* hi_plane, long long plane, long long off, float x) {
+  __nv_bfloat16 h, l;
+  split_bf16(x, h, l);
+  hi_plane[off] = h;
+  hi_plane[plane + off] = l;
+}
+__device__ __forceinline__ float t_load_split(const __nv_bfloat16* hi_plane, long long plane, long long off) {
+  return __bfloat162float(hi_plane[off]) + __bfloat162float(hi_plane[plane + off]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Transpose with optional format change: in [R, C] (fp32, row stride ld_in) or split -> out split [C, R]
+// (row stride ld_out >= R, padded columns zero-filled by the caller's allocation).  32x32 smem tiles.
+// ------------------------------------------------------------------------------------------------
+__global__ void transpose_to_split_kernel(const float* __restrict__ in_f32, const __nv_bfloat16* __restrict__ in_split,
+                                          long long in_plane, long long ld_in, int R, int C,
+                                          __nv_bfloat16* __restrict__ out, long long out_plane, long long ld_out) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (r < R && c < C) {
+      const long long off = static_cast<long long>(r) * ld_in + c;
+      v = in_f32 ? in_f32[off] : t_load_split(in_split, in_plane, off);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < C && r < R) t_store_split(out, out_plane, static_cast<long long>(c) * ld_out + r, tile[threadIdx.x][i]);
+  }
+}
+
+// fp32 [M, C] -> split [M, C] (same layout): GEMM A operand from an fp32 gradient.
+__global__ void to_split_kernel(const float* __restrict__ in, long long total, __nv_bfloat16* __restrict__ out,
+                                long long plane) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    t_store_split(out, plane, i, in[i]);
+}
+
+// Column sums of an fp32 [M, C] matrix (bias gradients): out[c] (+)= sum_r in[r, c].  Deterministic:
+// grid.x column tiles of 32, one block walks all rows with 32x8 threads, smem reduce.
+__global__ void colsum_kernel(const float* __restrict__ in, long long ld, int M, int C, float* __restrict__ out,
+                              int accumulate) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (c < C)
+    for (int r = threadIdx.y; r < M; r += 8) acc += in[static_cast<long long>(r) * ld + c];
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+    out[c] = accumulate ? out[c] + s : s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward.  y = (x - mean) * rstd * g + b.  One warp per row:
+//   dx = rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat))        (+ add_to, the residual-stream gradient)
+// dgamma / dbeta partials are accumulated per block into part[blockIdx][2][D]; ln_bwd_reduce sums them.
+// ------------------------------------------------------------------------------------------------
+__global__ void ln_bwd_kernel(const float* __restrict__ x, long long x_ld, const float* __restrict__ dy,
+                              const float* __restrict__ gamma, float eps, int M, int D, const float* __restrict__ add_to,
+                              float* __restrict__ dx, float* __restrict__ part) {
+  extern __shared__ float sh[];  // [2][D] block partials
+  float* sg = sh;
+  float* sb = sh + D;
+  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per = D >> 5;
+  for (int row = blockIdx.x * warps + wid; row < M; row += gridDim.x * warps) {
+    const float* xr = x + static_cast<long long>(row) * x_ld;
+    const float* dyr = dy + static_cast<long long>(row) * D;
+    float xv[32], gv[32];
+    float s = 0.f;
+    for (int i = 0; i < per; ++i) { xv[i] = xr[lane + 32 * i]; s += xv[i]; }
+    const float mean = t_warp_sum(s) / D;
+    float sq = 0.f;
+    for (int i = 0; i < per; ++i) { const float d = xv[i] - mean; sq += d * d; }
+    const float rstd = rsqrtf(t_warp_sum(sq) / D + eps);
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = 0; i < per; ++i) {
+      const int c = lane + 32 * i;
+      const float xh = (xv[i] - mean) * rstd;
+      const float d = dyr[c];
+      atomicAdd(&sg[c], d * xh);
+      atomicAdd(&sb[c], d);
+      gv[i] = d * gamma[c];
+      xv[i] = xh;
+      s1 += gv[i];
+      s2 += gv[i] * xh;
+    }
+    s1 = t_warp_sum(s1) / D;
+    s2 = t_warp_sum(s2) / D;
+    for (int i = 0; i < per; ++i) {
+      const int c = lane + 32 * i;
+      float v = rstd * (gv[i] - s1 - xv[i] * s2);
+      const long long off = static_cast<long long>(row) * D + c;
+      if (add_to) v += add_to[off];
+      dx[off] = v;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) part[static_cast<long long>(blockIdx.x) * 2 * D + i] = sh[i];
+}
+__global__ void ln_bwd_reduce_kernel(const float* __restrict__ part, int nblocks, int D, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * D) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) s += part[static_cast<long long>(b) * 2 * D + i];
+  if (i < D) dgamma[i] = s; else dbeta[i - D] = s;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Attention backward (fp32), same addressing conventions as attention_kernel in nn_kernels.cu.
+//   P_ij = exp(q_i.k_j*scale - lse_i) (0 where masked), delta_i = sum_d dO_i[d]*O_i[d]
+//   dV_j = sum_i P_ij dO_i ; dS_ij = P_ij (dO_i.v_j - delta_i) ; dQ_i = scale sum_j dS_ij k_j ; dK_j = scale sum_i dS_ij q_i
+// Kernel 1: thread per query -> dQ, delta.   Kernel 2: thread per key -> dK, dV (two passes to bound registers).
+// ------------------------------------------------------------------------------------------------
+template <int DH>
+__global__ void __launch_bounds__(128)
+attn_bwd_dq_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, const float* __restrict__ v, int ldk,
+                   const unsigned char* __restrict__ mask, int Tq, int Tk, int causal, float scale,
+                   const __nv_bfloat16* __restrict__ o_split, long long o_plane, const float* __restrict__ dO, int ldo,
+                   const float* __restrict__ lse, float* __restrict__ delta, float* __restrict__ dq, int lddq) {
+  constexpr int KT = 64;
+  __shared__ __align__(16) float ks[KT][DH];
+  __shared__ __align__(16) float vs[KT][DH];
+  __shared__ unsigned char ms[KT];
+  const int b = blockIdx.z, h = blockIdx.y, H = gridDim.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = t < Tq;
+  float qr[DH], dor[DH], acc[DH];
+  float my_lse = 0.f, dl = 0.f;
+  if (active) {
+    const long long qrow = static_cast<long long>(b) * Tq + t;
+    const float* qp = q + qrow * ldq + h * DH;
+    const float* dp = dO + qrow * ldo + h * DH;
+#pragma unroll
+    for (int i = 0; i < DH; ++i) {
+      qr[i] = qp[i] * scale;
+      dor[i] = dp[i];
+      dl = fmaf(dor[i], t_load_split(o_split, o_plane, qrow * ldo + h * DH + i), dl);
+      acc[i] = 0.f;
+    }
+    my_lse = lse[(static_cast<long long>(b) * H + h) * Tq + t];
+    delta[(static_cast<long long>(b) * H + h) * Tq + t] = dl;
+  }
+  const int kmax = causal ? min(Tk, (blockIdx.x + 1) * static_cast<int>(blockDim.x)) : Tk;
+  for (int j0 = 0; j0 < kmax; j0 += KT) {
+    __syncthreads();
+    const int nk = min(KT, Tk - j0);
+    for (int i = threadIdx.x; i < KT * (DH / 4); i += blockDim.x) {
+      const int r = i / (DH / 4), c = (i % (DH / 4)) * 4;
+      float4 fk = make_float4(0.f, 0.f, 0.f, 0.f), fv = fk;
+      if (r < nk) {
+        const long long off = (static_cast<long long>(b) * Tk + j0 + r) * ldk + h * DH + c;
+        fk = *reinterpret_cast<const float4*>(k + off);
+        fv = *reinterpret_cast<const float4*>(v + off);
+      }
+      *reinterpret_cast<float4*>(&ks[r][c]) = fk;
+      *reinterpret_cast<float4*>(&vs[r][c]) = fv;
+    }
+    for (int i = threadIdx.x; i < KT; i += blockDim.x)
+      ms[i] = (i < nk) ? (mask ? mask[static_cast<long long>(b) * Tk + j0 + i] : 0) : 1;
+    __syncthreads();
+    if (!active) continue;
+    for (int j = 0; j < nk; ++j) {
+      if (ms[j] || (causal && (j0 + j) > t)) continue;
+      float s = 0.f, dpv = 0.f;
+#pragma unroll
+      for (int i = 0; i < DH; ++i) {
+        s = fmaf(qr[i], ks[j][i], s);
+        dpv = fmaf(dor[i], vs[j][i], dpv);
+      }
+      const float ds = __expf(s - my_lse) * (dpv - dl) * scale;
+#pragma unroll
+      for (int i = 0; i < DH; ++i) acc[i] = fmaf(ds, ks[j][i], acc[i]);
+    }
+  }
+  if (!active) return;
+  float* out = dq + (static_cast<long long>(b) * Tq + t) * lddq + h * DH;
+#pragma unroll
+  for (int i = 0; i < DH; ++i) out[i] = acc[i];
+}
+
+template <int DH>
+__global__ void __launch_bounds__(128)
+attn_bwd_dkv_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, const float* __restrict__ v, int ldk,
+                    const unsigned char* __restrict__ mask, int Tq, int Tk, int causal, float scale,
+                    const float* __restrict__ dO, int ldo, const float* __restrict__ lse, const float* __restrict__ delta,
+                    float* __restrict__ dk, float* __restrict__ dv, int lddk) {
+  constexpr int QT = 64;
+  __shared__ __align__(16) float qs[QT][DH];
+  __shared__ __align__(16) float ds_[QT][DH];  // dO tile
+  __shared__ float ls[QT], dls[QT];
+  const int b = blockIdx.z, h = blockIdx.y, H = gridDim.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = j < Tk;
+  const bool dead = active && mask && mask[static_cast<long long>(b) * Tk + j];
+  float kr[DH], acc[DH];
+  const float* vrow = v + (static_cast<long long>(b) * Tk + (active ? j : 0)) * ldk + h * DH;
+  if (active) {
+    const float* kp = k + (static_cast<long long>(b) * Tk + j) * ldk + h * DH;
+#pragma unroll
+    for (int i = 0; i < DH; ++i) kr[i] = kp[i] * scale;
+  }
+  for (int pass = 0; pass < 2; ++pass) {  // pass 0: dV, pass 1: dK
+#pragma unroll
+    for (int i = 0; i < DH; ++i) acc[i] = 0.f;
+    const int i_begin = causal ? (blockIdx.x * static_cast<int>(blockDim.x)) / QT * QT : 0;  // queries t >= j only
+    for (int i0 = i_begin; i0 < Tq; i0 += QT) {
+      __syncthreads();
+      const int nq = min(QT, Tq - i0);
+      for (int e = threadIdx.x; e < QT * (DH / 4); e += blockDim.x) {
+        const int r = e / (DH / 4), c = (e % (DH / 4)) * 4;
+        float4 fq = make_float4(0.f, 0.f, 0.f, 0.f), fd = fq;
+        if (r < nq) {
+          const long long row = static_cast<long long>(b) * Tq + i0 + r;
+          fq = *reinterpret_cast<const float4*>(q + row * ldq + h * DH + c);
+          fd = *reinterpret_cast<const float4*>(dO + row * ldo + h * DH + c);
+        }
+        *reinterpret_cast<float4*>(&qs[r][c]) = fq;
+        *reinterpret_cast<float4*>(&ds_[r][c]) = fd;
+      }
+      for (int e = threadIdx.x; e < QT; e += blockDim.x) {
+        const long long idx = (static_cast<long long>(b) * H + h) * Tq + i0 + e;
+        ls[e] = (e < nq) ? lse[idx] : 0.f;
+        dls[e] = (e < nq) ? delta[idx] : 0.f;
+      }
+      __syncthreads();
+      if (!active || dead) continue;
+      for (int r = 0; r < nq; ++r) {
+        if (causal && j > (i0 + r)) continue;
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < DH; ++i) s = fmaf(qs[r][i], kr[i], s);
+        const float p = __expf(s - ls[r]);
+        if (pass == 0) {
+#pragma unroll
+          for (int i = 0; i < DH; ++i) acc[i] = fmaf(p, ds_[r][i], acc[i]);
+        } else {
+          float dpv = 0.f;
+#pragma unroll
+          for (int i = 0; i < DH; ++i) dpv = fmaf(ds_[r][i], vrow[i], dpv);
+          const float dsv = p * (dpv - dls[r]) * scale;
+#pragma unroll
+          for (int i = 0; i < DH; ++i) acc[i] = fmaf(dsv, qs[r][i], acc[i]);
+        }
+      }
+    }
+    if (active) {
+      float* out = (pass == 0 ? dv : dk) + (static_cast<long long>(b) * Tk + j) * lddk + h * DH;
+#pragma unroll
+      for (int i = 0; i < DH; ++i) out[i] = acc[i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cross-entropy (label smoothing) backward: dlogits = (softmax - ((1-eps)*onehot + eps/V)) / n_valid,
+// zero for ignored rows.  One warp per row; n_valid read from the forward's workspace sum.
+// ------------------------------------------------------------------------------------------------
+__global__ void ce_bwd_kernel(const float* __restrict__ logits, int ldl, const long long* __restrict__ tgt, int M, int V,
+                              float eps, long long ignore, const float* __restrict__ row_valid, float scale,
+                              float* __restrict__ dlogits, int ldd) {
+  __shared__ float nvalid_s;
+  if (threadIdx.x == 0) {
+    float n = 0.f;
+    for (int i = 0; i < M; ++i) n += row_valid[i];
+    nvalid_s = n;
+  }
+  __syncthreads();
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const float* x = logits + static_cast<long long>(row) * ldl;
+  float* d = dlogits + static_cast<long long>(row) * ldd;
+  const long long t = tgt[row];
+  if (t == ignore) {
+    for (int c = lane; c < V; c += 32) d[c] = 0.f;
+    return;
+  }
+  float mx = -INFINITY;
+  for (int c = lane; c < V; c += 32) mx = fmaxf(mx, x[c]);
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  float se = 0.f;
+  for (int c = lane; c < V; c += 32) se += expf(x[c] - mx);
+  se = t_warp_sum(se);
+  const float inv = scale / nvalid_s;
+  for (int c = lane; c < V; c += 32) {
+    const float p = expf(x[c] - mx) / se;
+    d[c] = (p - ((c == t ? (1.f - eps) : 0.f) + eps / V)) * inv;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Global gradient norm + fused clip + AdamW (train.py:450-454; torch.optim.AdamW semantics).
+// ------------------------------------------------------------------------------------------------
+__global__ void sqnorm_partial_kernel(const float* __restrict__ g, long long n, float* __restrict__ part) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    acc = fmaf(g[i], g[i], acc);
+  acc = t_warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = t_warp_sum(v);
+    if (threadIdx.x == 0) part[blockIdx.x] = v;
+  }
+}
+__global__ void sqnorm_final_kernel(const float* __restrict__ part, int n, float* __restrict__ out_norm) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += part[i];
+  acc = t_warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = t_warp_sum(v);
+    if (threadIdx.x == 0) out_norm[0] = sqrtf(v);
+  }
+}
+// p, g, m, v: contiguous range of one (lr, weight_decay) group.  clip = min(1, max_norm / (norm + 1e-6))
+// (torch.nn.utils.clip_grad_norm_); decoupled weight decay then Adam with bias correction.
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, long long n, const float* __restrict__ norm, float max_norm,
+                             float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2) {
+  const float nrm = norm ? norm[0] : 0.f;
+  const float clip = (norm && max_norm > 0.f) ? fminf(1.f, max_norm / (nrm + 1e-6f)) : 1.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * clip;
+    float pi = p[i];
+    pi -= lr * wd * pi;
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+    pi -= (lr / bc1) * (mi / denom);
+    p[i] = pi;
+  }
+}
+
+static inline int t_grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  return static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace ralf
+
+using namespace ralf;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
+#define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+
+extern "C" int ralf_transpose_to_split(const float* in_f32, const void* in_split, long long in_plane, long long ld_in,
+                                       int R, int C, void* out, long long out_plane, long long ld_out, void* stream) {
+  if ((!in_f32 && !in_split) || !out) return RALF_ERR_NULL;
+  if (R <= 0 || C <= 0 || ld_out < R) return RALF_ERR_SHAPE;
+  dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
+  transpose_to_split_kernel<<<grid, block, 0, ST(stream)>>>(in_f32, CBF(in_split), in_plane, ld_in, R, C, BF(out),
+                                                           out_plane, ld_out);
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_to_split(const float* in, long long total, void* out, long long out_plane, void* stream) {
+  if (!in || !out) return RALF_ERR_NULL;
+  if (total <= 0) return RALF_ERR_SHAPE;
+  to_split_kernel<<<t_grid_for(total, 256), 256, 0, ST(stream)>>>(in, total, BF(out), out_plane);
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_colsum(const float* in, long long ld, int M, int C, float* out, int accumulate, void* stream) {
+  if (!in || !out) return RALF_ERR_NULL;
+  if (M <= 0 || C <= 0) return RALF_ERR_SHAPE;
+  colsum_kernel<<<(C + 31) / 32, dim3(32, 8), 0, ST(stream)>>>(in, ld, M, C, out, accumulate);
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_layernorm_bwd(const float* x, long long x_ld, const float* dy, const float* gamma, float eps, int M,
+                                  int D, const float* add_to, float* dx, float* dgamma, float* dbeta,
+                                  float* workspace /* 2*D*nblocks floats, nblocks = min(M/8+1, 4*SMs) */,
+                                  void* stream) {
+  if (!x || !dy || !gamma || !dx || !dgamma || !dbeta || !workspace) return RALF_ERR_NULL;
+  if (M <= 0 || D <= 0 || D > 1024 || (D & 31)) return RALF_ERR_SHAPE;
+  int nblocks = (M + 7) / 8;
+  const int cap = num_sms() * 4;
+  if (nblocks > cap) nblocks = cap;
+  ln_bwd_kernel<<<nblocks, 256, 2 * D * sizeof(float), ST(stream)>>>(x, x_ld, dy, gamma, eps, M, D, add_to, dx, workspace);
+  ln_bwd_reduce_kernel<<<(2 * D + 255) / 256, 256, 0, ST(stream)>>>(workspace, nblocks, D, dgamma, dbeta);
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_ce_label_smooth_bwd(const float* logits, int ldl, const long long* targets, int M, int V, float eps,
+                                        long long ignore_index, const float* fwd_workspace, float scale, float* dlogits,
+                                        int ldd, void* stream) {
+  if (!logits || !targets || !fwd_workspace || !dlogits) return RALF_ERR_NULL;
+  if (M <= 0 || V <= 0) return RALF_ERR_SHAPE;
+  ce_bwd_kernel<<<(M + 7) / 8, 256, 0, ST(stream)>>>(logits, ldl, targets, M, V, eps, ignore_index, fwd_workspace + M,
+                                                    scale, dlogits, ldd);
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_grad_norm(const float* grads, long long n, float* workspace /* 1024 floats */, float* out_norm,
+                              void* stream) {
+  if (!grads || !workspace || !out_norm) return RALF_ERR_NULL;
+  if (n <= 0) return RALF_ERR_SHAPE;
+  int blocks = t_grid_for(n, 256);
+  if (blocks > 1024) blocks = 1024;
+  sqnorm_partial_kernel<<<blocks, 256, 0, ST(stream)>>>(grads, n, workspace);
+  sqnorm_final_kernel<<<1, 256, 0, ST(stream)>>>(workspace, blocks, out_norm);
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                               const float* grad_norm, float max_norm, float lr, float beta1, float beta2, float eps,
+                               float weight_decay, int step, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq) return RALF_ERR_NULL;
+  if (n <= 0 || step <= 0) return RALF_ERR_SHAPE;
+  const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
+  const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
+  adamw_kernel<<<t_grid_for(n, 256), 256, 0, ST(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, grad_norm, max_norm, lr,
+                                                         beta1, beta2, eps, weight_decay, bc1, bc2);
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_attention_bwd(const float* q, int ldq, const float* k, const float* v, int ldk,
+                                  const unsigned char* key_padding_mask, int B, int H, int Tq, int Tk, int head_dim,
+                                  int causal, float scale, const void* o_split, long long o_plane, const float* dO,
+                                  int ldo, const float* lse, float* delta_ws, float* dq, int lddq, float* dk, float* dv,
+                                  int lddk, void* stream) {
+  if (!q || !k || !v || !o_split || !dO || !lse || !delta_ws || !dq || !dk || !dv) return RALF_ERR_NULL;
+  if (B <= 0 || H <= 0 || Tq <= 0 || Tk <= 0 || (head_dim != 32 && head_dim != 64)) return RALF_ERR_SHAPE;
+  if ((ldq & 3) || (ldk & 3) || (ldo & 3)) return RALF_ERR_ALIGN;
+  const int tq = Tq >= 128 ? 128 : ((Tq + 31) / 32) * 32;
+  const int tk = Tk >= 128 ? 128 : ((Tk + 31) / 32) * 32;
+  dim3 g1((Tq + tq - 1) / tq, H, B), g2((Tk + tk - 1) / tk, H, B);
+  if (head_dim == 32) {
+    attn_bwd_dq_kernel<32><<<g1, tq, 0, ST(stream)>>>(q, ldq, k, v, ldk, key_padding_mask, Tq, Tk, causal, scale,
+                                                     CBF(o_split), o_plane, dO, ldo, lse, delta_ws, dq, lddq);
+    attn_bwd_dkv_kernel<32><<<g2, tk, 0, ST(stream)>>>(q, ldq, k, v, ldk, key_padding_mask, Tq, Tk, causal, scale, dO, ldo,
+                                                      lse, delta_ws, dk, dv, lddk);
+  } else {
+    attn_bwd_dq_kernel<64><<<g1, tq, 0, ST(stream)>>>(q, ldq, k, v, ldk, key_padding_mask, Tq, Tk, causal, scale,
+                                                     CBF(o_split), o_plane, dO, ldo, lse, delta_ws, dq, lddq);
+    attn_bwd_dkv_kernel<64><<<g2, tk, 0, ST(stream)>>>(q, ldq, k, v, ldk, key_padding_mask, Tq, Tk, causal, scale, dO, ldo,
+                                                      lse, delta_ws, dk, dv, lddk);
+  }
+  return set_cuda_error(cudaGetLastError());
+}
