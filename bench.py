@@ -268,7 +268,8 @@ def cpu_baseline(args, budget_canvases: int = 2):
     from oracle import synth
     from tests import helpers
 
-    cores = os.cpu_count() or 1
+    # all host threads torch can use productively: beyond ~32 threads these small fp32 ops get slower, not faster
+    cores = min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
     E = args.elems
     tok = helpers.make_tokenizer(max_seq_length=E)

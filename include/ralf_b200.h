@@ -130,6 +130,11 @@ int ralf_attention_decode(const float* q, int ldq, const float* k, const float* 
                           int ldk, const unsigned char* key_padding_mask, int mask_ld, int Tk, int B, int H,
                           int head_dim, float scale, void* out_split, long long out_plane, int ldo,
                           void* stream);
+/* Self-attention decode step with the cache append fused in: qkv [B, 3*H*head_dim] (this step's fused
+ * projection), K/V caches [B, S, H*head_dim]; writes row `pos` of both caches, then attends over keys 0..pos. */
+int ralf_attention_decode_append(const float* qkv, int ldqkv, float* kcache, float* vcache, int S, int pos,
+                                 const unsigned char* key_padding_mask, int mask_ld, int B, int H, int head_dim,
+                                 float scale, void* out_split, long long out_plane, int ldo, void* stream);
 /* ResNet50 stem (common/image.py:69-77): image fp32 NCHW [B,4,H,W] -> split im2col rows
  * [B*Ho*Wo, KP] for the 7x7/s2/p3 conv, k = (kh*7+kw)*4 + c, KP = 200 (zero padded). */
 int ralf_stem_im2col(const float* img, int B, int H, int W, int KP, void* out, long long out_plane,

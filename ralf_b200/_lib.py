@@ -67,6 +67,7 @@ def lib() -> C.CDLL:
         L.ralf_layernorm.argtypes = [vp, ll, vp, vp, f, i, i, vp, vp, ll, vp]
         L.ralf_attention.argtypes = [vp, i, vp, vp, i, vp, i, i, i, i, i, i, f, vp, ll, vp, i, vp]
         L.ralf_attention_decode.argtypes = [vp, i, vp, vp, ll, i, vp, i, i, i, i, i, f, vp, ll, i, vp]
+        L.ralf_attention_decode_append.argtypes = [vp, i, vp, vp, i, i, vp, i, i, i, i, f, vp, ll, i, vp]
         L.ralf_stem_im2col.argtypes = [vp, i, i, i, i, vp, ll, vp]
         L.ralf_im2col.argtypes = [vp, ll, i, i, i, i, i, i, i, i, vp, ll, vp]
         L.ralf_maxpool3x3s2.argtypes = [vp, ll, i, i, i, i, vp, ll, vp]

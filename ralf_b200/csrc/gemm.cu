@@ -8,7 +8,9 @@
 // product to ~2^-17 relative -- that is what lets the logits / token ids match the fp32
 // reference (common/common.py:84-135, nn.Linear / nn.Conv2d in fp32).  NPASS = 1 is plain bf16.
 //
-// One CTA per 128 x BN output tile.  Warp 0 = TMA producer (SWIZZLE_128B boxes of 64 bf16 along
+// Persistent CTAs (grid = min(#tiles, #SMs)) walk the 128 x BN output tiles round-robin (n fastest, so CTAs that
+// run together share the A tile in L2).  Two TMEM accumulator buffers: the epilogue of tile i overlaps the
+// TMA/MMA main loop of tile i+1.  Warp 0 = TMA producer (SWIZZLE_128B boxes of 64 bf16 along
 // K), warp 1 = TMEM allocator + single-thread tcgen05.mma issuer, warps 2-5 = epilogue
 // (tcgen05.ld 32x32b, one accumulator row per thread, fused bias / ReLU / GELU / residual /
 // bf16 split, direct vectorised global stores).  smem ring of STAGES stages, full/empty
@@ -59,8 +61,8 @@ struct GemmCfg {
   static constexpr int MAX_STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   // The ring depth is a launch-time choice (min(MAX_STAGES, k-blocks)): short-K GEMMs then take little
   // shared memory and several CTAs share an SM, hiding each other's prologue / epilogue.
-  static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/; }
-  static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/; }
+  static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator buffers
 };
 
 template <int BN, int NPASS>
@@ -74,13 +76,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* accum_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* tfull_bar = empty_bar + STAGES;  // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;      // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * 128;
-  const int n0 = blockIdx.x * BN;
+  const int tiles_n = (N + BN - 1) / BN;
+  const int num_tiles = ((M + 127) / 128) * tiles_n;
   const int nkb = (K + 63) / 64;
 
   if (warp == 0 && lane == 0) {
@@ -90,7 +93,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 128);
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -103,16 +109,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * 128, n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          uint8_t* st = smem + s * Cfg::STAGE_BYTES;
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
-          tma_load_3d(&tmA, &full_bar[s], st + p * Cfg::A_BYTES, kb * 64, m0, p);
-          tma_load_3d(&tmB, &full_bar[s], st + P * Cfg::A_BYTES + p * Cfg::B_BYTES, kb * 64, n0, p);
+          for (int p = 0; p < P; ++p) {
+            tma_load_3d(&tmA, &full_bar[s], st + p * Cfg::A_BYTES, kb * 64, m0, p);
+            tma_load_3d(&tmB, &full_bar[s], st + P * Cfg::A_BYTES + p * Cfg::B_BYTES, kb * 64, n0, p);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -120,36 +129,48 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       constexpr uint32_t idesc = make_idesc(1, 128, BN);
       int s = 0;
       uint32_t ph = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&full_bar[s], ph);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t a_hi = base_u32 + s * Cfg::STAGE_BYTES;
-        const uint32_t b_hi = a_hi + P * Cfg::A_BYTES;
-        const uint64_t da_hi = make_sw128_kmajor_desc(a_hi);
-        const uint64_t db_hi = make_sw128_kmajor_desc(b_hi);
+        const uint32_t tacc = tmem_base + buf * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_hi = base_u32 + s * Cfg::STAGE_BYTES;
+          const uint32_t b_hi = a_hi + P * Cfg::A_BYTES;
+          const uint64_t da_hi = make_sw128_kmajor_desc(a_hi);
+          const uint64_t db_hi = make_sw128_kmajor_desc(b_hi);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t koff = static_cast<uint64_t>(2 * k);  // 32 bytes >> 4 per UMMA_K = 16
-          if (NPASS == 3) {
-            const uint64_t da_lo = make_sw128_kmajor_desc(a_hi + Cfg::A_BYTES);
-            const uint64_t db_lo = make_sw128_kmajor_desc(b_hi + Cfg::B_BYTES);
-            mma_bf16_ss(tmem_base, da_hi + koff, db_lo + koff, idesc, (kb | k) != 0);
-            mma_bf16_ss(tmem_base, da_lo + koff, db_hi + koff, idesc, 1);
-            mma_bf16_ss(tmem_base, da_hi + koff, db_hi + koff, idesc, 1);
-          } else {
-            mma_bf16_ss(tmem_base, da_hi + koff, db_hi + koff, idesc, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t koff = static_cast<uint64_t>(2 * k);  // 32 bytes >> 4 per UMMA_K = 16
+            if (NPASS == 3) {
+              const uint64_t da_lo = make_sw128_kmajor_desc(a_hi + Cfg::A_BYTES);
+              const uint64_t db_lo = make_sw128_kmajor_desc(b_hi + Cfg::B_BYTES);
+              mma_bf16_ss(tacc, da_hi + koff, db_lo + koff, idesc, (kb | k) != 0);
+              mma_bf16_ss(tacc, da_lo + koff, db_hi + koff, idesc, 1);
+              mma_bf16_ss(tacc, da_hi + koff, db_hi + koff, idesc, 1);
+            } else {
+              mma_bf16_ss(tacc, da_hi + koff, db_hi + koff, idesc, (kb | k) != 0);
+            }
           }
+          tc_commit(&empty_bar[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        tc_commit(&empty_bar[s]);
-        if (++s == STAGES) { s = 0; ph ^= 1; }
+        tc_commit(&tfull_bar[buf]);
       }
-      tc_commit(accum_bar);
     }
   } else {
     // ------------------------------- epilogue ---------------------------------------------
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int m0 = (tile / tiles_n) * 128, n0 = (tile % tiles_n) * BN;
+    mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+    tc_fence_after();
+    const uint32_t tacc = tmem_base + buf * BN;
     const int r = m0 + quad * 32 + lane;
     const bool row_ok = r < M;
     const long long out_row =
@@ -159,7 +180,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int c = 0; c < BN; c += 32) {
       if (n0 + c >= N) break;
       uint32_t v[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c, v);
+      tmem_ld_32x32(tacc + (static_cast<uint32_t>(quad * 32) << 16) + c, v);
       tmem_ld_wait();
       if (!row_ok) continue;
       const int nbase = n0 + c;
@@ -256,6 +277,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
+    tc_fence_before();
+    mbar_arrive(&tempty_bar[buf]);
+    }  // tile loop
   }
   tc_fence_before();
   __syncthreads();
@@ -351,7 +375,9 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
     if (e != cudaSuccess) return set_cuda_error(e);
     attr_set = true;
   }
-  dim3 grid((N + BN - 1) / BN, (M + 127) / 128);
+  const long long num_tiles = static_cast<long long>((N + BN - 1) / BN) * ((M + 127) / 128);
+  const int sms = num_sms();
+  dim3 grid(static_cast<unsigned>(num_tiles < sms ? num_tiles : sms));
   const int nkb = (K + 63) / 64;
   const int stages = nkb < Cfg::MAX_STAGES ? nkb : Cfg::MAX_STAGES;
   gemm_bf16_kernel<BN, NPASS><<<grid, 192, Cfg::smem_bytes(stages), st>>>(ta, tb, ep, M, N, K, stages);
@@ -369,13 +395,14 @@ extern "C" int ralf_gemm(const RalfGemmArgs* a, void* stream) {
   if ((a->lda % 8) || (a->ldw % 8)) return RALF_ERR_ALIGN;
   const int planes = a->npass == 3 ? 2 : 1;
   int bn = a->block_n;
-  if (bn == 0) {
+  if (bn == 0) {  // widest tile that still yields ~one tile per SM; skinny (decode, M <= 128) GEMMs get BN = 32
     const long long mt = (a->M + 127) / 128;
     if (mt * ((a->N + 255) / 256) >= 120 && a->N >= 256 && a->npass == 1) bn = 256;
     else if (mt * ((a->N + 127) / 128) >= 120 && a->N >= 128) bn = 128;
-    else bn = 64;
+    else if (mt * ((a->N + 63) / 64) >= 60 && a->N >= 64) bn = 64;
+    else bn = 32;
   }
-  if (bn != 64 && bn != 128 && bn != 256) return RALF_ERR_SHAPE;
+  if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return RALF_ERR_SHAPE;
   CUtensorMap ta, tb;
   int rc = make_kmajor_tmap(&ta, a->A, 2, a->K, a->M, planes, a->lda, a->a_plane, 128);
   if (rc) return rc;
@@ -407,9 +434,11 @@ extern "C" int ralf_gemm(const RalfGemmArgs* a, void* stream) {
   const int np = a->npass;
 #define RALF_GEMM_CASE(BN_, NP_) \
   if (bn == BN_ && np == NP_) return launch_gemm<BN_, NP_>(ta, tb, ep, a->M, a->N, a->K, st);
+  RALF_GEMM_CASE(32, 3)
   RALF_GEMM_CASE(64, 3)
   RALF_GEMM_CASE(128, 3)
   RALF_GEMM_CASE(256, 3)
+  RALF_GEMM_CASE(32, 1)
   RALF_GEMM_CASE(64, 1)
   RALF_GEMM_CASE(128, 1)
   RALF_GEMM_CASE(256, 1)

@@ -9,7 +9,8 @@
 // buffers of 256 columns so the epilogue of tile t overlaps the MMAs of tile t+1).  Epilogue
 // thread q owns query q: it reads its accumulator row from TMEM and keeps a running top-C
 // candidate list (C >= 2k) in shared memory -- one fp32 compare per score in the steady state,
-// append on success, warp-synchronous insertion-sort compaction when a list nears capacity.
+// append on success; when any list of a warp nears capacity the warp sorts the over-full lists
+// cooperatively (bitonic network in registers, one list at a time) and tightens their thresholds.
 // TF32 scores only nominate candidates; they never decide the result.
 // Phase 2 (knn_rerank_kernel): per query, merge the per-CTA candidate lists, re-score the best
 // C candidates with the canonical fp32 dot product (bit-identical to oracle/knn_oracle.c),
@@ -54,32 +55,80 @@ __device__ __forceinline__ float canonical_dot_warp(const float* __restrict__ a,
 
 template <int C>
 struct KnnCfg {
-  static constexpr int CAP = C + 16;
-  static constexpr int A_BYTES = 128 * 128;  // 128 queries x 32 fp32
-  static constexpr int B_BYTES = 256 * 128;  // 256 gallery rows x 32 fp32
+  static constexpr int NS = C / 16;            // sort slots per lane: bitonic network over 32*NS keys
+  static constexpr int CAP = (C <= 32) ? 64 : 96;  // candidate-list capacity per query (C kept + appends)
+  static constexpr int STRIDE = CAP + 1;       // u64 per query list (+1: spreads the appends over banks)
+  static constexpr int A_BYTES = 128 * 128;    // 128 queries x 32 fp32
+  static constexpr int B_BYTES = 256 * 128;    // 256 gallery rows x 32 fp32
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (C <= 32) ? 3 : 2;
-  static constexpr int CAND_BYTES = CAP * 128 * 8;
+  static constexpr int CAND_BYTES = ((128 * STRIDE * 8 + 1023) / 1024) * 1024;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + CAND_BYTES + 1024 + 256;
+  static_assert(32 * NS >= CAP, "sort network must cover the list");
 };
 
-// Insert the unsorted tail [m, cnt) of this thread's candidate column into its sorted (descending)
-// prefix [0, m), keeping at most C entries.  Columns are interleaved: entry e of thread t lives at
-// col[e * 128] (col already offset by t) -> conflict-free shared-memory access across a warp.
-template <int C>
-__device__ __forceinline__ void knn_compact(uint64_t* col, int& m, int& cnt, float& thr) {
-  for (int e = m; e < cnt; ++e) {
-    const uint64_t key = col[e * 128];
-    int j = m;
-    while (j > 0 && col[(j - 1) * 128] < key) {
-      if (j < C) col[j * 128] = col[(j - 1) * 128];
-      --j;
+// Bitonic sort (descending) of 32*NS u64 keys held NS per lane; key index i = lane + 32*slot.
+// After the sort x[s] of lane l is the key of rank l + 32*s.
+template <int NS>
+__device__ __forceinline__ void bitonic_desc(uint64_t (&x)[NS], const int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32 * NS; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {  // partner lives in another slot of the same lane
+        const int js = j >> 5;
+        uint64_t y[NS];
+#pragma unroll
+        for (int sl = 0; sl < NS; ++sl) {
+          const uint64_t o = x[sl ^ js];
+          const int i = lane + 32 * sl;
+          const bool keep_max = (((i & k) == 0) == ((i & j) == 0));
+          y[sl] = keep_max ? (x[sl] > o ? x[sl] : o) : (x[sl] < o ? x[sl] : o);
+        }
+#pragma unroll
+        for (int sl = 0; sl < NS; ++sl) x[sl] = y[sl];
+      } else {
+#pragma unroll
+        for (int sl = 0; sl < NS; ++sl) {
+          const uint64_t o = __shfl_xor_sync(0xffffffffu, x[sl], j);
+          const int i = lane + 32 * sl;
+          const bool keep_max = (((i & k) == 0) == ((i & j) == 0));
+          x[sl] = keep_max ? (x[sl] > o ? x[sl] : o) : (x[sl] < o ? x[sl] : o);
+        }
+      }
     }
-    if (j < C) col[j * 128] = key;
-    if (m < C) ++m;
   }
-  cnt = m;
-  thr = (m == C) ? knn_key_score(col[(C - 1) * 128]) : -INFINITY;
+}
+
+// Warp-cooperative compaction round.  Each lane owns one query list (cnt entries, unsorted, in shared memory
+// at lists + lane*STRIDE).  For every list longer than C the whole warp sorts it (bitonic network in registers),
+// keeps the best C and publishes the new threshold (score of rank C-1) to the owning lane.  Lists with
+// <= C entries are left alone (their threshold stays, any new score still passes).
+template <int C>
+__device__ __forceinline__ void knn_compact_round(uint64_t* lists, const int lane, int& cnt, float& thr) {
+  using Cfg = KnnCfg<C>;
+  constexpr int NS = Cfg::NS;
+#pragma unroll 1
+  for (int ql = 0; ql < 32; ++ql) {
+    const int n = __shfl_sync(0xffffffffu, cnt, ql);
+    if (n <= C) continue;  // warp-uniform
+    uint64_t* col = lists + ql * Cfg::STRIDE;
+    uint64_t x[NS];
+#pragma unroll
+    for (int sl = 0; sl < NS; ++sl) {
+      const int e = lane + 32 * sl;
+      x[sl] = (e < n && e < Cfg::CAP) ? col[e] : 0ull;
+    }
+    bitonic_desc<NS>(x, lane);
+#pragma unroll
+    for (int sl = 0; sl < C / 32; ++sl) col[lane + 32 * sl] = x[sl];
+    const uint64_t kth = __shfl_sync(0xffffffffu, x[(C - 1) >> 5], (C - 1) & 31);
+    if (lane == ql) {
+      cnt = C;
+      thr = knn_key_score(kth);
+    }
+    __syncwarp();
+  }
 }
 
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
@@ -181,8 +230,9 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int quad = warp & 3;
     const int ql = quad * 32 + lane;  // query lane within the tile == TMEM lane
     const bool active = (qtile * 128 + ql) < nq;
-    uint64_t* col = cand_s + ql;
-    int m = 0, cnt = 0;
+    uint64_t* lists = cand_s + static_cast<size_t>(quad) * 32 * Cfg::STRIDE;  // this warp's 32 query lists
+    uint64_t* mine = lists + lane * Cfg::STRIDE;
+    int cnt = 0;
     float thr = -INFINITY;
     int it = 0;
     for (int t = t_begin; t < t_end; ++t, ++it) {
@@ -194,7 +244,7 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t tacc = tmem_base + buf * 256 + (static_cast<uint32_t>(quad * 32) << 16);
 #pragma unroll 1
       for (int c0 = 0; c0 < ncols; c0 += 16) {
-        if (__any_sync(0xffffffffu, cnt > Cfg::CAP - 16)) knn_compact<C>(col, m, cnt, thr);
+        if (__any_sync(0xffffffffu, cnt > Cfg::CAP - 16)) knn_compact_round<C>(lists, lane, cnt, thr);
         uint32_t v[16];
         tmem_ld_32x16(tacc + c0, v);
         tmem_ld_wait();
@@ -204,7 +254,7 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int j = 0; j < 16; ++j) {
             const float s = __uint_as_float(v[j]);
             if (s > thr && j < lim) {
-              col[cnt * 128] = knn_key(s, static_cast<uint32_t>(g0 + c0 + j));
+              mine[cnt] = knn_key(s, static_cast<uint32_t>(g0 + c0 + j));
               ++cnt;
             }
           }
@@ -213,11 +263,16 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_before();
       mbar_arrive(&tempty_bar[buf]);
     }
-    knn_compact<C>(col, m, cnt, thr);
-    // candidate lists: [qtile][cta][query lane][C]
-    uint64_t* out = cand + ((static_cast<size_t>(qtile) * gridDim.x + blockIdx.x) * 128 + ql) * C;
-#pragma unroll 4
-    for (int e = 0; e < C; ++e) out[e] = (e < m) ? col[e * 128] : 0ull;
+    __syncwarp();
+    knn_compact_round<C>(lists, lane, cnt, thr);  // trims every list to <= C entries
+    // candidate lists: [qtile][cta][query lane][C]; unused slots are 0 (= empty)
+    uint64_t* out_w = cand + ((static_cast<size_t>(qtile) * gridDim.x + blockIdx.x) * 128 + quad * 32) * C;
+#pragma unroll 1
+    for (int q = 0; q < 32; ++q) {
+      const int n_q = __shfl_sync(0xffffffffu, cnt, q);
+      const uint64_t* col = lists + q * Cfg::STRIDE;
+      for (int e = lane; e < C; e += 32) out_w[static_cast<size_t>(q) * C + e] = (e < n_q) ? col[e] : 0ull;
+    }
   }
   tc_fence_before();
   __syncthreads();

@@ -177,10 +177,16 @@ attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__
 // ------------------------------------------------------------------------------------------------
 template <int DH>
 __global__ void __launch_bounds__(128)
-attention_decode_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k,
-                        const float* __restrict__ v, long long kv_bstride, int ldk,
+attention_decode_kernel(const float* __restrict__ q, int ldq, const float* k /* may alias kc_w */,
+                        const float* v /* may alias vc_w */, long long kv_bstride, int ldk,
                         const unsigned char* __restrict__ mask, int mask_ld, int Tk, int B, int H, float scale,
-                        __nv_bfloat16* __restrict__ out_split, long long out_plane, int ldo) {
+                        __nv_bfloat16* __restrict__ out_split, long long out_plane, int ldo,
+                        const float* __restrict__ knew, const float* __restrict__ vnew, int ldnew,
+                        float* kc_w, float* vc_w) {
+  // Lane mapping: CPL = DH/4 lanes cover one key row (16 B each), KPI = 32/CPL keys per warp iteration, so
+  // every warp-wide LDG.128 reads KPI full, contiguous 128/256-byte rows (100 % sector efficiency).
+  constexpr int CPL = DH / 4;
+  constexpr int KPI = 32 / CPL;
   extern __shared__ float probs[];  // [warps][Tk_pad]
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.x * (blockDim.x >> 5) + wid;
@@ -188,29 +194,40 @@ attention_decode_kernel(const float* __restrict__ q, int ldq, const float* __res
   const int b = bh / H, h = bh - b * H;
   const int tk_pad = (Tk + 31) & ~31;
   float* pr = probs + wid * tk_pad;
-  float qr[DH];
-  const float* qp = q + static_cast<long long>(b) * ldq + h * DH;
-#pragma unroll
-  for (int i = 0; i < DH; i += 4) {
-    const float4 f = *reinterpret_cast<const float4*>(qp + i);
-    qr[i] = f.x * scale; qr[i + 1] = f.y * scale; qr[i + 2] = f.z * scale; qr[i + 3] = f.w * scale;
-  }
-  const float* kb = k + static_cast<long long>(b) * kv_bstride * ldk + h * DH;
-  const float* vb = v + static_cast<long long>(b) * kv_bstride * ldk + h * DH;
-  float lmax = -INFINITY;
-  for (int j = lane; j < Tk; j += 32) {
-    const float* kr = kb + static_cast<long long>(j) * ldk;
-    float acc = 0.f;
-#pragma unroll
-    for (int i = 0; i < DH; i += 4) {
-      const float4 f = *reinterpret_cast<const float4*>(kr + i);
-      acc = fmaf(qr[i], f.x, acc); acc = fmaf(qr[i + 1], f.y, acc);
-      acc = fmaf(qr[i + 2], f.z, acc); acc = fmaf(qr[i + 3], f.w, acc);
+  const int kk = lane / CPL, c = lane % CPL;
+  if (knew) {  // append this step's K/V row (position Tk-1) to the cache before attending over it
+    const long long dst = (static_cast<long long>(b) * kv_bstride + (Tk - 1)) * ldk + h * DH;
+    for (int i = lane; i < DH; i += 32) {
+      kc_w[dst + i] = knew[static_cast<long long>(b) * ldnew + h * DH + i];
+      vc_w[dst + i] = vnew[static_cast<long long>(b) * ldnew + h * DH + i];
     }
-    if (mask && mask[static_cast<long long>(b) * mask_ld + j]) acc = -INFINITY;
-    pr[j] = acc;
-    lmax = fmaxf(lmax, acc);
+    __syncwarp();
   }
+  float4 q4 = *reinterpret_cast<const float4*>(q + static_cast<long long>(b) * ldq + h * DH + 4 * c);
+  q4.x *= scale; q4.y *= scale; q4.z *= scale; q4.w *= scale;
+  const float* kb = k + static_cast<long long>(b) * kv_bstride * ldk + h * DH + 4 * c;
+  const float* vb = v + static_cast<long long>(b) * kv_bstride * ldk + h * DH + 4 * c;
+  // scores
+  for (int j0 = 0; j0 < Tk; j0 += KPI * 4) {
+    float part[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * KPI + kk;
+      float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < Tk) f = *reinterpret_cast<const float4*>(kb + static_cast<long long>(j) * ldk);
+      part[u] = q4.x * f.x + q4.y * f.y + q4.z * f.z + q4.w * f.w;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int off = CPL >> 1; off >= 1; off >>= 1) part[u] += __shfl_xor_sync(0xffffffffu, part[u], off);
+      const int j = j0 + u * KPI + kk;
+      if (c == 0 && j < Tk) pr[j] = (mask && mask[static_cast<long long>(b) * mask_ld + j]) ? -INFINITY : part[u];
+    }
+  }
+  __syncwarp();
+  float lmax = -INFINITY;
+  for (int j = lane; j < Tk; j += 32) lmax = fmaxf(lmax, pr[j]);
   lmax = warp_max(lmax);
   float lsum = 0.f;
   for (int j = lane; j < Tk; j += 32) {
@@ -221,33 +238,39 @@ attention_decode_kernel(const float* __restrict__ q, int ldq, const float* __res
   lsum = warp_sum(lsum);
   __syncwarp();
   const float inv = 1.f / lsum;
-  // o[d] = sum_j p_j V[j][d]; lane owns dims lane (+32)
-  float o0 = 0.f, o1 = 0.f;
-  int j = 0;
-  for (; j + 4 <= Tk; j += 4) {
-    float a[4], c[4];
+  // o[4c..4c+3] over this lane's keys (j = kk mod KPI), then reduce across the KPI key groups
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j0 = 0; j0 < Tk; j0 += KPI * 4) {
+    float4 f[4];
+    float p[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const float* vr = vb + static_cast<long long>(j + u) * ldk;
-      a[u] = vr[lane];
-      c[u] = (DH == 64) ? vr[lane + 32] : 0.f;
+      const int j = j0 + u * KPI + kk;
+      f[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      p[u] = 0.f;
+      if (j < Tk) {
+        f[u] = *reinterpret_cast<const float4*>(vb + static_cast<long long>(j) * ldk);
+        p[u] = pr[j];
+      }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const float p = pr[j + u];
-      o0 = fmaf(p, a[u], o0);
-      o1 = fmaf(p, c[u], o1);
+      o.x = fmaf(p[u], f[u].x, o.x); o.y = fmaf(p[u], f[u].y, o.y);
+      o.z = fmaf(p[u], f[u].z, o.z); o.w = fmaf(p[u], f[u].w, o.w);
     }
   }
-  for (; j < Tk; ++j) {
-    const float* vr = vb + static_cast<long long>(j) * ldk;
-    const float p = pr[j];
-    o0 = fmaf(p, vr[lane], o0);
-    if (DH == 64) o1 = fmaf(p, vr[lane + 32], o1);
+#pragma unroll
+  for (int off = CPL; off < 32; off <<= 1) {
+    o.x += __shfl_xor_sync(0xffffffffu, o.x, off); o.y += __shfl_xor_sync(0xffffffffu, o.y, off);
+    o.z += __shfl_xor_sync(0xffffffffu, o.z, off); o.w += __shfl_xor_sync(0xffffffffu, o.w, off);
   }
-  const long long orow = static_cast<long long>(b) * ldo + h * DH;
-  store_split(out_split, out_plane, orow + lane, o0 * inv);
-  if (DH == 64) store_split(out_split, out_plane, orow + lane + 32, o1 * inv);
+  if (kk == 0) {
+    const long long orow = static_cast<long long>(b) * ldo + h * DH + 4 * c;
+    store_split(out_split, out_plane, orow + 0, o.x * inv);
+    store_split(out_split, out_plane, orow + 1, o.y * inv);
+    store_split(out_split, out_plane, orow + 2, o.z * inv);
+    store_split(out_split, out_plane, orow + 3, o.w * inv);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -632,10 +655,10 @@ extern "C" int ralf_attention(const float* q, int ldq, const float* k, const flo
   return set_cuda_error(cudaGetLastError());
 }
 
-extern "C" int ralf_attention_decode(const float* q, int ldq, const float* k, const float* v, long long kv_bstride,
-                                     int ldk, const unsigned char* key_padding_mask, int mask_ld, int Tk, int B, int H,
-                                     int head_dim, float scale, void* out_split, long long out_plane, int ldo,
-                                     void* stream) {
+static int attention_decode_impl(const float* q, int ldq, const float* k, const float* v, long long kv_bstride, int ldk,
+                                 const unsigned char* key_padding_mask, int mask_ld, int Tk, int B, int H, int head_dim,
+                                 float scale, void* out_split, long long out_plane, int ldo, const float* knew,
+                                 const float* vnew, int ldnew, float* kc_w, float* vc_w, void* stream) {
   if (!q || !k || !v || !out_split) return RALF_ERR_NULL;
   if (B <= 0 || H <= 0 || Tk <= 0 || Tk > 2048 || (head_dim != 32 && head_dim != 64)) return RALF_ERR_SHAPE;
   if ((ldq & 3) || (ldk & 3)) return RALF_ERR_ALIGN;
@@ -645,12 +668,31 @@ extern "C" int ralf_attention_decode(const float* q, int ldq, const float* k, co
   if (head_dim == 32)
     attention_decode_kernel<32><<<grid, warps * 32, smem, ST(stream)>>>(q, ldq, k, v, kv_bstride, ldk, key_padding_mask,
                                                                        mask_ld, Tk, B, H, scale, BF(out_split),
-                                                                       out_plane, ldo);
+                                                                       out_plane, ldo, knew, vnew, ldnew, kc_w, vc_w);
   else
     attention_decode_kernel<64><<<grid, warps * 32, smem, ST(stream)>>>(q, ldq, k, v, kv_bstride, ldk, key_padding_mask,
                                                                        mask_ld, Tk, B, H, scale, BF(out_split),
-                                                                       out_plane, ldo);
+                                                                       out_plane, ldo, knew, vnew, ldnew, kc_w, vc_w);
   return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_attention_decode(const float* q, int ldq, const float* k, const float* v, long long kv_bstride,
+                                     int ldk, const unsigned char* key_padding_mask, int mask_ld, int Tk, int B, int H,
+                                     int head_dim, float scale, void* out_split, long long out_plane, int ldo,
+                                     void* stream) {
+  return attention_decode_impl(q, ldq, k, v, kv_bstride, ldk, key_padding_mask, mask_ld, Tk, B, H, head_dim, scale,
+                               out_split, out_plane, ldo, nullptr, nullptr, 0, nullptr, nullptr, stream);
+}
+
+extern "C" int ralf_attention_decode_append(const float* qkv, int ldqkv, float* kcache, float* vcache, int S, int pos,
+                                            const unsigned char* key_padding_mask, int mask_ld, int B, int H,
+                                            int head_dim, float scale, void* out_split, long long out_plane, int ldo,
+                                            void* stream) {
+  if (!qkv || !kcache || !vcache) return RALF_ERR_NULL;
+  if (pos < 0 || pos >= S) return RALF_ERR_SHAPE;
+  const int Dm = H * head_dim;
+  return attention_decode_impl(qkv, ldqkv, kcache, vcache, S, Dm, key_padding_mask, mask_ld, pos + 1, B, H, head_dim,
+                               scale, out_split, out_plane, ldo, qkv + Dm, qkv + 2 * Dm, ldqkv, kcache, vcache, stream);
 }
 
 extern "C" int ralf_stem_im2col(const float* img, int B, int H, int W, int KP, void* out, long long out_plane,

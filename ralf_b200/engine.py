@@ -407,9 +407,7 @@ class Engine:
                 p = f"decoder.transformer.layers.{i}"
                 _, h = self._ln(x, p + ".norm1")
                 qkv, _ = self._gemm(h, p + ".qkv")
-                ops.kv_append(qkv, kc[i], vc[i], t)
-                a = ops.attention_decode(qkv, kc[i].view(B * steps, D), vc[i].view(B * steps, D), steps, t + 1, B,
-                                         NHEAD, 32, mask=pad_mask)
+                a = ops.attention_decode_append(qkv, kc[i], vc[i], t, B, NHEAD, 32, mask=pad_mask)
                 self._gemm(a, p + ".o", res=x, out_f32=x)
                 _, h = self._ln(x, p + ".norm2")
                 q, _ = self._gemm(h, p + ".cq")

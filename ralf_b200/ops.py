@@ -202,6 +202,19 @@ def attention_decode(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, kv_bstri
     return out
 
 
+def attention_decode_append(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, pos: int, B: int, H: int,
+                            dh: int, *, mask: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
+    """Self-attention decode step: append K/V (columns [D,3D) of qkv) at `pos`, attend over keys 0..pos."""
+    if out is None:
+        out = _split_out(B, H * dh, qkv.device)
+    check(_lib.lib().ralf_attention_decode_append(qkv.data_ptr(), qkv.stride(0), kcache.data_ptr(), vcache.data_ptr(),
+                                                  kcache.shape[1], pos, _ptr(mask),
+                                                  mask.stride(0) if mask is not None else 0, B, H, dh, dh ** -0.5,
+                                                  out.data_ptr(), out.stride(0), H * dh, _stream()),
+          "ralf_attention_decode_append")
+    return out
+
+
 def stem_im2col(img: torch.Tensor, KP: int = 200):
     B, C, H, W = img.shape
     assert C == 4 and img.is_contiguous() and img.dtype == torch.float32

@@ -23,6 +23,7 @@ def _ref(a, w, bias=None, act=None, res=None, post_relu=False):
 @pytest.mark.parametrize("M,N,K,bn", [
     (128, 64, 64, 64), (128, 128, 256, 128), (300, 768, 256, 0), (1000, 1024, 256, 0), (77, 519, 256, 0),
     (256, 256, 1024, 64), (4096, 256, 2304, 0), (130, 256, 200, 64), (4, 256, 256, 0), (513, 3072, 256, 256),
+    (128, 256, 256, 32), (128, 1024, 256, 32), (100, 519, 256, 32), (40000, 256, 128, 128), (33000, 64, 576, 64),
 ])
 def test_gemm_bf16x3_matches_fp64(cuda_device, M, N, K, bn):
     from ralf_b200 import ops
