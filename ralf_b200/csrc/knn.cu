@@ -100,32 +100,73 @@ __device__ __forceinline__ void bitonic_desc(uint64_t (&x)[NS], const int lane) 
   }
 }
 
-// Warp-cooperative compaction round.  Each lane owns one query list (cnt entries, unsorted, in shared memory
-// at lists + lane*STRIDE).  For every list longer than C the whole warp sorts it (bitonic network in registers),
-// keeps the best C and publishes the new threshold (score of rank C-1) to the owning lane.  Lists with
-// <= C entries are left alone (their threshold stays, any new score still passes).
+// One key per lane: bitonic sort (descending) of 32 keys across the warp.
+__device__ __forceinline__ uint64_t warp_sort32_desc(uint64_t x, const int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const uint64_t o = __shfl_xor_sync(0xffffffffu, x, j);
+      const bool keep_max = (((lane & k) == 0) == ((lane & j) == 0));
+      x = keep_max ? (x > o ? x : o) : (x < o ? x : o);
+    }
+  }
+  return x;
+}
+// a, b sorted descending (one key per lane each) -> the 32 largest of the 64, sorted descending.
+__device__ __forceinline__ uint64_t warp_merge_top32(uint64_t a, uint64_t b, const int lane) {
+  const uint64_t rb = __shfl_sync(0xffffffffu, b, 31 - lane);
+  uint64_t c = a > rb ? a : rb;  // bitonic sequence holding the top half
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+    const uint64_t o = __shfl_xor_sync(0xffffffffu, c, j);
+    c = ((lane & j) == 0) ? (c > o ? c : o) : (c < o ? c : o);
+  }
+  return c;
+}
+
+// Warp-cooperative compaction round.  Each lane owns one query list (cnt entries in shared memory at
+// lists + lane*STRIDE).  For every list longer than C the whole warp reduces it to its best C entries and
+// publishes the new threshold (score of rank C-1) to the owning lane; shorter lists are left alone (their
+// threshold stays, any new score still passes).
+//   C == 32: the first 32 entries stay sorted between rounds (`sorted` flag per list), so a round sorts only
+//            the <= 32 appended keys (15 compare-exchange steps) and merges (1 + 5 steps);
+//   C == 64: full bitonic sort of the 128-slot list.
 template <int C>
-__device__ __forceinline__ void knn_compact_round(uint64_t* lists, const int lane, int& cnt, float& thr) {
+__device__ __forceinline__ void knn_compact_round(uint64_t* lists, const int lane, int& cnt, float& thr, int& sorted) {
   using Cfg = KnnCfg<C>;
-  constexpr int NS = Cfg::NS;
 #pragma unroll 1
   for (int ql = 0; ql < 32; ++ql) {
     const int n = __shfl_sync(0xffffffffu, cnt, ql);
     if (n <= C) continue;  // warp-uniform
     uint64_t* col = lists + ql * Cfg::STRIDE;
-    uint64_t x[NS];
+    uint64_t kth;
+    if constexpr (C == 32) {
+      const int was_sorted = __shfl_sync(0xffffffffu, sorted, ql);
+      uint64_t a = col[lane];
+      uint64_t b = (32 + lane < n) ? col[32 + lane] : 0ull;
+      if (!was_sorted) a = warp_sort32_desc(a, lane);
+      b = warp_sort32_desc(b, lane);
+      a = warp_merge_top32(a, b, lane);
+      col[lane] = a;
+      kth = __shfl_sync(0xffffffffu, a, 31);
+    } else {
+      constexpr int NS = Cfg::NS;
+      uint64_t x[NS];
 #pragma unroll
-    for (int sl = 0; sl < NS; ++sl) {
-      const int e = lane + 32 * sl;
-      x[sl] = (e < n && e < Cfg::CAP) ? col[e] : 0ull;
+      for (int sl = 0; sl < NS; ++sl) {
+        const int e = lane + 32 * sl;
+        x[sl] = (e < n && e < Cfg::CAP) ? col[e] : 0ull;
+      }
+      bitonic_desc<NS>(x, lane);
+#pragma unroll
+      for (int sl = 0; sl < C / 32; ++sl) col[lane + 32 * sl] = x[sl];
+      kth = __shfl_sync(0xffffffffu, x[(C - 1) >> 5], (C - 1) & 31);
     }
-    bitonic_desc<NS>(x, lane);
-#pragma unroll
-    for (int sl = 0; sl < C / 32; ++sl) col[lane + 32 * sl] = x[sl];
-    const uint64_t kth = __shfl_sync(0xffffffffu, x[(C - 1) >> 5], (C - 1) & 31);
     if (lane == ql) {
       cnt = C;
       thr = knn_key_score(kth);
+      sorted = 1;
     }
     __syncwarp();
   }
@@ -232,7 +273,7 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const bool active = (qtile * 128 + ql) < nq;
     uint64_t* lists = cand_s + static_cast<size_t>(quad) * 32 * Cfg::STRIDE;  // this warp's 32 query lists
     uint64_t* mine = lists + lane * Cfg::STRIDE;
-    int cnt = 0;
+    int cnt = 0, sorted = 0;
     float thr = -INFINITY;
     int it = 0;
     for (int t = t_begin; t < t_end; ++t, ++it) {
@@ -244,7 +285,7 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t tacc = tmem_base + buf * 256 + (static_cast<uint32_t>(quad * 32) << 16);
 #pragma unroll 1
       for (int c0 = 0; c0 < ncols; c0 += 16) {
-        if (__any_sync(0xffffffffu, cnt > Cfg::CAP - 16)) knn_compact_round<C>(lists, lane, cnt, thr);
+        if (__any_sync(0xffffffffu, cnt > Cfg::CAP - 16)) knn_compact_round<C>(lists, lane, cnt, thr, sorted);
         uint32_t v[16];
         tmem_ld_32x16(tacc + c0, v);
         tmem_ld_wait();
@@ -264,7 +305,7 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_arrive(&tempty_bar[buf]);
     }
     __syncwarp();
-    knn_compact_round<C>(lists, lane, cnt, thr);  // trims every list to <= C entries
+    knn_compact_round<C>(lists, lane, cnt, thr, sorted);  // trims every list to <= C entries
     // candidate lists: [qtile][cta][query lane][C]; unused slots are 0 (= empty)
     uint64_t* out_w = cand + ((static_cast<size_t>(qtile) * gridDim.x + blockIdx.x) * 128 + quad * 32) * C;
 #pragma unroll 1

@@ -183,80 +183,81 @@ attention_decode_kernel(const float* __restrict__ q, int ldq, const float* k /* 
                         __nv_bfloat16* __restrict__ out_split, long long out_plane, int ldo,
                         const float* __restrict__ knew, const float* __restrict__ vnew, int ldnew,
                         float* kc_w, float* vc_w) {
-  // Lane mapping: CPL = DH/4 lanes cover one key row (16 B each), KPI = 32/CPL keys per warp iteration, so
-  // every warp-wide LDG.128 reads KPI full, contiguous 128/256-byte rows (100 % sector efficiency).
+  // One CTA (4 warps) per (batch, head); each warp owns a contiguous quarter of the keys (flash-decoding split),
+  // partial (max, sum, o) are combined through shared memory.  Lane mapping inside a warp: CPL = DH/4 lanes cover
+  // one key row (16 B each), KPI = 32/CPL keys per iteration, 8 iterations in flight -> every warp-wide LDG.128
+  // reads KPI full contiguous rows and ~4 KB per warp are outstanding (the cross-attention K/V stream is HBM bound).
   constexpr int CPL = DH / 4;
   constexpr int KPI = 32 / CPL;
-  extern __shared__ float probs[];  // [warps][Tk_pad]
+  constexpr int UN = 8;
+  extern __shared__ float probs[];  // [Tk_pad]
+  __shared__ float red_m[4], red_l[4];
+  __shared__ float red_o[4][DH];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bh = blockIdx.x * (blockDim.x >> 5) + wid;
-  if (bh >= B * H) return;
+  const int bh = blockIdx.x;
   const int b = bh / H, h = bh - b * H;
-  const int tk_pad = (Tk + 31) & ~31;
-  float* pr = probs + wid * tk_pad;
   const int kk = lane / CPL, c = lane % CPL;
   if (knew) {  // append this step's K/V row (position Tk-1) to the cache before attending over it
-    const long long dst = (static_cast<long long>(b) * kv_bstride + (Tk - 1)) * ldk + h * DH;
-    for (int i = lane; i < DH; i += 32) {
-      kc_w[dst + i] = knew[static_cast<long long>(b) * ldnew + h * DH + i];
-      vc_w[dst + i] = vnew[static_cast<long long>(b) * ldnew + h * DH + i];
+    if (threadIdx.x < DH) {
+      const long long dst = (static_cast<long long>(b) * kv_bstride + (Tk - 1)) * ldk + h * DH + threadIdx.x;
+      kc_w[dst] = knew[static_cast<long long>(b) * ldnew + h * DH + threadIdx.x];
+      vc_w[dst] = vnew[static_cast<long long>(b) * ldnew + h * DH + threadIdx.x];
     }
-    __syncwarp();
+    __syncthreads();
   }
+  const int seg = (((Tk + 3) / 4) + KPI - 1) / KPI * KPI;  // keys per warp, multiple of KPI
+  const int j_lo = wid * seg, j_hi = min(Tk, j_lo + seg);
   float4 q4 = *reinterpret_cast<const float4*>(q + static_cast<long long>(b) * ldq + h * DH + 4 * c);
   q4.x *= scale; q4.y *= scale; q4.z *= scale; q4.w *= scale;
   const float* kb = k + static_cast<long long>(b) * kv_bstride * ldk + h * DH + 4 * c;
   const float* vb = v + static_cast<long long>(b) * kv_bstride * ldk + h * DH + 4 * c;
-  // scores
-  for (int j0 = 0; j0 < Tk; j0 += KPI * 4) {
-    float part[4];
+  float lmax = -INFINITY;
+  for (int j0 = j_lo; j0 < j_hi; j0 += KPI * UN) {
+    float part[UN];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < UN; ++u) {
       const int j = j0 + u * KPI + kk;
       float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (j < Tk) f = *reinterpret_cast<const float4*>(kb + static_cast<long long>(j) * ldk);
+      if (j < j_hi) f = *reinterpret_cast<const float4*>(kb + static_cast<long long>(j) * ldk);
       part[u] = q4.x * f.x + q4.y * f.y + q4.z * f.z + q4.w * f.w;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < UN; ++u) {
 #pragma unroll
       for (int off = CPL >> 1; off >= 1; off >>= 1) part[u] += __shfl_xor_sync(0xffffffffu, part[u], off);
       const int j = j0 + u * KPI + kk;
-      if (c == 0 && j < Tk) pr[j] = (mask && mask[static_cast<long long>(b) * mask_ld + j]) ? -INFINITY : part[u];
+      if (j < j_hi) {
+        const float sc = (mask && mask[static_cast<long long>(b) * mask_ld + j]) ? -INFINITY : part[u];
+        if (c == 0) probs[j] = sc;
+        lmax = fmaxf(lmax, sc);
+      }
     }
   }
-  __syncwarp();
-  float lmax = -INFINITY;
-  for (int j = lane; j < Tk; j += 32) lmax = fmaxf(lmax, pr[j]);
   lmax = warp_max(lmax);
-  float lsum = 0.f;
-  for (int j = lane; j < Tk; j += 32) {
-    const float p = __expf(pr[j] - lmax);
-    pr[j] = p;
-    lsum += p;
-  }
-  lsum = warp_sum(lsum);
-  __syncwarp();
-  const float inv = 1.f / lsum;
-  // o[4c..4c+3] over this lane's keys (j = kk mod KPI), then reduce across the KPI key groups
+  if (lane == 0) red_m[wid] = lmax;
+  __syncthreads();
+  const float gmax = fmaxf(fmaxf(red_m[0], red_m[1]), fmaxf(red_m[2], red_m[3]));
+  // o[4c..4c+3] over this lane's keys, exponentials computed once per key (lanes of a key share it)
   float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int j0 = 0; j0 < Tk; j0 += KPI * 4) {
-    float4 f[4];
-    float p[4];
+  float lsum = 0.f;
+  for (int j0 = j_lo; j0 < j_hi; j0 += KPI * UN) {
+    float4 f[UN];
+    float pj[UN];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < UN; ++u) {
       const int j = j0 + u * KPI + kk;
       f[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      p[u] = 0.f;
-      if (j < Tk) {
+      pj[u] = 0.f;
+      if (j < j_hi) {
         f[u] = *reinterpret_cast<const float4*>(vb + static_cast<long long>(j) * ldk);
-        p[u] = pr[j];
+        pj[u] = __expf(probs[j] - gmax);
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      o.x = fmaf(p[u], f[u].x, o.x); o.y = fmaf(p[u], f[u].y, o.y);
-      o.z = fmaf(p[u], f[u].z, o.z); o.w = fmaf(p[u], f[u].w, o.w);
+    for (int u = 0; u < UN; ++u) {
+      o.x = fmaf(pj[u], f[u].x, o.x); o.y = fmaf(pj[u], f[u].y, o.y);
+      o.z = fmaf(pj[u], f[u].z, o.z); o.w = fmaf(pj[u], f[u].w, o.w);
+      if (c == 0) lsum += pj[u];
     }
   }
 #pragma unroll
@@ -264,12 +265,17 @@ attention_decode_kernel(const float* __restrict__ q, int ldq, const float* k /* 
     o.x += __shfl_xor_sync(0xffffffffu, o.x, off); o.y += __shfl_xor_sync(0xffffffffu, o.y, off);
     o.z += __shfl_xor_sync(0xffffffffu, o.z, off); o.w += __shfl_xor_sync(0xffffffffu, o.w, off);
   }
+  lsum = warp_sum(lsum);
   if (kk == 0) {
-    const long long orow = static_cast<long long>(b) * ldo + h * DH + 4 * c;
-    store_split(out_split, out_plane, orow + 0, o.x * inv);
-    store_split(out_split, out_plane, orow + 1, o.y * inv);
-    store_split(out_split, out_plane, orow + 2, o.z * inv);
-    store_split(out_split, out_plane, orow + 3, o.w * inv);
+    red_o[wid][4 * c + 0] = o.x; red_o[wid][4 * c + 1] = o.y;
+    red_o[wid][4 * c + 2] = o.z; red_o[wid][4 * c + 3] = o.w;
+  }
+  if (lane == 0) red_l[wid] = lsum;
+  __syncthreads();
+  if (threadIdx.x < DH) {
+    const float inv = 1.f / (red_l[0] + red_l[1] + red_l[2] + red_l[3]);
+    const float y = (red_o[0][threadIdx.x] + red_o[1][threadIdx.x] + red_o[2][threadIdx.x] + red_o[3][threadIdx.x]) * inv;
+    store_split(out_split, out_plane, static_cast<long long>(b) * ldo + h * DH + threadIdx.x, y);
   }
 }
 
@@ -662,9 +668,9 @@ static int attention_decode_impl(const float* q, int ldq, const float* k, const 
   if (!q || !k || !v || !out_split) return RALF_ERR_NULL;
   if (B <= 0 || H <= 0 || Tk <= 0 || Tk > 2048 || (head_dim != 32 && head_dim != 64)) return RALF_ERR_SHAPE;
   if ((ldq & 3) || (ldk & 3)) return RALF_ERR_ALIGN;
+  const size_t smem = static_cast<size_t>((Tk + 31) & ~31) * sizeof(float);
+  const int grid = B * H;
   const int warps = 4;
-  const size_t smem = static_cast<size_t>(warps) * ((Tk + 31) & ~31) * sizeof(float);
-  const int grid = (B * H + warps - 1) / warps;
   if (head_dim == 32)
     attention_decode_kernel<32><<<grid, warps * 32, smem, ST(stream)>>>(q, ldq, k, v, kv_bstride, ldk, key_padding_mask,
                                                                        mask_ld, Tk, B, H, scale, BF(out_split),
