@@ -181,6 +181,65 @@ int ralf_ce_label_smooth(const float* logits, int ldl, const long long* targets,
 /* Append this step's K,V (columns [D,3D) of the fused QKV row) to the self-attention cache [B,S,D]. */
 int ralf_kv_append(const float* qkv, int B, int D, float* kcache, float* vcache, int S, int pos, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * K4. Training step (train.py:431-459): backward of the ops above, BatchNorm in training mode, and the
+ * optimizer.  The backward contractions dX = dY.W and dW = dY^T.X reuse ralf_gemm on K-major operands
+ * produced by ralf_to_split / ralf_transpose_to_split.  csrc/train_kernels.cu, csrc/conv_train_kernels.cu.
+ * ------------------------------------------------------------------------------------------- */
+/* [R, C] fp32 or split -> split [C, R] with row pitch ld_out (>= R, multiple of 8). */
+int ralf_transpose_to_split(const float* in_f32, const void* in_split, long long in_plane, long long ld_in, int R,
+                            int C, void* out, long long out_plane, long long ld_out, void* stream);
+int ralf_to_split(const float* in, long long total, void* out, long long out_plane, void* stream);
+/* out[c] (+)= sum_r in[r, c]  (bias gradients; deterministic order). */
+int ralf_colsum(const float* in, long long ld, int M, int C, float* out, int accumulate, void* stream);
+/* nn.LayerNorm backward; dx = add_to + dLN; workspace = 2*D*min(ceil(M/8), 4*SMs) floats. */
+int ralf_layernorm_bwd(const float* x, long long x_ld, const float* dy, const float* gamma, float eps, int M, int D,
+                       const float* add_to, float* dx, float* dgamma, float* dbeta, float* workspace, void* stream);
+/* Backward of ralf_attention (same addressing); lse_ws / delta_ws: B*H*Tq floats each. */
+int ralf_attention_bwd(const float* q, int ldq, const float* k, const float* v, int ldk,
+                       const unsigned char* key_padding_mask, int B, int H, int Tq, int Tk, int head_dim, int causal,
+                       float scale, const void* o_split, long long o_plane, const float* dO, int ldo, float* lse_ws,
+                       float* delta_ws, float* dq, int lddq, float* dk, float* dv, int lddk, void* stream);
+/* dlogits of ralf_ce_label_smooth (fwd_workspace = the forward's workspace), scaled by `scale`. */
+int ralf_ce_label_smooth_bwd(const float* logits, int ldl, const long long* targets, int M, int V, float eps,
+                             long long ignore_index, const float* fwd_workspace, float scale, float* dlogits, int ldd,
+                             void* stream);
+int ralf_relu_bwd(float* dy, const void* y_split_hi, long long total, void* stream);
+int ralf_gelu_fwd(const float* z, long long total, void* out_split, long long out_plane, void* stream);
+int ralf_gelu_bwd(float* dy, const float* z, long long total, void* stream);
+int ralf_axpy(float* a, const float* b, float alpha, long long total, void* stream);
+/* dst[r,:] (+)= scale * src[map(r),:] -- backward of ralf_rows_affine / concatenations. */
+int ralf_rows_gather(const float* src, long long src_ld, int M, int D, float scale, int rows_per_group,
+                     int group_stride, int group_offset, float* dst, int accumulate, void* stream);
+int ralf_embed_bwd(const long long* tok, long long tok_ld, int tok_col, int B, int S, const float* dy, int D,
+                   float scale, float* demb, void* stream);
+/* torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW over flat buffers (train.py:450-454). */
+int ralf_grad_norm(const float* grads, long long n, float* workspace /* 1024 floats */, float* out_norm, void* stream);
+int ralf_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                    const float* grad_norm, float max_norm, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, int step, void* stream);
+/* BatchNorm2d in training mode on NHWC rows [M, C]: mode 0 = batch mean / rstd (+ running-stat update),
+ * mode 1 = (sum a, sum a*xhat) for the backward; workspace = 2*C*ceil(M/2048) floats. */
+int ralf_bn_colstats(const float* a, const float* z, const float* mean, const float* rstd, int mode, int M, int C,
+                     float eps, float momentum, float* out0, float* out1, float* running_mean, float* running_var,
+                     float* workspace, void* stream);
+int ralf_bn_apply(const float* z, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                  const void* res_split, long long res_plane, int relu, int M, int C, void* out_split,
+                  long long out_plane, float* out_f32, void* stream);
+int ralf_bn_bwd_apply(const float* dy, const float* z, const float* mean, const float* rstd, const float* gamma,
+                      const float* sum_dy, const float* sum_dy_xhat, int M, int C, float* dz, void* stream);
+/* Backward data movement of the convolutions / pooling / FPN upsample. */
+int ralf_col2im(const float* dcol, int B, int H, int W, int C, int KH, int KW, int stride, int pad, float* dx,
+                int accumulate, void* stream);
+int ralf_maxpool3x3s2_bwd(const void* x_split, long long x_plane, const float* dy, int B, int H, int W, int C,
+                          float* dx_zeroed, void* stream);
+int ralf_upsample_nearest_bwd(const float* dbig, long long ld_big, int B, int h5, int w5, int h4, int w4, int C,
+                              float* dsmall, void* stream);
+/* nn.Conv2d weight [N, C, T] <-> GEMM layout [N, T*C] (split, plus transposed copy) and gradient back. */
+int ralf_conv_weight_to_gemm(const float* w, int N, int C, int T, int Kp, void* out, long long out_plane, void* outT,
+                             long long outT_plane, int Np, void* stream);
+int ralf_conv_grad_from_gemm(const float* dwg, int N, int C, int T, int ldg, float* dw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -95,7 +95,13 @@ def _pe1d(sd, p, x):
 # ---------------------------------------------------------------------------------------------------
 # image encoder
 # ---------------------------------------------------------------------------------------------------
+BN_TRAIN = False  # tests of the training step set this: BatchNorm2d batch statistics (model.train())
+
+
 def _bn(sd, p, x):
+    if BN_TRAIN:
+        return F.batch_norm(x, sd[p + ".running_mean"].clone(), sd[p + ".running_var"].clone(), sd[p + ".weight"],
+                            sd[p + ".bias"], True, 0.1, 1e-5)
     return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
                         False, 0.0, 1e-5)
 

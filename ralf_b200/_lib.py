@@ -79,6 +79,28 @@ def lib() -> C.CDLL:
         L.ralf_kv_append.argtypes = [vp, i, i, vp, vp, i, i, vp]
         L.ralf_gather_layouts.argtypes = [vp, vp, i, i, ll, ll, vp, vp]
         L.ralf_fid_embed_packed.argtypes = [vp, i, i, i, vp, vp, vp, i, vp, ll, vp, vp]
+        L.ralf_transpose_to_split.argtypes = [vp, vp, ll, ll, i, i, vp, ll, ll, vp]
+        L.ralf_to_split.argtypes = [vp, ll, vp, ll, vp]
+        L.ralf_colsum.argtypes = [vp, ll, i, i, vp, i, vp]
+        L.ralf_layernorm_bwd.argtypes = [vp, ll, vp, vp, f, i, i, vp, vp, vp, vp, vp, vp]
+        L.ralf_attention_bwd.argtypes = [vp, i, vp, vp, i, vp, i, i, i, i, i, i, f, vp, ll, vp, i, vp, vp, vp, i, vp, vp, i, vp]
+        L.ralf_ce_label_smooth_bwd.argtypes = [vp, i, vp, i, i, f, ll, vp, f, vp, i, vp]
+        L.ralf_relu_bwd.argtypes = [vp, vp, ll, vp]
+        L.ralf_gelu_fwd.argtypes = [vp, ll, vp, ll, vp]
+        L.ralf_gelu_bwd.argtypes = [vp, vp, ll, vp]
+        L.ralf_axpy.argtypes = [vp, vp, f, ll, vp]
+        L.ralf_rows_gather.argtypes = [vp, ll, i, i, f, i, i, i, vp, i, vp]
+        L.ralf_embed_bwd.argtypes = [vp, ll, i, i, i, vp, i, f, vp, vp]
+        L.ralf_grad_norm.argtypes = [vp, ll, vp, vp, vp]
+        L.ralf_adamw_step.argtypes = [vp, vp, vp, vp, ll, vp, f, f, f, f, f, f, i, vp]
+        L.ralf_bn_colstats.argtypes = [vp, vp, vp, vp, i, i, i, f, f, vp, vp, vp, vp, vp, vp]
+        L.ralf_bn_apply.argtypes = [vp, vp, vp, vp, vp, vp, ll, i, i, i, vp, ll, vp, vp]
+        L.ralf_bn_bwd_apply.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, vp, vp]
+        L.ralf_col2im.argtypes = [vp, i, i, i, i, i, i, i, i, vp, i, vp]
+        L.ralf_maxpool3x3s2_bwd.argtypes = [vp, ll, vp, i, i, i, i, vp, vp]
+        L.ralf_upsample_nearest_bwd.argtypes = [vp, ll, i, i, i, i, i, i, vp, vp]
+        L.ralf_conv_weight_to_gemm.argtypes = [vp, i, i, i, i, vp, ll, vp, ll, i, vp]
+        L.ralf_conv_grad_from_gemm.argtypes = [vp, i, i, i, i, vp, vp]
         L.ralf_ce_label_smooth.argtypes = [vp, i, vp, i, i, f, ll, vp, vp, vp]
         _lib = L
     return _lib

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(128)
 attn_bwd_dq_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, const float* __restrict__ v, int ldk,
                    const unsigned char* __restrict__ mask, int Tq, int Tk, int causal, float scale,
                    const __nv_bfloat16* __restrict__ o_split, long long o_plane, const float* __restrict__ dO, int ldo,
-                   const float* __restrict__ lse, float* __restrict__ delta, float* __restrict__ dq, int lddq) {
+                   float* __restrict__ lse, float* __restrict__ delta, float* __restrict__ dq, int lddq) {
   constexpr int KT = 64;
   __shared__ __align__(16) float ks[KT][DH];
   __shared__ __align__(16) float vs[KT][DH];
@@ -170,10 +170,38 @@ attn_bwd_dq_kernel(const float* __restrict__ q, int ldq, const float* __restrict
       dl = fmaf(dor[i], t_load_split(o_split, o_plane, qrow * ldo + h * DH + i), dl);
       acc[i] = 0.f;
     }
-    my_lse = lse[(static_cast<long long>(b) * H + h) * Tq + t];
     delta[(static_cast<long long>(b) * H + h) * Tq + t] = dl;
   }
   const int kmax = causal ? min(Tk, (blockIdx.x + 1) * static_cast<int>(blockDim.x)) : Tk;
+  // pass 0: log-sum-exp of this query's scores (recomputed here so the forward kernel need not save it)
+  {
+    float mrun = -INFINITY, lrun = 0.f;
+    for (int j0 = 0; j0 < kmax; j0 += KT) {
+      __syncthreads();
+      const int nk = min(KT, Tk - j0);
+      for (int i = threadIdx.x; i < KT * (DH / 4); i += blockDim.x) {
+        const int r = i / (DH / 4), c = (i % (DH / 4)) * 4;
+        float4 fk = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nk) fk = *reinterpret_cast<const float4*>(k + (static_cast<long long>(b) * Tk + j0 + r) * ldk + h * DH + c);
+        *reinterpret_cast<float4*>(&ks[r][c]) = fk;
+      }
+      for (int i = threadIdx.x; i < KT; i += blockDim.x)
+        ms[i] = (i < nk) ? (mask ? mask[static_cast<long long>(b) * Tk + j0 + i] : 0) : 1;
+      __syncthreads();
+      if (!active) continue;
+      for (int j = 0; j < nk; ++j) {
+        if (ms[j] || (causal && (j0 + j) > t)) continue;
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < DH; ++i) s = fmaf(qr[i], ks[j][i], s);
+        const float mnew = fmaxf(mrun, s);
+        lrun = lrun * __expf(mrun - mnew) + __expf(s - mnew);
+        mrun = mnew;
+      }
+    }
+    my_lse = mrun + __logf(lrun);
+    if (active) lse[(static_cast<long long>(b) * H + h) * Tq + t] = my_lse;
+  }
   for (int j0 = 0; j0 < kmax; j0 += KT) {
     __syncthreads();
     const int nk = min(KT, Tk - j0);
@@ -375,6 +403,63 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   }
 }
 
+
+// dy *= (y > 0) in place (ReLU backward; y = saved post-activation, split hi plane sign is enough)
+__global__ void relu_bwd_kernel(float* __restrict__ dy, const __nv_bfloat16* __restrict__ y_hi, long long total) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    if (!(__bfloat162float(y_hi[i]) > 0.f)) dy[i] = 0.f;
+}
+// GELU (erf) forward on fp32 pre-activations -> split; backward dz = dy * gelu'(z) in place.
+__global__ void gelu_fwd_kernel(const float* __restrict__ z, long long total, __nv_bfloat16* __restrict__ out,
+                                long long plane) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float x = z[i];
+    t_store_split(out, plane, i, 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)));
+  }
+}
+__global__ void gelu_bwd_kernel(float* __restrict__ dy, const float* __restrict__ z, long long total) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float x = z[i];
+    const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+    dy[i] *= cdf + x * pdf;
+  }
+}
+// a += alpha * b
+__global__ void axpy_kernel(float* __restrict__ a, const float* __restrict__ b, float alpha, long long total) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    a[i] = fmaf(alpha, b[i], a[i]);
+}
+// Backward of rows_affine / concatenation: dst[r, :] (+)= scale * src[map(r), :],  map(r) = (r/rpg)*gs + go + r%rpg
+__global__ void rows_gather_kernel(const float* __restrict__ src, long long src_ld, int M, int D, float scale, int rpg,
+                                   int gs, int go, float* __restrict__ dst, int accumulate) {
+  const long long total = static_cast<long long>(M) * D;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % D);
+    const int r = static_cast<int>(i / D);
+    const long long srow = static_cast<long long>(r / rpg) * gs + go + r % rpg;
+    const float v = scale * src[srow * src_ld + c];
+    dst[i] = accumulate ? dst[i] + v : v;
+  }
+}
+// Embedding backward: demb[tok[r], :] += scale * dy[r, :]   (atomic scatter-add)
+__global__ void embed_bwd_kernel(const long long* __restrict__ tok, long long tok_ld, int tok_col, int Bn, int S,
+                                 const float* __restrict__ dy, int D, float scale, float* __restrict__ demb) {
+  const long long total = static_cast<long long>(Bn) * S * D;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % D);
+    const long long r = i / D;
+    const long long t = tok[(r / S) * tok_ld + tok_col + (r % S)];
+    atomicAdd(&demb[t * D + c], scale * dy[i]);
+  }
+}
+
 static inline int t_grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = static_cast<long long>(num_sms()) * 16;
@@ -462,8 +547,9 @@ extern "C" int ralf_adamw_step(float* params, const float* grads, float* exp_avg
 extern "C" int ralf_attention_bwd(const float* q, int ldq, const float* k, const float* v, int ldk,
                                   const unsigned char* key_padding_mask, int B, int H, int Tq, int Tk, int head_dim,
                                   int causal, float scale, const void* o_split, long long o_plane, const float* dO,
-                                  int ldo, const float* lse, float* delta_ws, float* dq, int lddq, float* dk, float* dv,
+                                  int ldo, float* lse_ws, float* delta_ws, float* dq, int lddq, float* dk, float* dv,
                                   int lddk, void* stream) {
+  float* lse = lse_ws;
   if (!q || !k || !v || !o_split || !dO || !lse || !delta_ws || !dq || !dk || !dv) return RALF_ERR_NULL;
   if (B <= 0 || H <= 0 || Tq <= 0 || Tk <= 0 || (head_dim != 32 && head_dim != 64)) return RALF_ERR_SHAPE;
   if ((ldq & 3) || (ldk & 3) || (ldo & 3)) return RALF_ERR_ALIGN;
@@ -481,5 +567,48 @@ extern "C" int ralf_attention_bwd(const float* q, int ldq, const float* k, const
     attn_bwd_dkv_kernel<64><<<g2, tk, 0, ST(stream)>>>(q, ldq, k, v, ldk, key_padding_mask, Tq, Tk, causal, scale, dO, ldo,
                                                       lse, delta_ws, dk, dv, lddk);
   }
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_relu_bwd(float* dy, const void* y_split_hi, long long total, void* stream) {
+  if (!dy || !y_split_hi) return RALF_ERR_NULL;
+  if (total <= 0) return RALF_ERR_SHAPE;
+  relu_bwd_kernel<<<t_grid_for(total, 256), 256, 0, ST(stream)>>>(dy, CBF(y_split_hi), total);
+  return set_cuda_error(cudaGetLastError());
+}
+extern "C" int ralf_gelu_fwd(const float* z, long long total, void* out_split, long long out_plane, void* stream) {
+  if (!z || !out_split) return RALF_ERR_NULL;
+  if (total <= 0) return RALF_ERR_SHAPE;
+  gelu_fwd_kernel<<<t_grid_for(total, 256), 256, 0, ST(stream)>>>(z, total, BF(out_split), out_plane);
+  return set_cuda_error(cudaGetLastError());
+}
+extern "C" int ralf_gelu_bwd(float* dy, const float* z, long long total, void* stream) {
+  if (!dy || !z) return RALF_ERR_NULL;
+  if (total <= 0) return RALF_ERR_SHAPE;
+  gelu_bwd_kernel<<<t_grid_for(total, 256), 256, 0, ST(stream)>>>(dy, z, total);
+  return set_cuda_error(cudaGetLastError());
+}
+extern "C" int ralf_axpy(float* a, const float* b, float alpha, long long total, void* stream) {
+  if (!a || !b) return RALF_ERR_NULL;
+  if (total <= 0) return RALF_ERR_SHAPE;
+  axpy_kernel<<<t_grid_for(total, 256), 256, 0, ST(stream)>>>(a, b, alpha, total);
+  return set_cuda_error(cudaGetLastError());
+}
+extern "C" int ralf_rows_gather(const float* src, long long src_ld, int M, int D, float scale, int rows_per_group,
+                                int group_stride, int group_offset, float* dst, int accumulate, void* stream) {
+  if (!src || !dst) return RALF_ERR_NULL;
+  if (M <= 0 || D <= 0) return RALF_ERR_SHAPE;
+  const int rpg = rows_per_group > 0 ? rows_per_group : M;
+  rows_gather_kernel<<<t_grid_for(static_cast<long long>(M) * D, 256), 256, 0, ST(stream)>>>(
+      src, src_ld, M, D, scale, rpg, rows_per_group > 0 ? group_stride : 0, rows_per_group > 0 ? group_offset : 0, dst,
+      accumulate);
+  return set_cuda_error(cudaGetLastError());
+}
+extern "C" int ralf_embed_bwd(const long long* tok, long long tok_ld, int tok_col, int B, int S, const float* dy, int D,
+                              float scale, float* demb, void* stream) {
+  if (!tok || !dy || !demb) return RALF_ERR_NULL;
+  if (B <= 0 || S <= 0 || D <= 0) return RALF_ERR_SHAPE;
+  embed_bwd_kernel<<<t_grid_for(static_cast<long long>(B) * S * D, 256), 256, 0, ST(stream)>>>(tok, tok_ld, tok_col, B, S, dy,
+                                                                                             D, scale, demb);
   return set_cuda_error(cudaGetLastError());
 }

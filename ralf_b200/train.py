@@ -1,0 +1,289 @@
+"""Training step of the RALF model on the ralf_b200 kernels.
+
+Mirrors ``train()`` of the reference (image2layout/train/train.py:431-459): forward (teacher forced) ->
+label-smoothed CE -> backward -> clip_grad_norm_(0.1) -> AdamW (4 parameter groups from
+``BaseModel.optim_groups``, base_model.py:207-347: decay / no-decay x {ResNet body lr*0.1, rest}) ->
+(data parallel) gradient all-reduce over NCCL BEFORE the clip, i.e. what DDP is meant to do -- the reference's
+own wrapper never arms the reducer, we deliberately do the real thing.
+
+Status (round 1): every trainable parameter of the reference trains through the tape in autograd.py -- the
+ResNet50-FPN trunk (BatchNorm in training mode, train_conv.py), image encoder, layout adapter, fusion attention,
+head, constraint encoder, decoder, loss; FIDNetV3 stays frozen like in the reference
+(retrieval_augmented_autoreg.py:150-154).  Not applied yet: dropout (p = 0.1 in the reference's encoder /
+decoder / positional encodings) -- reported by ``TrainEngine.limits`` and in DESIGN.md.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import autograd as ag
+from . import ops
+from .autograd import Node, ParamStore, Tape
+from .engine import D, NHEAD, NLAYER, Engine, _sine_pe_1d
+
+
+def _is_decay(name: str, p: torch.Tensor) -> bool:
+    """base_model.py:207-247: Linear / Conv / MultiheadAttention weights decay; biases, LayerNorm / BatchNorm /
+    Embedding weights do not."""
+    if name.endswith("bias") or p.dim() < 2:
+        return False
+    if "emb" in name.split(".")[-2] if "." in name else False:
+        return False
+    return True
+
+
+class TrainEngine:
+    limits = ("dropout not applied",)
+
+    def __init__(self, model, *, lr: float = 1e-4, weight_decay: float = 1e-4, body_lr_scale: float = 0.1,
+                 max_grad_norm: float = 0.1, world_size: int = 1, process_group=None, train_trunk: bool = True) -> None:
+        self.model = model
+        self.dev = model.device
+        self.lr, self.wd, self.body_scale, self.max_norm = lr, weight_decay, body_lr_scale, max_grad_norm
+        self.world, self.pg = world_size, process_group
+        self.step_count = 0
+        self.infer = Engine(model.state_dict(), self.dev, is_ralf=True, top_k=model.top_k)  # frozen trunk + FIDNet
+        self.train_trunk = train_trunk
+        named = [(n, p) for n, p in model.named_parameters()
+                 if p.requires_grad and (train_trunk or not n.startswith("encoder.extractor"))]
+        # optim_groups(custom_lr={"encoder.extractor.body": lr * 0.1}) -> body decay / body no-decay / decay / no-decay
+        groups = [[], [], [], []]
+        for n, p in named:
+            body = n.startswith("encoder.extractor.body")
+            groups[(0 if body else 2) + (0 if _is_decay(n, p) else 1)].append(n)
+        groups = [sorted(g) for g in groups]
+        self.ps = ParamStore(named, groups, self.dev)
+        self.group_cfg = [(lr * body_lr_scale, weight_decay), (lr * body_lr_scale, 0.0), (lr, weight_decay), (lr, 0.0)]
+        for n, p in named:  # the module's parameters become views of the flat master buffer
+            p.data = self.ps.p(n)
+        self._register_weights()
+        self.trunk = None
+        if train_trunk:
+            from .train_conv import Trunk
+
+            self.trunk = Trunk(self.ps, model, self.dev)
+        self.pe = _sine_pe_1d(5000, D).to(self.dev)
+        self.refresh_operands()
+
+    def refresh_operands(self) -> None:
+        self.ps.refresh_operands()
+        if self.trunk is not None:
+            self.trunk.refresh_operands()
+
+    # ------------------------------------------------------------------------------------------
+    def _register_weights(self) -> None:
+        ps = self.ps
+        reg = ps.register_gemm_weight
+
+        def enc(p):
+            reg(p + ".qkv", p + ".self_attn.in_proj_weight")
+            reg(p + ".o", p + ".self_attn.out_proj.weight")
+            reg(p + ".l1", p + ".linear1.weight")
+            reg(p + ".l2", p + ".linear2.weight")
+
+        for i in range(NLAYER):
+            enc(f"transformer_encoder.layers.{i}")
+            enc(f"user_const_encoder.encoder.layers.{i}")
+            p = f"decoder.transformer.layers.{i}"
+            enc(p)
+            reg(p + ".cq", p + ".multihead_attn.in_proj_weight", 0, D)
+            reg(p + ".ckv", p + ".multihead_attn.in_proj_weight", D, 2 * D)
+            reg(p + ".co", p + ".multihead_attn.out_proj.weight")
+        for n in ("layout_adapter.net.1", "layout_adapter.net.4", "head.net.1", "head.net.4", "attn.to_q", "attn.to_kv",
+                  "attn.to_out.0"):
+            reg(n, n + ".weight")
+        reg("decoder.head.1", "decoder.head.1.weight")
+
+    # ------------------------------------------------------------------------------------------
+    def _enc_layer(self, tape, x: Node, p: str, B: int, T: int, mask=None) -> Node:
+        ps = self.ps
+        h = ag.layernorm(tape, ps, x, p + ".norm1")
+        qkv = ag.linear(tape, ps, h, p + ".qkv", p + ".self_attn.in_proj_bias")
+        a = ag.self_attention(tape, qkv, B, T, NHEAD, D // NHEAD, mask=mask)
+        x1 = ag.linear(tape, ps, a, p + ".o", p + ".self_attn.out_proj.bias", res=x)
+        h = ag.layernorm(tape, ps, x1, p + ".norm2")
+        f = ag.linear(tape, ps, h, p + ".l1", p + ".linear1.bias", act="relu", want_f32=False)
+        return ag.linear(tape, ps, f, p + ".l2", p + ".linear2.bias", res=x1)
+
+    def _ffn_gelu(self, tape, x: Node, p: str) -> Node:
+        """common/attention.py:15-30  LN -> Linear -> GELU -> Linear."""
+        ps = self.ps
+        h = ag.layernorm(tape, ps, x, p + ".net.0")
+        z = ag.linear(tape, ps, h, p + ".net.1", p + ".net.1.bias")
+        g = ag.gelu(tape, z)
+        return ag.linear(tape, ps, g, p + ".net.4", p + ".net.4.bias")
+
+    def _scalar_add_bwd(self, tape, node: Node, pname: str, row: int) -> None:
+        """y = x + task_emb[row] was applied while concatenating; route sum(dy) to the scalar parameter."""
+        ps = self.ps
+
+        def bwd() -> None:
+            if node.grad is None:
+                return
+            cs = torch.empty(node.Cn, dtype=torch.float32, device=self.dev)
+            ag.colsum(node.grad, cs)
+            ag.colsum(cs.view(node.Cn, 1), ps.g(pname).view(-1)[row:row + 1], accumulate=True)
+
+        tape.record(bwd)
+
+    # ------------------------------------------------------------------------------------------
+    def forward_loss(self, inputs: dict, targets: dict):
+        """Teacher-forced forward + loss through the tape.  Returns (loss 0-dim tensor, tape, logits Node)."""
+        ps, dev = self.ps, self.dev
+        tape = Tape()
+        image = inputs["image"].to(dev, torch.float32)
+        B = image.shape[0]
+        K = self.model.top_k
+        # ---- ResNet50-FPN trunk: on the tape (BatchNorm batch statistics), or frozen through the inference kernels ----
+        if self.trunk is not None:
+            x, h, w = self.trunk.forward(tape, image, self.infer.pos2d)
+        else:
+            tokens, h, w = self.infer.resnet_fpn(image)
+            x = Node(B * h * w, D, tokens, None, need_grad=False)
+        T = h * w
+        for i in range(NLAYER):
+            x = self._enc_layer(tape, x, f"transformer_encoder.layers.{i}", B, T)
+        # ---- retrieved layouts: frozen FIDNet CLS features -> trainable adapter ----
+        cls = self._fid_cls(inputs["retrieved"], B)              # fp32 [B*K, 256]
+        ref0 = self._ffn_gelu(tape, Node(B * K, D, cls, None, need_grad=False), "layout_adapter")
+        ref = Node(B * K, D, torch.empty((B * K, D), dtype=torch.float32, device=dev),
+                   torch.empty((2, B * K, D), dtype=torch.bfloat16, device=dev))
+        ops.rows_affine(ref0.f32, B * K, D, scale=math.sqrt(D), table=self.pe, tab_mod=K, out_f32=ref.f32, out_split=ref.s)
+
+        def ref_bwd() -> None:  # d(ref0) = sqrt(d) * d(ref)
+            if ref.grad is None:
+                return
+            g = torch.empty_like(ref0.f32)
+            ag.check(ag._L().ralf_rows_gather(ref.grad.data_ptr(), ref.grad.stride(0), B * K, D, math.sqrt(D), 0, 0, 0,
+                                              g.data_ptr(), 0, ag._stream()), "ralf_rows_gather")
+            ag.accumulate(ref0, g)
+
+        tape.record(ref_bwd)
+        # ---- fusion attention + head over cat[img, ca, ref] ----
+        hq = ag.layernorm(tape, ps, x, "attn.norm")
+        q = ag.linear(tape, ps, hq, "attn.to_q")
+        kv = ag.linear(tape, ps, ref, "attn.to_kv")
+        a = ag.cross_attention(tape, q, kv, 0, 512, B, T, K, 8, 64)
+        ca = ag.linear(tape, ps, a, "attn.to_out.0", "attn.to_out.0.bias")
+        Tcat = 2 * T + K
+        cat = Node(B * Tcat, D, torch.empty((B * Tcat, D), dtype=torch.float32, device=dev), None)
+        ag.place_rows(tape, x, cat.f32, cat, T, Tcat, 0)
+        ag.place_rows(tape, ca, cat.f32, cat, T, Tcat, T)
+        ag.place_rows(tape, ref, cat.f32, cat, K, Tcat, 2 * T)
+        mem_img = self._ffn_gelu(tape, cat, "head")
+        # ---- constraint encoder ----
+        sc = inputs["seq_layout_const"].to(dev).contiguous()
+        Tc = sc.shape[1]
+        uc = ag.embed(tape, ps, sc, Tc, "user_const_encoder.emb.weight", math.sqrt(D), self.pe)
+        m = inputs["seq_layout_const_pad_mask"].to(dev).to(torch.uint8).contiguous()
+        for i in range(NLAYER):
+            uc = self._enc_layer(tape, uc, f"user_const_encoder.encoder.layers.{i}", B, Tc, mask=m)
+        # ---- memory = cat[mem_img + task_emb[0], uc + task_emb[1]] ----
+        Mlen = Tcat + Tc
+        mem = Node(B * Mlen, D, torch.empty((B * Mlen, D), dtype=torch.float32, device=dev),
+                   torch.empty((2, B * Mlen, D), dtype=torch.bfloat16, device=dev))
+        te = ps.p("task_emb.weight").view(-1)
+        tv0 = te[0:1].expand(D).contiguous().view(1, D)
+        tv1 = te[1:2].expand(D).contiguous().view(1, D)
+        ops.rows_affine(mem_img.f32, B * Tcat, D, table=tv0, tab_mod=1, rows_per_group=Tcat, group_stride=Mlen,
+                        group_offset=0, out_f32=mem.f32, out_split=mem.s)
+        ops.rows_affine(uc.f32, B * Tc, D, table=tv1, tab_mod=1, rows_per_group=Tc, group_stride=Mlen,
+                        group_offset=Tcat, out_f32=mem.f32, out_split=mem.s)
+
+        def mem_bwd() -> None:
+            if mem.grad is None:
+                return
+            for src, rpg, go, row in ((mem_img, Tcat, 0, 0), (uc, Tc, Tcat, 1)):
+                g = torch.empty_like(src.f32)
+                ag.check(ag._L().ralf_rows_gather(mem.grad.data_ptr(), mem.grad.stride(0), src.M, D, 1.0, rpg, Mlen, go,
+                                                  g.data_ptr(), 0, ag._stream()), "ralf_rows_gather")
+                cs = torch.empty(D, dtype=torch.float32, device=dev)
+                ag.colsum(g, cs)
+                ag.colsum(cs.view(D, 1), ps.g("task_emb.weight").view(-1)[row:row + 1], accumulate=True)
+                ag.accumulate(src, g)
+
+        tape.record(mem_bwd)
+        # ---- decoder (teacher forced, causal + key padding) ----
+        seq = inputs["seq"].to(dev).contiguous()
+        S = seq.shape[1]
+        pm = inputs["tgt_key_padding_mask"].to(dev).to(torch.uint8).contiguous()
+        y = ag.embed(tape, ps, seq, S, "decoder.emb.weight", math.sqrt(D), self.pe)
+        for i in range(NLAYER):
+            p = f"decoder.transformer.layers.{i}"
+            hh = ag.layernorm(tape, ps, y, p + ".norm1")
+            qkv = ag.linear(tape, ps, hh, p + ".qkv", p + ".self_attn.in_proj_bias")
+            a = ag.self_attention(tape, qkv, B, S, NHEAD, 32, mask=pm, causal=True)
+            y = ag.linear(tape, ps, a, p + ".o", p + ".self_attn.out_proj.bias", res=y)
+            hh = ag.layernorm(tape, ps, y, p + ".norm2")
+            qn = ag.linear(tape, ps, hh, p + ".cq", None)
+            kvn = ag.linear(tape, ps, mem, p + ".ckv", None)
+            # in_proj_bias is one parameter [768]: q part and k/v part are added by bias-only epilogues below
+            self._add_bias_slice(tape, qn, p + ".multihead_attn.in_proj_bias", 0, D)
+            self._add_bias_slice(tape, kvn, p + ".multihead_attn.in_proj_bias", D, 2 * D)
+            a = ag.cross_attention(tape, qn, kvn, 0, D, B, S, Mlen, NHEAD, 32)
+            y = ag.linear(tape, ps, a, p + ".co", p + ".multihead_attn.out_proj.bias", res=y)
+            hh = ag.layernorm(tape, ps, y, p + ".norm3")
+            f = ag.linear(tape, ps, hh, p + ".l1", p + ".linear1.bias", act="relu", want_f32=False)
+            y = ag.linear(tape, ps, f, p + ".l2", p + ".linear2.bias", res=y)
+        hh = ag.layernorm(tape, ps, y, "decoder.head.0")
+        logits = ag.linear(tape, ps, hh, "decoder.head.1", None)
+        loss = ag.ce_loss(tape, logits, targets["seq"].to(dev), 0.1, self.model.tokenizer.name_to_id("pad"))
+        return loss, tape, logits
+
+    def _add_bias_slice(self, tape, node: Node, bias_name: str, off: int, n: int) -> None:
+        """node.f32 += bias[off:off+n] (row broadcast) with the bias gradient routed to that slice."""
+        ps = self.ps
+        b = ps.p(bias_name)[off:off + n]
+        ops.rows_affine(node.f32, node.M, node.Cn, table=b.view(1, n), tab_mod=1, out_f32=node.f32)
+
+        def bwd() -> None:
+            if node.grad is not None:
+                ag.colsum(node.grad, ps.g(bias_name)[off:off + n])
+
+        tape.record(bwd)
+
+    def _fid_cls(self, retrieved, B: int) -> torch.Tensor:
+        """Frozen FIDNetV3 CLS features [B*K, 256] (fid/model.py:95-103) via the inference kernels."""
+        eng = self.infer
+        K = eng.top_k
+        packed = retrieved if torch.is_tensor(retrieved) else eng.pack_retrieved(retrieved, K, self.dev)
+        E = packed.shape[-1]
+        N, T = B * K, E + 1
+        f = "layout_encoer"
+        rows, pad = ops.fid_embed_packed(packed.view(N, 6, E), eng.w[f + ".fc_bbox.w"], eng.w[f + ".fc_bbox.b"],
+                                         eng.w[f + ".emb_label"])
+        x = torch.empty((N * T, D), dtype=torch.float32, device=self.dev)
+        xs = torch.empty((2, N * T, D), dtype=torch.bfloat16, device=self.dev)
+        ops.rows_affine(None, N, D, table=eng.w[f + ".token"], tab_mod=1, rows_per_group=1, group_stride=T, group_offset=0,
+                        out_f32=x, out_split=xs)
+        eng._gemm(rows, f + ".enc_fc_in", act="relu", out_f32=x, out_split=xs, rows_per_group=E, group_stride=T,
+                  group_offset=1)
+        for i in range(4):
+            x, xs = eng._postnorm_layer(x, xs, f"{f}.enc_transformer.core.layers.{i}", N, T, pad, 4)
+        cls = torch.empty((N, D), dtype=torch.float32, device=self.dev)
+        ops.rows_affine(x, N, D, in_ld=T * D, out_f32=cls)
+        return cls
+
+    # ------------------------------------------------------------------------------------------
+    def train_step(self, inputs: dict, targets: dict, lr: Optional[float] = None) -> torch.Tensor:
+        """One optimisation step (train.py:440-454).  Returns the loss (device scalar; no host sync)."""
+        ps = self.ps
+        ps.flat_g.zero_()
+        loss, tape, _ = self.forward_loss(inputs, targets)
+        tape.backward()
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(ps.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
+            ps.flat_g.mul_(1.0 / self.world)
+        norm = ag.grad_norm(ps.flat_g)
+        self.step_count += 1
+        scale = 1.0 if lr is None else lr / self.lr  # scheduler (MultiStepLR) scales every group alike
+        cfg = [(g_lr * scale, wd) for (g_lr, wd) in self.group_cfg]
+        ag.adamw_step(ps, cfg, self.step_count, self.max_norm, norm)
+        self.refresh_operands()
+        self.last_grad_norm = norm
+        return loss
