@@ -45,10 +45,17 @@ def _L():
 
 
 def to_split(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [M, C] -> split [2, M, C]; the row pitch is padded to a multiple of 8 elements when C is not (TMA needs
+    16-byte row pitches), in which case a [:, :, :C] view of the padded buffer is returned."""
     M, Cn = x.shape
-    out = torch.empty((2, M, Cn), dtype=torch.bfloat16, device=x.device)
-    check(_L().ralf_to_split(x.data_ptr(), x.numel(), out.data_ptr(), out.stride(0), _stream()), "ralf_to_split")
-    return out
+    if Cn % 8 == 0 and x.is_contiguous():
+        out = torch.empty((2, M, Cn), dtype=torch.bfloat16, device=x.device)
+        check(_L().ralf_to_split(x.data_ptr(), x.numel(), out.data_ptr(), out.stride(0), _stream()), "ralf_to_split")
+        return out
+    Cp = (Cn + 7) // 8 * 8
+    out = torch.empty((2, M, Cp), dtype=torch.bfloat16, device=x.device)
+    ops.rows_affine(x, M, Cn, in_ld=x.stride(0), out_split=out, out_ld=Cp)
+    return out[:, :, :Cn]
 
 
 def transpose_to_split(x_f32: Optional[torch.Tensor] = None, x_split: Optional[torch.Tensor] = None) -> torch.Tensor:
