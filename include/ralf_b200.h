@@ -106,6 +106,11 @@ typedef struct RalfGemmArgs {
   int group_offset;
 } RalfGemmArgs;
 int ralf_gemm(const RalfGemmArgs* args, void* stream);
+/* D = LayerNorm(x)[M,256] . W^T with the LayerNorm computed inside the GEMM (decode path: M <= 128, K = 256,
+ * npass = 3).  x fp32 [M, 256] (row stride ldx); `args` supplies W and the epilogue (its A fields are ignored).
+ * Replaces nn.LayerNorm + nn.Linear pairs of the pre-LN decoder layer / LM head (common/common.py:26-41). */
+int ralf_gemm_ln(const float* x, int ldx, const float* gamma, const float* beta, float eps,
+                 const RalfGemmArgs* args, void* stream);
 
 
 /* ---------------------------------------------------------------------------------------------

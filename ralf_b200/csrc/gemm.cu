@@ -65,6 +65,118 @@ struct GemmCfg {
   static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator buffers
 };
 
+// Epilogue of one 128 x BN accumulator tile: each thread owns one row (TMEM lane), walks the columns in chunks of 32.
+template <int BN>
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmEpi& ep, const uint32_t tacc, const int quad, const int lane,
+                                                   const int m0, const int n0, const int M, const int N) {
+    const int r = m0 + quad * 32 + lane;
+    const bool row_ok = r < M;
+    const long long out_row =
+        (long long)(r / ep.rows_per_group) * ep.group_stride + ep.group_offset + r % ep.rows_per_group;
+    const long long res_row = ep.res_row_mod > 0 ? (r % ep.res_row_mod) : r;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      if (n0 + c >= N) break;
+      uint32_t v[32];
+      tmem_ld_32x32(tacc + (static_cast<uint32_t>(quad * 32) << 16) + c, v);
+      tmem_ld_wait();
+      if (!row_ok) continue;
+      const int nbase = n0 + c;
+      float x[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+      const bool full = ep.vec_ok && (nbase + 32 <= N);
+      if (full) {
+        if (ep.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + nbase + j));
+            x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
+          }
+        }
+        if (ep.act) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = apply_act(x[j], ep.act);
+        }
+        if (ep.res) {
+          const float* rp = ep.res + res_row * ep.res_ld + nbase;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(rp + j);
+            x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
+          }
+        }
+        if (ep.res_split) {
+          const __nv_bfloat16* rh = ep.res_split + res_row * ep.res_ld + nbase;
+          const __nv_bfloat16* rl = rh + ep.res_plane;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const uint4 h = *reinterpret_cast<const uint4*>(rh + j);
+            const uint4 l = *reinterpret_cast<const uint4*>(rl + j);
+            const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+            const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              x[j + 2 * q] += __uint_as_float(hw[q] << 16) + __uint_as_float(lw[q] << 16);
+              x[j + 2 * q + 1] +=
+                  __uint_as_float(hw[q] & 0xffff0000u) + __uint_as_float(lw[q] & 0xffff0000u);
+            }
+          }
+        }
+        if (ep.post_relu) {  // ResNet bottleneck tail: relu(bn3(conv3) + identity)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+        }
+        if (ep.out_f32) {
+          float* op = ep.out_f32 + out_row * ep.out_ld + ep.out_col0 + nbase;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(op + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+        }
+        if (ep.out_split) {
+          __nv_bfloat16* oh = ep.out_split + out_row * ep.out_ld + ep.out_col0 + nbase;
+          __nv_bfloat16* ol = oh + ep.out_plane;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(x[j + 2 * q], h0, l0);
+              split_bf16(x[j + 2 * q + 1], h1, l1);
+              hw[q] = pack_bf16(h0, h1);
+              lw[q] = pack_bf16(l0, l1);
+            }
+            *reinterpret_cast<uint4*>(oh + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            if (ep.split_lo) *reinterpret_cast<uint4*>(ol + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int j = 0; j < 32; ++j) {
+          const int n = nbase + j;
+          if (n >= N) break;
+          float y = x[j];
+          if (ep.bias) y += __ldg(ep.bias + n);
+          if (ep.act) y = apply_act(y, ep.act);
+          if (ep.res) y += ep.res[res_row * ep.res_ld + n];
+          if (ep.res_split) {
+            y += __bfloat162float(ep.res_split[res_row * ep.res_ld + n]) +
+                 __bfloat162float(ep.res_split[ep.res_plane + res_row * ep.res_ld + n]);
+          }
+          if (ep.post_relu) y = fmaxf(y, 0.f);
+          if (ep.out_f32) ep.out_f32[out_row * ep.out_ld + ep.out_col0 + n] = y;
+          if (ep.out_split) {
+            __nv_bfloat16 h, l;
+            split_bf16(y, h, l);
+            ep.out_split[out_row * ep.out_ld + ep.out_col0 + n] = h;
+            if (ep.split_lo) ep.out_split[ep.out_plane + out_row * ep.out_ld + ep.out_col0 + n] = l;
+          }
+        }
+      }
+    }
+}
+
 template <int BN, int NPASS>
 __global__ void __launch_bounds__(192, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -191,112 +303,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
     tc_fence_after();
     const uint32_t tacc = tmem_base + buf * BN;
-    const int r = m0 + quad * 32 + lane;
-    const bool row_ok = r < M;
-    const long long out_row =
-        (long long)(r / ep.rows_per_group) * ep.group_stride + ep.group_offset + r % ep.rows_per_group;
-    const long long res_row = ep.res_row_mod > 0 ? (r % ep.res_row_mod) : r;
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      if (n0 + c >= N) break;
-      uint32_t v[32];
-      tmem_ld_32x32(tacc + (static_cast<uint32_t>(quad * 32) << 16) + c, v);
-      tmem_ld_wait();
-      if (!row_ok) continue;
-      const int nbase = n0 + c;
-      float x[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-      const bool full = ep.vec_ok && (nbase + 32 <= N);
-      if (full) {
-        if (ep.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + nbase + j));
-            x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
-          }
-        }
-        if (ep.act) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = apply_act(x[j], ep.act);
-        }
-        if (ep.res) {
-          const float* rp = ep.res + res_row * ep.res_ld + nbase;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(rp + j);
-            x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
-          }
-        }
-        if (ep.res_split) {
-          const __nv_bfloat16* rh = ep.res_split + res_row * ep.res_ld + nbase;
-          const __nv_bfloat16* rl = rh + ep.res_plane;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const uint4 h = *reinterpret_cast<const uint4*>(rh + j);
-            const uint4 l = *reinterpret_cast<const uint4*>(rl + j);
-            const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
-            const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              x[j + 2 * q] += __uint_as_float(hw[q] << 16) + __uint_as_float(lw[q] << 16);
-              x[j + 2 * q + 1] +=
-                  __uint_as_float(hw[q] & 0xffff0000u) + __uint_as_float(lw[q] & 0xffff0000u);
-            }
-          }
-        }
-        if (ep.post_relu) {  // ResNet bottleneck tail: relu(bn3(conv3) + identity)
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
-        }
-        if (ep.out_f32) {
-          float* op = ep.out_f32 + out_row * ep.out_ld + ep.out_col0 + nbase;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(op + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
-        }
-        if (ep.out_split) {
-          __nv_bfloat16* oh = ep.out_split + out_row * ep.out_ld + ep.out_col0 + nbase;
-          __nv_bfloat16* ol = oh + ep.out_plane;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint32_t hw[4], lw[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(x[j + 2 * q], h0, l0);
-              split_bf16(x[j + 2 * q + 1], h1, l1);
-              hw[q] = pack_bf16(h0, h1);
-              lw[q] = pack_bf16(l0, l1);
-            }
-            *reinterpret_cast<uint4*>(oh + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            if (ep.split_lo) *reinterpret_cast<uint4*>(ol + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-          }
-        }
-      } else {
-#pragma unroll 1
-        for (int j = 0; j < 32; ++j) {
-          const int n = nbase + j;
-          if (n >= N) break;
-          float y = x[j];
-          if (ep.bias) y += __ldg(ep.bias + n);
-          if (ep.act) y = apply_act(y, ep.act);
-          if (ep.res) y += ep.res[res_row * ep.res_ld + n];
-          if (ep.res_split) {
-            y += __bfloat162float(ep.res_split[res_row * ep.res_ld + n]) +
-                 __bfloat162float(ep.res_split[ep.res_plane + res_row * ep.res_ld + n]);
-          }
-          if (ep.post_relu) y = fmaxf(y, 0.f);
-          if (ep.out_f32) ep.out_f32[out_row * ep.out_ld + ep.out_col0 + n] = y;
-          if (ep.out_split) {
-            __nv_bfloat16 h, l;
-            split_bf16(y, h, l);
-            ep.out_split[out_row * ep.out_ld + ep.out_col0 + n] = h;
-            if (ep.split_lo) ep.out_split[ep.out_plane + out_row * ep.out_ld + ep.out_col0 + n] = l;
-          }
-        }
-      }
-    }
+    gemm_epilogue_tile<BN>(ep, tacc, quad, lane, m0, n0, M, N);
     tc_fence_before();
     mbar_arrive(&tempty_bar[buf]);
     }  // tile loop
@@ -306,6 +313,136 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm fused into the GEMM's A operand (decode path: M <= 128 rows, K = 256 = d_model).
+//   D[M,N] = LN(x)[M,256] . W[N,256]^T  (+ epilogue)      x fp32 (row stride ldx), gamma/beta fp32 [256]
+// The epilogue warps first normalise their 32 rows each (two LDG.128 per lane, warp-shuffle statistics),
+// split the result into bf16 hi/lo and store it straight into shared memory in the K-major SWIZZLE_128B
+// layout the UMMA descriptor expects (16-byte chunk index XOR (row & 7)) -- exactly what a TMA load of a
+// pre-normalised tensor would have produced, minus the separate LayerNorm kernel and its HBM round trip.
+// W streams in by TMA (all 4 k-blocks issued up front).  One CTA per n-tile.
+// Replaces nn.LayerNorm + nn.Linear pairs of the pre-LN decoder layers (common/common.py:26-41).
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+gemm_ln_kernel(const __grid_constant__ CUtensorMap tmB, const float* __restrict__ x, const int ldx,
+               const float* __restrict__ gamma, const float* __restrict__ beta, const float eps, const GemmEpi ep,
+               const int M, const int N) {
+  constexpr int KB = 4;                      // K = 256 -> 4 k-blocks of 64
+  constexpr int A_PLANE = 128 * 128;         // 16 KB per k-block per plane
+  constexpr int A_BYTES = KB * 2 * A_PLANE;  // 128 KB
+  constexpr int B_PLANE = BN * 128;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
+  uint8_t* smem_b = smem + A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + KB * 2 * B_PLANE);
+  uint64_t* aready_bar = full_bar + KB;
+  uint64_t* tfull_bar = aready_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmB);
+    for (int kb = 0; kb < KB; ++kb) mbar_init(&full_bar[kb], 1);
+    mbar_init(aready_bar, 128);
+    mbar_init(tfull_bar, 1);
+    fence_mbar_init();
+    for (int kb = 0; kb < KB; ++kb) {
+      mbar_expect_tx(&full_bar[kb], 2 * B_PLANE);
+      tma_load_3d(&tmB, &full_bar[kb], smem_b + (kb * 2 + 0) * B_PLANE, kb * 64, n0, 0);
+      tma_load_3d(&tmB, &full_bar[kb], smem_b + (kb * 2 + 1) * B_PLANE, kb * 64, n0, 1);
+    }
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(1, 128, BN);
+      mbar_wait(aready_bar, 0);
+      tc_fence_after();
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(&full_bar[kb], 0);
+        tc_fence_after();
+        const uint32_t a_hi = base_u32 + kb * 2 * A_PLANE;
+        const uint32_t b_hi = base_u32 + A_BYTES + kb * 2 * B_PLANE;
+        const uint64_t da_hi = make_sw128_kmajor_desc(a_hi), da_lo = make_sw128_kmajor_desc(a_hi + A_PLANE);
+        const uint64_t db_hi = make_sw128_kmajor_desc(b_hi), db_lo = make_sw128_kmajor_desc(b_hi + B_PLANE);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t koff = static_cast<uint64_t>(2 * k);
+          mma_bf16_ss(tmem_base, da_hi + koff, db_lo + koff, idesc, (kb | k) != 0);
+          mma_bf16_ss(tmem_base, da_lo + koff, db_hi + koff, idesc, 1);
+          mma_bf16_ss(tmem_base, da_hi + koff, db_hi + koff, idesc, 1);
+        }
+      }
+      tc_commit(tfull_bar);
+    }
+  } else if (warp >= 2) {
+    // ---- LayerNorm prologue: warp (warp-2) normalises rows [32*(warp-2), +32); lane owns columns 8*lane .. 8*lane+7 ----
+    const int w4 = warp - 2;
+    const int kb = lane >> 3, chunk = lane & 7;  // the lane's 8 columns are one 16-byte chunk of k-block kb
+    float g[8], bt[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { g[i] = gamma[lane * 8 + i]; bt[i] = beta[lane * 8 + i]; }
+    for (int rr = 0; rr < 32; ++rr) {
+      const int r = w4 * 32 + rr;
+      float v[8];
+      if (r < M) {
+        const float4 f0 = *reinterpret_cast<const float4*>(x + static_cast<long long>(r) * ldx + lane * 8);
+        const float4 f1 = *reinterpret_cast<const float4*>(x + static_cast<long long>(r) * ldx + lane * 8 + 4);
+        v[0] = f0.x; v[1] = f0.y; v[2] = f0.z; v[3] = f0.w; v[4] = f1.x; v[5] = f1.y; v[6] = f1.z; v[7] = f1.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      }
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += v[i];
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      const float mean = s * (1.f / 256.f);
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; sq += d * d; }
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+      const float rstd = rsqrtf(sq * (1.f / 256.f) + eps);
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16((v[i] - mean) * rstd * g[i] + bt[i], h0, l0);
+        split_bf16((v[i + 1] - mean) * rstd * g[i + 1] + bt[i + 1], h1, l1);
+        hw[i >> 1] = pack_bf16(h0, h1);
+        lw[i >> 1] = pack_bf16(l0, l1);
+      }
+      uint8_t* dst = smem + kb * 2 * A_PLANE + r * 128 + ((chunk ^ (r & 7)) << 4);
+      *reinterpret_cast<uint4*>(dst) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      *reinterpret_cast<uint4*>(dst + A_PLANE) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
+    fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor-core (async proxy) reads
+    mbar_arrive(aready_bar);
+    // ---- epilogue ----
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    gemm_epilogue_tile<BN>(ep, tmem_base, warp & 3, lane, 0, n0, M, N);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
@@ -464,4 +601,56 @@ extern "C" int ralf_gemm(const RalfGemmArgs* a, void* stream) {
   RALF_GEMM_CASE(256, 1)
 #undef RALF_GEMM_CASE
   return RALF_ERR_SHAPE;
+}
+
+template <int BN>
+static int launch_gemm_ln(const CUtensorMap& tb, const float* x, int ldx, const float* gamma, const float* beta, float eps,
+                          const GemmEpi& ep, int M, int N, cudaStream_t st) {
+  constexpr int SMEM = 4 * 2 * 128 * 128 + 4 * 2 * BN * 128 + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_ln_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return set_cuda_error(e);
+    attr_set = true;
+  }
+  gemm_ln_kernel<BN><<<(N + BN - 1) / BN, 192, SMEM, st>>>(tb, x, ldx, gamma, beta, eps, ep, M, N);
+  return set_cuda_error(cudaGetLastError());
+}
+
+// LayerNorm(x) . W^T with the LayerNorm computed inside the GEMM (M <= 128, K = 256, bf16x3).  `a` supplies W and the
+// epilogue fields (its A / lda / a_plane are ignored).
+extern "C" int ralf_gemm_ln(const float* x, int ldx, const float* gamma, const float* beta, float eps,
+                            const RalfGemmArgs* a, void* stream) {
+  if (!x || !gamma || !beta || !a || !a->W) return RALF_ERR_NULL;
+  if (a->M <= 0 || a->M > 128 || a->K != 256 || a->N <= 0 || a->npass != 3) return RALF_ERR_SHAPE;
+  if ((ldx % 4) || (a->ldw % 8) || (reinterpret_cast<uintptr_t>(x) & 15)) return RALF_ERR_ALIGN;
+  const int bn = a->N >= 1024 ? 64 : 32;
+  CUtensorMap tb;
+  int rc = make_kmajor_tmap(&tb, a->W, 2, a->K, a->N, 2, a->ldw, a->w_plane, bn);
+  if (rc) return rc;
+  GemmEpi ep;
+  ep.bias = a->bias;
+  ep.res = a->res;
+  ep.res_split = reinterpret_cast<const __nv_bfloat16*>(a->res_split);
+  ep.res_plane = a->res_plane;
+  ep.res_ld = a->res_ld;
+  ep.res_row_mod = a->res_row_mod;
+  ep.out_f32 = a->out_f32;
+  ep.out_split = reinterpret_cast<__nv_bfloat16*>(a->out_split);
+  ep.out_plane = a->out_plane;
+  ep.out_ld = a->out_ld;
+  ep.out_col0 = a->out_col0;
+  ep.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : a->M;
+  ep.group_stride = a->rows_per_group > 0 ? a->group_stride : 0;
+  ep.group_offset = a->rows_per_group > 0 ? a->group_offset : 0;
+  ep.act = a->act;
+  ep.post_relu = a->post_relu;
+  ep.split_lo = a->out_split_lo;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  ep.vec_ok = (a->out_ld % 8 == 0) && (a->out_col0 % 8 == 0) && al16(a->out_f32) && al16(a->out_split) &&
+              (a->out_plane % 8 == 0) && al16(a->bias) && al16(a->res) && al16(a->res_split) &&
+              (a->res_ld % 8 == 0 || (!a->res && !a->res_split)) && (a->res_plane % 8 == 0);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (bn == 64) return launch_gemm_ln<64>(tb, x, ldx, gamma, beta, eps, ep, a->M, a->N, st);
+  return launch_gemm_ln<32>(tb, x, ldx, gamma, beta, eps, ep, a->M, a->N, st);
 }

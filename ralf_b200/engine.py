@@ -190,6 +190,14 @@ class Engine:
     def _ln(self, x, name, **kw):
         return ops.layernorm(x, self.w[name + ".g"], self.w[name + ".beta"], **kw)
 
+    def _gemm_ln(self, x, ln_name, name, **kw):
+        """LayerNorm fused into the consuming GEMM (M <= 128 rows: the decode path); falls back to two kernels above."""
+        if x.shape[0] > 128 or self.npass != 3:
+            _, h = self._ln(x, ln_name)
+            return self._gemm(h, name, **kw)
+        return ops.gemm_ln(x, self.w[ln_name + ".g"], self.w[ln_name + ".beta"], self.w[name + ".w"],
+                           bias=self.w.get(name + ".b"), **kw)
+
     def pos2d(self, h: int, w: int) -> torch.Tensor:
         if (h, w) not in self._pos2d:
             self._pos2d[(h, w)] = _pos_emb_2d(h, w, D).to(self.dev)
@@ -405,20 +413,17 @@ class Engine:
         for t in range(steps):
             for i in range(NLAYER):
                 p = f"decoder.transformer.layers.{i}"
-                _, h = self._ln(x, p + ".norm1")
-                qkv, _ = self._gemm(h, p + ".qkv")
+                # every LayerNorm of the step is folded into the GEMM that consumes it (ralf_gemm_ln)
+                qkv, _ = self._gemm_ln(x, p + ".norm1", p + ".qkv")
                 a = ops.attention_decode_append(qkv, kc[i], vc[i], t, B, NHEAD, 32, mask=pad_mask)
                 self._gemm(a, p + ".o", res=x, out_f32=x)
-                _, h = self._ln(x, p + ".norm2")
-                q, _ = self._gemm(h, p + ".cq")
+                q, _ = self._gemm_ln(x, p + ".norm2", p + ".cq")
                 a = ops.attention_decode(q, kvm[:, i * 512:i * 512 + D], kvm[:, i * 512 + D:(i + 1) * 512], Mlen,
                                          Mlen, B, NHEAD, 32)
                 self._gemm(a, p + ".co", res=x, out_f32=x)
-                _, h = self._ln(x, p + ".norm3")
-                _, f = self._gemm(h, p + ".linear1", act="relu", want_f32=False, want_split=True)
+                _, f = self._gemm_ln(x, p + ".norm3", p + ".linear1", act="relu", want_f32=False, want_split=True)
                 self._gemm(f, p + ".linear2", res=x, out_f32=x)
-            _, h = self._ln(x, "decoder.head.0")
-            logits, _ = self._gemm(h, "decoder.head.1")
+            logits, _ = self._gemm_ln(x, "decoder.head.0", "decoder.head.1")
             if return_logits:
                 all_logits.append(logits)
             ops.argmax_next(logits, tm[t], seq, t + 1, pad_mask, pad_id, self.w["decoder.emb"], math.sqrt(D),

@@ -114,6 +114,40 @@ def gemm(
     return out_f32, out_split
 
 
+def gemm_ln(
+    x: torch.Tensor,      # fp32 [M <= 128, 256]
+    gamma: torch.Tensor,
+    beta: torch.Tensor,
+    w: torch.Tensor,      # split bf16 [2, N, 256]
+    *,
+    bias: Optional[torch.Tensor] = None,
+    act: Optional[str] = None,
+    res: Optional[torch.Tensor] = None,
+    out_f32: Optional[torch.Tensor] = None,
+    want_f32: bool = True,
+    want_split: bool = False,
+    eps: float = 1e-5,
+) -> tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """LayerNorm(x) . W^T with the LayerNorm fused into the GEMM prologue (ralf_gemm_ln; decode path)."""
+    M, K = x.shape
+    N = w.shape[1]
+    if out_f32 is None and want_f32:
+        out_f32 = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    out_split = torch.empty((2, M, N), dtype=torch.bfloat16, device=x.device) if want_split else None
+    g = GemmArgs()
+    g.W, g.w_plane, g.ldw = w.data_ptr(), w.stride(0), w.stride(1)
+    g.M, g.N, g.K, g.npass = M, N, K, 3
+    g.bias, g.act = _ptr(bias), ACT[act]
+    g.res, g.res_ld = _ptr(res), (res.stride(-2) if res is not None else 0)
+    g.out_f32, g.out_split = _ptr(out_f32), _ptr(out_split)
+    g.out_plane = out_split.stride(0) if out_split is not None else 0
+    g.out_split_lo = 1
+    g.out_ld = out_f32.stride(-2) if out_f32 is not None else N
+    check(_lib.lib().ralf_gemm_ln(x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(), eps, C.byref(g), _stream()),
+          "ralf_gemm_ln")
+    return out_f32, out_split
+
+
 def knn_topk(
     gallery: torch.Tensor,
     queries: torch.Tensor,

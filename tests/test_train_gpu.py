@@ -95,6 +95,10 @@ def test_training_gradients_match_oracle(cuda_device, train_trunk):
         worst.append((err / (scale + 1e-12), name, scale))
     worst.sort(reverse=True)
     print("worst grads:", worst[:5])
+    import json, os
+    os.makedirs(os.path.join(helpers.ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(helpers.ROOT, "gpurun_out", f"train_grad_errors_trunk{int(train_trunk)}.json"), "w") as f:
+        json.dump([[round(e, 6), n, s_] for e, n, s_ in worst], f, indent=0)
     bad = [w for w in worst if w[0] > GRAD_RTOL and w[2] > 1e-9]
     assert not bad, bad[:10]
     assert set(ref_grads) == set(te.ps.offsets), set(te.ps.offsets) ^ set(ref_grads)
