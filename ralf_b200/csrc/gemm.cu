@@ -320,8 +320,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 // LayerNorm fused into the GEMM's A operand (decode path: M <= 128 rows, K = 256 = d_model).
 //   D[M,N] = LN(x)[M,256] . W[N,256]^T  (+ epilogue)      x fp32 (row stride ldx), gamma/beta fp32 [256]
-// The epilogue warps first normalise their 32 rows each (two LDG.128 per lane, warp-shuffle statistics),
-// split the result into bf16 hi/lo and store it straight into shared memory in the K-major SWIZZLE_128B
+// The 128 epilogue threads first normalise one row each (two sweeps of independent LDG.128s), split the
+// result into bf16 hi/lo and store it straight into shared memory in the K-major SWIZZLE_128B
 // layout the UMMA descriptor expects (16-byte chunk index XOR (row & 7)) -- exactly what a TMA load of a
 // pre-normalised tensor would have produced, minus the separate LayerNorm kernel and its HBM round trip.
 // W streams in by TMA (all 4 k-blocks issued up front).  One CTA per n-tile.
@@ -389,44 +389,45 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmB, const float* __restrict_
       tc_commit(tfull_bar);
     }
   } else if (warp >= 2) {
-    // ---- LayerNorm prologue: warp (warp-2) normalises rows [32*(warp-2), +32); lane owns columns 8*lane .. 8*lane+7 ----
-    const int w4 = warp - 2;
-    const int kb = lane >> 3, chunk = lane & 7;  // the lane's 8 columns are one 16-byte chunk of k-block kb
-    float g[8], bt[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { g[i] = gamma[lane * 8 + i]; bt[i] = beta[lane * 8 + i]; }
-    for (int rr = 0; rr < 32; ++rr) {
-      const int r = w4 * 32 + rr;
-      float v[8];
+    // ---- LayerNorm prologue: one thread per row (128 epilogue threads <-> 128 rows).  Sweep 1 streams the row
+    // (64 independent LDG.128 in flight per thread) for sum / sum of squares; sweep 2 re-reads it (L2 hit), normalises,
+    // splits to bf16 hi/lo and stores 16-byte chunks into the SWIZZLE_128B K-major layout. ----
+    const int r = static_cast<int>(threadIdx.x) - 64;
+    const float* xr = x + static_cast<long long>(r < M ? r : 0) * ldx;
+    float s = 0.f, ss = 0.f;
+    if (r < M) {
+#pragma unroll 16
+      for (int c = 0; c < 64; ++c) {
+        const float4 f = *reinterpret_cast<const float4*>(xr + 4 * c);
+        s += (f.x + f.y) + (f.z + f.w);
+        ss = fmaf(f.x, f.x, ss); ss = fmaf(f.y, f.y, ss); ss = fmaf(f.z, f.z, ss); ss = fmaf(f.w, f.w, ss);
+      }
+    }
+    const float mean = s * (1.f / 256.f);
+    const float rstd = rsqrtf(fmaxf(ss * (1.f / 256.f) - mean * mean, 0.f) + eps);
+#pragma unroll 4
+    for (int ch32 = 0; ch32 < 32; ++ch32) {  // 32 chunks of 8 columns
+      uint32_t hw[4] = {0, 0, 0, 0}, lw[4] = {0, 0, 0, 0};
       if (r < M) {
-        const float4 f0 = *reinterpret_cast<const float4*>(x + static_cast<long long>(r) * ldx + lane * 8);
-        const float4 f1 = *reinterpret_cast<const float4*>(x + static_cast<long long>(r) * ldx + lane * 8 + 4);
-        v[0] = f0.x; v[1] = f0.y; v[2] = f0.z; v[3] = f0.w; v[4] = f1.x; v[5] = f1.y; v[6] = f1.z; v[7] = f1.w;
-      } else {
+        const float4 f0 = *reinterpret_cast<const float4*>(xr + 8 * ch32);
+        const float4 f1 = *reinterpret_cast<const float4*>(xr + 8 * ch32 + 4);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + 8 * ch32));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + 8 * ch32 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + 8 * ch32));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + 8 * ch32 + 4));
+        const float v[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        for (int i = 0; i < 8; i += 2) {
+          __nv_bfloat16 h0, l0, h1, l1;
+          split_bf16((v[i] - mean) * rstd * g[i] + bt[i], h0, l0);
+          split_bf16((v[i + 1] - mean) * rstd * g[i + 1] + bt[i + 1], h1, l1);
+          hw[i >> 1] = pack_bf16(h0, h1);
+          lw[i >> 1] = pack_bf16(l0, l1);
+        }
       }
-      float s = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) s += v[i];
-#pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-      const float mean = s * (1.f / 256.f);
-      float sq = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; sq += d * d; }
-#pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
-      const float rstd = rsqrtf(sq * (1.f / 256.f) + eps);
-      uint32_t hw[4], lw[4];
-#pragma unroll
-      for (int i = 0; i < 8; i += 2) {
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16((v[i] - mean) * rstd * g[i] + bt[i], h0, l0);
-        split_bf16((v[i + 1] - mean) * rstd * g[i + 1] + bt[i + 1], h1, l1);
-        hw[i >> 1] = pack_bf16(h0, h1);
-        lw[i >> 1] = pack_bf16(l0, l1);
-      }
+      const int kb = ch32 >> 3, chunk = ch32 & 7;
       uint8_t* dst = smem + kb * 2 * A_PLANE + r * 128 + ((chunk ^ (r & 7)) << 4);
       *reinterpret_cast<uint4*>(dst) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
       *reinterpret_cast<uint4*>(dst + A_PLANE) = make_uint4(lw[0], lw[1], lw[2], lw[3]);

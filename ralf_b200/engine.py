@@ -17,6 +17,7 @@ Reference citations are relative to image2layout/train/.
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -26,6 +27,8 @@ from . import ops
 NHEAD = 8
 NLAYER = 6
 D = 256
+# LayerNorm folded into the consuming decode GEMM (ralf_gemm_ln); RALF_FUSE_LN=0 keeps the two-kernel form (A/B switch).
+FUSE_LN = os.environ.get("RALF_FUSE_LN", "1") != "0"
 
 
 def _sine_pe_1d(max_len: int, d_model: int) -> torch.Tensor:
@@ -192,7 +195,7 @@ class Engine:
 
     def _gemm_ln(self, x, ln_name, name, **kw):
         """LayerNorm fused into the consuming GEMM (M <= 128 rows: the decode path); falls back to two kernels above."""
-        if x.shape[0] > 128 or self.npass != 3:
+        if x.shape[0] > 128 or self.npass != 3 or not FUSE_LN:
             _, h = self._ln(x, ln_name)
             return self._gemm(h, name, **kw)
         return ops.gemm_ln(x, self.w[ln_name + ".g"], self.w[ln_name + ".beta"], self.w[name + ".w"],
