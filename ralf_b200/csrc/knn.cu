@@ -19,6 +19,7 @@
 // Algorithmic HBM bytes per call: n*d*4 (gallery once) + q*d*4 + q*k*12.
 #include <float.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ralf_internal.h"
@@ -184,7 +185,9 @@ __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
 template <int C>
 __global__ void __launch_bounds__(192, 1)
 knn_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmG,
-                const int n, const int d, const int nq, uint64_t* __restrict__ cand) {
+                const int n, const int d, const int nq, uint64_t* __restrict__ cand, const int debug_mode) {
+  // debug_mode (RALF_KNN_DEBUG, profiling only; results are garbage): 1 = epilogue reads TMEM but skips the candidate
+  // filter, 2 = epilogue only hands the accumulator back.  Used to separate pipeline time from epilogue time.
   using Cfg = KnnCfg<C>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -285,11 +288,12 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // 8 columns per piece: a list can take at most 8 appends between capacity checks, so compaction is deferred
       // until a list holds > CAP - 8 keys (24 appended keys per round instead of 16 -> ~40 % fewer rounds).
       for (int c0 = 0; c0 < ncols; c0 += 8) {
+        if (debug_mode == 2) break;
         if (__any_sync(0xffffffffu, cnt > Cfg::CAP - 8)) knn_compact_round<C>(lists, lane, cnt, thr, sorted, Cfg::CAP - 8);
         uint32_t v[8];
         tmem_ld_32x8(tacc + c0, v);
         tmem_ld_wait();
-        if (active) {
+        if (active && debug_mode == 0) {
           const int lim = ncols - c0;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -557,7 +561,8 @@ static int knn_topk_impl(const float* gallery, int n, int d, const float* querie
   if (rc) return rc;
   const int gx = knn_grid_x(n);
   dim3 grid(gx, (q + 127) / 128);
-  knn_scan_kernel<C><<<grid, 192, Cfg::SMEM_BYTES, st>>>(tq, tg, n, d, q, cand);
+  static const int debug_mode = getenv("RALF_KNN_DEBUG") ? atoi(getenv("RALF_KNN_DEBUG")) : 0;
+  knn_scan_kernel<C><<<grid, 192, Cfg::SMEM_BYTES, st>>>(tq, tg, n, d, q, cand, debug_mode);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e);
   const size_t rr_smem = static_cast<size_t>(gx) * C * 8 < 2 * C * 8 ? 2 * C * 8 : static_cast<size_t>(gx) * C * 8;

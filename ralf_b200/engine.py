@@ -27,8 +27,10 @@ from . import ops
 NHEAD = 8
 NLAYER = 6
 D = 256
-# LayerNorm folded into the consuming decode GEMM (ralf_gemm_ln); RALF_FUSE_LN=0 keeps the two-kernel form (A/B switch).
-FUSE_LN = os.environ.get("RALF_FUSE_LN", "1") != "0"
+# LayerNorm folded into the consuming decode GEMM (ralf_gemm_ln) is OFF by default: measured on B200 (profiles/r1_notes.md) the
+# in-kernel row normalisation costs more than the separate 4 us LayerNorm launch it removes (1698 vs 2162 layouts/s).
+# RALF_FUSE_LN=1 switches it on for A/B runs.
+FUSE_LN = os.environ.get("RALF_FUSE_LN", "0") != "0"
 
 
 def _sine_pe_1d(max_len: int, d_model: int) -> torch.Tensor:
