@@ -174,20 +174,32 @@ __device__ __forceinline__ void knn_compact_round(uint64_t* lists, const int lan
   }
 }
 
-__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-      : "r"(taddr)
-      : "memory");
+// Algorithm outline of the tensor-core path (all launches on the caller's stream):
+//   1. knn_scan_kernel<C, true>   "pre-pass": <= 128 gallery tiles (strided over the whole gallery) are scored and
+//      only the maximum per 32-row group and query is kept (8 values per tile).
+//   2. knn_threshold_kernel<C>    per query: the C-th largest group maximum.  At least C distinct rows score >= that
+//      value, so it is a valid lower bound of the final C-th best TF32 score; the scan starts from it.
+//   3. knn_scan_kernel<C, false>  the full gallery scan.  Steady state per 8 scores: 8 compares + one warp vote; the
+//      (rare) passing scores are appended to the query's candidate list in shared memory.
+//   4. knn_rerank_kernel<C>       merge the per-CTA lists, exact canonical re-score, order, certificate.
+constexpr int KNN_SAMPLE_TILES = 128;  // pre-pass tiles (32 K rows)
+constexpr int KNN_GROUPS = 8;          // group maxima per tile (32 columns each)
+
+__device__ __forceinline__ float knn_next_below(float s) {
+  if (isinf(s) || isnan(s)) return s;
+  uint32_t u = __float_as_uint(s);
+  if (s > 0.f) u -= 1u;
+  else if (s < 0.f) u += 1u;
+  else u = 0x80000001u;
+  return __uint_as_float(u);
 }
 
-template <int C>
+template <int C, bool PRE>
 __global__ void __launch_bounds__(192, 1)
 knn_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmG,
-                const int n, const int d, const int nq, uint64_t* __restrict__ cand, const int debug_mode) {
-  // debug_mode (RALF_KNN_DEBUG, profiling only; results are garbage): 1 = epilogue reads TMEM but skips the candidate
-  // filter, 2 = epilogue only hands the accumulator back.  Used to separate pipeline time from epilogue time.
+                const int n, const int d, const int nq, uint64_t* __restrict__ cand,
+                const float* __restrict__ thr_init, float* __restrict__ tmax, const int debug_mode) {
+  // debug_mode (RALF_KNN_DEBUG, profiling only; results are garbage): 2 = the epilogue only hands the accumulator back.
   using Cfg = KnnCfg<C>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -204,8 +216,10 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int lane = threadIdx.x & 31;
   const int qtile = blockIdx.y;
   const int total_tiles = (n + 255) / 256;
+  // scan: CTA x owns a contiguous range of tiles; pre-pass: CTA x scores ONE tile, strided over the gallery
   const int t_begin = static_cast<int>((static_cast<long long>(blockIdx.x) * total_tiles) / gridDim.x);
-  const int t_end = static_cast<int>((static_cast<long long>(blockIdx.x + 1) * total_tiles) / gridDim.x);
+  const int t_end = PRE ? t_begin + 1
+                        : static_cast<int>((static_cast<long long>(blockIdx.x + 1) * total_tiles) / gridDim.x);
   const int nkb = (d + 31) / 32;
 
   if (warp == 0 && lane == 0) {
@@ -275,7 +289,8 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint64_t* lists = cand_s + static_cast<size_t>(quad) * 32 * Cfg::STRIDE;  // this warp's 32 query lists
     uint64_t* mine = lists + lane * Cfg::STRIDE;
     int cnt = 0, sorted = 0;
-    float thr = -INFINITY;
+    // inactive lanes (query >= nq) never pass the filter
+    float thr = !active ? INFINITY : (thr_init ? thr_init[qtile * 128 + ql] : -INFINITY);
     int it = 0;
     for (int t = t_begin; t < t_end; ++t, ++it) {
       const int buf = it & 1;
@@ -284,23 +299,46 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int g0 = t * 256;
       const int ncols = min(256, n - g0);
       const uint32_t tacc = tmem_base + buf * 256 + (static_cast<uint32_t>(quad * 32) << 16);
+      if constexpr (PRE) {
+        float* out = tmax + (static_cast<size_t>(qtile) * gridDim.x + blockIdx.x) * KNN_GROUPS * 128 + ql;
 #pragma unroll 1
-      // 8 columns per piece: a list can take at most 8 appends between capacity checks, so compaction is deferred
-      // until a list holds > CAP - 8 keys (24 appended keys per round instead of 16 -> ~40 % fewer rounds).
-      for (int c0 = 0; c0 < ncols; c0 += 8) {
-        if (debug_mode == 2) break;
-        if (__any_sync(0xffffffffu, cnt > Cfg::CAP - 8)) knn_compact_round<C>(lists, lane, cnt, thr, sorted, Cfg::CAP - 8);
-        uint32_t v[8];
-        tmem_ld_32x8(tacc + c0, v);
-        tmem_ld_wait();
-        if (active && debug_mode == 0) {
-          const int lim = ncols - c0;
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tacc + c0, v);
+          tmem_ld_wait();
+          float m = -INFINITY;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float s = __uint_as_float(v[j]);
-            if (s > thr && j < lim) {
-              mine[cnt] = knn_key(s, static_cast<uint32_t>(g0 + c0 + j));
-              ++cnt;
+          for (int j = 0; j < 32; ++j) m = fmaxf(m, (c0 + j < ncols) ? __uint_as_float(v[j]) : -INFINITY);
+          out[(c0 >> 5) * 128] = m;
+        }
+      } else {
+#pragma unroll 1
+        for (int c0 = 0; c0 < ncols; c0 += 64) {
+          if (debug_mode == 2) break;
+          uint32_t v[64];
+          tmem_ld_32x32(tacc + c0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          tmem_ld_32x32(tacc + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            // steady state: 8 compares + one vote.  Columns >= ncols hold zero-row products: they may trigger the slow
+            // path spuriously, where the `j < lim` test rejects them.
+            bool hit = false;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hit |= __uint_as_float(v[g * 8 + j]) > thr;
+            if (__any_sync(0xffffffffu, hit)) {
+              // at most 8 appends before the next capacity check
+              if (__any_sync(0xffffffffu, cnt > Cfg::CAP - 8))
+                knn_compact_round<C>(lists, lane, cnt, thr, sorted, Cfg::CAP - 8);
+              const int lim = ncols - c0 - g * 8;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float s = __uint_as_float(v[g * 8 + j]);
+                if (s > thr && j < lim) {
+                  mine[cnt] = knn_key(s, static_cast<uint32_t>(g0 + c0 + g * 8 + j));
+                  ++cnt;
+                }
+              }
             }
           }
         }
@@ -308,15 +346,17 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_before();
       mbar_arrive(&tempty_bar[buf]);
     }
-    __syncwarp();
-    knn_compact_round<C>(lists, lane, cnt, thr, sorted, C);  // trims every list to <= C entries
-    // candidate lists: [qtile][cta][query lane][C]; unused slots are 0 (= empty)
-    uint64_t* out_w = cand + ((static_cast<size_t>(qtile) * gridDim.x + blockIdx.x) * 128 + quad * 32) * C;
+    if constexpr (!PRE) {
+      __syncwarp();
+      knn_compact_round<C>(lists, lane, cnt, thr, sorted, C);  // trims every list to <= C entries
+      // candidate lists: [qtile][cta][query lane][C]; unused slots are 0 (= empty)
+      uint64_t* out_w = cand + ((static_cast<size_t>(qtile) * gridDim.x + blockIdx.x) * 128 + quad * 32) * C;
 #pragma unroll 1
-    for (int q = 0; q < 32; ++q) {
-      const int n_q = __shfl_sync(0xffffffffu, cnt, q);
-      const uint64_t* col = lists + q * Cfg::STRIDE;
-      for (int e = lane; e < C; e += 32) out_w[static_cast<size_t>(q) * C + e] = (e < n_q) ? col[e] : 0ull;
+      for (int q = 0; q < 32; ++q) {
+        const int n_q = __shfl_sync(0xffffffffu, cnt, q);
+        const uint64_t* col = lists + q * Cfg::STRIDE;
+        for (int e = lane; e < C; e += 32) out_w[static_cast<size_t>(q) * C + e] = (e < n_q) ? col[e] : 0ull;
+      }
     }
   }
   tc_fence_before();
@@ -327,61 +367,116 @@ knn_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
-// Phase 2.  One CTA (256 threads) per query.  `parts` candidate lists of C keys each.
+// Block-wide (256 threads) selection of the C largest keys out of `parts` lists of C keys (0 = empty slot).
+// Every warp folds its share of the lists into a running sorted top-C held in registers (warp bitonic sort + merge),
+// then warp 0 merges the eight partial results.  sel[0..C) ends sorted descending; scratch = 8*C keys.
+template <int C, typename LoadFn>
+__device__ __forceinline__ void block_top_c(LoadFn load, const int parts, uint64_t* sel, uint64_t* scratch) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if constexpr (C == 32) {
+    uint64_t r = 0ull;
+    for (int p = warp; p < parts; p += 8) {
+      uint64_t b = load(p, lane);
+      if (!__any_sync(0xffffffffu, b != 0ull)) continue;
+      b = warp_sort32_desc(b, lane);
+      r = warp_merge_top32(r, b, lane);
+    }
+    scratch[warp * 32 + lane] = r;
+    __syncthreads();
+    if (warp == 0) {
+      r = scratch[lane];
+      for (int w = 1; w < 8; ++w) r = warp_merge_top32(r, scratch[w * 32 + lane], lane);
+      sel[lane] = r;
+    }
+  } else {
+    uint64_t x[4] = {0ull, 0ull, 0ull, 0ull};
+    for (int p = warp; p < parts; p += 8) {
+      x[2] = load(p, lane);
+      x[3] = load(p, 32 + lane);
+      if (!__any_sync(0xffffffffu, (x[2] | x[3]) != 0ull)) continue;
+      bitonic_desc<4>(x, lane);
+    }
+    scratch[warp * 64 + lane] = x[0];
+    scratch[warp * 64 + 32 + lane] = x[1];
+    __syncthreads();
+    if (warp == 0) {
+      x[0] = scratch[lane];
+      x[1] = scratch[32 + lane];
+      for (int w = 1; w < 8; ++w) {
+        x[2] = scratch[w * 64 + lane];
+        x[3] = scratch[w * 64 + 32 + lane];
+        bitonic_desc<4>(x, lane);
+      }
+      sel[lane] = x[0];
+      sel[32 + lane] = x[1];
+    }
+  }
+  __syncthreads();
+}
+
+// Step 2: starting threshold per query = just below the C-th largest of the pre-pass group maxima
+// (tmax: [qtile][sample tile][group][128 query lanes]); -inf when fewer than C groups exist.
+template <int C>
+__global__ void __launch_bounds__(256)
+knn_threshold_kernel(const float* __restrict__ tmax, const int sample_tiles, float* __restrict__ thr_out) {
+  __shared__ uint64_t sel[C];
+  __shared__ uint64_t scratch[8 * C];
+  const int q = blockIdx.x;
+  const int qtile = q >> 7, ql = q & 127;
+  const int ns = sample_tiles * KNN_GROUPS;
+  const float* src = tmax + static_cast<size_t>(qtile) * ns * 128 + ql;
+  auto load = [&](int p, int e) -> uint64_t {
+    const int i = p * C + e;
+    return (i < ns) ? knn_key(src[static_cast<size_t>(i) * 128], static_cast<uint32_t>(i)) : 0ull;
+  };
+  block_top_c<C>(load, (ns + C - 1) / C, sel, scratch);
+  if (threadIdx.x == 0) thr_out[q] = (sel[C - 1] != 0ull) ? knn_next_below(knn_key_score(sel[C - 1])) : -INFINITY;
+}
+
+// Step 4.  One CTA (256 threads) per query.  `parts` candidate lists of C keys each (0 = empty slot).
 template <int C>
 __global__ void __launch_bounds__(256)
 knn_rerank_kernel(const uint64_t* __restrict__ cand, const int parts, const float* __restrict__ gallery,
                   const float* __restrict__ queries, const int n, const int d, const int k,
-                  const long long index_base, const float gmax_norm, long long* __restrict__ out_idx,
-                  float* __restrict__ out_score, int* __restrict__ certified) {
-  extern __shared__ uint64_t keys[];  // parts * C
+                  const long long index_base, const float gmax_norm, const float* __restrict__ thr_init,
+                  long long* __restrict__ out_idx, float* __restrict__ out_score, int* __restrict__ certified) {
   __shared__ uint64_t sel[C];
+  __shared__ uint64_t scratch[8 * C];
   __shared__ float exact[C];
-  __shared__ uint64_t red_key[8];
-  __shared__ int red_pos[8];
+  __shared__ uint64_t fin[C];
+  __shared__ int frank[C];
   __shared__ float qnorm2_s[8];
   const int q = blockIdx.x;
   const int qtile = q >> 7, ql = q & 127;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int total = parts * C;
-  for (int i = tid; i < total; i += 256) {
-    const int p = i / C, e = i - p * C;
-    keys[i] = cand[((static_cast<size_t>(qtile) * parts + p) * 128 + ql) * C + e];
-  }
-  __syncthreads();
-  // top-C by approximate key: C rounds of block arg-max (keys are unique per gallery row).
-  for (int r = 0; r < C; ++r) {
-    uint64_t best = 0;
-    int pos = -1;
-    for (int i = tid; i < total; i += 256) {
-      const uint64_t kv = keys[i];
-      if (kv > best) { best = kv; pos = i; }
+  const uint64_t* src = cand + (static_cast<size_t>(qtile) * parts * 128 + ql) * C;
+  auto load = [&](int p, int e) -> uint64_t { return src[static_cast<size_t>(p) * 128 * C + e]; };
+  block_top_c<C>(load, parts, sel, scratch);  // top-C by approximate (TF32) key
+  // exact canonical re-score of the selected candidates: warp w owns candidates w*C/8 .. +C/8, four at a time so
+  // their gallery rows stream concurrently (each accumulator chain keeps the canonical order).
+  const float* qv = queries + static_cast<size_t>(q) * d;
+  constexpr int PER_WARP = C / 8;
+#pragma unroll 1
+  for (int c0 = warp * PER_WARP; c0 < (warp + 1) * PER_WARP; c0 += 4) {
+    const float* g[4];
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint64_t kv = sel[c0 + u];
+      g[u] = gallery + static_cast<size_t>(kv != 0ull ? knn_key_index(kv) : 0u) * d;
+    }
+    for (int i = lane; i < d; i += 32) {
+      const float a = qv[i];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] = fmaf(a, g[u][i], acc[u]);
     }
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-      const uint64_t ob = __shfl_xor_sync(0xffffffffu, best, off);
-      const int op = __shfl_xor_sync(0xffffffffu, pos, off);
-      if (ob > best) { best = ob; pos = op; }
+    for (int u = 0; u < 4; ++u) {
+      float s = acc[u];
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, off);
+      if (lane == 0) exact[c0 + u] = (sel[c0 + u] != 0ull) ? s : -INFINITY;
     }
-    if (lane == 0) { red_key[warp] = best; red_pos[warp] = pos; }
-    __syncthreads();
-    if (tid == 0) {
-      uint64_t b = 0;
-      int p = -1;
-      for (int w = 0; w < 8; ++w)
-        if (red_key[w] > b) { b = red_key[w]; p = red_pos[w]; }
-      sel[r] = b;
-      if (p >= 0) keys[p] = 0;
-    }
-    __syncthreads();
-  }
-  // exact canonical re-score of the selected candidates (warp per candidate)
-  const float* qv = queries + static_cast<size_t>(q) * d;
-  for (int c = warp; c < C; c += 8) {
-    const uint64_t kv = sel[c];
-    float s = -INFINITY;
-    if (kv != 0) s = canonical_dot_warp(qv, gallery + static_cast<size_t>(knn_key_index(kv)) * d, d);
-    if (lane == 0) exact[c] = s;
   }
   {
     float a = 0.f;
@@ -406,24 +501,27 @@ knn_rerank_kernel(const uint64_t* __restrict__ cand, const int parts, const floa
           (kv != 0) ? static_cast<long long>(knn_key_index(kv)) + index_base : -1ll;
       out_score[static_cast<size_t>(q) * k + rank] = (kv != 0) ? exact[tid] : -INFINITY;
     }
-    // stash the final key so thread 0 can find the k-th exact score
-    keys[tid] = mine;
-    keys[C + tid] = static_cast<uint64_t>(rank);
+    fin[tid] = mine;
+    frank[tid] = rank;
   }
   __syncthreads();
   if (tid == 0 && certified) {
+    // Every row that is NOT a candidate has an approximate score <= a_c: the C-th candidate's when C candidates
+    // exist, else the scan's starting threshold (-inf without a pre-pass: then every row was a candidate).
+    const float a_c = (sel[C - 1] != 0ull) ? knn_key_score(sel[C - 1]) : (thr_init ? thr_init[q] : -INFINITY);
     int ok = 1;
-    if (sel[C - 1] != 0 && gmax_norm > 0.f) {  // otherwise every gallery row was a candidate
-      float qn2 = 0.f;
-      for (int w = 0; w < 8; ++w) qn2 += qnorm2_s[w];
-      const float err = (1.953125e-3f + static_cast<float>(d) * 1.2e-7f) * sqrtf(qn2) * gmax_norm;
-      const float a_c = knn_key_score(sel[C - 1]);  // approx score of the weakest candidate
-      float s_k = -INFINITY;
-      for (int j = 0; j < C; ++j)
-        if (static_cast<int>(keys[C + j]) == k - 1) s_k = knn_key_score(keys[j]);
-      ok = (s_k > a_c + err) ? 1 : 0;
-    } else if (sel[C - 1] != 0) {
-      ok = 0;  // no norm bound supplied: cannot certify
+    if (a_c != -INFINITY) {
+      if (gmax_norm > 0.f) {
+        float qn2 = 0.f;
+        for (int w = 0; w < 8; ++w) qn2 += qnorm2_s[w];
+        const float err = (1.953125e-3f + static_cast<float>(d) * 1.2e-7f) * sqrtf(qn2) * gmax_norm;
+        float s_k = -INFINITY;
+        for (int j = 0; j < C; ++j)
+          if (frank[j] == k - 1 && fin[j] != 0ull) s_k = knn_key_score(fin[j]);
+        ok = (s_k > a_c + err) ? 1 : 0;
+      } else {
+        ok = 0;  // no norm bound supplied: cannot certify
+      }
     }
     certified[q] = ok;
   }
@@ -515,35 +613,31 @@ static int knn_exact_slices(int C) { return C <= 32 ? 64 : 32; }
 
 using namespace ralf;
 
-extern "C" size_t ralf_knn_workspace_bytes(int n, int d, int q, int k) {
-  (void)d;
-  const int C = knn_c_for_k(k);
-  if (C == 0 || n <= 0 || q <= 0) return 0;
+static int knn_sample_tiles(int n) {
+  const int tiles = (n + 255) / 256;
+  return tiles < KNN_SAMPLE_TILES ? tiles : KNN_SAMPLE_TILES;
+}
+static size_t knn_cand_bytes(int n, int q, int C) {
   const size_t qtiles = (q + 127) / 128;
   size_t parts = knn_grid_x(n);
   if (parts < static_cast<size_t>(knn_exact_slices(C)) * 8) parts = static_cast<size_t>(knn_exact_slices(C)) * 8;
   return qtiles * parts * 128 * C * sizeof(uint64_t);
 }
 
-// knn_rerank_kernel serves both the tensor-core path (<= 148 lists) and the exact path (<= 512 lists).
-template <int C>
-static int knn_rerank_attr() {
-  static bool attr_set = false;
-  if (!attr_set) {
-    size_t need = static_cast<size_t>(knn_exact_slices(C)) * 8 * C * 8;
-    if (need < static_cast<size_t>(160) * C * 8) need = static_cast<size_t>(160) * C * 8;
-    cudaError_t e = cudaFuncSetAttribute(knn_rerank_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(need));
-    if (e != cudaSuccess) return set_cuda_error(e);
-    attr_set = true;
-  }
-  return 0;
+// workspace = [candidate lists][pre-pass group maxima: qtiles x 128 tiles x 8 groups x 128 lanes f32][thresholds]
+extern "C" size_t ralf_knn_workspace_bytes(int n, int d, int q, int k) {
+  (void)d;
+  const int C = knn_c_for_k(k);
+  if (C == 0 || n <= 0 || q <= 0) return 0;
+  const size_t qtiles = (q + 127) / 128;
+  return knn_cand_bytes(n, q, C) + qtiles * KNN_SAMPLE_TILES * KNN_GROUPS * 128 * sizeof(float) +
+         qtiles * 128 * sizeof(float);
 }
 
 template <int C>
 static int knn_topk_impl(const float* gallery, int n, int d, const float* queries, int q, int k,
                          long long index_base, float gmax, long long* out_idx, float* out_score, int* certified,
-                         uint64_t* cand, cudaStream_t st) {
+                         void* workspace, cudaStream_t st) {
   using Cfg = KnnCfg<C>;
   CUtensorMap tq, tg;
   int rc = make_kmajor_tmap(&tq, queries, 4, d, q, 1, d, 0, 128);
@@ -552,22 +646,30 @@ static int knn_topk_impl(const float* gallery, int n, int d, const float* querie
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(knn_scan_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(knn_scan_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(knn_scan_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_cuda_error(e);
     attr_set = true;
   }
-  rc = knn_rerank_attr<C>();
-  if (rc) return rc;
-  const int gx = knn_grid_x(n);
-  dim3 grid(gx, (q + 127) / 128);
+  const int qtiles = (q + 127) / 128;
+  uint64_t* cand = reinterpret_cast<uint64_t*>(workspace);
+  float* tmax = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + knn_cand_bytes(n, q, C));
+  float* thr = tmax + static_cast<size_t>(qtiles) * KNN_SAMPLE_TILES * KNN_GROUPS * 128;
   static const int debug_mode = getenv("RALF_KNN_DEBUG") ? atoi(getenv("RALF_KNN_DEBUG")) : 0;
-  knn_scan_kernel<C><<<grid, 192, Cfg::SMEM_BYTES, st>>>(tq, tg, n, d, q, cand, debug_mode);
+  const int ns = knn_sample_tiles(n);
+  knn_scan_kernel<C, true><<<dim3(ns, qtiles), 192, Cfg::SMEM_BYTES, st>>>(tq, tg, n, d, q, nullptr, nullptr, tmax,
+                                                                            debug_mode);
+  knn_threshold_kernel<C><<<qtiles * 128, 256, 0, st>>>(tmax, ns, thr);
+  const int gx = knn_grid_x(n);
+  knn_scan_kernel<C, false><<<dim3(gx, qtiles), 192, Cfg::SMEM_BYTES, st>>>(tq, tg, n, d, q, cand, thr, nullptr,
+                                                                            debug_mode);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e);
-  const size_t rr_smem = static_cast<size_t>(gx) * C * 8 < 2 * C * 8 ? 2 * C * 8 : static_cast<size_t>(gx) * C * 8;
-  knn_rerank_kernel<C><<<q, 256, rr_smem, st>>>(cand, gx, gallery, queries, n, d, k, index_base, gmax, out_idx,
-                                                 out_score, certified);
+  knn_rerank_kernel<C><<<q, 256, 0, st>>>(cand, gx, gallery, queries, n, d, k, index_base, gmax, thr, out_idx,
+                                          out_score, certified);
   return set_cuda_error(cudaGetLastError());
 }
 
@@ -582,12 +684,11 @@ extern "C" int ralf_knn_topk(const float* gallery, int n, int d, const float* qu
   if (d % 4) return RALF_ERR_ALIGN;  // TMA needs 16-byte row pitch
   if (!workspace || workspace_bytes < ralf_knn_workspace_bytes(n, d, q, k)) return RALF_ERR_WORKSPACE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  uint64_t* cand = reinterpret_cast<uint64_t*>(workspace);
   if (C == 32)
     return knn_topk_impl<32>(gallery, n, d, queries, q, k, index_base, gallery_max_norm, out_idx, out_score,
-                             certified, cand, st);
+                             certified, workspace, st);
   return knn_topk_impl<64>(gallery, n, d, queries, q, k, index_base, gallery_max_norm, out_idx, out_score,
-                           certified, cand, st);
+                           certified, workspace, st);
 }
 
 template <int C>
@@ -595,14 +696,12 @@ static int knn_exact_impl(const float* gallery, int n, int d, const float* queri
                           long long index_base, long long* out_idx, float* out_score, uint64_t* cand,
                           cudaStream_t st) {
   const int parts = knn_exact_slices(C) * 8;
-  int rc = knn_rerank_attr<C>();
-  if (rc) return rc;
   dim3 grid(knn_exact_slices(C), q);
   knn_exact_scan_kernel<C><<<grid, 256, 0, st>>>(gallery, queries, n, d, cand);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e);
-  knn_rerank_kernel<C><<<q, 256, static_cast<size_t>(parts) * C * 8, st>>>(
-      cand, parts, gallery, queries, n, d, k, index_base, 0.f, out_idx, out_score, nullptr);
+  knn_rerank_kernel<C><<<q, 256, 0, st>>>(cand, parts, gallery, queries, n, d, k, index_base, 0.f, nullptr, out_idx,
+                                          out_score, nullptr);
   return set_cuda_error(cudaGetLastError());
 }
 

@@ -13,7 +13,7 @@ ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2}
 
 # Number of OUR kernels launched through the C ABI (bench.py reports the delta over the timed region).
 _LAUNCHES = 0
-_KERNELS_PER_CALL = {"ralf_knn_topk": 2, "ralf_knn_topk_exact": 2, "ralf_knn_merge": 2, "ralf_ce_label_smooth": 2}
+_KERNELS_PER_CALL = {"ralf_knn_topk": 4, "ralf_knn_topk_exact": 2, "ralf_knn_merge": 2, "ralf_ce_label_smooth": 2}
 
 
 def launch_count() -> int:
