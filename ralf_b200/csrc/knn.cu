@@ -639,10 +639,8 @@ static int knn_topk_impl(const float* gallery, int n, int d, const float* querie
                          long long index_base, float gmax, long long* out_idx, float* out_score, int* certified,
                          void* workspace, cudaStream_t st) {
   using Cfg = KnnCfg<C>;
-  CUtensorMap tq, tg;
-  int rc = make_kmajor_tmap(&tq, queries, 4, d, q, 1, d, 0, 128);
-  if (rc) return rc;
-  rc = make_kmajor_tmap(&tg, gallery, 4, d, n, 1, d, 0, 256);
+  CUtensorMap tg;
+  int rc = make_kmajor_tmap(&tg, gallery, 4, d, n, 1, d, 0, 256);
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
@@ -654,23 +652,35 @@ static int knn_topk_impl(const float* gallery, int n, int d, const float* querie
     if (e != cudaSuccess) return set_cuda_error(e);
     attr_set = true;
   }
-  const int qtiles = (q + 127) / 128;
+  // Queries go through in passes of 128 (one query tile): every pass streams the gallery once and stays in the
+  // HBM-bound regime the kernel is built for (beyond ~280 queries per pass the TF32 MMAs, not HBM, set the time --
+  // SURVEY.md 8d).  The workspace is reused by the passes (stream order).
   uint64_t* cand = reinterpret_cast<uint64_t*>(workspace);
   float* tmax = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + knn_cand_bytes(n, q, C));
-  float* thr = tmax + static_cast<size_t>(qtiles) * KNN_SAMPLE_TILES * KNN_GROUPS * 128;
+  float* thr = tmax + static_cast<size_t>((q + 127) / 128) * KNN_SAMPLE_TILES * KNN_GROUPS * 128;
   static const int debug_mode = getenv("RALF_KNN_DEBUG") ? atoi(getenv("RALF_KNN_DEBUG")) : 0;
   const int ns = knn_sample_tiles(n);
-  knn_scan_kernel<C, true><<<dim3(ns, qtiles), 192, Cfg::SMEM_BYTES, st>>>(tq, tg, n, d, q, nullptr, nullptr, tmax,
-                                                                            debug_mode);
-  knn_threshold_kernel<C><<<qtiles * 128, 256, 0, st>>>(tmax, ns, thr);
   const int gx = knn_grid_x(n);
-  knn_scan_kernel<C, false><<<dim3(gx, qtiles), 192, Cfg::SMEM_BYTES, st>>>(tq, tg, n, d, q, cand, thr, nullptr,
-                                                                            debug_mode);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return set_cuda_error(e);
-  knn_rerank_kernel<C><<<q, 256, 0, st>>>(cand, gx, gallery, queries, n, d, k, index_base, gmax, thr, out_idx,
-                                          out_score, certified);
-  return set_cuda_error(cudaGetLastError());
+  for (int q0 = 0; q0 < q; q0 += 128) {
+    const int qn = q - q0 < 128 ? q - q0 : 128;
+    CUtensorMap tq;
+    rc = make_kmajor_tmap(&tq, queries + static_cast<size_t>(q0) * d, 4, d, qn, 1, d, 0, 128);
+    if (rc) return rc;
+    knn_scan_kernel<C, true><<<dim3(ns, 1), 192, Cfg::SMEM_BYTES, st>>>(tq, tg, n, d, qn, nullptr, nullptr, tmax,
+                                                                        debug_mode);
+    knn_threshold_kernel<C><<<128, 256, 0, st>>>(tmax, ns, thr);
+    knn_scan_kernel<C, false><<<dim3(gx, 1), 192, Cfg::SMEM_BYTES, st>>>(tq, tg, n, d, qn, cand, thr, nullptr,
+                                                                         debug_mode);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e);
+    knn_rerank_kernel<C><<<qn, 256, 0, st>>>(cand, gx, gallery, queries + static_cast<size_t>(q0) * d, n, d, k,
+                                             index_base, gmax, thr, out_idx + static_cast<size_t>(q0) * k,
+                                             out_score + static_cast<size_t>(q0) * k,
+                                             certified ? certified + q0 : nullptr);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e);
+  }
+  return 0;
 }
 
 extern "C" int ralf_knn_topk(const float* gallery, int n, int d, const float* queries, int q, int k,

@@ -374,9 +374,22 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # decoder
     # ------------------------------------------------------------------------------------------
-    def cross_kv(self, mem_s: torch.Tensor) -> torch.Tensor:
-        """K/V of the memory for all 6 decoder layers in one GEMM: fp32 [B*M, 6*512]."""
-        return self._gemm(mem_s, "decoder.ckv")[0]
+    def alloc_cross_kv(self, rows: int) -> list:
+        """Decoder cross-attention K/V cache, layer-major: 6 x fp32 [rows, 512] (K = cols 0..255, V = 256..511), so
+        one layer's K/V of a canvas is ONE contiguous 2 KB x M stream for the decode kernel."""
+        return [torch.empty((rows, 2 * D), dtype=torch.float32, device=self.dev) for _ in range(NLAYER)]
+
+    def cross_kv(self, mem_s: torch.Tensor, out: Optional[list] = None, row0: int = 0) -> list:
+        """K/V of the memory rows for all 6 decoder layers (one GEMM per layer, N = 512); written into rows
+        [row0, row0 + rows) of ``out`` when given (micro-batched encode)."""
+        rows = mem_s.shape[1]
+        if out is None:
+            out = self.alloc_cross_kv(rows)
+        w, b = self.w["decoder.ckv.w"], self.w["decoder.ckv.b"]
+        for i in range(NLAYER):
+            ops.gemm(mem_s, w[:, i * 2 * D:(i + 1) * 2 * D], bias=b[i * 2 * D:(i + 1) * 2 * D], npass=self.npass,
+                     out_f32=out[i][row0:row0 + rows])
+        return out
 
     def decoder_logits(self, seq: torch.Tensor, pad_mask: torch.Tensor, mem_s: torch.Tensor, B: int, Mlen: int):
         """Teacher-forced BaseDecoder.forward (common/common.py:84-135), causal + key padding masks."""
@@ -392,7 +405,7 @@ class Engine:
             x, _ = self._gemm(a, p + ".o", res=x)
             _, h = self._ln(x, p + ".norm2")
             q, _ = self._gemm(h, p + ".cq")
-            a = ops.attention(q, kvm[:, i * 512:i * 512 + D], kvm[:, i * 512 + D:(i + 1) * 512], B, NHEAD, S, Mlen, 32)
+            a = ops.attention(q, kvm[i][:, :D], kvm[i][:, D:], B, NHEAD, S, Mlen, 32)
             x, _ = self._gemm(a, p + ".co", res=x)
             _, h = self._ln(x, p + ".norm3")
             _, f = self._gemm(h, p + ".linear1", act="relu", want_f32=False, want_split=True)
@@ -401,12 +414,13 @@ class Engine:
         logits, _ = self._gemm(h, "decoder.head.1")
         return logits.view(B, S, self.vocab)
 
-    def generate(self, mem_s: torch.Tensor, B: int, Mlen: int, token_mask: torch.Tensor, bos_id: int, pad_id: int,
-                 steps: int, return_logits: bool = False):
+    def generate(self, mem_s: Optional[torch.Tensor], B: int, Mlen: int, token_mask: torch.Tensor, bos_id: int,
+                 pad_id: int, steps: int, return_logits: bool = False, kv: Optional[list] = None):
         """Greedy decode (retrieval_augmented_autoreg.py:244-300, cond_type uncond) with KV caches.
-        token_mask: uint8 [steps, V] (tokenizer.token_mask).  Returns seq int64 [B, steps] (BOS dropped)."""
+        token_mask: uint8 [steps, V] (tokenizer.token_mask).  Returns seq int64 [B, steps] (BOS dropped).
+        ``kv``: precomputed cross-attention cache (cross_kv) of all B canvases; else built from ``mem_s``."""
         dev = self.dev
-        kvm = self.cross_kv(mem_s)
+        kvm = kv if kv is not None else self.cross_kv(mem_s)
         seq = torch.full((B, steps + 1), pad_id, dtype=torch.int64, device=dev)
         seq[:, 0] = bos_id
         pad_mask = torch.zeros((B, steps + 1), dtype=torch.uint8, device=dev)
@@ -423,8 +437,7 @@ class Engine:
                 a = ops.attention_decode_append(qkv, kc[i], vc[i], t, B, NHEAD, 32, mask=pad_mask)
                 self._gemm(a, p + ".o", res=x, out_f32=x)
                 q, _ = self._gemm_ln(x, p + ".norm2", p + ".cq")
-                a = ops.attention_decode(q, kvm[:, i * 512:i * 512 + D], kvm[:, i * 512 + D:(i + 1) * 512], Mlen,
-                                         Mlen, B, NHEAD, 32)
+                a = ops.attention_decode(q, kvm[i][:, :D], kvm[i][:, D:], Mlen, Mlen, B, NHEAD, 32)
                 self._gemm(a, p + ".co", res=x, out_f32=x)
                 _, f = self._gemm_ln(x, p + ".norm3", p + ".linear1", act="relu", want_f32=False, want_split=True)
                 self._gemm(f, p + ".linear2", res=x, out_f32=x)

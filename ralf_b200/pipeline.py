@@ -21,9 +21,13 @@ from .retrieval import GpuRetriever
 
 class LayoutPipeline:
     def __init__(self, model, retriever: GpuRetriever, batch: int, height: int, width: int, *, top_k: int = 16,
-                 emb_dim: int = 512, use_graph: bool = True) -> None:
+                 emb_dim: int = 512, use_graph: bool = True, micro_batch: int = 128) -> None:
+        """``micro_batch``: canvases per encode pass.  Retrieval and the decode loop run over the whole batch; the
+        ResNet/encoder activations (im2col buffers, ~60 MB per canvas) only ever exist for one micro-batch, whose
+        memory K/V rows land in the batch-wide cross-attention cache."""
         self.model, self.retr = model, retriever
         self.B, self.H, self.W, self.k = batch, height, width, top_k
+        self.mb = min(micro_batch, batch)
         self.dev = model.device
         self.world, self.rank = retriever.world, retriever.rank
         self.eng = model.engine()
@@ -57,9 +61,17 @@ class LayoutPipeline:
     def _stage_main(self, idx: torch.Tensor):
         """idx: global top-k of this rank's canvases [B, k]."""
         self.idx_out.copy_(idx)
-        retrieved = self.retr.fetch(idx)
-        mem, mem_s = self.eng.encode(self.img, retrieved["packed"], self.const_seq, self.const_pad)
-        seq = self.eng.generate(mem_s, self.B, mem.shape[1], self.token_mask, self.ids["bos"], self.ids["pad"], self.S)
+        packed = self.retr.fetch(idx)["packed"]
+        kv, Mlen = None, 0
+        for b0 in range(0, self.B, self.mb):
+            b1 = min(self.B, b0 + self.mb)
+            mem, mem_s = self.eng.encode(self.img[b0:b1], packed[b0:b1], self.const_seq[b0:b1], self.const_pad[b0:b1])
+            Mlen = mem.shape[1]
+            if kv is None:
+                kv = self.eng.alloc_cross_kv(self.B * Mlen)
+            self.eng.cross_kv(mem_s, out=kv, row0=b0 * Mlen)
+            del mem, mem_s
+        seq = self.eng.generate(None, self.B, Mlen, self.token_mask, self.ids["bos"], self.ids["pad"], self.S, kv=kv)
         self.seq_out.copy_(seq)
 
     def _merge(self, idx, score):

@@ -95,3 +95,20 @@ def test_knn_large_roundtrip_property(cuda_device):
     assert cert.all()
     ei, es, _ = ops.knn_topk(G, G[rows[:2]].contiguous(), 16, exact=True)
     assert torch.equal(ei, idx[:2]) and torch.equal(es, score[:2])
+
+
+def test_knn_adversarial_row_order(cuda_device):
+    """Gallery sorted by the score of query 0 (ascending: every later row beats all earlier ones, so the running
+    threshold never protects the candidate lists and they overflow / compact constantly), descending for query 1
+    after a flip, plus a query batch wider than one 128-query pass."""
+    from ralf_b200 import ops
+
+    G, Q = _data(60000, 512, 130, seed=21)
+    G = G[np.argsort(G @ Q[0], kind="stable")]
+    for Gx in (G, np.ascontiguousarray(G[::-1])):
+        oi, os_ = oracle_knn.topk(Gx, Q, 16)
+        gi, gs, cert = ops.knn_topk(torch.from_numpy(Gx).to(cuda_device), torch.from_numpy(Q).to(cuda_device), 16,
+                                    gallery_max_norm=1.0001)
+        np.testing.assert_array_equal(gi.cpu().numpy(), oi)
+        np.testing.assert_array_equal(gs.cpu().numpy().view(np.uint32), os_.view(np.uint32))
+        assert cert.cpu().numpy().all()
