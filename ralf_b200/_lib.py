@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libralf_b200.so")
+LIB_PATH = os.environ.get("RALF_B200_LIB", os.path.join(HERE, "libralf_b200.so"))  # override: A/B builds
 
 STATUS = {
     0: "RALF_OK", -1: "RALF_ERR_SHAPE", -2: "RALF_ERR_ALIGN", -3: "RALF_ERR_NULL", -4: "RALF_ERR_CUDA",

@@ -17,6 +17,7 @@
 // mbarriers, tcgen05.commit releases stages and signals the epilogue.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <unordered_map>
@@ -57,35 +58,134 @@ struct GemmCfg {
   static constexpr int A_BYTES = 128 * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = P * (A_BYTES + B_BYTES);
-  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES_RAW = (192 * 1024) / STAGE_BYTES;
   static constexpr int MAX_STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   // The ring depth is a launch-time choice (min(MAX_STAGES, k-blocks)): short-K GEMMs then take little
   // shared memory and several CTAs share an SM, hiding each other's prologue / epilogue.
-  static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/; }
+  static constexpr int smem_bytes(int stages) {
+    return stages * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/ + 32768 /*epilogue staging: 8 warps x 4 KB*/;
+  }
   static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator buffers
 };
 
-// Epilogue of one 128 x BN accumulator tile: each thread owns one row (TMEM lane), walks the columns in chunks of 32.
+// ---- warp-level staging: row-per-thread registers <-> coalesced global memory ------------------------------------
+// The TMEM accumulator hands every epilogue thread ONE ROW of the tile (32 fp32 columns per chunk).  Storing / loading
+// global memory in that shape makes each warp instruction touch 32 different rows (32 L1 wavefronts per instruction).
+// Instead every warp owns a 4 KB shared-memory buffer: rows are written 16 bytes at a time with an XOR swizzle
+// (conflict free) and then moved with the lanes running ALONG the rows, so a warp instruction covers full 64 / 128-byte
+// row segments.  NV = 16-byte vectors per row chunk: 8 for fp32 (32 columns = 128 B), 4 for one bf16 plane (64 B).
+template <int NV>
+__device__ __forceinline__ int epi_swz(int row) { return NV == 8 ? (row & 7) : ((row >> 1) & 3); }
+
+// coalesced global -> registers: pass p moves rows p*(32/NV) .. +32/NV; lane = (row within pass, vector).
+// my_base = global address of this lane's own row chunk (0 when the row is out of range).
+template <int NV>
+__device__ __forceinline__ void epi_load_coalesced(const unsigned long long my_base, const int lane, uint4 (&r)[NV]) {
+#pragma unroll
+  for (int p = 0; p < NV; ++p) {
+    const int rr = p * (32 / NV) + lane / NV;
+    const unsigned long long base = __shfl_sync(0xffffffffu, my_base, rr);
+    r[p] = make_uint4(0u, 0u, 0u, 0u);
+    if (base) r[p] = *reinterpret_cast<const uint4*>(base + static_cast<unsigned long long>(lane % NV) * 16ull);
+  }
+}
+// registers (coalesced order) -> shared -> this thread's own row
+template <int NV>
+__device__ __forceinline__ void epi_stage_to_row(uint4* buf, const int lane, const uint4 (&r)[NV], uint4 (&mine)[NV]) {
+#pragma unroll
+  for (int p = 0; p < NV; ++p) {
+    const int rr = p * (32 / NV) + lane / NV;
+    buf[rr * NV + ((lane % NV) ^ epi_swz<NV>(rr))] = r[p];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) mine[i] = buf[lane * NV + (i ^ epi_swz<NV>(lane))];
+  __syncwarp();
+}
+// this thread's own row -> shared -> coalesced global store
+template <int NV>
+__device__ __forceinline__ void epi_row_to_global(uint4* buf, const int lane, const uint4 (&mine)[NV],
+                                                  const unsigned long long my_base) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) buf[lane * NV + (i ^ epi_swz<NV>(lane))] = mine[i];
+  __syncwarp();
+#pragma unroll
+  for (int p = 0; p < NV; ++p) {
+    const int rr = p * (32 / NV) + lane / NV;
+    const unsigned long long base = __shfl_sync(0xffffffffu, my_base, rr);
+    const uint4 v = buf[rr * NV + ((lane % NV) ^ epi_swz<NV>(rr))];
+    if (base) *reinterpret_cast<uint4*>(base + static_cast<unsigned long long>(lane % NV) * 16ull) = v;
+  }
+  __syncwarp();
+}
+
+// two bf16 planes (hi, lo) at once: plane p lives in buf[p*128 ..], one barrier pair for both
+__device__ __forceinline__ void epi_stage_to_row2(uint4* buf, const int lane, const uint4 (&rh)[4], const uint4 (&rl)[4],
+                                                  uint4 (&mh)[4], uint4 (&ml)[4]) {
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int rr = p * 8 + lane / 4;
+    const int o = rr * 4 + ((lane % 4) ^ epi_swz<4>(rr));
+    buf[o] = rh[p];
+    buf[128 + o] = rl[p];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int o = lane * 4 + (i ^ epi_swz<4>(lane));
+    mh[i] = buf[o];
+    ml[i] = buf[128 + o];
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void epi_row_to_global2(uint4* buf, const int lane, const uint4 (&mh)[4], const uint4 (&ml)[4],
+                                                   const unsigned long long base_hi, const unsigned long long base_lo,
+                                                   const bool write_lo) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int o = lane * 4 + (i ^ epi_swz<4>(lane));
+    buf[o] = mh[i];
+    buf[128 + o] = ml[i];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int rr = p * 8 + lane / 4;
+    const unsigned long long bh = __shfl_sync(0xffffffffu, base_hi, rr);
+    const unsigned long long bl = __shfl_sync(0xffffffffu, base_lo, rr);
+    const int o = rr * 4 + ((lane % 4) ^ epi_swz<4>(rr));
+    const unsigned long long off = static_cast<unsigned long long>(lane % 4) * 16ull;
+    if (bh) {
+      *reinterpret_cast<uint4*>(bh + off) = buf[o];
+      if (write_lo) *reinterpret_cast<uint4*>(bl + off) = buf[128 + o];
+    }
+  }
+  __syncwarp();
+}
+
+// Epilogue of columns [c_begin, c_end) of one 128 x BN accumulator tile: each thread owns one row (TMEM lane) and
+// walks the columns in chunks of 32.  stg = this warp's 4 KB staging buffer (256 uint4).
 template <int BN>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpi& ep, const uint32_t tacc, const int quad, const int lane,
-                                                   const int m0, const int n0, const int M, const int N) {
+                                                   const int m0, const int n0, const int M, const int N, uint4* stg,
+                                                   const int c_begin = 0, const int c_end = BN) {
     const int r = m0 + quad * 32 + lane;
     const bool row_ok = r < M;
     const long long out_row =
         (long long)(r / ep.rows_per_group) * ep.group_stride + ep.group_offset + r % ep.rows_per_group;
     const long long res_row = ep.res_row_mod > 0 ? (r % ep.res_row_mod) : r;
+    auto gaddr = [&](const void* p) { return row_ok ? reinterpret_cast<unsigned long long>(p) : 0ull; };
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
+    for (int c = c_begin; c < c_end; c += 32) {
       if (n0 + c >= N) break;
+      const int nbase = n0 + c;
+      const bool full = ep.vec_ok && (nbase + 32 <= N);  // warp-uniform
       uint32_t v[32];
       tmem_ld_32x32(tacc + (static_cast<uint32_t>(quad * 32) << 16) + c, v);
       tmem_ld_wait();
-      if (!row_ok) continue;
-      const int nbase = n0 + c;
       float x[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-      const bool full = ep.vec_ok && (nbase + 32 <= N);
       if (full) {
         if (ep.bias) {
 #pragma unroll
@@ -94,31 +194,37 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpi& ep, const uint
             x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
           }
         }
-        if (ep.act) {
+        if (ep.act == 1) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = apply_act(x[j], ep.act);
+          for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+        } else if (ep.act == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = 0.5f * x[j] * (1.f + erff(x[j] * 0.70710678118654752440f));
         }
         if (ep.res) {
-          const float* rp = ep.res + res_row * ep.res_ld + nbase;
+          uint4 rq[8], mine[8];
+          epi_load_coalesced<8>(gaddr(ep.res + res_row * ep.res_ld + nbase), lane, rq);
+          epi_stage_to_row<8>(stg, lane, rq, mine);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(rp + j);
-            x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
+          for (int j = 0; j < 8; ++j) {
+            x[4 * j] += __uint_as_float(mine[j].x); x[4 * j + 1] += __uint_as_float(mine[j].y);
+            x[4 * j + 2] += __uint_as_float(mine[j].z); x[4 * j + 3] += __uint_as_float(mine[j].w);
           }
         }
         if (ep.res_split) {
+          uint4 rqh[4], rql[4], mh[4], ml[4];
           const __nv_bfloat16* rh = ep.res_split + res_row * ep.res_ld + nbase;
-          const __nv_bfloat16* rl = rh + ep.res_plane;
+          epi_load_coalesced<4>(gaddr(rh), lane, rqh);
+          epi_load_coalesced<4>(gaddr(rh + ep.res_plane), lane, rql);
+          epi_stage_to_row2(stg, lane, rqh, rql, mh, ml);
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const uint4 h = *reinterpret_cast<const uint4*>(rh + j);
-            const uint4 l = *reinterpret_cast<const uint4*>(rl + j);
-            const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
-            const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t hw[4] = {mh[j].x, mh[j].y, mh[j].z, mh[j].w};
+            const uint32_t lw[4] = {ml[j].x, ml[j].y, ml[j].z, ml[j].w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              x[j + 2 * q] += __uint_as_float(hw[q] << 16) + __uint_as_float(lw[q] << 16);
-              x[j + 2 * q + 1] +=
+              x[8 * j + 2 * q] += __uint_as_float(hw[q] << 16) + __uint_as_float(lw[q] << 16);
+              x[8 * j + 2 * q + 1] +=
                   __uint_as_float(hw[q] & 0xffff0000u) + __uint_as_float(lw[q] & 0xffff0000u);
             }
           }
@@ -128,49 +234,55 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpi& ep, const uint
           for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
         }
         if (ep.out_f32) {
-          float* op = ep.out_f32 + out_row * ep.out_ld + ep.out_col0 + nbase;
+          uint4 mine[8];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(op + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+          for (int j = 0; j < 8; ++j)
+            mine[j] = make_uint4(__float_as_uint(x[4 * j]), __float_as_uint(x[4 * j + 1]), __float_as_uint(x[4 * j + 2]),
+                                 __float_as_uint(x[4 * j + 3]));
+          epi_row_to_global<8>(stg, lane, mine, gaddr(ep.out_f32 + out_row * ep.out_ld + ep.out_col0 + nbase));
         }
         if (ep.out_split) {
-          __nv_bfloat16* oh = ep.out_split + out_row * ep.out_ld + ep.out_col0 + nbase;
-          __nv_bfloat16* ol = oh + ep.out_plane;
+          uint4 mh[4], ml[4];
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
+          for (int j = 0; j < 4; ++j) {
             uint32_t hw[4], lw[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(x[j + 2 * q], h0, l0);
-              split_bf16(x[j + 2 * q + 1], h1, l1);
+              split_bf16(x[8 * j + 2 * q], h0, l0);
+              split_bf16(x[8 * j + 2 * q + 1], h1, l1);
               hw[q] = pack_bf16(h0, h1);
               lw[q] = pack_bf16(l0, l1);
             }
-            *reinterpret_cast<uint4*>(oh + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            if (ep.split_lo) *reinterpret_cast<uint4*>(ol + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            mh[j] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            ml[j] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
           }
+          __nv_bfloat16* oh = ep.out_split + out_row * ep.out_ld + ep.out_col0 + nbase;
+          epi_row_to_global2(stg, lane, mh, ml, gaddr(oh), gaddr(oh + ep.out_plane), ep.split_lo != 0);
         }
-      } else {
-#pragma unroll 1
+      } else if (row_ok) {
+        // ragged / unaligned tail: scalar, but with STATIC register indices (a dynamically indexed x[] would push the
+        // whole accumulator chunk into local memory for the vector path above as well)
+#pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int n = nbase + j;
-          if (n >= N) break;
-          float y = x[j];
-          if (ep.bias) y += __ldg(ep.bias + n);
-          if (ep.act) y = apply_act(y, ep.act);
-          if (ep.res) y += ep.res[res_row * ep.res_ld + n];
-          if (ep.res_split) {
-            y += __bfloat162float(ep.res_split[res_row * ep.res_ld + n]) +
-                 __bfloat162float(ep.res_split[ep.res_plane + res_row * ep.res_ld + n]);
-          }
-          if (ep.post_relu) y = fmaxf(y, 0.f);
-          if (ep.out_f32) ep.out_f32[out_row * ep.out_ld + ep.out_col0 + n] = y;
-          if (ep.out_split) {
-            __nv_bfloat16 h, l;
-            split_bf16(y, h, l);
-            ep.out_split[out_row * ep.out_ld + ep.out_col0 + n] = h;
-            if (ep.split_lo) ep.out_split[ep.out_plane + out_row * ep.out_ld + ep.out_col0 + n] = l;
+          if (n < N) {
+            float y = x[j];
+            if (ep.bias) y += __ldg(ep.bias + n);
+            if (ep.act) y = apply_act(y, ep.act);
+            if (ep.res) y += ep.res[res_row * ep.res_ld + n];
+            if (ep.res_split) {
+              y += __bfloat162float(ep.res_split[res_row * ep.res_ld + n]) +
+                   __bfloat162float(ep.res_split[ep.res_plane + res_row * ep.res_ld + n]);
+            }
+            if (ep.post_relu) y = fmaxf(y, 0.f);
+            if (ep.out_f32) ep.out_f32[out_row * ep.out_ld + ep.out_col0 + n] = y;
+            if (ep.out_split) {
+              __nv_bfloat16 h, l;
+              split_bf16(y, h, l);
+              ep.out_split[out_row * ep.out_ld + ep.out_col0 + n] = h;
+              if (ep.split_lo) ep.out_split[ep.out_plane + out_row * ep.out_ld + ep.out_col0 + n] = l;
+            }
           }
         }
       }
@@ -178,7 +290,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpi& ep, const uint
 }
 
 template <int BN, int NPASS>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmEpi ep, const int M, const int N, const int K, const int STAGES) {
   using Cfg = GemmCfg<BN, NPASS>;
@@ -191,6 +303,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull_bar = empty_bar + STAGES;  // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;      // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint4* stage_all = reinterpret_cast<uint4*>(smem + STAGES * Cfg::STAGE_BYTES + 512);  // 4 x 4 KB, 16-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -207,7 +320,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 128);
+      mbar_init(&tempty_bar[b], BN >= 64 ? 256 : 128);
     }
     fence_mbar_init();
     // Prologue prefetch: the first ring of TMA loads needs nothing but the barriers this thread just initialised,
@@ -295,15 +408,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ------------------------------- epilogue ---------------------------------------------
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // Eight epilogue warps: warp w may only touch TMEM lanes 32*(w%4)..; warps 2-5 take the first half of the tile's
+    // columns, warps 6-9 the second half (BN = 32: one chunk, the second group idles).
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int CH = BN >= 64 ? BN / 2 : BN;
     int it = 0;
+    if (BN >= 64 || half == 0)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
     const int buf = it & 1;
     const int m0 = (tile / tiles_n) * 128, n0 = (tile % tiles_n) * BN;
     mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
     tc_fence_after();
     const uint32_t tacc = tmem_base + buf * BN;
-    gemm_epilogue_tile<BN>(ep, tacc, quad, lane, m0, n0, M, N);
+    gemm_epilogue_tile<BN>(ep, tacc, quad, lane, m0, n0, M, N, stage_all + (warp - 2) * 256, half * CH, half * CH + CH);
     tc_fence_before();
     mbar_arrive(&tempty_bar[buf]);
     }  // tile loop
@@ -345,6 +463,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmB, const float* __restrict_
   uint64_t* aready_bar = full_bar + KB;
   uint64_t* tfull_bar = aready_bar + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+  uint4* stage_all = reinterpret_cast<uint4*>(smem_b + KB * 2 * B_PLANE + 256);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;
 
@@ -437,7 +556,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmB, const float* __restrict_
     // ---- epilogue ----
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
-    gemm_epilogue_tile<BN>(ep, tmem_base, warp & 3, lane, 0, n0, M, N);
+    gemm_epilogue_tile<BN>(ep, tmem_base, warp & 3, lane, 0, n0, M, N, stage_all + (warp & 3) * 256);
   }
   tc_fence_before();
   __syncthreads();
@@ -531,14 +650,34 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::smem_bytes(Cfg::MAX_STAGES));
     if (e != cudaSuccess) return set_cuda_error(e);
+    // several CTAs per SM only materialise when the SM is configured with the full shared-memory carve-out
+    e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, NPASS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return set_cuda_error(e);
     attr_set = true;
   }
   const long long num_tiles = static_cast<long long>((N + BN - 1) / BN) * ((M + 127) / 128);
   const int sms = num_sms();
-  dim3 grid(static_cast<unsigned>(num_tiles < sms ? num_tiles : sms));
   const int nkb = (K + 63) / 64;
   const int stages = nkb < Cfg::MAX_STAGES ? nkb : Cfg::MAX_STAGES;
-  gemm_bf16_kernel<BN, NPASS><<<grid, 192, Cfg::smem_bytes(stages), st>>>(ta, tb, ep, M, N, K, stages);
+  // Short-K GEMMs are bound by their epilogue's memory traffic, not by the MMAs: their small smem ring lets several
+  // persistent CTAs share an SM (limited by shared memory, 512 TMEM columns and an env override for A/B runs), which
+  // multiplies the loads / stores in flight per SM.
+  static const int occ_cap = getenv("RALF_GEMM_OCC") ? atoi(getenv("RALF_GEMM_OCC")) : 4;
+  static int occ_cache[16] = {0};
+  int occ = occ_cache[stages];
+  if (occ == 0) {
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gemm_bf16_kernel<BN, NPASS>, 320,
+                                                                  Cfg::smem_bytes(stages));
+    if (e != cudaSuccess) return set_cuda_error(e);
+    if (occ > static_cast<int>(512 / Cfg::TMEM_COLS)) occ = 512 / Cfg::TMEM_COLS;
+    if (occ < 1) occ = 1;
+    occ_cache[stages] = occ;
+  }
+  if (occ > occ_cap) occ = occ_cap;
+  const long long max_ctas = static_cast<long long>(sms) * occ;
+  dim3 grid(static_cast<unsigned>(num_tiles < max_ctas ? num_tiles : max_ctas));
+  gemm_bf16_kernel<BN, NPASS><<<grid, 320, Cfg::smem_bytes(stages), st>>>(ta, tb, ep, M, N, K, stages);
   return set_cuda_error(cudaGetLastError());
 }
 
@@ -607,7 +746,7 @@ extern "C" int ralf_gemm(const RalfGemmArgs* a, void* stream) {
 template <int BN>
 static int launch_gemm_ln(const CUtensorMap& tb, const float* x, int ldx, const float* gamma, const float* beta, float eps,
                           const GemmEpi& ep, int M, int N, cudaStream_t st) {
-  constexpr int SMEM = 4 * 2 * 128 * 128 + 4 * 2 * BN * 128 + 1024 + 256;
+  constexpr int SMEM = 4 * 2 * 128 * 128 + 4 * 2 * BN * 128 + 1024 + 256 + 16384;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_ln_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
