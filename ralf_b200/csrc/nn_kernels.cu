@@ -35,6 +35,9 @@ __device__ __forceinline__ float load_split(const __nv_bfloat16* hi_plane, long 
 // LayerNorm over the last dim (nn.LayerNorm, eps 1e-5; common/attention.py:20, nn.Transformer*Layer
 // norms).  One warp per row; D <= 1024, D % 32 == 0.
 // ------------------------------------------------------------------------------------------------
+// PER = D / 32 as a template parameter keeps the row in registers (a run-time trip count indexes v[] dynamically and
+// pushes it to local memory).
+template <int PER>
 __global__ void layernorm_kernel(const float* __restrict__ x, long long in_ld, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float eps, int M, int D,
                                  float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_split,
@@ -43,23 +46,23 @@ __global__ void layernorm_kernel(const float* __restrict__ x, long long in_ld, c
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
   const float* xr = x + static_cast<long long>(row) * in_ld;
-  float v[32];
-  const int per = D >> 5;
+  float v[PER];
+  constexpr int per = PER;
   float s = 0.f;
-#pragma unroll 8
+#pragma unroll
   for (int i = 0; i < per; ++i) {
     v[i] = xr[lane + 32 * i];
     s += v[i];
   }
   const float mean = warp_sum(s) / static_cast<float>(D);
   float sq = 0.f;
-#pragma unroll 8
+#pragma unroll
   for (int i = 0; i < per; ++i) {
     const float dlt = v[i] - mean;
     sq += dlt * dlt;
   }
   const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(D) + eps);
-#pragma unroll 8
+#pragma unroll
   for (int i = 0; i < per; ++i) {
     const int c = lane + 32 * i;
     const float y = (v[i] - mean) * rstd * gamma[c] + beta[c];
@@ -276,6 +279,86 @@ attention_decode_kernel(const float* __restrict__ q, int ldq, const float* k /* 
     const float inv = 1.f / (red_l[0] + red_l[1] + red_l[2] + red_l[3]);
     const float y = (red_o[0][threadIdx.x] + red_o[1][threadIdx.x] + red_o[2][threadIdx.x] + red_o[3][threadIdx.x]) * inv;
     store_split(out_split, out_plane, static_cast<long long>(b) * ldo + h * DH + threadIdx.x, y);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cross-attention decode step over the memory K/V cache, single pass ("flash decoding" per head): one CTA per
+// canvas, one warp per head.  A warp walks its head's keys 32 at a time: the K AND V rows of the batch are requested
+// together (16 x LDG.128 per lane = 8 KB per warp in flight), scores, online-softmax rescale and the P.V update follow
+// from registers -- half the dependent HBM round trips of the two-pass kernel above, and the eight warps of a CTA
+// consume the canvas's K/V rows (layer-major cache: 2 KB contiguous per memory token) as one sequential stream.
+// No key-padding mask (BaseDecoder passes none for the memory, common/common.py:123-131).
+// ------------------------------------------------------------------------------------------------
+template <int DH>
+__global__ void __launch_bounds__(256)
+attention_decode_stream_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k,
+                               const float* __restrict__ v, long long kv_bstride, int ldk, int Tk, int H, float scale,
+                               __nv_bfloat16* __restrict__ out_split, long long out_plane, int ldo) {
+  constexpr int CPL = DH / 4;    // lanes per key row (16 B each)
+  constexpr int KPI = 32 / CPL;  // keys per warp-wide load
+  constexpr int UN = 32 / KPI;   // loads per batch of 32 keys
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x;
+  if (h >= H) return;
+  const int kk = lane / CPL, c = lane % CPL;
+  float4 q4 = *reinterpret_cast<const float4*>(q + static_cast<long long>(b) * ldq + h * DH + 4 * c);
+  q4.x *= scale; q4.y *= scale; q4.z *= scale; q4.w *= scale;
+  const float* kb = k + static_cast<long long>(b) * kv_bstride * ldk + h * DH + 4 * c;
+  const float* vb = v + static_cast<long long>(b) * kv_bstride * ldk + h * DH + 4 * c;
+  float m = -INFINITY, l = 0.f;
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+  for (int j0 = 0; j0 < Tk; j0 += 32) {
+    float4 kf[UN], vf[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int j = j0 + u * KPI + kk;
+      kf[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      vf[u] = kf[u];
+      if (j < Tk) {
+        kf[u] = __ldcs(reinterpret_cast<const float4*>(kb + static_cast<long long>(j) * ldk));
+        vf[u] = __ldcs(reinterpret_cast<const float4*>(vb + static_cast<long long>(j) * ldk));
+      }
+    }
+    float s[UN];
+    float bm = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      float d = q4.x * kf[u].x + q4.y * kf[u].y + q4.z * kf[u].z + q4.w * kf[u].w;
+#pragma unroll
+      for (int off = CPL >> 1; off >= 1; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+      s[u] = (j0 + u * KPI + kk < Tk) ? d : -INFINITY;
+      bm = fmaxf(bm, s[u]);
+    }
+#pragma unroll
+    for (int off = CPL; off < 32; off <<= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, off));
+    const float m_new = fmaxf(m, bm);  // finite: every batch holds at least one valid key
+    const float corr = __expf(m - m_new);
+    l *= corr;
+    o.x *= corr; o.y *= corr; o.z *= corr; o.w *= corr;
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const float p = __expf(s[u] - m_new);  // -inf -> 0
+      l += p;
+      o.x = fmaf(p, vf[u].x, o.x); o.y = fmaf(p, vf[u].y, o.y);
+      o.z = fmaf(p, vf[u].z, o.z); o.w = fmaf(p, vf[u].w, o.w);
+    }
+    m = m_new;
+  }
+#pragma unroll
+  for (int off = CPL; off < 32; off <<= 1) {
+    o.x += __shfl_xor_sync(0xffffffffu, o.x, off); o.y += __shfl_xor_sync(0xffffffffu, o.y, off);
+    o.z += __shfl_xor_sync(0xffffffffu, o.z, off); o.w += __shfl_xor_sync(0xffffffffu, o.w, off);
+    l += __shfl_xor_sync(0xffffffffu, l, off);
+  }
+  if (kk == 0) {
+    const float inv = 1.f / l;
+    const long long off0 = static_cast<long long>(b) * ldo + h * DH + 4 * c;
+    store_split(out_split, out_plane, off0 + 0, o.x * inv);
+    store_split(out_split, out_plane, off0 + 1, o.y * inv);
+    store_split(out_split, out_plane, off0 + 2, o.z * inv);
+    store_split(out_split, out_plane, off0 + 3, o.w * inv);
   }
 }
 
@@ -638,9 +721,16 @@ extern "C" int ralf_layernorm(const float* x, long long in_ld, const float* gamm
                               int M, int D, float* out_f32, void* out_split, long long out_plane, void* stream) {
   if (!x || !gamma || !beta) return RALF_ERR_NULL;
   if (M <= 0 || D <= 0 || D > 1024 || (D & 31)) return RALF_ERR_SHAPE;
-  layernorm_kernel<<<(M + 7) / 8, 256, 0, ST(stream)>>>(x, in_ld, gamma, beta, eps, M, D, out_f32, BF(out_split),
-                                                       out_plane);
-  return set_cuda_error(cudaGetLastError());
+#define RALF_LN_CASE(P)                                                                                          \
+  if (D == 32 * P) {                                                                                            \
+    layernorm_kernel<P><<<(M + 7) / 8, 256, 0, ST(stream)>>>(x, in_ld, gamma, beta, eps, M, D, out_f32,         \
+                                                             BF(out_split), out_plane);                         \
+    return set_cuda_error(cudaGetLastError());                                                                  \
+  }
+  RALF_LN_CASE(8)   // d_model = 256: every LayerNorm of the RALF path
+  RALF_LN_CASE(1) RALF_LN_CASE(2) RALF_LN_CASE(4) RALF_LN_CASE(16) RALF_LN_CASE(32)
+#undef RALF_LN_CASE
+  return RALF_ERR_SHAPE;  // D / 32 must be a power of two <= 32
 }
 
 extern "C" int ralf_attention(const float* q, int ldq, const float* k, const float* v, int ldk,
@@ -668,6 +758,15 @@ static int attention_decode_impl(const float* q, int ldq, const float* k, const 
   if (!q || !k || !v || !out_split) return RALF_ERR_NULL;
   if (B <= 0 || H <= 0 || Tk <= 0 || Tk > 2048 || (head_dim != 32 && head_dim != 64)) return RALF_ERR_SHAPE;
   if ((ldq & 3) || (ldk & 3)) return RALF_ERR_ALIGN;
+  if (!key_padding_mask && !knew && H <= 8 && Tk >= 64) {  // memory cross-attention: streaming single-pass kernel
+    if (head_dim == 32)
+      attention_decode_stream_kernel<32><<<B, 32 * H, 0, ST(stream)>>>(q, ldq, k, v, kv_bstride, ldk, Tk, H, scale,
+                                                                      BF(out_split), out_plane, ldo);
+    else
+      attention_decode_stream_kernel<64><<<B, 32 * H, 0, ST(stream)>>>(q, ldq, k, v, kv_bstride, ldk, Tk, H, scale,
+                                                                      BF(out_split), out_plane, ldo);
+    return set_cuda_error(cudaGetLastError());
+  }
   const size_t smem = static_cast<size_t>((Tk + 31) & ~31) * sizeof(float);
   const int grid = B * H;
   const int warps = 4;
