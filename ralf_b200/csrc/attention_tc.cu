@@ -1,0 +1,283 @@
+// Multi-head self-attention of the image encoder on the 5th-gen tensor cores (tcgen05 + TMEM), fp32-faithful.
+//
+// Replaces the scalar attention of nn.MultiheadAttention inside nn.TransformerEncoderLayer
+// (image2layout/train/models/retrieval_augmented_autoreg.py:116-126; 8 heads x 32, T = h*w image tokens) for the
+// shape class that dominates the step: head_dim 32, no mask, Tk <= 256 keys (one key tile), any Tq.
+//
+// One CTA (128 threads) per (batch, head); it keeps the head's K and V^T in shared memory and walks the queries in
+// tiles of 128:
+//   S[128, 256]  = Q K^T           tcgen05.mma kind::f16, operands "split" bf16 (hi | lo of every fp32 value, 3 passes:
+//                                  hi.lo + lo.hi + hi.hi  ->  ~2^-17 relative, see gemm.cu), fp32 accumulators in TMEM
+//   P            = exp(scale (S - rowmax))   thread r owns row r: tcgen05.ld, 2 sweeps, P written BACK TO TMEM as
+//                                  split bf16 (tcgen05.st) -- it never touches shared or global memory
+//   O[128, 32]   = P V             tcgen05.mma with the A operand read from TMEM (P), B = V^T from shared memory
+//   out          = O / rowsum      split bf16 rows for the out-projection GEMM
+// TMEM columns: [0,256) S, later O in [0,32);  [256,384) P hi;  [384,512) P lo  (bf16 pairs, 2 keys per column).
+// Shared-memory operands are K-major rows of 128 bytes in the SWIZZLE_128B layout; Q and K rows hold
+// [hi(32) | lo(32)] so one tile serves both planes (descriptor start offset 0 / 64 bytes).
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "ralf_internal.h"
+
+namespace ralf {
+
+__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+constexpr int ATC_Q_BYTES = 128 * 128;       // 128 queries x [hi 64 B | lo 64 B]
+constexpr int ATC_K_BYTES = 256 * 128;       // 256 keys
+constexpr int ATC_VT_PLANE = 4 * 32 * 128;   // 4 key blocks x 32 d-rows x 128 B (64 keys)
+constexpr int ATC_SMEM = ATC_Q_BYTES + ATC_K_BYTES + 2 * ATC_VT_PLANE + 1024 + 64;
+
+// fp32 row segment (8 values) -> hi / lo bf16 chunks (16 B each)
+__device__ __forceinline__ void split8(const float4 a, const float4 b, uint4& hi, uint4& lo) {
+  const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(f[2 * i], h0, l0);
+    split_bf16(f[2 * i + 1], h1, l1);
+    h[i] = pack_bf16(h0, h1);
+    l[i] = pack_bf16(l0, l1);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__global__ void __launch_bounds__(128)
+attention_tc_kernel(const float* __restrict__ q, const int ldq, const float* __restrict__ k,
+                    const float* __restrict__ v, const int ldk, const int Tq, const int Tk, const float scale,
+                    __nv_bfloat16* __restrict__ out_split, const long long out_plane, float* __restrict__ out_f32,
+                    const int ldo) {
+  constexpr int DH = 32;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + ATC_Q_BYTES;
+  uint8_t* sVt = sK + ATC_K_BYTES;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sVt + 2 * ATC_VT_PLANE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int h = blockIdx.x, b = blockIdx.y;
+
+  // ---- K rows -> [hi | lo] swizzled rows; V -> V^T key blocks (both planes); rows >= Tk are zero ----
+  for (int it = tid; it < 256 * 4; it += 128) {
+    const int j = it >> 2, g = it & 3;
+    uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+    if (j < Tk) {
+      const float* src = k + (static_cast<long long>(b) * Tk + j) * ldk + h * DH + 8 * g;
+      split8(*reinterpret_cast<const float4*>(src), *reinterpret_cast<const float4*>(src + 4), hi, lo);
+    }
+    *reinterpret_cast<uint4*>(sK + j * 128 + ((g ^ (j & 7)) << 4)) = hi;
+    *reinterpret_cast<uint4*>(sK + j * 128 + (((g + 4) ^ (j & 7)) << 4)) = lo;
+  }
+  for (int it = tid; it < 128 * 8; it += 128) {
+    const int jp = it >> 3, g = it & 7;  // key pair (2jp, 2jp+1), channels 4g..4g+3
+    const int j = 2 * jp;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+    const float* src = v + (static_cast<long long>(b) * Tk + j) * ldk + h * DH + 4 * g;
+    if (j < Tk) a = *reinterpret_cast<const float4*>(src);
+    if (j + 1 < Tk) c = *reinterpret_cast<const float4*>(src + ldk);
+    const float fa[4] = {a.x, a.y, a.z, a.w}, fc[4] = {c.x, c.y, c.z, c.w};
+    const int kb = j >> 6, jj = j & 63;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int d = 4 * g + e;
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(fa[e], h0, l0);
+      split_bf16(fc[e], h1, l1);
+      const int off = kb * 4096 + d * 128 + (((jj >> 3) ^ (d & 7)) << 4) + (jj & 7) * 2;
+      *reinterpret_cast<uint32_t*>(sVt + off) = pack_bf16(h0, h1);
+      *reinterpret_cast<uint32_t*>(sVt + ATC_VT_PLANE + off) = pack_bf16(l0, l1);
+    }
+  }
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  // TMEM is requested only now: a second CTA resident on this SM converts its K / V while the first one computes
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tPh = tmem_base + 256, tPl = tmem_base + 384;
+  const uint32_t trow = static_cast<uint32_t>(warp * 32) << 16;  // this warp's TMEM lane quadrant
+  uint32_t phase = 0;
+  const int nks = (Tk + 15) >> 4;  // P.V k-steps that hold real keys
+
+  for (int q0 = 0; q0 < Tq; q0 += 128) {
+    // ---- Q tile -> [hi | lo] rows ----
+    for (int it = tid; it < 128 * 4; it += 128) {
+      const int r = it >> 2, g = it & 3;
+      uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+      if (q0 + r < Tq) {
+        const float* src = q + (static_cast<long long>(b) * Tq + q0 + r) * ldq + h * DH + 8 * g;
+        split8(*reinterpret_cast<const float4*>(src), *reinterpret_cast<const float4*>(src + 4), hi, lo);
+      }
+      *reinterpret_cast<uint4*>(sQ + r * 128 + ((g ^ (r & 7)) << 4)) = hi;
+      *reinterpret_cast<uint4*>(sQ + r * 128 + (((g + 4) ^ (r & 7)) << 4)) = lo;
+    }
+    fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core
+    tc_fence_before();         // (also orders the previous tile's TMEM reads before the MMAs below)
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      constexpr uint32_t idesc_s = make_idesc(1, 128, 256);
+      const uint64_t dq = make_sw128_kmajor_desc(smem_u32(sQ));
+      const uint64_t dk = make_sw128_kmajor_desc(smem_u32(sK));
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {  // K = 32 = 2 k-steps of 16; +4 = the lo half of the row (64 B)
+        mma_bf16_ss(tS, dq + 2 * s, dk + 4 + 2 * s, idesc_s, s != 0);
+        mma_bf16_ss(tS, dq + 4 + 2 * s, dk + 2 * s, idesc_s, 1);
+        mma_bf16_ss(tS, dq + 2 * s, dk + 2 * s, idesc_s, 1);
+      }
+      tc_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- softmax: thread = query row ----
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < 256; c += 32) {
+      if (c >= Tk) break;
+      uint32_t sv[32];
+      tmem_ld_32x32(tS + trow + c, sv);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (c + j < Tk) ? __uint_as_float(sv[j]) : -INFINITY);
+    }
+    float lsum = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 256; c += 32) {
+      uint32_t ph[16], pl[16];
+      if (c < Tk) {
+        uint32_t sv[32];
+        tmem_ld_32x32(tS + trow + c, sv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float p0 = (c + j < Tk) ? __expf((__uint_as_float(sv[j]) - mx) * scale) : 0.f;
+          const float p1 = (c + j + 1 < Tk) ? __expf((__uint_as_float(sv[j + 1]) - mx) * scale) : 0.f;
+          lsum += p0 + p1;
+          __nv_bfloat16 h0, l0, h1, l1;
+          split_bf16(p0, h0, l0);
+          split_bf16(p1, h1, l1);
+          ph[j >> 1] = pack_bf16(h0, h1);
+          pl[j >> 1] = pack_bf16(l0, l1);
+        }
+      } else {
+        if (c >= nks * 16) break;  // k-steps past the last key are never issued
+#pragma unroll
+        for (int j = 0; j < 16; ++j) ph[j] = pl[j] = 0u;
+      }
+      tmem_st_32x16(tPh + trow + (c >> 1), ph);
+      tmem_st_32x16(tPl + trow + (c >> 1), pl);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      constexpr uint32_t idesc_o = make_idesc(1, 128, 32);
+      for (int ks = 0; ks < nks; ++ks) {
+        const uint32_t vt = smem_u32(sVt) + (ks >> 2) * 4096;
+        const uint64_t bh = make_sw128_kmajor_desc(vt) + 2 * (ks & 3);
+        const uint64_t bl = make_sw128_kmajor_desc(vt + ATC_VT_PLANE) + 2 * (ks & 3);
+        mma_bf16_ts(tS, tPh + ks * 8, bl, idesc_o, ks != 0);  // O overwrites S columns [0, 32): S is consumed
+        mma_bf16_ts(tS, tPl + ks * 8, bh, idesc_o, 1);
+        mma_bf16_ts(tS, tPh + ks * 8, bh, idesc_o, 1);
+      }
+      tc_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    {
+      uint32_t ov[32];
+      tmem_ld_32x32(tS + trow, ov);
+      tmem_ld_wait();
+      const int r = q0 + tid;
+      if (r < Tq) {
+        const float inv = 1.f / lsum;
+        const long long orow = (static_cast<long long>(b) * Tq + r) * ldo + h * DH;
+        if (out_f32) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(out_f32 + orow + j) =
+                make_float4(__uint_as_float(ov[j]) * inv, __uint_as_float(ov[j + 1]) * inv,
+                            __uint_as_float(ov[j + 2]) * inv, __uint_as_float(ov[j + 3]) * inv);
+        }
+        if (out_split) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(__uint_as_float(ov[j + 2 * e]) * inv, h0, l0);
+              split_bf16(__uint_as_float(ov[j + 2 * e + 1]) * inv, h1, l1);
+              hw[e] = pack_bf16(h0, h1);
+              lw[e] = pack_bf16(l0, l1);
+            }
+            *reinterpret_cast<uint4*>(out_split + orow + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(out_split + out_plane + orow + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// Returns 1 when the tensor-core kernel took the call, 0 when the shape is outside its class, < 0 on error.
+int attention_tc_try(const float* q, int ldq, const float* k, const float* v, int ldk, const unsigned char* mask, int B,
+                     int H, int Tq, int Tk, int head_dim, int causal, float scale, void* out_split,
+                     long long out_plane, float* out_f32, int ldo, cudaStream_t st) {
+  static const bool enabled = !(getenv("RALF_ATTN_TC") && atoi(getenv("RALF_ATTN_TC")) == 0);
+  if (!enabled || mask || causal || head_dim != 32 || Tk > 256 || Tk < 64 || Tq < 64) return 0;
+  if ((ldq & 3) || (ldk & 3) || (ldo & 7) || (reinterpret_cast<uintptr_t>(out_split) & 15) ||
+      (reinterpret_cast<uintptr_t>(out_f32) & 15) || (out_plane & 7))
+    return 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                               cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return set_cuda_error(e);
+    attr_set = true;
+  }
+  attention_tc_kernel<<<dim3(H, B), 128, ATC_SMEM, st>>>(q, ldq, k, v, ldk, Tq, Tk, scale,
+                                                          reinterpret_cast<__nv_bfloat16*>(out_split), out_plane,
+                                                          out_f32, ldo);
+  const int rc = set_cuda_error(cudaGetLastError());
+  return rc ? rc : 1;
+}
+
+}  // namespace ralf

@@ -375,11 +375,17 @@ __device__ __forceinline__ void block_top_c(LoadFn load, const int parts, uint64
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if constexpr (C == 32) {
     uint64_t r = 0ull;
-    for (int p = warp; p < parts; p += 8) {
-      uint64_t b = load(p, lane);
-      if (!__any_sync(0xffffffffu, b != 0ull)) continue;
-      b = warp_sort32_desc(b, lane);
-      r = warp_merge_top32(r, b, lane);
+    for (int p0 = warp; p0 < parts; p0 += 64) {  // 8 lists requested at once: one memory round trip per 8 merges
+      uint64_t pre[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) pre[u] = (p0 + 8 * u < parts) ? load(p0 + 8 * u, lane) : 0ull;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        uint64_t b = pre[u];
+        if (!__any_sync(0xffffffffu, b != 0ull)) continue;
+        b = warp_sort32_desc(b, lane);
+        r = warp_merge_top32(r, b, lane);
+      }
     }
     scratch[warp * 32 + lane] = r;
     __syncthreads();

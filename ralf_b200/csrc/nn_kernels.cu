@@ -740,6 +740,10 @@ extern "C" int ralf_attention(const float* q, int ldq, const float* k, const flo
   if (!q || !k || !v) return RALF_ERR_NULL;
   if (B <= 0 || H <= 0 || Tq <= 0 || Tk <= 0 || (head_dim != 32 && head_dim != 64)) return RALF_ERR_SHAPE;
   if ((ldq & 3) || (ldk & 3)) return RALF_ERR_ALIGN;
+  // image-encoder shape class (8 x 32 heads, no mask, <= 256 keys): tcgen05 kernel (attention_tc.cu)
+  const int tc = attention_tc_try(q, ldq, k, v, ldk, key_padding_mask, B, H, Tq, Tk, head_dim, causal, scale, out_split,
+                                  out_plane, out_f32, ldo, ST(stream));
+  if (tc != 0) return tc < 0 ? tc : 0;
   const int threads = Tq >= 128 ? 128 : ((Tq + 31) / 32) * 32;
   dim3 grid((Tq + threads - 1) / threads, H, B);
   if (head_dim == 32)

@@ -13,4 +13,8 @@ int set_cuda_error(cudaError_t e);
 int make_kmajor_tmap(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t K, uint64_t rows,
                      uint64_t planes, uint64_t ld, uint64_t plane_stride, uint32_t box_rows);
 int num_sms();
+// attention_tc.cu: tcgen05 attention for (head_dim 32, no mask, 64 <= Tk <= 256); 1 = launched, 0 = not applicable.
+int attention_tc_try(const float* q, int ldq, const float* k, const float* v, int ldk, const unsigned char* mask, int B,
+                     int H, int Tq, int Tk, int head_dim, int causal, float scale, void* out_split,
+                     long long out_plane, float* out_f32, int ldo, cudaStream_t st);
 }  // namespace ralf

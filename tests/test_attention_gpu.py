@@ -71,3 +71,24 @@ def test_layernorm_matches_fp64(cuda_device, M, D):
     ref = torch.nn.functional.layer_norm(x.double(), (D,), gamma.double(), beta.double(), 1e-5)
     assert (y.double() - ref).abs().max().item() <= 1e-5
     assert (ops.unsplit(ys).double() - ref).abs().max().item() <= 2e-4
+
+
+@pytest.mark.parametrize("B,Tq,Tk,H", [(3, 256, 256, 8), (2, 200, 200, 8), (5, 128, 64, 8), (1, 300, 150, 8),
+                                       (130, 256, 256, 8)])
+def test_encoder_attention_tcgen05_matches_fp64(cuda_device, B, Tq, Tk, H):
+    """Image-encoder self-attention shape class (head_dim 32, no mask, <= 256 keys): tcgen05 kernel with split-bf16
+    operands and P kept in TMEM, against the float64 softmax(q k^T / sqrt(dh)) v of the same fp32 inputs."""
+    from ralf_b200 import ops
+
+    dh = 32
+    D = H * dh
+    g = torch.Generator(device=cuda_device).manual_seed(B + Tq + Tk)
+    q = torch.randn(B * Tq, D, device=cuda_device, generator=g) * 1.5
+    kv = torch.randn(B * Tk, 2 * D, device=cuda_device, generator=g) * 1.5
+    out = ops.unsplit(ops.attention(q, kv[:, :D], kv[:, D:], B, H, Tq, Tk, dh)).double()
+    qd = q.double().view(B, Tq, H, dh).permute(0, 2, 1, 3)
+    kd = kv[:, :D].double().view(B, Tk, H, dh).permute(0, 2, 1, 3)
+    vd = kv[:, D:].double().view(B, Tk, H, dh).permute(0, 2, 1, 3)
+    ref = (torch.softmax(qd @ kd.transpose(-1, -2) * dh ** -0.5, -1) @ vd).permute(0, 2, 1, 3).reshape(B * Tq, D)
+    err = (out - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= 3e-5, err
