@@ -106,6 +106,12 @@ typedef struct RalfGemmArgs {
   int group_offset;
 } RalfGemmArgs;
 int ralf_gemm(const RalfGemmArgs* args, void* stream);
+/* Stride-1 "same" convolution (nn.Conv2d(C, N, KH, padding=KH/2), BatchNorm folded; common/image.py:39-83 -- the 3x3
+ * convolutions of the ResNet50 bottlenecks and of the FPN) as an IMPLICIT GEMM: args->A is the NHWC split activation
+ * [planes][B*H*W, C] itself, each k-block of the main loop is one (filter tap, 64-channel slice) fetched by a 5-D TMA
+ * box whose out-of-image part is zero-filled (= the padding); no im2col buffer exists.
+ * args->W = [planes][N, KH*KW*C] with k = (kh*KW + kw)*C + c; args->M = B*H*W; args->K = KH*KW*C; C % 64 == 0. */
+int ralf_conv_gemm(const RalfGemmArgs* args, int B, int H, int W, int C, int KH, int KW, void* stream);
 /* D = LayerNorm(x)[M,256] . W^T with the LayerNorm computed inside the GEMM (decode path: M <= 128, K = 256,
  * npass = 3).  x fp32 [M, 256] (row stride ldx); `args` supplies W and the epilogue (its A fields are ignored).
  * Replaces nn.LayerNorm + nn.Linear pairs of the pre-LN decoder layer / LM head (common/common.py:26-41). */

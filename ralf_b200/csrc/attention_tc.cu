@@ -62,7 +62,7 @@ __device__ __forceinline__ void split8(const float4 a, const float4 b, uint4& hi
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 2)
 attention_tc_kernel(const float* __restrict__ q, const int ldq, const float* __restrict__ k,
                     const float* __restrict__ v, const int ldk, const int Tq, const int Tk, const float scale,
                     __nv_bfloat16* __restrict__ out_split, const long long out_plane, float* __restrict__ out_f32,
@@ -79,35 +79,56 @@ attention_tc_kernel(const float* __restrict__ q, const int ldq, const float* __r
   const int tid = threadIdx.x, warp = tid >> 5;
   const int h = blockIdx.x, b = blockIdx.y;
 
-  // ---- K rows -> [hi | lo] swizzled rows; V -> V^T key blocks (both planes); rows >= Tk are zero ----
-  for (int it = tid; it < 256 * 4; it += 128) {
-    const int j = it >> 2, g = it & 3;
-    uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
-    if (j < Tk) {
-      const float* src = k + (static_cast<long long>(b) * Tk + j) * ldk + h * DH + 8 * g;
-      split8(*reinterpret_cast<const float4*>(src), *reinterpret_cast<const float4*>(src + 4), hi, lo);
+  // ---- K rows -> [hi | lo] swizzled rows; V -> V^T key blocks (both planes); rows >= Tk are zero.
+  // Every thread first requests ALL its global data (2 rows x 128 B), then converts: one memory round trip. ----
+  {
+    float4 kr[2][8];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int j = tid + 128 * u;
+      const float* src = k + (static_cast<long long>(b) * Tk + j) * ldk + h * DH;
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        kr[u][g] = (j < Tk) ? *reinterpret_cast<const float4*>(src + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    *reinterpret_cast<uint4*>(sK + j * 128 + ((g ^ (j & 7)) << 4)) = hi;
-    *reinterpret_cast<uint4*>(sK + j * 128 + (((g + 4) ^ (j & 7)) << 4)) = lo;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int j = tid + 128 * u;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 hi, lo;
+        split8(kr[u][2 * g], kr[u][2 * g + 1], hi, lo);
+        *reinterpret_cast<uint4*>(sK + j * 128 + ((g ^ (j & 7)) << 4)) = hi;
+        *reinterpret_cast<uint4*>(sK + j * 128 + (((g + 4) ^ (j & 7)) << 4)) = lo;
+      }
+    }
   }
-  for (int it = tid; it < 128 * 8; it += 128) {
-    const int jp = it >> 3, g = it & 7;  // key pair (2jp, 2jp+1), channels 4g..4g+3
-    const int j = 2 * jp;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
-    const float* src = v + (static_cast<long long>(b) * Tk + j) * ldk + h * DH + 4 * g;
-    if (j < Tk) a = *reinterpret_cast<const float4*>(src);
-    if (j + 1 < Tk) c = *reinterpret_cast<const float4*>(src + ldk);
-    const float fa[4] = {a.x, a.y, a.z, a.w}, fc[4] = {c.x, c.y, c.z, c.w};
+  {
+    float4 vr[2][8];  // key pair (2 tid, 2 tid + 1)
+    const int j = 2 * tid;
+    const float* src = v + (static_cast<long long>(b) * Tk + j) * ldk + h * DH;
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        vr[u][g] = (j + u < Tk) ? *reinterpret_cast<const float4*>(src + static_cast<long long>(u) * ldk + 4 * g)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
     const int kb = j >> 6, jj = j & 63;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int d = 4 * g + e;
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(fa[e], h0, l0);
-      split_bf16(fc[e], h1, l1);
-      const int off = kb * 4096 + d * 128 + (((jj >> 3) ^ (d & 7)) << 4) + (jj & 7) * 2;
-      *reinterpret_cast<uint32_t*>(sVt + off) = pack_bf16(h0, h1);
-      *reinterpret_cast<uint32_t*>(sVt + ATC_VT_PLANE + off) = pack_bf16(l0, l1);
+    for (int g = 0; g < 8; ++g) {
+      const float fa[4] = {vr[0][g].x, vr[0][g].y, vr[0][g].z, vr[0][g].w};
+      const float fc[4] = {vr[1][g].x, vr[1][g].y, vr[1][g].z, vr[1][g].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int d = 4 * g + e;
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(fa[e], h0, l0);
+        split_bf16(fc[e], h1, l1);
+        // a warp writes 32 consecutive key pairs of one d-row: consecutive words, conflict free
+        const int off = kb * 4096 + d * 128 + (((jj >> 3) ^ (d & 7)) << 4) + (jj & 7) * 2;
+        *reinterpret_cast<uint32_t*>(sVt + off) = pack_bf16(h0, h1);
+        *reinterpret_cast<uint32_t*>(sVt + ATC_VT_PLANE + off) = pack_bf16(l0, l1);
+      }
     }
   }
   if (tid == 0) {
@@ -126,16 +147,21 @@ attention_tc_kernel(const float* __restrict__ q, const int ldq, const float* __r
   const int nks = (Tk + 15) >> 4;  // P.V k-steps that hold real keys
 
   for (int q0 = 0; q0 < Tq; q0 += 128) {
-    // ---- Q tile -> [hi | lo] rows ----
-    for (int it = tid; it < 128 * 4; it += 128) {
-      const int r = it >> 2, g = it & 3;
-      uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
-      if (q0 + r < Tq) {
-        const float* src = q + (static_cast<long long>(b) * Tq + q0 + r) * ldq + h * DH + 8 * g;
-        split8(*reinterpret_cast<const float4*>(src), *reinterpret_cast<const float4*>(src + 4), hi, lo);
+    // ---- Q tile -> [hi | lo] rows (thread = row) ----
+    {
+      const int r = tid;
+      float4 qr[8];
+      const float* src = q + (static_cast<long long>(b) * Tq + q0 + r) * ldq + h * DH;
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        qr[g] = (q0 + r < Tq) ? *reinterpret_cast<const float4*>(src + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 hi, lo;
+        split8(qr[2 * g], qr[2 * g + 1], hi, lo);
+        *reinterpret_cast<uint4*>(sQ + r * 128 + ((g ^ (r & 7)) << 4)) = hi;
+        *reinterpret_cast<uint4*>(sQ + r * 128 + (((g + 4) ^ (r & 7)) << 4)) = lo;
       }
-      *reinterpret_cast<uint4*>(sQ + r * 128 + ((g ^ (r & 7)) << 4)) = hi;
-      *reinterpret_cast<uint4*>(sQ + r * 128 + (((g + 4) ^ (r & 7)) << 4)) = lo;
     }
     fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core
     tc_fence_before();         // (also orders the previous tile's TMEM reads before the MMAs below)
@@ -168,6 +194,7 @@ attention_tc_kernel(const float* __restrict__ q, const int ldq, const float* __r
       for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (c + j < Tk) ? __uint_as_float(sv[j]) : -INFINITY);
     }
     float lsum = 0.f;
+    const float sl2 = scale * 1.4426950408889634f, mxs = mx * sl2;  // exp(scale (s - mx)) = 2^(s sl2 - mx sl2)
 #pragma unroll 1
     for (int c = 0; c < 256; c += 32) {
       uint32_t ph[16], pl[16];
@@ -177,8 +204,8 @@ attention_tc_kernel(const float* __restrict__ q, const int ldq, const float* __r
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          const float p0 = (c + j < Tk) ? __expf((__uint_as_float(sv[j]) - mx) * scale) : 0.f;
-          const float p1 = (c + j + 1 < Tk) ? __expf((__uint_as_float(sv[j + 1]) - mx) * scale) : 0.f;
+          const float p0 = (c + j < Tk) ? exp2f(fmaf(__uint_as_float(sv[j]), sl2, -mxs)) : 0.f;
+          const float p1 = (c + j + 1 < Tk) ? exp2f(fmaf(__uint_as_float(sv[j + 1]), sl2, -mxs)) : 0.f;
           lsum += p0 + p1;
           __nv_bfloat16 h0, l0, h1, l1;
           split_bf16(p0, h0, l0);

@@ -46,6 +46,28 @@ struct GemmEpi {
   int split_lo;                                    // write the lo plane too
 };
 
+// Implicit-GEMM convolution (stride 1, "same" padding): the A operand is never materialised.  k-block kb maps to
+// filter tap (kh, kw) = kb / cblocks and input channels 64 * (kb % cblocks) ...; an M tile is a (Wo x BH x NB) brick
+// of output positions, loaded per tap as ONE 5-D TMA box over the NHWC activation shifted by (kh - pad, kw - pad) --
+// out-of-image coordinates are zero-filled by TMA, which is exactly the convolution's zero padding.
+struct ConvGeom {
+  int enabled;
+  int B, Ho, Wo;      // output positions = input positions (stride 1)
+  int BH, NB;         // rows / images per M tile: rows_box = Wo * BH * NB <= 128
+  int hblocks;        // ceil(Ho / BH)
+  int cblocks;        // C / 64
+  int KW, pad;
+};
+
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == 1) return fmaxf(x, 0.f);
   if (act == 2) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
@@ -292,7 +314,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpi& ep, const uint
 template <int BN, int NPASS>
 __global__ void __launch_bounds__(320, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const GemmEpi ep, const int M, const int N, const int K, const int STAGES) {
+                 const GemmEpi ep, const int M, const int N, const int K, const int STAGES, const ConvGeom cg) {
   using Cfg = GemmCfg<BN, NPASS>;
   constexpr int P = Cfg::P;
   extern __shared__ uint8_t smem_raw[];
@@ -308,8 +330,44 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_n = (N + BN - 1) / BN;
-  const int num_tiles = ((M + 127) / 128) * tiles_n;
+  const int tiles_m = cg.enabled ? ((cg.B + cg.NB - 1) / cg.NB) * cg.hblocks : (M + 127) / 128;
+  const int num_tiles = tiles_m * tiles_n;
   const int nkb = (K + 63) / 64;
+  const uint32_t a_tx = cg.enabled ? static_cast<uint32_t>(cg.Wo * cg.BH * cg.NB) * 128u : Cfg::A_BYTES;
+  const uint32_t stage_tx = P * (a_tx + Cfg::B_BYTES);
+  // first output row and row limit of M tile mt
+  auto tile_rows = [&](const int mt, int& m0, int& m_end) {
+    if (cg.enabled) {
+      const int g = mt / cg.hblocks, hb = mt - g * cg.hblocks;
+      const int b0 = g * cg.NB, h0 = hb * cg.BH;
+      m0 = (b0 * cg.Ho + h0) * cg.Wo;
+      const int valid = cg.NB > 1 ? min(cg.NB, cg.B - b0) * cg.Ho * cg.Wo : min(cg.BH, cg.Ho - h0) * cg.Wo;
+      m_end = m0 + valid;
+    } else {
+      m0 = mt * 128;
+      m_end = M;
+    }
+  };
+  // one pipeline stage: A (both planes) + W (both planes) of k-block kb for tile (mt, n0)
+  auto load_stage = [&](const int mt, const int n0, const int kb, const int s) {
+    mbar_expect_tx(&full_bar[s], stage_tx);
+    uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+    if (cg.enabled) {
+      const int g = mt / cg.hblocks, hb = mt - g * cg.hblocks;
+      const int tap = kb / cg.cblocks, cb = kb - tap * cg.cblocks;
+      const int kh = tap / cg.KW, kw = tap - kh * cg.KW;
+#pragma unroll
+      for (int p = 0; p < P; ++p)
+        tma_load_5d(&tmA, &full_bar[s], st + p * Cfg::A_BYTES, cb * 64, kw - cg.pad, hb * cg.BH + kh - cg.pad,
+                    g * cg.NB, p);
+    } else {
+#pragma unroll
+      for (int p = 0; p < P; ++p) tma_load_3d(&tmA, &full_bar[s], st + p * Cfg::A_BYTES, kb * 64, mt * 128, p);
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+      tma_load_3d(&tmB, &full_bar[s], st + P * Cfg::A_BYTES + p * Cfg::B_BYTES, kb * 64, n0, p);
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -326,17 +384,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // Prologue prefetch: the first ring of TMA loads needs nothing but the barriers this thread just initialised,
     // so it is issued BEFORE the TMEM allocation / block sync below (hides ~0.5 us on latency-bound decode GEMMs).
     {
-      const int m0 = (blockIdx.x / tiles_n) * 128, n0 = (blockIdx.x % tiles_n) * BN;
+      const int mt = blockIdx.x / tiles_n, n0 = (blockIdx.x % tiles_n) * BN;
       const int npre = nkb < STAGES ? nkb : STAGES;
-      for (int kb = 0; kb < npre; ++kb) {
-        mbar_expect_tx(&full_bar[kb], Cfg::STAGE_BYTES);
-        uint8_t* st = smem + kb * Cfg::STAGE_BYTES;
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-          tma_load_3d(&tmA, &full_bar[kb], st + p * Cfg::A_BYTES, kb * 64, m0, p);
-          tma_load_3d(&tmB, &full_bar[kb], st + P * Cfg::A_BYTES + p * Cfg::B_BYTES, kb * 64, n0, p);
-        }
-      }
+      for (int kb = 0; kb < npre; ++kb) load_stage(mt, n0, kb, kb);
     }
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -351,20 +401,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t ph = 0;
       const int npre = nkb < STAGES ? nkb : STAGES;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * 128, n0 = (tile % tiles_n) * BN;
+        const int mt = tile / tiles_n, n0 = (tile % tiles_n) * BN;
         for (int kb = 0; kb < nkb; ++kb) {
           if (tile == static_cast<int>(blockIdx.x) && kb < npre) {  // already issued in the prologue
             if (++s == STAGES) { s = 0; ph ^= 1; }
             continue;
           }
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-          uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-#pragma unroll
-          for (int p = 0; p < P; ++p) {
-            tma_load_3d(&tmA, &full_bar[s], st + p * Cfg::A_BYTES, kb * 64, m0, p);
-            tma_load_3d(&tmB, &full_bar[s], st + P * Cfg::A_BYTES + p * Cfg::B_BYTES, kb * 64, n0, p);
-          }
+          load_stage(mt, n0, kb, s);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -417,11 +461,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (BN >= 64 || half == 0)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
     const int buf = it & 1;
-    const int m0 = (tile / tiles_n) * 128, n0 = (tile % tiles_n) * BN;
+    const int n0 = (tile % tiles_n) * BN;
+    int m0, m_end;
+    tile_rows(tile / tiles_n, m0, m_end);
     mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
     tc_fence_after();
     const uint32_t tacc = tmem_base + buf * BN;
-    gemm_epilogue_tile<BN>(ep, tacc, quad, lane, m0, n0, M, N, stage_all + (warp - 2) * 256, half * CH, half * CH + CH);
+    gemm_epilogue_tile<BN>(ep, tacc, quad, lane, m0, n0, m_end, N, stage_all + (warp - 2) * 256, half * CH, half * CH + CH);
     tc_fence_before();
     mbar_arrive(&tempty_bar[buf]);
     }  // tile loop
@@ -643,7 +689,7 @@ int make_kmajor_tmap(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t
 
 template <int BN, int NPASS>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi& ep, int M, int N, int K,
-                       cudaStream_t st) {
+                       cudaStream_t st, const ConvGeom& cg) {
   using Cfg = GemmCfg<BN, NPASS>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -656,7 +702,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
     if (e != cudaSuccess) return set_cuda_error(e);
     attr_set = true;
   }
-  const long long num_tiles = static_cast<long long>((N + BN - 1) / BN) * ((M + 127) / 128);
+  const long long tiles_m = cg.enabled ? static_cast<long long>((cg.B + cg.NB - 1) / cg.NB) * cg.hblocks : (M + 127) / 128;
+  const long long num_tiles = static_cast<long long>((N + BN - 1) / BN) * tiles_m;
   const int sms = num_sms();
   const int nkb = (K + 63) / 64;
   const int stages = nkb < Cfg::MAX_STAGES ? nkb : Cfg::MAX_STAGES;
@@ -677,7 +724,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
   if (occ > occ_cap) occ = occ_cap;
   const long long max_ctas = static_cast<long long>(sms) * occ;
   dim3 grid(static_cast<unsigned>(num_tiles < max_ctas ? num_tiles : max_ctas));
-  gemm_bf16_kernel<BN, NPASS><<<grid, 320, Cfg::smem_bytes(stages), st>>>(ta, tb, ep, M, N, K, stages);
+  gemm_bf16_kernel<BN, NPASS><<<grid, 320, Cfg::smem_bytes(stages), st>>>(ta, tb, ep, M, N, K, stages, cg);
   return set_cuda_error(cudaGetLastError());
 }
 
@@ -685,25 +732,30 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
 
 using namespace ralf;
 
-extern "C" int ralf_gemm(const RalfGemmArgs* a, void* stream) {
-  if (!a || a->M <= 0 || a->N <= 0 || a->K <= 0) return RALF_ERR_SHAPE;
-  if (a->npass != 1 && a->npass != 3) return RALF_ERR_SHAPE;
-  if (!a->A || !a->W) return RALF_ERR_NULL;
-  if ((a->lda % 8) || (a->ldw % 8)) return RALF_ERR_ALIGN;
-  const int planes = a->npass == 3 ? 2 : 1;
-  int bn = a->block_n;
-  if (bn == 0) {  // widest tile that still yields ~one tile per SM; skinny (decode, M <= 128) GEMMs get BN = 32
-    const long long mt = (a->M + 127) / 128;
-    if (mt * ((a->N + 255) / 256) >= 120 && a->N >= 256 && a->npass == 1) bn = 256;
-    else if (mt * ((a->N + 127) / 128) >= 120 && a->N >= 128) bn = 128;
-    else if (mt * ((a->N + 63) / 64) >= 60 && a->N >= 64) bn = 64;
-    else bn = 32;
+// NHWC split activation [planes][B, H, W, C] -> 5-D tensor map (C, W, H, B, plane); box = 64 channels x Wo x BH x NB.
+static int make_conv_tmap(CUtensorMap* out, const void* ptr, uint64_t C_, uint64_t W_, uint64_t H_, uint64_t B_,
+                          uint64_t planes, uint64_t plane_stride, uint32_t bw, uint32_t bh, uint32_t nb) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return RALF_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((C_ * 2) & 15) || ((plane_stride * 2) & 15)) return RALF_ERR_ALIGN;
+  cuuint64_t gdim[5] = {C_, W_, H_, B_, planes};
+  cuuint64_t gstr[4] = {C_ * 2, W_ * C_ * 2, H_ * W_ * C_ * 2, (planes > 1 ? plane_stride : B_ * H_ * W_ * C_) * 2};
+  cuuint32_t box[5] = {64, bw, bh, nb, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "ralf_b200: cuTensorMapEncodeTiled (conv) failed (%d)\n", (int)r);
+    return RALF_ERR_DRIVER;
   }
-  if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return RALF_ERR_SHAPE;
-  CUtensorMap ta, tb;
-  int rc = make_kmajor_tmap(&ta, a->A, 2, a->K, a->M, planes, a->lda, a->a_plane, 128);
-  if (rc) return rc;
-  rc = make_kmajor_tmap(&tb, a->W, 2, a->K, a->N, planes, a->ldw, a->w_plane, bn);
+  return 0;
+}
+
+static int gemm_dispatch(const RalfGemmArgs* a, const CUtensorMap& ta, int bn, const ConvGeom& cg, void* stream) {
+  const int planes = a->npass == 3 ? 2 : 1;
+  CUtensorMap tb;
+  int rc = make_kmajor_tmap(&tb, a->W, 2, a->K, a->N, planes, a->ldw, a->w_plane, bn);
   if (rc) return rc;
   GemmEpi ep;
   ep.bias = a->bias;
@@ -730,7 +782,7 @@ extern "C" int ralf_gemm(const RalfGemmArgs* a, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int np = a->npass;
 #define RALF_GEMM_CASE(BN_, NP_) \
-  if (bn == BN_ && np == NP_) return launch_gemm<BN_, NP_>(ta, tb, ep, a->M, a->N, a->K, st);
+  if (bn == BN_ && np == NP_) return launch_gemm<BN_, NP_>(ta, tb, ep, a->M, a->N, a->K, st, cg);
   RALF_GEMM_CASE(32, 3)
   RALF_GEMM_CASE(64, 3)
   RALF_GEMM_CASE(128, 3)
@@ -741,6 +793,66 @@ extern "C" int ralf_gemm(const RalfGemmArgs* a, void* stream) {
   RALF_GEMM_CASE(256, 1)
 #undef RALF_GEMM_CASE
   return RALF_ERR_SHAPE;
+}
+
+static int gemm_pick_bn(const RalfGemmArgs* a, long long mt) {
+  int bn = a->block_n;
+  if (bn == 0) {  // widest tile that still yields ~one tile per SM; skinny (decode, M <= 128) GEMMs get BN = 32
+    if (mt * ((a->N + 255) / 256) >= 120 && a->N >= 256 && a->npass == 1) bn = 256;
+    else if (mt * ((a->N + 127) / 128) >= 120 && a->N >= 128) bn = 128;
+    else if (mt * ((a->N + 63) / 64) >= 60 && a->N >= 64) bn = 64;
+    else bn = 32;
+  }
+  return bn;
+}
+
+extern "C" int ralf_gemm(const RalfGemmArgs* a, void* stream) {
+  if (!a || a->M <= 0 || a->N <= 0 || a->K <= 0) return RALF_ERR_SHAPE;
+  if (a->npass != 1 && a->npass != 3) return RALF_ERR_SHAPE;
+  if (!a->A || !a->W) return RALF_ERR_NULL;
+  if ((a->lda % 8) || (a->ldw % 8)) return RALF_ERR_ALIGN;
+  const int planes = a->npass == 3 ? 2 : 1;
+  const int bn = gemm_pick_bn(a, (a->M + 127) / 128);
+  if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return RALF_ERR_SHAPE;
+  CUtensorMap ta;
+  int rc = make_kmajor_tmap(&ta, a->A, 2, a->K, a->M, planes, a->lda, a->a_plane, 128);
+  if (rc) return rc;
+  ConvGeom cg;
+  cg.enabled = 0;
+  cg.B = cg.Ho = cg.Wo = cg.BH = cg.NB = cg.hblocks = cg.cblocks = cg.KW = 1;
+  cg.pad = 0;
+  return gemm_dispatch(a, ta, bn, cg, stream);
+}
+
+// Stride-1 "same" convolution as an implicit GEMM: args->A = NHWC split activation [planes][B*H*W, C] (dense rows,
+// lda == C), args->W = [planes][N, KH*KW*C] with k = (kh*KW + kw)*C + c, args->M = B*H*W, args->K = KH*KW*C.
+// The epilogue fields mean what they mean for ralf_gemm.  C % 64 == 0, W <= 128.
+extern "C" int ralf_conv_gemm(const RalfGemmArgs* a, int B, int H, int W, int C, int KH, int KW, void* stream) {
+  if (!a || a->M <= 0 || a->N <= 0 || a->K <= 0) return RALF_ERR_SHAPE;
+  if (a->npass != 1 && a->npass != 3) return RALF_ERR_SHAPE;
+  if (!a->A || !a->W) return RALF_ERR_NULL;
+  if (B <= 0 || H <= 0 || W <= 0 || W > 128 || C <= 0 || (C % 64) || KH != KW || !(KH & 1) || KH > 7) return RALF_ERR_SHAPE;
+  if (a->M != B * H * W || a->K != KH * KW * C || a->lda != C) return RALF_ERR_SHAPE;
+  if (a->ldw % 8) return RALF_ERR_ALIGN;
+  const int planes = a->npass == 3 ? 2 : 1;
+  ConvGeom cg;
+  cg.enabled = 1;
+  cg.B = B; cg.Ho = H; cg.Wo = W;
+  cg.BH = 128 / W < H ? 128 / W : H;
+  cg.NB = cg.BH == H ? 128 / (W * H) : 1;
+  if (cg.NB < 1) cg.NB = 1;
+  if (cg.NB > B) cg.NB = B;
+  cg.hblocks = (H + cg.BH - 1) / cg.BH;
+  cg.cblocks = C / 64;
+  cg.KW = KW;
+  cg.pad = KH / 2;
+  const long long mt = static_cast<long long>((B + cg.NB - 1) / cg.NB) * cg.hblocks;
+  const int bn = gemm_pick_bn(a, mt);
+  if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return RALF_ERR_SHAPE;
+  CUtensorMap ta;
+  int rc = make_conv_tmap(&ta, a->A, C, W, H, B, planes, a->a_plane, W, cg.BH, cg.NB);
+  if (rc) return rc;
+  return gemm_dispatch(a, ta, bn, cg, stream);
 }
 
 template <int BN>

@@ -31,6 +31,8 @@ D = 256
 # in-kernel row normalisation costs more than the separate 4 us LayerNorm launch it removes (1698 vs 2162 layouts/s).
 # RALF_FUSE_LN=1 switches it on for A/B runs.
 FUSE_LN = os.environ.get("RALF_FUSE_LN", "0") != "0"
+# 3x3 stride-1 convolutions as implicit GEMMs (ralf_conv_gemm); RALF_IMPLICIT_CONV=0 restores im2col + GEMM for A/B runs.
+IMPLICIT_CONV = os.environ.get("RALF_IMPLICIT_CONV", "1") != "0"
 
 
 def _sine_pe_1d(max_len: int, d_model: int) -> torch.Tensor:
@@ -222,9 +224,15 @@ class Engine:
         feats = {}
         for (p, li, stride, planes, has_ds) in self.blocks:
             _, t1 = self._gemm(x, p + ".c1", act="relu", want_f32=False, want_split=True)
-            a2, Ho, Wo = ops.im2col(t1, B, H, W, planes, 3, 3, stride, 1)
-            _, t2 = self._gemm(a2, p + ".c2", act="relu", want_f32=False, want_split=True)
-            del a2, t1
+            if stride == 1 and IMPLICIT_CONV and W <= 128:  # implicit GEMM: the 3x3 taps are TMA boxes, no im2col
+                Ho, Wo = H, W
+                _, t2 = self._gemm(t1, p + ".c2", act="relu", want_f32=False, want_split=True,
+                                   conv=(B, H, W, planes, 3, 3))
+            else:
+                a2, Ho, Wo = ops.im2col(t1, B, H, W, planes, 3, 3, stride, 1)
+                _, t2 = self._gemm(a2, p + ".c2", act="relu", want_f32=False, want_split=True)
+                del a2
+            del t1
             if has_ds:
                 xs = x if stride == 1 else ops.im2col(x, B, H, W, C, 1, 1, stride, 0)[0]
                 _, idt = self._gemm(xs, p + ".ds", want_f32=False, want_split=True)
@@ -239,8 +247,11 @@ class Engine:
         c4, _ = self._gemm(l3, e + ".fpn_conv11_4")
         c5, _ = self._gemm(l4, e + ".fpn_conv11_5")
         fused, summ = ops.fpn_merge(c5, c4, B, h5, w5, h4, w4, D)
-        a33, _, _ = ops.im2col(summ, B, h4, w4, D, 3, 3, 1, 1)
-        self._gemm(a33, e + ".fpn_conv33", out_split=fused, out_col0=D, want_f32=False)
+        if IMPLICIT_CONV and w4 <= 128:
+            self._gemm(summ, e + ".fpn_conv33", out_split=fused, out_col0=D, want_f32=False, conv=(B, h4, w4, D, 3, 3))
+        else:
+            a33, _, _ = ops.im2col(summ, B, h4, w4, D, 3, 3, 1, 1)
+            self._gemm(a33, e + ".fpn_conv33", out_split=fused, out_col0=D, want_f32=False)
         tokens, _ = self._gemm(fused, e + ".proj", res=self.pos2d(h4, w4), res_row_mod=h4 * w4)
         return tokens, h4, w4
 

@@ -71,13 +71,20 @@ def gemm(
     block_n: int = 0,
     want_f32: bool = True,
     want_split: bool = False,
+    conv: Optional[tuple] = None,
 ) -> tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """D = A . W^T with the fused epilogue of ``ralf_gemm`` (include/ralf_b200.h).
 
-    Outputs are allocated when not supplied ([M, N] fp32 and/or [2, M, N] split bf16)."""
+    Outputs are allocated when not supplied ([M, N] fp32 and/or [2, M, N] split bf16).
+    ``conv = (B, H, W, C, KH, KW)``: ``a`` is the NHWC activation [2, B*H*W, C] and the call is the stride-1 "same"
+    convolution ``ralf_conv_gemm`` (implicit GEMM, K = KH*KW*C taken from ``w``)."""
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 3 and w.dim() == 3
     M, K = a.shape[1], a.shape[2]
     N = w.shape[1]
+    if conv is not None:
+        cB, cH, cW, cC, cKH, cKW = conv
+        assert M == cB * cH * cW and K == cC and a.stride(1) == cC and w.shape[2] == cKH * cKW * cC, (a.shape, w.shape)
+        K = w.shape[2]
     assert w.shape[2] == K, (a.shape, w.shape)
     assert a.stride(2) == 1 and w.stride(2) == 1
     if out_f32 is None and want_f32:
@@ -110,7 +117,10 @@ def gemm(
     g.out_split_lo = 1 if npass == 3 else 0
     g.out_ld, g.out_col0 = out_ld, out_col0
     g.rows_per_group, g.group_stride, g.group_offset = rows_per_group, group_stride, group_offset
-    check(_lib.lib().ralf_gemm(C.byref(g), _stream()), "ralf_gemm")
+    if conv is not None:
+        check(_lib.lib().ralf_conv_gemm(C.byref(g), *conv, _stream()), "ralf_conv_gemm")
+    else:
+        check(_lib.lib().ralf_gemm(C.byref(g), _stream()), "ralf_gemm")
     return out_f32, out_split
 
 

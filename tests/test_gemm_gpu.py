@@ -93,3 +93,25 @@ def test_gemm_row_remap_and_col_offset(cuda_device):
     got = out.view(B, T + 1, 2 * N)
     assert (got[:, 1:, N:] - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
     assert got[:, 0].abs().max().item() == 0 and got[:, :, :N].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("B,H,W,C,N,KH", [(2, 64, 64, 64, 64, 3), (3, 32, 32, 128, 128, 3), (2, 16, 16, 256, 256, 3),
+                                          (3, 8, 8, 512, 512, 3), (2, 22, 15, 256, 256, 3), (3, 11, 8, 512, 64, 3),
+                                          (1, 44, 30, 128, 128, 3), (5, 16, 16, 64, 96, 1)])
+def test_conv_gemm_implicit_matches_conv2d_fp64(cuda_device, B, H, W, C, N, KH):
+    """ralf_conv_gemm (3x3 / stride 1 / pad 1 taps as 5-D TMA boxes with zero fill) against torch conv2d in float64,
+    including tiles that are not full (22x15, 11x8 feature maps of the 350x240 canvases) and multi-image tiles (8x8)."""
+    from ralf_b200 import ops
+
+    g = torch.Generator(device=cuda_device).manual_seed(B * H + W + C)
+    x = torch.randn(B, H, W, C, device=cuda_device, generator=g)             # NHWC
+    w = torch.randn(N, C, KH, KH, device=cuda_device, generator=g) / (C * KH * KH) ** 0.5
+    bias = torch.randn(N, device=cuda_device, generator=g)
+    xs = ops.split_bf16(x.reshape(B * H * W, C))
+    ws = ops.split_bf16(w.permute(0, 2, 3, 1).reshape(N, KH * KH * C).contiguous())
+    y, _ = ops.gemm(xs, ws, bias=bias, act="relu", conv=(B, H, W, C, KH, KH))
+    ref = torch.nn.functional.conv2d(ops.unsplit(xs).view(B, H, W, C).permute(0, 3, 1, 2).double(),
+                                     ops.unsplit(ws).view(N, KH, KH, C).permute(0, 3, 1, 2).double(), bias.double(),
+                                     padding=KH // 2).relu().permute(0, 2, 3, 1).reshape(B * H * W, N)
+    err = (y.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= 2e-5, err
