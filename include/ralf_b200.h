@@ -112,6 +112,13 @@ int ralf_gemm(const RalfGemmArgs* args, void* stream);
  * box whose out-of-image part is zero-filled (= the padding); no im2col buffer exists.
  * args->W = [planes][N, KH*KW*C] with k = (kh*KW + kw)*C + c; args->M = B*H*W; args->K = KH*KW*C; C % 64 == 0. */
 int ralf_conv_gemm(const RalfGemmArgs* args, int B, int H, int W, int C, int KH, int KW, void* stream);
+/* ResNet50 stem (7x7 / stride 2 / pad 3 on the 4-channel canvas, common/image.py:69-77) in space-to-depth form:
+ * ralf_stem_s2d turns the fp32 NCHW image [B,4,H,W] (H, W even) into a zero-bordered NHWC split buffer
+ * [planes][B, H/2+3, W/2+3, 16] (channel = (dy*2+dx)*4 + c); ralf_stem_gemm runs the equivalent 4x4 / stride 1
+ * convolution over it as an implicit GEMM: args->A = that buffer, args->W = [planes][N, 256] with
+ * k = kh'*64 + kw'*16 + (dy*2+dx)*4 + c, args->M = B*Ho*Wo (Ho = H/2, Wo = W/2 <= 128), args->K = 256. */
+int ralf_stem_s2d(const float* img, int B, int H, int W, void* out, long long out_plane, void* stream);
+int ralf_stem_gemm(const RalfGemmArgs* args, int B, int Ho, int Wo, void* stream);
 /* D = LayerNorm(x)[M,256] . W^T with the LayerNorm computed inside the GEMM (decode path: M <= 128, K = 256,
  * npass = 3).  x fp32 [M, 256] (row stride ldx); `args` supplies W and the epilogue (its A fields are ignored).
  * Replaces nn.LayerNorm + nn.Linear pairs of the pre-LN decoder layer / LM head (common/common.py:26-41). */

@@ -63,6 +63,8 @@ def lib() -> C.CDLL:
                                      C.c_void_p]
         L.ralf_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
         L.ralf_conv_gemm.argtypes = [C.POINTER(GemmArgs)] + [C.c_int] * 6 + [C.c_void_p]
+        L.ralf_stem_gemm.argtypes = [C.POINTER(GemmArgs)] + [C.c_int] * 3 + [C.c_void_p]
+        L.ralf_stem_s2d.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]
         L.ralf_gemm_ln.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.POINTER(GemmArgs), C.c_void_p]
         L.ralf_check_device.argtypes = [C.c_int]
         vp, i, ll, f = C.c_void_p, C.c_int, C.c_longlong, C.c_float

@@ -855,6 +855,51 @@ extern "C" int ralf_conv_gemm(const RalfGemmArgs* a, int B, int H, int W, int C,
   return gemm_dispatch(a, ta, bn, cg, stream);
 }
 
+// ResNet stem as an implicit GEMM over the space-to-depth image of ralf_stem_s2d (nn_kernels.cu):
+// A = [planes][B, Hp, Wp, 16] (Hp = Ho + 3, Wp = Wo + 3, zero border), W = [planes][N, 256] with
+// k = kh'*64 + kw'*16 + (dy*2+dx)*4 + c.  k-block kh' of output pixel (b, ho, wo) is the 128 contiguous bytes starting
+// at pixel (b, ho + kh', wo): the tensor map's W dimension steps by ONE pixel (32 bytes) while its innermost extent is
+// four pixels (overlapping windows), so a (64 x Wo x BH) box is the whole A tile of a k-block.
+extern "C" int ralf_stem_gemm(const RalfGemmArgs* a, int B, int Ho, int Wo, void* stream) {
+  if (!a || a->M <= 0 || a->N <= 0) return RALF_ERR_SHAPE;
+  if (a->npass != 1 && a->npass != 3) return RALF_ERR_SHAPE;
+  if (!a->A || !a->W) return RALF_ERR_NULL;
+  if (B <= 0 || Ho <= 0 || Wo <= 0 || Wo > 128 || a->M != B * Ho * Wo || a->K != 256) return RALF_ERR_SHAPE;
+  if (a->ldw % 8) return RALF_ERR_ALIGN;
+  const int planes = a->npass == 3 ? 2 : 1;
+  const int Hp = Ho + 3, Wp = Wo + 3;
+  ConvGeom cg;
+  cg.enabled = 1;
+  cg.B = B; cg.Ho = Ho; cg.Wo = Wo;
+  cg.BH = 128 / Wo < Ho ? 128 / Wo : Ho;
+  cg.NB = 1;  // a box must not run over the bottom border rows into the next image
+  cg.hblocks = (Ho + cg.BH - 1) / cg.BH;
+  cg.cblocks = 1;  // k-block = kh' (tap = kb, kw = 0, channel block 0)
+  cg.KW = 1;
+  cg.pad = 0;
+  const long long mt = static_cast<long long>(B) * cg.hblocks;
+  const int bn = gemm_pick_bn(a, mt);
+  if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return RALF_ERR_SHAPE;
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return RALF_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(a->A) & 15) || ((a->a_plane * 2) & 15)) return RALF_ERR_ALIGN;
+  CUtensorMap ta;
+  cuuint64_t gdim[5] = {64, static_cast<cuuint64_t>(Wo), static_cast<cuuint64_t>(Hp), static_cast<cuuint64_t>(B),
+                        static_cast<cuuint64_t>(planes)};
+  cuuint64_t gstr[4] = {32, static_cast<cuuint64_t>(Wp) * 32, static_cast<cuuint64_t>(Hp) * Wp * 32,
+                        static_cast<cuuint64_t>(planes > 1 ? a->a_plane : static_cast<long long>(B) * Hp * Wp * 16) * 2};
+  cuuint32_t box[5] = {64, static_cast<cuuint32_t>(Wo), static_cast<cuuint32_t>(cg.BH), 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(a->A), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "ralf_b200: cuTensorMapEncodeTiled (stem) failed (%d)\n", (int)r);
+    return RALF_ERR_DRIVER;
+  }
+  return gemm_dispatch(a, ta, bn, cg, stream);
+}
+
 template <int BN>
 static int launch_gemm_ln(const CUtensorMap& tb, const float* x, int ldx, const float* gamma, const float* beta, float eps,
                           const GemmEpi& ep, int M, int N, cudaStream_t st) {

@@ -396,6 +396,52 @@ __global__ void stem_im2col_kernel(const float* __restrict__ img, int B, int H, 
   }
 }
 
+// ResNet stem, space-to-depth form: the 7x7 / stride 2 / pad 3 convolution on 4 channels equals a 4x4 / stride 1
+// convolution on the 2x2-blocked image with 16 channels (s2d channel = (dy*2+dx)*4 + c; taps (kh', dy) = ((kh+1)/2,
+// (kh+1)%2), the 8th tap row/column carries zero weights).  In NHWC the four w-taps x 16 channels of one kh' row are 128
+// CONTIGUOUS bytes -- exactly one tensor-core k-block -- so the stem runs as an implicit GEMM (ralf_stem_gemm) over this
+// zero-bordered buffer: out [2][B, H/2 + 3, W/2 + 3, 16] split bf16, 2 border pixels left / top, 1 right / bottom.
+__global__ void stem_s2d_kernel(const float* __restrict__ img, int B, int H, int W, int Hp, int Wp,
+                                __nv_bfloat16* __restrict__ out, long long plane) {
+  const long long total = static_cast<long long>(B) * Hp * Wp;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int px = static_cast<int>(i % Wp);
+    const int py = static_cast<int>((i / Wp) % Hp);
+    const int b = static_cast<int>(i / (static_cast<long long>(Wp) * Hp));
+    const int x = px - 2, y = py - 2;
+    float v[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = 0.f;
+    if (x >= 0 && 2 * x < W && y >= 0 && 2 * y < H) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+          const float2 f = *reinterpret_cast<const float2*>(
+              img + ((static_cast<long long>(b) * 4 + c) * H + 2 * y + dy) * W + 2 * x);
+          v[(dy * 2 + 0) * 4 + c] = f.x;
+          v[(dy * 2 + 1) * 4 + c] = f.y;
+        }
+    }
+    uint32_t hw[8], lw[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(v[2 * e], h0, l0);
+      split_bf16(v[2 * e + 1], h1, l1);
+      hw[e] = pack_bf16(h0, h1);
+      lw[e] = pack_bf16(l0, l1);
+    }
+    uint4* oh = reinterpret_cast<uint4*>(out + i * 16);
+    uint4* ol = reinterpret_cast<uint4*>(out + plane + i * 16);
+    oh[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    oh[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+    ol[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    ol[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+  }
+}
+
 // Generic NHWC im2col on split activations: in [2][B,H,W,C] -> out [2][B*Ho*Wo, KH*KW*C]
 // (k = (kh*KW + kw)*C + c), 8 channels (16 bytes) per thread.  Used for the 3x3 convolutions and
 // the strided 1x1 downsample convolutions of ResNet50 / the FPN 3x3.
@@ -430,16 +476,19 @@ __global__ void im2col_kernel(const __nv_bfloat16* __restrict__ in, long long in
 // 3x3 / stride 2 / pad 1 max-pool on split NHWC (ResNet stem pool).  2 channels per thread.
 __global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ in, long long in_plane, int B, int H, int W, int C,
                                int Ho, int Wo, __nv_bfloat16* __restrict__ out, long long out_plane) {
-  const int c2 = C >> 1;
-  const long long total = static_cast<long long>(B) * Ho * Wo * c2;
+  // 8 channels (16 bytes per plane) per thread
+  const int c8 = C >> 3;
+  const long long total = static_cast<long long>(B) * Ho * Wo * c8;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cc = static_cast<int>(i % c2);
-    const long long pix = i / c2;
+    const int cc = static_cast<int>(i % c8);
+    const long long pix = i / c8;
     const int ox = static_cast<int>(pix % Wo);
     const int oy = static_cast<int>((pix / Wo) % Ho);
     const int b = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
-    float m0 = -INFINITY, m1 = -INFINITY;
+    float m[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const int iy = oy * 2 - 1 + kh;
@@ -448,19 +497,29 @@ __global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ in, long long i
       for (int kw = 0; kw < 3; ++kw) {
         const int ix = ox * 2 - 1 + kw;
         if (ix < 0 || ix >= W) continue;
-        const long long src = ((static_cast<long long>(b) * H + iy) * W + ix) * C + cc * 2;
-        const uint32_t hw = *reinterpret_cast<const uint32_t*>(in + src);
-        const uint32_t lw = *reinterpret_cast<const uint32_t*>(in + in_plane + src);
-        m0 = fmaxf(m0, __uint_as_float(hw << 16) + __uint_as_float(lw << 16));
-        m1 = fmaxf(m1, __uint_as_float(hw & 0xffff0000u) + __uint_as_float(lw & 0xffff0000u));
+        const long long src = ((static_cast<long long>(b) * H + iy) * W + ix) * C + cc * 8;
+        const uint4 h4 = *reinterpret_cast<const uint4*>(in + src);
+        const uint4 l4 = *reinterpret_cast<const uint4*>(in + in_plane + src);
+        const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          m[2 * e] = fmaxf(m[2 * e], __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16));
+          m[2 * e + 1] = fmaxf(m[2 * e + 1], __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u));
+        }
       }
     }
-    __nv_bfloat16 h0, l0, h1, l1;
-    split_bf16(m0, h0, l0);
-    split_bf16(m1, h1, l1);
-    const long long dst = pix * C + cc * 2;
-    *reinterpret_cast<uint32_t*>(out + dst) = pack_bf16(h0, h1);
-    *reinterpret_cast<uint32_t*>(out + out_plane + dst) = pack_bf16(l0, l1);
+    uint32_t oh[4], ol[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(m[2 * e], h0, l0);
+      split_bf16(m[2 * e + 1], h1, l1);
+      oh[e] = pack_bf16(h0, h1);
+      ol[e] = pack_bf16(l0, l1);
+    }
+    const long long dst = pix * C + cc * 8;
+    *reinterpret_cast<uint4*>(out + dst) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+    *reinterpret_cast<uint4*>(out + out_plane + dst) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
   }
 }
 
@@ -814,6 +873,15 @@ extern "C" int ralf_stem_im2col(const float* img, int B, int H, int W, int KP, v
   return set_cuda_error(cudaGetLastError());
 }
 
+extern "C" int ralf_stem_s2d(const float* img, int B, int H, int W, void* out, long long out_plane, void* stream) {
+  if (!img || !out) return RALF_ERR_NULL;
+  if (B <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) return RALF_ERR_SHAPE;
+  const int Hp = H / 2 + 3, Wp = W / 2 + 3;
+  const long long total = static_cast<long long>(B) * Hp * Wp;
+  stem_s2d_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(img, B, H, W, Hp, Wp, BF(out), out_plane);
+  return set_cuda_error(cudaGetLastError());
+}
+
 extern "C" int ralf_im2col(const void* in, long long in_plane, int B, int H, int W, int C, int KH, int KW, int stride,
                            int pad, void* out, long long out_plane, void* stream) {
   if (!in || !out) return RALF_ERR_NULL;
@@ -828,9 +896,9 @@ extern "C" int ralf_im2col(const void* in, long long in_plane, int B, int H, int
 extern "C" int ralf_maxpool3x3s2(const void* in, long long in_plane, int B, int H, int W, int C, void* out,
                                  long long out_plane, void* stream) {
   if (!in || !out) return RALF_ERR_NULL;
-  if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 1)) return RALF_ERR_SHAPE;
+  if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 7)) return RALF_ERR_SHAPE;
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const long long total = static_cast<long long>(B) * Ho * Wo * (C >> 1);
+  const long long total = static_cast<long long>(B) * Ho * Wo * (C >> 3);
   maxpool_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(CBF(in), in_plane, B, H, W, C, Ho, Wo, BF(out),
                                                               out_plane);
   return set_cuda_error(cudaGetLastError());

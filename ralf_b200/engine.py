@@ -98,6 +98,19 @@ class Engine:
         self._put_w(name + ".w", w.permute(0, 2, 3, 1).reshape(cout, -1))  # k = (kh*KW + kw)*Cin + c
         self._put(name + ".b", bias)
 
+    def _stem_s2d_weight(self, sd, conv: str, bn: str) -> None:
+        """7x7 / stride 2 stem weight (BN folded) in space-to-depth form [64, 4(kh') * 4(kw') * 2(dy) * 2(dx) * 4(c)]:
+        original tap kh -> (kh', dy) = ((kh+1)//2, (kh+1)%2) (input row 2*ho - 3 + kh = 2*(ho + kh' - 2) + dy)."""
+        w = sd[conv + ".weight"].float()
+        scale = sd[bn + ".weight"].float() / torch.sqrt(sd[bn + ".running_var"].float() + 1e-5)
+        w = w * scale[:, None, None, None]
+        w2 = torch.zeros(w.shape[0], 4, 4, 2, 2, 4)
+        for kh in range(7):
+            for kw in range(7):
+                w2[:, (kh + 1) // 2, (kw + 1) // 2, (kh + 1) % 2, (kw + 1) % 2, :] = w[:, :, kh, kw]
+        self._put_w("stem_s2d.w", w2.reshape(w.shape[0], 256))
+        self.w["stem_s2d.b"] = self.w["stem.b"]
+
     def _lin(self, sd, key: str, name: Optional[str] = None, wscale: float = 1.0, badd: float = 0.0) -> None:
         name = name or key
         self._put_w(name + ".w", sd[key + ".weight"].float() * wscale)
@@ -120,6 +133,7 @@ class Engine:
     def _prepare(self, sd: dict) -> None:
         b = "encoder.extractor.body"
         self._conv_bn(sd, b + ".conv1", b + ".bn1", "stem")
+        self._stem_s2d_weight(sd, b + ".conv1", b + ".bn1")
         self.blocks = []
         for li, (nblk, stride, planes) in enumerate([(3, 1, 64), (4, 2, 128), (6, 2, 256), (3, 2, 512)], start=1):
             for bi in range(nblk):
@@ -216,8 +230,12 @@ class Engine:
     def resnet_fpn(self, img: torch.Tensor) -> tuple[torch.Tensor, int, int]:
         """img fp32 [B,4,H,W] -> tokens fp32 [B*h*w, 256] with the 2-D sine PE already added."""
         B = img.shape[0]
-        a, H, W = ops.stem_im2col(img.contiguous())
-        _, x = self._gemm(a, "stem", act="relu", want_f32=False, want_split=True)
+        if IMPLICIT_CONV and img.shape[2] % 2 == 0 and img.shape[3] % 2 == 0 and img.shape[3] <= 256:
+            a, H, W = ops.stem_s2d(img.contiguous())  # space-to-depth + implicit GEMM: no im2col rows
+            _, x = self._gemm(a, "stem_s2d", act="relu", want_f32=False, want_split=True, stem=(B, H, W))
+        else:
+            a, H, W = ops.stem_im2col(img.contiguous())
+            _, x = self._gemm(a, "stem", act="relu", want_f32=False, want_split=True)
         del a
         x, H, W = ops.maxpool3x3s2(x, B, H, W, 64)
         C = 64

@@ -72,15 +72,22 @@ def gemm(
     want_f32: bool = True,
     want_split: bool = False,
     conv: Optional[tuple] = None,
+    stem: Optional[tuple] = None,
 ) -> tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """D = A . W^T with the fused epilogue of ``ralf_gemm`` (include/ralf_b200.h).
 
     Outputs are allocated when not supplied ([M, N] fp32 and/or [2, M, N] split bf16).
     ``conv = (B, H, W, C, KH, KW)``: ``a`` is the NHWC activation [2, B*H*W, C] and the call is the stride-1 "same"
-    convolution ``ralf_conv_gemm`` (implicit GEMM, K = KH*KW*C taken from ``w``)."""
+    convolution ``ralf_conv_gemm`` (implicit GEMM, K = KH*KW*C taken from ``w``).
+    ``stem = (B, Ho, Wo)``: ``a`` is the space-to-depth buffer of :func:`stem_s2d` ([2, B*(Ho+3)*(Wo+3), 16]) and the
+    call is ``ralf_stem_gemm`` (K = 256)."""
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 3 and w.dim() == 3
     M, K = a.shape[1], a.shape[2]
     N = w.shape[1]
+    if stem is not None:
+        sB, sHo, sWo = stem
+        assert a.shape[1] == sB * (sHo + 3) * (sWo + 3) and K == 16 and w.shape[2] == 256 and a.is_contiguous()
+        M, K = sB * sHo * sWo, 256
     if conv is not None:
         cB, cH, cW, cC, cKH, cKW = conv
         assert M == cB * cH * cW and K == cC and a.stride(1) == cC and w.shape[2] == cKH * cKW * cC, (a.shape, w.shape)
@@ -117,7 +124,9 @@ def gemm(
     g.out_split_lo = 1 if npass == 3 else 0
     g.out_ld, g.out_col0 = out_ld, out_col0
     g.rows_per_group, g.group_stride, g.group_offset = rows_per_group, group_stride, group_offset
-    if conv is not None:
+    if stem is not None:
+        check(_lib.lib().ralf_stem_gemm(C.byref(g), *stem, _stream()), "ralf_stem_gemm")
+    elif conv is not None:
         check(_lib.lib().ralf_conv_gemm(C.byref(g), *conv, _stream()), "ralf_conv_gemm")
     else:
         check(_lib.lib().ralf_gemm(C.byref(g), _stream()), "ralf_gemm")
@@ -268,6 +277,16 @@ def stem_im2col(img: torch.Tensor, KP: int = 200):
     out = _split_out(B * Ho * Wo, KP, img.device)
     check(_lib.lib().ralf_stem_im2col(img.data_ptr(), B, H, W, KP, out.data_ptr(), out.stride(0), _stream()),
           "ralf_stem_im2col")
+    return out, Ho, Wo
+
+
+def stem_s2d(img: torch.Tensor):
+    """fp32 NCHW [B,4,H,W] -> zero-bordered space-to-depth split buffer [2, B*(H/2+3)*(W/2+3), 16] (ralf_stem_s2d)."""
+    B, C4, H, W = img.shape
+    assert C4 == 4 and img.is_contiguous() and img.dtype == torch.float32 and H % 2 == 0 and W % 2 == 0
+    Ho, Wo = H // 2, W // 2
+    out = _split_out(B * (Ho + 3) * (Wo + 3), 16, img.device)
+    check(_lib.lib().ralf_stem_s2d(img.data_ptr(), B, H, W, out.data_ptr(), out.stride(0), _stream()), "ralf_stem_s2d")
     return out, Ho, Wo
 
 

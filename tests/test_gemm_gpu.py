@@ -115,3 +115,32 @@ def test_conv_gemm_implicit_matches_conv2d_fp64(cuda_device, B, H, W, C, N, KH):
                                      padding=KH // 2).relu().permute(0, 2, 3, 1).reshape(B * H * W, N)
     err = (y.double() - ref).abs().max().item() / ref.abs().max().item()
     assert err <= 2e-5, err
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 256, 256), (3, 64, 96), (1, 350, 240), (2, 128, 128)])
+def test_stem_s2d_gemm_matches_conv2d_fp64(cuda_device, B, H, W):
+    """7x7 / stride 2 / pad 3 stem on the 4-channel canvas (common/image.py:69-77) through the space-to-depth implicit
+    GEMM (ralf_stem_s2d + ralf_stem_gemm) against torch conv2d in float64; then the vectorised 3x3/s2 max-pool."""
+    from ralf_b200 import ops
+
+    g = torch.Generator(device=cuda_device).manual_seed(H + W)
+    img = torch.rand(B, 4, H, W, device=cuda_device, generator=g)
+    w = torch.randn(64, 4, 7, 7, device=cuda_device, generator=g) / 14.0
+    bias = torch.randn(64, device=cuda_device, generator=g)
+    w2 = torch.zeros(64, 4, 4, 2, 2, 4, device=cuda_device)
+    for kh in range(7):
+        for kw in range(7):
+            w2[:, (kh + 1) // 2, (kw + 1) // 2, (kh + 1) % 2, (kw + 1) % 2, :] = w[:, :, kh, kw]
+    ws = ops.split_bf16(w2.reshape(64, 256))
+    a, Ho, Wo = ops.stem_s2d(img)
+    y, ys = ops.gemm(a, ws, bias=bias, act="relu", stem=(B, Ho, Wo), want_split=True)
+    # reference on the SAME rounded operands (split bf16 keeps ~17 bits of every input / weight)
+    img_r = ops.unsplit(ops.split_bf16(img.reshape(-1, 8))).view_as(img)
+    w_r = ops.unsplit(ops.split_bf16(w.reshape(64, -1))).view_as(w)
+    ref = torch.nn.functional.conv2d(img_r.double(), w_r.double(), bias.double(), stride=2, padding=3).relu()
+    assert ref.shape[2] == Ho and ref.shape[3] == Wo
+    err = (y.double().view(B, Ho, Wo, 64).permute(0, 3, 1, 2) - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= 2e-5, err
+    p, Hp, Wp = ops.maxpool3x3s2(ys, B, Ho, Wo, 64)
+    pref = torch.nn.functional.max_pool2d(ops.unsplit(ys).view(B, Ho, Wo, 64).permute(0, 3, 1, 2), 3, 2, 1)
+    assert torch.equal(ops.unsplit(p).view(B, Hp, Wp, 64).permute(0, 3, 1, 2), pref)
