@@ -210,6 +210,7 @@ def run_ours(args):
             step_e2e()
         ms_e2e = timed(lambda: step_e2e(), args.steps, record=None)
 
+    other = secondary_rooflines(model, B, dev) if rank == 0 else None
     if rank == 0:
         peaks = {}
         try:
@@ -217,6 +218,11 @@ def run_ours(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        knn_traffic = None
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of one k-NN pass (ncu --set full; profiles/r1_knn_pass_f_ncu.md)
+            knn_traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_knn_pass_f_ncu.json")))["traffic_bytes_per_pass"]
+        except Exception:
+            pass
         q_tot = world * B
         knn_passes = (q_tot + 127) // 128  # one gallery pass (pre-pass, threshold, scan, re-rank) per 128 queries
         knn_ms = sum(a.elapsed_time(b) for a, b in knn_ev) / max(1, len(knn_ev)) / knn_passes
@@ -249,7 +255,8 @@ def run_ours(args):
                                    "knn_scan_kernel<32> (TF32 tcgen05 scan + fused top-C filter) + knn_rerank_kernel<32>",
                          "bound": "hbm", "launches_per_step": knn_passes,
                          "achieved": round(knn_bytes / (knn_ms / 1e3) / 1e9, 1), "peak": hbm_peak, "unit": "GB/s",
-                         "frac": round(knn_bytes / (knn_ms / 1e3) / 1e9 / hbm_peak, 4), "traffic": None,
+                         "frac": round(knn_bytes / (knn_ms / 1e3) / 1e9 / hbm_peak, 4),
+                         "traffic": knn_traffic if (knn_traffic and n_local == 1_000_000) else None,
                          "algorithmic_bytes_per_launch": int(knn_bytes), "ms_per_launch": round(knn_ms, 4),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
             "model_flops": {"algorithmic_gflop_per_layout": round(flops_layout / 1e9, 2),
@@ -257,6 +264,10 @@ def run_ours(args):
                             "bf16_peak_tflops": peaks.get("bf16_tflops_sustained"),
                             "note": "per-GPU algorithmic FLOP rate of the whole step (SURVEY.md 8d), x3 tensor passes in bf16x3"},
         }
+        for o in other or []:  # the two kernels that dominate the step's time, timed alone right after the timed region
+            pk = hbm_peak if o["bound"] == "hbm" else peaks.get("bf16_tflops", 1590.0)
+            o["peak"], o["frac"] = pk, round(o["achieved"] / pk, 4)
+        line["roofline_other"] = other
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line))
@@ -264,6 +275,49 @@ def run_ours(args):
         import torch.distributed as dist
 
         dist.destroy_process_group()
+
+
+def secondary_rooflines(model, B, dev):
+    """The step's two dominant kernels timed alone (CUDA events, 20 launches each, operands >> L2):
+    (1) memory cross-attention of one decode step over the layer-major K/V cache of B canvases -- HBM bound,
+        algorithmic bytes = B * M * 512 * 4 (every K and V row read once) + q / out rows;
+    (2) a ResNet layer-3 3x3 convolution as implicit GEMM (micro-batch 128: M = 32768, N = 256, K = 2304) -- tensor
+        bound; achieved counts the 3 bf16 passes of the fp32-faithful product (3 * 2 * M * N * K)."""
+    from ralf_b200 import ops
+
+    out = []
+    M = 532
+    kv = torch.randn(B * M, 512, device=dev)
+    q = torch.randn(B, 256, device=dev)
+    o = torch.empty(2, B, 256, dtype=torch.bfloat16, device=dev)
+
+    def t(fn, n=20):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    ms = t(lambda: ops.attention_decode(q, kv[:, :256], kv[:, 256:], M, M, B, 8, 32, out=o))
+    byt = B * M * 512 * 4 + B * 256 * 4 + B * 256 * 4
+    out.append({"kernel": "attention_decode_stream_kernel<32> (decode-step cross-attention over the memory K/V cache)",
+                "bound": "hbm", "achieved": round(byt / ms / 1e6, 1), "unit": "GB/s", "ms_per_launch": round(ms, 4),
+                "algorithmic_bytes_per_launch": byt, "launches_per_step": 360})
+    del kv
+    Bc, H, W, C, N = 128, 16, 16, 256, 256
+    x = torch.randn(2, Bc * H * W, C, device=dev).to(torch.bfloat16)
+    w = torch.randn(2, N, 9 * C, device=dev).to(torch.bfloat16)
+    y = torch.empty(2, Bc * H * W, N, dtype=torch.bfloat16, device=dev)
+    ms = t(lambda: ops.gemm(x, w, act="relu", out_split=y, want_f32=False, conv=(Bc, H, W, C, 3, 3)))
+    fl = 3 * 2.0 * Bc * H * W * N * 9 * C
+    out.append({"kernel": "gemm_bf16_kernel<128,3> as implicit-GEMM 3x3 convolution (ResNet layer3 conv2, 128 canvases)",
+                "bound": "tensor", "achieved": round(fl / ms / 1e9, 1), "unit": "TFLOP/s", "ms_per_launch": round(ms, 4),
+                "flops_per_launch_3pass": fl, "launches_per_step": 48})
+    return out
 
 
 def cpu_baseline(args, budget_canvases: int = 2):

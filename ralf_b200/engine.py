@@ -444,7 +444,7 @@ class Engine:
         return logits.view(B, S, self.vocab)
 
     def generate(self, mem_s: Optional[torch.Tensor], B: int, Mlen: int, token_mask: torch.Tensor, bos_id: int,
-                 pad_id: int, steps: int, return_logits: bool = False, kv: Optional[list] = None):
+                 pad_id: int, steps: int, return_logits: bool = False, kv: Optional[list] = None, step_hook=None):
         """Greedy decode (retrieval_augmented_autoreg.py:244-300, cond_type uncond) with KV caches.
         token_mask: uint8 [steps, V] (tokenizer.token_mask).  Returns seq int64 [B, steps] (BOS dropped).
         ``kv``: precomputed cross-attention cache (cross_kv) of all B canvases; else built from ``mem_s``."""
@@ -459,6 +459,8 @@ class Engine:
         tm = token_mask.to(dev).to(torch.uint8).contiguous()
         all_logits = []
         for t in range(steps):
+            if step_hook is not None:  # profiling aid (profiles/launch_slice.py): called before every decode step
+                step_hook(t)
             for i in range(NLAYER):
                 p = f"decoder.transformer.layers.{i}"
                 # every LayerNorm of the step is folded into the GEMM that consumes it (ralf_gemm_ln)

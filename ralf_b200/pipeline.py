@@ -122,12 +122,19 @@ class LayoutPipeline:
             import torch.distributed as dist
 
             dist.all_gather_into_tensor(self.q_all, self.qry, group=self.retr.pg)
-        if not self.use_graph:
-            self._eager()
-            return self.seq_out
+        e0 = e1 = None
         if events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
+        if not self.use_graph:
+            idx, score = self._stage_search()
+            if events is not None:
+                e1.record()
+                events.append((e0, e1))
+            if self.world > 1:
+                idx = self._merge(idx, score)
+            self._stage_main(idx)
+            return self.seq_out
         self.g_search.replay()
         if events is not None:
             e1.record()
