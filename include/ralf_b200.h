@@ -104,6 +104,11 @@ typedef struct RalfGemmArgs {
   int rows_per_group; /* >0: out_row = (r / rpg) * group_stride + group_offset + r % rpg  */
   int group_stride;
   int group_offset;
+  void* out_kv24;     /* decoder cross-attention K/V cache rows in the 24-bit format, or NULL (N must be 512):
+                       * row r = 1536 bytes [K hi 256 x u16 | V hi 256 x u16 | K lo 256 x u8 | V lo 256 x u8]; a value
+                       * is the fp32 result rounded to 24 bits, hi = bits 31..16, lo = bits 15..8 (16-bit mantissa,
+                       * the accuracy class of the bf16x3 product that made it) -- 3 instead of 4 bytes per element on
+                       * the stream the decode loop is bound by */
 } RalfGemmArgs;
 int ralf_gemm(const RalfGemmArgs* args, void* stream);
 /* Stride-1 "same" convolution (nn.Conv2d(C, N, KH, padding=KH/2), BatchNorm folded; common/image.py:39-83 -- the 3x3
@@ -148,6 +153,10 @@ int ralf_attention_decode(const float* q, int ldq, const float* k, const float* 
                           int ldk, const unsigned char* key_padding_mask, int mask_ld, int Tk, int B, int H,
                           int head_dim, float scale, void* out_split, long long out_plane, int ldo,
                           void* stream);
+/* ralf_attention_decode over a 24-bit K/V cache written by ralf_gemm(out_kv24): rows (b*kv_bstride + j) of 1536 bytes,
+ * 8 heads x 32, no mask (memory cross-attention of the decode loop). */
+int ralf_attention_decode_kv24(const float* q, int ldq, const void* kv24, long long kv_bstride, int Tk, int B, int H,
+                               float scale, void* out_split, long long out_plane, int ldo, void* stream);
 /* Self-attention decode step with the cache append fused in: qkv [B, 3*H*head_dim] (this step's fused
  * projection), K/V caches [B, S, H*head_dim]; writes row `pos` of both caches, then attends over keys 0..pos. */
 int ralf_attention_decode_append(const float* qkv, int ldqkv, float* kcache, float* vcache, int S, int pos,

@@ -45,7 +45,7 @@ def main():
         mem, mem_s = eng.encode(img[b0:b0 + MB], packed, cs[b0:b0 + MB], cp[b0:b0 + MB])
         Mlen = mem.shape[1]
         if kv is None:
-            kv = eng.alloc_cross_kv(B * Mlen)
+            kv = eng.alloc_cross_kv(B * Mlen, kv24=True)
         eng.cross_kv(mem_s, out=kv, row0=b0 * Mlen)
         if profile:
             torch.cuda.synchronize()

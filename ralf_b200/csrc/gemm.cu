@@ -44,6 +44,8 @@ struct GemmEpi {
   int post_relu;                                   // relu after the residual add
   int vec_ok;                                      // all strides/offsets allow 16-byte accesses
   int split_lo;                                    // write the lo plane too
+  uint8_t* out_kv24;                               // 24-bit K/V cache rows (see ralf_b200.h) or null
+  long long kv24_ld;                               // bytes per cache row (1536)
 };
 
 // Implicit-GEMM convolution (stride 1, "same" padding): the A operand is never materialised.  k-block kb maps to
@@ -97,7 +99,9 @@ struct GemmCfg {
 // (conflict free) and then moved with the lanes running ALONG the rows, so a warp instruction covers full 64 / 128-byte
 // row segments.  NV = 16-byte vectors per row chunk: 8 for fp32 (32 columns = 128 B), 4 for one bf16 plane (64 B).
 template <int NV>
-__device__ __forceinline__ int epi_swz(int row) { return NV == 8 ? (row & 7) : ((row >> 1) & 3); }
+__device__ __forceinline__ int epi_swz(int row) {
+  return NV == 8 ? (row & 7) : (NV == 4 ? ((row >> 1) & 3) : ((row >> 2) & 1));
+}
 
 // coalesced global -> registers: pass p moves rows p*(32/NV) .. +32/NV; lane = (row within pass, vector).
 // my_base = global address of this lane's own row chunk (0 when the row is out of range).
@@ -262,6 +266,31 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpi& ep, const uint
             mine[j] = make_uint4(__float_as_uint(x[4 * j]), __float_as_uint(x[4 * j + 1]), __float_as_uint(x[4 * j + 2]),
                                  __float_as_uint(x[4 * j + 3]));
           epi_row_to_global<8>(stg, lane, mine, gaddr(ep.out_f32 + out_row * ep.out_ld + ep.out_col0 + nbase));
+        }
+        if (ep.out_kv24) {
+          // fp32 rounded to 24 bits: bf16-sized top half (2 B) + one extra mantissa byte -- 3 bytes per value
+          uint4 mh[4], ml[2];
+          uint32_t hw[16], lb[8];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const uint32_t u0 = __float_as_uint(x[j]) + 0x80u, u1 = __float_as_uint(x[j + 1]) + 0x80u;
+            hw[j >> 1] = (u0 >> 16) | (u1 & 0xffff0000u);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w |= (((__float_as_uint(x[j + e]) + 0x80u) >> 8) & 0xffu) << (8 * e);
+            lb[j >> 2] = w;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mh[j] = make_uint4(hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
+          ml[0] = make_uint4(lb[0], lb[1], lb[2], lb[3]);
+          ml[1] = make_uint4(lb[4], lb[5], lb[6], lb[7]);
+          const int part = nbase >> 8, cc = nbase & 255;  // K (0) or V (1) half of the 512 columns
+          uint8_t* row = ep.out_kv24 + out_row * ep.kv24_ld;
+          epi_row_to_global<4>(stg, lane, mh, gaddr(row + part * 512 + cc * 2));
+          epi_row_to_global<2>(stg, lane, ml, gaddr(row + 1024 + part * 256 + cc));
         }
         if (ep.out_split) {
           uint4 mh[4], ml[4];
@@ -706,7 +735,13 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
   const long long num_tiles = static_cast<long long>((N + BN - 1) / BN) * tiles_m;
   const int sms = num_sms();
   const int nkb = (K + 63) / 64;
-  const int stages = nkb < Cfg::MAX_STAGES ? nkb : Cfg::MAX_STAGES;
+  // The smem ring may span tiles (RALF_GEMM_MIN_STAGES > k-blocks: the producer runs ahead into the next tiles).  Measured
+  // (profiles/r1_gemm_epilogue_e_notes.md): no gain for the short-K GEMMs -- their epilogue, not the operand fetch, is
+  // the limiter -- so the default keeps the small ring.
+  static const int min_stages = getenv("RALF_GEMM_MIN_STAGES") ? atoi(getenv("RALF_GEMM_MIN_STAGES")) : 1;
+  const bool multi_tile = num_tiles > static_cast<long long>(sms);
+  int stages = nkb < Cfg::MAX_STAGES ? nkb : Cfg::MAX_STAGES;
+  if (multi_tile && stages < min_stages) stages = min_stages < Cfg::MAX_STAGES ? min_stages : Cfg::MAX_STAGES;
   // Short-K GEMMs are bound by their epilogue's memory traffic, not by the MMAs: their small smem ring lets several
   // persistent CTAs share an SM (limited by shared memory, 512 TMEM columns and an env override for A/B runs), which
   // multiplies the loads / stores in flight per SM.
@@ -775,10 +810,13 @@ static int gemm_dispatch(const RalfGemmArgs* a, const CUtensorMap& ta, int bn, c
   ep.act = a->act;
   ep.post_relu = a->post_relu;
   ep.split_lo = a->out_split_lo;
+  ep.out_kv24 = reinterpret_cast<uint8_t*>(a->out_kv24);
+  ep.kv24_ld = 1536;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   ep.vec_ok = (a->out_ld % 8 == 0) && (a->out_col0 % 8 == 0) && al16(a->out_f32) && al16(a->out_split) &&
               (a->out_plane % 8 == 0) && al16(a->bias) && al16(a->res) && al16(a->res_split) &&
               (a->res_ld % 8 == 0 || (!a->res && !a->res_split)) && (a->res_plane % 8 == 0);
+  if (a->out_kv24 && (a->N != 512 || !ep.vec_ok || !al16(a->out_kv24))) return RALF_ERR_SHAPE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int np = a->npass;
 #define RALF_GEMM_CASE(BN_, NP_) \
@@ -943,6 +981,8 @@ extern "C" int ralf_gemm_ln(const float* x, int ldx, const float* gamma, const f
   ep.act = a->act;
   ep.post_relu = a->post_relu;
   ep.split_lo = a->out_split_lo;
+  ep.out_kv24 = nullptr;
+  ep.kv24_ld = 0;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   ep.vec_ok = (a->out_ld % 8 == 0) && (a->out_col0 % 8 == 0) && al16(a->out_f32) && al16(a->out_split) &&
               (a->out_plane % 8 == 0) && al16(a->bias) && al16(a->res) && al16(a->res_split) &&

@@ -362,6 +362,95 @@ attention_decode_stream_kernel(const float* __restrict__ q, int ldq, const float
   }
 }
 
+// The same single-pass cross-attention over the 24-bit K/V cache (ralf_gemm out_kv24): a cache row is 1536 bytes
+// [K hi 256 x u16 | V hi 256 x u16 | K lo 256 x u8 | V lo 256 x u8]; a value is (hi << 16 | lo << 8) as fp32 bits.
+// 25 % fewer bytes on the stream that bounds the decode loop.  8 lanes cover one key of one head (4 channels each:
+// 8 B of hi + 4 B of lo per operand), 4 keys per warp-wide load, 32 keys per batch.
+__device__ __forceinline__ float4 kv24_unpack(const uint2 hi, const uint32_t lo) {
+  float4 f;
+  f.x = __uint_as_float((hi.x << 16) | ((lo & 0xffu) << 8));
+  f.y = __uint_as_float((hi.x & 0xffff0000u) | (lo & 0xff00u));
+  f.z = __uint_as_float((hi.y << 16) | ((lo >> 8) & 0xff00u));
+  f.w = __uint_as_float((hi.y & 0xffff0000u) | ((lo >> 16) & 0xff00u));
+  return f;
+}
+
+__global__ void __launch_bounds__(256)
+attention_decode_kv24_kernel(const float* __restrict__ q, int ldq, const uint8_t* __restrict__ kv, long long kv_bstride,
+                             int Tk, int H, float scale, __nv_bfloat16* __restrict__ out_split, long long out_plane,
+                             int ldo) {
+  constexpr int DH = 32, CPL = 8, KPI = 4, UN = 8, ROW = 1536;
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x;
+  if (h >= H) return;
+  const int kk = lane / CPL, c = lane % CPL;
+  float4 q4 = *reinterpret_cast<const float4*>(q + static_cast<long long>(b) * ldq + h * DH + 4 * c);
+  q4.x *= scale; q4.y *= scale; q4.z *= scale; q4.w *= scale;
+  const uint8_t* base = kv + static_cast<long long>(b) * kv_bstride * ROW;
+  const int o_khi = h * 64 + c * 8, o_vhi = 512 + h * 64 + c * 8, o_klo = 1024 + h * 32 + c * 4,
+            o_vlo = 1280 + h * 32 + c * 4;
+  float m = -INFINITY, l = 0.f;
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+  for (int j0 = 0; j0 < Tk; j0 += 32) {
+    uint2 kh[UN], vh[UN];
+    uint32_t kl[UN], vl[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int j = j0 + u * KPI + kk;
+      kh[u] = vh[u] = make_uint2(0u, 0u);
+      kl[u] = vl[u] = 0u;
+      if (j < Tk) {
+        const uint8_t* r = base + static_cast<long long>(j) * ROW;
+        kh[u] = __ldcs(reinterpret_cast<const uint2*>(r + o_khi));
+        vh[u] = __ldcs(reinterpret_cast<const uint2*>(r + o_vhi));
+        kl[u] = __ldcs(reinterpret_cast<const uint32_t*>(r + o_klo));
+        vl[u] = __ldcs(reinterpret_cast<const uint32_t*>(r + o_vlo));
+      }
+    }
+    float s[UN];
+    float bm = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const float4 kf = kv24_unpack(kh[u], kl[u]);
+      float d = q4.x * kf.x + q4.y * kf.y + q4.z * kf.z + q4.w * kf.w;
+#pragma unroll
+      for (int off = CPL >> 1; off >= 1; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+      s[u] = (j0 + u * KPI + kk < Tk) ? d : -INFINITY;
+      bm = fmaxf(bm, s[u]);
+    }
+#pragma unroll
+    for (int off = CPL; off < 32; off <<= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, off));
+    const float m_new = fmaxf(m, bm);
+    const float corr = __expf(m - m_new);
+    l *= corr;
+    o.x *= corr; o.y *= corr; o.z *= corr; o.w *= corr;
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const float p = __expf(s[u] - m_new);
+      const float4 vf = kv24_unpack(vh[u], vl[u]);
+      l += p;
+      o.x = fmaf(p, vf.x, o.x); o.y = fmaf(p, vf.y, o.y);
+      o.z = fmaf(p, vf.z, o.z); o.w = fmaf(p, vf.w, o.w);
+    }
+    m = m_new;
+  }
+#pragma unroll
+  for (int off = CPL; off < 32; off <<= 1) {
+    o.x += __shfl_xor_sync(0xffffffffu, o.x, off); o.y += __shfl_xor_sync(0xffffffffu, o.y, off);
+    o.z += __shfl_xor_sync(0xffffffffu, o.z, off); o.w += __shfl_xor_sync(0xffffffffu, o.w, off);
+    l += __shfl_xor_sync(0xffffffffu, l, off);
+  }
+  if (kk == 0) {
+    const float inv = 1.f / l;
+    const long long off0 = static_cast<long long>(b) * ldo + h * DH + 4 * c;
+    store_split(out_split, out_plane, off0 + 0, o.x * inv);
+    store_split(out_split, out_plane, off0 + 1, o.y * inv);
+    store_split(out_split, out_plane, off0 + 2, o.z * inv);
+    store_split(out_split, out_plane, off0 + 3, o.w * inv);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // ResNet stem im2col: image fp32 NCHW [B, 4, H, W] -> split rows [B*Ho*Wo, KP] with k = (kh*7+kw)*4+c
 // for the 7x7 / stride 2 / pad 3 convolution (common/image.py:69-77), zero padded to KP columns.
@@ -850,6 +939,17 @@ extern "C" int ralf_attention_decode(const float* q, int ldq, const float* k, co
                                      void* stream) {
   return attention_decode_impl(q, ldq, k, v, kv_bstride, ldk, key_padding_mask, mask_ld, Tk, B, H, head_dim, scale,
                                out_split, out_plane, ldo, nullptr, nullptr, 0, nullptr, nullptr, stream);
+}
+
+extern "C" int ralf_attention_decode_kv24(const float* q, int ldq, const void* kv24, long long kv_bstride, int Tk, int B,
+                                          int H, float scale, void* out_split, long long out_plane, int ldo,
+                                          void* stream) {
+  if (!q || !kv24 || !out_split) return RALF_ERR_NULL;
+  if (B <= 0 || H != 8 || Tk <= 0) return RALF_ERR_SHAPE;  // row format: 8 heads x 32 (d_model 256)
+  if ((ldq & 3) || (reinterpret_cast<uintptr_t>(kv24) & 15)) return RALF_ERR_ALIGN;
+  attention_decode_kv24_kernel<<<B, 32 * H, 0, ST(stream)>>>(q, ldq, reinterpret_cast<const uint8_t*>(kv24), kv_bstride,
+                                                             Tk, H, scale, BF(out_split), out_plane, ldo);
+  return set_cuda_error(cudaGetLastError());
 }
 
 extern "C" int ralf_attention_decode_append(const float* qkv, int ldqkv, float* kcache, float* vcache, int S, int pos,

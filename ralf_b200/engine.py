@@ -31,6 +31,8 @@ D = 256
 # in-kernel row normalisation costs more than the separate 4 us LayerNorm launch it removes (1698 vs 2162 layouts/s).
 # RALF_FUSE_LN=1 switches it on for A/B runs.
 FUSE_LN = os.environ.get("RALF_FUSE_LN", "0") != "0"
+# Decoder cross-attention K/V cache of the greedy loop in the 24-bit format (3 bytes per value); RALF_KV24=0 keeps fp32.
+KV24 = os.environ.get("RALF_KV24", "1") != "0"
 # 3x3 stride-1 convolutions as implicit GEMMs (ralf_conv_gemm); RALF_IMPLICIT_CONV=0 restores im2col + GEMM for A/B runs.
 IMPLICIT_CONV = os.environ.get("RALF_IMPLICIT_CONV", "1") != "0"
 
@@ -403,21 +405,29 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # decoder
     # ------------------------------------------------------------------------------------------
-    def alloc_cross_kv(self, rows: int) -> list:
-        """Decoder cross-attention K/V cache, layer-major: 6 x fp32 [rows, 512] (K = cols 0..255, V = 256..511), so
-        one layer's K/V of a canvas is ONE contiguous 2 KB x M stream for the decode kernel."""
+    def alloc_cross_kv(self, rows: int, kv24: bool = False) -> list:
+        """Decoder cross-attention K/V cache, layer-major.  fp32: 6 x [rows, 512] (K = cols 0..255, V = 256..511), so
+        one layer's K/V of a canvas is ONE contiguous 2 KB x M stream for the decode kernel.  ``kv24``: 6 x uint8
+        [rows, 1536] rows in the 24-bit format of include/ralf_b200.h (3 bytes per value: the greedy decode loop is bound
+        by this stream)."""
+        if kv24:
+            return [torch.empty((rows, 1536), dtype=torch.uint8, device=self.dev) for _ in range(NLAYER)]
         return [torch.empty((rows, 2 * D), dtype=torch.float32, device=self.dev) for _ in range(NLAYER)]
 
-    def cross_kv(self, mem_s: torch.Tensor, out: Optional[list] = None, row0: int = 0) -> list:
+    def cross_kv(self, mem_s: torch.Tensor, out: Optional[list] = None, row0: int = 0, kv24: bool = False) -> list:
         """K/V of the memory rows for all 6 decoder layers (one GEMM per layer, N = 512); written into rows
         [row0, row0 + rows) of ``out`` when given (micro-batched encode)."""
         rows = mem_s.shape[1]
         if out is None:
-            out = self.alloc_cross_kv(rows)
+            out = self.alloc_cross_kv(rows, kv24)
+        kv24 = out[0].dtype == torch.uint8
         w, b = self.w["decoder.ckv.w"], self.w["decoder.ckv.b"]
         for i in range(NLAYER):
-            ops.gemm(mem_s, w[:, i * 2 * D:(i + 1) * 2 * D], bias=b[i * 2 * D:(i + 1) * 2 * D], npass=self.npass,
-                     out_f32=out[i][row0:row0 + rows])
+            wi, bi = w[:, i * 2 * D:(i + 1) * 2 * D], b[i * 2 * D:(i + 1) * 2 * D]
+            if kv24:
+                ops.gemm(mem_s, wi, bias=bi, npass=self.npass, want_f32=False, out_kv24=out[i][row0:row0 + rows])
+            else:
+                ops.gemm(mem_s, wi, bias=bi, npass=self.npass, out_f32=out[i][row0:row0 + rows])
         return out
 
     def decoder_logits(self, seq: torch.Tensor, pad_mask: torch.Tensor, mem_s: torch.Tensor, B: int, Mlen: int):
@@ -449,7 +459,8 @@ class Engine:
         token_mask: uint8 [steps, V] (tokenizer.token_mask).  Returns seq int64 [B, steps] (BOS dropped).
         ``kv``: precomputed cross-attention cache (cross_kv) of all B canvases; else built from ``mem_s``."""
         dev = self.dev
-        kvm = kv if kv is not None else self.cross_kv(mem_s)
+        kvm = kv if kv is not None else self.cross_kv(mem_s, kv24=KV24 and self.npass == 3)
+        kv24 = kvm[0].dtype == torch.uint8
         seq = torch.full((B, steps + 1), pad_id, dtype=torch.int64, device=dev)
         seq[:, 0] = bos_id
         pad_mask = torch.zeros((B, steps + 1), dtype=torch.uint8, device=dev)
@@ -468,7 +479,10 @@ class Engine:
                 a = ops.attention_decode_append(qkv, kc[i], vc[i], t, B, NHEAD, 32, mask=pad_mask)
                 self._gemm(a, p + ".o", res=x, out_f32=x)
                 q, _ = self._gemm_ln(x, p + ".norm2", p + ".cq")
-                a = ops.attention_decode(q, kvm[i][:, :D], kvm[i][:, D:], Mlen, Mlen, B, NHEAD, 32)
+                if kv24:
+                    a = ops.attention_decode_kv24(q, kvm[i], Mlen, Mlen, B, NHEAD)
+                else:
+                    a = ops.attention_decode(q, kvm[i][:, :D], kvm[i][:, D:], Mlen, Mlen, B, NHEAD, 32)
                 self._gemm(a, p + ".co", res=x, out_f32=x)
                 _, f = self._gemm_ln(x, p + ".norm3", p + ".linear1", act="relu", want_f32=False, want_split=True)
                 self._gemm(f, p + ".linear2", res=x, out_f32=x)

@@ -73,6 +73,7 @@ def gemm(
     want_split: bool = False,
     conv: Optional[tuple] = None,
     stem: Optional[tuple] = None,
+    out_kv24: Optional[torch.Tensor] = None,
 ) -> tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """D = A . W^T with the fused epilogue of ``ralf_gemm`` (include/ralf_b200.h).
 
@@ -124,6 +125,11 @@ def gemm(
     g.out_split_lo = 1 if npass == 3 else 0
     g.out_ld, g.out_col0 = out_ld, out_col0
     g.rows_per_group, g.group_stride, g.group_offset = rows_per_group, group_stride, group_offset
+    if out_kv24 is not None:  # uint8 [M, 1536] rows of the 24-bit K/V cache (N = 512)
+        assert out_kv24.dtype == torch.uint8 and out_kv24.shape[-1] == 1536 and out_kv24.is_contiguous() and N == 512
+        g.out_kv24 = out_kv24.data_ptr()
+        if out_f32 is None and out_split is None:
+            g.out_ld = 512  # unused, keeps the alignment checks trivially true
     if stem is not None:
         check(_lib.lib().ralf_stem_gemm(C.byref(g), *stem, _stream()), "ralf_stem_gemm")
     elif conv is not None:
@@ -254,6 +260,18 @@ def attention_decode(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, kv_bstri
                                            k.stride(0), _ptr(mask), mask.stride(0) if mask is not None else 0, Tk, B,
                                            H, dh, dh ** -0.5, out.data_ptr(), out.stride(0), H * dh, _stream()),
           "ralf_attention_decode")
+    return out
+
+
+def attention_decode_kv24(q: torch.Tensor, kv24: torch.Tensor, kv_bstride: int, Tk: int, B: int, H: int, *,
+                          out: Optional[torch.Tensor] = None):
+    """Decode-step cross-attention over the 24-bit K/V cache (uint8 [rows, 1536]); returns split [2, B, 256]."""
+    assert kv24.dtype == torch.uint8 and kv24.shape[-1] == 1536 and H == 8
+    if out is None:
+        out = _split_out(B, H * 32, q.device)
+    check(_lib.lib().ralf_attention_decode_kv24(q.data_ptr(), q.stride(0), kv24.data_ptr(), kv_bstride, Tk, B, H,
+                                                32 ** -0.5, out.data_ptr(), out.stride(0), H * 32, _stream()),
+          "ralf_attention_decode_kv24")
     return out
 
 

@@ -68,7 +68,9 @@ class LayoutPipeline:
             mem, mem_s = self.eng.encode(self.img[b0:b1], packed[b0:b1], self.const_seq[b0:b1], self.const_pad[b0:b1])
             Mlen = mem.shape[1]
             if kv is None:
-                kv = self.eng.alloc_cross_kv(self.B * Mlen)
+                from .engine import KV24
+
+                kv = self.eng.alloc_cross_kv(self.B * Mlen, kv24=KV24 and self.eng.npass == 3)
             self.eng.cross_kv(mem_s, out=kv, row0=b0 * Mlen)
             del mem, mem_s
         seq = self.eng.generate(None, self.B, Mlen, self.token_mask, self.ids["bos"], self.ids["pad"], self.S, kv=kv)

@@ -92,3 +92,28 @@ def test_encoder_attention_tcgen05_matches_fp64(cuda_device, B, Tq, Tk, H):
     ref = (torch.softmax(qd @ kd.transpose(-1, -2) * dh ** -0.5, -1) @ vd).permute(0, 2, 1, 3).reshape(B * Tq, D)
     err = (out - ref).abs().max().item() / ref.abs().max().item()
     assert err <= 3e-5, err
+
+
+@pytest.mark.parametrize("B,Tk", [(3, 532), (130, 334), (2, 40)])
+def test_kv24_cache_gemm_and_cross_attention(cuda_device, B, Tk):
+    """24-bit K/V cache: ralf_gemm(out_kv24) must store exactly round-to-24-bit of its fp32 result, and the kv24 decode
+    kernel must equal float64 attention over those stored values."""
+    from ralf_b200 import ops
+
+    H, dh, D = 8, 32, 256
+    g = torch.Generator(device=cuda_device).manual_seed(B + Tk)
+    mem = ops.split_bf16(torch.randn(B * Tk, D, device=cuda_device, generator=g))
+    w = ops.split_bf16(torch.randn(2 * D, D, device=cuda_device, generator=g) / 16)
+    bias = torch.randn(2 * D, device=cuda_device, generator=g)
+    ref32, _ = ops.gemm(mem, w, bias=bias)
+    kv24 = torch.empty(B * Tk, 1536, dtype=torch.uint8, device=cuda_device)
+    ops.gemm(mem, w, bias=bias, want_f32=False, out_kv24=kv24)
+    hi = kv24[:, :1024].contiguous().view(torch.int16).to(torch.int32) & 0xFFFF   # [rows, 512]: K | V
+    lo = kv24[:, 1024:].to(torch.int32)
+    got = ((hi << 16) | (lo << 8)).view(torch.float32)
+    want = ((ref32.view(torch.int32) + 0x80) & ~0xFF).view(torch.float32)
+    assert torch.equal(got, want)
+    q = torch.randn(B, D, device=cuda_device, generator=g) * 2
+    out = ops.unsplit(ops.attention_decode_kv24(q, kv24, Tk, Tk, B, H)).double()
+    ref = _ref_decode(q, want[:, :D], want[:, D:], B, H, dh, Tk)
+    assert (out - ref).abs().max().item() <= 2e-5 * ref.abs().max().item() + 1e-6
