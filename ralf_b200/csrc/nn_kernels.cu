@@ -6,6 +6,8 @@
 #include <float.h>
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ralf_internal.h"
 
@@ -292,9 +294,11 @@ attention_decode_kernel(const float* __restrict__ q, int ldq, const float* k /* 
 // ------------------------------------------------------------------------------------------------
 template <int DH>
 __global__ void __launch_bounds__(256)
-attention_decode_stream_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k,
-                               const float* __restrict__ v, long long kv_bstride, int ldk, int Tk, int H, float scale,
-                               __nv_bfloat16* __restrict__ out_split, long long out_plane, int ldo) {
+attention_decode_stream_kernel(const float* __restrict__ q, int ldq, const float* k, const float* v,
+                               long long kv_bstride, int ldk, int Tk, int H, float scale,
+                               __nv_bfloat16* __restrict__ out_split, long long out_plane, int ldo,
+                               const unsigned char* __restrict__ mask, int mask_ld, const float* __restrict__ knew,
+                               const float* __restrict__ vnew, int ldnew, float* kc_w, float* vc_w) {
   constexpr int CPL = DH / 4;    // lanes per key row (16 B each)
   constexpr int KPI = 32 / CPL;  // keys per warp-wide load
   constexpr int UN = 32 / KPI;   // loads per batch of 32 keys
@@ -306,19 +310,32 @@ attention_decode_stream_kernel(const float* __restrict__ q, int ldq, const float
   q4.x *= scale; q4.y *= scale; q4.z *= scale; q4.w *= scale;
   const float* kb = k + static_cast<long long>(b) * kv_bstride * ldk + h * DH + 4 * c;
   const float* vb = v + static_cast<long long>(b) * kv_bstride * ldk + h * DH + 4 * c;
+  if (knew) {  // self-attention step: append this step's K/V row (position Tk-1) of this head, then attend over it
+    if (kk == 0) {
+      const long long dst = (static_cast<long long>(b) * kv_bstride + (Tk - 1)) * ldk + h * DH + 4 * c;
+      const long long src = static_cast<long long>(b) * ldnew + h * DH + 4 * c;
+      *reinterpret_cast<float4*>(kc_w + dst) = *reinterpret_cast<const float4*>(knew + src);
+      *reinterpret_cast<float4*>(vc_w + dst) = *reinterpret_cast<const float4*>(vnew + src);
+    }
+    __syncwarp();
+  }
+  const unsigned char* mrow = mask ? mask + static_cast<long long>(b) * mask_ld : nullptr;
   float m = -INFINITY, l = 0.f;
   float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
   for (int j0 = 0; j0 < Tk; j0 += 32) {
     float4 kf[UN], vf[UN];
+    bool live[UN];
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
       const int j = j0 + u * KPI + kk;
       kf[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       vf[u] = kf[u];
+      live[u] = j < Tk;
       if (j < Tk) {
         kf[u] = __ldcs(reinterpret_cast<const float4*>(kb + static_cast<long long>(j) * ldk));
         vf[u] = __ldcs(reinterpret_cast<const float4*>(vb + static_cast<long long>(j) * ldk));
+        if (mrow && mrow[j]) live[u] = false;  // padded key
       }
     }
     float s[UN];
@@ -328,12 +345,13 @@ attention_decode_stream_kernel(const float* __restrict__ q, int ldq, const float
       float d = q4.x * kf[u].x + q4.y * kf[u].y + q4.z * kf[u].z + q4.w * kf[u].w;
 #pragma unroll
       for (int off = CPL >> 1; off >= 1; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
-      s[u] = (j0 + u * KPI + kk < Tk) ? d : -INFINITY;
+      s[u] = live[u] ? d : -INFINITY;
       bm = fmaxf(bm, s[u]);
     }
 #pragma unroll
     for (int off = CPL; off < 32; off <<= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, off));
-    const float m_new = fmaxf(m, bm);  // finite: every batch holds at least one valid key
+    if (bm == -INFINITY) continue;     // a batch of masked keys only (warp-uniform)
+    const float m_new = fmaxf(m, bm);
     const float corr = __expf(m - m_new);
     l *= corr;
     o.x *= corr; o.y *= corr; o.z *= corr; o.w *= corr;
@@ -910,13 +928,20 @@ static int attention_decode_impl(const float* q, int ldq, const float* k, const 
   if (!q || !k || !v || !out_split) return RALF_ERR_NULL;
   if (B <= 0 || H <= 0 || Tk <= 0 || Tk > 2048 || (head_dim != 32 && head_dim != 64)) return RALF_ERR_SHAPE;
   if ((ldq & 3) || (ldk & 3)) return RALF_ERR_ALIGN;
-  if (!key_padding_mask && !knew && H <= 8 && Tk >= 64) {  // memory cross-attention: streaming single-pass kernel
+  // Single-pass streaming kernel (CTA per canvas, warp per head): the memory cross-attention (no mask, long Tk) and the
+  // decode self-attention over the short token cache (append fused, key-padding mask).  RALF_DECODE_2PASS=1 keeps the
+  // two-pass kernel for the masked / appended case (A/B runs).
+  static const bool two_pass = getenv("RALF_DECODE_2PASS") && atoi(getenv("RALF_DECODE_2PASS")) != 0;
+  const bool plain = !key_padding_mask && !knew;
+  if (H <= 8 && (plain ? Tk >= 64 : !two_pass)) {
     if (head_dim == 32)
-      attention_decode_stream_kernel<32><<<B, 32 * H, 0, ST(stream)>>>(q, ldq, k, v, kv_bstride, ldk, Tk, H, scale,
-                                                                      BF(out_split), out_plane, ldo);
+      attention_decode_stream_kernel<32><<<B, 32 * H, 0, ST(stream)>>>(
+          q, ldq, k, v, kv_bstride, ldk, Tk, H, scale, BF(out_split), out_plane, ldo, key_padding_mask, mask_ld, knew,
+          vnew, ldnew, kc_w, vc_w);
     else
-      attention_decode_stream_kernel<64><<<B, 32 * H, 0, ST(stream)>>>(q, ldq, k, v, kv_bstride, ldk, Tk, H, scale,
-                                                                      BF(out_split), out_plane, ldo);
+      attention_decode_stream_kernel<64><<<B, 32 * H, 0, ST(stream)>>>(
+          q, ldq, k, v, kv_bstride, ldk, Tk, H, scale, BF(out_split), out_plane, ldo, key_padding_mask, mask_ld, knew,
+          vnew, ldnew, kc_w, vc_w);
     return set_cuda_error(cudaGetLastError());
   }
   const size_t smem = static_cast<size_t>((Tk + 31) & ~31) * sizeof(float);
