@@ -45,7 +45,11 @@ class LayoutPipeline:
         self.seq_out = torch.zeros(batch, self.S, dtype=torch.int64, device=self.dev)
         self.idx_out = torch.zeros(batch, top_k, dtype=torch.int64, device=self.dev)
         self.g_search: Optional[torch.cuda.CUDAGraph] = None
-        self.g_main: Optional[torch.cuda.CUDAGraph] = None
+        self.g_fetch: Optional[torch.cuda.CUDAGraph] = None
+        self.g_enc: list = []
+        self.g_dec: Optional[torch.cuda.CUDAGraph] = None
+        self.kv, self.Mlen = None, 0
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.use_graph = use_graph
         self.kernels_per_step = 0
         self._local = None  # (idx, score) of the local search when sharded
@@ -58,23 +62,32 @@ class LayoutPipeline:
         idx, score = self.retr.search_local(self.q_all, self.k)
         return idx, score
 
-    def _stage_main(self, idx: torch.Tensor):
-        """idx: global top-k of this rank's canvases [B, k]."""
+    def _stage_fetch(self, idx: torch.Tensor):
+        """idx: global top-k of this rank's canvases [B, k] -> packed exemplar layouts [B, k, 6, E]."""
         self.idx_out.copy_(idx)
-        packed = self.retr.fetch(idx)["packed"]
-        kv, Mlen = None, 0
-        for b0 in range(0, self.B, self.mb):
-            b1 = min(self.B, b0 + self.mb)
-            mem, mem_s = self.eng.encode(self.img[b0:b1], packed[b0:b1], self.const_seq[b0:b1], self.const_pad[b0:b1])
-            Mlen = mem.shape[1]
-            if kv is None:
-                from .engine import KV24
+        return self.retr.fetch(idx)["packed"]
 
-                kv = self.eng.alloc_cross_kv(self.B * Mlen, kv24=KV24 and self.eng.npass == 3)
-            self.eng.cross_kv(mem_s, out=kv, row0=b0 * Mlen)
-            del mem, mem_s
-        seq = self.eng.generate(None, self.B, Mlen, self.token_mask, self.ids["bos"], self.ids["pad"], self.S, kv=kv)
+    def _stage_encode(self, packed: torch.Tensor, b0: int) -> None:
+        """One encoder micro-batch (canvases b0 .. b0+mb): memory -> rows of the batch-wide cross-attention K/V cache."""
+        b1 = min(self.B, b0 + self.mb)
+        mem, mem_s = self.eng.encode(self.img[b0:b1], packed[b0:b1], self.const_seq[b0:b1], self.const_pad[b0:b1])
+        self.Mlen = mem.shape[1]
+        if self.kv is None:
+            from .engine import KV24
+
+            self.kv = self.eng.alloc_cross_kv(self.B * self.Mlen, kv24=KV24 and self.eng.npass == 3)
+        self.eng.cross_kv(mem_s, out=self.kv, row0=b0 * self.Mlen)
+
+    def _stage_decode(self) -> None:
+        seq = self.eng.generate(None, self.B, self.Mlen, self.token_mask, self.ids["bos"], self.ids["pad"], self.S,
+                                kv=self.kv)
         self.seq_out.copy_(seq)
+
+    def _stage_main(self, idx: torch.Tensor):
+        packed = self._stage_fetch(idx)
+        for b0 in range(0, self.B, self.mb):
+            self._stage_encode(packed, b0)
+        self._stage_decode()
 
     def _merge(self, idx, score):
         from . import ops
@@ -109,15 +122,28 @@ class LayoutPipeline:
             self._local = self._stage_search()
         self._my_idx = self._local[0] if self.world == 1 else torch.zeros(self.B, self.k, dtype=torch.int64,
                                                                          device=self.dev)
-        self.g_main = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_main):
-            self._stage_main(self._my_idx)
+        # everything after the search: fetch, one graph per encoder micro-batch (so the host->device copy of micro-batch
+        # i+1 can run under the encode of micro-batch i, see __call__), the decode loop.  The graphs share one memory
+        # pool and are always replayed in capture order.
+        pool = self.g_search.pool()
+        self.g_fetch = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_fetch, pool=pool):
+            self._packed = self._stage_fetch(self._my_idx)
+        self.g_enc = []
+        for b0 in range(0, self.B, self.mb):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                self._stage_encode(self._packed, b0)
+            self.g_enc.append(g)
+        self.g_dec = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_dec, pool=pool):
+            self._stage_decode()
         # kernels of OURS recorded into the two graphs = kernels launched per replayed step
         self.kernels_per_step = ops.launch_count() - n0 + (2 if self.world > 1 else 0)
         torch.cuda.synchronize()
 
     # ---- run -----------------------------------------------------------------------------------
-    def step(self, events: Optional[list] = None) -> torch.Tensor:
+    def step(self, events: Optional[list] = None, copy_events: Optional[list] = None) -> torch.Tensor:
         """One pass over the static inputs (self.img, self.qry already filled).  Returns token ids [B, S] (device).
         ``events``: optional list that receives a (start, end) CUDA-event pair around the k-NN phase."""
         if self.world > 1:
@@ -143,14 +169,32 @@ class LayoutPipeline:
             events.append((e0, e1))
         if self.world > 1:
             self._my_idx.copy_(self._merge(*self._local))
-        self.g_main.replay()
+        self.g_fetch.replay()
+        for i, g in enumerate(self.g_enc):
+            if copy_events is not None:  # micro-batch i's canvases must have landed
+                torch.cuda.current_stream().wait_event(copy_events[i])
+            g.replay()
+        self.g_dec.replay()
         return self.seq_out
 
     def __call__(self, image: torch.Tensor, query: torch.Tensor) -> torch.Tensor:
-        """image [B,4,H,W] and query [B,d] on host (pinned) or device -> token ids [B, S] on the device."""
-        self.img.copy_(image, non_blocking=True)
+        """image [B,4,H,W] and query [B,d] on host (pinned) or device -> token ids [B, S] on the device.
+        The canvases are copied micro-batch by micro-batch on a side stream; the search and the encoder graphs of the
+        earlier micro-batches run underneath the later copies."""
+        main = torch.cuda.current_stream()
         self.qry.copy_(query, non_blocking=True)
-        return self.step()
+        if not self.use_graph:
+            self.img.copy_(image, non_blocking=True)
+            return self.step()
+        self.copy_stream.wait_stream(main)  # the previous step has consumed self.img
+        evs = []
+        with torch.cuda.stream(self.copy_stream):
+            for b0 in range(0, self.B, self.mb):
+                self.img[b0:b0 + self.mb].copy_(image[b0:b0 + self.mb], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+                evs.append(ev)
+        return self.step(copy_events=evs)
 
     def generate_layouts(self, image: torch.Tensor, query: torch.Tensor) -> dict:
         """Host-facing call: returns the decoded layout dict on the CPU like ``model.sample`` does
