@@ -109,7 +109,11 @@ typedef struct RalfGemmArgs {
                        * is the fp32 result rounded to 24 bits, hi = bits 31..16, lo = bits 15..8 (16-bit mantissa,
                        * the accuracy class of the bf16x3 product that made it) -- 3 instead of 4 bytes per element on
                        * the stream the decode loop is bound by */
+  void* splitk_ws;    /* optional workspace: lets a plain fp32-output GEMM with few M x N tiles and a long K (weight
+                       * gradients: K = all rows of the batch) run split-K (k slices -> partials -> deterministic sum) */
+  size_t splitk_ws_bytes; /* >= ralf_gemm_splitk_workspace_bytes(M, N, K) */
 } RalfGemmArgs;
+size_t ralf_gemm_splitk_workspace_bytes(int M, int N, int K);
 int ralf_gemm(const RalfGemmArgs* args, void* stream);
 /* Stride-1 "same" convolution (nn.Conv2d(C, N, KH, padding=KH/2), BatchNorm folded; common/image.py:39-83 -- the 3x3
  * convolutions of the ResNet50 bottlenecks and of the FPN) as an IMPLICIT GEMM: args->A is the NHWC split activation
@@ -245,6 +249,11 @@ int ralf_grad_norm(const float* grads, long long n, float* workspace /* 1024 flo
 int ralf_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
                     const float* grad_norm, float max_norm, float lr, float beta1, float beta2, float eps,
                     float weight_decay, int step, void* stream);
+/* Same, with the per-step scalars in device memory (dyn = {lr scale, 1 - beta1^t, 1 - beta2^t}) so that a captured
+ * CUDA graph of the whole training step can be replayed. */
+int ralf_adamw_step_dyn(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                        const float* grad_norm, float max_norm, float lr, float beta1, float beta2, float eps,
+                        float weight_decay, const float* dyn, void* stream);
 /* BatchNorm2d in training mode on NHWC rows [M, C]: mode 0 = batch mean / rstd (+ running-stat update),
  * mode 1 = (sum a, sum a*xhat) for the backward; workspace = 2*C*ceil(M/2048) floats. */
 int ralf_bn_colstats(const float* a, const float* z, const float* mean, const float* rstd, int mode, int M, int C,

@@ -34,6 +34,7 @@ class GemmArgs(C.Structure):
         ("out_split_lo", C.c_int), ("out_ld", C.c_int), ("out_col0", C.c_int),
         ("rows_per_group", C.c_int), ("group_stride", C.c_int), ("group_offset", C.c_int),
         ("out_kv24", C.c_void_p),
+        ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_size_t),
     ]
 
 
@@ -63,6 +64,8 @@ def lib() -> C.CDLL:
         L.ralf_knn_merge.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_void_p]
         L.ralf_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
+        L.ralf_gemm_splitk_workspace_bytes.restype = C.c_size_t
+        L.ralf_gemm_splitk_workspace_bytes.argtypes = [C.c_int] * 3
         L.ralf_conv_gemm.argtypes = [C.POINTER(GemmArgs)] + [C.c_int] * 6 + [C.c_void_p]
         L.ralf_stem_gemm.argtypes = [C.POINTER(GemmArgs)] + [C.c_int] * 3 + [C.c_void_p]
         L.ralf_stem_s2d.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]
@@ -99,6 +102,7 @@ def lib() -> C.CDLL:
         L.ralf_embed_bwd.argtypes = [vp, ll, i, i, i, vp, i, f, vp, vp]
         L.ralf_grad_norm.argtypes = [vp, ll, vp, vp, vp]
         L.ralf_adamw_step.argtypes = [vp, vp, vp, vp, ll, vp, f, f, f, f, f, f, i, vp]
+        L.ralf_adamw_step_dyn.argtypes = [vp, vp, vp, vp, ll, vp, f, f, f, f, f, f, vp, vp]
         L.ralf_bn_colstats.argtypes = [vp, vp, vp, vp, i, i, i, f, f, vp, vp, vp, vp, vp, vp]
         L.ralf_bn_apply.argtypes = [vp, vp, vp, vp, vp, vp, ll, i, i, i, vp, ll, vp, vp]
         L.ralf_bn_bwd_apply.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, vp, vp]

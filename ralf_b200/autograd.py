@@ -44,31 +44,37 @@ def _L():
     return _lib.lib()
 
 
-def to_split(x: torch.Tensor) -> torch.Tensor:
+def to_split(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """fp32 [M, C] -> split [2, M, C]; the row pitch is padded to a multiple of 8 elements when C is not (TMA needs
-    16-byte row pitches), in which case a [:, :, :C] view of the padded buffer is returned."""
+    16-byte row pitches), in which case a [:, :, :C] view of the padded buffer is returned.  ``out``: a tensor this
+    function returned earlier for the same shape -- rewritten in place (operand buffers must keep their address across
+    optimiser steps so that a captured training graph keeps reading the live weights)."""
     M, Cn = x.shape
     if Cn % 8 == 0 and x.is_contiguous():
-        out = torch.empty((2, M, Cn), dtype=torch.bfloat16, device=x.device)
+        if out is None:
+            out = torch.empty((2, M, Cn), dtype=torch.bfloat16, device=x.device)
         check(_L().ralf_to_split(x.data_ptr(), x.numel(), out.data_ptr(), out.stride(0), _stream()), "ralf_to_split")
         return out
     Cp = (Cn + 7) // 8 * 8
-    out = torch.empty((2, M, Cp), dtype=torch.bfloat16, device=x.device)
+    if out is None:
+        out = torch.empty((2, M, Cp), dtype=torch.bfloat16, device=x.device)[:, :, :Cn]
     ops.rows_affine(x, M, Cn, in_ld=x.stride(0), out_split=out, out_ld=Cp)
-    return out[:, :, :Cn]
+    return out
 
 
-def transpose_to_split(x_f32: Optional[torch.Tensor] = None, x_split: Optional[torch.Tensor] = None) -> torch.Tensor:
+def transpose_to_split(x_f32: Optional[torch.Tensor] = None, x_split: Optional[torch.Tensor] = None,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[R, C] (fp32 or split) -> split [2, C, Rp] with Rp = R rounded up to 8 (row pitch for the tensor map);
     the logical K extent of the result is R (columns >= R are never read)."""
     src = x_f32 if x_f32 is not None else x_split[0]
     R, Cn = src.shape[-2], src.shape[-1]
     Rp = (R + 7) // 8 * 8
-    out = torch.empty((2, Cn, Rp), dtype=torch.bfloat16, device=src.device)
+    if out is None:  # else: the [2, C, R] view (row stride Rp) returned by an earlier call, rewritten in place
+        out = torch.empty((2, Cn, Rp), dtype=torch.bfloat16, device=src.device)[:, :, :R]
     check(_L().ralf_transpose_to_split(_ptr(x_f32), _ptr(x_split), x_split.stride(0) if x_split is not None else 0,
                                        src.stride(-2), R, Cn, out.data_ptr(), out.stride(0), Rp, _stream()),
           "ralf_transpose_to_split")
-    return out[:, :, :R]  # view: shape [2, C, R], row stride Rp
+    return out  # shape [2, C, R], row stride Rp
 
 
 def colsum(x: torch.Tensor, out: torch.Tensor, accumulate: bool = False) -> None:
@@ -143,8 +149,8 @@ class ParamStore:
         """master fp32 weights -> split W [2,N,K] and W^T [2,K,N] for every registered GEMM weight."""
         for name in self.gemm_weights:
             w = self.weight_view(name)
-            self.w[name] = to_split(w)
-            self.wT[name] = transpose_to_split(x_f32=w)
+            self.w[name] = to_split(w, out=self.w.get(name))
+            self.wT[name] = transpose_to_split(x_f32=w, out=self.wT.get(name))
 
 
 # ---- ops --------------------------------------------------------------------------------------------
@@ -168,7 +174,7 @@ def linear(tape: Tape, ps: ParamStore, x: Node, wname: str, bias: Optional[str] 
             accumulate(res, dy)  # residual branch shares dy (read-only from here on)
         dyT = transpose_to_split(x_f32=dy)            # [2, N, M]
         xT = transpose_to_split(x_split=x.s)          # [2, K, M]
-        ops.gemm(dyT, xT, out_f32=ps.weight_view(wname, grad=True), npass=npass)   # dW = dY^T X
+        ops.gemm(dyT, xT, out_f32=ps.weight_view(wname, grad=True), npass=npass, splitk=True)   # dW = dY^T X
         if bias is not None:
             colsum(dy, ps.g(bias))
         if x.need_grad:
@@ -343,12 +349,18 @@ def grad_norm(flat_g: torch.Tensor) -> torch.Tensor:
 
 
 def adamw_step(ps: ParamStore, group_cfg: list[tuple[float, float]], step: int, max_norm: float, norm: torch.Tensor,
-               betas=(0.9, 0.999), eps: float = 1e-8) -> None:
-    """torch.optim.AdamW + clip_grad_norm_(max_norm) over the flat buffers, one launch per (lr, wd) group."""
+               betas=(0.9, 0.999), eps: float = 1e-8, dyn: Optional[torch.Tensor] = None) -> None:
+    """torch.optim.AdamW + clip_grad_norm_(max_norm) over the flat buffers, one launch per (lr, wd) group.
+    ``dyn``: device fp32 [3] = {lr scale, 1 - beta1^t, 1 - beta2^t} read by the kernel instead of ``step`` (graph replay)."""
     for (a, b), (lr, wd) in zip(ps.group_ranges, group_cfg):
         if b <= a:
             continue
         n = b - a
+        if dyn is not None:
+            check(_L().ralf_adamw_step_dyn(ps.flat_p[a:b].data_ptr(), ps.flat_g[a:b].data_ptr(), ps.flat_m[a:b].data_ptr(),
+                                           ps.flat_v[a:b].data_ptr(), n, norm.data_ptr(), max_norm, lr, betas[0], betas[1],
+                                           eps, wd, dyn.data_ptr(), _stream()), "ralf_adamw_step_dyn")
+            continue
         check(_L().ralf_adamw_step(ps.flat_p[a:b].data_ptr(), ps.flat_g[a:b].data_ptr(), ps.flat_m[a:b].data_ptr(),
                                    ps.flat_v[a:b].data_ptr(), n, norm.data_ptr(), max_norm, lr, betas[0], betas[1], eps, wd,
                                    step, _stream()), "ralf_adamw_step")

@@ -194,7 +194,8 @@ __device__ __forceinline__ void epi_row_to_global2(uint4* buf, const int lane, c
 template <int BN>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpi& ep, const uint32_t tacc, const int quad, const int lane,
                                                    const int m0, const int n0, const int M, const int N, uint4* stg,
-                                                   const int c_begin = 0, const int c_end = BN) {
+                                                   const int c_begin = 0, const int c_end = BN,
+                                                   const long long f32_off = 0) {
     const int r = m0 + quad * 32 + lane;
     const bool row_ok = r < M;
     const long long out_row =
@@ -265,7 +266,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpi& ep, const uint
           for (int j = 0; j < 8; ++j)
             mine[j] = make_uint4(__float_as_uint(x[4 * j]), __float_as_uint(x[4 * j + 1]), __float_as_uint(x[4 * j + 2]),
                                  __float_as_uint(x[4 * j + 3]));
-          epi_row_to_global<8>(stg, lane, mine, gaddr(ep.out_f32 + out_row * ep.out_ld + ep.out_col0 + nbase));
+          epi_row_to_global<8>(stg, lane, mine, gaddr(ep.out_f32 + f32_off + out_row * ep.out_ld + ep.out_col0 + nbase));
         }
         if (ep.out_kv24) {
           // fp32 rounded to 24 bits: bf16-sized top half (2 B) + one extra mantissa byte -- 3 bytes per value
@@ -327,7 +328,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpi& ep, const uint
                    __bfloat162float(ep.res_split[ep.res_plane + res_row * ep.res_ld + n]);
             }
             if (ep.post_relu) y = fmaxf(y, 0.f);
-            if (ep.out_f32) ep.out_f32[out_row * ep.out_ld + ep.out_col0 + n] = y;
+            if (ep.out_f32) ep.out_f32[f32_off + out_row * ep.out_ld + ep.out_col0 + n] = y;
             if (ep.out_split) {
               __nv_bfloat16 h, l;
               split_bf16(y, h, l);
@@ -343,7 +344,8 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpi& ep, const uint
 template <int BN, int NPASS>
 __global__ void __launch_bounds__(320, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const GemmEpi ep, const int M, const int N, const int K, const int STAGES, const ConvGeom cg) {
+                 const GemmEpi ep, const int M, const int N, const int K, const int STAGES, const ConvGeom cg,
+                 const int splits, const long long split_stride) {
   using Cfg = GemmCfg<BN, NPASS>;
   constexpr int P = Cfg::P;
   extern __shared__ uint8_t smem_raw[];
@@ -360,8 +362,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int lane = threadIdx.x & 31;
   const int tiles_n = (N + BN - 1) / BN;
   const int tiles_m = cg.enabled ? ((cg.B + cg.NB - 1) / cg.NB) * cg.hblocks : (M + 127) / 128;
-  const int num_tiles = tiles_m * tiles_n;
+  // split-K (weight-gradient GEMMs: tiny M x N, K = all rows of the batch): tile = (mn tile, k slice); slice s writes
+  // its raw fp32 partial to out_f32 + s * split_stride, a second kernel sums the slices (deterministic).
+  const int num_tiles = tiles_m * tiles_n * splits;
   const int nkb = (K + 63) / 64;
+  const int nkb_s = (nkb + splits - 1) / splits;
   const uint32_t a_tx = cg.enabled ? static_cast<uint32_t>(cg.Wo * cg.BH * cg.NB) * 128u : Cfg::A_BYTES;
   const uint32_t stage_tx = P * (a_tx + Cfg::B_BYTES);
   // first output row and row limit of M tile mt
@@ -413,9 +418,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // Prologue prefetch: the first ring of TMA loads needs nothing but the barriers this thread just initialised,
     // so it is issued BEFORE the TMEM allocation / block sync below (hides ~0.5 us on latency-bound decode GEMMs).
     {
-      const int mt = blockIdx.x / tiles_n, n0 = (blockIdx.x % tiles_n) * BN;
-      const int npre = nkb < STAGES ? nkb : STAGES;
-      for (int kb = 0; kb < npre; ++kb) load_stage(mt, n0, kb, kb);
+      const int mn = blockIdx.x / splits, kb0 = (blockIdx.x % splits) * nkb_s;
+      const int mt = mn / tiles_n, n0 = (mn % tiles_n) * BN;
+      const int nk = min(nkb, kb0 + nkb_s) - kb0;
+      const int npre = nk < STAGES ? nk : STAGES;
+      for (int kb = 0; kb < npre; ++kb) load_stage(mt, n0, kb0 + kb, kb);
     }
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -428,11 +435,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      const int npre = nkb < STAGES ? nkb : STAGES;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile / tiles_n, n0 = (tile % tiles_n) * BN;
-        for (int kb = 0; kb < nkb; ++kb) {
-          if (tile == static_cast<int>(blockIdx.x) && kb < npre) {  // already issued in the prologue
+        const int mn = tile / splits, kb0 = (tile % splits) * nkb_s;
+        const int mt = mn / tiles_n, n0 = (mn % tiles_n) * BN;
+        const int kb1 = min(nkb, kb0 + nkb_s);
+        const int npre = (kb1 - kb0) < STAGES ? (kb1 - kb0) : STAGES;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          if (tile == static_cast<int>(blockIdx.x) && kb - kb0 < npre) {  // already issued in the prologue
             if (++s == STAGES) { s = 0; ph ^= 1; }
             continue;
           }
@@ -453,7 +462,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tacc = tmem_base + buf * BN;
-        for (int kb = 0; kb < nkb; ++kb) {
+        const int kb0 = (tile % splits) * nkb_s, kb1 = min(nkb, kb0 + nkb_s);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t a_hi = base_u32 + s * Cfg::STAGE_BYTES;
@@ -466,11 +476,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (NPASS == 3) {
               const uint64_t da_lo = make_sw128_kmajor_desc(a_hi + Cfg::A_BYTES);
               const uint64_t db_lo = make_sw128_kmajor_desc(b_hi + Cfg::B_BYTES);
-              mma_bf16_ss(tacc, da_hi + koff, db_lo + koff, idesc, (kb | k) != 0);
+              mma_bf16_ss(tacc, da_hi + koff, db_lo + koff, idesc, ((kb - kb0) | k) != 0);
               mma_bf16_ss(tacc, da_lo + koff, db_hi + koff, idesc, 1);
               mma_bf16_ss(tacc, da_hi + koff, db_hi + koff, idesc, 1);
             } else {
-              mma_bf16_ss(tacc, da_hi + koff, db_hi + koff, idesc, (kb | k) != 0);
+              mma_bf16_ss(tacc, da_hi + koff, db_hi + koff, idesc, ((kb - kb0) | k) != 0);
             }
           }
           tc_commit(&empty_bar[s]);
@@ -490,13 +500,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (BN >= 64 || half == 0)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
     const int buf = it & 1;
-    const int n0 = (tile % tiles_n) * BN;
+    const int mn = tile / splits;
+    const int n0 = (mn % tiles_n) * BN;
     int m0, m_end;
-    tile_rows(tile / tiles_n, m0, m_end);
+    tile_rows(mn / tiles_n, m0, m_end);
     mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
     tc_fence_after();
     const uint32_t tacc = tmem_base + buf * BN;
-    gemm_epilogue_tile<BN>(ep, tacc, quad, lane, m0, n0, m_end, N, stage_all + (warp - 2) * 256, half * CH, half * CH + CH);
+    gemm_epilogue_tile<BN>(ep, tacc, quad, lane, m0, n0, m_end, N, stage_all + (warp - 2) * 256, half * CH, half * CH + CH,
+                           static_cast<long long>(tile % splits) * split_stride);
     tc_fence_before();
     mbar_arrive(&tempty_bar[buf]);
     }  // tile loop
@@ -718,7 +730,7 @@ int make_kmajor_tmap(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t
 
 template <int BN, int NPASS>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi& ep, int M, int N, int K,
-                       cudaStream_t st, const ConvGeom& cg) {
+                       cudaStream_t st, const ConvGeom& cg, int splits = 1, long long split_stride = 0) {
   using Cfg = GemmCfg<BN, NPASS>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -732,7 +744,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
     attr_set = true;
   }
   const long long tiles_m = cg.enabled ? static_cast<long long>((cg.B + cg.NB - 1) / cg.NB) * cg.hblocks : (M + 127) / 128;
-  const long long num_tiles = static_cast<long long>((N + BN - 1) / BN) * tiles_m;
+  const long long num_tiles = static_cast<long long>((N + BN - 1) / BN) * tiles_m * splits;
   const int sms = num_sms();
   const int nkb = (K + 63) / 64;
   // The smem ring may span tiles (RALF_GEMM_MIN_STAGES > k-blocks: the producer runs ahead into the next tiles).  Measured
@@ -740,7 +752,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
   // the limiter -- so the default keeps the small ring.
   static const int min_stages = getenv("RALF_GEMM_MIN_STAGES") ? atoi(getenv("RALF_GEMM_MIN_STAGES")) : 1;
   const bool multi_tile = num_tiles > static_cast<long long>(sms);
-  int stages = nkb < Cfg::MAX_STAGES ? nkb : Cfg::MAX_STAGES;
+  const int nkb_per = (nkb + splits - 1) / splits;
+  int stages = nkb_per < Cfg::MAX_STAGES ? nkb_per : Cfg::MAX_STAGES;
   if (multi_tile && stages < min_stages) stages = min_stages < Cfg::MAX_STAGES ? min_stages : Cfg::MAX_STAGES;
   // Short-K GEMMs are bound by their epilogue's memory traffic, not by the MMAs: their small smem ring lets several
   // persistent CTAs share an SM (limited by shared memory, 512 TMEM columns and an env override for A/B runs), which
@@ -759,7 +772,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
   if (occ > occ_cap) occ = occ_cap;
   const long long max_ctas = static_cast<long long>(sms) * occ;
   dim3 grid(static_cast<unsigned>(num_tiles < max_ctas ? num_tiles : max_ctas));
-  gemm_bf16_kernel<BN, NPASS><<<grid, 320, Cfg::smem_bytes(stages), st>>>(ta, tb, ep, M, N, K, stages, cg);
+  gemm_bf16_kernel<BN, NPASS><<<grid, 320, Cfg::smem_bytes(stages), st>>>(ta, tb, ep, M, N, K, stages, cg, splits,
+                                                                          split_stride);
   return set_cuda_error(cudaGetLastError());
 }
 
@@ -785,6 +799,39 @@ static int make_conv_tmap(CUtensorMap* out, const void* ptr, uint64_t C_, uint64
     return RALF_ERR_DRIVER;
   }
   return 0;
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int S, long long stride, int M, int N,
+                                     float* __restrict__ out, int out_ld) {
+  const long long total = static_cast<long long>(M) * N;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < S; ++s) acc += ws[s * stride + i];  // fixed order: deterministic
+    out[(i / N) * out_ld + (i % N)] = acc;
+  }
+}
+
+// Split-K plan for a plain fp32-output GEMM whose M x N tiles cannot fill the GPU (weight gradients): number of k
+// slices (1 = no split) such that tiles * slices ~ #SMs and every slice keeps >= 8 k-blocks.
+static int splitk_plan(int M, int N, int K, int bn) {
+  const long long tiles = static_cast<long long>((M + 127) / 128) * ((N + bn - 1) / bn);
+  const int nkb = (K + 63) / 64;
+  const int sms = num_sms();
+  if (tiles * 2 > sms || nkb < 32) return 1;
+  int s = static_cast<int>(sms / tiles);
+  if (s > nkb / 8) s = nkb / 8;
+  if (s > 64) s = 64;
+  if (s < 2) return 1;
+  const int per = (nkb + s - 1) / s;
+  return (nkb + per - 1) / per;  // no empty slice
+}
+
+extern "C" size_t ralf_gemm_splitk_workspace_bytes(int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  const int bn = N >= 64 ? 64 : 32;
+  const int s = splitk_plan(M, N, K, bn);
+  return s > 1 ? static_cast<size_t>(s) * M * N * sizeof(float) : 0;
 }
 
 static int gemm_dispatch(const RalfGemmArgs* a, const CUtensorMap& ta, int bn, const ConvGeom& cg, void* stream) {
@@ -819,6 +866,30 @@ static int gemm_dispatch(const RalfGemmArgs* a, const CUtensorMap& ta, int bn, c
   if (a->out_kv24 && (a->N != 512 || !ep.vec_ok || !al16(a->out_kv24))) return RALF_ERR_SHAPE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int np = a->npass;
+  if (a->splitk_ws && !cg.enabled && a->out_f32 && !a->out_split && !a->bias && !a->act && !a->res && !a->res_split &&
+      a->rows_per_group <= 0 && np == 3) {
+    const int sbn = a->N >= 64 ? 64 : 32;
+    const int S = splitk_plan(a->M, a->N, a->K, sbn);
+    if (S > 1 && a->splitk_ws_bytes >= static_cast<size_t>(S) * a->M * a->N * sizeof(float)) {
+      CUtensorMap tbs;
+      rc = make_kmajor_tmap(&tbs, a->W, 2, a->K, a->N, planes, a->ldw, a->w_plane, sbn);
+      if (rc) return rc;
+      GemmEpi es = ep;
+      es.out_f32 = reinterpret_cast<float*>(a->splitk_ws);
+      es.out_ld = a->N;
+      es.out_col0 = 0;
+      es.vec_ok = (a->N % 8 == 0) && al16(a->splitk_ws);
+      const long long stride = static_cast<long long>(a->M) * a->N;
+      rc = sbn == 64 ? launch_gemm<64, 3>(ta, tbs, es, a->M, a->N, a->K, st, cg, S, stride)
+                     : launch_gemm<32, 3>(ta, tbs, es, a->M, a->N, a->K, st, cg, S, stride);
+      if (rc) return rc;
+      const long long total = stride;
+      const int blocks = static_cast<int>((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+      splitk_reduce_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(a->splitk_ws), S, stride, a->M, a->N,
+                                                   a->out_f32 + a->out_col0, a->out_ld);
+      return set_cuda_error(cudaGetLastError());
+    }
+  }
 #define RALF_GEMM_CASE(BN_, NP_) \
   if (bn == BN_ && np == NP_) return launch_gemm<BN_, NP_>(ta, tb, ep, a->M, a->N, a->K, st, cg);
   RALF_GEMM_CASE(32, 3)

@@ -253,61 +253,74 @@ attn_bwd_dkv_kernel(const float* __restrict__ q, int ldq, const float* __restric
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = j < Tk;
   const bool dead = active && mask && mask[static_cast<long long>(b) * Tk + j];
-  float kr[DH], acc[DH];
-  const float* vrow = v + (static_cast<long long>(b) * Tk + (active ? j : 0)) * ldk + h * DH;
+  // one sweep over the queries: dV and dK accumulate together, K and V rows of this thread's key live in registers
+  float kr[DH], vr[DH], accv[DH], acck[DH];
   if (active) {
     const float* kp = k + (static_cast<long long>(b) * Tk + j) * ldk + h * DH;
+    const float* vp = v + (static_cast<long long>(b) * Tk + j) * ldk + h * DH;
 #pragma unroll
-    for (int i = 0; i < DH; ++i) kr[i] = kp[i] * scale;
+    for (int i = 0; i < DH; i += 4) {
+      const float4 fk = *reinterpret_cast<const float4*>(kp + i);
+      const float4 fv = *reinterpret_cast<const float4*>(vp + i);
+      kr[i] = fk.x * scale; kr[i + 1] = fk.y * scale; kr[i + 2] = fk.z * scale; kr[i + 3] = fk.w * scale;
+      vr[i] = fv.x; vr[i + 1] = fv.y; vr[i + 2] = fv.z; vr[i + 3] = fv.w;
+    }
   }
-  for (int pass = 0; pass < 2; ++pass) {  // pass 0: dV, pass 1: dK
 #pragma unroll
-    for (int i = 0; i < DH; ++i) acc[i] = 0.f;
-    const int i_begin = causal ? (blockIdx.x * static_cast<int>(blockDim.x)) / QT * QT : 0;  // queries t >= j only
-    for (int i0 = i_begin; i0 < Tq; i0 += QT) {
-      __syncthreads();
-      const int nq = min(QT, Tq - i0);
-      for (int e = threadIdx.x; e < QT * (DH / 4); e += blockDim.x) {
-        const int r = e / (DH / 4), c = (e % (DH / 4)) * 4;
-        float4 fq = make_float4(0.f, 0.f, 0.f, 0.f), fd = fq;
-        if (r < nq) {
-          const long long row = static_cast<long long>(b) * Tq + i0 + r;
-          fq = *reinterpret_cast<const float4*>(q + row * ldq + h * DH + c);
-          fd = *reinterpret_cast<const float4*>(dO + row * ldo + h * DH + c);
-        }
-        *reinterpret_cast<float4*>(&qs[r][c]) = fq;
-        *reinterpret_cast<float4*>(&ds_[r][c]) = fd;
+  for (int i = 0; i < DH; ++i) accv[i] = acck[i] = 0.f;
+  const int i_begin = causal ? (blockIdx.x * static_cast<int>(blockDim.x)) / QT * QT : 0;  // queries t >= j only
+  for (int i0 = i_begin; i0 < Tq; i0 += QT) {
+    __syncthreads();
+    const int nq = min(QT, Tq - i0);
+    for (int e = threadIdx.x; e < QT * (DH / 4); e += blockDim.x) {
+      const int r = e / (DH / 4), c = (e % (DH / 4)) * 4;
+      float4 fq = make_float4(0.f, 0.f, 0.f, 0.f), fd = fq;
+      if (r < nq) {
+        const long long row = static_cast<long long>(b) * Tq + i0 + r;
+        fq = *reinterpret_cast<const float4*>(q + row * ldq + h * DH + c);
+        fd = *reinterpret_cast<const float4*>(dO + row * ldo + h * DH + c);
       }
-      for (int e = threadIdx.x; e < QT; e += blockDim.x) {
-        const long long idx = (static_cast<long long>(b) * H + h) * Tq + i0 + e;
-        ls[e] = (e < nq) ? lse[idx] : 0.f;
-        dls[e] = (e < nq) ? delta[idx] : 0.f;
+      *reinterpret_cast<float4*>(&qs[r][c]) = fq;
+      *reinterpret_cast<float4*>(&ds_[r][c]) = fd;
+    }
+    for (int e = threadIdx.x; e < QT; e += blockDim.x) {
+      const long long idx = (static_cast<long long>(b) * H + h) * Tq + i0 + e;
+      ls[e] = (e < nq) ? lse[idx] : 0.f;
+      dls[e] = (e < nq) ? delta[idx] : 0.f;
+    }
+    __syncthreads();
+    if (!active || dead) continue;
+    for (int r = 0; r < nq; ++r) {
+      if (causal && j > (i0 + r)) continue;
+      float s = 0.f, dpv = 0.f;
+#pragma unroll
+      for (int i = 0; i < DH; i += 4) {
+        const float4 fq = *reinterpret_cast<const float4*>(&qs[r][i]);
+        const float4 fd = *reinterpret_cast<const float4*>(&ds_[r][i]);
+        s = fmaf(fq.x, kr[i], s); s = fmaf(fq.y, kr[i + 1], s); s = fmaf(fq.z, kr[i + 2], s); s = fmaf(fq.w, kr[i + 3], s);
+        dpv = fmaf(fd.x, vr[i], dpv); dpv = fmaf(fd.y, vr[i + 1], dpv);
+        dpv = fmaf(fd.z, vr[i + 2], dpv); dpv = fmaf(fd.w, vr[i + 3], dpv);
       }
-      __syncthreads();
-      if (!active || dead) continue;
-      for (int r = 0; r < nq; ++r) {
-        if (causal && j > (i0 + r)) continue;
-        float s = 0.f;
+      const float p = __expf(s - ls[r]);
+      const float dsv = p * (dpv - dls[r]) * scale;
 #pragma unroll
-        for (int i = 0; i < DH; ++i) s = fmaf(qs[r][i], kr[i], s);
-        const float p = __expf(s - ls[r]);
-        if (pass == 0) {
-#pragma unroll
-          for (int i = 0; i < DH; ++i) acc[i] = fmaf(p, ds_[r][i], acc[i]);
-        } else {
-          float dpv = 0.f;
-#pragma unroll
-          for (int i = 0; i < DH; ++i) dpv = fmaf(ds_[r][i], vrow[i], dpv);
-          const float dsv = p * (dpv - dls[r]) * scale;
-#pragma unroll
-          for (int i = 0; i < DH; ++i) acc[i] = fmaf(dsv, qs[r][i], acc[i]);
-        }
+      for (int i = 0; i < DH; i += 4) {
+        const float4 fq = *reinterpret_cast<const float4*>(&qs[r][i]);
+        const float4 fd = *reinterpret_cast<const float4*>(&ds_[r][i]);
+        accv[i] = fmaf(p, fd.x, accv[i]); accv[i + 1] = fmaf(p, fd.y, accv[i + 1]);
+        accv[i + 2] = fmaf(p, fd.z, accv[i + 2]); accv[i + 3] = fmaf(p, fd.w, accv[i + 3]);
+        acck[i] = fmaf(dsv, fq.x, acck[i]); acck[i + 1] = fmaf(dsv, fq.y, acck[i + 1]);
+        acck[i + 2] = fmaf(dsv, fq.z, acck[i + 2]); acck[i + 3] = fmaf(dsv, fq.w, acck[i + 3]);
       }
     }
-    if (active) {
-      float* out = (pass == 0 ? dv : dk) + (static_cast<long long>(b) * Tk + j) * lddk + h * DH;
+  }
+  if (active) {
+    float* ov = dv + (static_cast<long long>(b) * Tk + j) * lddk + h * DH;
+    float* ok = dk + (static_cast<long long>(b) * Tk + j) * lddk + h * DH;
 #pragma unroll
-      for (int i = 0; i < DH; ++i) out[i] = acc[i];
+    for (int i = 0; i < DH; i += 4) {
+      *reinterpret_cast<float4*>(ov + i) = make_float4(accv[i], accv[i + 1], accv[i + 2], accv[i + 3]);
+      *reinterpret_cast<float4*>(ok + i) = make_float4(acck[i], acck[i + 1], acck[i + 2], acck[i + 3]);
     }
   }
 }
@@ -385,7 +398,13 @@ __global__ void sqnorm_final_kernel(const float* __restrict__ part, int n, float
 // (torch.nn.utils.clip_grad_norm_); decoupled weight decay then Adam with bias correction.
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, long long n, const float* __restrict__ norm, float max_norm,
-                             float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2) {
+                             float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2,
+                             const float* __restrict__ dyn) {
+  if (dyn) {  // per-step scalars from device memory (CUDA-graph replay): lr scale, bias corrections
+    lr *= dyn[0];
+    bc1 = dyn[1];
+    bc2 = dyn[2];
+  }
   const float nrm = norm ? norm[0] : 0.f;
   const float clip = (norm && max_norm > 0.f) ? fminf(1.f, max_norm / (nrm + 1e-6f)) : 1.f;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
@@ -540,7 +559,19 @@ extern "C" int ralf_adamw_step(float* params, const float* grads, float* exp_avg
   const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
   const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
   adamw_kernel<<<t_grid_for(n, 256), 256, 0, ST(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, grad_norm, max_norm, lr,
-                                                         beta1, beta2, eps, weight_decay, bc1, bc2);
+                                                         beta1, beta2, eps, weight_decay, bc1, bc2, nullptr);
+  return set_cuda_error(cudaGetLastError());
+}
+
+// Same step with the per-step scalars read from device memory, so a captured CUDA graph of the training step can be
+// replayed: dyn = {lr scale (scheduler), 1 - beta1^t, 1 - beta2^t}, written by the host before each replay.
+extern "C" int ralf_adamw_step_dyn(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                                   const float* grad_norm, float max_norm, float lr, float beta1, float beta2, float eps,
+                                   float weight_decay, const float* dyn, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !dyn) return RALF_ERR_NULL;
+  if (n <= 0) return RALF_ERR_SHAPE;
+  adamw_kernel<<<t_grid_for(n, 256), 256, 0, ST(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, grad_norm, max_norm, lr,
+                                                         beta1, beta2, eps, weight_decay, 1.f, 1.f, dyn);
   return set_cuda_error(cudaGetLastError());
 }
 
@@ -552,7 +583,7 @@ extern "C" int ralf_attention_bwd(const float* q, int ldq, const float* k, const
   float* lse = lse_ws;
   if (!q || !k || !v || !o_split || !dO || !lse || !delta_ws || !dq || !dk || !dv) return RALF_ERR_NULL;
   if (B <= 0 || H <= 0 || Tq <= 0 || Tk <= 0 || (head_dim != 32 && head_dim != 64)) return RALF_ERR_SHAPE;
-  if ((ldq & 3) || (ldk & 3) || (ldo & 3)) return RALF_ERR_ALIGN;
+  if ((ldq & 3) || (ldk & 3) || (ldo & 3) || (lddk & 3) || (lddq & 3)) return RALF_ERR_ALIGN;
   const int tq = Tq >= 128 ? 128 : ((Tq + 31) / 32) * 32;
   const int tk = Tk >= 128 ? 128 : ((Tk + 31) / 32) * 32;
   dim3 g1((Tq + tq - 1) / tq, H, B), g2((Tk + tk - 1) / tk, H, B);

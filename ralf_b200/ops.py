@@ -74,6 +74,7 @@ def gemm(
     conv: Optional[tuple] = None,
     stem: Optional[tuple] = None,
     out_kv24: Optional[torch.Tensor] = None,
+    splitk: bool = False,
 ) -> tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """D = A . W^T with the fused epilogue of ``ralf_gemm`` (include/ralf_b200.h).
 
@@ -125,6 +126,13 @@ def gemm(
     g.out_split_lo = 1 if npass == 3 else 0
     g.out_ld, g.out_col0 = out_ld, out_col0
     g.rows_per_group, g.group_stride, g.group_offset = rows_per_group, group_stride, group_offset
+    if splitk:  # weight-gradient shape class: few output tiles, K = all rows -> k slices + deterministic sum
+        nbytes = _lib.lib().ralf_gemm_splitk_workspace_bytes(M, N, K)
+        if nbytes:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=a.device)
+            g.splitk_ws, g.splitk_ws_bytes = ws.data_ptr(), nbytes
+            global _LAUNCHES
+            _LAUNCHES += 1
     if out_kv24 is not None:  # uint8 [M, 1536] rows of the 24-bit K/V cache (N = 512)
         assert out_kv24.dtype == torch.uint8 and out_kv24.shape[-1] == 1536 and out_kv24.is_contiguous() and N == 512
         g.out_kv24 = out_kv24.data_ptr()

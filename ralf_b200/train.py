@@ -66,6 +66,9 @@ class TrainEngine:
 
             self.trunk = Trunk(self.ps, model, self.dev)
         self.pe = _sine_pe_1d(5000, D).to(self.dev)
+        self._dyn_host = torch.ones(3, dtype=torch.float32).pin_memory()
+        self._dyn = torch.ones(3, dtype=torch.float32, device=self.dev)
+        self._graph = None
         self.refresh_operands()
 
     def refresh_operands(self) -> None:
@@ -268,8 +271,16 @@ class TrainEngine:
         return cls
 
     # ------------------------------------------------------------------------------------------
-    def train_step(self, inputs: dict, targets: dict, lr: Optional[float] = None) -> torch.Tensor:
-        """One optimisation step (train.py:440-454).  Returns the loss (device scalar; no host sync)."""
+    def _set_step_scalars(self, lr: Optional[float]) -> None:
+        """Per-step scalars of the optimiser go through device memory (a captured step must not bake them in)."""
+        self.step_count += 1
+        t = self.step_count
+        self._dyn_host[0] = 1.0 if lr is None else lr / self.lr  # scheduler (MultiStepLR) scales every group alike
+        self._dyn_host[1] = 1.0 - 0.9 ** t
+        self._dyn_host[2] = 1.0 - 0.999 ** t
+        self._dyn.copy_(self._dyn_host, non_blocking=True)
+
+    def _step_body(self, inputs: dict, targets: dict) -> torch.Tensor:
         ps = self.ps
         ps.flat_g.zero_()
         loss, tape, _ = self.forward_loss(inputs, targets)
@@ -280,10 +291,52 @@ class TrainEngine:
             dist.all_reduce(ps.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
             ps.flat_g.mul_(1.0 / self.world)
         norm = ag.grad_norm(ps.flat_g)
-        self.step_count += 1
-        scale = 1.0 if lr is None else lr / self.lr  # scheduler (MultiStepLR) scales every group alike
-        cfg = [(g_lr * scale, wd) for (g_lr, wd) in self.group_cfg]
-        ag.adamw_step(ps, cfg, self.step_count, self.max_norm, norm)
+        ag.adamw_step(ps, self.group_cfg, 0, self.max_norm, norm, dyn=self._dyn)
         self.refresh_operands()
         self.last_grad_norm = norm
         return loss
+
+    def train_step(self, inputs: dict, targets: dict, lr: Optional[float] = None) -> torch.Tensor:
+        """One optimisation step (train.py:440-454), eager launches.  Returns the loss (device scalar; no host sync)."""
+        self._set_step_scalars(lr)
+        return self._step_body(inputs, targets)
+
+    # ------------------------------------------------------------------------------------------
+    # CUDA-graph replay of the whole step (fixed batch shape): ~1.9 k kernel launches become one graph launch
+    # ------------------------------------------------------------------------------------------
+    def capture(self, inputs: dict, targets: dict) -> None:
+        """Capture forward + backward + all-reduce + clip + AdamW for this batch SHAPE.  The example batch is copied into
+        static device buffers; `train_step_graph` refills them and replays."""
+        dev = self.dev
+
+        def static(v):
+            if torch.is_tensor(v):
+                return v.to(dev).clone()
+            return {k: static(x) for k, x in v.items()}
+
+        self._g_in, self._g_tg = static(inputs), static(targets)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up (a real step): kernel attributes, tensor-map cache, allocator
+            self.train_step(self._g_in, self._g_tg)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._g_loss = self._step_body(self._g_in, self._g_tg)
+
+    def train_step_graph(self, inputs: dict, targets: dict, lr: Optional[float] = None) -> torch.Tensor:
+        assert getattr(self, "_graph", None) is not None, "call capture(inputs, targets) first"
+
+        def fill(dst, src):
+            if torch.is_tensor(dst):
+                dst.copy_(src, non_blocking=True)
+            else:
+                for k in dst:
+                    fill(dst[k], src[k])
+
+        fill(self._g_in, inputs)
+        fill(self._g_tg, targets)
+        self._set_step_scalars(lr)
+        self._graph.replay()
+        return self._g_loss

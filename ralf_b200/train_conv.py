@@ -121,10 +121,10 @@ class Trunk:
         dzT = ag.transpose_to_split(x_f32=dz)
         colT = ag.transpose_to_split(x_split=col)
         if k == 1:
-            ops.gemm(dzT, colT, out_f32=ps.weight_view(conv, grad=True))
+            ops.gemm(dzT, colT, out_f32=ps.weight_view(conv, grad=True), splitk=True)
         else:
             N, Kp = self.cw[pname].shape[1], self.cw[pname].shape[2]
-            dwg, _ = ops.gemm(dzT, colT)                                    # [N, Kcol] in (tap, cin) order
+            dwg, _ = ops.gemm(dzT, colT, splitk=True)                                # [N, Kcol] in (tap, cin) order
             _, Nn, Cc, T = next(kc for kc in self.kconvs if kc[0] == pname)
             check(_L().ralf_conv_grad_from_gemm(dwg.data_ptr(), Nn, Cc, T, dwg.stride(0), ps.g(pname).data_ptr(), _stream()),
                   "ralf_conv_grad_from_gemm")

@@ -144,3 +144,21 @@ def test_stem_s2d_gemm_matches_conv2d_fp64(cuda_device, B, H, W):
     p, Hp, Wp = ops.maxpool3x3s2(ys, B, Ho, Wo, 64)
     pref = torch.nn.functional.max_pool2d(ops.unsplit(ys).view(B, Ho, Wo, 64).permute(0, 3, 1, 2), 3, 2, 1)
     assert torch.equal(ops.unsplit(p).view(B, Hp, Wp, 64).permute(0, 3, 1, 2), pref)
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 64, 131072), (256, 64, 32768), (64, 576, 40000), (519, 256, 3200), (128, 40, 9000)])
+def test_gemm_splitk_matches_fp64(cuda_device, M, N, K):
+    """Weight-gradient shape class (tiny M x N, K = all rows): split-K slices + deterministic reduction."""
+    from ralf_b200 import ops
+
+    g = torch.Generator(device=cuda_device).manual_seed(M + N)
+    a = ops.split_bf16(torch.randn(M, K, device=cuda_device, generator=g))
+    w = ops.split_bf16(torch.randn(N, K, device=cuda_device, generator=g))
+    out = torch.full((M, N + 8), 7.0, device=cuda_device)
+    ops.gemm(a, w, out_f32=out[:, :N], splitk=True)
+    ref = ops.unsplit(a).double() @ ops.unsplit(w).double().t()
+    assert (out[:, :N].double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    assert torch.all(out[:, N:] == 7.0)
+    out2 = torch.empty_like(out)
+    ops.gemm(a, w, out_f32=out2[:, :N], splitk=True)
+    assert torch.equal(out[:, :N], out2[:, :N])  # deterministic
