@@ -205,6 +205,16 @@ int ralf_fid_embed_packed(const float* packed, int nseq, int E, int D, const flo
 int ralf_argmax_next(const float* logits, int ldl, int B, int V, const unsigned char* allowed, long long* seq,
                      int seq_ld, int pos, unsigned char* pad_mask, int mask_ld, long long pad_id,
                      const float* emb, int D, float scale, const float* pe, float* x_next, void* stream);
+/* Constrained / stochastic step tail: replaces the per-sample python loops of
+ * DECODE_SPACE_RESTRICTION (layoutformerpp/decoding_space_restriction.py:5-106) and helpers/sampling.py:18-68.
+ * forced: int32 [B, forced_ld] or NULL; forced[b, step] >= 0 -> emit that token.  mode: 0 greedy, 1 random, 2 top_k,
+ * 3 top_p, 4 gumbel.  uniform: fp32 [B] in [0,1) (modes 1-4), noise: fp32 [B, noise_ld] uniforms (mode 4).  The draw is
+ * the inverse CDF over the kept tokens in (logit desc, index asc) order.  V <= 1024.  Tail as ralf_argmax_next. */
+int ralf_sample_next(const float* logits, int ldl, int B, int V, const unsigned char* allowed, const int* forced,
+                     int forced_ld, int step, int mode, float temperature, int top_k, float top_p,
+                     const float* uniform, const float* noise, int noise_ld, long long* seq, int seq_ld, int pos,
+                     unsigned char* pad_mask, int mask_ld, long long pad_id, const float* emb, int D, float scale,
+                     const float* pe, float* x_next, void* stream);
 /* nn.CrossEntropyLoss(label_smoothing=eps, ignore_index) with mean reduction over logits [M, V]
  * (retrieval_augmented_autoreg.py:140-142,213-214); workspace = 2*M floats; out_loss = 1 float. */
 int ralf_ce_label_smooth(const float* logits, int ldl, const long long* targets, int M, int V, float eps,

@@ -260,3 +260,101 @@ def greedy_sample(sd, memory, token_mask, bos_id, pad_id, max_token_length, retu
             step_logits.append(logits)
         inp = torch.cat([inp, torch.argmax(logits, dim=1, keepdim=True)], dim=1)
     return (inp[:, 1:], torch.stack(step_logits, 1)) if return_logits else inp[:, 1:]
+
+
+# ---------------------------------------------------------------------------------------------------
+# constrained tasks: decoding-space restriction, literal per-sample restatement
+# ---------------------------------------------------------------------------------------------------
+def restrict_logits(cond_type, sampling_idx, cond_seq, logits, pad_id, eos_id):
+    """DECODE_SPACE_RESTRICTION[cond_type] (layoutformerpp/decoding_space_restriction.py:5-106): c / cwh keep only the
+    given token (or <eos> from the first <pad> on); refinement does the same at label slots only; others: identity."""
+    if cond_type in (None, "none", "uncond", "partial"):
+        return logits
+    if cond_type == "refinement" and (sampling_idx - 1) % 5 != 0:
+        return logits
+    for b in range(cond_seq.shape[0]):
+        row = cond_seq[b]
+        pads = (row == pad_id).nonzero()
+        first_pad = int(pads[0]) if len(pads) else float("inf")
+        given = int(row[sampling_idx])
+        if sampling_idx < first_pad:
+            if given == pad_id or given == -1:
+                continue
+            keep = given
+        else:
+            keep = eos_id
+        v = logits[b, keep].clone()
+        logits[b] = float("-inf")
+        logits[b, keep] = v
+    return logits
+
+
+def constrained_greedy_sample(sd, memory, token_mask, cond_type, cond_seq, bos_id, pad_id, eos_id, max_token_length):
+    """BaseRetrievalAugmentedAutoreg.sample for the constrained tasks (retrieval_augmented_autoreg.py:244-300), greedy,
+    no KV cache.  ``cond_seq`` is cond.seq AFTER the task preprocessor ran (it rewrites <eos> to <pad> in place)."""
+    B = memory.shape[0]
+    inp = torch.full((B, 1), bos_id, dtype=torch.long)
+    start = 0
+    if cond_type == "partial":
+        inp = torch.cat([inp, cond_seq[:, 1:6]], dim=1)
+        start = 5
+    for i in range(start, max_token_length):
+        logits = decoder_logits(sd, inp, memory, inp == pad_id)[:, i].clone()
+        logits[:, ~token_mask[i]] = float("-inf")
+        logits = restrict_logits(cond_type, i + 1, cond_seq, logits, pad_id, eos_id)
+        inp = torch.cat([inp, torch.argmax(logits, dim=1, keepdim=True)], dim=1)
+    return inp[:, 1:]
+
+
+# ---------------------------------------------------------------------------------------------------
+# stochastic sampling (helpers/sampling.py:10-68)
+# ---------------------------------------------------------------------------------------------------
+def filtered_logits(logits, name, temperature=1.0, top_k=5, top_p=0.9):
+    """logits / temperature with helpers/sampling.py's filter applied (-inf = dropped), name in random / top_k / top_p.
+    top_k keeps every logit >= the k-th largest (ties included, :10-15); top_p sorts descending, drops every entry whose
+    inclusive cumulative probability exceeds top_p except the first (:35-50)."""
+    x = logits / temperature
+    if name == "top_k":
+        kth = torch.topk(x, top_k, dim=1).values[:, -1:]
+        x = torch.where(x < kth, torch.full_like(x, float("-inf")), x)
+    elif name == "top_p":
+        s, idx = torch.sort(x, descending=True, dim=1)
+        cum = torch.cumsum(torch.softmax(s, dim=1), dim=1)
+        drop = cum > top_p
+        drop[:, 0] = False
+        s = torch.where(drop, torch.full_like(s, float("-inf")), s)
+        x = torch.empty_like(s).scatter_(1, idx, s)
+    elif name != "random":
+        raise NotImplementedError(name)
+    return x
+
+
+def filtered_probs(logits, name, temperature=1.0, top_k=5, top_p=0.9):
+    """The probabilities helpers/sampling.py hands to torch.multinomial (:60)."""
+    return torch.softmax(filtered_logits(logits, name, temperature, top_k, top_p), dim=1)
+
+
+def inverse_cdf_draw(x, u):
+    """The draw ralf_b200 defines in place of torch.multinomial's generator-specific one (same distribution): walk the
+    kept tokens of the filtered logits ``x`` in (logit desc, index asc) order and return the first whose cumulative
+    softmax mass exceeds u * (kept mass).  float64 here.  Also returns, per row, the set of tokens that are acceptable
+    when fp32 rounding moves the boundary: every token whose cumulative interval comes within 1e-5 of the target."""
+    x = x.double()
+    picks, accept = [], []
+    for b in range(x.shape[0]):
+        order = sorted((c for c in range(x.shape[1]) if x[b, c] > float("-inf")), key=lambda c: (-float(x[b, c]), c))
+        m = float(x[b, order[0]])
+        p = [math.exp(float(x[b, c]) - m) for c in order]
+        tot = sum(p)
+        target = float(u[b]) * tot
+        acc, pick, ok = 0.0, order[-1], set()
+        found = False
+        for c, pc in zip(order, p):
+            lo, acc = acc, acc + pc
+            if lo - 1e-5 * tot <= target <= acc + 1e-5 * tot:
+                ok.add(c)
+            if not found and acc > target:
+                pick, found = c, True
+        picks.append(pick)
+        accept.append(ok | {pick})
+    return torch.tensor(picks), accept

@@ -86,6 +86,8 @@ def lib() -> C.CDLL:
         L.ralf_fid_embed.argtypes = [vp, vp, vp, vp, vp, i, i, vp, vp, vp, vp, ll, vp]
         L.ralf_argmax_next.argtypes = [vp, i, i, i, vp, vp, i, i, vp, i, ll, vp, i, f, vp, vp, vp]
         L.ralf_kv_append.argtypes = [vp, i, i, vp, vp, i, i, vp]
+        L.ralf_sample_next.argtypes = [vp, i, i, i, vp, vp, i, i, i, f, i, f, vp, vp, i, vp, i, i, vp, i, ll, vp, i, f, vp,
+                                       vp, vp]
         L.ralf_gather_layouts.argtypes = [vp, vp, i, i, ll, ll, vp, vp]
         L.ralf_fid_embed_packed.argtypes = [vp, i, i, i, vp, vp, vp, i, vp, ll, vp, vp]
         L.ralf_transpose_to_split.argtypes = [vp, vp, ll, ll, i, i, vp, ll, ll, vp]

@@ -36,10 +36,23 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     deps.append(os.path.join(ROOT, "include", "ralf_b200.h"))
     if force or _stale(LIB, deps):
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-        cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, *srcs]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
-        subprocess.run(cmd, check=True)
+        hdrs = [d for d in deps if not d.endswith(".cu")]
+        objdir = os.path.join(HERE, "build")
+        os.makedirs(objdir, exist_ok=True)
+        flags = [f for f in NVCC_FLAGS if f != "-shared"]
+        procs, objs = [], []
+        for src in srcs:  # one nvcc per translation unit, in parallel; only stale objects are recompiled
+            obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+            objs.append(obj)
+            if force or _stale(obj, [src] + hdrs):
+                cmd = [nvcc, *flags, "-c", "-o", obj, src]
+                if verbose:
+                    cmd.insert(1, "-Xptxas=-v")
+                procs.append((cmd, subprocess.Popen(cmd)))
+        for cmd, pr in procs:
+            if pr.wait() != 0:
+                raise subprocess.CalledProcessError(pr.returncode, cmd)
+        subprocess.run([nvcc, "-shared", "-o", LIB, *objs], check=True)
     return LIB
 
 

@@ -813,6 +813,134 @@ __global__ void argmax_next_kernel(const float* __restrict__ logits, int ldl, in
   }
 }
 
+// Stochastic / constrained step tail.  One CTA per canvas.
+//   forced[b, step] >= 0  -> that token (DECODE_SPACE_RESTRICTION for c / cwh / refinement and the teacher-forced prefix of
+//                            `partial`, precomputed on the host as one int32 table: decoding_space_restriction.py:5-106)
+//   mode 0                -> greedy (first maximum of the masked logits, helpers/sampling.py:24-25)
+//   mode 1 random, 2 top_k, 3 top_p, 4 gumbel (helpers/sampling.py:28-58): x = logits / temperature (+ gumbel noise),
+//     sorted descending by (x, then lower index); top_k keeps every x >= the k-th largest; top_p drops every rank r > 0
+//     whose inclusive cumulative softmax mass exceeds top_p; the token is the first rank whose cumulative mass among the
+//     kept ranks exceeds uniform[b] * (kept mass)  (an inverse-CDF draw: same distribution as torch.multinomial).
+// Then, like argmax_next_kernel: seq[b, pos] = tok; pad_mask; x_next = emb[tok] * scale + pe[pos].
+constexpr int kSampleSlots = 1024;
+__global__ void __launch_bounds__(256) sample_next_kernel(
+    const float* __restrict__ logits, int ldl, int V, const unsigned char* __restrict__ allowed,
+    const int* __restrict__ forced, int forced_ld, int step, int mode, float temperature, int top_k, float top_p,
+    const float* __restrict__ uniform, const float* __restrict__ noise, int noise_ld, long long* __restrict__ seq,
+    int seq_ld, int pos, unsigned char* __restrict__ pad_mask, int mask_ld, long long pad_id,
+    const float* __restrict__ emb, int D, float scale, const float* __restrict__ pe, float* __restrict__ x_next) {
+  __shared__ float val[kSampleSlots];
+  __shared__ int idx[kSampleSlots];
+  __shared__ int win;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int f = forced ? forced[static_cast<long long>(b) * forced_ld + step] : -1;
+  if (f >= 0) {
+    if (tid == 0) win = f;
+  } else {
+    for (int c = tid; c < kSampleSlots; c += blockDim.x) {
+      float x = -INFINITY;
+      if (c < V && allowed[c]) {
+        x = logits[static_cast<long long>(b) * ldl + c];
+        if (mode != 0) {
+          x = x / temperature;
+          if (mode == 4) {
+            const float u = noise[static_cast<long long>(b) * noise_ld + c];
+            x += -logf(-logf(u + 1e-30f) + 1e-30f);
+          }
+        }
+      }
+      val[c] = x;
+      idx[c] = c;
+    }
+    __syncthreads();
+    if (mode == 0) {  // greedy: block arg-max, first maximum wins
+      for (int s = kSampleSlots / 2; s >= 1; s >>= 1) {
+        for (int i = tid; i < s; i += blockDim.x) {
+          const float a = val[i], o = val[i + s];
+          const int ia = idx[i], io = idx[i + s];
+          if (o > a || (o == a && io < ia)) { val[i] = o; idx[i] = io; }
+        }
+        __syncthreads();
+      }
+      if (tid == 0) win = idx[0];
+    } else {
+      // bitonic sort, descending by (value, -index)
+      for (int k = 2; k <= kSampleSlots; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = tid; i < kSampleSlots; i += blockDim.x) {
+            const int l = i ^ j;
+            if (l > i) {
+              const float a = val[i], o = val[l];
+              const int ia = idx[i], io = idx[l];
+              const bool i_first = (a > o) || (a == o && ia < io);  // i already ranks before l in descending order
+              const bool desc = ((i & k) == 0);
+              if (desc ? !i_first : i_first) { val[i] = o; val[l] = a; idx[i] = io; idx[l] = ia; }
+            }
+          }
+          __syncthreads();
+        }
+      }
+      const float m = val[0];
+      __shared__ int nvalid_s;
+      if (tid == 0) nvalid_s = 0;
+      __syncthreads();
+      int cnt = 0;
+      for (int i = tid; i < kSampleSlots; i += blockDim.x) cnt += (val[i] > -INFINITY) ? 1 : 0;
+      if (cnt) atomicAdd(&nvalid_s, cnt);
+      __syncthreads();
+      const int nvalid = nvalid_s;
+      float kth = -INFINITY;
+      if (mode == 2 && top_k >= 1) kth = val[min(top_k, kSampleSlots) - 1];
+      __syncthreads();
+      for (int i = tid; i < kSampleSlots; i += blockDim.x) {  // unnormalised probabilities, in sorted order
+        const float x = val[i];
+        val[i] = (x > -INFINITY) ? expf(x - m) : 0.f;
+        if (mode == 2 && x < kth) val[i] = 0.f;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int nkeep = nvalid;
+        if (nvalid == 0) {
+          win = idx[0];
+        } else {
+          if (mode == 3) {
+            float total = 0.f;
+            for (int r = 0; r < nvalid; ++r) total += val[r];
+            float cum = 0.f;
+            nkeep = 1;
+            for (int r = 0; r < nvalid; ++r) {
+              cum += val[r] / total;
+              if (r > 0 && cum > top_p) break;
+              nkeep = r + 1;
+            }
+          }
+          float kept = 0.f;
+          for (int r = 0; r < nkeep; ++r) kept += val[r];
+          const float target = uniform[b] * kept;
+          float acc = 0.f;
+          int pick = 0;
+          for (int r = 0; r < nkeep; ++r) {
+            if (val[r] <= 0.f) break;
+            pick = r;
+            acc += val[r];
+            if (acc > target) break;
+          }
+          win = idx[pick];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int t = win;
+  if (tid == 0) {
+    seq[static_cast<long long>(b) * seq_ld + pos] = t;
+    if (pad_mask) pad_mask[static_cast<long long>(b) * mask_ld + pos] = (t == pad_id) ? 1 : 0;
+  }
+  if (x_next)
+    for (int c = tid; c < D; c += blockDim.x)
+      x_next[static_cast<long long>(b) * D + c] = emb[static_cast<long long>(t) * D + c] * scale + pe[static_cast<long long>(pos) * D + c];
+}
+
 // Scatter this step's K and V (columns [D, 3D) of the fused QKV projection) into the self-attention cache.
 __global__ void kv_append_kernel(const float* __restrict__ qkv, int B, int D, float* __restrict__ kcache,
                                  float* __restrict__ vcache, int S, int pos) {
@@ -1084,6 +1212,25 @@ extern "C" int ralf_argmax_next(const float* logits, int ldl, int B, int V, cons
   if (B <= 0 || V <= 0) return RALF_ERR_SHAPE;
   argmax_next_kernel<<<B, 128, 0, ST(stream)>>>(logits, ldl, V, allowed, seq, seq_ld, pos, pad_mask, mask_ld, pad_id,
                                                emb, D, scale, pe, x_next);
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_sample_next(const float* logits, int ldl, int B, int V, const unsigned char* allowed,
+                                const int* forced, int forced_ld, int step, int mode, float temperature, int top_k,
+                                float top_p, const float* uniform, const float* noise, int noise_ld, long long* seq,
+                                int seq_ld, int pos, unsigned char* pad_mask, int mask_ld, long long pad_id,
+                                const float* emb, int D, float scale, const float* pe, float* x_next, void* stream) {
+  if (!logits || !allowed || !seq) return RALF_ERR_NULL;
+  if (B <= 0 || V <= 0 || V > kSampleSlots) return RALF_ERR_SHAPE;
+  if (mode < 0 || mode > 4) return RALF_ERR_SHAPE;
+  if (mode != 0 && (!uniform || !(temperature > 0.f))) return RALF_ERR_NULL;
+  if (mode == 4 && !noise) return RALF_ERR_NULL;
+  if (mode == 2 && top_k < 1) return RALF_ERR_SHAPE;
+  if (mode == 3 && !(top_p > 0.f && top_p <= 1.f)) return RALF_ERR_SHAPE;
+  if (x_next && (!emb || !pe)) return RALF_ERR_NULL;
+  sample_next_kernel<<<B, 256, 0, ST(stream)>>>(logits, ldl, V, allowed, forced, forced_ld, step, mode, temperature, top_k,
+                                               top_p, uniform, noise, noise_ld, seq, seq_ld, pos, pad_mask, mask_ld,
+                                               pad_id, emb, D, scale, pe, x_next);
   return set_cuda_error(cudaGetLastError());
 }
 

@@ -454,10 +454,15 @@ class Engine:
         return logits.view(B, S, self.vocab)
 
     def generate(self, mem_s: Optional[torch.Tensor], B: int, Mlen: int, token_mask: torch.Tensor, bos_id: int,
-                 pad_id: int, steps: int, return_logits: bool = False, kv: Optional[list] = None, step_hook=None):
-        """Greedy decode (retrieval_augmented_autoreg.py:244-300, cond_type uncond) with KV caches.
+                 pad_id: int, steps: int, return_logits: bool = False, kv: Optional[list] = None, step_hook=None,
+                 forced: Optional[torch.Tensor] = None, sampling: Optional[dict] = None,
+                 uniform: Optional[torch.Tensor] = None, rng: Optional[torch.Generator] = None):
+        """Autoregressive decode (retrieval_augmented_autoreg.py:244-300) with KV caches.
         token_mask: uint8 [steps, V] (tokenizer.token_mask).  Returns seq int64 [B, steps] (BOS dropped).
-        ``kv``: precomputed cross-attention cache (cross_kv) of all B canvases; else built from ``mem_s``."""
+        ``kv``: precomputed cross-attention cache (cross_kv) of all B canvases; else built from ``mem_s``.
+        ``forced``: int32 [B, steps] decoding-space restriction table (ralf_b200.task.forced_token_table), -1 = free.
+        ``sampling``: {"name": deterministic|random|top_k|top_p|gumbel, "temperature", "top_k", "top_p"}
+        (helpers/sampling.py:18-68); the uniforms come from ``uniform`` fp32 [steps, B] or are drawn with ``rng``."""
         dev = self.dev
         kvm = kv if kv is not None else self.cross_kv(mem_s, kv24=KV24 and self.npass == 3)
         kv24 = kvm[0].dtype == torch.uint8
@@ -469,6 +474,19 @@ class Engine:
         x = ops.embed(seq, 0, 1, self.w["decoder.emb"], math.sqrt(D), self.w["pe1d"], 0)
         tm = token_mask.to(dev).to(torch.uint8).contiguous()
         all_logits = []
+        mode = (sampling or {}).get("name") or "deterministic"
+        if mode not in ops.SAMPLING_MODES:
+            raise NotImplementedError(f"sampling {mode!r}")
+        plain = forced is None and mode == "deterministic"
+        noise = None
+        if not plain:
+            if forced is not None:
+                forced = forced.to(dev, torch.int32).contiguous()
+                assert forced.shape == (B, steps), f"{forced.shape=}"
+            if mode != "deterministic" and uniform is None:
+                uniform = torch.rand((steps, B), dtype=torch.float32, device=dev, generator=rng)
+            if mode == "gumbel":
+                noise = torch.empty((B, self.vocab), dtype=torch.float32, device=dev)
         for t in range(steps):
             if step_hook is not None:  # profiling aid (profiles/launch_slice.py): called before every decode step
                 step_hook(t)
@@ -489,7 +507,16 @@ class Engine:
             logits, _ = self._gemm_ln(x, "decoder.head.0", "decoder.head.1")
             if return_logits:
                 all_logits.append(logits)
-            ops.argmax_next(logits, tm[t], seq, t + 1, pad_mask, pad_id, self.w["decoder.emb"], math.sqrt(D),
-                            self.w["pe1d"], x)
+            if plain:
+                ops.argmax_next(logits, tm[t], seq, t + 1, pad_mask, pad_id, self.w["decoder.emb"], math.sqrt(D),
+                                self.w["pe1d"], x)
+                continue
+            if noise is not None:
+                noise.uniform_(generator=rng)
+            ops.sample_next(logits, tm[t], seq, t + 1, pad_mask, pad_id, self.w["decoder.emb"], math.sqrt(D),
+                            self.w["pe1d"], x, forced=forced, step=t, mode=mode,
+                            temperature=(sampling or {}).get("temperature", 1.0), top_k=(sampling or {}).get("top_k", 5),
+                            top_p=(sampling or {}).get("top_p", 0.9), uniform=uniform[t] if uniform is not None else None,
+                            noise=noise)
         out = seq[:, 1:]
         return (out, torch.stack(all_logits, 1)) if return_logits else out

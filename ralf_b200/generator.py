@@ -6,9 +6,10 @@ keep that contract -- constructor kwargs, ``state_dict`` key names/shapes (stric
 reference checkpoint), and the methods ``train.py`` / ``inference.py`` call -- while every
 tensor operation runs in :class:`ralf_b200.engine.Engine` (hand-written sm_100a kernels, no CPU fallback).
 
-Scope: unconstrained generation (``uncond``) forward / loss / greedy sampling.  The
-constrained tasks (c, cwh, partial, refinement, relation) and stochastic sampling are row f3 ("next") and
-raise NotImplementedError rather than silently taking another path.
+Scope: forward / loss / sampling for the tasks uncond, c, cwh, partial, refinement (host side in
+ralf_b200/task.py, decoding-space restriction + deterministic / random / top_k / top_p / gumbel sampling in the device
+kernel ``ralf_sample_next``).  ``relation`` (Gen-R with backtracking) raises NotImplementedError rather than silently
+taking another path.
 """
 from __future__ import annotations
 
@@ -19,70 +20,22 @@ import torch
 import torch.nn as nn
 from torch import Tensor
 
+from . import task as T
 from .engine import Engine
+from .task import ConditionalInputs, TaskPreprocessor, get_condition  # noqa: F401  (re-exported: reference import sites)
 from .tokenizer import LayoutSequenceTokenizer
 
-TASK_TOKENS = ["end_of_task", "label", "label_size", "relationship", "refinement", "completion", "uncondition"]
-PREPROCESS_SPECIAL = ["sep", "relation_sep", "canvas"]
-N_REL_LOC, N_REL_SIZE = 6, 4  # helpers/relationships.py:11-24
+UnconditionalPreprocessor = TaskPreprocessor  # task=None/"uncond" (task_preprocessor.py:354-384)
 
 
-# ------------------------------------------------------------------------------------------------
-# conditional inputs (models/common/base_model.py:17-109), uncond subset
-# ------------------------------------------------------------------------------------------------
-@dataclass
-class ConditionalInputs:
-    image: Tensor
-    id: Any = None
-    task: Optional[str] = None
-    seq: Optional[Tensor] = None
-    mask: Optional[Tensor] = None
-    retrieved: dict = field(default_factory=dict)
 
-    def to(self, x: Any) -> "ConditionalInputs":
-        self.image = self.image.to(x)
-        self.retrieved = {k: (v.to(x) if torch.is_tensor(v) else v) for k, v in self.retrieved.items()}
-        return self
-
-
-def get_condition(batch: dict, cond_type: Optional[str], tokenizer: LayoutSequenceTokenizer):
-    """helpers/task.py:45-183 for cond_type in (None, "none", "uncond")."""
-    if cond_type not in (None, "none", "uncond"):
-        raise NotImplementedError(f"cond_type={cond_type!r}: constrained tasks are SURVEY.md 8(f3), not built yet")
-    image = batch["image"] if batch["image"].size(1) == 4 else torch.cat([batch["image"], batch["saliency"]], dim=1)
-    try:
-        ids = torch.tensor(list(map(int, batch["id"])), dtype=torch.long)
-    except Exception:
-        ids = batch.get("id")
-    retrieved = batch.get("retrieved", {})
-    if isinstance(retrieved, list):
-        assert len(retrieved) == 1
-        retrieved = retrieved[0]
-    return ConditionalInputs(image=image, id=ids, task=cond_type, retrieved=retrieved), batch
-
-
-class UnconditionalPreprocessor:
-    """layoutformerpp/task_preprocessor.py:58-140,354-384: constraint sequence [bos, uncondition, end_of_task, eos]."""
-
-    def __init__(self, tokenizer: LayoutSequenceTokenizer) -> None:
-        self.tokenizer = tokenizer
-        self.tokens = TASK_TOKENS + PREPROCESS_SPECIAL + [f"rel_elem_{i}" for i in range(tokenizer.max_seq_length)] + \
-            [f"rel_loc_{i}" for i in range(N_REL_LOC)] + [f"rel_size_{i}" for i in range(N_REL_SIZE)]
-
-    @property
-    def N_total(self) -> int:
-        return self.tokenizer.N_total + len(self.tokens)
-
-    def name_to_id(self, name: str) -> int:
-        if name in self.tokenizer.special_tokens:
-            return self.tokenizer.name_to_id(name)
-        return self.tokens.index(name) + self.tokenizer.N_total
-
-    def __call__(self, cond) -> dict:
-        B = cond.image.size(0)
-        ids = [self.name_to_id(n) for n in ("bos", "uncondition", "end_of_task", "eos")]
-        seq = torch.tensor(ids, dtype=torch.long, device=cond.image.device)[None].expand(B, -1).contiguous()
-        return {"seq": seq, "pad_mask": seq == self.tokenizer.name_to_id("pad")}
+def _cfg_get(cfg: Any, key: str, default: Any = None) -> Any:
+    """Hydra DictConfig / dataclass / plain dict access."""
+    if cfg is None:
+        return default
+    if isinstance(cfg, dict):
+        return cfg.get(key, default)
+    return getattr(cfg, key, default)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -201,8 +154,7 @@ class _B200LayoutModel(nn.Module):
         super().__init__()
         if d_model != 256:
             raise NotImplementedError("the B200 kernels are specialised for d_model = 256 (reference default)")
-        if auxilary_task not in (None, "uncond"):
-            raise NotImplementedError(f"auxilary_task={auxilary_task!r}: constrained tasks are SURVEY.md 8(f3)")
+        assert auxilary_task in T.COND_TYPES, f"{auxilary_task=} must be one of {T.COND_TYPES}"
         self.features = features
         self.tokenizer = self._host_tokenizer(tokenizer)
         self.dataset_name = dataset_name
@@ -212,11 +164,11 @@ class _B200LayoutModel(nn.Module):
         self.retrieval_backbone = retrieval_backbone
         self.random_retrieval = random_retrieval
         self.saliency_k = saliency_k
-        self.auxilary_task = auxilary_task or "uncond"
+        self.auxilary_task = auxilary_task
         self.use_multitask = use_multitask
         self.use_flag_embedding = use_flag_embedding
         self.precision = precision
-        self.preprocessor = UnconditionalPreprocessor(self.tokenizer)
+        self.preprocessor = TaskPreprocessor(self.tokenizer, auxilary_task)
         g = torch.Generator().manual_seed(0)
         for entry in param_schema(self.tokenizer.N_label, self.tokenizer.N_total, self.preprocessor.N_total, self.IS_RALF):
             name, shape = entry[0], entry[1]
@@ -288,9 +240,26 @@ class _B200LayoutModel(nn.Module):
     def aggregate_sampling_config(self, sampling_cfg, test_cfg=None):
         return sampling_cfg
 
+    # ---- multitask plumbing (retrieval_augmented_autoreg.py:707-750) --------------------------------
+    def set_task_preprocessor(self, task: Optional[str]) -> None:
+        assert task in T.COND_TYPES, f"{task=} must be one of {T.COND_TYPES}"
+        if not self.use_multitask:
+            return
+        self.auxilary_task = task
+        self.preprocessor = TaskPreprocessor(self.tokenizer, task)
+
+    def get_random_task(self) -> str:
+        """Task mixture of LayoutFormer++ (Tab. 3 of its supplement), without `relation` (not built)."""
+        import random
+
+        tasks = ["uncond", "c", "cwh", "partial", "refinement"]
+        return random.choices(tasks, weights=[1 / 12, 1 / 3, 1 / 3, 1 / 12, 1 / 3])[0]
+
     # ---- train.py / inference.py surface --------------------------------------------------------
     def preprocess(self, inputs: dict) -> tuple[dict, dict]:
         """retrieval_augmented_autoreg.py:764-785 -> :509-523 (autoreg.py equivalent)."""
+        if self.use_multitask:
+            self.set_task_preprocessor(self.get_random_task())
         cond, inputs = get_condition(inputs, self.auxilary_task, self.tokenizer)
         const = self.preprocessor(cond)
         data = self.tokenizer.encode(inputs)
@@ -331,32 +300,48 @@ class _B200LayoutModel(nn.Module):
     @torch.no_grad()
     def sample(self, cond: Any, batch_size: Optional[int] = None, sampling_cfg: Any = None,
                cond_type: Optional[str] = "uncond", return_violation: bool = False, use_backtrack: bool = True,
-               return_decoded_cond: bool = False, return_seq: bool = False, **kwargs: Any):
-        """Greedy generation (retrieval_augmented_autoreg.py:218-325) with KV caches on the GPU."""
-        if cond_type not in (None, "none", "uncond"):
-            raise NotImplementedError(f"cond_type={cond_type!r}: SURVEY.md 8(f3)")
-        name = getattr(sampling_cfg, "name", None) if sampling_cfg is not None else "deterministic"
-        if name not in (None, "deterministic"):
-            raise NotImplementedError(f"sampling {name!r}: only greedy (helpers/sampling.py:24-25) is built")
+               return_decoded_cond: bool = False, return_seq: bool = False, generator: Optional[torch.Generator] = None,
+               **kwargs: Any):
+        """Generation (retrieval_augmented_autoreg.py:218-325) with KV caches on the GPU: tasks uncond / c / cwh /
+        partial / refinement; sampling deterministic / random / top_k / top_p / gumbel (helpers/sampling.py:18-68).
+        ``generator``: optional torch CUDA generator for the uniforms of the stochastic samplers."""
+        if cond_type == "relation":
+            raise NotImplementedError("cond_type='relation' (Gen-R + backtracking): SURVEY.md 8(f3)")
+        assert cond_type in T.COND_TYPES, f"{cond_type=}"
+        if self.use_multitask:
+            self.set_task_preprocessor(getattr(cond, "task", cond_type))
+        name = _cfg_get(sampling_cfg, "name", "deterministic") or "deterministic"
+        sampling = {"name": name, "temperature": _cfg_get(sampling_cfg, "temperature", 1.0),
+                    "top_k": _cfg_get(sampling_cfg, "top_k", 5), "top_p": _cfg_get(sampling_cfg, "top_p", 0.9)}
         image = cond.image
         B = image.size(0)
         if B == 1 and batch_size and batch_size > 1:
+            assert cond_type in T.UNCOND, "batch_size expansion is only defined for unconstrained generation"
             B = batch_size
             image = image.expand(B, -1, -1, -1)
-        const = self.preprocessor(cond if cond.image.size(0) == B else ConditionalInputs(image=image))
+            cond = ConditionalInputs(image=image, task=cond_type, retrieved=getattr(cond, "retrieved", {}))
+        const = self.preprocessor(cond)  # rewrites <eos> -> <pad> inside cond.seq like the reference (task.py)
+        ids = self.special_token_ids
+        steps = self.tokenizer.max_token_length
+        forced = T.forced_token_table(cond_type, getattr(cond, "seq", None), ids["pad"], ids["eos"], steps,
+                                      self.tokenizer.N_var_per_element)
         eng = self.engine()
         mem, mem_s = eng.encode(image, getattr(cond, "retrieved", None) if self.IS_RALF else None, const["seq"],
                                 const["pad_mask"])
-        ids = self.special_token_ids
-        seq = eng.generate(mem_s, B, mem.shape[1], self.tokenizer.token_mask, ids["bos"], ids["pad"],
-                           self.tokenizer.max_token_length)
+        seq = eng.generate(mem_s, B, mem.shape[1], self.tokenizer.token_mask, ids["bos"], ids["pad"], steps,
+                           forced=forced, sampling=sampling, rng=generator)
         seq = seq.cpu()
         out = self.tokenizer.decode(seq)  # BaseModel.postprocess (base_model.py:367-389)
         if return_seq:
             out["seq"] = seq
+        if return_decoded_cond:
+            out["decoded_tokens"] = self.preprocessor.decode_tokens(const["seq"])
         if not return_violation:
             return out
-        return out, {"total": 1, "viorated": 0}  # violate.py:81-88 (uncond)
+        vio = T.calculate_violation(cond_type, cond, seq, self.tokenizer)  # violate.py:24-139
+        if cond_type in ("none", "uncond", "c", "cwh", "refinement"):
+            assert vio["viorated"] == 0, f"{vio=}"
+        return out, vio
 
 
 class ConcateAuxilaryTaskConcateCrossAttnRetrievalAugmentedAutoreg(_B200LayoutModel):

@@ -380,6 +380,23 @@ def argmax_next(logits, allowed, seq, pos, pad_mask, pad_id, emb, scale, pe, x_n
                                       _ptr(x_next), _stream()), "ralf_argmax_next")
 
 
+SAMPLING_MODES = {"deterministic": 0, "random": 1, "top_k": 2, "top_p": 3, "gumbel": 4}
+
+
+def sample_next(logits, allowed, seq, pos, pad_mask, pad_id, emb, scale, pe, x_next, *, forced=None, step=0,
+                mode="deterministic", temperature=1.0, top_k=5, top_p=0.9, uniform=None, noise=None):
+    """Step tail with decoding-space restriction (``forced`` int32 [B, S], -1 = free) and helpers/sampling.py's
+    stochastic samplers; ``uniform`` fp32 [B] (and ``noise`` fp32 [B, V] for gumbel) are the random numbers."""
+    B, V = logits.shape
+    check(_lib.lib().ralf_sample_next(logits.data_ptr(), logits.stride(0), B, V, allowed.data_ptr(), _ptr(forced),
+                                      forced.stride(0) if forced is not None else 0, step, SAMPLING_MODES[mode],
+                                      float(temperature), int(top_k), float(top_p), _ptr(uniform), _ptr(noise),
+                                      noise.stride(0) if noise is not None else 0, seq.data_ptr(), seq.stride(0), pos,
+                                      _ptr(pad_mask), pad_mask.stride(0) if pad_mask is not None else 0, pad_id, _ptr(emb),
+                                      emb.shape[1] if emb is not None else 0, scale, _ptr(pe), _ptr(x_next), _stream()),
+          "ralf_sample_next")
+
+
 def kv_append(qkv, kcache, vcache, pos):
     B, D = qkv.shape[0], qkv.shape[1] // 3
     check(_lib.lib().ralf_kv_append(qkv.data_ptr(), B, D, kcache.data_ptr(), vcache.data_ptr(), kcache.shape[1], pos,

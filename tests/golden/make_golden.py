@@ -8,6 +8,9 @@ Outputs (committed):
   ralf_cgl_256.npz      RALF (shipped class), B=2, 256x256 canvases, k=16, E=10  (BASELINE configs 2/3/5 shape)
   ralf_cgl_350x240.npz  RALF, B=1, real canvas size 350x240
   autoreg_cgl_350x240.npz  Autoreg baseline, B=1 (BASELINE config 1)
+  tasks_cgl_256.npz     constrained tasks c / cwh / partial / refinement through the reference's get_condition,
+                        task preprocessors, DECODE_SPACE_RESTRICTION and greedy sample() (same weights/batch as ralf_cgl_256)
+  sampling_filters.npz  helpers/sampling.py on random logits: the post-filter probabilities handed to torch.multinomial
 Each npz: tokenizer outputs (seq, mask, token_mask), constraint sequence, encoder memory, teacher-forced
 logits, nll loss, greedy token ids + per-step masked logits, decoded layout.
 """
@@ -87,6 +90,109 @@ def run(model, tok, name, B, H, W, seed, is_ralf):
     print(name, {k: getattr(v, "shape", None) for k, v in out.items()})
 
 
+TASKS = ["c", "cwh", "partial", "refinement"]
+
+
+def run_tasks(tok, name, B, H, W, seed):
+    """Constrained tasks on the shipped RALF class built with use_multitask=True, which makes sample()
+    pick the task preprocessor from cond.task (retrieval_augmented_autoreg.py:745-750); same weights as `run`."""
+    import copy
+
+    from image2layout.train.helpers.task import get_condition
+    from image2layout.train.models.layoutformerpp.decoding_space_restriction import DECODE_SPACE_RESTRICTION
+    from image2layout.train.models.retrieval_augmented_autoreg import (
+        ConcateAuxilaryTaskConcateCrossAttnRetrievalAugmentedAutoreg as RALF,
+    )
+
+    _, features = rb.make_tokenizer("cgl", 10)
+    model = RALF(features=features, tokenizer=tok, dataset_name="cgl", max_seq_length=10, db_dataset=None,
+                 retrieval_backbone="dreamsim", random_retrieval=False, top_k=16, saliency_k="None",
+                 auxilary_task="uncond", use_multitask=True)
+    torch.manual_seed(0)
+    model.load_state_dict(synth.synth_state_dict(schema_of(model), seed=seed), strict=True)
+    model.eval()
+    batch = synth.synth_batch(B, H, W, 10, 16, tok.N_label, seed=seed)
+    ids = model.special_token_ids
+    out = {}
+    for ti, task in enumerate(TASKS):
+        rng_seed = 100 + ti
+        with torch.no_grad():
+            # (1) the reference's own sample(): decoded layout + violation
+            torch.manual_seed(rng_seed)
+            cond, _ = get_condition(copy.deepcopy(batch), task, tok)
+            res, vio = model.sample(cond=cond, sampling_cfg=rb.DictConfig(name="deterministic"), cond_type=task,
+                                    return_violation=True)
+            # (2) replay with the same host RNG stream, recording every intermediate of the boundary
+            torch.manual_seed(rng_seed)
+            b2 = copy.deepcopy(batch)
+            cond, b2 = get_condition(b2, task, tok)
+            out[f"{task}_cond_seq"], out[f"{task}_cond_mask"] = cond.seq.clone().numpy(), cond.mask.clone().numpy()
+            if task == "refinement":
+                for k in ["center_x", "center_y", "width", "height"]:
+                    out[f"{task}_noisy_{k}"] = b2[k].numpy()
+            model.set_task_preprocessor(task)
+            enc_in, const = model._create_encoder_inputs(cond)
+            out[f"{task}_const_seq"], out[f"{task}_const_pad_mask"] = const["seq"].numpy(), const["pad_mask"].numpy()
+            out[f"{task}_cond_seq_after"] = cond.seq.clone().numpy()  # parse_seq_into_vars rewrites <eos> in place
+            enc_in["retrieved"] = {k: v.type_as(cond.image) for k, v in enc_in["retrieved"].items() if torch.is_tensor(v)}
+            memory = model._encode_into_memory(enc_in)
+            inp = torch.full((B, 1), ids["bos"])
+            start = 0
+            if task == "partial":
+                inp = torch.cat([inp, cond.seq[:, 1:6]], dim=1)
+                start = 5
+            for i in range(start, tok.max_token_length):
+                lg = model.decoder(tgt=inp, tgt_key_padding_mask=(inp == ids["pad"]), is_causal=True, **memory)[:, i].clone()
+                lg[:, ~tok.token_mask[i]] = -float("inf")
+                lg = DECODE_SPACE_RESTRICTION[task](i + 1, cond.seq, lg, pad_id=ids["pad"], eos_id=ids["eos"],
+                                                    max_length=tok.max_token_length)
+                inp = torch.cat([inp, lg.argmax(dim=1, keepdim=True)], dim=1)
+            out[f"{task}_gen_seq"] = inp[:, 1:].numpy()
+            dec = tok.decode(inp[:, 1:])
+            for k in ["label", "mask", "center_x", "center_y", "width", "height"]:
+                assert torch.equal(dec[k], res[k]), f"{task}: sample() and replay disagree on {k}"
+                out[f"{task}_gen_{k}"] = res[k].numpy()
+            out[f"{task}_violation"] = np.array([vio["total"], vio["viorated"]])
+    out["meta"] = np.array(json.dumps({"B": B, "H": H, "W": W, "seed": seed, "tasks": TASKS,
+                                       "rng_seed": {t: 100 + i for i, t in enumerate(TASKS)}}))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, {k: getattr(v, "shape", None) for k, v in out.items()})
+
+
+def run_sampling_filters():
+    """helpers/sampling.py:18-68 on random masked logits: capture what the reference hands to torch.multinomial."""
+    from image2layout.train.helpers import sampling as S
+
+    g = torch.Generator().manual_seed(5)
+    N, V = 24, 519
+    logits = torch.randn((N, V), generator=g) * 3.0
+    logits[:, 4:] += torch.where(torch.rand((N, V - 4), generator=g) < 0.5, -float("inf"), 0.0)  # masked vocabulary
+    logits[3] = -float("inf")
+    logits[3, 7] = 0.25  # a forced token: single finite entry
+    logits[5, 10:14] = 2.0  # ties
+    cfgs = [dict(name="random", temperature=1.0), dict(name="random", temperature=0.7),
+            dict(name="top_k", top_k=5, temperature=1.0), dict(name="top_k", top_k=1, temperature=1.3),
+            dict(name="top_k", top_k=40, temperature=0.5), dict(name="top_p", top_p=0.9, temperature=1.0),
+            dict(name="top_p", top_p=0.5, temperature=2.0), dict(name="top_p", top_p=1.0, temperature=1.0)]
+    out = {"logits": logits.numpy(), "cfgs": np.array(json.dumps(cfgs))}
+    captured = []
+    real = torch.multinomial
+
+    def spy(probs, num_samples, *a, **k):
+        captured.append(probs.clone())
+        return real(probs, num_samples, *a, **k)
+
+    torch.multinomial = spy
+    try:
+        for i, c in enumerate(cfgs):
+            S.sample(logits.clone(), rb.DictConfig(**c))
+            out[f"probs_{i}"] = captured[-1].numpy()
+    finally:
+        torch.multinomial = real
+    np.savez_compressed(os.path.join(OUT, "sampling_filters.npz"), **out)
+    print("sampling_filters", len(cfgs))
+
+
 def main():
     rb.bootstrap("/tmp/ralf_ref_work")
     torch.backends.mha.set_fastpath_enabled(False)
@@ -94,7 +200,13 @@ def main():
     ralf, tok, _ = rb.make_ralf("cgl")
     with open(os.path.join(OUT, "schema_ralf_cgl.json"), "w") as f:
         json.dump(schema_of(ralf), f)
+    if "--tasks-only" in sys.argv:
+        run_tasks(tok, "tasks_cgl_256", B=2, H=256, W=256, seed=1)
+        run_sampling_filters()
+        return
     run(ralf, tok, "ralf_cgl_256", B=2, H=256, W=256, seed=1, is_ralf=True)
+    run_tasks(tok, "tasks_cgl_256", B=2, H=256, W=256, seed=1)
+    run_sampling_filters()
     run(ralf, tok, "ralf_cgl_350x240", B=1, H=350, W=240, seed=2, is_ralf=True)
     ar, tok2, _ = rb.make_autoreg("cgl")
     with open(os.path.join(OUT, "schema_autoreg_cgl.json"), "w") as f:
