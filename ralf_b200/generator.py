@@ -190,6 +190,7 @@ class _B200LayoutModel(nn.Module):
                 t = torch.randn(shape, generator=g) * (0.02 if "emb" in name else fan_in ** -0.5)
             _register(self, name, t, kind)
         self._engine: Optional[Engine] = None
+        self._train_engine = None
 
     @staticmethod
     def _host_tokenizer(tok: Any) -> LayoutSequenceTokenizer:
@@ -208,10 +209,12 @@ class _B200LayoutModel(nn.Module):
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
         out = super().load_state_dict(state_dict, strict=strict, **kw)
         self._engine = None
+        self._train_engine = None
         return out
 
     def _apply(self, fn, *a, **k):
         self._engine = None
+        self._train_engine = None  # parameter storage may move: the flat master buffer is rebuilt on next use
         return super()._apply(fn, *a, **k)
 
     def engine(self) -> Engine:
@@ -287,11 +290,51 @@ class _B200LayoutModel(nn.Module):
         logits = self.engine().decoder_logits(inputs["seq"], inputs["tgt_key_padding_mask"], mem_s, B, Mlen)
         return {"logits": logits}
 
+    def optim_groups(self, base_lr: Optional[float] = None, weight_decay: float = 0.0,
+                     forced_no_weight_decay: Optional[list] = None, custom_lr: Optional[dict] = None) -> list:
+        """models/common/base_model.py:207-347: Linear / MultiheadAttention / Conv weights decay, biases and LayerNorm /
+        BatchNorm / Embedding weights do not; ``custom_lr`` {prefix: lr} groups come first (train.py:217-223 passes
+        {"encoder.extractor.body": lr * 0.1}); parameter names sorted inside every group, frozen parameters left out."""
+        from .train import _is_decay
+
+        named = {n: p for n, p in self.named_parameters() if p.requires_grad}
+        forced = set(forced_no_weight_decay or [])
+        decay = {n for n, p in named.items() if _is_decay(n, p) and n not in forced}
+        no_decay = set(named) - decay
+        groups, taken = [], set()
+        for prefix, lr in (custom_lr or {}).items():
+            for names, wd in ((decay, weight_decay), (no_decay, 0.0)):
+                sel = sorted(n for n in names if n.startswith(prefix))
+                taken.update(sel)
+                if sel:
+                    groups.append({"params": [named[n] for n in sel], "weight_decay": wd, "lr": lr})
+        for names, wd in ((decay, weight_decay), (no_decay, 0.0)):
+            sel = sorted(names - taken)
+            if sel or not custom_lr:
+                groups.append({"params": [named[n] for n in sel], "weight_decay": wd, "lr": base_lr})
+        return groups
+
+    def trainer(self, **kw):
+        """The TrainEngine bound to this module (created on first use; its flat fp32 buffer becomes the storage of the
+        module's parameters).  ``trainer().train_step`` is the fused path; ``train_loss`` below is the drop-in one."""
+        if self._train_engine is None:
+            from .train import TrainEngine
+
+            self._train_engine = TrainEngine(self, **kw)
+        return self._train_engine
+
     def train_loss(self, inputs: dict, targets: dict, test: bool = False):
         """CrossEntropyLoss(label_smoothing=0.1, ignore_index=pad) over b s c -> b c s (:209-216).
-        Forward value only: the backward/optimizer kernels are SURVEY.md 8 rows a12/a13 (round 2)."""
+        model.train() with grad enabled: the loss carries a backward that runs our kernels and fills ``p.grad``
+        (TrainEngine.loss_with_grad), so train.py:440-454 works as is.  Otherwise (evaluate(): eval + no_grad): value only."""
         from . import ops
 
+        if self.training and torch.is_grad_enabled() and not test:
+            if not self.IS_RALF:
+                raise NotImplementedError("training is built for the RALF class (SURVEY.md 8 a13)")
+            loss, logits = self.trainer().loss_with_grad(inputs, targets)
+            self._engine = None  # inference operands are re-prepared from the updated parameters on demand
+            return {"logits": logits}, {"nll_loss": loss}
         outputs = self(inputs)
         loss = ops.ce_label_smooth(outputs["logits"], targets["seq"].to(outputs["logits"].device), 0.1,
                                    self.tokenizer.name_to_id("pad"))

@@ -35,6 +35,21 @@ def _is_decay(name: str, p: torch.Tensor) -> bool:
     return True
 
 
+class _TapeLoss(torch.autograd.Function):
+    """Bridge between the kernel tape and torch.autograd (see TrainEngine.loss_with_grad)."""
+
+    @staticmethod
+    def forward(ctx, anchor, loss, tape, engine):
+        ctx.tape, ctx.engine = tape, engine
+        return loss.detach().clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        ctx.tape.backward()
+        ctx.engine._publish_grads(g)
+        return None, None, None, None
+
+
 class TrainEngine:
     limits = ("dropout not applied",)
 
@@ -59,6 +74,7 @@ class TrainEngine:
         self.group_cfg = [(lr * body_lr_scale, weight_decay), (lr * body_lr_scale, 0.0), (lr, weight_decay), (lr, 0.0)]
         for n, p in named:  # the module's parameters become views of the flat master buffer
             p.data = self.ps.p(n)
+        self._named = named
         self._register_weights()
         self.trunk = None
         if train_trunk:
@@ -235,6 +251,35 @@ class TrainEngine:
         logits = ag.linear(tape, ps, hh, "decoder.head.1", None)
         loss = ag.ce_loss(tape, logits, targets["seq"].to(dev), 0.1, self.model.tokenizer.name_to_id("pad"))
         return loss, tape, logits
+
+    # ------------------------------------------------------------------------------------------
+    # drop-in loss for the reference's own loop (train.py:440-454): loss.backward() fills p.grad
+    # ------------------------------------------------------------------------------------------
+    def loss_with_grad(self, inputs: dict, targets: dict):
+        """Forward through the tape and return (loss, logits [B, S, V]) where ``loss`` is a scalar tensor attached to
+        torch.autograd by ONE node: its backward replays the tape (our kernels), all-reduces in data-parallel runs and
+        points every trainable parameter's ``.grad`` at its slice of the flat gradient buffer, so that the reference's
+        ``loss.backward(); clip_grad_norm_(model.parameters(), c); optimizer.step()`` works unchanged.  The parameters
+        are views of the flat master buffer, so an external optimiser updates the master weights in place; the GEMM
+        operands are refreshed from them at the start of the next call."""
+        self.refresh_operands()
+        self.ps.flat_g.zero_()
+        loss, tape, logits = self.forward_loss(inputs, targets)
+        anchor = next(p for _, p in self._named)
+        B = inputs["image"].shape[0]
+        return _TapeLoss.apply(anchor, loss, tape, self), logits.f32.view(B, -1, logits.Cn)
+
+    def _publish_grads(self, scale: Optional[torch.Tensor]) -> None:
+        ps = self.ps
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(ps.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
+            ps.flat_g.mul_(1.0 / self.world)
+        if scale is not None:
+            ps.flat_g.mul_(scale)
+        for n, p in self._named:
+            p.grad = ps.g(n)
 
     def _add_bias_slice(self, tape, node: Node, bias_name: str, off: int, n: int) -> None:
         """node.f32 += bias[off:off+n] (row broadcast) with the bias gradient routed to that slice."""

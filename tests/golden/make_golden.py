@@ -193,6 +193,16 @@ def run_sampling_filters():
     print("sampling_filters", len(cfgs))
 
 
+def run_optim_groups(model):
+    """BaseModel.optim_groups as train.py:217-223 calls it -> [(lr, weight_decay, [parameter names])]."""
+    names = {id(p): n for n, p in model.named_parameters()}
+    groups = model.optim_groups(base_lr=1e-4, weight_decay=1e-4, custom_lr={"encoder.extractor.body": 1e-5})
+    out = [{"lr": g["lr"], "weight_decay": g["weight_decay"], "params": [names[id(p)] for p in g["params"]]} for g in groups]
+    with open(os.path.join(OUT, "optim_groups_ralf_cgl.json"), "w") as f:
+        json.dump(out, f)
+    print("optim_groups", [(g["lr"], g["weight_decay"], len(g["params"])) for g in out])
+
+
 def main():
     rb.bootstrap("/tmp/ralf_ref_work")
     torch.backends.mha.set_fastpath_enabled(False)
@@ -203,6 +213,7 @@ def main():
     if "--tasks-only" in sys.argv:
         run_tasks(tok, "tasks_cgl_256", B=2, H=256, W=256, seed=1)
         run_sampling_filters()
+        run_optim_groups(ralf)
         return
     run(ralf, tok, "ralf_cgl_256", B=2, H=256, W=256, seed=1, is_ralf=True)
     run_tasks(tok, "tasks_cgl_256", B=2, H=256, W=256, seed=1)

@@ -87,3 +87,23 @@ def test_uncond_constraint_sequence_matches_reference():
     out = pre(G.ConditionalInputs(image=torch.zeros(2, 4, 8, 8)))
     assert out["seq"].tolist() == z["seq_layout_const"].tolist()
     assert out["pad_mask"].tolist() == z["seq_layout_const_pad_mask"].tolist()
+
+
+def test_optim_groups_match_reference():
+    """models/common/base_model.py:207-347 through train.py:217-223's call: same groups, order, lr and weight decay
+    (fixture dumped from the reference class by tests/golden/make_golden.py)."""
+    import json
+    import os
+
+    from ralf_b200 import generator as G
+    from tests import helpers
+
+    with open(os.path.join(helpers.GOLDEN, "optim_groups_ralf_cgl.json")) as f:
+        ref = json.load(f)
+    model = G.RALF(features=None, tokenizer=helpers.make_tokenizer(), dataset_name="cgl", max_seq_length=10)
+    names = {id(p): n for n, p in model.named_parameters()}
+    groups = model.optim_groups(base_lr=1e-4, weight_decay=1e-4, custom_lr={"encoder.extractor.body": 1e-5})
+    mine = [{"lr": g["lr"], "weight_decay": g["weight_decay"], "params": [names[id(p)] for p in g["params"]]} for g in groups]
+    assert mine == ref
+    plain = model.optim_groups(base_lr=1e-4, weight_decay=1e-4)
+    assert len(plain) == 2 and sum(len(g["params"]) for g in plain) == sum(len(g["params"]) for g in ref)

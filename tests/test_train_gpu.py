@@ -178,3 +178,43 @@ def test_graph_replayed_train_step_equals_eager(cuda_device):
     assert max(abs(a - b) for a, b in zip(la[1:], lb)) <= 1e-4 * abs(la[1]), (la, lb)
     pa, pb = ta.ps.flat_p, tb.ps.flat_p
     assert (pa - pb).abs().max().item() <= 5e-3 * pa.abs().max().item()
+
+
+def test_reference_train_loop_runs_unchanged(cuda_device):
+    """The reference's own loop (train.py:440-454): optimizer built from optim_groups, zero_grad, train_loss,
+    loss.backward(), clip_grad_norm_, optimizer.step().  Must give the same losses / parameters as the fused
+    TrainEngine.train_step on a twin model (same kernels for forward/backward; torch's AdamW vs ours)."""
+    from oracle import synth
+    from ralf_b200.train import TrainEngine
+
+    batch = synth.synth_batch(4, 128, 128, 10, 16, 4, seed=14)
+    ma, mb = _model(cuda_device, seed=25), _model(cuda_device, seed=25)
+    ma.train()
+    mb.train()
+    inputs, targets = ma.preprocess(batch)
+    inputs = {k: (v.to(cuda_device) if torch.is_tensor(v) else v) for k, v in inputs.items()}
+    targets = {k: v.to(cuda_device) for k, v in targets.items()}
+    opt = torch.optim.AdamW(ma.optim_groups(base_lr=1e-3, weight_decay=1e-4, custom_lr={"encoder.extractor.body": 1e-4}),
+                            betas=(0.9, 0.999))
+    la = []
+    for _ in range(3):
+        ma.zero_grad()
+        outputs, losses = ma.train_loss(inputs, targets)
+        loss = sum(losses.values())
+        assert loss.requires_grad and outputs["logits"].shape[:2] == inputs["seq"].shape
+        loss.backward()
+        gn = torch.nn.utils.clip_grad_norm_(ma.parameters(), 0.1)
+        opt.step()
+        la.append(float(loss))
+    tb = TrainEngine(mb, lr=1e-3, weight_decay=1e-4, body_lr_scale=0.1, max_grad_norm=0.1)
+    lb = [float(tb.train_step(inputs, targets)) for _ in range(3)]
+    assert float(gn) > 0 and all(p.grad is not None for p in ma.parameters() if p.requires_grad)
+    assert max(abs(a - b) for a, b in zip(la, lb)) <= 1e-4 * abs(la[0]), (la, lb)
+    pa = torch.cat([p.detach().reshape(-1) for n, p in sorted(ma.named_parameters()) if p.requires_grad])
+    pb = torch.cat([p.detach().reshape(-1) for n, p in sorted(mb.named_parameters()) if p.requires_grad])
+    assert (pa - pb).abs().max().item() <= 5e-3 * pa.abs().max().item()
+    # evaluate() path: eval + no_grad gives a plain value and sees the UPDATED parameters
+    ma.eval()
+    with torch.no_grad():
+        _, lv = ma.train_loss(inputs, targets, test=True)
+    assert not lv["nll_loss"].requires_grad and math.isfinite(float(lv["nll_loss"]))
