@@ -236,6 +236,29 @@ int ralf_colsum(const float* in, long long ld, int M, int C, float* out, int acc
 /* nn.LayerNorm backward; dx = add_to + dLN; workspace = 2*D*min(ceil(M/8), 4*SMs) floats. */
 int ralf_layernorm_bwd(const float* x, long long x_ld, const float* dy, const float* gamma, float eps, int M, int D,
                        const float* add_to, float* dx, float* dgamma, float* dbeta, float* workspace, void* stream);
+/* ---- dropout (training; nn.Dropout / nn.MultiheadAttention(dropout=p) of the reference's encoder / decoder layers and
+ * positional encodings, retrieval_augmented_autoreg.py:105,116-126; common/common.py:26-35,216; positional_encoding.py:67-107).
+ * Masks are counter-based: element idx of call site `site` is kept iff SplitMix64(*seed ^ f(site), idx) >> 40 >= p * 2^24;
+ * `seed` is a DEVICE pointer (one value per step) so captured graphs draw fresh masks per replay.  Forward and backward
+ * recompute the mask; nothing is stored. */
+/* y = (res ? res : 0) + dropout(x): x fp32 [total] or split (in_plane); y fp32 and / or split.  In place allowed. */
+int ralf_dropout(const float* in_f32, const void* in_split, long long in_plane, const float* res, long long total,
+                 const unsigned long long* seed, unsigned int site, float p, float* out_f32, void* out_split,
+                 long long out_plane, void* stream);
+/* Keep mask (1 = kept) of elements [0, total) of a site: test / debugging aid. */
+int ralf_dropout_mask(const unsigned long long* seed, unsigned int site, float p, long long total, unsigned char* out,
+                      void* stream);
+/* ralf_attention with dropout on the attention probabilities: O = (softmax(S) o M / (1-p)) V; mask element index
+ * ((b*H + h)*Tq + t)*Tk + j.  Always the CUDA-core kernel. */
+int ralf_attention_dropout(const float* q, int ldq, const float* k, const float* v, int ldk,
+                           const unsigned char* key_padding_mask, int B, int H, int Tq, int Tk, int head_dim, int causal,
+                           float scale, void* out_split, long long out_plane, float* out_f32, int ldo,
+                           const unsigned long long* seed, unsigned int site, float p, void* stream);
+int ralf_attention_bwd_dropout(const float* q, int ldq, const float* k, const float* v, int ldk,
+                               const unsigned char* key_padding_mask, int B, int H, int Tq, int Tk, int head_dim,
+                               int causal, float scale, const void* o_split, long long o_plane, const float* dO, int ldo,
+                               float* lse_ws, float* delta_ws, float* dq, int lddq, float* dk, float* dv, int lddk,
+                               const unsigned long long* seed, unsigned int site, float p, void* stream);
 /* Backward of ralf_attention (same addressing); lse_ws / delta_ws: B*H*Tq floats each. */
 int ralf_attention_bwd(const float* q, int ldq, const float* k, const float* v, int ldk,
                        const unsigned char* key_padding_mask, int B, int H, int Tq, int Tk, int head_dim, int causal,

@@ -26,9 +26,22 @@ class Node:
         self.M, self.Cn, self.f32, self.s, self.grad, self.need_grad = M, Cn, f32, s, None, need_grad
 
 
+class DropoutState:
+    """Dropout of one training step: probability, the device-resident step seed and a call-site counter (sites are
+    numbered in forward order, so forward and backward of an op agree and a captured graph keeps its numbering)."""
+
+    def __init__(self, p: float, seed: torch.Tensor) -> None:
+        self.p, self.seed, self.site = p, seed, 0
+
+    def next_site(self) -> int:
+        self.site += 1
+        return self.site
+
+
 class Tape:
-    def __init__(self) -> None:
+    def __init__(self, drop: Optional[DropoutState] = None) -> None:
         self.ops: list[Callable[[], None]] = []
+        self.drop = drop if (drop is not None and drop.p > 0.0) else None
 
     def record(self, fn: Callable[[], None]) -> None:
         self.ops.append(fn)
@@ -230,10 +243,65 @@ def layernorm(tape: Tape, ps: ParamStore, x: Node, name: str, *, want_f32: bool 
     return y
 
 
-def _attention_bwd(q, ldq, k, v, ldk, mask, B, H, Tq, Tk, dh, causal, o_split, dO, dq, lddq, dk, dv, lddk):
+def dropout_inplace(tape: Tape, node: Node) -> None:
+    """nn.Dropout applied to ``node`` in place (fp32 and / or split storage); the backward masks node.grad in place,
+    between the consumer that produced it and the producer that reads it."""
+    dr = tape.drop
+    if dr is None:
+        return
+    site = dr.next_site()
+    if node.f32 is not None:
+        ops.dropout(dr.seed, site, dr.p, x_f32=node.f32, out_f32=node.f32, out_split=node.s)
+    else:
+        ops.dropout(dr.seed, site, dr.p, x_split=node.s, out_split=node.s)
+
+    def bwd() -> None:
+        if node.grad is not None:
+            ops.dropout(dr.seed, site, dr.p, x_f32=node.grad, out_f32=node.grad)
+
+    tape.record(bwd)
+
+
+def dropout_add(tape: Tape, z: Node, res: Node) -> Node:
+    """y = res + dropout(z)  (the ``x + dropoutN(sublayer(x))`` of nn.TransformerEncoder/DecoderLayer)."""
+    dr = tape.drop
+    site = dr.next_site()
+    y = Node(z.M, z.Cn, torch.empty_like(z.f32), None)
+    ops.dropout(dr.seed, site, dr.p, x_f32=z.f32, res=res.f32, out_f32=y.f32)
+
+    def bwd() -> None:
+        dy = y.grad
+        if dy is None:
+            return
+        g = torch.empty_like(dy)
+        ops.dropout(dr.seed, site, dr.p, x_f32=dy, out_f32=g)
+        accumulate(z, g)
+        accumulate(res, dy)
+        y.grad = None
+
+    tape.record(bwd)
+    return y
+
+
+def linear_res(tape: Tape, ps: ParamStore, x: Node, wname: str, bias: Optional[str], res: Node) -> Node:
+    """res + dropout(x W^T + b): fused into the GEMM epilogue when dropout is off."""
+    if tape.drop is None:
+        return linear(tape, ps, x, wname, bias, res=res)
+    return dropout_add(tape, linear(tape, ps, x, wname, bias), res)
+
+
+def _attention_bwd(q, ldq, k, v, ldk, mask, B, H, Tq, Tk, dh, causal, o_split, dO, dq, lddq, dk, dv, lddk, dropout=None):
     dev = dO.device
     lse = torch.empty(B * H * Tq, dtype=torch.float32, device=dev)
     delta = torch.empty(B * H * Tq, dtype=torch.float32, device=dev)
+    if dropout is not None:
+        seed, site, p = dropout
+        check(_L().ralf_attention_bwd_dropout(q.data_ptr(), ldq, k.data_ptr(), v.data_ptr(), ldk, _ptr(mask), B, H, Tq, Tk,
+                                              dh, int(causal), dh ** -0.5, o_split.data_ptr(), o_split.stride(0),
+                                              dO.data_ptr(), dO.stride(0), lse.data_ptr(), delta.data_ptr(), dq.data_ptr(),
+                                              lddq, dk.data_ptr(), dv.data_ptr(), lddk, seed.data_ptr(), site, p,
+                                              _stream()), "ralf_attention_bwd_dropout")
+        return
     check(_L().ralf_attention_bwd(q.data_ptr(), ldq, k.data_ptr(), v.data_ptr(), ldk, _ptr(mask), B, H, Tq, Tk, dh,
                                   int(causal), dh ** -0.5, o_split.data_ptr(), o_split.stride(0), dO.data_ptr(),
                                   dO.stride(0), lse.data_ptr(), delta.data_ptr(), dq.data_ptr(), lddq, dk.data_ptr(),
@@ -245,7 +313,10 @@ def self_attention(tape: Tape, qkv: Node, B: int, T: int, H: int, dh: int, *, ma
     """qkv.f32 [B*T, 3*H*dh] (fused projection) -> attention output (split) [B*T, H*dh]."""
     Dm = H * dh
     x = qkv.f32
-    out = ops.attention(x[:, :Dm], x[:, Dm:2 * Dm], x[:, 2 * Dm:], B, H, T, T, dh, mask=mask, causal=causal)
+    dr = tape.drop
+    dropout = (dr.seed, dr.next_site(), dr.p) if dr is not None else None  # attention-probability dropout
+    out = ops.attention(x[:, :Dm], x[:, Dm:2 * Dm], x[:, 2 * Dm:], B, H, T, T, dh, mask=mask, causal=causal,
+                        dropout=dropout)
     y = Node(qkv.M, Dm, None, out)
 
     def bwd() -> None:
@@ -253,7 +324,7 @@ def self_attention(tape: Tape, qkv: Node, B: int, T: int, H: int, dh: int, *, ma
             return
         d = torch.empty_like(x)
         _attention_bwd(x[:, :Dm], x.stride(0), x[:, Dm:2 * Dm], x[:, 2 * Dm:], x.stride(0), mask, B, H, T, T, dh, causal,
-                       out, y.grad, d[:, :Dm], d.stride(0), d[:, Dm:2 * Dm], d[:, 2 * Dm:], d.stride(0))
+                       out, y.grad, d[:, :Dm], d.stride(0), d[:, Dm:2 * Dm], d[:, 2 * Dm:], d.stride(0), dropout=dropout)
         accumulate(qkv, d)
         y.grad = None
 
@@ -261,11 +332,15 @@ def self_attention(tape: Tape, qkv: Node, B: int, T: int, H: int, dh: int, *, ma
     return y
 
 
-def cross_attention(tape: Tape, q: Node, kv: Node, kcol: int, vcol: int, B: int, Tq: int, Tk: int, H: int, dh: int) -> Node:
-    """q.f32 [B*Tq, H*dh]; kv.f32 [B*Tk, ncols] with K at columns [kcol, kcol+H*dh), V at [vcol, ...)."""
+def cross_attention(tape: Tape, q: Node, kv: Node, kcol: int, vcol: int, B: int, Tq: int, Tk: int, H: int, dh: int, *,
+                    use_dropout: bool = True) -> Node:
+    """q.f32 [B*Tq, H*dh]; kv.f32 [B*Tk, ncols] with K at columns [kcol, kcol+H*dh), V at [vcol, ...).
+    ``use_dropout=False``: the fusion Attention of the reference is built with dropout=0.0 (:701-703)."""
     Dm = H * dh
     kk, vv = kv.f32[:, kcol:kcol + Dm], kv.f32[:, vcol:vcol + Dm]
-    out = ops.attention(q.f32, kk, vv, B, H, Tq, Tk, dh)
+    dr = tape.drop if use_dropout else None
+    dropout = (dr.seed, dr.next_site(), dr.p) if dr is not None else None
+    out = ops.attention(q.f32, kk, vv, B, H, Tq, Tk, dh, dropout=dropout)
     y = Node(q.M, Dm, None, out)
 
     def bwd() -> None:
@@ -275,7 +350,7 @@ def cross_attention(tape: Tape, q: Node, kv: Node, kcol: int, vcol: int, B: int,
         dq = torch.empty_like(q.f32)
         g = torch.empty_like(kv.f32)
         _attention_bwd(q.f32, q.f32.stride(0), kk, vv, kv.f32.stride(0), None, B, H, Tq, Tk, dh, False, out, y.grad, dq,
-                       dq.stride(0), g[:, kcol:kcol + Dm], g[:, vcol:vcol + Dm], g.stride(0))
+                       dq.stride(0), g[:, kcol:kcol + Dm], g[:, vcol:vcol + Dm], g.stride(0), dropout=dropout)
         accumulate(kv, g)
         accumulate(q, dq)
         y.grad = None

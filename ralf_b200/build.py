@@ -52,7 +52,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
         for cmd, pr in procs:
             if pr.wait() != 0:
                 raise subprocess.CalledProcessError(pr.returncode, cmd)
-        subprocess.run([nvcc, "-shared", "-o", LIB, *objs], check=True)
+        subprocess.run([nvcc, "-arch=sm_100a", "-shared", "-o", LIB, *objs], check=True)
     return LIB
 
 

@@ -17,6 +17,37 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
+// ----------------------------------------------------------------------------------------------
+// Counter-based dropout masks (training): element `idx` of dropout site `site` in the step whose
+// seed sits in device memory (so a captured CUDA graph draws fresh masks on every replay) is kept iff the top 24 bits
+// of SplitMix64(seed ^ site-constant, counter idx) reach the threshold.  Forward and backward kernels recompute the
+// same bit instead of storing masks.
+// ----------------------------------------------------------------------------------------------
+struct DropArgs {
+  const unsigned long long* seed;  // device pointer, one value per optimisation step
+  unsigned int site;               // unique per dropout call site
+  unsigned int thresh24;           // p * 2^24; 0 = dropout off
+  float inv_keep;                  // 1 / (1 - p)
+};
+__host__ __device__ __forceinline__ unsigned long long drop_stream(unsigned long long seed, unsigned int site) {
+  return seed ^ (0xD1B54A32D192ED03ull * (static_cast<unsigned long long>(site) + 1ull));
+}
+__host__ __device__ __forceinline__ bool drop_keep(unsigned long long stream, unsigned long long idx, unsigned int thresh24) {
+  unsigned long long z = stream + 0x9E3779B97F4A7C15ull * (idx + 1ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return static_cast<unsigned int>(z >> 40) >= thresh24;
+}
+__host__ inline DropArgs make_drop_args(const unsigned long long* seed, unsigned int site, float p) {
+  DropArgs a;
+  a.seed = seed;
+  a.site = site;
+  a.thresh24 = (seed && p > 0.f) ? static_cast<unsigned int>(p * 16777216.f) : 0u;
+  a.inv_keep = 1.f / (1.f - p);
+  return a;
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(

@@ -86,7 +86,8 @@ template <int DH>
 __global__ void __launch_bounds__(128)
 attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, const float* __restrict__ v,
                  int ldk, const unsigned char* __restrict__ mask, int Tq, int Tk, int causal, float scale,
-                 __nv_bfloat16* __restrict__ out_split, long long out_plane, float* __restrict__ out_f32, int ldo) {
+                 __nv_bfloat16* __restrict__ out_split, long long out_plane, float* __restrict__ out_f32, int ldo,
+                 DropArgs da) {
   constexpr int KT = 64;
   __shared__ __align__(16) float ks[KT][DH];
   __shared__ __align__(16) float vs[KT][DH];
@@ -106,6 +107,10 @@ attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__
 #pragma unroll
   for (int i = 0; i < DH; ++i) o[i] = 0.f;
   float mrun = -INFINITY, lrun = 0.f;
+  // attention-probability dropout (nn.MultiheadAttention(dropout=p) in training): O = (P o M / keep) V, P normalised
+  // over ALL keys; mask element index = ((b*H + h)*Tq + t)*Tk + j
+  const unsigned long long dstream = da.thresh24 ? drop_stream(*da.seed, da.site) : 0ull;
+  const unsigned long long drow = ((static_cast<unsigned long long>(b) * gridDim.y + h) * Tq + t) * Tk;
   const int kmax = causal ? min(Tk, (blockIdx.x + 1) * static_cast<int>(blockDim.x)) : Tk;
   for (int j0 = 0; j0 < kmax; j0 += KT) {
     __syncthreads();
@@ -150,8 +155,9 @@ attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__
       for (int i = 0; i < DH; ++i) o[i] *= corr;
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
-        const float p = __expf(s[jj] - mnew);  // -inf -> 0
+        float p = __expf(s[jj] - mnew);  // -inf -> 0
         lrun += p;
+        if (da.thresh24) p = drop_keep(dstream, drow + j0 + c0 + jj, da.thresh24) ? p * da.inv_keep : 0.f;
         const int j = (c0 + jj) & (KT - 1);
 #pragma unroll
         for (int i = 0; i < DH; i += 4) {
@@ -1027,26 +1033,46 @@ extern "C" int ralf_layernorm(const float* x, long long in_ld, const float* gamm
   return RALF_ERR_SHAPE;  // D / 32 must be a power of two <= 32
 }
 
-extern "C" int ralf_attention(const float* q, int ldq, const float* k, const float* v, int ldk,
-                              const unsigned char* key_padding_mask, int B, int H, int Tq, int Tk, int head_dim,
-                              int causal, float scale, void* out_split, long long out_plane, float* out_f32, int ldo,
-                              void* stream) {
+static int attention_impl(const float* q, int ldq, const float* k, const float* v, int ldk,
+                          const unsigned char* key_padding_mask, int B, int H, int Tq, int Tk, int head_dim, int causal,
+                          float scale, void* out_split, long long out_plane, float* out_f32, int ldo, DropArgs da,
+                          void* stream) {
   if (!q || !k || !v) return RALF_ERR_NULL;
   if (B <= 0 || H <= 0 || Tq <= 0 || Tk <= 0 || (head_dim != 32 && head_dim != 64)) return RALF_ERR_SHAPE;
   if ((ldq & 3) || (ldk & 3)) return RALF_ERR_ALIGN;
-  // image-encoder shape class (8 x 32 heads, no mask, <= 256 keys): tcgen05 kernel (attention_tc.cu)
-  const int tc = attention_tc_try(q, ldq, k, v, ldk, key_padding_mask, B, H, Tq, Tk, head_dim, causal, scale, out_split,
-                                  out_plane, out_f32, ldo, ST(stream));
-  if (tc != 0) return tc < 0 ? tc : 0;
+  if (!da.thresh24) {
+    // image-encoder shape class (8 x 32 heads, no mask, <= 256 keys): tcgen05 kernel (attention_tc.cu)
+    const int tc = attention_tc_try(q, ldq, k, v, ldk, key_padding_mask, B, H, Tq, Tk, head_dim, causal, scale, out_split,
+                                    out_plane, out_f32, ldo, ST(stream));
+    if (tc != 0) return tc < 0 ? tc : 0;
+  }
   const int threads = Tq >= 128 ? 128 : ((Tq + 31) / 32) * 32;
   dim3 grid((Tq + threads - 1) / threads, H, B);
   if (head_dim == 32)
     attention_kernel<32><<<grid, threads, 0, ST(stream)>>>(q, ldq, k, v, ldk, key_padding_mask, Tq, Tk, causal, scale,
-                                                          BF(out_split), out_plane, out_f32, ldo);
+                                                          BF(out_split), out_plane, out_f32, ldo, da);
   else
     attention_kernel<64><<<grid, threads, 0, ST(stream)>>>(q, ldq, k, v, ldk, key_padding_mask, Tq, Tk, causal, scale,
-                                                          BF(out_split), out_plane, out_f32, ldo);
+                                                          BF(out_split), out_plane, out_f32, ldo, da);
   return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_attention(const float* q, int ldq, const float* k, const float* v, int ldk,
+                              const unsigned char* key_padding_mask, int B, int H, int Tq, int Tk, int head_dim,
+                              int causal, float scale, void* out_split, long long out_plane, float* out_f32, int ldo,
+                              void* stream) {
+  return attention_impl(q, ldq, k, v, ldk, key_padding_mask, B, H, Tq, Tk, head_dim, causal, scale, out_split, out_plane,
+                        out_f32, ldo, make_drop_args(nullptr, 0, 0.f), stream);
+}
+
+extern "C" int ralf_attention_dropout(const float* q, int ldq, const float* k, const float* v, int ldk,
+                                      const unsigned char* key_padding_mask, int B, int H, int Tq, int Tk, int head_dim,
+                                      int causal, float scale, void* out_split, long long out_plane, float* out_f32,
+                                      int ldo, const unsigned long long* seed, unsigned int site, float p, void* stream) {
+  if (!seed) return RALF_ERR_NULL;
+  if (!(p >= 0.f && p < 1.f)) return RALF_ERR_SHAPE;
+  return attention_impl(q, ldq, k, v, ldk, key_padding_mask, B, H, Tq, Tk, head_dim, causal, scale, out_split, out_plane,
+                        out_f32, ldo, make_drop_args(seed, site, p), stream);
 }
 
 static int attention_decode_impl(const float* q, int ldq, const float* k, const float* v, long long kv_bstride, int ldk,

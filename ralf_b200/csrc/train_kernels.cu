@@ -3,6 +3,7 @@
 // embedding scatter, global gradient norm and the fused clip + AdamW update.  The dense contractions of the
 // backward pass (dX = dY.W, dW = dY^T.X) reuse the tcgen05 GEMM in gemm.cu with K-major operands produced here.
 // fp32 arithmetic; GEMM operands are emitted as split bf16 (hi, lo planes).
+#include <algorithm>
 #include <float.h>
 #include <math.h>
 
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(128)
 attn_bwd_dq_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, const float* __restrict__ v, int ldk,
                    const unsigned char* __restrict__ mask, int Tq, int Tk, int causal, float scale,
                    const __nv_bfloat16* __restrict__ o_split, long long o_plane, const float* __restrict__ dO, int ldo,
-                   float* __restrict__ lse, float* __restrict__ delta, float* __restrict__ dq, int lddq) {
+                   float* __restrict__ lse, float* __restrict__ delta, float* __restrict__ dq, int lddq, DropArgs da) {
   constexpr int KT = 64;
   __shared__ __align__(16) float ks[KT][DH];
   __shared__ __align__(16) float vs[KT][DH];
@@ -159,6 +160,10 @@ attn_bwd_dq_kernel(const float* __restrict__ q, int ldq, const float* __restrict
   const bool active = t < Tq;
   float qr[DH], dor[DH], acc[DH];
   float my_lse = 0.f, dl = 0.f;
+  // with attention-probability dropout (mask M' = keep / (1-p)): O = (P o M') V, so dP = M' o (dO V^T) and
+  // delta = sum_j P_ij dP_ij = dO_i . O_i still holds; dS = P o (dP - delta)
+  const unsigned long long dstream = da.thresh24 ? drop_stream(*da.seed, da.site) : 0ull;
+  const unsigned long long drow = ((static_cast<unsigned long long>(b) * H + h) * Tq + t) * Tk;
   if (active) {
     const long long qrow = static_cast<long long>(b) * Tq + t;
     const float* qp = q + qrow * ldq + h * DH;
@@ -228,6 +233,7 @@ attn_bwd_dq_kernel(const float* __restrict__ q, int ldq, const float* __restrict
         s = fmaf(qr[i], ks[j][i], s);
         dpv = fmaf(dor[i], vs[j][i], dpv);
       }
+      if (da.thresh24) dpv = drop_keep(dstream, drow + j0 + j, da.thresh24) ? dpv * da.inv_keep : 0.f;
       const float ds = __expf(s - my_lse) * (dpv - dl) * scale;
 #pragma unroll
       for (int i = 0; i < DH; ++i) acc[i] = fmaf(ds, ks[j][i], acc[i]);
@@ -244,7 +250,7 @@ __global__ void __launch_bounds__(128)
 attn_bwd_dkv_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, const float* __restrict__ v, int ldk,
                     const unsigned char* __restrict__ mask, int Tq, int Tk, int causal, float scale,
                     const float* __restrict__ dO, int ldo, const float* __restrict__ lse, const float* __restrict__ delta,
-                    float* __restrict__ dk, float* __restrict__ dv, int lddk) {
+                    float* __restrict__ dk, float* __restrict__ dv, int lddk, DropArgs da) {
   constexpr int QT = 64;
   __shared__ __align__(16) float qs[QT][DH];
   __shared__ __align__(16) float ds_[QT][DH];  // dO tile
@@ -253,6 +259,8 @@ attn_bwd_dkv_kernel(const float* __restrict__ q, int ldq, const float* __restric
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = j < Tk;
   const bool dead = active && mask && mask[static_cast<long long>(b) * Tk + j];
+  const unsigned long long dstream = da.thresh24 ? drop_stream(*da.seed, da.site) : 0ull;
+  const unsigned long long dhead = (static_cast<unsigned long long>(b) * H + h) * Tq;
   // one sweep over the queries: dV and dK accumulate together, K and V rows of this thread's key live in registers
   float kr[DH], vr[DH], accv[DH], acck[DH];
   if (active) {
@@ -302,13 +310,19 @@ attn_bwd_dkv_kernel(const float* __restrict__ q, int ldq, const float* __restric
         dpv = fmaf(fd.z, vr[i + 2], dpv); dpv = fmaf(fd.w, vr[i + 3], dpv);
       }
       const float p = __expf(s - ls[r]);
+      float pm = p;  // P o M' (what multiplied V in the forward)
+      if (da.thresh24) {
+        const float mk = drop_keep(dstream, (dhead + i0 + r) * Tk + j, da.thresh24) ? da.inv_keep : 0.f;
+        pm = p * mk;
+        dpv *= mk;
+      }
       const float dsv = p * (dpv - dls[r]) * scale;
 #pragma unroll
       for (int i = 0; i < DH; i += 4) {
         const float4 fq = *reinterpret_cast<const float4*>(&qs[r][i]);
         const float4 fd = *reinterpret_cast<const float4*>(&ds_[r][i]);
-        accv[i] = fmaf(p, fd.x, accv[i]); accv[i + 1] = fmaf(p, fd.y, accv[i + 1]);
-        accv[i + 2] = fmaf(p, fd.z, accv[i + 2]); accv[i + 3] = fmaf(p, fd.w, accv[i + 3]);
+        accv[i] = fmaf(pm, fd.x, accv[i]); accv[i + 1] = fmaf(pm, fd.y, accv[i + 1]);
+        accv[i + 2] = fmaf(pm, fd.z, accv[i + 2]); accv[i + 3] = fmaf(pm, fd.w, accv[i + 3]);
         acck[i] = fmaf(dsv, fq.x, acck[i]); acck[i + 1] = fmaf(dsv, fq.y, acck[i + 1]);
         acck[i + 2] = fmaf(dsv, fq.z, acck[i + 2]); acck[i + 3] = fmaf(dsv, fq.w, acck[i + 3]);
       }
@@ -575,11 +589,11 @@ extern "C" int ralf_adamw_step_dyn(float* params, const float* grads, float* exp
   return set_cuda_error(cudaGetLastError());
 }
 
-extern "C" int ralf_attention_bwd(const float* q, int ldq, const float* k, const float* v, int ldk,
+static int attention_bwd_impl(const float* q, int ldq, const float* k, const float* v, int ldk,
                                   const unsigned char* key_padding_mask, int B, int H, int Tq, int Tk, int head_dim,
                                   int causal, float scale, const void* o_split, long long o_plane, const float* dO,
                                   int ldo, float* lse_ws, float* delta_ws, float* dq, int lddq, float* dk, float* dv,
-                                  int lddk, void* stream) {
+                                  int lddk, DropArgs da, void* stream) {
   float* lse = lse_ws;
   if (!q || !k || !v || !o_split || !dO || !lse || !delta_ws || !dq || !dk || !dv) return RALF_ERR_NULL;
   if (B <= 0 || H <= 0 || Tq <= 0 || Tk <= 0 || (head_dim != 32 && head_dim != 64)) return RALF_ERR_SHAPE;
@@ -589,15 +603,83 @@ extern "C" int ralf_attention_bwd(const float* q, int ldq, const float* k, const
   dim3 g1((Tq + tq - 1) / tq, H, B), g2((Tk + tk - 1) / tk, H, B);
   if (head_dim == 32) {
     attn_bwd_dq_kernel<32><<<g1, tq, 0, ST(stream)>>>(q, ldq, k, v, ldk, key_padding_mask, Tq, Tk, causal, scale,
-                                                     CBF(o_split), o_plane, dO, ldo, lse, delta_ws, dq, lddq);
+                                                     CBF(o_split), o_plane, dO, ldo, lse, delta_ws, dq, lddq, da);
     attn_bwd_dkv_kernel<32><<<g2, tk, 0, ST(stream)>>>(q, ldq, k, v, ldk, key_padding_mask, Tq, Tk, causal, scale, dO, ldo,
-                                                      lse, delta_ws, dk, dv, lddk);
+                                                      lse, delta_ws, dk, dv, lddk, da);
   } else {
     attn_bwd_dq_kernel<64><<<g1, tq, 0, ST(stream)>>>(q, ldq, k, v, ldk, key_padding_mask, Tq, Tk, causal, scale,
-                                                     CBF(o_split), o_plane, dO, ldo, lse, delta_ws, dq, lddq);
+                                                     CBF(o_split), o_plane, dO, ldo, lse, delta_ws, dq, lddq, da);
     attn_bwd_dkv_kernel<64><<<g2, tk, 0, ST(stream)>>>(q, ldq, k, v, ldk, key_padding_mask, Tq, Tk, causal, scale, dO, ldo,
-                                                      lse, delta_ws, dk, dv, lddk);
+                                                      lse, delta_ws, dk, dv, lddk, da);
   }
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_attention_bwd(const float* q, int ldq, const float* k, const float* v, int ldk,
+                                  const unsigned char* key_padding_mask, int B, int H, int Tq, int Tk, int head_dim,
+                                  int causal, float scale, const void* o_split, long long o_plane, const float* dO,
+                                  int ldo, float* lse_ws, float* delta_ws, float* dq, int lddq, float* dk, float* dv,
+                                  int lddk, void* stream) {
+  return attention_bwd_impl(q, ldq, k, v, ldk, key_padding_mask, B, H, Tq, Tk, head_dim, causal, scale, o_split, o_plane, dO,
+                            ldo, lse_ws, delta_ws, dq, lddq, dk, dv, lddk, make_drop_args(nullptr, 0, 0.f), stream);
+}
+
+extern "C" int ralf_attention_bwd_dropout(const float* q, int ldq, const float* k, const float* v, int ldk,
+                                          const unsigned char* key_padding_mask, int B, int H, int Tq, int Tk,
+                                          int head_dim, int causal, float scale, const void* o_split, long long o_plane,
+                                          const float* dO, int ldo, float* lse_ws, float* delta_ws, float* dq, int lddq,
+                                          float* dk, float* dv, int lddk, const unsigned long long* seed,
+                                          unsigned int site, float p, void* stream) {
+  if (!seed) return RALF_ERR_NULL;
+  if (!(p >= 0.f && p < 1.f)) return RALF_ERR_SHAPE;
+  return attention_bwd_impl(q, ldq, k, v, ldk, key_padding_mask, B, H, Tq, Tk, head_dim, causal, scale, o_split, o_plane, dO,
+                            ldo, lse_ws, delta_ws, dq, lddq, dk, dv, lddk, make_drop_args(seed, site, p), stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Elementwise dropout (nn.Dropout(p) in training; same op for the backward applied to the gradient):
+//   y[i] = (res ? res[i] : 0) + (keep(i) ? x[i] / (1-p) : 0),  i = linear element index of the [M, C] tensor.
+// x is fp32 or split bf16 (hi + lo); y is written as fp32 and / or split.  In-place use (out == in) is fine.
+// ------------------------------------------------------------------------------------------------
+__global__ void dropout_kernel(const float* __restrict__ in_f32, const __nv_bfloat16* __restrict__ in_split,
+                               long long in_plane, const float* __restrict__ res, long long total, DropArgs da,
+                               float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_split, long long out_plane) {
+  const unsigned long long dstream = da.thresh24 ? drop_stream(*da.seed, da.site) : 0ull;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float x = in_f32 ? in_f32[i] : (__bfloat162float(in_split[i]) + __bfloat162float(in_split[in_plane + i]));
+    if (da.thresh24) x = drop_keep(dstream, static_cast<unsigned long long>(i), da.thresh24) ? x * da.inv_keep : 0.f;
+    if (res) x += res[i];
+    if (out_f32) out_f32[i] = x;
+    if (out_split) t_store_split(out_split, out_plane, i, x);
+  }
+}
+
+__global__ void dropout_mask_kernel(DropArgs da, long long total, unsigned char* __restrict__ out) {
+  const unsigned long long dstream = drop_stream(*da.seed, da.site);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = drop_keep(dstream, static_cast<unsigned long long>(i), da.thresh24) ? 1 : 0;
+}
+
+extern "C" int ralf_dropout(const float* in_f32, const void* in_split, long long in_plane, const float* res,
+                            long long total, const unsigned long long* seed, unsigned int site, float p,
+                            float* out_f32, void* out_split, long long out_plane, void* stream) {
+  if ((!in_f32 && !in_split) || (!out_f32 && !out_split) || !seed) return RALF_ERR_NULL;
+  if (total <= 0 || !(p >= 0.f && p < 1.f)) return RALF_ERR_SHAPE;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 16));
+  dropout_kernel<<<blocks, 256, 0, ST(stream)>>>(in_f32, CBF(in_split), in_plane, res, total, make_drop_args(seed, site, p),
+                                                out_f32, BF(out_split), out_plane);
+  return set_cuda_error(cudaGetLastError());
+}
+
+/* Test / debugging aid: the keep mask (1 = kept) the kernels derive for elements [0, total) of a site. */
+extern "C" int ralf_dropout_mask(const unsigned long long* seed, unsigned int site, float p, long long total,
+                                 unsigned char* out, void* stream) {
+  if (!seed || !out) return RALF_ERR_NULL;
+  if (total <= 0 || !(p > 0.f && p < 1.f)) return RALF_ERR_SHAPE;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 16));
+  dropout_mask_kernel<<<blocks, 256, 0, ST(stream)>>>(make_drop_args(seed, site, p), total, out);
   return set_cuda_error(cudaGetLastError());
 }
 

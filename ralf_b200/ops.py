@@ -248,11 +248,20 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, rows:
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, H: int, Tq: int, Tk: int, dh: int, *,
-              mask: Optional[torch.Tensor] = None, causal: bool = False, scale: Optional[float] = None):
-    """q [B*Tq, >=H*dh] / k, v [B*Tk, >=H*dh] fp32 views (row stride = stride(0)); returns split [2, B*Tq, H*dh]."""
+              mask: Optional[torch.Tensor] = None, causal: bool = False, scale: Optional[float] = None,
+              dropout: Optional[tuple] = None):
+    """q [B*Tq, >=H*dh] / k, v [B*Tk, >=H*dh] fp32 views (row stride = stride(0)); returns split [2, B*Tq, H*dh].
+    ``dropout`` = (seed int64 device tensor [1], site, p): dropout on the attention probabilities (training)."""
     out = _split_out(B * Tq, H * dh, q.device)
     assert k.stride(0) == v.stride(0)
     sc = scale if scale is not None else dh ** -0.5
+    if dropout is not None:
+        seed, site, p = dropout
+        check(_lib.lib().ralf_attention_dropout(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0),
+                                                _ptr(mask), B, H, Tq, Tk, dh, int(causal), sc, out.data_ptr(),
+                                                out.stride(0), None, H * dh, seed.data_ptr(), site, p, _stream()),
+              "ralf_attention_dropout")
+        return out
     check(_lib.lib().ralf_attention(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), _ptr(mask),
                                     B, H, Tq, Tk, dh, int(causal), sc, out.data_ptr(), out.stride(0), None, H * dh,
                                     _stream()), "ralf_attention")
@@ -378,6 +387,25 @@ def argmax_next(logits, allowed, seq, pos, pad_mask, pad_id, emb, scale, pe, x_n
                                       seq.stride(0), pos, _ptr(pad_mask), pad_mask.stride(0) if pad_mask is not None else 0,
                                       pad_id, _ptr(emb), emb.shape[1] if emb is not None else 0, scale, _ptr(pe),
                                       _ptr(x_next), _stream()), "ralf_argmax_next")
+
+
+def dropout(seed: torch.Tensor, site: int, p: float, *, x_f32: Optional[torch.Tensor] = None,
+            x_split: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None,
+            out_f32: Optional[torch.Tensor] = None, out_split: Optional[torch.Tensor] = None) -> None:
+    """y = (res or 0) + dropout_p(x) elementwise over a contiguous [M, C] tensor (fp32 or split planes); the keep mask
+    of element i is a pure function of (seed, site, i) -- see include/ralf_b200.h."""
+    src = x_f32 if x_f32 is not None else x_split[0]
+    assert src.is_contiguous() and (res is None or res.is_contiguous())
+    assert out_f32 is None or out_f32.is_contiguous()
+    check(_lib.lib().ralf_dropout(_ptr(x_f32), _ptr(x_split), x_split.stride(0) if x_split is not None else 0, _ptr(res),
+                                  src.numel(), seed.data_ptr(), site, p, _ptr(out_f32), _ptr(out_split),
+                                  out_split.stride(0) if out_split is not None else 0, _stream()), "ralf_dropout")
+
+
+def dropout_mask(seed: torch.Tensor, site: int, p: float, total: int) -> torch.Tensor:
+    out = torch.empty(total, dtype=torch.uint8, device=seed.device)
+    check(_lib.lib().ralf_dropout_mask(seed.data_ptr(), site, p, total, out.data_ptr(), _stream()), "ralf_dropout_mask")
+    return out
 
 
 SAMPLING_MODES = {"deterministic": 0, "random": 1, "top_k": 2, "top_p": 3, "gumbel": 4}

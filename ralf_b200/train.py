@@ -9,8 +9,14 @@ own wrapper never arms the reducer, we deliberately do the real th
 Status (round 1): every trainable parameter of the reference trains through the tape in autograd.py -- the
 ResNet50-FPN trunk (BatchNorm in training mode, train_conv.py), image encoder, layout adapter, fusion attention,
 head, constraint encoder, decoder, loss; FIDNetV3 stays frozen like in the reference
-(retrieval_augmented_autoreg.py:150-154).  Not applied yet: dropout (p = 0.1 in the reference's encoder /
-decoder / positional encodings) -- reported by ``TrainEngine.limits`` and in DESIGN.md.
+(retrieval_augmented_autoreg.py:150-154).  Dropout (p = 0.1) is applied at the reference's sites: attention
+probabilities, the three residual branches and the FFN activation of every image-encoder / constraint-encoder / decoder
+layer (nn.TransformerEncoder/DecoderLayer(dropout=0.1), :105,116-126; common/common.py:26-35,216) and the three
+1-D positional encodings (positional_encoding.py:67-107); the fusion Attention, head and layout adapter are built with
+dropout 0.0 in the reference.  Masks come from a counter-based generator (csrc/common.cuh), not torch's Philox stream,
+so runs are reproducible per ``seed`` but not mask-identical to the reference.  One deliberate deviation: the frozen
+FIDNetV3 is evaluated without dropout (the reference leaves it in train mode under ``model.train()``, which only adds
+noise to a frozen feature extractor) -- reported by ``TrainEngine.limits``.
 """
 from __future__ import annotations
 
@@ -51,11 +57,14 @@ class _TapeLoss(torch.autograd.Function):
 
 
 class TrainEngine:
-    limits = ("dropout not applied",)
+    limits = ("frozen FIDNetV3 evaluated without dropout",)
 
     def __init__(self, model, *, lr: float = 1e-4, weight_decay: float = 1e-4, body_lr_scale: float = 0.1,
-                 max_grad_norm: float = 0.1, world_size: int = 1, process_group=None, train_trunk: bool = True) -> None:
+                 max_grad_norm: float = 0.1, world_size: int = 1, process_group=None, train_trunk: bool = True,
+                 dropout: float = 0.1, seed: int = 0, rank: int = 0) -> None:
         self.model = model
+        self.dropout = float(dropout)
+        self.seed = (int(seed) * 0x9E3779B97F4A7C15 + int(rank) * 0xD1B54A32D192ED03) & (2 ** 64 - 1)
         self.dev = model.device
         self.lr, self.wd, self.body_scale, self.max_norm = lr, weight_decay, body_lr_scale, max_grad_norm
         self.world, self.pg = world_size, process_group
@@ -82,8 +91,11 @@ class TrainEngine:
 
             self.trunk = Trunk(self.ps, model, self.dev)
         self.pe = _sine_pe_1d(5000, D).to(self.dev)
-        self._dyn_host = torch.ones(3, dtype=torch.float32).pin_memory()
+        # per-step host scalars go through a ring of pinned slots: the async copy of step t must not see step t+1's values
+        self._dyn_host = torch.ones((64, 3), dtype=torch.float32).pin_memory()
         self._dyn = torch.ones(3, dtype=torch.float32, device=self.dev)
+        self._seed_host = torch.zeros(64, dtype=torch.int64).pin_memory()
+        self._seed_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self._graph = None
         self.refresh_operands()
 
@@ -122,10 +134,11 @@ class TrainEngine:
         h = ag.layernorm(tape, ps, x, p + ".norm1")
         qkv = ag.linear(tape, ps, h, p + ".qkv", p + ".self_attn.in_proj_bias")
         a = ag.self_attention(tape, qkv, B, T, NHEAD, D // NHEAD, mask=mask)
-        x1 = ag.linear(tape, ps, a, p + ".o", p + ".self_attn.out_proj.bias", res=x)
+        x1 = ag.linear_res(tape, ps, a, p + ".o", p + ".self_attn.out_proj.bias", x)
         h = ag.layernorm(tape, ps, x1, p + ".norm2")
         f = ag.linear(tape, ps, h, p + ".l1", p + ".linear1.bias", act="relu", want_f32=False)
-        return ag.linear(tape, ps, f, p + ".l2", p + ".linear2.bias", res=x1)
+        ag.dropout_inplace(tape, f)
+        return ag.linear_res(tape, ps, f, p + ".l2", p + ".linear2.bias", x1)
 
     def _ffn_gelu(self, tape, x: Node, p: str) -> Node:
         """common/attention.py:15-30  LN -> Linear -> GELU -> Linear."""
@@ -152,7 +165,7 @@ class TrainEngine:
     def forward_loss(self, inputs: dict, targets: dict):
         """Teacher-forced forward + loss through the tape.  Returns (loss 0-dim tensor, tape, logits Node)."""
         ps, dev = self.ps, self.dev
-        tape = Tape()
+        tape = Tape(ag.DropoutState(self.dropout, self._seed_dev))
         image = inputs["image"].to(dev, torch.float32)
         B = image.shape[0]
         K = self.model.top_k
@@ -181,11 +194,12 @@ class TrainEngine:
             ag.accumulate(ref0, g)
 
         tape.record(ref_bwd)
+        ag.dropout_inplace(tape, ref)  # pos_emb_1d's dropout (positional_encoding.py:107)
         # ---- fusion attention + head over cat[img, ca, ref] ----
         hq = ag.layernorm(tape, ps, x, "attn.norm")
         q = ag.linear(tape, ps, hq, "attn.to_q")
         kv = ag.linear(tape, ps, ref, "attn.to_kv")
-        a = ag.cross_attention(tape, q, kv, 0, 512, B, T, K, 8, 64)
+        a = ag.cross_attention(tape, q, kv, 0, 512, B, T, K, 8, 64, use_dropout=False)
         ca = ag.linear(tape, ps, a, "attn.to_out.0", "attn.to_out.0.bias")
         Tcat = 2 * T + K
         cat = Node(B * Tcat, D, torch.empty((B * Tcat, D), dtype=torch.float32, device=dev), None)
@@ -197,6 +211,7 @@ class TrainEngine:
         sc = inputs["seq_layout_const"].to(dev).contiguous()
         Tc = sc.shape[1]
         uc = ag.embed(tape, ps, sc, Tc, "user_const_encoder.emb.weight", math.sqrt(D), self.pe)
+        ag.dropout_inplace(tape, uc)
         m = inputs["seq_layout_const_pad_mask"].to(dev).to(torch.uint8).contiguous()
         for i in range(NLAYER):
             uc = self._enc_layer(tape, uc, f"user_const_encoder.encoder.layers.{i}", B, Tc, mask=m)
@@ -230,12 +245,13 @@ class TrainEngine:
         S = seq.shape[1]
         pm = inputs["tgt_key_padding_mask"].to(dev).to(torch.uint8).contiguous()
         y = ag.embed(tape, ps, seq, S, "decoder.emb.weight", math.sqrt(D), self.pe)
+        ag.dropout_inplace(tape, y)
         for i in range(NLAYER):
             p = f"decoder.transformer.layers.{i}"
             hh = ag.layernorm(tape, ps, y, p + ".norm1")
             qkv = ag.linear(tape, ps, hh, p + ".qkv", p + ".self_attn.in_proj_bias")
             a = ag.self_attention(tape, qkv, B, S, NHEAD, 32, mask=pm, causal=True)
-            y = ag.linear(tape, ps, a, p + ".o", p + ".self_attn.out_proj.bias", res=y)
+            y = ag.linear_res(tape, ps, a, p + ".o", p + ".self_attn.out_proj.bias", y)
             hh = ag.layernorm(tape, ps, y, p + ".norm2")
             qn = ag.linear(tape, ps, hh, p + ".cq", None)
             kvn = ag.linear(tape, ps, mem, p + ".ckv", None)
@@ -243,10 +259,11 @@ class TrainEngine:
             self._add_bias_slice(tape, qn, p + ".multihead_attn.in_proj_bias", 0, D)
             self._add_bias_slice(tape, kvn, p + ".multihead_attn.in_proj_bias", D, 2 * D)
             a = ag.cross_attention(tape, qn, kvn, 0, D, B, S, Mlen, NHEAD, 32)
-            y = ag.linear(tape, ps, a, p + ".co", p + ".multihead_attn.out_proj.bias", res=y)
+            y = ag.linear_res(tape, ps, a, p + ".co", p + ".multihead_attn.out_proj.bias", y)
             hh = ag.layernorm(tape, ps, y, p + ".norm3")
             f = ag.linear(tape, ps, hh, p + ".l1", p + ".linear1.bias", act="relu", want_f32=False)
-            y = ag.linear(tape, ps, f, p + ".l2", p + ".linear2.bias", res=y)
+            ag.dropout_inplace(tape, f)
+            y = ag.linear_res(tape, ps, f, p + ".l2", p + ".linear2.bias", y)
         hh = ag.layernorm(tape, ps, y, "decoder.head.0")
         logits = ag.linear(tape, ps, hh, "decoder.head.1", None)
         loss = ag.ce_loss(tape, logits, targets["seq"].to(dev), 0.1, self.model.tokenizer.name_to_id("pad"))
@@ -264,6 +281,8 @@ class TrainEngine:
         operands are refreshed from them at the start of the next call."""
         self.refresh_operands()
         self.ps.flat_g.zero_()
+        self.step_count += 1
+        self._set_step_seed()
         loss, tape, logits = self.forward_loss(inputs, targets)
         anchor = next(p for _, p in self._named)
         B = inputs["image"].shape[0]
@@ -320,10 +339,22 @@ class TrainEngine:
         """Per-step scalars of the optimiser go through device memory (a captured step must not bake them in)."""
         self.step_count += 1
         t = self.step_count
-        self._dyn_host[0] = 1.0 if lr is None else lr / self.lr  # scheduler (MultiStepLR) scales every group alike
-        self._dyn_host[1] = 1.0 - 0.9 ** t
-        self._dyn_host[2] = 1.0 - 0.999 ** t
-        self._dyn.copy_(self._dyn_host, non_blocking=True)
+        slot = self._dyn_host[t % 64]
+        slot[0] = 1.0 if lr is None else lr / self.lr  # scheduler (MultiStepLR) scales every group alike
+        slot[1] = 1.0 - 0.9 ** t
+        slot[2] = 1.0 - 0.999 ** t
+        self._dyn.copy_(slot, non_blocking=True)
+        self._set_step_seed()
+
+    def _set_step_seed(self) -> None:
+        """Dropout seed of step ``step_count`` (SplitMix64 of base seed + step) -> device memory (graph-replay safe)."""
+        z = (self.seed + 0x9E3779B97F4A7C15 * self.step_count) & (2 ** 64 - 1)
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & (2 ** 64 - 1)
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & (2 ** 64 - 1)
+        z ^= z >> 31
+        slot = self._seed_host[self.step_count % 64:self.step_count % 64 + 1]
+        slot[0] = z - 2 ** 64 if z >= 2 ** 63 else z
+        self._seed_dev.copy_(slot, non_blocking=True)
 
     def _step_body(self, inputs: dict, targets: dict) -> torch.Tensor:
         ps = self.ps

@@ -1,6 +1,7 @@
 """GPU: training-step parity.  Gradients from the kernel tape (ralf_b200/autograd.py)
 vs torch.autograd on the CPU oracle for the same seeded weights/batch; optimizer vs torch.optim.AdamW.
-Dropout is off on both sides (round-1 limit); BatchNorm uses batch statistics when the trunk trains."""
+Dropout is off on both sides here (masks are generator-specific; tests/test_dropout_gpu.py covers the dropout ops and
+the whole step with dropout on); BatchNorm uses batch statistics when the trunk trains."""
 import math
 
 import numpy as np
@@ -117,7 +118,7 @@ def test_training_gradients_match_oracle(cuda_device, train_trunk):
     pad = model.tokenizer.name_to_id("pad")
     loss64, g64 = _oracle_loss_and_grads(sd, batch, inputs, targets, pad, train_trunk, torch.float64)
     _, g32 = _oracle_loss_and_grads(sd, batch, inputs, targets, pad, train_trunk, torch.float32)
-    te = TrainEngine(model, train_trunk=train_trunk)
+    te = TrainEngine(model, train_trunk=train_trunk, dropout=0.0)  # the fp64 oracle has no dropout; see test_dropout_gpu.py
     te.ps.flat_g.zero_()
     loss, tape, _ = te.forward_loss(inputs, targets)
     tape.backward()
