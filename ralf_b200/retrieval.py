@@ -81,13 +81,13 @@ class GpuRetriever:
     # -- reference cache-table format -----------------------------------------------------------
     def build_table(self, queries: torch.Tensor, query_ids: list, db_ids: list, k: int, drop_self: bool) -> dict:
         """``dict[data_id -> list[db_index]]`` like preprocess_retrieval_cache (retriever.py:193-221):
-        search k+1, and on the train split drop the first hit (the query itself)."""
+        search k+1, and on the train split drop the first hit (the query itself); the other splits keep all k+1 hits
+        like the reference (``load_cache_table`` cuts to top_k when reading)."""
         idx, _ = self.search(queries, k + 1)
         idx = idx.cpu().tolist()
         table = {}
         for qid, row in zip(query_ids, idx):
-            row = row[1:] if drop_self else row[:k]
-            table[qid] = row
+            table[qid] = row[1:] if drop_self else row
         return table
 
 

@@ -1,0 +1,133 @@
+"""CPU: wire formats of the retrieval tables, host collation (f1), LR schedule / checkpoint files (f4),
+and the reference's own property checks for the task preprocessors (tests/train/helpers/test_task_preprocessor.py:28-58)."""
+import collections
+import os
+
+import pytest
+import torch
+
+from tests import helpers
+
+
+def test_cache_table_roundtrip_and_reference_pickle(tmp_path):
+    from ralf_b200 import data as D
+
+    table = {i: [(i * 7 + j) % 100 for j in range(33)] for i in range(20)}
+    p = D.cache_table_path("cgl", "val", "dreamsim", 32, root=str(tmp_path))
+    assert os.path.basename(p) == "cgl_val_dreamsim_wo_head_table_between_dataset_indexes_top_k32.pt"
+    D.save_cache_table(table, p)
+    assert D.load_cache_table(p, 16) == {k: v[:16] for k, v in table.items()}
+    # what the reference writes: a pickled defaultdict(list) (retriever.py:189,226)
+    dd = collections.defaultdict(list)
+    dd.update(table)
+    torch.save(dd, p)
+    assert D.load_cache_table(p, 16) == {k: v[:16] for k, v in table.items()}
+    # and what the reference's loader does with ours: torch.load + slicing (retrieval_dataset_wrapper.py:30-32)
+    D.save_cache_table(table, p)
+    ref = {k: v[:16] for k, v in torch.load(p).items()}
+    assert ref == {k: v[:16] for k, v in table.items()}
+    with pytest.raises(ValueError):
+        D.load_cache_table(str(tmp_path / "missing.pt"), 16)
+
+
+def test_retrieval_yaml_roundtrip(tmp_path):
+    from ralf_b200 import data as D
+
+    db_ids = [str(1000 + i) for i in range(50)]
+    table = {str(i): [(i + j) % 50 for j in range(20)] for i in range(5)}
+    p = str(tmp_path / "cgl" / "val.yaml")
+    D.export_retrieval_yaml(table, db_ids, p, top_k=16)
+    raw = D.load_retrieval_yaml(p)
+    assert raw["3"] == [db_ids[(3 + j) % 50] for j in range(16)]
+    back = D.load_retrieval_yaml(p, id_to_index={i: n for n, i in enumerate(db_ids)})
+    assert back == {k: v[:16] for k, v in table.items()}
+    text = open(p).read()
+    assert text.startswith("'0':\n- '1000'\n")  # same scalar style as data_splits/retrieval/*/*.yaml
+
+
+def test_reference_yaml_tables_parse_when_present():
+    from ralf_b200 import data as D
+
+    p = "/root/reference/data_splits/retrieval/pku/val.yaml"
+    if not os.path.exists(p):
+        pytest.skip("reference tree not mounted")
+    t = D.load_retrieval_yaml(p)
+    assert len(t) > 100 and all(len(v) == 16 and all(isinstance(x, str) for x in v) for v in t.values())
+
+
+def test_collate_main_matches_padding_rules():
+    from ralf_b200 import data as D
+
+    col = D.RetrievalCollator(layouts=None, max_seq_length=5, top_k=2, table_idx={})
+    ex = [{"id": "7", "label": [1, 2], "center_x": [0.1, 0.2], "center_y": [0.3, 0.4], "width": [0.5, 0.6], "height": [0.7, 0.8]},
+          {"id": "9", "label": [], "center_x": [], "center_y": [], "width": [], "height": []}]
+    out = col.collate_main(ex)
+    assert out["label"].tolist() == [[1, 2, 0, 0, 0], [0, 0, 0, 0, 0]]
+    assert out["mask"].tolist() == [[True, True, False, False, False], [True, False, False, False, False]]
+    assert out["width"][1].tolist() == pytest.approx([0.05, 0, 0, 0, 0]) and out["id"] == ["7", "9"]
+    assert out["center_x"].dtype == torch.float32 and out["label"].dtype == torch.int64
+
+
+def test_layout_table_from_rows_packs_valid_first():
+    from ralf_b200 import data as D
+
+    rows = [{"id": 3, "label": [2, 0, 1], "center_x": [.1, .2, .3], "center_y": [.4, .5, .6], "width": [.7, .8, .9], "height": [.15, .25, .35]},
+            {"id": 4, "label": [1], "center_x": [.5], "center_y": [.5], "width": [.2], "height": [.2]}]
+    t = D.LayoutTable.from_rows(rows, max_seq_length=2)
+    assert tuple(t.packed.shape) == (2, 6, 2) and t.ids == [3, 4]
+    assert t.packed[0, 0].tolist() == [2.0, 0.0] and t.packed[0, 1].tolist() == [1.0, 1.0]
+    assert t.packed[1, 1].tolist() == [1.0, 0.0] and t.packed[1, 4].tolist() == pytest.approx([0.2, 0.0])
+
+
+def test_multistep_lr_matches_torch_scheduler():
+    from ralf_b200.checkpoint import multistep_lr
+
+    for epochs, ms in ((50, (0.7,)), (10, (0.5, 0.9)), (20, (3, 15))):
+        p = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.AdamW([p], lr=1e-4)
+        mil = [int(m * epochs) if isinstance(m, float) else m for m in ms]
+        sch = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=mil, gamma=0.1)
+        for epoch in range(1, epochs + 1):
+            assert multistep_lr(1e-4, epoch, epochs, ms) == pytest.approx(opt.param_groups[0]["lr"], rel=1e-12)
+            opt.step()
+            sch.step()
+
+
+def test_model_files_use_reference_names(tmp_path):
+    from ralf_b200 import checkpoint as C
+    from ralf_b200 import generator as G
+
+    m = G.RALF(features=None, tokenizer=helpers.make_tokenizer(), dataset_name="cgl", max_seq_length=10)
+    path = C.save_model(m, str(tmp_path), best_or_final="final", prefix="gen")
+    assert os.path.basename(path) == "gen_final_model.pt"
+    sd = torch.load(path, map_location="cpu")          # inference.py:319 reads it exactly like this
+    assert list(sd.keys()) == list(m.state_dict().keys())
+    m2 = G.RALF(features=None, tokenizer=helpers.make_tokenizer(), dataset_name="cgl", max_seq_length=10)
+    C.load_model(m2, str(tmp_path), "cpu", best_or_final="final", prefix="gen")
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+
+
+@pytest.mark.parametrize("task", ["uncond", "c", "cwh", "partial", "refinement"])
+def test_task_preprocessor_reference_properties(task):
+    """check_get_condition / check_output of the reference's test_task_preprocessor.py:28-58 over random batches."""
+    import copy
+
+    from oracle import synth
+    from ralf_b200 import task as T
+
+    tok = helpers.make_tokenizer()
+    pre = T.TaskPreprocessor(tok, task)
+    for seed in range(12):
+        batch = synth.synth_batch(5, 8, 8, 10, 1, 4, seed=seed)
+        torch.manual_seed(seed)
+        cond, _ = T.get_condition(copy.deepcopy(batch), task, tok)
+        if task != "uncond":
+            assert -1 not in cond.seq[cond.mask].tolist()
+            assert len(set(cond.seq[~cond.mask].tolist())) <= 1
+        out = pre(cond)
+        seq, pad_mask = out["seq"], out["pad_mask"]
+        assert seq.min() >= 0 and seq.max() < pre.N_total
+        assert set(seq[pad_mask].tolist()) <= {pre.name_to_id("pad")}
+        assert pre.name_to_id("pad") not in seq[~pad_mask].tolist()
+        assert (seq[:, 0] == pre.name_to_id("bos")).all() and (seq[:, 1] == pre.name_to_id(pre.TASK)).all()
+        assert ((seq == pre.name_to_id("eos")).sum(dim=1) == 1).all()
