@@ -98,7 +98,8 @@ def evaluate(model, batches: Iterable[dict], *, rank: int = 0, world_size: int =
     if world_size > 1:
         import torch.distributed as dist
 
-        dist.all_reduce(packed, group=process_group)
+        if dist.is_available() and dist.is_initialized():  # otherwise: this shard's local mean
+            dist.all_reduce(packed, group=process_group)
     out = {k: float(packed[i] / packed[-1].clamp(min=1)) for i, k in enumerate(names)}
     out["total"] = sum(v for k, v in out.items() if "loss" in k)
     if was_training:
