@@ -16,7 +16,7 @@ def main(path):
         name = re.sub(r"\(.*", "", row["Kernel Name"]).replace("void ", "")
         order.append((name, v))
     # the decode slice starts with LayerNorm -> QKV GEMM -> self-attention (append) of layer 0
-    dec_start = next(i for i, (n, _) in enumerate(order) if "attention_decode_kernel" in n) - 2
+    dec_start = next(i for i, (n, _) in enumerate(order) if "attention_decode" in n) - 2
     enc, dec = order[:dec_start], order[dec_start:]
     agg = collections.defaultdict(lambda: [0, 0.0])
     for n, v in enc:

@@ -181,6 +181,95 @@ attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
+// Attention over a handful of keys (the fusion Attention of RALF: 256-330 image tokens attend to the 16 retrieved
+// layouts, 8 heads x 64; common/attention.py:49-71).  The generic kernel above is bound by its scattered 2-byte
+// output stores here (HBM floor 20 us, measured 198 us per 128 canvases); this one keeps a 32-query x H-head tile per
+// CTA (warp = head, lane = query), reads K/V through L1 broadcast loads, and stages the output tile in shared memory
+// so that every global store is a full 128/256-byte row segment.
+//   q row (b, t): q + (b*Tq + t)*ldq + h*64 ; k/v row (b, j): base + (b*Tk + j)*ldk + h*64 ; Tk <= 16, no masks.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFewKeysMax = 16;
+__global__ void __launch_bounds__(256)
+attention_fewkeys_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, const float* __restrict__ v,
+                         int ldk, int Tq, int Tk, float scale, __nv_bfloat16* __restrict__ out_split, long long out_plane,
+                         float* __restrict__ out_f32, int ldo) {
+  constexpr int DH = 64, PITCH = DH + 4;  // 68 words: float4 accesses of 8 consecutive rows cover all 32 banks
+  extern __shared__ __align__(16) float stage[];  // [H][32][PITCH]
+  const int b = blockIdx.y, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t0 = blockIdx.x * 32, t = t0 + lane;
+  const bool active = t < Tq;
+  float qr[DH], o[DH], s[kFewKeysMax];
+  if (active) {
+    const float* qp = q + (static_cast<long long>(b) * Tq + t) * ldq + h * DH;
+#pragma unroll
+    for (int i = 0; i < DH; i += 4) {
+      const float4 f = *reinterpret_cast<const float4*>(qp + i);
+      qr[i] = f.x * scale; qr[i + 1] = f.y * scale; qr[i + 2] = f.z * scale; qr[i + 3] = f.w * scale;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < DH; ++i) qr[i] = 0.f;
+  }
+  const float* kb = k + static_cast<long long>(b) * Tk * ldk + h * DH;
+  const float* vb = v + static_cast<long long>(b) * Tk * ldk + h * DH;
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < kFewKeysMax; ++j) {
+    float acc = 0.f;
+    if (j < Tk) {
+      const float* kp = kb + static_cast<long long>(j) * ldk;  // same address in every lane: one broadcast transaction
+#pragma unroll
+      for (int i = 0; i < DH; i += 4) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(kp + i));
+        acc = fmaf(qr[i], f.x, acc); acc = fmaf(qr[i + 1], f.y, acc);
+        acc = fmaf(qr[i + 2], f.z, acc); acc = fmaf(qr[i + 3], f.w, acc);
+      }
+      mx = fmaxf(mx, acc);
+    }
+    s[j] = acc;
+  }
+  float l = 0.f;
+#pragma unroll
+  for (int i = 0; i < DH; ++i) o[i] = 0.f;
+#pragma unroll
+  for (int j = 0; j < kFewKeysMax; ++j) {
+    if (j < Tk) {
+      const float p = __expf(s[j] - mx);
+      l += p;
+      const float* vp = vb + static_cast<long long>(j) * ldk;
+#pragma unroll
+      for (int i = 0; i < DH; i += 4) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(vp + i));
+        o[i] = fmaf(p, f.x, o[i]); o[i + 1] = fmaf(p, f.y, o[i + 1]);
+        o[i + 2] = fmaf(p, f.z, o[i + 2]); o[i + 3] = fmaf(p, f.w, o[i + 3]);
+      }
+    }
+  }
+  const float inv = 1.f / l;
+  float* mine = stage + (h * 32 + lane) * PITCH;
+#pragma unroll
+  for (int i = 0; i < DH; i += 4)
+    *reinterpret_cast<float4*>(mine + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+  __syncwarp();
+  // warp h stores its 32 x 64 tile: half a warp per row -> 256 B (fp32) / 128 B (each bf16 plane) contiguous segments
+  const int c4 = (lane & 15) * 4;
+  for (int r = lane >> 4; r < 32; r += 2) {
+    if (t0 + r >= Tq) break;
+    const float4 f = *reinterpret_cast<const float4*>(stage + (h * 32 + r) * PITCH + c4);
+    const long long off = (static_cast<long long>(b) * Tq + t0 + r) * ldo + h * DH + c4;
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + off) = f;
+    if (out_split) {
+      __align__(8) __nv_bfloat16 hi[4];
+      __align__(8) __nv_bfloat16 lo[4];
+      split_bf16(f.x, hi[0], lo[0]); split_bf16(f.y, hi[1], lo[1]);
+      split_bf16(f.z, hi[2], lo[2]); split_bf16(f.w, hi[3], lo[3]);
+      *reinterpret_cast<uint2*>(out_split + off) = *reinterpret_cast<const uint2*>(hi);
+      *reinterpret_cast<uint2*>(out_split + out_plane + off) = *reinterpret_cast<const uint2*>(lo);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Single-query attention against a K/V cache (greedy decode).  One warp per (batch, head).
 //   q: [B, ldq] fp32 (+ h*DH);  K/V row j of batch b: base + (b*kv_bstride + j)*ldk + h*DH
 //   mask: uint8 [B, mask_ld] or null; Tk keys.  Output: split bf16 [2, B, H*DH].
@@ -1045,6 +1134,22 @@ static int attention_impl(const float* q, int ldq, const float* k, const float* 
     const int tc = attention_tc_try(q, ldq, k, v, ldk, key_padding_mask, B, H, Tq, Tk, head_dim, causal, scale, out_split,
                                     out_plane, out_f32, ldo, ST(stream));
     if (tc != 0) return tc < 0 ? tc : 0;
+  }
+  // few keys, wide heads (fusion Attention over the 16 retrieved layouts): tile kernel with coalesced stores
+  static const bool fewkeys_on = !(getenv("RALF_ATTN_FEWKEYS") && atoi(getenv("RALF_ATTN_FEWKEYS")) == 0);
+  if (fewkeys_on && !da.thresh24 && head_dim == 64 && Tk <= kFewKeysMax && H <= 8 && !key_padding_mask && !causal &&
+      (ldo & 3) == 0 && (out_plane & 3) == 0) {
+    static bool attr_set = false;
+    const int smem = H * 32 * (64 + 4) * static_cast<int>(sizeof(float));
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(attention_fewkeys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 32 * 68 * 4);
+      if (e != cudaSuccess) return set_cuda_error(e);
+      attr_set = true;
+    }
+    dim3 g2((Tq + 31) / 32, B);
+    attention_fewkeys_kernel<<<g2, 32 * H, smem, ST(stream)>>>(q, ldq, k, v, ldk, Tq, Tk, scale, BF(out_split), out_plane,
+                                                              out_f32, ldo);
+    return set_cuda_error(cudaGetLastError());
   }
   const int threads = Tq >= 128 ? 128 : ((Tq + 31) / 32) * 32;
   dim3 grid((Tq + threads - 1) / threads, H, B);

@@ -318,8 +318,14 @@ class _B200LayoutModel(nn.Module):
         """The TrainEngine bound to this module (created on first use; its flat fp32 buffer becomes the storage of the
         module's parameters).  ``trainer().train_step`` is the fused path; ``train_loss`` below is the drop-in one."""
         if self._train_engine is None:
+            import torch.distributed as dist
+
             from .train import TrainEngine
 
+            if dist.is_available() and dist.is_initialized() and "world_size" not in kw:
+                # launched through the reference's ddp_setup (helpers/distrubuted.py:10-20): do the gradient all-reduce
+                # its DDPWrapper was meant to do (train_loss is reached through __getattr__, so DDP's reducer never arms)
+                kw = {**kw, "world_size": dist.get_world_size(), "rank": dist.get_rank()}
             self._train_engine = TrainEngine(self, **kw)
         return self._train_engine
 

@@ -117,3 +117,22 @@ def test_kv24_cache_gemm_and_cross_attention(cuda_device, B, Tk):
     out = ops.unsplit(ops.attention_decode_kv24(q, kv24, Tk, Tk, B, H)).double()
     ref = _ref_decode(q, want[:, :D], want[:, D:], B, H, dh, Tk)
     assert (out - ref).abs().max().item() <= 2e-5 * ref.abs().max().item() + 1e-6
+
+
+@pytest.mark.parametrize("B,Tq,Tk,H", [(3, 256, 16, 8), (2, 330, 16, 8), (5, 100, 7, 8), (130, 256, 16, 8), (1, 31, 1, 4)])
+def test_fusion_attention_fewkeys_matches_fp64(cuda_device, B, Tq, Tk, H):
+    """Fusion Attention shape class (common/attention.py:49-71: 8 heads x 64, image tokens over the 16 retrieved layouts):
+    the tile kernel with staged, coalesced stores against float64 attention; q / k / v are column slices of wider
+    projections like in the engine (q [B*Tq, 512], kv [B*Tk, 1024])."""
+    from ralf_b200 import ops
+
+    dh, Dm = 64, H * 64
+    g = torch.Generator(device=cuda_device).manual_seed(B * 1000 + Tq + Tk)
+    q = torch.randn(B * Tq, Dm, device=cuda_device, generator=g)
+    kv = torch.randn(B * Tk, 2 * Dm, device=cuda_device, generator=g)
+    out = ops.attention(q, kv[:, :Dm], kv[:, Dm:], B, H, Tq, Tk, dh)
+    sp = lambda t, T: t.double().view(B, T, H, dh).transpose(1, 2)
+    ref = (torch.softmax(sp(q, Tq) @ sp(kv[:, :Dm], Tk).transpose(-1, -2) * dh ** -0.5, -1) @ sp(kv[:, Dm:], Tk))
+    ref = ref.transpose(1, 2).reshape(B * Tq, Dm)
+    err = (ops.unsplit(out).double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-5, err
