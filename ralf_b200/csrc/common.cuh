@@ -18,6 +18,17 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// begin while its predecessor drains; pdl_wait() blocks until every prerequisite grid has completed and its writes are
+// visible, so a kernel may do anything that touches no global memory (barrier init, TMEM allocation, descriptor
+// prefetch) before it.  Every kernel launched through launch_pdl() MUST execute pdl_wait() in at least one thread
+// before exiting (completion order of the chain), and before its first dependent global access in every thread that
+// makes one.  pdl_trigger() lets the NEXT kernel's CTAs become resident early.  Both are no-ops for plain launches.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // Counter-based dropout masks (training): element `idx` of dropout site `site` in the step whose
 // seed sits in device memory (so a captured CUDA graph draws fresh masks on every replay) is kept iff the top 24 bits
 // of SplitMix64(seed ^ site-constant, counter idx) reach the threshold.  Forward and backward kernels recompute the

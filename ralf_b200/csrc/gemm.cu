@@ -348,6 +348,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const int splits, const long long split_stride) {
   using Cfg = GemmCfg<BN, NPASS>;
   constexpr int P = Cfg::P;
+  pdl_trigger();  // the next kernel of the stream may become resident and run its own prologue while this one works
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
@@ -415,6 +416,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tempty_bar[b], BN >= 64 ? 256 : 128);
     }
     fence_mbar_init();
+    pdl_wait();  // PDL: the A operand is the previous kernel's output (everything above touched no global memory)
     // Prologue prefetch: the first ring of TMA loads needs nothing but the barriers this thread just initialised,
     // so it is issued BEFORE the TMEM allocation / block sync below (hides ~0.5 us on latency-bound decode GEMMs).
     {
@@ -429,6 +431,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // every thread: epilogue operands (residual) and outputs are ordered after the previous kernel too
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -772,9 +775,9 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
   if (occ > occ_cap) occ = occ_cap;
   const long long max_ctas = static_cast<long long>(sms) * occ;
   dim3 grid(static_cast<unsigned>(num_tiles < max_ctas ? num_tiles : max_ctas));
-  gemm_bf16_kernel<BN, NPASS><<<grid, 320, Cfg::smem_bytes(stages), st>>>(ta, tb, ep, M, N, K, stages, cg, splits,
-                                                                          split_stride);
-  return set_cuda_error(cudaGetLastError());
+  const cudaError_t le = launch_pdl(gemm_bf16_kernel<BN, NPASS>, grid, dim3(320), Cfg::smem_bytes(stages), st, ta, tb, ep, M,
+                                    N, K, stages, cg, splits, split_stride);
+  return set_cuda_error(le != cudaSuccess ? le : cudaGetLastError());
 }
 
 }  // namespace ralf

@@ -44,6 +44,8 @@ __global__ void layernorm_kernel(const float* __restrict__ x, long long in_ld, c
                                  const float* __restrict__ beta, float eps, int M, int D,
                                  float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_split,
                                  long long out_plane) {
+  pdl_trigger();
+  pdl_wait();  // every thread, before the early return: keeps the completion order of a PDL chain
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -186,13 +188,14 @@ attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__
 // output stores here (HBM floor 20 us, measured 198 us per 128 canvases); this one keeps a 32-query x H-head tile per
 // CTA (warp = head, lane = query), reads K/V through L1 broadcast loads, and stages the output tile in shared memory
 // so that every global store is a full 128/256-byte row segment.
-//   q row (b, t): q + (b*Tq + t)*ldq + h*64 ; k/v row (b, j): base + (b*Tk + j)*ldk + h*64 ; Tk <= 16, no masks.
+// Also the FIDNetV3 layout encoder (fid/model.py:26-33: B*16 sequences of <= 11 tokens, 4 heads x 64, key padding).
+//   q row (b, t): q + (b*Tq + t)*ldq + h*64 ; k/v row (b, j): base + (b*Tk + j)*ldk + h*64 ; Tk <= 16, not causal.
 // ------------------------------------------------------------------------------------------------
 constexpr int kFewKeysMax = 16;
 __global__ void __launch_bounds__(256)
 attention_fewkeys_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, const float* __restrict__ v,
-                         int ldk, int Tq, int Tk, float scale, __nv_bfloat16* __restrict__ out_split, long long out_plane,
-                         float* __restrict__ out_f32, int ldo) {
+                         int ldk, const unsigned char* __restrict__ mask, int Tq, int Tk, float scale,
+                         __nv_bfloat16* __restrict__ out_split, long long out_plane, float* __restrict__ out_f32, int ldo) {
   constexpr int DH = 64, PITCH = DH + 4;  // 68 words: float4 accesses of 8 consecutive rows cover all 32 banks
   extern __shared__ __align__(16) float stage[];  // [H][32][PITCH]
   const int b = blockIdx.y, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -224,6 +227,7 @@ attention_fewkeys_kernel(const float* __restrict__ q, int ldq, const float* __re
         acc = fmaf(qr[i], f.x, acc); acc = fmaf(qr[i + 1], f.y, acc);
         acc = fmaf(qr[i + 2], f.z, acc); acc = fmaf(qr[i + 3], f.w, acc);
       }
+      if (mask && mask[static_cast<long long>(b) * Tk + j]) acc = -INFINITY;  // key is padding
       mx = fmaxf(mx, acc);
     }
     s[j] = acc;
@@ -397,6 +401,8 @@ attention_decode_stream_kernel(const float* __restrict__ q, int ldq, const float
   constexpr int CPL = DH / 4;    // lanes per key row (16 B each)
   constexpr int KPI = 32 / CPL;  // keys per warp-wide load
   constexpr int UN = 32 / KPI;   // loads per batch of 32 keys
+  pdl_trigger();
+  pdl_wait();
   const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x;
   if (h >= H) return;
@@ -493,6 +499,8 @@ attention_decode_kv24_kernel(const float* __restrict__ q, int ldq, const uint8_t
                              int Tk, int H, float scale, __nv_bfloat16* __restrict__ out_split, long long out_plane,
                              int ldo) {
   constexpr int DH = 32, CPL = 8, KPI = 4, UN = 8, ROW = 1536;
+  pdl_trigger();
+  pdl_wait();
   const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x;
   if (h >= H) return;
@@ -872,6 +880,8 @@ __global__ void argmax_next_kernel(const float* __restrict__ logits, int ldl, in
                                    int pos, unsigned char* __restrict__ pad_mask, int mask_ld, long long pad_id,
                                    const float* __restrict__ emb, int D, float scale, const float* __restrict__ pe,
                                    float* __restrict__ x_next) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   __shared__ float bv[8];
@@ -927,6 +937,8 @@ __global__ void __launch_bounds__(256) sample_next_kernel(
   __shared__ float val[kSampleSlots];
   __shared__ int idx[kSampleSlots];
   __shared__ int win;
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x, tid = threadIdx.x;
   const int f = forced ? forced[static_cast<long long>(b) * forced_ld + step] : -1;
   if (f >= 0) {
@@ -1112,9 +1124,9 @@ extern "C" int ralf_layernorm(const float* x, long long in_ld, const float* gamm
   if (M <= 0 || D <= 0 || D > 1024 || (D & 31)) return RALF_ERR_SHAPE;
 #define RALF_LN_CASE(P)                                                                                          \
   if (D == 32 * P) {                                                                                            \
-    layernorm_kernel<P><<<(M + 7) / 8, 256, 0, ST(stream)>>>(x, in_ld, gamma, beta, eps, M, D, out_f32,         \
-                                                             BF(out_split), out_plane);                         \
-    return set_cuda_error(cudaGetLastError());                                                                  \
+    const cudaError_t e = launch_pdl(layernorm_kernel<P>, dim3((M + 7) / 8), dim3(256), 0, ST(stream), x, in_ld, \
+                                     gamma, beta, eps, M, D, out_f32, BF(out_split), out_plane);                \
+    return set_cuda_error(e != cudaSuccess ? e : cudaGetLastError());                                           \
   }
   RALF_LN_CASE(8)   // d_model = 256: every LayerNorm of the RALF path
   RALF_LN_CASE(1) RALF_LN_CASE(2) RALF_LN_CASE(4) RALF_LN_CASE(16) RALF_LN_CASE(32)
@@ -1137,7 +1149,7 @@ static int attention_impl(const float* q, int ldq, const float* k, const float* 
   }
   // few keys, wide heads (fusion Attention over the 16 retrieved layouts): tile kernel with coalesced stores
   static const bool fewkeys_on = !(getenv("RALF_ATTN_FEWKEYS") && atoi(getenv("RALF_ATTN_FEWKEYS")) == 0);
-  if (fewkeys_on && !da.thresh24 && head_dim == 64 && Tk <= kFewKeysMax && H <= 8 && !key_padding_mask && !causal &&
+  if (fewkeys_on && !da.thresh24 && head_dim == 64 && Tk <= kFewKeysMax && H <= 8 && !causal &&
       (ldo & 3) == 0 && (out_plane & 3) == 0) {
     static bool attr_set = false;
     const int smem = H * 32 * (64 + 4) * static_cast<int>(sizeof(float));
@@ -1147,8 +1159,8 @@ static int attention_impl(const float* q, int ldq, const float* k, const float* 
       attr_set = true;
     }
     dim3 g2((Tq + 31) / 32, B);
-    attention_fewkeys_kernel<<<g2, 32 * H, smem, ST(stream)>>>(q, ldq, k, v, ldk, Tq, Tk, scale, BF(out_split), out_plane,
-                                                              out_f32, ldo);
+    attention_fewkeys_kernel<<<g2, 32 * H, smem, ST(stream)>>>(q, ldq, k, v, ldk, key_padding_mask, Tq, Tk, scale,
+                                                              BF(out_split), out_plane, out_f32, ldo);
     return set_cuda_error(cudaGetLastError());
   }
   const int threads = Tq >= 128 ? 128 : ((Tq + 31) / 32) * 32;
@@ -1193,15 +1205,16 @@ static int attention_decode_impl(const float* q, int ldq, const float* k, const 
   static const bool two_pass = getenv("RALF_DECODE_2PASS") && atoi(getenv("RALF_DECODE_2PASS")) != 0;
   const bool plain = !key_padding_mask && !knew;
   if (H <= 8 && (plain ? Tk >= 64 : !two_pass)) {
+    cudaError_t e;
     if (head_dim == 32)
-      attention_decode_stream_kernel<32><<<B, 32 * H, 0, ST(stream)>>>(
-          q, ldq, k, v, kv_bstride, ldk, Tk, H, scale, BF(out_split), out_plane, ldo, key_padding_mask, mask_ld, knew,
-          vnew, ldnew, kc_w, vc_w);
+      e = launch_pdl(attention_decode_stream_kernel<32>, dim3(B), dim3(32 * H), 0, ST(stream), q, ldq, k, v, kv_bstride,
+                     ldk, Tk, H, scale, BF(out_split), out_plane, ldo, key_padding_mask, mask_ld, knew, vnew, ldnew, kc_w,
+                     vc_w);
     else
-      attention_decode_stream_kernel<64><<<B, 32 * H, 0, ST(stream)>>>(
-          q, ldq, k, v, kv_bstride, ldk, Tk, H, scale, BF(out_split), out_plane, ldo, key_padding_mask, mask_ld, knew,
-          vnew, ldnew, kc_w, vc_w);
-    return set_cuda_error(cudaGetLastError());
+      e = launch_pdl(attention_decode_stream_kernel<64>, dim3(B), dim3(32 * H), 0, ST(stream), q, ldq, k, v, kv_bstride,
+                     ldk, Tk, H, scale, BF(out_split), out_plane, ldo, key_padding_mask, mask_ld, knew, vnew, ldnew, kc_w,
+                     vc_w);
+    return set_cuda_error(e != cudaSuccess ? e : cudaGetLastError());
   }
   const size_t smem = static_cast<size_t>((Tk + 31) & ~31) * sizeof(float);
   const int grid = B * H;
@@ -1231,9 +1244,10 @@ extern "C" int ralf_attention_decode_kv24(const float* q, int ldq, const void* k
   if (!q || !kv24 || !out_split) return RALF_ERR_NULL;
   if (B <= 0 || H != 8 || Tk <= 0) return RALF_ERR_SHAPE;  // row format: 8 heads x 32 (d_model 256)
   if ((ldq & 3) || (reinterpret_cast<uintptr_t>(kv24) & 15)) return RALF_ERR_ALIGN;
-  attention_decode_kv24_kernel<<<B, 32 * H, 0, ST(stream)>>>(q, ldq, reinterpret_cast<const uint8_t*>(kv24), kv_bstride,
-                                                             Tk, H, scale, BF(out_split), out_plane, ldo);
-  return set_cuda_error(cudaGetLastError());
+  const cudaError_t e = launch_pdl(attention_decode_kv24_kernel, dim3(B), dim3(32 * H), 0, ST(stream), q, ldq,
+                                   reinterpret_cast<const uint8_t*>(kv24), kv_bstride, Tk, H, scale, BF(out_split),
+                                   out_plane, ldo);
+  return set_cuda_error(e != cudaSuccess ? e : cudaGetLastError());
 }
 
 extern "C" int ralf_attention_decode_append(const float* qkv, int ldqkv, float* kcache, float* vcache, int S, int pos,
@@ -1341,9 +1355,9 @@ extern "C" int ralf_argmax_next(const float* logits, int ldl, int B, int V, cons
                                 void* stream) {
   if (!logits || !allowed || !seq) return RALF_ERR_NULL;
   if (B <= 0 || V <= 0) return RALF_ERR_SHAPE;
-  argmax_next_kernel<<<B, 128, 0, ST(stream)>>>(logits, ldl, V, allowed, seq, seq_ld, pos, pad_mask, mask_ld, pad_id,
-                                               emb, D, scale, pe, x_next);
-  return set_cuda_error(cudaGetLastError());
+  const cudaError_t e = launch_pdl(argmax_next_kernel, dim3(B), dim3(128), 0, ST(stream), logits, ldl, V, allowed, seq, seq_ld,
+                                   pos, pad_mask, mask_ld, pad_id, emb, D, scale, pe, x_next);
+  return set_cuda_error(e != cudaSuccess ? e : cudaGetLastError());
 }
 
 extern "C" int ralf_sample_next(const float* logits, int ldl, int B, int V, const unsigned char* allowed,
@@ -1359,10 +1373,10 @@ extern "C" int ralf_sample_next(const float* logits, int ldl, int B, int V, cons
   if (mode == 2 && top_k < 1) return RALF_ERR_SHAPE;
   if (mode == 3 && !(top_p > 0.f && top_p <= 1.f)) return RALF_ERR_SHAPE;
   if (x_next && (!emb || !pe)) return RALF_ERR_NULL;
-  sample_next_kernel<<<B, 256, 0, ST(stream)>>>(logits, ldl, V, allowed, forced, forced_ld, step, mode, temperature, top_k,
-                                               top_p, uniform, noise, noise_ld, seq, seq_ld, pos, pad_mask, mask_ld,
-                                               pad_id, emb, D, scale, pe, x_next);
-  return set_cuda_error(cudaGetLastError());
+  const cudaError_t e = launch_pdl(sample_next_kernel, dim3(B), dim3(256), 0, ST(stream), logits, ldl, V, allowed, forced,
+                                   forced_ld, step, mode, temperature, top_k, top_p, uniform, noise, noise_ld, seq, seq_ld,
+                                   pos, pad_mask, mask_ld, pad_id, emb, D, scale, pe, x_next);
+  return set_cuda_error(e != cudaSuccess ? e : cudaGetLastError());
 }
 
 extern "C" int ralf_kv_append(const float* qkv, int B, int D, float* kcache, float* vcache, int S, int pos,

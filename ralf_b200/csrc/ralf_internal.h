@@ -13,6 +13,25 @@ int set_cuda_error(cudaError_t e);
 int make_kmajor_tmap(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t K, uint64_t rows,
                      uint64_t planes, uint64_t ld, uint64_t plane_stride, uint32_t box_rows);
 int num_sms();
+// RALF_PDL=0 turns programmatic dependent launch off (A/B runs); default on.
+bool pdl_enabled();
+
+// kernel<<<grid, block, smem, st>>>(args...) with the programmatic-stream-serialization attribute (see common.cuh).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 // attention_tc.cu: tcgen05 attention for (head_dim 32, no mask, 64 <= Tk <= 256); 1 = launched, 0 = not applicable.
 int attention_tc_try(const float* q, int ldq, const float* k, const float* v, int ldk, const unsigned char* mask, int B,
                      int H, int Tq, int Tk, int head_dim, int causal, float scale, void* out_split,

@@ -1,4 +1,5 @@
 // Error plumbing and device queries shared by all entry points.
+#include <stdlib.h>
 #include <string.h>
 
 #include "ralf_internal.h"
@@ -22,6 +23,11 @@ int num_sms() {
     if (sms <= 0) sms = 148;
   }
   return sms;
+}
+
+bool pdl_enabled() {
+  static const bool on = !(getenv("RALF_PDL") && atoi(getenv("RALF_PDL")) == 0);
+  return on;
 }
 }  // namespace ralf
 

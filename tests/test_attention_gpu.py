@@ -136,3 +136,22 @@ def test_fusion_attention_fewkeys_matches_fp64(cuda_device, B, Tq, Tk, H):
     ref = ref.transpose(1, 2).reshape(B * Tq, Dm)
     err = (ops.unsplit(out).double() - ref).abs().max().item() / ref.abs().max().item()
     assert err < 2e-5, err
+
+
+@pytest.mark.parametrize("N,T,H", [(48, 11, 4), (2080, 13, 4), (7, 16, 4)])
+def test_fidnet_attention_fewkeys_with_padding_matches_fp64(cuda_device, N, T, H):
+    """FIDNetV3 shape class (fid/model.py:26-33): many short sequences, 4 heads x 64, key-padding mask, fused QKV."""
+    from ralf_b200 import ops
+
+    dh, Dm = 64, H * 64
+    g = torch.Generator(device=cuda_device).manual_seed(N + T)
+    qkv = torch.randn(N * T, 3 * Dm, device=cuda_device, generator=g)
+    n_valid = torch.randint(1, T + 1, (N,), device=cuda_device, generator=g)
+    pad = (torch.arange(T, device=cuda_device)[None] >= n_valid[:, None]).to(torch.uint8).contiguous()
+    out = ops.attention(qkv[:, :Dm], qkv[:, Dm:2 * Dm], qkv[:, 2 * Dm:], N, H, T, T, dh, mask=pad)
+    sp = lambda t: t.double().view(N, T, H, dh).transpose(1, 2)
+    s = sp(qkv[:, :Dm]) @ sp(qkv[:, Dm:2 * Dm]).transpose(-1, -2) * dh ** -0.5
+    s = s.masked_fill(pad.bool()[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ sp(qkv[:, 2 * Dm:])).transpose(1, 2).reshape(N * T, Dm)
+    err = (ops.unsplit(out).double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-5, err
