@@ -13,7 +13,7 @@ int set_cuda_error(cudaError_t e);
 int make_kmajor_tmap(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t K, uint64_t rows,
                      uint64_t planes, uint64_t ld, uint64_t plane_stride, uint32_t box_rows);
 int num_sms();
-// RALF_PDL=0 turns programmatic dependent launch off (A/B runs); default on.
+// RALF_PDL=1 turns programmatic dependent launch on (A/B runs); default off, see runtime.cu.
 bool pdl_enabled();
 
 // kernel<<<grid, block, smem, st>>>(args...) with the programmatic-stream-serialization attribute (see common.cuh).
