@@ -88,6 +88,56 @@ def build_cache_table(retriever: GpuRetriever, queries: torch.Tensor, query_ids:
 
 
 # --------------------------------------------------------------------------------------------------------------------
+# f1: per-example element ordering (data.transforms of experiment/ralf.yaml:8 = [image, sort_label, sort_lexicographic])
+# --------------------------------------------------------------------------------------------------------------------
+def _reorder(example: dict, order: Sequence[int]) -> dict:
+    """Apply ``order`` to every list field of the example (helpers/hfds_instance_wise_transforms.py:25-37; the keys
+    ``transforms``, ``retrieved`` and ``id`` are left alone)."""
+    for key, value in example.items():
+        if key not in ("transforms", "retrieved", "id") and isinstance(value, list):
+            example[key] = [value[i] for i in order]
+    return example
+
+
+def sort_label_transform(example: dict) -> dict:
+    """Stable sort of the elements by label id (:58-64)."""
+    labels = example["label"]
+    return _reorder(example, sorted(range(len(labels)), key=labels.__getitem__)) if labels else example
+
+
+def lexicographic_order(example: dict) -> list:
+    """Element indexes sorted by (top, left) of the boxes (:67-78)."""
+    as_float = lambda x: x.tolist() if torch.is_tensor(x) else x  # noqa: E731
+    left = [as_float(cx - w / 2.0) for cx, w in zip(example["center_x"], example["width"])]
+    top = [as_float(cy - h / 2.0) for cy, h in zip(example["center_y"], example["height"])]
+    return sorted(range(len(top)), key=lambda i: (top[i], left[i]))
+
+
+def sort_lexicographic_transform(example: dict) -> dict:
+    return _reorder(example, lexicographic_order(example)) if len(example["center_x"]) else example
+
+
+def shuffle_transform(example: dict) -> dict:
+    """Random element order from python's ``random`` like the reference (:47-55)."""
+    import random
+
+    n = len(example["label"])
+    return _reorder(example, random.sample(list(range(n)), n)) if n else example
+
+
+INSTANCE_TRANSFORMS = {"sort_label": sort_label_transform, "sort_lexicographic": sort_lexicographic_transform,
+                       "shuffle": shuffle_transform}
+
+
+def apply_transforms(example: dict, names: Sequence[str] = ("sort_label", "sort_lexicographic")) -> dict:
+    """``data.transforms`` minus ``image`` (PIL -> tensor conversion happens where the images are decoded)."""
+    for n in names:
+        if n != "image":
+            example = INSTANCE_TRANSFORMS[n](example)
+    return example
+
+
+# --------------------------------------------------------------------------------------------------------------------
 # f1: GPU-resident exemplar layouts
 # --------------------------------------------------------------------------------------------------------------------
 class LayoutTable:
@@ -144,9 +194,10 @@ class RetrievalCollator:
     "online retrieval") by one device gather."""
 
     def __init__(self, layouts: LayoutTable, max_seq_length: int, top_k: int = 16, table_idx: Optional[dict] = None,
-                 retriever: Optional[GpuRetriever] = None, int_ids: bool = False) -> None:
+                 retriever: Optional[GpuRetriever] = None, int_ids: bool = False, transforms: Sequence[str] = ()) -> None:
         self.layouts, self.E, self.top_k = layouts, max_seq_length, top_k
         self.table_idx, self.retriever, self.int_ids = table_idx, retriever, int_ids
+        self.transforms = tuple(transforms)  # e.g. ("sort_label", "sort_lexicographic") when the dataset is raw
 
     def indices(self, ids: Sequence) -> torch.Tensor:
         rows = []
@@ -161,6 +212,8 @@ class RetrievalCollator:
         """Padding / masks of the query samples: list fields padded with 0 to ``max_seq_length``, ``mask`` = valid-first;
         empty layouts get the reference's dummy element (global_variables.DUMMY_LAYOUT)."""
         B, E = len(examples), self.E
+        if self.transforms:
+            examples = [apply_transforms(dict(ex), self.transforms) for ex in examples]
         out: dict[str, Any] = {"label": torch.zeros((B, E), dtype=torch.int64), "mask": torch.zeros((B, E), dtype=torch.bool)}
         for key in GEO:
             out[key] = torch.zeros((B, E), dtype=torch.float32)

@@ -131,3 +131,38 @@ def test_task_preprocessor_reference_properties(task):
         assert pre.name_to_id("pad") not in seq[~pad_mask].tolist()
         assert (seq[:, 0] == pre.name_to_id("bos")).all() and (seq[:, 1] == pre.name_to_id(pre.TASK)).all()
         assert ((seq == pre.name_to_id("eos")).sum(dim=1) == 1).all()
+
+
+def test_instance_transforms_reference_kats():
+    """Known-answer tests of the reference: tests/train/helpers/test_hfds_instance_wise_transforms.py:7-37."""
+    from ralf_b200 import data as D
+
+    assert D.sort_label_transform({"label": [1, 2, 0], "data": ["a", "b", "c"]}) == {"label": [0, 1, 2], "data": ["c", "a", "b"]}
+    assert D.sort_label_transform({"label": [1, 0], "data": [[0, 1], [2, 3]]}) == {"label": [0, 1], "data": [[2, 3], [0, 1]]}
+    inputs = {"center_x": [0.5, 0.5, 0.4], "center_y": [0.5, 0.3, 0.3], "width": [1.0, 0.5, 0.5], "height": [0.8, 0.6, 0.6]}
+    assert D.lexicographic_order(inputs) == [2, 1, 0]
+    ex = {"id": "x", "label": [2, 0, 2], "center_x": [0.5, 0.5, 0.2], "center_y": [0.5, 0.5, 0.5], "width": [0.2, 0.2, 0.2],
+          "height": [0.2, 0.2, 0.6], "retrieved": [1, 2, 3]}
+    out = D.apply_transforms(dict(ex), ("image", "sort_label", "sort_lexicographic"))
+    assert out["id"] == "x" and out["retrieved"] == [1, 2, 3]
+    assert out["center_x"] == [0.2, 0.5, 0.5] and out["label"] == [2, 0, 2]  # the second sort wins, like in the reference
+    assert D.shuffle_transform({"label": []}) == {"label": []}
+    col = D.RetrievalCollator(layouts=None, max_seq_length=4, top_k=1, table_idx={}, transforms=("sort_label",))
+    got = col.collate_main([{"id": "1", "label": [3, 1], "center_x": [.1, .2], "center_y": [.3, .4], "width": [.5, .6], "height": [.7, .8]}])
+    assert got["label"][0].tolist() == [1, 3, 0, 0] and got["center_x"][0].tolist() == pytest.approx([.2, .1, 0, 0])
+
+
+def test_linear_bucketizer_cycle_property():
+    """Reference tests/train/helpers/test_bucketizer.py:26-38: decode(encode(x)) within half a bin, ids idempotent."""
+    from ralf_b200.tokenizer import LinearBucketizer
+
+    g = torch.Generator().manual_seed(0)
+    for _ in range(100):
+        n_data = int(torch.randint(1, 11, (1,), generator=g))
+        n_boundaries = 2 ** int(torch.randint(1, 9, (1,), generator=g))
+        x = torch.rand((n_data, 4), generator=g)
+        b = LinearBucketizer(n_boundaries)
+        ids = b.encode(x)
+        x_cycle = b.decode(ids)
+        assert (torch.abs(x - x_cycle) <= 1 / (2 * n_boundaries) + 1e-7).all()
+        assert (ids == b.encode(x_cycle)).all()
