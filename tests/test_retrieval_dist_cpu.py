@@ -62,3 +62,48 @@ def test_shard_bounds_cover_exactly():
         for w in (1, 2, 3, 8):
             b = [shard_bounds(n, w, r) for r in range(w)]
             assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+
+
+class _StubModel(torch.nn.Module):
+    """Host-side stand-in with the surface checkpoint.evaluate() uses (preprocess / train_loss / device / eval)."""
+
+    def __init__(self):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.zeros(1))
+
+    @property
+    def device(self):
+        return self.w.device
+
+    def preprocess(self, batch):
+        return {"x": batch["x"]}, {"y": batch["x"]}
+
+    def train_loss(self, inputs, targets, test=False):
+        assert test and not torch.is_grad_enabled()
+        return {}, {"nll_loss": inputs["x"].float().mean()}
+
+
+def _eval_worker(rank, world, port, values, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ralf_b200.checkpoint import evaluate
+
+    batches = [{"x": torch.tensor([v])} for v in values]
+    out = evaluate(_StubModel(), batches, rank=rank, world_size=world)
+    ret[rank] = out["nll_loss"]
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_evaluate_returns_global_mean_on_every_rank():
+    """the validation set is sharded over ranks (the reference evaluates all of it on every rank) and the
+    mean is all-reduced; world_size 2 over gloo, an odd number of batches so the shards are uneven."""
+    values = [1.0, 2.0, 4.0, 8.0, 16.0]
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_eval_worker, args=(2, port, values, ret), nprocs=2, join=True)
+    want = sum(values) / len(values)
+    assert abs(ret[0] - want) < 1e-6 and abs(ret[1] - want) < 1e-6
