@@ -341,8 +341,13 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpi& ep, const uint
     }
 }
 
-template <int BN, int NPASS>
-__global__ void __launch_bounds__(320, 1)
+// MINB = minimum resident CTAs per SM the register allocation must allow.  ptxas (12.9) gives the MINB = 1 build 165
+// registers per thread: 52.8 k per CTA, i.e. never a second CTA on an SM whatever the shared-memory ring -- the short-K,
+// epilogue-bound shapes then run 8 epilogue warps per SM at half the HBM roofline.  MINB = 2 compiles to 96 registers with
+// 40-48 bytes of spill (profiles/r1_gemm_minb2_ptxas.md) and lets cudaOccupancyMaxActiveBlocksPerMultiprocessor return 2
+// for the small rings.  Not yet measured on hardware (round-1 GPU budget was spent): opt-in, RALF_GEMM_MINB=2.
+template <int BN, int NPASS, int MINB>
+__global__ void __launch_bounds__(320, MINB)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmEpi ep, const int M, const int N, const int K, const int STAGES, const ConvGeom cg,
                  const int splits, const long long split_stride) {
@@ -731,17 +736,17 @@ int make_kmajor_tmap(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t
   return 0;
 }
 
-template <int BN, int NPASS>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi& ep, int M, int N, int K,
-                       cudaStream_t st, const ConvGeom& cg, int splits = 1, long long split_stride = 0) {
+template <int BN, int NPASS, int MINB>
+static int launch_gemm_v(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi& ep, int M, int N, int K,
+                         cudaStream_t st, const ConvGeom& cg, int splits, long long split_stride) {
   using Cfg = GemmCfg<BN, NPASS>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, NPASS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::smem_bytes(Cfg::MAX_STAGES));
     if (e != cudaSuccess) return set_cuda_error(e);
     // several CTAs per SM only materialise when the SM is configured with the full shared-memory carve-out
-    e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, NPASS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, NPASS, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return set_cuda_error(e);
     attr_set = true;
@@ -759,13 +764,13 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
   int stages = nkb_per < Cfg::MAX_STAGES ? nkb_per : Cfg::MAX_STAGES;
   if (multi_tile && stages < min_stages) stages = min_stages < Cfg::MAX_STAGES ? min_stages : Cfg::MAX_STAGES;
   // Short-K GEMMs are bound by their epilogue's memory traffic, not by the MMAs: their small smem ring lets several
-  // persistent CTAs share an SM (limited by shared memory, 512 TMEM columns and an env override for A/B runs), which
-  // multiplies the loads / stores in flight per SM.
+  // persistent CTAs share an SM (limited by registers -- see MINB above --, shared memory, 512 TMEM columns and an env
+  // override for A/B runs), which multiplies the loads / stores in flight per SM.
   static const int occ_cap = getenv("RALF_GEMM_OCC") ? atoi(getenv("RALF_GEMM_OCC")) : 4;
   static int occ_cache[16] = {0};
   int occ = occ_cache[stages];
   if (occ == 0) {
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gemm_bf16_kernel<BN, NPASS>, 320,
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gemm_bf16_kernel<BN, NPASS, MINB>, 320,
                                                                   Cfg::smem_bytes(stages));
     if (e != cudaSuccess) return set_cuda_error(e);
     if (occ > static_cast<int>(512 / Cfg::TMEM_COLS)) occ = 512 / Cfg::TMEM_COLS;
@@ -775,9 +780,17 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
   if (occ > occ_cap) occ = occ_cap;
   const long long max_ctas = static_cast<long long>(sms) * occ;
   dim3 grid(static_cast<unsigned>(num_tiles < max_ctas ? num_tiles : max_ctas));
-  const cudaError_t le = launch_pdl(gemm_bf16_kernel<BN, NPASS>, grid, dim3(320), Cfg::smem_bytes(stages), st, ta, tb, ep, M,
-                                    N, K, stages, cg, splits, split_stride);
+  const cudaError_t le = launch_pdl(gemm_bf16_kernel<BN, NPASS, MINB>, grid, dim3(320), Cfg::smem_bytes(stages), st, ta, tb,
+                                    ep, M, N, K, stages, cg, splits, split_stride);
   return set_cuda_error(le != cudaSuccess ? le : cudaGetLastError());
+}
+
+template <int BN, int NPASS>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi& ep, int M, int N, int K,
+                       cudaStream_t st, const ConvGeom& cg, int splits = 1, long long split_stride = 0) {
+  static const bool minb2 = getenv("RALF_GEMM_MINB") && atoi(getenv("RALF_GEMM_MINB")) == 2;
+  if (minb2) return launch_gemm_v<BN, NPASS, 2>(ta, tb, ep, M, N, K, st, cg, splits, split_stride);
+  return launch_gemm_v<BN, NPASS, 1>(ta, tb, ep, M, N, K, st, cg, splits, split_stride);
 }
 
 }  // namespace ralf
