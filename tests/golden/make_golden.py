@@ -10,6 +10,8 @@ Outputs (committed):
   autoreg_cgl_350x240.npz  Autoreg baseline, B=1 (BASELINE config 1)
   tasks_cgl_256.npz     constrained tasks c / cwh / partial / refinement through the reference's get_condition,
                         task preprocessors, DECODE_SPACE_RESTRICTION and greedy sample() (same weights/batch as ralf_cgl_256)
+  optim_groups_ralf_cgl.json   BaseModel.optim_groups as train.py calls it -> [(lr, weight_decay, [parameter names])]
+  schema_ralf_pku.json / tokenizer_pku.npz   PKU (3 labels) variants of the state-dict schema and tokenizer outputs
   sampling_filters.npz  helpers/sampling.py on random logits: the post-filter probabilities handed to torch.multinomial
 Each npz: tokenizer outputs (seq, mask, token_mask), constraint sequence, encoder memory, teacher-forced
 logits, nll loss, greedy token ids + per-step masked logits, decoded layout.
@@ -203,6 +205,19 @@ def run_optim_groups(model):
     print("optim_groups", [(g["lr"], g["weight_decay"], len(g["params"])) for g in out])
 
 
+def run_pku_contract():
+    """BASELINE configs[2] (PKU, 3 labels): state-dict schema of the reference class and the tokenizer's outputs."""
+    ralf, tok, _ = rb.make_ralf("pku")
+    with open(os.path.join(OUT, "schema_ralf_pku.json"), "w") as f:
+        json.dump(schema_of(ralf), f)
+    b = synth.synth_batch(3, 8, 8, 10, 1, tok.N_label, seed=21)
+    enc = tok.encode({k: b[k] for k in ["label", "mask", "center_x", "center_y", "width", "height"]})
+    np.savez_compressed(os.path.join(OUT, "tokenizer_pku.npz"), seq=enc["seq"].numpy(), mask=enc["mask"].numpy(),
+                        token_mask=tok.token_mask.numpy(),
+                        special=np.array([tok.name_to_id("pad"), tok.name_to_id("bos"), tok.name_to_id("eos")]))
+    print("pku contract", tok.N_total)
+
+
 def main():
     rb.bootstrap("/tmp/ralf_ref_work")
     torch.backends.mha.set_fastpath_enabled(False)
@@ -214,6 +229,7 @@ def main():
         run_tasks(tok, "tasks_cgl_256", B=2, H=256, W=256, seed=1)
         run_sampling_filters()
         run_optim_groups(ralf)
+        run_pku_contract()
         return
     run(ralf, tok, "ralf_cgl_256", B=2, H=256, W=256, seed=1, is_ralf=True)
     run_tasks(tok, "tasks_cgl_256", B=2, H=256, W=256, seed=1)

@@ -107,3 +107,28 @@ def test_optim_groups_match_reference():
     assert mine == ref
     plain = model.optim_groups(base_lr=1e-4, weight_decay=1e-4)
     assert len(plain) == 2 and sum(len(g["params"]) for g in plain) == sum(len(g["params"]) for g in ref)
+
+
+def test_state_dict_contract_pku():
+    """BASELINE configs[2] names the PKU dataset (3 labels -> vocabulary 518, constraint vocabulary 548): key names, order,
+    shapes and dtypes of the reference class built for PKU (tests/golden/schema_ralf_pku.json, dumped from the reference),
+    and the PKU tokenizer's ids / per-position mask (tests/golden/tokenizer_pku.npz)."""
+    import numpy as np
+
+    from oracle import synth
+    from ralf_b200 import generator as G
+
+    tok = helpers.make_tokenizer("pku")
+    model = G.RALF(features=None, tokenizer=tok, dataset_name="pku", max_seq_length=10, top_k=16, auxilary_task="uncond")
+    ref = helpers.load_schema("ralf_pku")
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(ref.keys())
+    for k, v in sd.items():
+        assert list(v.shape) == ref[k]["shape"] and str(v.dtype).replace("torch.", "") == ref[k]["dtype"], k
+    z = np.load(helpers.GOLDEN + "/tokenizer_pku.npz")
+    b = synth.synth_batch(3, 8, 8, 10, 1, tok.N_label, seed=21)
+    enc = tok.encode({k: b[k] for k in ["label", "mask", "center_x", "center_y", "width", "height"]})
+    np.testing.assert_array_equal(enc["seq"].numpy(), z["seq"])
+    np.testing.assert_array_equal(enc["mask"].numpy(), z["mask"])
+    np.testing.assert_array_equal(tok.token_mask.numpy(), z["token_mask"])
+    assert [tok.name_to_id("pad"), tok.name_to_id("bos"), tok.name_to_id("eos")] == z["special"].tolist()
