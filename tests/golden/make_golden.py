@@ -216,6 +216,32 @@ def run_pku_contract():
                         token_mask=tok.token_mask.numpy(),
                         special=np.array([tok.name_to_id("pad"), tok.name_to_id("bos"), tok.name_to_id("eos")]))
     print("pku contract", tok.N_total)
+    # a small PKU forward golden: memory + greedy token ids of the reference class on 2 canvases of 128x128
+    import copy
+
+    from image2layout.train.helpers.task import get_condition
+
+    sd = synth.synth_state_dict(schema_of(ralf), seed=4)
+    ralf.load_state_dict(sd, strict=True)
+    ralf.eval()
+    B, H, W = 2, 128, 128
+    batch = synth.synth_batch(B, H, W, 10, 16, tok.N_label, seed=6)
+    with torch.no_grad():
+        cond, _ = get_condition(copy.deepcopy(batch), "uncond", tok)
+        enc_in, _ = ralf._create_encoder_inputs(cond)
+        enc_in["retrieved"] = {k: v.type_as(cond.image) for k, v in enc_in["retrieved"].items() if torch.is_tensor(v)}
+        mem = ralf._encode_into_memory(enc_in)["memory"]
+        ids = ralf.special_token_ids
+        inp = torch.full((B, 1), ids["bos"])
+        for i in range(tok.max_token_length):
+            lg = ralf.decoder(tgt=inp, tgt_key_padding_mask=(inp == ids["pad"]), is_causal=True, memory=mem)[:, i].clone()
+            lg[:, ~tok.token_mask[i]] = -float("inf")
+            inp = torch.cat([inp, lg.argmax(dim=1, keepdim=True)], dim=1)
+    np.savez_compressed(os.path.join(OUT, "ralf_pku_128.npz"), memory=mem.numpy(), gen_seq=inp[:, 1:].numpy(),
+                        seq_layout_const=enc_in["seq_layout_const"].numpy(),
+                        seq_layout_const_pad_mask=enc_in["seq_layout_const_pad_mask"].numpy(),
+                        meta=np.array(json.dumps({"B": B, "H": H, "W": W, "seed": 6, "weights_seed": 4, "E": 10, "K": 16,
+                                                  "dataset": "pku", "special": {k: int(v) for k, v in ids.items()}})))
 
 
 def main():

@@ -101,3 +101,39 @@ def test_engine_batch_matches_oracle_with_margin(cuda_device):
         top2 = torch.topk(lg_o[b, t], 2).values
         margin = float(top2[0] - top2[1]) / float(lg_o[b, t][torch.isfinite(lg_o[b, t])].abs().max())
         assert margin < LOGIT_RTOL, f"canvas {b} diverges at step {t} with oracle margin {margin:.3e}"
+
+
+def test_engine_matches_reference_golden_pku(cuda_device):
+    """BASELINE configs[2] names PKU (3 labels, vocabulary 518): memory within tolerance of the reference's own output;
+    token ids equal, a divergence tolerated only where the oracle's top-2 margin at that step is below the logit
+    tolerance (first-divergence rule)."""
+    from oracle import ralf_oracle as O
+    from oracle import synth
+    from ralf_b200.engine import Engine
+
+    z, meta = helpers.load_golden("ralf_pku_128")
+    sd = synth.synth_state_dict(helpers.load_schema("ralf_pku"), seed=meta["weights_seed"])
+    tok = helpers.make_tokenizer("pku")
+    B = meta["B"]
+    batch = synth.synth_batch(B, meta["H"], meta["W"], meta["E"], meta["K"], tok.N_label, seed=meta["seed"])
+    sc, spm = torch.from_numpy(z["seq_layout_const"]), torch.from_numpy(z["seq_layout_const_pad_mask"])
+    eng = Engine(sd, cuda_device, is_ralf=True)
+    mem, mem_s = eng.encode(helpers.image4(batch), batch["retrieved"], sc, spm)
+    e_mem = _relerr(mem.cpu().numpy(), z["memory"])
+    assert e_mem < LOGIT_RTOL, e_mem
+    sp = meta["special"]
+    seq = eng.generate(mem_s, B, mem.shape[1], tok.token_mask, sp["bos"], sp["pad"], tok.max_token_length).cpu()
+    ref = torch.from_numpy(z["gen_seq"])
+    if not torch.equal(seq, ref):
+        torch.set_num_threads(8)
+        with torch.no_grad():
+            _, lg_o = O.greedy_sample(sd, torch.from_numpy(z["memory"]), tok.token_mask, sp["bos"], sp["pad"],
+                                      tok.max_token_length, return_logits=True)
+        for b in range(B):
+            diff = (seq[b] != ref[b]).nonzero()
+            if len(diff) == 0:
+                continue
+            t = int(diff[0])
+            top2 = torch.topk(lg_o[b, t], 2).values
+            margin = float(top2[0] - top2[1]) / float(lg_o[b, t][torch.isfinite(lg_o[b, t])].abs().max())
+            assert margin < LOGIT_RTOL, f"canvas {b} diverges at step {t} with oracle margin {margin:.3e}"
