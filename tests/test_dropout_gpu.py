@@ -143,3 +143,15 @@ def test_train_step_with_dropout_gradient_matches_finite_difference(cuda_device)
     te._set_step_seed()
     l_other, _ = loss_at()
     assert abs(float(l_other) - float(loss0)) > 1e-5
+
+
+def test_device_mask_equals_cpu_restatement(cuda_device):
+    """The mask the kernels derive on the device equals oracle/dropout_oracle.py (itself checked on the CPU against the
+    host compilation of the same __host__ __device__ functions, tests/test_dropout_rng_cpu.py)."""
+    from oracle import dropout_oracle as D
+    from ralf_b200 import ops
+
+    n = 50000
+    for seed, site, p in [(1234567, 3, 0.1), (-5, 77, 0.25), (2 ** 62 + 11, 0, 0.1), (0, 200, 0.5)]:
+        dev = ops.dropout_mask(_seed(cuda_device, seed), site, p, n).cpu().numpy()
+        np.testing.assert_array_equal(dev, D.keep_mask(seed, site, p, n))
