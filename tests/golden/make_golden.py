@@ -205,6 +205,31 @@ def run_optim_groups(model):
     print("optim_groups", [(g["lr"], g["weight_decay"], len(g["params"])) for g in out])
 
 
+def run_tokenizer_edge_cases():
+    """Reference LayoutSequenceTokenizer on empty / full layouts, out-of-range and bin-edge geometry, and its decode of
+    arbitrary (also invalid) token sequences."""
+    tok, _ = rb.make_tokenizer("cgl", 10)
+    g = torch.Generator().manual_seed(0)
+    B, E = 64, 10
+    n = torch.randint(0, E + 1, (B,), generator=g)
+    n[0], n[1], n[2] = 0, E, 1
+    mask = torch.arange(E)[None] < n[:, None]
+    lay = {"label": torch.randint(0, 4, (B, E), generator=g) * mask, "mask": mask}
+    for k in ["center_x", "center_y", "width", "height"]:
+        v = torch.rand((B, E), generator=g) * 1.4 - 0.2
+        v[3, :], v[4, :], v[5, :] = 0.0, 1.0, torch.arange(E) / 128.0
+        lay[k] = v * mask
+    enc = tok.encode({k: v.clone() for k, v in lay.items()})
+    seqs = torch.randint(0, tok.N_total, (B, 50), generator=g)
+    seqs[0, :], seqs[1, :], seqs[2, 7] = tok.name_to_id("eos"), tok.name_to_id("pad"), tok.name_to_id("bos")
+    dec = tok.decode(seqs.clone())
+    keys = ["label", "mask", "center_x", "center_y", "width", "height"]
+    np.savez_compressed(os.path.join(OUT, "tokenizer_edge_cases.npz"), **{f"in_{k}": v.numpy() for k, v in lay.items()},
+                        seq=enc["seq"].numpy(), mask=enc["mask"].numpy(), dec_in=seqs.numpy(),
+                        **{f"dec_{k}": dec[k].numpy() for k in keys})
+    print("tokenizer edge cases", enc["seq"].shape)
+
+
 def run_pku_contract():
     """BASELINE configs[2] (PKU, 3 labels): state-dict schema of the reference class and the tokenizer's outputs."""
     ralf, tok, _ = rb.make_ralf("pku")
@@ -256,6 +281,7 @@ def main():
         run_sampling_filters()
         run_optim_groups(ralf)
         run_pku_contract()
+        run_tokenizer_edge_cases()
         return
     run(ralf, tok, "ralf_cgl_256", B=2, H=256, W=256, seed=1, is_ralf=True)
     run_tasks(tok, "tasks_cgl_256", B=2, H=256, W=256, seed=1)
