@@ -230,6 +230,39 @@ def run_tokenizer_edge_cases():
     print("tokenizer edge cases", enc["seq"].shape)
 
 
+def edge_case_batch(seed, B=6):
+    """Random layouts; every fifth seed forces a single-element layout, a full layout and a layout with one label."""
+    batch = synth.synth_batch(B, 8, 8, 10, 1, 4, seed=1000 + seed)
+    if seed % 5 == 0:
+        batch["mask"][0] = torch.arange(10) < 1
+        batch["mask"][1] = True
+        batch["label"][2] = 1
+        for k in ["label", "center_x", "center_y", "width", "height"]:
+            batch[k] = batch[k] * batch["mask"]
+    return batch
+
+
+def run_task_edge_cases():
+    """get_condition + task preprocessors of the reference on the batches of `edge_case_batch` (seeds 0, 5, 17)."""
+    import copy
+
+    from image2layout.train.helpers.task import get_condition
+    from image2layout.train.models.layoutformerpp.task_preprocessor import PREPROCESSOR
+
+    tok, _ = rb.make_tokenizer("cgl", 10)
+    out = {}
+    for seed in (0, 5, 17):
+        batch = edge_case_batch(seed)
+        for task in TASKS:
+            torch.manual_seed(seed)
+            cond, _ = get_condition(copy.deepcopy(batch), task, tok)
+            out[f"{seed}_{task}_cond_seq"], out[f"{seed}_{task}_cond_mask"] = cond.seq.clone().numpy(), cond.mask.numpy()
+            const = PREPROCESSOR[task](tokenizer=tok, global_task_embedding=False)(cond)
+            out[f"{seed}_{task}_const_seq"] = const["seq"].numpy()
+    np.savez_compressed(os.path.join(OUT, "tasks_edge_cases.npz"), **out)
+    print("task edge cases", len(out))
+
+
 def run_pku_contract():
     """BASELINE configs[2] (PKU, 3 labels): state-dict schema of the reference class and the tokenizer's outputs."""
     ralf, tok, _ = rb.make_ralf("pku")
@@ -282,6 +315,7 @@ def main():
         run_optim_groups(ralf)
         run_pku_contract()
         run_tokenizer_edge_cases()
+        run_task_edge_cases()
         return
     run(ralf, tok, "ralf_cgl_256", B=2, H=256, W=256, seed=1, is_ralf=True)
     run_tasks(tok, "tasks_cgl_256", B=2, H=256, W=256, seed=1)
