@@ -263,6 +263,46 @@ def run_task_edge_cases():
     print("task edge cases", len(out))
 
 
+def corrupted_output(tok, batch, cond_seq, task, seed):
+    """A generated sequence that reproduces the condition except for ~15 % corrupted label / geometry tokens."""
+    pad, eos = tok.name_to_id("pad"), tok.name_to_id("eos")
+    keys = ["label", "mask", "center_x", "center_y", "width", "height"]
+    gt = cond_seq[:, 1:].clone() if task == "refinement" else tok.encode({k: batch[k] for k in keys})["seq"][:, 1:]
+    out = gt.clone()
+    out[out == pad] = eos
+    g = torch.Generator().manual_seed(seed)
+    flip = torch.rand(out.shape, generator=g) < 0.15
+    valid = (gt != pad) & (gt != eos)
+    noise = torch.randint(0, 4, out.shape, generator=g)
+    lab = (torch.arange(out.shape[1])[None] % 5 == 0).expand_as(out)
+    out = torch.where(flip & valid & lab, noise, out)
+    return torch.where(flip & valid & ~lab, torch.clamp(out + 1, max=515), out)
+
+
+def run_violation_cases():
+    """calculate_violation of the reference (violate.py:24-139) on corrupted outputs, tasks c / cwh / refinement."""
+    import copy
+
+    from image2layout.train.helpers.task import get_condition
+    from image2layout.train.models.layoutformerpp.task_preprocessor import PREPROCESSOR
+    from image2layout.train.models.layoutformerpp.violate import calculate_violation
+
+    tok, _ = rb.make_tokenizer("cgl", 10)
+    out = {}
+    for seed in (1, 3, 7):
+        batch = synth.synth_batch(5, 8, 8, 10, 1, 4, seed=2000 + seed)
+        for task in ("c", "cwh", "refinement"):
+            torch.manual_seed(seed)
+            cond, _ = get_condition(copy.deepcopy(batch), task, tok)
+            PREPROCESSOR[task](tokenizer=tok, global_task_embedding=False)(cond)
+            seq = corrupted_output(tok, batch, cond.seq, task, seed)
+            vio = calculate_violation(task, cond, seq.clone(), tok.decode(seq.clone()), tok, [])
+            out[f"{seed}_{task}_seq"] = seq.numpy()
+            out[f"{seed}_{task}_violation"] = np.array([vio["total"], vio["viorated"]])
+    np.savez_compressed(os.path.join(OUT, "violation_cases.npz"), **out)
+    print("violation cases", {k: v.tolist() for k, v in out.items() if k.endswith("violation")})
+
+
 def run_pku_contract():
     """BASELINE configs[2] (PKU, 3 labels): state-dict schema of the reference class and the tokenizer's outputs."""
     ralf, tok, _ = rb.make_ralf("pku")
@@ -316,6 +356,7 @@ def main():
         run_pku_contract()
         run_tokenizer_edge_cases()
         run_task_edge_cases()
+        run_violation_cases()
         return
     run(ralf, tok, "ralf_cgl_256", B=2, H=256, W=256, seed=1, is_ralf=True)
     run_tasks(tok, "tasks_cgl_256", B=2, H=256, W=256, seed=1)

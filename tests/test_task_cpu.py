@@ -139,3 +139,21 @@ def test_task_edge_cases_match_reference(seed):
         np.testing.assert_array_equal(cond.mask.numpy(), z[f"{seed}_{task}_cond_mask"])
         const = T.TaskPreprocessor(tok, task)(cond)
         np.testing.assert_array_equal(const["seq"].numpy(), z[f"{seed}_{task}_const_seq"])
+
+
+@pytest.mark.parametrize("seed", [1, 3, 7])
+def test_violation_counts_match_reference_on_corrupted_outputs(seed):
+    """violate.py:24-139 on sequences with ~15 % corrupted tokens (fixture: the reference's own counts)."""
+    from oracle import synth
+    from ralf_b200 import task as T
+
+    z = np.load(helpers.GOLDEN + "/violation_cases.npz")
+    tok = helpers.make_tokenizer()
+    batch = synth.synth_batch(5, 8, 8, 10, 1, 4, seed=2000 + seed)
+    for task in ("c", "cwh", "refinement"):
+        torch.manual_seed(seed)
+        cond, _ = T.get_condition(copy.deepcopy(batch), task, tok)
+        T.TaskPreprocessor(tok, task)(cond)
+        vio = T.calculate_violation(task, cond, torch.from_numpy(z[f"{seed}_{task}_seq"]), tok)
+        assert [vio["total"], vio["viorated"]] == z[f"{seed}_{task}_violation"].tolist(), (seed, task)
+        assert vio["viorated"] > 0
