@@ -303,6 +303,47 @@ def run_violation_cases():
     print("violation cases", {k: v.tolist() for k, v in out.items() if k.endswith("violation")})
 
 
+def collate_examples(trial):
+    """Ragged dataset rows (0, 1, 3 or 10 elements) as `dataset[i]` yields them (lists + image tensors)."""
+    import random
+
+    rnd = random.Random(trial)
+    exs = []
+    for b in range(rnd.randint(1, 6)):
+        n = rnd.choice([0, 1, 3, 10])
+        g = torch.Generator().manual_seed(trial * 100 + b)
+        exs.append({"id": str(trial * 10 + b), "label": [rnd.randint(0, 3) for _ in range(n)],
+                    **{k: [rnd.random() for _ in range(n)] for k in ["center_x", "center_y", "width", "height"]},
+                    "image": torch.rand((3, 4, 4), generator=g), "saliency": torch.rand((1, 4, 4), generator=g)})
+    return exs
+
+
+def run_collate_cases():
+    """The reference's collate_fn (data.py:42-117) on ragged rows.  data.py cannot be imported here (hydra config store), so
+    the function object is built from its source in the reference tree with the module globals it uses."""
+    import ast
+    import copy
+    from typing import Optional
+
+    from torch.utils.data import default_collate
+
+    from image2layout.train.global_variables import DUMMY_LAYOUT, RETRIEVED_KEYS
+
+    src = open(os.path.join(rb.REFERENCE_ROOT, "image2layout/train/data.py")).read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "collate_fn"][0]
+    glb = {"torch": torch, "Tensor": torch.Tensor, "default_collate": default_collate, "Optional": Optional,
+           "compute_validity": None, "RETRIEVED_KEYS": RETRIEVED_KEYS, "DUMMY_LAYOUT": DUMMY_LAYOUT}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "reference_collate_fn", "exec"), glb)
+    out = {}
+    for trial in (0, 1, 2, 3):
+        ref = glb["collate_fn"](copy.deepcopy(collate_examples(trial)), max_seq_length=10)
+        for k in ["label", "mask", "center_x", "center_y", "width", "height", "image", "saliency"]:
+            out[f"{trial}_{k}"] = ref[k].numpy()
+        out[f"{trial}_id"] = np.array(list(ref["id"]))
+    np.savez_compressed(os.path.join(OUT, "collate_cases.npz"), **out)
+    print("collate cases", len(out))
+
+
 def run_pku_contract():
     """BASELINE configs[2] (PKU, 3 labels): state-dict schema of the reference class and the tokenizer's outputs."""
     ralf, tok, _ = rb.make_ralf("pku")
@@ -357,6 +398,7 @@ def main():
         run_tokenizer_edge_cases()
         run_task_edge_cases()
         run_violation_cases()
+        run_collate_cases()
         return
     run(ralf, tok, "ralf_cgl_256", B=2, H=256, W=256, seed=1, is_ralf=True)
     run_tasks(tok, "tasks_cgl_256", B=2, H=256, W=256, seed=1)

@@ -166,3 +166,30 @@ def test_linear_bucketizer_cycle_property():
         x_cycle = b.decode(ids)
         assert (torch.abs(x - x_cycle) <= 1 / (2 * n_boundaries) + 1e-7).all()
         assert (ids == b.encode(x_cycle)).all()
+
+
+@pytest.mark.parametrize("trial", [0, 1, 2, 3])
+def test_collate_main_matches_reference_collate_fn(trial):
+    """Ragged rows (empty layouts get the reference's dummy element): values AND dtypes of the reference's collate_fn
+    (data.py:42-117; fixture tests/golden/collate_cases.npz, rows rebuilt here by the generator's recipe)."""
+    import random
+
+    import numpy as np
+
+    from ralf_b200 import data as D
+
+    rnd = random.Random(trial)
+    exs = []
+    for b in range(rnd.randint(1, 6)):
+        n = rnd.choice([0, 1, 3, 10])
+        g = torch.Generator().manual_seed(trial * 100 + b)
+        exs.append({"id": str(trial * 10 + b), "label": [rnd.randint(0, 3) for _ in range(n)],
+                    **{k: [rnd.random() for _ in range(n)] for k in ["center_x", "center_y", "width", "height"]},
+                    "image": torch.rand((3, 4, 4), generator=g), "saliency": torch.rand((1, 4, 4), generator=g)})
+    z = np.load(helpers.GOLDEN + "/collate_cases.npz")
+    out = D.RetrievalCollator(layouts=None, max_seq_length=10, top_k=1, table_idx={}).collate_main(exs)
+    for k in ["label", "mask", "center_x", "center_y", "width", "height", "image", "saliency"]:
+        ref = z[f"{trial}_{k}"]
+        assert out[k].numpy().dtype == ref.dtype, k
+        np.testing.assert_array_equal(out[k].numpy(), ref)
+    assert out["id"] == z[f"{trial}_id"].tolist()
