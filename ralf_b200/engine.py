@@ -453,6 +453,28 @@ class Engine:
         logits, _ = self._gemm(h, "decoder.head.1")
         return logits.view(B, S, self.vocab)
 
+    def _decode_step(self, x: torch.Tensor, t: int, kc: list, vc: list, kvm: list, pad_mask: torch.Tensor, B: int,
+                     Mlen: int) -> torch.Tensor:
+        """One KV-cached pass of the 6 decoder layers + head over the token embeddings ``x`` [B, 256] at position ``t``
+        (updates ``x`` and rows ``t`` of the self-attention caches in place) -> logits [B, V]."""
+        kv24 = kvm[0].dtype == torch.uint8
+        for i in range(NLAYER):
+            p = f"decoder.transformer.layers.{i}"
+            # every LayerNorm of the step is folded into the GEMM that consumes it (ralf_gemm_ln)
+            qkv, _ = self._gemm_ln(x, p + ".norm1", p + ".qkv")
+            a = ops.attention_decode_append(qkv, kc[i], vc[i], t, B, NHEAD, 32, mask=pad_mask)
+            self._gemm(a, p + ".o", res=x, out_f32=x)
+            q, _ = self._gemm_ln(x, p + ".norm2", p + ".cq")
+            if kv24:
+                a = ops.attention_decode_kv24(q, kvm[i], Mlen, Mlen, B, NHEAD)
+            else:
+                a = ops.attention_decode(q, kvm[i][:, :D], kvm[i][:, D:], Mlen, Mlen, B, NHEAD, 32)
+            self._gemm(a, p + ".co", res=x, out_f32=x)
+            _, f = self._gemm_ln(x, p + ".norm3", p + ".linear1", act="relu", want_f32=False, want_split=True)
+            self._gemm(f, p + ".linear2", res=x, out_f32=x)
+        logits, _ = self._gemm_ln(x, "decoder.head.0", "decoder.head.1")
+        return logits
+
     def generate(self, mem_s: Optional[torch.Tensor], B: int, Mlen: int, token_mask: torch.Tensor, bos_id: int,
                  pad_id: int, steps: int, return_logits: bool = False, kv: Optional[list] = None, step_hook=None,
                  forced: Optional[torch.Tensor] = None, sampling: Optional[dict] = None,
@@ -465,7 +487,6 @@ class Engine:
         (helpers/sampling.py:18-68); the uniforms come from ``uniform`` fp32 [steps, B] or are drawn with ``rng``."""
         dev = self.dev
         kvm = kv if kv is not None else self.cross_kv(mem_s, kv24=KV24 and self.npass == 3)
-        kv24 = kvm[0].dtype == torch.uint8
         seq = torch.full((B, steps + 1), pad_id, dtype=torch.int64, device=dev)
         seq[:, 0] = bos_id
         pad_mask = torch.zeros((B, steps + 1), dtype=torch.uint8, device=dev)
@@ -490,21 +511,7 @@ class Engine:
         for t in range(steps):
             if step_hook is not None:  # profiling aid (profiles/launch_slice.py): called before every decode step
                 step_hook(t)
-            for i in range(NLAYER):
-                p = f"decoder.transformer.layers.{i}"
-                # every LayerNorm of the step is folded into the GEMM that consumes it (ralf_gemm_ln)
-                qkv, _ = self._gemm_ln(x, p + ".norm1", p + ".qkv")
-                a = ops.attention_decode_append(qkv, kc[i], vc[i], t, B, NHEAD, 32, mask=pad_mask)
-                self._gemm(a, p + ".o", res=x, out_f32=x)
-                q, _ = self._gemm_ln(x, p + ".norm2", p + ".cq")
-                if kv24:
-                    a = ops.attention_decode_kv24(q, kvm[i], Mlen, Mlen, B, NHEAD)
-                else:
-                    a = ops.attention_decode(q, kvm[i][:, :D], kvm[i][:, D:], Mlen, Mlen, B, NHEAD, 32)
-                self._gemm(a, p + ".co", res=x, out_f32=x)
-                _, f = self._gemm_ln(x, p + ".norm3", p + ".linear1", act="relu", want_f32=False, want_split=True)
-                self._gemm(f, p + ".linear2", res=x, out_f32=x)
-            logits, _ = self._gemm_ln(x, "decoder.head.0", "decoder.head.1")
+            logits = self._decode_step(x, t, kc, vc, kvm, pad_mask, B, Mlen)
             if return_logits:
                 all_logits.append(logits)
             if plain:
@@ -520,3 +527,43 @@ class Engine:
                             noise=noise)
         out = seq[:, 1:]
         return (out, torch.stack(all_logits, 1)) if return_logits else out
+
+
+class DecodeSession:
+    """KV-cached next-token logits for ONE canvas with rewind, for samplers that backtrack on the host
+    (``ralf_b200.relation.sample_with_backtracking``; reference: retrieval_augmented_autoreg.py:365-383, which re-runs the
+    whole decoder over the prefix at every step).  ``logits_of(prefix)`` keeps the self-attention K/V rows of the longest
+    prefix it has in common with the previous call and only runs the decoder for the tokens after it, so a rewind to
+    position p costs nothing but the re-decode of what follows p."""
+
+    def __init__(self, engine: "Engine", kvm: list, Mlen: int, steps: int, pad_id: int) -> None:
+        self.eng, self.kvm, self.Mlen, self.steps, self.pad_id = engine, kvm, Mlen, steps, pad_id
+        dev = engine.dev
+        self.seq = torch.full((1, steps + 1), pad_id, dtype=torch.int64, device=dev)
+        self.pad_mask = torch.zeros((1, steps + 1), dtype=torch.uint8, device=dev)
+        self.kc = [torch.empty((1, steps, D), dtype=torch.float32, device=dev) for _ in range(NLAYER)]
+        self.vc = [torch.empty((1, steps, D), dtype=torch.float32, device=dev) for _ in range(NLAYER)]
+        self.cached: list = []       # tokens whose K/V rows are in the cache
+        self.last_logits: Optional[torch.Tensor] = None
+
+    def logits_of(self, prefix: list) -> torch.Tensor:
+        """prefix = [<bos>, t1, ..., t_s] (1 <= len <= steps) -> host fp32 [V] logits of token s + 1."""
+        n = len(prefix)
+        assert 1 <= n <= self.steps, f"prefix of {n} tokens, cache holds {self.steps}"
+        keep = 0
+        while keep < min(n, len(self.cached)) and self.cached[keep] == prefix[keep]:
+            keep += 1
+        if keep == n and keep == len(self.cached) and self.last_logits is not None:
+            return self.last_logits
+        keep = min(keep, n - 1)  # the last token is always re-run: its logits are what the caller wants
+        eng = self.eng
+        new = torch.tensor(prefix[keep:], dtype=torch.int64)
+        self.seq[0, keep:n] = new.to(eng.dev)
+        self.pad_mask[0, keep:n] = (new == self.pad_id).to(torch.uint8).to(eng.dev)
+        logits = None
+        for t in range(keep, n):
+            x = ops.embed(self.seq, t, 1, eng.w["decoder.emb"], math.sqrt(D), eng.w["pe1d"], t)
+            logits = eng._decode_step(x, t, self.kc, self.vc, self.kvm, self.pad_mask, 1, self.Mlen)
+        self.cached = list(prefix)
+        self.last_logits = logits[0].float().cpu()
+        return self.last_logits

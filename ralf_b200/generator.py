@@ -8,7 +8,8 @@ tensor operation runs in :class:`ralf_b200.engine.Engine` (hand-written sm_100a 
 
 Scope: forward / loss / sampling for the tasks uncond, c, cwh, partial, refinement (host side in
 ralf_b200/task.py, decoding-space restriction + deterministic / random / top_k / top_p / gumbel sampling in the device
-kernel ``ralf_sample_next``).  ``relation`` (Gen-R with backtracking) raises NotImplementedError rather than silently
+kernel ``ralf_sample_next``).  ``relation`` (Gen-R) decodes per canvas through ``engine.DecodeSession`` under the host-side
+backtracking sampler of ``ralf_b200/relation.py``.  Anything else raises NotImplementedError rather than silently
 taking another path.
 """
 from __future__ import annotations
@@ -150,7 +151,7 @@ class _B200LayoutModel(nn.Module):
                  db_dataset: Any = None, d_model: int = 256, top_k: int = 16, retrieval_backbone: str = "saliency",
                  random_retrieval: bool = False, saliency_k: Any = 8, auxilary_task: Optional[str] = "uncond",
                  use_multitask: bool = False, use_flag_embedding: bool = True, precision: str = "bf16x3",
-                 **kwargs: Any) -> None:
+                 relation_table: Any = None, **kwargs: Any) -> None:
         super().__init__()
         if d_model != 256:
             raise NotImplementedError("the B200 kernels are specialised for d_model = 256 (reference default)")
@@ -168,7 +169,8 @@ class _B200LayoutModel(nn.Module):
         self.use_multitask = use_multitask
         self.use_flag_embedding = use_flag_embedding
         self.precision = precision
-        self.preprocessor = TaskPreprocessor(self.tokenizer, auxilary_task)
+        self.relation_table = relation_table  # dict / path; None -> the reference's cache locations, read on first use
+        self.preprocessor = self._make_preprocessor(auxilary_task)
         g = torch.Generator().manual_seed(0)
         for entry in param_schema(self.tokenizer.N_label, self.tokenizer.N_total, self.preprocessor.N_total, self.IS_RALF):
             name, shape = entry[0], entry[1]
@@ -200,6 +202,26 @@ class _B200LayoutModel(nn.Module):
         assert tok.geo_quantization == "linear" and not tok.is_loc_vocab_shared, "only the linear tokenizer is mirrored"
         return LayoutSequenceTokenizer(list(tok._label_feature.names), tok.max_seq_length, tok.N_bbox_per_var,
                                        list(tok.var_order), list(tok.special_tokens))
+
+    def _make_preprocessor(self, task: Optional[str]) -> TaskPreprocessor:
+        """PREPROCESSOR[task](tokenizer=...) (task_preprocessor.py:593-602).  The relation task reads its relationship
+        table from ``relation_table`` (dict or file) or from where the reference keeps it (task_preprocessor.py:498-506)."""
+        if task != "relation":
+            return TaskPreprocessor(self.tokenizer, task)
+        import os
+
+        from . import relation as R
+
+        table = self.relation_table
+        if table is None:
+            for cand in (os.path.join("cache", R.REFERENCE_TABLE_NAME),
+                         os.path.join("cache", "PRECOMPUTED_WEIGHT_DIR", "relationship", R.REFERENCE_TABLE_NAME)):
+                if os.path.exists(cand):
+                    table = cand
+                    break
+            else:
+                raise FileNotFoundError(f"relation task: pass relation_table= or provide cache/{R.REFERENCE_TABLE_NAME}")
+        return R.RelationPreprocessor(self.tokenizer, table)
 
     # ---- nn.Module plumbing --------------------------------------------------------------------
     @property
@@ -249,14 +271,14 @@ class _B200LayoutModel(nn.Module):
         if not self.use_multitask:
             return
         self.auxilary_task = task
-        self.preprocessor = TaskPreprocessor(self.tokenizer, task)
+        self.preprocessor = self._make_preprocessor(task)
 
     def get_random_task(self) -> str:
-        """Task mixture of LayoutFormer++ (Tab. 3 of its supplement), without `relation` (not built)."""
+        """Task mixture of LayoutFormer++ (Tab. 3 of its supplement; retrieval_augmented_autoreg.py:721-735)."""
         import random
 
-        tasks = ["uncond", "c", "cwh", "partial", "refinement"]
-        return random.choices(tasks, weights=[1 / 12, 1 / 3, 1 / 3, 1 / 12, 1 / 3])[0]
+        tasks = ["uncond", "c", "cwh", "partial", "refinement", "relation"]
+        return random.choices(tasks, weights=[1 / 12, 1 / 3, 1 / 3, 1 / 12, 1 / 3, 1 / 12])[0]
 
     # ---- train.py / inference.py surface --------------------------------------------------------
     def preprocess(self, inputs: dict) -> tuple[dict, dict]:
@@ -352,11 +374,14 @@ class _B200LayoutModel(nn.Module):
                return_decoded_cond: bool = False, return_seq: bool = False, generator: Optional[torch.Generator] = None,
                **kwargs: Any):
         """Generation (retrieval_augmented_autoreg.py:218-325) with KV caches on the GPU: tasks uncond / c / cwh /
-        partial / refinement; sampling deterministic / random / top_k / top_p / gumbel (helpers/sampling.py:18-68).
-        ``generator``: optional torch CUDA generator for the uniforms of the stochastic samplers."""
-        if cond_type == "relation":
-            raise NotImplementedError("cond_type='relation' (Gen-R + backtracking): SURVEY.md 8(f3)")
+        partial / refinement / relation; sampling deterministic / random / top_k / top_p / gumbel
+        (helpers/sampling.py:18-68).  ``generator``: optional torch CUDA generator for the uniforms of the stochastic
+        samplers.  ``relation`` with ``use_backtrack`` goes through ``sample_relation`` (:335-507)."""
         assert cond_type in T.COND_TYPES, f"{cond_type=}"
+        if cond_type == "relation" and use_backtrack:
+            return self.sample_relation(cond, batch_size=batch_size, sampling_cfg=sampling_cfg,
+                                        return_violation=return_violation, return_decoded_cond=return_decoded_cond,
+                                        return_seq=return_seq, **kwargs)
         if self.use_multitask:
             self.set_task_preprocessor(getattr(cond, "task", cond_type))
         name = _cfg_get(sampling_cfg, "name", "deterministic") or "deterministic"
@@ -387,10 +412,66 @@ class _B200LayoutModel(nn.Module):
             out["decoded_tokens"] = self.preprocessor.decode_tokens(const["seq"])
         if not return_violation:
             return out
-        vio = T.calculate_violation(cond_type, cond, seq, self.tokenizer)  # violate.py:24-139
+        prepared = None
+        if cond_type == "relation":  # only the label slots were restricted (:97-105); the relations are scored afterwards
+            from .relation import RelationConstraint
+
+            fn = RelationConstraint(self.preprocessor)
+            prepared = [fn.prepare(const["seq"][b]) for b in range(B)]
+        vio = T.calculate_violation(cond_type, cond, seq, self.tokenizer, output=out,
+                                    prepared_rel_constraints=prepared)  # violate.py:24-139
         if cond_type in ("none", "uncond", "c", "cwh", "refinement"):
             assert vio["viorated"] == 0, f"{vio=}"
         return out, vio
+
+    @torch.no_grad()
+    def sample_relation(self, cond: Any, batch_size: Optional[int] = None, sampling_cfg: Any = None,
+                        return_violation: bool = False, prob_gate: float = 0.3, RELATION_SIZE: int = 10,
+                        return_decoded_cond: bool = False, return_seq: bool = False, **kwargs: Any):
+        """Gen-R with backtracking (retrieval_augmented_autoreg.py:335-507).  The batch is encoded once on the GPU; every
+        canvas is then decoded on its own through a KV-cached ``DecodeSession`` (a rewind keeps the cache rows of the
+        surviving prefix) under ``relation.sample_with_backtracking``, which owns the host RNG draws of the reference
+        (``random.randint`` for the rewind position, ``torch.multinomial`` on the host row for the token)."""
+        from . import relation as R
+        from .engine import KV24, DecodeSession
+
+        if self.use_multitask:
+            self.set_task_preprocessor("relation")
+        pre = self.preprocessor
+        assert isinstance(pre, R.RelationPreprocessor), "the model was not built / switched to the relation task"
+        pre.set_relation_size(RELATION_SIZE)
+        image = cond.image
+        B = image.size(0)
+        if B == 1 and batch_size and batch_size > 1:
+            raise NotImplementedError("batch_size expansion is only defined for unconstrained generation")
+        const = pre(cond)
+        ids = self.special_token_ids
+        steps = self.tokenizer.max_token_length
+        forced = T.forced_token_table("relation", cond.seq, ids["pad"], ids["eos"], steps,
+                                      self.tokenizer.N_var_per_element)
+        eng = self.engine()
+        mem, mem_s = eng.encode(image, getattr(cond, "retrieved", None) if self.IS_RALF else None, const["seq"],
+                                const["pad_mask"])
+        Mlen = mem.shape[1]
+        kvm = eng.cross_kv(mem_s, kv24=KV24 and eng.npass == 3)
+        fn = R.RelationConstraint(pre)
+        rows, prepared = [], []
+        for b in range(B):
+            cons = fn.prepare(const["seq"][b])
+            session = DecodeSession(eng, [k[b * Mlen:(b + 1) * Mlen] for k in kvm], Mlen, steps, ids["pad"])
+            rows.append(R.sample_with_backtracking(session.logits_of, fn, cons, forced[b], bos_id=ids["bos"],
+                                                   eos_id=ids["eos"], max_token_length=steps,
+                                                   sampling_cfg=sampling_cfg, prob_gate=prob_gate))
+            prepared.append(cons)
+        seq = R.pad_like_reference(rows, steps)
+        out = self.tokenizer.decode(seq)
+        if return_seq:
+            out["seq"] = seq
+        if return_decoded_cond:
+            out["decoded_tokens"] = pre.decode_tokens(const["seq"])
+        if not return_violation:
+            return out
+        return out, R.violation_count(out, prepared)
 
 
 class ConcateAuxilaryTaskConcateCrossAttnRetrievalAugmentedAutoreg(_B200LayoutModel):

@@ -9,8 +9,8 @@ Mirrors, for the tasks ``uncond / c / cwh / partial / refinement``:
 The reference restricts the decoding space with per-sample python loops and ``.item()`` syncs at every step; every
 restriction it implements reduces to "at step i sample b must emit token f" or "is free", so here it becomes ONE int32
 table ``forced[B, S]`` (-1 = free) computed before the loop and consumed by the device sampling kernel
-(``ralf_sample_next``).  ``relation`` (Gen-R, relation backtracking) is not built: it needs the relation cache file of
-the reference and is inherently sequential per sample ("last").
+(``ralf_sample_next``).  ``relation`` (Gen-R) shares ``get_condition`` / the label restriction with the tasks here; its
+relationship table, constraint sequence, per-step relation masks and backtracking sampler live in ``ralf_b200/relation.py``.
 
 RNG contract: the pieces of the reference that draw random numbers on the host (refinement noise, element shuffles)
 are drawn here with the same torch calls in the same order, so a seeded run reproduces the reference's constraint
@@ -34,6 +34,7 @@ TASK_VARS = {  # helpers/task.py:33-42
     "cwh": ["label", "width", "height"],
     "refinement": ["label", "width", "height", "center_x", "center_y"],
     "partial": ["label", "width", "height", "center_x", "center_y"],
+    "relation": ["label"],
 }
 TASK_TOKEN = {"c": "label", "cwh": "label_size", "refinement": "refinement", "partial": "completion",
               "uncond": "uncondition", "none": "uncondition", None: "uncondition"}
@@ -53,6 +54,8 @@ class ConditionalInputs:
     seq: Optional[Tensor] = None
     mask: Optional[Tensor] = None
     seq_observed: Any = None
+    edge_indexes: Optional[Tensor] = None     # relation only: [B, P, 2] node pairs, node 0 = canvas (relation.compute_relation)
+    edge_attributes: Optional[Tensor] = None  # relation only: [B, P] bit sets 1 << RelSize | 1 << RelLoc
     retrieved: dict = field(default_factory=dict)
 
     def __post_init__(self) -> None:
@@ -61,7 +64,7 @@ class ConditionalInputs:
             r["image"] = torch.cat([r["image"], r["saliency"]], dim=2)
 
     def to(self, x: Any) -> "ConditionalInputs":
-        for name in ("image", "id", "seq", "mask"):
+        for name in ("image", "id", "seq", "mask", "edge_indexes", "edge_attributes"):
             v = getattr(self, name)
             if torch.is_tensor(v):
                 setattr(self, name, v.to(x))
@@ -74,8 +77,6 @@ def get_condition(batch: dict, cond_type: Optional[str], tokenizer: LayoutSequen
     ``batch`` with the perturbed values."""
     if cond_type not in COND_TYPES:
         raise AssertionError(f"cond_type={cond_type!r} is not one of {COND_TYPES}")
-    if cond_type == "relation":
-        raise NotImplementedError("cond_type='relation' (Gen-R + backtracking) is not built: SURVEY.md 8(f3)")
     image = batch["image"] if batch["image"].size(1) == 4 else torch.cat([batch["image"], batch["saliency"]], dim=1)
     pad_id = tokenizer.name_to_id("pad")
     mask_id = tokenizer.name_to_id("mask") if "mask" in tokenizer.special_tokens else -1
@@ -96,7 +97,11 @@ def get_condition(batch: dict, cond_type: Optional[str], tokenizer: LayoutSequen
         new_seq[:, :n_keep] = seq[:, :n_keep]
         new_mask[:, :n_keep] = True
         seq, mask = new_seq, new_mask
-    elif cond_type in ("c", "cwh"):
+    elif cond_type in ("c", "cwh", "relation"):
+        if cond_type == "relation":  # drawn before anything else of this branch, like task.py:112-113
+            from .relation import compute_relation
+
+            extra.update(compute_relation(batch))
         slot = (torch.arange(S) - 1) % C
         slot[0] = -1
         keep = torch.zeros(S, dtype=torch.bool)
@@ -140,7 +145,7 @@ class TaskPreprocessor:
 
     def __init__(self, tokenizer: LayoutSequenceTokenizer, task: Optional[str] = "uncond") -> None:
         if task == "relation":
-            raise NotImplementedError("RelationshipPreprocessor is not built: SURVEY.md 8(f3)")
+            raise ValueError("the relation task needs its relationship table: use ralf_b200.relation.RelationPreprocessor")
         self.tokenizer = tokenizer
         self.task = task
         self.tokens = TASK_TOKENS + PREPROCESS_SPECIAL + [f"rel_elem_{i}" for i in range(tokenizer.max_seq_length)] + \
@@ -232,7 +237,7 @@ def forced_token_table(cond_type: Optional[str], cond_seq: Optional[Tensor], pad
     sampling index s = i + 1 into ``cond_seq`` [B, max_length + 1]:
         s <  first <pad> position of the row:  token given and not <pad>/-1 -> only that token;  else free
         s >= first <pad> position            :  only <eos>
-    (refinement: label slots only).  ``partial`` teacher-forces tokens 1..5 of ``cond_seq`` and starts at step 5
+    (refinement and relation: label slots only).  ``partial`` teacher-forces tokens 1..5 of ``cond_seq`` and starts at step 5
     (retrieval_augmented_autoreg.py:257-259), i.e. the same thing as forcing steps 0..4."""
     if cond_type in UNCOND:
         return None
@@ -243,7 +248,7 @@ def forced_token_table(cond_type: Optional[str], cond_seq: Optional[Tensor], pad
     if cond_type == "partial":
         forced[:, :n_var] = seq[:, 1:1 + n_var].to(torch.int32)
         return forced
-    if cond_type not in ("c", "cwh", "refinement"):
+    if cond_type not in ("c", "cwh", "refinement", "relation"):
         raise NotImplementedError(f"cond_type={cond_type!r}")
     is_pad = seq == pad_id
     first_pad = torch.where(is_pad.any(dim=1), is_pad.float().argmax(dim=1), torch.full((B,), S1 + 1))
@@ -252,14 +257,21 @@ def forced_token_table(cond_type: Optional[str], cond_seq: Optional[Tensor], pad
     before = s < first_pad[:, None]
     f = torch.where(before, torch.where((given == pad_id) | (given == -1), torch.full_like(given, -1), given),
                     torch.full_like(given, eos_id))
-    if cond_type == "refinement":
+    if cond_type in ("refinement", "relation"):  # restrict_only_category: label slots only (:42-84, :97-105)
         f = torch.where(((s - 1) % n_var == 0).expand_as(f), f, torch.full_like(f, -1))
     return f.to(torch.int32)
 
 
 def calculate_violation(cond_type: Optional[str], cond: ConditionalInputs, out_seq: Tensor,
-                        tokenizer: LayoutSequenceTokenizer) -> dict:
-    """violate.py:24-139 for the tasks built here: how many given tokens the output failed to reproduce."""
+                        tokenizer: LayoutSequenceTokenizer, output: Optional[dict] = None,
+                        prepared_rel_constraints: Optional[list] = None) -> dict:
+    """violate.py:24-139: how many given tokens the output failed to reproduce; ``relation`` counts the relationships the
+    decoded layout ``output`` breaks (violate.py:142-236)."""
+    if cond_type == "relation":
+        from .relation import violation_count
+
+        assert len(prepared_rel_constraints) == cond.seq.size(0)
+        return violation_count(output, prepared_rel_constraints)
     if cond_type in UNCOND or cond_type == "partial":
         return {"total": 1, "viorated": 0}
     pad_id, eos_id = tokenizer.name_to_id("pad"), tokenizer.name_to_id("eos")

@@ -383,6 +383,276 @@ def run_pku_contract():
                                                   "dataset": "pku", "special": {k: int(v) for k, v in ids.items()}})))
 
 
+# ---- relation (Gen-R) ------------------------------------------------------------------------------------------------
+REL_SEEDS = {"deterministic": 400, "random": 401}
+
+
+def _reference_table_builder():
+    """describe_relationships / generate_unique_labels of preprocess/precompute_relationship.py:31-131, executed
+    unmodified.  The module itself cannot be imported here (hydra / dataset plumbing at import time), so the two function
+    definitions are compiled from its source; the drawing calls (cv2 / seaborn) only paint a scratch canvas."""
+    import ast
+
+    import cv2
+    from image2layout.train.helpers import relationships as R
+    from image2layout.train.helpers.util import convert_xywh_to_ltrb
+
+    path = os.path.join(rb.REFERENCE_ROOT, "image2layout/preprocess/precompute_relationship.py")
+    tree = ast.parse(open(path).read())
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("generate_unique_labels", "describe_relationships")]
+    sns = type("sns", (), {"color_palette": staticmethod(lambda name, n: [(0.1, 0.2, 0.3)] * n)})
+    from typing import Any
+
+    ns = {"cv2": cv2, "np": np, "sns": sns, "torch": torch, "Tensor": torch.Tensor, "Any": Any, "PAD_ELEMENT": "pad",
+          "RelElement": R.RelElement, "convert_xywh_to_ltrb": convert_xywh_to_ltrb,
+          "detect_loc_relation_between_element_and_canvas": R.detect_loc_relation_between_element_and_canvas,
+          "detect_loc_relation_between_elements": R.detect_loc_relation_between_elements,
+          "detect_size_relation": R.detect_size_relation,
+          # the script's own name lists are alphabetical; the fixture uses the tokenizer's order so that names round-trip
+          "ELEMENTS": {"cgl": rb.LABELS["cgl"], "pku": rb.LABELS["pku"]}}
+    exec(compile(ast.Module(keep, []), path, "exec"), ns)
+    return ns["describe_relationships"]
+
+
+def relation_batch(B, H, W, seed):
+    """Small canvases (2-5 elements), elements sorted by label like the reference's sort_label transform; canvas 0 carries a
+    single label so that the label shuffle of the constraint sequence cannot disagree with the decoding order."""
+    batch = synth.synth_batch(B, H, W, 10, 16, 4, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    n = torch.randint(2, 6, (B,), generator=g)
+    mask = torch.arange(10)[None] < n[:, None]
+    label = torch.where(mask, batch["label"], torch.full_like(batch["label"], 99))
+    label[0] = torch.where(mask[0], torch.ones_like(label[0]), label[0])
+    order = torch.argsort(label, dim=1, stable=True)
+    batch["mask"] = mask
+    batch["label"] = torch.where(mask, torch.gather(label, 1, order), torch.zeros_like(label))
+    for k in ["center_x", "center_y", "width", "height"]:
+        v = torch.gather(batch[k], 1, order)
+        if k in ("width", "height"):
+            v = v * 0.5 + 0.05
+        batch[k] = torch.where(mask, v, torch.zeros_like(v))
+    return batch
+
+
+def run_relation(name="relation_cgl_128", B=3, H=128, W=128, seed=5):
+    """cond_type="relation": relationship table, compute_relation, RelationshipPreprocessor, prepare(), every per-step
+    relation mask + back index the backtracking sampler asked for, final tokens, decoded layouts, violation counts --
+    all from the UNMODIFIED reference (retrieval_augmented_autoreg.py:335-507 and the modules it calls), under recorded
+    seeds of `random` and torch."""
+    import copy
+    import random
+
+    from image2layout.train.helpers import relationships as R
+    from image2layout.train.helpers.task import get_condition
+    from image2layout.train.models.layoutformerpp import relation_restriction as RR
+    from image2layout.train.models.retrieval_augmented_autoreg import (
+        ConcateAuxilaryTaskConcateCrossAttnRetrievalAugmentedAutoreg as RALF,
+    )
+
+    import seaborn
+
+    if not hasattr(seaborn, "color_palette"):  # the stub module: violate.py only uses it to paint a scratch canvas
+        seaborn.color_palette = lambda name, n: [(0.1, 0.2, 0.3)] * n
+    tok, features = rb.make_tokenizer("cgl", 10)
+    batch = relation_batch(B, H, W, seed)
+    out = {k: batch[k].numpy() for k in ["label", "mask", "center_x", "center_y", "width", "height"]}
+    # (a) the table, written where the reference constructor looks for it
+    table = _reference_table_builder()(batch, "cgl")
+    os.makedirs("cache", exist_ok=True)
+    torch.save(table, "cache/pku_cgl_relationships_dic_using_canvas_sort_label_lexico.pt")
+    torch.save(table, os.path.join(OUT, "relation_table_reference_pickle.pt"))
+    random.seed(300)
+    # torch >= 2.6 loads with weights_only=True unless told otherwise; the reference (torch 2.0) expects plain pickle
+    torch.serialization.add_safe_globals([R.RelElement, R.RelLoc, R.RelSize])
+    model = RALF(features=features, tokenizer=tok, dataset_name="cgl", max_seq_length=10, db_dataset=None,
+                 retrieval_backbone="dreamsim", random_retrieval=False, top_k=16, saliency_k="None",
+                 auxilary_task="relation")
+    model.load_state_dict(synth.synth_state_dict(schema_of(model), seed=seed), strict=True)
+    model.eval()
+    pre = model.preprocessor
+    for key, rows in table.items():
+        out[f"table_{key}"] = np.array([[pre.name_to_id(x) for x in r] for r in rows], dtype=np.int64).reshape(-1, 5)
+    for key, rows in pre.table.items():  # after the constructor's shuffle
+        out[f"table_shuffled_{key}"] = np.array([[pre.name_to_id(x) for x in r] for r in rows], dtype=np.int64).reshape(-1, 5)
+
+    def encode_constraints(cons):
+        rows = []
+        for e, mine in enumerate(cons):
+            for kind, tgt in mine:
+                rows.append([e, -1, int(tgt)] if kind == "canvas" else [e, int(kind), int(tgt)])
+        return np.array(rows, dtype=np.int64).reshape(-1, 3)
+
+    ids = model.special_token_ids
+    for mode, rng_seed in REL_SEEDS.items():
+        cfg = rb.DictConfig(name=mode, temperature=1.0, top_k=5, top_p=0.9)
+        random.seed(rng_seed)
+        torch.manual_seed(rng_seed)
+        cond, _ = get_condition(copy.deepcopy(batch), "relation", tok)
+        if mode == "deterministic":
+            out["cond_seq"], out["cond_mask"] = cond.seq.clone().numpy(), cond.mask.clone().numpy()
+            out["edge_indexes"], out["edge_attributes"] = cond.edge_indexes.numpy(), cond.edge_attributes.numpy()
+        log = {"calls": [], "const": None, "memory": None, "prepared": []}
+        enc0, mem0, call0, prep0 = model._create_encoder_inputs, model._encode_into_memory, \
+            RR.TransformerSortByDictRelationConstraint.__call__, RR.TransformerSortByDictRelationConstraint.prepare
+
+        def enc_spy(c):
+            r = enc0(c)
+            log["const"] = (r[1]["seq"].clone(), r[1]["pad_mask"].clone())
+            return r
+
+        def mem_spy(x):
+            r = mem0(x)
+            log["memory"] = r["memory"].clone()
+            return r
+
+        def prep_spy(self, seq):
+            r = prep0(self, seq)
+            log["prepared"].append(copy.deepcopy(r))
+            return r
+
+        def call_spy(self, token_ids, rel_constraints):
+            m, back = call0(self, token_ids, rel_constraints)
+            log["calls"].append((len(log["prepared"]) - 1, token_ids[0].tolist(), m.clone(), -1 if back is None else int(back)))
+            return m, back
+
+        model._create_encoder_inputs, model._encode_into_memory = enc_spy, mem_spy
+        RR.TransformerSortByDictRelationConstraint.__call__ = call_spy
+        RR.TransformerSortByDictRelationConstraint.prepare = prep_spy
+        try:
+            with torch.no_grad():
+                res, vio = model.sample(cond=cond, sampling_cfg=cfg, cond_type="relation", return_violation=True,
+                                        use_backtrack=True)
+        finally:
+            model._create_encoder_inputs, model._encode_into_memory = enc0, mem0
+            RR.TransformerSortByDictRelationConstraint.__call__ = call0
+            RR.TransformerSortByDictRelationConstraint.prepare = prep0
+        p = f"bt_{mode}_"
+        out[p + "const_seq"], out[p + "const_pad_mask"] = log["const"][0].numpy(), log["const"][1].numpy()
+        out[p + "cond_seq_after"] = cond.seq.clone().numpy()
+        if mode == "deterministic":
+            out["memory"] = log["memory"].numpy()  # the constraint sequence differs per mode (shuffles), so does the memory
+        else:
+            out[p + "memory"] = log["memory"].numpy()
+        for b, cons in enumerate(log["prepared"]):
+            out[p + f"prepared_{b}"] = encode_constraints(cons)
+        calls = log["calls"]
+        out[p + "call_sample"] = np.array([c[0] for c in calls], dtype=np.int64)
+        out[p + "call_len"] = np.array([len(c[1]) for c in calls], dtype=np.int64)
+        pref = np.full((len(calls), tok.max_token_length + 2), -1, dtype=np.int64)
+        for i, c in enumerate(calls):
+            pref[i, :len(c[1])] = c[1]
+        out[p + "call_prefix"] = pref
+        out[p + "call_mask"] = np.packbits(torch.stack([c[2] for c in calls]).numpy(), axis=1)
+        out[p + "call_back"] = np.array([c[3] for c in calls], dtype=np.int64)
+        for k in ["label", "mask", "center_x", "center_y", "width", "height"]:
+            out[p + f"gen_{k}"] = res[k].numpy()
+        out[p + "violation"] = np.array([vio["total"], vio["viorated"]])
+        print(name, mode, "constraint calls:", len(calls), "violation:", vio)
+    # (b') every relation kind: all table rows as constraints (relation size 100 %), random geometry prefixes walked forward
+    random.seed(420)
+    torch.manual_seed(420)
+    cond, _ = get_condition(copy.deepcopy(batch), "relation", tok)
+    pre.set_relation_size(100)
+    const = pre(cond)
+    pre.set_relation_size(10)
+    out["sweep_const_seq"] = const["seq"].numpy()
+    fn = RR.TransformerSortByDictRelationConstraint(pre)
+    g = torch.Generator().manual_seed(421)
+    sweep_pref, sweep_mask, sweep_back, sweep_sample = [], [], [], []
+    for b in range(B):
+        cons = fn.prepare(const["seq"][b])
+        out[f"sweep_prepared_{b}"] = encode_constraints(cons)
+        types = fn.type_constraint_token_id.tolist()
+        for trial in range(12):
+            fn.prepare(const["seq"][b])  # fresh decode state
+            toks = [ids["bos"]]
+            scale = [128, 64, 24][trial % 3]  # large, medium and small boxes
+            for e, lab in enumerate(types):
+                w, h = torch.randint(0, scale, (2,), generator=g).tolist()
+                cx, cy = torch.randint(0, 128, (2,), generator=g).tolist()
+                elem = [lab, fn.width_start_idx + w, fn.height_start_idx + h, fn.center_x_start_idx + cx,
+                        fn.center_y_start_idx + cy]
+                for t in elem:
+                    m, back = fn(torch.tensor([toks]), cons)
+                    sweep_pref.append(list(toks))
+                    sweep_mask.append(m.clone())
+                    sweep_back.append(-1 if back is None else int(back))
+                    sweep_sample.append(b)
+                    toks.append(t)
+            m, back = fn(torch.tensor([toks]), cons)  # all elements complete
+            sweep_pref.append(list(toks))
+            sweep_mask.append(m.clone())
+            sweep_back.append(-1 if back is None else int(back))
+            sweep_sample.append(b)
+    # crafted constraint lists: every relation kind against every earlier element, several per element
+    kinds = [R.RelSize.SMALLER, R.RelSize.EQUAL, R.RelSize.LARGER, R.RelSize.UNKNOWN, R.RelLoc.LEFT, R.RelLoc.TOP,
+             R.RelLoc.RIGHT, R.RelLoc.BOTTOM, R.RelLoc.CENTER, R.RelLoc.UNKNOWN]
+    canvas_kinds = [R.RelLoc.TOP, R.RelLoc.CENTER, R.RelLoc.BOTTOM]
+    n_craft = 40
+    for trial in range(n_craft):
+        b = trial % B
+        fn.prepare(const["seq"][b])
+        types = fn.type_constraint_token_id.tolist()
+        cons = [[] for _ in types]
+        for e in range(len(types)):
+            for _ in range(int(torch.randint(0, 4, (1,), generator=g))):
+                if e == 0 or int(torch.randint(0, 4, (1,), generator=g)) == 0:
+                    cons[e].append(("canvas", canvas_kinds[int(torch.randint(0, 3, (1,), generator=g))]))
+                else:
+                    cons[e].append((kinds[int(torch.randint(0, len(kinds), (1,), generator=g))],
+                                    int(torch.randint(0, e, (1,), generator=g))))
+        out[f"craft_prepared_{trial}"] = encode_constraints(cons)
+        toks = [ids["bos"]]
+        scale = [128, 48, 16][trial % 3]
+        for e, lab in enumerate(types):
+            w, h = torch.randint(0, scale, (2,), generator=g).tolist()
+            cx, cy = torch.randint(0, 128, (2,), generator=g).tolist()
+            for t in [lab, fn.width_start_idx + w, fn.height_start_idx + h, fn.center_x_start_idx + cx,
+                      fn.center_y_start_idx + cy]:
+                m, back = fn(torch.tensor([toks]), cons)
+                sweep_pref.append(list(toks))
+                sweep_mask.append(m.clone())
+                sweep_back.append(-1 if back is None else int(back))
+                sweep_sample.append(B + trial)  # B + trial: crafted constraint list `trial`
+                toks.append(t)
+    out["craft_count"] = np.array(n_craft)
+    pref = np.full((len(sweep_pref), tok.max_token_length + 2), -1, dtype=np.int64)
+    for i, c in enumerate(sweep_pref):
+        pref[i, :len(c)] = c
+    out["sweep_prefix"], out["sweep_len"] = pref, np.array([len(c) for c in sweep_pref], dtype=np.int64)
+    out["sweep_mask"] = np.packbits(torch.stack(sweep_mask).numpy(), axis=1)
+    out["sweep_back"], out["sweep_sample"] = np.array(sweep_back, dtype=np.int64), np.array(sweep_sample, dtype=np.int64)
+    print(name, "sweep calls:", len(sweep_pref), "relation kinds:",
+          sorted({int(r[1]) for b in range(B) for r in out[f"sweep_prepared_{b}"]}))
+    # (b'') helpers/sampling.py:18-68 on single rows, as the backtracking loop calls it (temperature override included)
+    from image2layout.train.helpers.sampling import sample as ref_sample
+
+    gl = torch.Generator().manual_seed(430)
+    rows = torch.randn(24, tok.N_total, generator=gl) * 2.0
+    rows[:, ::3] = -float("inf")
+    out["draw_logits"] = rows.numpy()
+    for mode in ["deterministic", "random", "top_k", "top_p", "gumbel"]:
+        cfg = rb.DictConfig(name=mode, temperature=0.8, top_k=5, top_p=0.9)
+        torch.manual_seed(431)
+        out[f"draw_{mode}"] = np.array([int(ref_sample(rows[i:i + 1].clone(), cfg, temperature=1.5 if i % 2 else None))
+                                        for i in range(rows.size(0))], dtype=np.int64)
+    # (c) without backtracking: batched decode under the label restriction only (:218-325)
+    random.seed(410)
+    torch.manual_seed(410)
+    cond, _ = get_condition(copy.deepcopy(batch), "relation", tok)
+    with torch.no_grad():
+        res, vio = model.sample(cond=cond, sampling_cfg=rb.DictConfig(name="deterministic", temperature=1.0),
+                                cond_type="relation", return_violation=True, use_backtrack=False)
+    for k in ["label", "mask", "center_x", "center_y", "width", "height"]:
+        out[f"nobt_gen_{k}"] = res[k].numpy()
+    out["nobt_violation"] = np.array([vio["total"], vio["viorated"]])
+    out["meta"] = np.array(json.dumps({"B": B, "H": H, "W": W, "seed": seed, "ctor_seed": 300, "rng_seed": REL_SEEDS,
+                                       "nobt_seed": 410, "special": {k: int(v) for k, v in ids.items()},
+                                       "label_names": rb.LABELS["cgl"]}))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, {k: getattr(v, "shape", None) for k, v in out.items() if not k.startswith("table")})
+
+
 def main():
     rb.bootstrap("/tmp/ralf_ref_work")
     torch.backends.mha.set_fastpath_enabled(False)
@@ -390,6 +660,9 @@ def main():
     ralf, tok, _ = rb.make_ralf("cgl")
     with open(os.path.join(OUT, "schema_ralf_cgl.json"), "w") as f:
         json.dump(schema_of(ralf), f)
+    if "--relation-only" in sys.argv:
+        run_relation()
+        return
     if "--tasks-only" in sys.argv:
         run_tasks(tok, "tasks_cgl_256", B=2, H=256, W=256, seed=1)
         run_sampling_filters()
@@ -399,6 +672,7 @@ def main():
         run_task_edge_cases()
         run_violation_cases()
         run_collate_cases()
+        run_relation()
         return
     run(ralf, tok, "ralf_cgl_256", B=2, H=256, W=256, seed=1, is_ralf=True)
     run_tasks(tok, "tasks_cgl_256", B=2, H=256, W=256, seed=1)

@@ -1,0 +1,237 @@
+"""cond_type="relation" (Gen-R) host logic against tests/golden/relation_cgl_128.npz, which holds what the UNMODIFIED
+reference produced under recorded `random` / torch seeds (tests/golden/make_golden.py:run_relation): relationship table,
+compute_relation edges, constraint sequences, prepare(), every per-step relation mask + backtrack index, the tokens the
+backtracking sampler ended with, decoded layouts and violation counts.  The model side of the sampler (next-token logits
+of a prefix) is the CPU oracle here; on the GPU it is engine.DecodeSession (tests/test_tasks_gpu.py)."""
+import copy
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from ralf_b200 import relation as R
+from ralf_b200 import task as T
+from tests import helpers
+
+GEO = ["center_x", "center_y", "width", "height"]
+
+
+@pytest.fixture(scope="module")
+def fx():
+    z, meta = helpers.load_golden("relation_cgl_128")
+    tok = helpers.make_tokenizer("cgl")
+    batch = {k: torch.from_numpy(z[k]) for k in ["label", "mask", *GEO]}
+    B = meta["B"]
+    batch["id"] = [str(i) for i in range(B)]
+    batch["image"] = torch.zeros(B, 3, 8, 8)
+    batch["saliency"] = torch.zeros(B, 1, 8, 8)
+    table = R.describe_relationships(batch, meta["label_names"])
+    return z, meta, tok, batch, table
+
+
+def _preprocessor(tok, table, meta):
+    random.seed(meta["ctor_seed"])
+    return R.RelationPreprocessor(tok, copy.deepcopy(table))
+
+
+def _rows(pre, rows):
+    return np.array([[pre.token_id(x) for x in r] for r in rows], dtype=np.int64).reshape(-1, 5)
+
+
+def _decode_constraints(arr):
+    n = int(arr[:, 0].max()) + 1 if len(arr) else 0
+    cons = [[] for _ in range(n)]
+    for e, kind, tgt in arr.tolist():
+        if kind == -1:
+            cons[e].append((R.CANVAS, R.RelLoc(tgt)))
+        else:
+            cons[e].append((R.RelSize(kind) if kind < 4 else R.RelLoc(kind), tgt))
+    return cons
+
+
+def _encode_constraints(cons):
+    rows = []
+    for e, mine in enumerate(cons):
+        for kind, tgt in mine:
+            rows.append([e, -1, int(tgt)] if kind == R.CANVAS else [e, int(kind), int(tgt)])
+    return np.array(rows, dtype=np.int64).reshape(-1, 3)
+
+
+def test_enums_are_the_reference_wire_values():
+    assert [int(x) for x in R.RelSize] == [0, 1, 2, 3] and [x.name for x in R.RelSize] == ["UNKNOWN", "SMALLER", "EQUAL", "LARGER"]
+    assert [int(x) for x in R.RelLoc] == [4, 5, 6, 7, 8, 9]
+    assert [x.name for x in R.RelLoc] == ["UNKNOWN", "LEFT", "TOP", "RIGHT", "BOTTOM", "CENTER"]
+    assert [int(x) for x in R.RelElement] == list(range(10, 21)) and R.RelElement.A.name == "A" and R.RelElement.K.name == "K"
+
+
+def test_relationship_table_matches_reference(fx):
+    z, meta, tok, batch, table = fx
+    pre = _preprocessor(tok, table, meta)
+    assert list(table) == [str(i) for i in range(meta["B"])]
+    for key, rows in table.items():
+        np.testing.assert_array_equal(_rows(pre, rows), z[f"table_{key}"])
+    for key, rows in pre.table.items():  # the constructor's shuffle draws from `random` like the reference's
+        np.testing.assert_array_equal(_rows(pre, rows), z[f"table_shuffled_{key}"])
+
+
+def test_reference_pickle_loads_without_the_reference_package(fx, tmp_path):
+    z, meta, tok, batch, table = fx
+    loaded = R.load_relation_table(os.path.join(helpers.GOLDEN, "relation_table_reference_pickle.pt"))
+    assert loaded == table
+    assert type(loaded["0"][0][1]) is R.RelElement
+    p = str(tmp_path / "t.pt")
+    R.save_relation_table(p, table)
+    assert R.load_relation_table(p) == table
+
+
+def test_get_condition_relation_matches_reference(fx):
+    z, meta, tok, batch, table = fx
+    random.seed(meta["rng_seed"]["deterministic"])
+    torch.manual_seed(meta["rng_seed"]["deterministic"])
+    cond, _ = T.get_condition(copy.deepcopy(batch), "relation", tok)
+    np.testing.assert_array_equal(cond.seq.numpy(), z["cond_seq"])
+    np.testing.assert_array_equal(cond.mask.numpy(), z["cond_mask"])
+    np.testing.assert_array_equal(cond.edge_indexes.numpy(), z["edge_indexes"])
+    np.testing.assert_array_equal(cond.edge_attributes.numpy(), z["edge_attributes"])
+    assert cond.task == "relation"
+
+
+def _oracle_logits_fn(sd, memory_row, pad_id):
+    from oracle import ralf_oracle as O
+
+    mem = memory_row[None]
+
+    def logits_of(prefix):
+        tgt = torch.tensor([prefix], dtype=torch.long)
+        with torch.no_grad():
+            return O.decoder_logits(sd, tgt, mem, tgt == pad_id)[0, -1]
+
+    return logits_of
+
+
+@pytest.mark.parametrize("mode", ["deterministic", "random"])
+def test_backtracking_sampler_matches_reference(fx, mode):
+    """Same seeds -> same constraint sequence (element shuffles + relation sample), same prepare(), same mask and
+    backtrack index at EVERY call the reference made (so the rewinds took the same path), same final tokens."""
+    z, meta, tok, batch, table = fx
+    torch.set_num_threads(8)
+    pre = _preprocessor(tok, table, meta)
+    seed = meta["rng_seed"][mode]
+    random.seed(seed)
+    torch.manual_seed(seed)
+    cond, _ = T.get_condition(copy.deepcopy(batch), "relation", tok)
+    const = pre(cond)
+    p = f"bt_{mode}_"
+    np.testing.assert_array_equal(const["seq"].numpy(), z[p + "const_seq"])
+    np.testing.assert_array_equal(const["pad_mask"].numpy(), z[p + "const_pad_mask"])
+    np.testing.assert_array_equal(cond.seq.numpy(), z[p + "cond_seq_after"])  # <eos> -> <pad> rewritten in place
+    sp = meta["special"]
+    forced = T.forced_token_table("relation", cond.seq, sp["pad"], sp["eos"], tok.max_token_length)
+    sd = helpers.synth_weights("ralf_cgl", meta["seed"])
+    memory = torch.from_numpy(z["memory" if mode == "deterministic" else p + "memory"])
+    fn = R.RelationConstraint(pre)
+    cfg = {"name": mode, "temperature": 1.0, "top_k": 5, "top_p": 0.9}
+    calls = []
+    real_mask = fn.mask
+
+    def spy(prefix, cons):
+        m, back = real_mask(prefix, cons)
+        calls.append((len(prepared) - 1, list(prefix), m, -1 if back is None else back))
+        return m, back
+
+    fn.mask = spy
+    prepared, rows = [], []
+    for b in range(meta["B"]):
+        cons = fn.prepare(const["seq"][b])
+        prepared.append(cons)
+        np.testing.assert_array_equal(_encode_constraints(cons), z[p + f"prepared_{b}"])
+        prefix = R.sample_with_backtracking(_oracle_logits_fn(sd, memory[b], sp["pad"]), fn, cons, forced[b],
+                                            bos_id=sp["bos"], eos_id=sp["eos"], max_token_length=tok.max_token_length,
+                                            sampling_cfg=cfg)
+        rows.append(prefix)
+    assert len(calls) == len(z[p + "call_sample"]), "the sampler took a different path through the rewinds"
+    ref_mask = np.unpackbits(z[p + "call_mask"], axis=1)[:, :tok.N_total].astype(bool)
+    for i, (b, prefix, m, back) in enumerate(calls):
+        assert b == z[p + "call_sample"][i]
+        assert prefix == z[p + "call_prefix"][i, :z[p + "call_len"][i]].tolist(), f"call {i}"
+        assert back == z[p + "call_back"][i], f"call {i}"
+        np.testing.assert_array_equal(m.numpy(), ref_mask[i], err_msg=f"call {i}")
+    seq = R.pad_like_reference(rows, tok.max_token_length)
+    out = tok.decode(seq)
+    for k in ["label", "mask", *GEO]:
+        np.testing.assert_array_equal(out[k].numpy(), z[p + f"gen_{k}"], err_msg=k)
+    vio = T.calculate_violation("relation", cond, seq, tok, output=out, prepared_rel_constraints=prepared)
+    assert [vio["total"], vio["viorated"]] == z[p + "violation"].tolist()
+
+
+def test_relation_masks_for_every_relation_kind(fx):
+    """1800 forward-walked prefixes: all table rows as constraints (relation size 100 %) and crafted constraint lists
+    covering every RelSize / RelLoc kind, several per element, boxes from tiny to canvas-sized."""
+    z, meta, tok, batch, table = fx
+    pre = _preprocessor(tok, table, meta)
+    random.seed(420)
+    torch.manual_seed(420)
+    cond, _ = T.get_condition(copy.deepcopy(batch), "relation", tok)
+    pre.set_relation_size(100)
+    const = pre(cond)
+    np.testing.assert_array_equal(const["seq"].numpy(), z["sweep_const_seq"])
+    fn = R.RelationConstraint(pre)
+    B = meta["B"]
+    cons_of, types_of = {}, {}
+    for b in range(B):
+        cons_of[b] = fn.prepare(const["seq"][b])
+        types_of[b] = fn.types.clone()
+        np.testing.assert_array_equal(_encode_constraints(cons_of[b]), z[f"sweep_prepared_{b}"])
+    for t in range(int(z["craft_count"])):
+        cons_of[B + t] = _decode_constraints(z[f"craft_prepared_{t}"])
+        n = len(types_of[t % B])
+        cons_of[B + t] += [[] for _ in range(n - len(cons_of[B + t]))]
+        types_of[B + t] = types_of[t % B]
+    ref_mask = np.unpackbits(z["sweep_mask"], axis=1)[:, :tok.N_total].astype(bool)
+    kinds = set()
+    for i in range(len(z["sweep_len"])):
+        s = int(z["sweep_sample"][i])
+        fn.types = types_of[s]
+        prefix = z["sweep_prefix"][i, :z["sweep_len"][i]].tolist()
+        m, back = fn.mask(prefix, cons_of[s])
+        assert (-1 if back is None else back) == z["sweep_back"][i], f"call {i}"
+        np.testing.assert_array_equal(m.numpy(), ref_mask[i], err_msg=f"call {i} sample {s} prefix {prefix}")
+        kinds |= {k for mine in cons_of[s] for k, _ in mine}
+    assert {R.CANVAS, *R.RelSize, *R.RelLoc} <= kinds
+
+
+def test_draw_token_matches_reference_sampler(fx):
+    z, meta, tok, batch, table = fx
+    rows = torch.from_numpy(z["draw_logits"])
+    for mode in ["deterministic", "random", "top_k", "top_p", "gumbel"]:
+        cfg = {"name": mode, "temperature": 0.8, "top_k": 5, "top_p": 0.9}
+        torch.manual_seed(431)
+        got = [R.draw_token(rows[i].clone(), cfg, temperature=1.5 if i % 2 else None) for i in range(rows.size(0))]
+        assert got == z[f"draw_{mode}"].tolist(), mode
+
+
+def test_label_only_restriction_without_backtracking(fx):
+    """use_backtrack=False (retrieval_augmented_autoreg.py:244-300): the batched decode under the label restriction;
+    host side (forced-token table, violation count on the reference's own output); the GPU decode is in tests/test_tasks_gpu.py."""
+    z, meta, tok, batch, table = fx
+    pre = _preprocessor(tok, table, meta)
+    random.seed(meta["nobt_seed"])
+    torch.manual_seed(meta["nobt_seed"])
+    cond, _ = T.get_condition(copy.deepcopy(batch), "relation", tok)
+    const = pre(cond)
+    sp = meta["special"]
+    forced = T.forced_token_table("relation", cond.seq, sp["pad"], sp["eos"], tok.max_token_length)
+    ref_forced = T.forced_token_table("refinement", cond.seq, sp["pad"], sp["eos"], tok.max_token_length)
+    assert torch.equal(forced, ref_forced)  # DECODE_SPACE_RESTRICTION maps both to restrict_only_category
+    fn = R.RelationConstraint(pre)
+    prepared = [fn.prepare(const["seq"][b]) for b in range(meta["B"])]
+    out = {k: torch.from_numpy(z[f"nobt_gen_{k}"]) for k in ["label", "mask", *GEO]}
+    vio = T.calculate_violation("relation", cond, None, tok, output=out, prepared_rel_constraints=prepared)
+    assert [vio["total"], vio["viorated"]] == z["nobt_violation"].tolist()
+    # every given label is reproduced by the reference's own output (the restriction the forced table encodes)
+    for b in range(meta["B"]):
+        k = int(out["mask"][b].sum())
+        given = cond.seq[b, 1::5][:k]
+        assert torch.equal(out["label"][b][:k], given[:k])

@@ -152,3 +152,102 @@ def test_model_sample_top_k_runs_and_respects_token_mask(cuda_device):
     out1 = model.sample(cond=cond, sampling_cfg={"name": "top_k", "top_k": 1, "temperature": 1.0}, cond_type="uncond",
                         return_seq=True, generator=gen)
     np.testing.assert_array_equal(out1["seq"].numpy(), z["gen_seq"])
+
+
+# ---- relation (Gen-R): tests/golden/relation_cgl_128.npz, host side pinned in tests/test_relation_cpu.py ----------------
+def _relation_setup(dev):
+    import random
+
+    from oracle import synth
+    from ralf_b200 import generator as G
+    from ralf_b200 import relation as R
+
+    z, meta = helpers.load_golden("relation_cgl_128")
+    tok = helpers.make_tokenizer()
+    batch = synth.synth_batch(meta["B"], meta["H"], meta["W"], 10, 16, 4, seed=meta["seed"])
+    for k in ["label", "mask", "center_x", "center_y", "width", "height"]:
+        batch[k] = torch.from_numpy(z[k])
+    table = R.describe_relationships(batch, meta["label_names"])
+    random.seed(meta["ctor_seed"])  # the preprocessor shuffles its table at construction (task_preprocessor.py:507)
+    model = G.RALF(features=None, tokenizer=tok, dataset_name="cgl", max_seq_length=10, top_k=16,
+                   auxilary_task="relation", relation_table=table)
+    model.load_state_dict(helpers.synth_weights("ralf_cgl", meta["seed"]), strict=True)
+    return model.eval().to(dev), tok, batch, z, meta
+
+
+@pytest.mark.hw_pending
+def test_decode_session_rewinds_match_oracle(cuda_device):
+    """DecodeSession (KV cache kept across rewinds) against the cache-free oracle decoder on the prefixes the reference's
+    backtracking sampler actually visited, rewinds included."""
+    from oracle import ralf_oracle as O
+    from ralf_b200.engine import KV24, DecodeSession
+
+    model, tok, batch, z, meta = _relation_setup(cuda_device)
+    eng = model.engine()
+    sd = helpers.synth_weights("ralf_cgl", meta["seed"])
+    memory = torch.from_numpy(z["memory"])
+    B, Mlen = memory.shape[0], memory.shape[1]
+    hi = memory.to(cuda_device).to(torch.bfloat16)
+    lo = (memory.to(cuda_device) - hi.float()).to(torch.bfloat16)
+    mem_s = torch.stack([hi.reshape(B * Mlen, -1), lo.reshape(B * Mlen, -1)])  # the split operand layout (DESIGN.md 3)
+    kvm = eng.cross_kv(mem_s, kv24=KV24 and eng.npass == 3)
+    pad = meta["special"]["pad"]
+    torch.set_num_threads(8)
+    checked = 0
+    for b in range(B):
+        session = DecodeSession(eng, [k[b * Mlen:(b + 1) * Mlen] for k in kvm], Mlen, tok.max_token_length, pad)
+        idx = np.nonzero(z["bt_deterministic_call_sample"] == b)[0][:60]
+        for n, i in enumerate(idx):
+            prefix = z["bt_deterministic_call_prefix"][i, :z["bt_deterministic_call_len"][i]].tolist()
+            got = session.logits_of(prefix)
+            if n % 6 and n != len(idx) - 1:
+                continue  # every call goes through the cache; every 6th is compared
+            tgt = torch.tensor([prefix])
+            with torch.no_grad():
+                ref = O.decoder_logits(sd, tgt, memory[b:b + 1], tgt == pad)[0, -1]
+            err = float((got - ref).abs().max() / ref.abs().max())
+            assert err < 1e-3, f"canvas {b} call {i} prefix length {len(prefix)}: {err:.3e}"
+            checked += 1
+    assert checked >= 3 * B
+
+
+@pytest.mark.hw_pending
+@pytest.mark.parametrize("mode", ["deterministic", "random"])
+def test_relation_backtracking_matches_reference_golden(cuda_device, mode):
+    """model.sample(cond_type="relation") end to end under the recorded seeds: decoded layouts and the violation count of
+    the reference's sample_relation (retrieval_augmented_autoreg.py:335-507)."""
+    import random
+
+    from ralf_b200 import task as T
+
+    model, tok, batch, z, meta = _relation_setup(cuda_device)
+    seed = meta["rng_seed"][mode]
+    random.seed(seed)
+    torch.manual_seed(seed)
+    cond, _ = T.get_condition(copy.deepcopy(batch), "relation", tok)
+    cond = cond.to(cuda_device)
+    cfg = {"name": mode, "temperature": 1.0, "top_k": 5, "top_p": 0.9}
+    out, vio = model.sample(cond=cond, sampling_cfg=cfg, cond_type="relation", return_violation=True, use_backtrack=True)
+    p = f"bt_{mode}_"
+    for k in ["label", "mask", "center_x", "center_y", "width", "height"]:
+        np.testing.assert_array_equal(out[k].numpy(), z[p + f"gen_{k}"], err_msg=k)
+    assert [vio["total"], vio["viorated"]] == z[p + "violation"].tolist()
+
+
+@pytest.mark.hw_pending
+def test_relation_without_backtracking_matches_reference_golden(cuda_device):
+    """use_backtrack=False: the batched device decode under the label restriction (:244-300), relations scored afterwards."""
+    import random
+
+    from ralf_b200 import task as T
+
+    model, tok, batch, z, meta = _relation_setup(cuda_device)
+    random.seed(meta["nobt_seed"])
+    torch.manual_seed(meta["nobt_seed"])
+    cond, _ = T.get_condition(copy.deepcopy(batch), "relation", tok)
+    cond = cond.to(cuda_device)
+    out, vio = model.sample(cond=cond, sampling_cfg={"name": "deterministic"}, cond_type="relation",
+                            return_violation=True, use_backtrack=False)
+    for k in ["label", "mask", "center_x", "center_y", "width", "height"]:
+        np.testing.assert_array_equal(out[k].numpy(), z[f"nobt_gen_{k}"], err_msg=k)
+    assert [vio["total"], vio["viorated"]] == z["nobt_violation"].tolist()
