@@ -358,8 +358,6 @@ class _B200LayoutModel(nn.Module):
         from . import ops
 
         if self.training and torch.is_grad_enabled() and not test:
-            if not self.IS_RALF:
-                raise NotImplementedError("training is built for the RALF class (SURVEY.md 8 a13)")
             loss, logits = self.trainer().loss_with_grad(inputs, targets)
             self._engine = None  # inference operands are re-prepared from the updated parameters on demand
             return {"logits": logits}, {"nll_loss": loss}

@@ -69,7 +69,8 @@ class TrainEngine:
         self.lr, self.wd, self.body_scale, self.max_norm = lr, weight_decay, body_lr_scale, max_grad_norm
         self.world, self.pg = world_size, process_group
         self.step_count = 0
-        self.infer = Engine(model.state_dict(), self.dev, is_ralf=True, top_k=model.top_k)  # frozen trunk + FIDNet
+        self.is_ralf = bool(getattr(model, "IS_RALF", True))  # False: the Autoreg baseline (models/autoreg.py:590-622)
+        self.infer = Engine(model.state_dict(), self.dev, is_ralf=self.is_ralf, top_k=model.top_k)  # frozen trunk + FIDNet
         self.train_trunk = train_trunk
         named = [(n, p) for n, p in model.named_parameters()
                  if p.requires_grad and (train_trunk or not n.startswith("encoder.extractor"))]
@@ -123,9 +124,10 @@ class TrainEngine:
             reg(p + ".cq", p + ".multihead_attn.in_proj_weight", 0, D)
             reg(p + ".ckv", p + ".multihead_attn.in_proj_weight", D, 2 * D)
             reg(p + ".co", p + ".multihead_attn.out_proj.weight")
-        for n in ("layout_adapter.net.1", "layout_adapter.net.4", "head.net.1", "head.net.4", "attn.to_q", "attn.to_kv",
-                  "attn.to_out.0"):
-            reg(n, n + ".weight")
+        if self.is_ralf:
+            for n in ("layout_adapter.net.1", "layout_adapter.net.4", "head.net.1", "head.net.4", "attn.to_q", "attn.to_kv",
+                      "attn.to_out.0"):
+                reg(n, n + ".weight")
         reg("decoder.head.1", "decoder.head.1.weight")
 
     # ------------------------------------------------------------------------------------------
@@ -178,35 +180,38 @@ class TrainEngine:
         T = h * w
         for i in range(NLAYER):
             x = self._enc_layer(tape, x, f"transformer_encoder.layers.{i}", B, T)
-        # ---- retrieved layouts: frozen FIDNet CLS features -> trainable adapter ----
-        cls = self._fid_cls(inputs["retrieved"], B)              # fp32 [B*K, 256]
-        ref0 = self._ffn_gelu(tape, Node(B * K, D, cls, None, need_grad=False), "layout_adapter")
-        ref = Node(B * K, D, torch.empty((B * K, D), dtype=torch.float32, device=dev),
-                   torch.empty((2, B * K, D), dtype=torch.bfloat16, device=dev))
-        ops.rows_affine(ref0.f32, B * K, D, scale=math.sqrt(D), table=self.pe, tab_mod=K, out_f32=ref.f32, out_split=ref.s)
+        if self.is_ralf:
+            # ---- retrieved layouts: frozen FIDNet CLS features -> trainable adapter ----
+            cls = self._fid_cls(inputs["retrieved"], B)              # fp32 [B*K, 256]
+            ref0 = self._ffn_gelu(tape, Node(B * K, D, cls, None, need_grad=False), "layout_adapter")
+            ref = Node(B * K, D, torch.empty((B * K, D), dtype=torch.float32, device=dev),
+                       torch.empty((2, B * K, D), dtype=torch.bfloat16, device=dev))
+            ops.rows_affine(ref0.f32, B * K, D, scale=math.sqrt(D), table=self.pe, tab_mod=K, out_f32=ref.f32, out_split=ref.s)
 
-        def ref_bwd() -> None:  # d(ref0) = sqrt(d) * d(ref)
-            if ref.grad is None:
-                return
-            g = torch.empty_like(ref0.f32)
-            ag.check(ag._L().ralf_rows_gather(ref.grad.data_ptr(), ref.grad.stride(0), B * K, D, math.sqrt(D), 0, 0, 0,
-                                              g.data_ptr(), 0, ag._stream()), "ralf_rows_gather")
-            ag.accumulate(ref0, g)
+            def ref_bwd() -> None:  # d(ref0) = sqrt(d) * d(ref)
+                if ref.grad is None:
+                    return
+                g = torch.empty_like(ref0.f32)
+                ag.check(ag._L().ralf_rows_gather(ref.grad.data_ptr(), ref.grad.stride(0), B * K, D, math.sqrt(D), 0, 0, 0,
+                                                  g.data_ptr(), 0, ag._stream()), "ralf_rows_gather")
+                ag.accumulate(ref0, g)
 
-        tape.record(ref_bwd)
-        ag.dropout_inplace(tape, ref)  # pos_emb_1d's dropout (positional_encoding.py:107)
-        # ---- fusion attention + head over cat[img, ca, ref] ----
-        hq = ag.layernorm(tape, ps, x, "attn.norm")
-        q = ag.linear(tape, ps, hq, "attn.to_q")
-        kv = ag.linear(tape, ps, ref, "attn.to_kv")
-        a = ag.cross_attention(tape, q, kv, 0, 512, B, T, K, 8, 64, use_dropout=False)
-        ca = ag.linear(tape, ps, a, "attn.to_out.0", "attn.to_out.0.bias")
-        Tcat = 2 * T + K
-        cat = Node(B * Tcat, D, torch.empty((B * Tcat, D), dtype=torch.float32, device=dev), None)
-        ag.place_rows(tape, x, cat.f32, cat, T, Tcat, 0)
-        ag.place_rows(tape, ca, cat.f32, cat, T, Tcat, T)
-        ag.place_rows(tape, ref, cat.f32, cat, K, Tcat, 2 * T)
-        mem_img = self._ffn_gelu(tape, cat, "head")
+            tape.record(ref_bwd)
+            ag.dropout_inplace(tape, ref)  # pos_emb_1d's dropout (positional_encoding.py:107)
+            # ---- fusion attention + head over cat[img, ca, ref] ----
+            hq = ag.layernorm(tape, ps, x, "attn.norm")
+            q = ag.linear(tape, ps, hq, "attn.to_q")
+            kv = ag.linear(tape, ps, ref, "attn.to_kv")
+            a = ag.cross_attention(tape, q, kv, 0, 512, B, T, K, 8, 64, use_dropout=False)
+            ca = ag.linear(tape, ps, a, "attn.to_out.0", "attn.to_out.0.bias")
+            Tcat = 2 * T + K
+            cat = Node(B * Tcat, D, torch.empty((B * Tcat, D), dtype=torch.float32, device=dev), None)
+            ag.place_rows(tape, x, cat.f32, cat, T, Tcat, 0)
+            ag.place_rows(tape, ca, cat.f32, cat, T, Tcat, T)
+            ag.place_rows(tape, ref, cat.f32, cat, K, Tcat, 2 * T)
+            mem_img = self._ffn_gelu(tape, cat, "head")
+        else:  # Autoreg baseline: the image tokens are the memory's first part as they are
+            mem_img, Tcat = x, T
         # ---- constraint encoder ----
         sc = inputs["seq_layout_const"].to(dev).contiguous()
         Tc = sc.shape[1]

@@ -47,7 +47,7 @@ def test_adamw_clip_matches_torch(cuda_device):
             assert (ps.p(n) - r.data).abs().max().item() <= 1e-6
 
 
-def _oracle_loss_and_grads(sd0, batch, inputs, targets, pad_id, train_trunk, dtype):
+def _oracle_loss_and_grads(sd0, batch, inputs, targets, pad_id, train_trunk, dtype, is_ralf=True):
     """torch.autograd over the CPU oracle in `dtype` (float64 = ground truth); model.train() semantics for BatchNorm
     when the trunk trains, dropout off, FIDNet frozen (evaluated in fp32 like the product does)."""
     from oracle import ralf_oracle as O
@@ -63,19 +63,23 @@ def _oracle_loss_and_grads(sd0, batch, inputs, targets, pad_id, train_trunk, dty
     O.pos_emb_2d = lambda h, w, d=256: orig_pos(h, w, d).to(dtype)
     O.BN_TRAIN = train_trunk
     try:
-        with torch.no_grad():
-            cls = []
-            for k in range(16):
-                lay = {key: batch["retrieved"][key][:, k] for key in ["center_x", "center_y", "width", "height", "label", "mask"]}
-                cls.append(O.fidnet_features(sd0, lay))
-        refs = [O._feed_forward(sd, "layout_adapter", c.to(dtype)) for c in cls]
-        ref = O._pe1d(sd, "pos_emb_1d", torch.stack(refs, 1))
+        if is_ralf:
+            with torch.no_grad():
+                cls = []
+                for k in range(16):
+                    lay = {key: batch["retrieved"][key][:, k] for key in ["center_x", "center_y", "width", "height", "label", "mask"]}
+                    cls.append(O.fidnet_features(sd0, lay))
+            refs = [O._feed_forward(sd, "layout_adapter", c.to(dtype)) for c in cls]
+            ref = O._pe1d(sd, "pos_emb_1d", torch.stack(refs, 1))
         memory = O.encode_image(sd, inputs["image"].to(dtype))
     finally:
         O.BN_TRAIN = False
         O.pos_emb_2d = orig_pos
-    ca = O.fusion_attention(sd, memory, ref)
-    mem = O._feed_forward(sd, "head", torch.cat([memory, ca, ref], 1))
+    if is_ralf:
+        ca = O.fusion_attention(sd, memory, ref)
+        mem = O._feed_forward(sd, "head", torch.cat([memory, ca, ref], 1))
+    else:  # Autoreg baseline (models/autoreg.py:590-622): the image tokens go into the memory as they are
+        mem = memory
     uc = O.constraint_encoder(sd, inputs["seq_layout_const"], inputs["seq_layout_const_pad_mask"])
     t = sd["task_emb.weight"]
     mem = torch.cat([mem + t[sd["flag_img"]], uc + t[sd["flag_user_const"]]], 1)
@@ -143,6 +147,44 @@ def test_training_gradients_match_oracle(cuda_device, train_trunk):
     assert abs(gn - gn64) <= 1e-3 * gn64
     assert worst_l2 <= 3e-2, sorted(ours, key=lambda e: -e[2])[:5]
     assert med_ours <= 2e-3 and med_ours <= max(4 * med_t32, 2e-4)
+
+
+@pytest.mark.hw_pending
+def test_autoreg_baseline_training_gradients_match_oracle(cuda_device):
+    """The Autoreg baseline class (BASELINE configs[0]'s model; configs/autoreg_*/*.sh train it) through the same tape:
+    loss and every parameter gradient vs the float64 oracle, bar as in test_training_gradients_match_oracle; then two
+    optimisation steps through the reference-style loop surface (train_loss().backward())."""
+    import statistics
+
+    from oracle import synth
+    from ralf_b200 import generator as G
+    from ralf_b200.train import TrainEngine
+
+    torch.set_num_threads(8)
+    model = G.ConcateAuxilaryTaskAutoreg(features=None, tokenizer=helpers.make_tokenizer(), auxilary_task="uncond")
+    sd = helpers.synth_weights("autoreg_cgl", 23)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(cuda_device)
+    batch = synth.synth_batch(2, 128, 128, 10, 16, 4, seed=10)
+    batch.pop("retrieved")
+    inputs, targets = model.preprocess(batch)
+    pad = model.tokenizer.name_to_id("pad")
+    loss64, g64 = _oracle_loss_and_grads(sd, batch, inputs, targets, pad, True, torch.float64, is_ralf=False)
+    te = TrainEngine(model, train_trunk=True, dropout=0.0)
+    te.ps.flat_g.zero_()
+    loss, tape, _ = te.forward_loss(inputs, targets)
+    tape.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - loss64) <= 1e-5 * abs(loss64), (float(loss), loss64)
+    assert set(g64) == set(te.ps.offsets), set(te.ps.offsets) ^ set(g64)
+    ours = _tensor_errors({n: te.ps.g(n).cpu() for n in g64}, g64)
+    gn = math.sqrt(sum(float((te.ps.g(n).double() ** 2).sum()) for n in g64))
+    gn64 = math.sqrt(sum(float((g64[n] ** 2).sum()) for n in g64))
+    assert abs(gn - gn64) <= 1e-3 * gn64
+    assert max(e[2] for e in ours) <= 3e-2, sorted(ours, key=lambda e: -e[2])[:5]
+    assert statistics.median(e[1] for e in ours) <= 2e-3
+    losses = [float(te.train_step(inputs, targets)) for _ in range(3)]
+    assert losses[-1] < losses[0], losses
 
 
 def test_train_steps_reduce_loss_and_update_state_dict(cuda_device):
