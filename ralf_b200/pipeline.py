@@ -204,3 +204,166 @@ class LayoutPipeline:
         out["seq"] = seq
         out["retrieved_idx"] = self.idx_out.cpu()
         return out
+
+
+class _Slot:
+    """One of the two batches in flight of :class:`OverlappedPipeline`."""
+
+    def __init__(self, kv: list, seq: torch.Tensor, idx: torch.Tensor, enc: list, dec: torch.cuda.CUDAGraph) -> None:
+        self.kv, self.seq, self.idx, self.enc, self.dec = kv, seq, idx, enc, dec
+        self.enc_done, self.dec_done, self.out_ready = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        self.host_seq = torch.zeros(seq.shape, dtype=seq.dtype).pin_memory()
+        self.host_idx = torch.zeros(idx.shape, dtype=idx.dtype).pin_memory()
+        self.busy = False  # submitted and not yet collected (host buffers in use)
+
+
+class OverlappedPipeline(LayoutPipeline):
+    """Two batches in flight: the decode loop of batch i runs on its own stream while search, fetch and the encoder
+    micro-batches of batch i+1 run on the caller's stream.
+
+    Why: the decode loop is latency / HBM bound (4 k launches with grids of a few dozen CTAs, plus the K/V stream), the
+    encoder is tensor bound; run back to back each leaves most of the other's resource idle ("what comes
+    next" item 2).  Nothing changes per canvas -- same graphs, same kernels, same results as :class:`LayoutPipeline`
+    (tests/test_pipeline_gpu.py) -- only the order in which the device sees them.
+
+    What that needs: two K/V caches + output buffers (slots, alternating by step), encoder graphs and a decode graph per
+    slot (graphs bake addresses in), and a SEPARATE graph memory pool for the decode graphs: graphs that share a pool
+    reuse each other's scratch memory, which is only safe while they never run concurrently.
+    Ordering: encode(i+1) -> slot s waits for decode(i-1), the last reader of that slot's K/V cache; decode(i) waits
+    for encode(i).  ``submit`` enqueues one batch and returns its slot; ``collect(slot)`` hands back its results;
+    ``drain`` joins the decode stream into the caller's stream.  ``step`` / ``__call__`` / ``generate_layouts`` keep the
+    parent's blocking semantics (submit + wait), so the class is a drop-in for it."""
+
+    def __init__(self, *args, **kwargs) -> None:
+        kwargs["use_graph"] = False  # the parent must not capture its single-slot graphs
+        super().__init__(*args, **kwargs)
+        self.use_graph = True
+        self.dec_stream = torch.cuda.Stream(device=self.dev)
+        self.slots: list = []
+        self._n = 0
+        self._capture_overlapped()
+
+    def _capture_overlapped(self) -> None:
+        from . import ops
+
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._eager()  # warm-up; allocates slot 0's K/V cache and fixes self.Mlen
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        n0 = ops.launch_count()
+        self.g_search = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_search):
+            self._local = self._stage_search()
+        self._my_idx = self._local[0] if self.world == 1 else torch.zeros(self.B, self.k, dtype=torch.int64,
+                                                                         device=self.dev)
+        pool = self.g_search.pool()
+        self.g_fetch = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_fetch, pool=pool):
+            self._packed = self._stage_fetch(self._my_idx)
+        n_front = ops.launch_count() - n0
+        dec_pool = torch.cuda.graph_pool_handle()
+        kv0 = self.kv
+        kv1 = self.eng.alloc_cross_kv(self.B * self.Mlen, kv24=kv0[0].dtype == torch.uint8)
+        n_slot = 0
+        for kv, seq in ((kv0, self.seq_out), (kv1, torch.zeros_like(self.seq_out))):
+            self.kv, self.seq_out = kv, seq  # the stage functions read these; capture bakes the addresses in
+            n1 = ops.launch_count()
+            enc = []
+            for b0 in range(0, self.B, self.mb):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    self._stage_encode(self._packed, b0)
+                enc.append(g)
+            dec = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(dec, pool=dec_pool):
+                self._stage_decode()
+            n_slot = ops.launch_count() - n1
+            self.slots.append(_Slot(kv, seq, torch.zeros_like(self.idx_out), enc, dec))
+        self.kv, self.seq_out = self.slots[0].kv, self.slots[0].seq
+        self.kernels_per_step = n_front + n_slot + (2 if self.world > 1 else 0)
+        torch.cuda.synchronize()
+
+    # ---- asynchronous interface ------------------------------------------------------------------
+    def submit(self, events: Optional[list] = None, copy_events: Optional[list] = None) -> int:
+        """Enqueue one batch over the static inputs (self.img / self.qry); returns the slot that will hold its results."""
+        main = torch.cuda.current_stream()
+        slot_id = self._n % 2
+        slot = self.slots[slot_id]
+        assert not slot.busy, "collect() the batch submitted two steps ago before submitting another one"
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.all_gather_into_tensor(self.q_all, self.qry, group=self.retr.pg)
+        if events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        self.g_search.replay()
+        if events is not None:
+            e1.record()
+            events.append((e0, e1))
+        if self.world > 1:
+            self._my_idx.copy_(self._merge(*self._local))
+        self.g_fetch.replay()
+        main.wait_event(slot.dec_done)  # the decode of two steps ago was the last reader of this slot's K/V cache
+        slot.idx.copy_(self.idx_out)
+        for i, g in enumerate(slot.enc):
+            if copy_events is not None:
+                main.wait_event(copy_events[i])
+            g.replay()
+        slot.enc_done.record(main)
+        self.dec_stream.wait_event(slot.enc_done)
+        with torch.cuda.stream(self.dec_stream):
+            slot.dec.replay()
+            slot.dec_done.record(self.dec_stream)
+        self._n += 1
+        return slot_id
+
+    def submit_host(self, image: torch.Tensor, query: torch.Tensor) -> int:
+        """``submit`` with host (pinned) inputs: canvases are copied per micro-batch on the copy stream (parent's
+        ``__call__``), so the copy of batch i+1 also runs under the decode of batch i."""
+        main = torch.cuda.current_stream()
+        self.qry.copy_(query, non_blocking=True)
+        self.copy_stream.wait_stream(main)  # the encoder graphs of the previous batch have consumed self.img
+        evs = []
+        with torch.cuda.stream(self.copy_stream):
+            for b0 in range(0, self.B, self.mb):
+                self.img[b0:b0 + self.mb].copy_(image[b0:b0 + self.mb], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+                evs.append(ev)
+        slot_id = self.submit(copy_events=evs)
+        slot = self.slots[slot_id]
+        with torch.cuda.stream(self.dec_stream):  # device -> host of the results right behind the decode
+            slot.host_seq.copy_(slot.seq, non_blocking=True)
+            slot.host_idx.copy_(slot.idx, non_blocking=True)
+            slot.out_ready.record(self.dec_stream)
+        slot.busy = True
+        return slot_id
+
+    def collect(self, slot_id: int) -> dict:
+        """Results of a batch submitted with ``submit_host``: decoded layout dict on the CPU (like ``generate_layouts``)."""
+        slot = self.slots[slot_id]
+        assert slot.busy, "nothing submitted into this slot"
+        slot.out_ready.synchronize()
+        seq = slot.host_seq.clone()
+        out = self.model.tokenizer.decode(seq)
+        out["seq"] = seq
+        out["retrieved_idx"] = slot.host_idx.clone()
+        slot.busy = False
+        return out
+
+    def drain(self) -> None:
+        """Make the caller's stream wait for every decode in flight."""
+        main = torch.cuda.current_stream()
+        for slot in self.slots:
+            main.wait_event(slot.dec_done)
+
+    # ---- blocking interface of the parent ---------------------------------------------------------
+    def step(self, events: Optional[list] = None, copy_events: Optional[list] = None) -> torch.Tensor:
+        slot = self.slots[self.submit(events=events, copy_events=copy_events)]
+        torch.cuda.current_stream().wait_event(slot.dec_done)
+        self.idx_out.copy_(slot.idx)
+        return slot.seq

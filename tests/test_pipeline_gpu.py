@@ -79,3 +79,47 @@ def test_graph_pipeline_equals_eager_and_oracle(cuda_device):
     # replay is deterministic
     out2 = pipe.generate_layouts(img, torch.from_numpy(Q))
     np.testing.assert_array_equal(out["seq"].numpy(), out2["seq"].numpy())
+
+
+@pytest.mark.hw_pending
+def test_overlapped_pipeline_equals_sequential(cuda_device):
+    """Two batches in flight (decode of batch i under search + encode of batch i+1, separate graph pools, two K/V
+    slots) give, batch for batch, the tokens and retrieved indices of the one-batch-at-a-time pipeline."""
+    from ralf_b200.pipeline import LayoutPipeline, OverlappedPipeline
+    from ralf_b200.retrieval import GpuRetriever
+
+    rng = np.random.default_rng(4)
+    n, B, E = 5000, 4, 10
+    G = rng.standard_normal((n, 512)).astype(np.float32)
+    gl = torch.Generator().manual_seed(6)
+    cnt = torch.randint(1, E + 1, (n,), generator=gl)
+    mask = torch.arange(E)[None] < cnt[:, None]
+    lay = {"mask": mask, "label": torch.randint(0, 4, (n, E), generator=gl) * mask}
+    for k in ["center_x", "center_y", "width", "height"]:
+        lay[k] = torch.rand(n, E, generator=gl) * mask
+    model = _model(cuda_device, seed=2)
+    retr = GpuRetriever(torch.from_numpy(G), lay, device=cuda_device)
+    batches = [(torch.rand(B, 4, 128, 128, generator=gl).pin_memory(),
+                torch.from_numpy(rng.standard_normal((B, 512)).astype(np.float32)).pin_memory()) for _ in range(5)]
+    seq_pipe = LayoutPipeline(model, retr, B, 128, 128, micro_batch=2)
+    want = [seq_pipe.generate_layouts(img, q) for img, q in batches]
+    pipe = OverlappedPipeline(model, retr, B, 128, 128, micro_batch=2)
+    assert pipe.kernels_per_step == seq_pipe.kernels_per_step
+    got, pending = [], None
+    for img, q in batches:  # steady state: collect batch i after batch i+1 has been submitted
+        slot = pipe.submit_host(img, q)
+        if pending is not None:
+            got.append(pipe.collect(pending))
+        pending = slot
+    got.append(pipe.collect(pending))
+    pipe.drain()
+    torch.cuda.synchronize()
+    for i, (w, g) in enumerate(zip(want, got)):
+        np.testing.assert_array_equal(g["retrieved_idx"].numpy(), w["retrieved_idx"].numpy(), err_msg=f"batch {i}")
+        np.testing.assert_array_equal(g["seq"].numpy(), w["seq"].numpy(), err_msg=f"batch {i}")
+        for k in ["label", "mask", "center_x", "center_y", "width", "height"]:
+            np.testing.assert_array_equal(g[k].numpy(), w[k].numpy(), err_msg=f"batch {i} {k}")
+    # the blocking interface of the parent class still works on the overlapped pipeline
+    again = pipe.generate_layouts(*batches[0])
+    np.testing.assert_array_equal(again["seq"].numpy(), want[0]["seq"].numpy())
+    np.testing.assert_array_equal(again["retrieved_idx"].numpy(), want[0]["retrieved_idx"].numpy())
