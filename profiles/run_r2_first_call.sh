@@ -1,0 +1,25 @@
+#!/bin/bash
+# First GPU call of round 2 (run under gpurun from the repo root, ~12 min of box time):
+#   1. the hw_pending tests (written after round 1's GPU budget was spent), then the whole -m gpu suite;
+#   2. A/B bench lines for the opt-in variants that are built but unmeasured:
+#        baseline | RALF_GEMM_MINB=2 (two GEMM CTAs per SM for the short-K shapes) | --overlap (two batches in flight)
+# Outputs: gpurun_out/r2_*.{log,json}.  Nothing here is a bench value by itself: copy what is kept into profiles/.
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -q -m "gpu and hw_pending" -p no:cacheprovider > gpurun_out/r2_pending_tests.log 2>&1
+timeout 1500 python -m pytest tests -x -q -m gpu -p no:cacheprovider > gpurun_out/r2_gpu_tests.log 2>&1
+B="--steps 5 --warmup 3 --no-cpu-baseline"
+timeout 600 python bench.py $B > gpurun_out/r2_bench_base.json 2> gpurun_out/r2_bench_base.err
+RALF_GEMM_MINB=2 timeout 600 python bench.py $B > gpurun_out/r2_bench_minb2.json 2> gpurun_out/r2_bench_minb2.err
+timeout 600 python bench.py $B --overlap > gpurun_out/r2_bench_overlap.json 2> gpurun_out/r2_bench_overlap.err
+RALF_GEMM_MINB=2 timeout 600 python bench.py $B --overlap > gpurun_out/r2_bench_overlap_minb2.json 2> gpurun_out/r2_bench_overlap_minb2.err
+tail -3 gpurun_out/r2_pending_tests.log gpurun_out/r2_gpu_tests.log
+for f in gpurun_out/r2_bench_*.json; do python - "$f" <<'PY'
+import json, sys
+try:
+    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print(sys.argv[1], d["value"], d["unit"], "ms/step", d["ms_per_step"], "e2e", d["e2e"]["value"], "knn frac", d["roofline"]["frac"])
+except Exception as e:
+    print(sys.argv[1], "no line:", e)
+PY
+done
