@@ -235,3 +235,64 @@ def test_label_only_restriction_without_backtracking(fx):
         k = int(out["mask"][b].sum())
         given = cond.seq[b, 1::5][:k]
         assert torch.equal(out["label"][b][:k], given[:k])
+
+
+def test_relation_preprocessor_reference_properties():
+    """The reference's own test for this preprocessor (tests/train/helpers/test_task_preprocessor.py:28-58,117-137):
+    check_get_condition, check_output, and prepare() on every row, over random batches."""
+    from oracle import synth
+
+    tok = helpers.make_tokenizer()
+    names = ["logo", "text", "underlay", "embellishment"]
+    for seed in range(8):
+        batch = synth.synth_batch(5, 8, 8, 10, 1, 4, seed=seed)
+        random.seed(seed)
+        torch.manual_seed(seed)
+        pre = R.RelationPreprocessor(tok, R.describe_relationships(batch, names), relation_size=[10, 50, 100][seed % 3])
+        cond, _ = T.get_condition(copy.deepcopy(batch), "relation", tok)
+        assert -1 not in cond.seq[cond.mask].tolist()
+        assert len(set(cond.seq[~cond.mask].tolist())) <= 1
+        out = pre(cond)
+        seq, pad_mask = out["seq"], out["pad_mask"]
+        assert pre.N_total > 0 and seq.min() >= 0 and seq.max() < pre.N_total
+        assert set(seq[pad_mask].tolist()) <= {pre.name_to_id("pad")}
+        assert pre.name_to_id("pad") not in seq[~pad_mask].tolist()
+        assert (seq[:, 0] == pre.name_to_id("bos")).all() and (seq[:, 1] == pre.name_to_id("relationship")).all()
+        torch.nn.Embedding(pre.N_total, 8)(seq)
+        fn = R.RelationConstraint(pre)
+        for b in range(seq.size(0)):
+            cons = fn.prepare(seq[b])
+            assert len(cons) == int(batch["mask"][b].sum())
+            for e, mine in enumerate(cons):
+                for kind, tgt in mine:
+                    assert (kind == R.CANVAS and isinstance(tgt, R.RelLoc)) or (isinstance(kind, (R.RelLoc, R.RelSize)) and 0 <= tgt < e)
+
+
+def test_ground_truth_layout_violates_none_of_its_own_relations():
+    """Size-independent property tying table builder, constraint sequence, prepare() and the violation count together:
+    with every table row used as a constraint (relation size 100 %), the layout the table was computed from breaks none
+    of them.  Single-label canvases, where the label shuffle of the constraint sequence cannot move positions."""
+    tok = helpers.make_tokenizer()
+    names = ["logo", "text", "underlay", "embellishment"]
+    g = torch.Generator().manual_seed(11)
+    B, E = 6, 10
+    n = torch.randint(1, E + 1, (B,), generator=g)
+    mask = torch.arange(E)[None] < n[:, None]
+    batch = {"mask": mask, "label": torch.randint(0, 4, (B, 1), generator=g).expand(B, E) * mask,
+             "id": [str(i) for i in range(B)], "image": torch.zeros(B, 3, 8, 8), "saliency": torch.zeros(B, 1, 8, 8)}
+    for k in GEO:
+        batch[k] = torch.rand(B, E, generator=g) * mask
+    table = R.describe_relationships(batch, names)
+    random.seed(1)
+    torch.manual_seed(1)
+    pre = R.RelationPreprocessor(tok, table, relation_size=100)
+    cond, _ = T.get_condition(copy.deepcopy(batch), "relation", tok)
+    const = pre(cond)
+    fn = R.RelationConstraint(pre)
+    prepared = [fn.prepare(const["seq"][b]) for b in range(B)]
+    vio = R.violation_count({k: batch[k] for k in GEO}, prepared)
+    assert vio["total"] == sum(len(v) for v in table.values()) and vio["viorated"] == 0, vio
+    # and a layout with one element moved does break some
+    moved = {k: batch[k].clone() for k in GEO}
+    moved["center_y"] = 1.0 - moved["center_y"]
+    assert R.violation_count(moved, prepared)["viorated"] > 0
