@@ -9,7 +9,6 @@ Node = a [M, C] activation held as fp32 (``f32``), split bf16 (``s``), or both, 
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import Callable, Optional
 
 import torch

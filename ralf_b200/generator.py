@@ -14,7 +14,6 @@ taking another path.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
 from typing import Any, Optional
 
 import torch

@@ -18,7 +18,6 @@ sequences bit for bit (tests/test_task_cpu.py checks this against fixtures dumpe
 """
 from __future__ import annotations
 
-import copy
 from dataclasses import dataclass, field
 from typing import Any, Optional
 

@@ -1,6 +1,5 @@
 """CPU: the C-ABI library loads and exports every symbol include/ralf_b200.h declares (no compute calls),
 and the drop-in classes keep the reference's state-dict contract."""
-import ctypes
 import json
 import os
 import re

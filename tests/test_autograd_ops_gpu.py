@@ -1,8 +1,6 @@
 """GPU: each tape op's backward (ralf_b200/autograd.py, train_conv.py) against torch.autograd on the same values
 (torch on the GPU is the test reference here, never the product path)."""
-import json
 import math
-import os
 
 import pytest
 import torch

@@ -4,7 +4,6 @@ Dropout is off on both sides here (masks are generator-specific; tests/test_drop
 the whole step with dropout on); BatchNorm uses batch statistics when the trunk trains."""
 import math
 
-import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
