@@ -194,12 +194,20 @@ class RetrievalCollator:
     "online retrieval") by one device gather."""
 
     def __init__(self, layouts: LayoutTable, max_seq_length: int, top_k: int = 16, table_idx: Optional[dict] = None,
-                 retriever: Optional[GpuRetriever] = None, int_ids: bool = False, transforms: Sequence[str] = ()) -> None:
+                 retriever: Optional[GpuRetriever] = None, int_ids: bool = False, transforms: Sequence[str] = (),
+                 random_retrieval: bool = False, num_query_rows: Optional[int] = None) -> None:
+        """``random_retrieval`` (generator config key; helpers/random_retrieval_dataset_wrapper.py:70-72): exemplars are
+        ``torch.randint(0, len(query split), [top_k])`` per sample, drawn on the host generator in batch order;
+        ``num_query_rows`` = len of the split being iterated (defaults to the table size)."""
         self.layouts, self.E, self.top_k = layouts, max_seq_length, top_k
+        self.random_retrieval, self.num_query_rows = random_retrieval, num_query_rows
         self.table_idx, self.retriever, self.int_ids = table_idx, retriever, int_ids
         self.transforms = tuple(transforms)  # e.g. ("sort_label", "sort_lexicographic") when the dataset is raw
 
     def indices(self, ids: Sequence) -> torch.Tensor:
+        if self.random_retrieval:
+            high = self.num_query_rows if self.num_query_rows is not None else len(self.layouts)
+            return torch.stack([torch.randint(low=0, high=high, size=[self.top_k]) for _ in ids])
         rows = []
         for i in ids:
             key = int(i) if self.int_ids else i  # "pku" ids are ints in the tables (retrieval_dataset_wrapper.py:103-104)

@@ -193,3 +193,18 @@ def test_collate_main_matches_reference_collate_fn(trial):
         assert out[k].numpy().dtype == ref.dtype, k
         np.testing.assert_array_equal(out[k].numpy(), ref)
     assert out["id"] == z[f"{trial}_id"].tolist()
+
+
+def test_random_retrieval_draws_like_the_reference_wrapper():
+    """RandomRetrievalDatasetWrapper.__getitem__ (helpers/random_retrieval_dataset_wrapper.py:70-72): one
+    torch.randint(0, len(split), [top_k]) per sample, in order."""
+    from ralf_b200 import data as D
+
+    table = object.__new__(D.LayoutTable)
+    table.packed = torch.zeros(500, 6, 10)
+    col = D.RetrievalCollator(table, max_seq_length=10, top_k=16, random_retrieval=True, num_query_rows=321)
+    torch.manual_seed(7)
+    got = col.indices(["a", "b", "c"])
+    torch.manual_seed(7)
+    want = torch.stack([torch.randint(low=0, high=321, size=[16]) for _ in range(3)])
+    assert torch.equal(got, want) and got.dtype == torch.int64 and int(got.max()) < 321
