@@ -12,6 +12,7 @@ B="--steps 5 --warmup 3 --no-cpu-baseline"
 timeout 600 python bench.py $B > gpurun_out/r2_bench_base.json 2> gpurun_out/r2_bench_base.err
 RALF_GEMM_MINB=2 timeout 600 python bench.py $B > gpurun_out/r2_bench_minb2.json 2> gpurun_out/r2_bench_minb2.err
 timeout 600 python bench.py $B --overlap > gpurun_out/r2_bench_overlap.json 2> gpurun_out/r2_bench_overlap.err
+RALF_GEMM_RESERVE_SMS=16 timeout 600 python bench.py $B --overlap > gpurun_out/r2_bench_overlap_reserve16.json 2> gpurun_out/r2_bench_overlap_reserve16.err
 RALF_GEMM_MINB=2 timeout 600 python bench.py $B --overlap > gpurun_out/r2_bench_overlap_minb2.json 2> gpurun_out/r2_bench_overlap_minb2.err
 tail -3 gpurun_out/r2_pending_tests.log gpurun_out/r2_gpu_tests.log
 for f in gpurun_out/r2_bench_*.json; do python - "$f" <<'PY'

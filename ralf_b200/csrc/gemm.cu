@@ -778,7 +778,12 @@ static int launch_gemm_v(const CUtensorMap& ta, const CUtensorMap& tb, const Gem
     occ_cache[stages] = occ;
   }
   if (occ > occ_cap) occ = occ_cap;
-  const long long max_ctas = static_cast<long long>(sms) * occ;
+  // RALF_GEMM_RESERVE_SMS=n (A/B knob for the two-batches-in-flight pipeline, default 0): multi-wave persistent grids leave
+  // n SMs unclaimed, so the small-grid kernels of a concurrent latency-bound stream (the decode loop of the previous
+  // batch) find an SM at once instead of queueing behind a whole GEMM.
+  static const int reserve_sms = getenv("RALF_GEMM_RESERVE_SMS") ? atoi(getenv("RALF_GEMM_RESERVE_SMS")) : 0;
+  const int grid_sms = (multi_tile && reserve_sms > 0 && reserve_sms < sms) ? sms - reserve_sms : sms;
+  const long long max_ctas = static_cast<long long>(grid_sms) * occ;
   dim3 grid(static_cast<unsigned>(num_tiles < max_ctas ? num_tiles : max_ctas));
   const cudaError_t le = launch_pdl(gemm_bf16_kernel<BN, NPASS, MINB>, grid, dim3(320), Cfg::smem_bytes(stages), st, ta, tb,
                                     ep, M, N, K, stages, cg, splits, split_stride);
