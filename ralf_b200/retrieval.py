@@ -113,3 +113,79 @@ def exchange_and_merge(idx: torch.Tensor, score: torch.Tensor, world: int, pg, m
 
 def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
     return (n * rank) // world, (n * (rank + 1)) // world
+
+
+class FlatIPIndex:
+    """``faiss.IndexFlat(d, faiss.METRIC_INNER_PRODUCT)`` as far as the reference uses it, on the B200.
+
+    The reference never talks to FAISS directly: ``Retriever.__init__`` hands HF ``datasets`` the vectors
+    (``add_faiss_index_from_external_arrays(vectors, index_name=..., metric_type=faiss.METRIC_INNER_PRODUCT)``,
+    retrieval/retriever.py:79-84) and later calls ``get_nearest_examples(index_name, query, k)`` (:112-114, :200-202);
+    ``datasets.search.FaissIndex`` only needs ``index.add(vecs)`` and ``index.search(queries, k) -> (scores, indices)``
+    on numpy arrays, and accepts any such object through its ``custom_index=`` keyword.  So the drop-in at the reference's
+    own boundary is ONE keyword at retriever.py:79:  ``custom_index=ralf_b200.retrieval.FlatIPIndex(vectors.shape[1])``.
+
+    ``add`` copies host rows into a device-resident gallery (fp32, unnormalised, row order = ids, like IndexFlat);
+    ``search`` runs ``ralf_knn_topk`` (uncertified queries re-run through the exact kernel) and returns host arrays:
+    scores fp32 [q, k] descending, labels int64 [q, k], ties towards the lower id, ``-1`` / ``-inf`` past ``ntotal``."""
+
+    metric_type = 0  # faiss.METRIC_INNER_PRODUCT
+    is_trained = True
+    verbose = False
+
+    def __init__(self, d: int, device=None) -> None:
+        if d <= 0 or d % 4:
+            raise ValueError(f"d = {d}: the search kernel needs a positive multiple of 4 (16-byte rows)")
+        self.d = int(d)
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else "cuda"
+        self.dev = torch.device(device)
+        self._chunks: list = []
+        self._retr: Optional[GpuRetriever] = None
+        self.ntotal = 0
+
+    def _rows(self, x, what: str) -> torch.Tensor:
+        t = torch.as_tensor(x)
+        if t.dim() != 2 or t.shape[1] != self.d:
+            raise ValueError(f"{what}: expected [n, {self.d}], got {tuple(t.shape)}")
+        return t.to(torch.float32)
+
+    def add(self, x) -> None:
+        rows = self._rows(x, "add")
+        if rows.shape[0] == 0:
+            return
+        self._chunks.append(rows.to(self.dev, non_blocking=True))
+        self.ntotal += rows.shape[0]
+        self._retr = None
+
+    def train(self, x) -> None:  # flat indexes have nothing to train
+        pass
+
+    def reset(self) -> None:
+        self._chunks, self._retr, self.ntotal = [], None, 0
+
+    def _gallery(self) -> GpuRetriever:
+        if self._retr is None:
+            emb = self._chunks[0] if len(self._chunks) == 1 else torch.cat(self._chunks, dim=0)
+            self._chunks = [emb]
+            self._retr = GpuRetriever(emb, device=self.dev)
+        return self._retr
+
+    def reconstruct(self, i: int):
+        return self._gallery().emb[int(i)].cpu().numpy()
+
+    def search(self, x, k: int, **kwargs):
+        import numpy as np
+
+        q = self._rows(x, "search")
+        k = int(k)
+        if k <= 0 or k > 48:
+            raise ValueError(f"k = {k}: the fused top-k filter keeps at most 48 results per query (the reference asks for <= 33)")
+        scores = np.full((q.shape[0], k), -np.inf, dtype=np.float32)
+        labels = np.full((q.shape[0], k), -1, dtype=np.int64)
+        if self.ntotal == 0 or q.shape[0] == 0:
+            return scores, labels
+        kk = min(k, self.ntotal)
+        idx, score = self._gallery().search(q.to(self.dev), kk, certify=True)
+        scores[:, :kk], labels[:, :kk] = score.cpu().numpy(), idx.cpu().numpy()
+        return scores, labels

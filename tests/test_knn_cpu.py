@@ -1,5 +1,6 @@
 """CPU: the C k-NN oracle (canonical fp32 dot, (score desc, idx asc)) against a float64 ranking."""
 import numpy as np
+import pytest
 
 from tests import oracle_knn
 
@@ -43,3 +44,49 @@ def test_thread_count_does_not_change_results():
     b = oracle_knn.topk(G, Q, 16, threads=7)
     np.testing.assert_array_equal(a[0], b[0])
     np.testing.assert_array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+
+
+def test_flat_ip_index_through_hf_datasets_custom_index(monkeypatch):
+    """The reference reaches FAISS only through HF datasets (retrieval/retriever.py:79-84,200-202).  FlatIPIndex plugs into
+    that boundary as ``custom_index=``: add_faiss_index_from_external_arrays -> get_nearest_examples return the oracle's
+    neighbours.  Host logic only: the kernel call is replaced by the C oracle here (GPU: tests/test_knn_gpu.py)."""
+    import sys
+    import types
+
+    import datasets as ds
+    import torch
+
+    from ralf_b200 import ops
+    from ralf_b200.retrieval import FlatIPIndex
+
+    def oracle_knn_topk(gallery, queries, k, *, index_base=0, gallery_max_norm=0.0, exact=False, workspace=None):
+        i, s = oracle_knn.topk(gallery.numpy(), queries.numpy(), k)
+        return torch.from_numpy(i) + index_base, torch.from_numpy(s), torch.ones(queries.shape[0], dtype=torch.int32)
+
+    monkeypatch.setattr(ops, "knn_topk", oracle_knn_topk)
+    monkeypatch.setitem(sys.modules, "faiss", sys.modules.get("faiss") or types.ModuleType("faiss"))  # not installed here
+    monkeypatch.setattr(ds.search, "_has_faiss", True)
+    rng = np.random.default_rng(5)
+    n, d = 2500, 64
+    vectors = rng.standard_normal((n, d)).astype(np.float32)
+    db = ds.Dataset.from_dict({"id": [str(i) for i in range(n)], "label": [[i % 4] for i in range(n)]})
+    index = FlatIPIndex(d, device="cpu")
+    db.add_faiss_index_from_external_arrays(vectors, index_name="search_feat", custom_index=index)
+    assert index.ntotal == n  # HF adds in batches of 1000: three add() calls
+    q = rng.standard_normal((3, d)).astype(np.float32)
+    oi, os_ = oracle_knn.topk(vectors, q, 17)
+    for j in range(3):
+        scores, examples = db.get_nearest_examples("search_feat", q[j], k=17)  # retriever.py:200-202 (top_k + 1)
+        assert examples["id"] == [str(i) for i in oi[j]]
+        np.testing.assert_array_equal(np.asarray(scores, dtype=np.float32).view(np.uint32), os_[j].view(np.uint32))
+    # FAISS conventions at the edges: k beyond ntotal pads with -1 / -inf, empty index, shape errors
+    small = FlatIPIndex(d, device="cpu")
+    small.add(vectors[:5])
+    s, i = small.search(q, 8)
+    assert (i[:, 5:] == -1).all() and np.isneginf(s[:, 5:]).all() and sorted(i[0, :5].tolist()) == [0, 1, 2, 3, 4]
+    small.reset()
+    assert small.ntotal == 0 and (small.search(q, 2)[1] == -1).all()
+    with pytest.raises(ValueError):
+        small.add(np.zeros((2, d + 4), np.float32))
+    with pytest.raises(ValueError):
+        small.search(q, 64)

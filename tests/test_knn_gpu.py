@@ -112,3 +112,33 @@ def test_knn_adversarial_row_order(cuda_device):
         np.testing.assert_array_equal(gi.cpu().numpy(), oi)
         np.testing.assert_array_equal(gs.cpu().numpy().view(np.uint32), os_.view(np.uint32))
         assert cert.cpu().numpy().all()
+
+
+@pytest.mark.hw_pending
+def test_flat_ip_index_as_hf_custom_index(cuda_device, monkeypatch):
+    """FlatIPIndex behind HF datasets' FaissIndex (``custom_index=``), the reference's own route to FAISS
+    (retrieval/retriever.py:79-84,200-202): neighbours and scores bit-exact against the C oracle, host arrays in/out."""
+    import sys
+    import types
+
+    import datasets as ds
+
+    from ralf_b200.retrieval import FlatIPIndex
+
+    monkeypatch.setitem(sys.modules, "faiss", sys.modules.get("faiss") or types.ModuleType("faiss"))
+    monkeypatch.setattr(ds.search, "_has_faiss", True)
+    G, Q = _data(6000, 512, 4, seed=77, normalize=False)
+    db = ds.Dataset.from_dict({"id": [str(i) for i in range(len(G))]})
+    index = FlatIPIndex(512, device=cuda_device)
+    db.add_faiss_index_from_external_arrays(G, index_name="search_feat", custom_index=index)
+    assert index.ntotal == len(G)
+    oi, os_ = oracle_knn.topk(G, Q, 17)
+    for j in range(len(Q)):
+        scores, examples = db.get_nearest_examples("search_feat", Q[j], k=17)
+        assert examples["id"] == [str(i) for i in oi[j]]
+        np.testing.assert_array_equal(np.asarray(scores, dtype=np.float32).view(np.uint32), os_[j].view(np.uint32))
+    s, i = index.search(Q, 33)  # batched, the k of the top_k32 cache tables
+    oi, os_ = oracle_knn.topk(G, Q, 33)
+    np.testing.assert_array_equal(i, oi)
+    np.testing.assert_array_equal(s.view(np.uint32), os_.view(np.uint32))
+    np.testing.assert_array_equal(index.reconstruct(123), G[123])
