@@ -189,3 +189,19 @@ class FlatIPIndex:
         idx, score = self._gallery().search(q.to(self.dev), kk, certify=True)
         scores[:, :kk], labels[:, :kk] = score.cpu().numpy(), idx.cpu().numpy()
         return scores, labels
+
+
+def coarse_saliency(saliency: torch.Tensor, size: tuple = (16, 16)) -> torch.Tensor:
+    """Batched ``coarse_saliency`` (models/retrieval/image.py:35-44): the retrieval feature of
+    ``retrieval_backbone="saliency"`` -- a nearest-neighbour ``size`` thumbnail of the saliency map, clamped to [0, 1] and
+    mapped to [-1, 1].  saliency [B, 1, H, W] (or [B, H, W]) on any device -> fp32 [B, size[0] * size[1]], ready to be the
+    gallery / query rows of the search (d = 256).  Pure index gather (source pixel = floor(dst * in / out), the rule of
+    ``F.interpolate(mode="nearest")``), so it runs where the canvases already are."""
+    if saliency.dim() == 4:
+        assert saliency.size(1) == 1, f"{saliency.shape=}"
+        saliency = saliency[:, 0]
+    B, H, W = saliency.shape
+    rows = torch.div(torch.arange(size[0], device=saliency.device) * H, size[0], rounding_mode="floor")
+    cols = torch.div(torch.arange(size[1], device=saliency.device) * W, size[1], rounding_mode="floor")
+    thumb = saliency[:, rows][:, :, cols].to(torch.float32)
+    return (2.0 * thumb.clamp(0.0, 1.0) - 1.0).reshape(B, -1)

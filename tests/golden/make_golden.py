@@ -13,6 +13,8 @@ Outputs (committed):
   optim_groups_ralf_cgl.json   BaseModel.optim_groups as train.py calls it -> [(lr, weight_decay, [parameter names])]
   schema_ralf_pku.json / tokenizer_pku.npz   PKU (3 labels) variants of the state-dict schema and tokenizer outputs
   sampling_filters.npz  helpers/sampling.py on random logits: the post-filter probabilities handed to torch.multinomial
+  relation_cgl_128.npz + relation_table_reference_pickle.pt   cond_type="relation" (Gen-R): see run_relation
+  coarse_saliency.npz   the retrieval feature of retrieval_backbone="saliency" (models/retrieval/image.py:35-44)
 Each npz: tokenizer outputs (seq, mask, token_mask), constraint sequence, encoder memory, teacher-forced
 logits, nll loss, greedy token ids + per-step masked logits, decoded layout.
 """
@@ -653,6 +655,28 @@ def run_relation(name="relation_cgl_128", B=3, H=128, W=128, seed=5):
     print(name, {k: getattr(v, "shape", None) for k, v in out.items() if not k.startswith("table")})
 
 
+def run_coarse_saliency():
+    """retrieval_backbone="saliency": the query / gallery feature is the 16x16 nearest-neighbour thumbnail of the saliency
+    map mapped to [-1, 1] (models/retrieval/image.py:35-44).  The module needs dreamsim at import time, so the function
+    definition alone is compiled from its source, unmodified."""
+    import ast
+
+    import torch.nn.functional as F
+    from einops import rearrange
+
+    path = os.path.join(rb.REFERENCE_ROOT, "image2layout/train/models/retrieval/image.py")
+    tree = ast.parse(open(path).read())
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "coarse_saliency"]
+    ns = {"F": F, "torch": torch, "rearrange": rearrange, "np": np, "Tensor": torch.Tensor}
+    exec(compile(ast.Module(keep, []), path, "exec"), ns)
+    g = torch.Generator().manual_seed(12)
+    # some values outside [0, 1] (the clamp matters); rounded to fp16 first so the fixture stores the exact inputs compactly
+    sal = (torch.rand(2, 1, 350, 240, generator=g) * 1.4 - 0.2).half().float()
+    out = np.stack([ns["coarse_saliency"](sal[i]) for i in range(sal.size(0))])
+    np.savez_compressed(os.path.join(OUT, "coarse_saliency.npz"), saliency=sal.numpy().astype(np.float16), feature=out)
+    print("coarse_saliency", out.shape)
+
+
 def main():
     rb.bootstrap("/tmp/ralf_ref_work")
     torch.backends.mha.set_fastpath_enabled(False)
@@ -662,6 +686,9 @@ def main():
         json.dump(schema_of(ralf), f)
     if "--relation-only" in sys.argv:
         run_relation()
+        return
+    if "--saliency-only" in sys.argv:
+        run_coarse_saliency()
         return
     if "--tasks-only" in sys.argv:
         run_tasks(tok, "tasks_cgl_256", B=2, H=256, W=256, seed=1)
@@ -673,6 +700,7 @@ def main():
         run_violation_cases()
         run_collate_cases()
         run_relation()
+        run_coarse_saliency()
         return
     run(ralf, tok, "ralf_cgl_256", B=2, H=256, W=256, seed=1, is_ralf=True)
     run_tasks(tok, "tasks_cgl_256", B=2, H=256, W=256, seed=1)

@@ -90,3 +90,22 @@ def test_flat_ip_index_through_hf_datasets_custom_index(monkeypatch):
         small.add(np.zeros((2, d + 4), np.float32))
     with pytest.raises(ValueError):
         small.search(q, 64)
+
+
+def test_coarse_saliency_matches_reference():
+    """retrieval_backbone="saliency" features vs the reference function (fixture: tests/golden/make_golden.py)."""
+    import os
+
+    import torch
+
+    from ralf_b200.retrieval import coarse_saliency
+    from tests import helpers
+
+    z = np.load(os.path.join(helpers.GOLDEN, "coarse_saliency.npz"))
+    sal = torch.from_numpy(z["saliency"].astype(np.float32))
+    np.testing.assert_array_equal(coarse_saliency(sal).numpy(), z["feature"])
+    np.testing.assert_array_equal(coarse_saliency(sal[:, 0]).numpy(), z["feature"])
+    # the interpolation rule for other canvas sizes (the synthetic 256 x 256 canvases of the bench)
+    x = torch.rand(3, 1, 256, 256)
+    want = 2 * torch.nn.functional.interpolate(x, size=(16, 16)).clamp(0, 1).flatten(1) - 1
+    assert torch.equal(coarse_saliency(x), want)
