@@ -296,3 +296,66 @@ def test_ground_truth_layout_violates_none_of_its_own_relations():
     moved = {k: batch[k].clone() for k in GEO}
     moved["center_y"] = 1.0 - moved["center_y"]
     assert R.violation_count(moved, prepared)["viorated"] > 0
+
+
+def test_decode_session_cache_bookkeeping(monkeypatch):
+    """engine.DecodeSession's rewind logic with the kernels replaced by a toy decoder whose logits depend on EVERY cached
+    row (position-weighted), so a stale or missing K/V row after a rewind changes the answer.  Random walks with rewinds,
+    as sample_with_backtracking produces them; the device kernels themselves are covered in tests/test_tasks_gpu.py."""
+    from ralf_b200 import engine as E
+
+    V, steps, pad = 23, 12, 21
+    calls = []
+
+    def fake_embed(seq, col, S, emb, scale, pe, pos0):
+        assert S == 1 and col == pos0
+        return seq[:, col:col + 1].to(torch.float32) + 1.0  # "embedding" = token id + 1
+
+    class FakeEngine:
+        dev = torch.device("cpu")
+        w = {"decoder.emb": None, "pe1d": None}
+
+        def _decode_step(self, x, t, kc, vc, kvm, pad_mask, B, Mlen):
+            calls.append(t)
+            kc[0][0, t, 0] = x[0, 0]                       # append this position's "key"
+            keys = kc[0][0, :t + 1, 0]
+            live = (pad_mask[0, :t + 1] == 0).to(torch.float32)
+            weights = torch.arange(1, t + 2, dtype=torch.float32)
+            h = (keys * weights * live).sum()              # every cached row matters, and so does its position
+            return (h * torch.arange(1, V + 1, dtype=torch.float32))[None]
+
+    def direct(prefix):
+        keys = torch.tensor(prefix, dtype=torch.float32) + 1.0
+        live = torch.tensor([p != pad for p in prefix], dtype=torch.float32)
+        h = (keys * torch.arange(1, len(prefix) + 1, dtype=torch.float32) * live).sum()
+        return h * torch.arange(1, V + 1, dtype=torch.float32)
+
+    monkeypatch.setattr(E.ops, "embed", fake_embed)
+    rng = random.Random(3)
+    for trial in range(20):
+        session = E.DecodeSession(FakeEngine(), kvm=[None], Mlen=1, steps=steps, pad_id=pad)
+        prefix = [20]
+        for _ in range(60):
+            calls.clear()
+            before = list(session.cached)
+            got = session.logits_of(prefix)
+            assert torch.equal(got, direct(prefix)), (trial, prefix)
+            common = 0
+            while common < min(len(before), len(prefix)) and before[common] == prefix[common]:
+                common += 1
+            if before == prefix:
+                assert calls == []                         # same question twice: answered from the last logits
+            else:
+                assert calls == list(range(min(common, len(prefix) - 1), len(prefix)))  # only the new suffix is decoded
+            move = rng.random()
+            if move < 0.25 and len(prefix) > 1:            # rewind (sample_with_backtracking: prefix[:idx])
+                prefix = prefix[:rng.randint(1, len(prefix) - 1)]
+            elif move < 0.35 and len(prefix) > 2:          # rewind and change a token in the middle
+                cut = rng.randint(1, len(prefix) - 1)
+                prefix = prefix[:cut] + [rng.randrange(V)]
+            elif len(prefix) < steps:
+                prefix = prefix + [rng.randrange(V)]
+            else:
+                prefix = [20]
+    with pytest.raises(AssertionError):
+        session.logits_of(list(range(steps + 1)))
