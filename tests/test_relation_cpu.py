@@ -359,3 +359,108 @@ def test_decode_session_cache_bookkeeping(monkeypatch):
                 prefix = [20]
     with pytest.raises(AssertionError):
         session.logits_of(list(range(steps + 1)))
+
+
+class _OracleEngine:
+    """Stands in for ralf_b200.engine.Engine on the CPU: the oracle computes what the kernels would.  Lets the model
+    class's relation plumbing (sample -> sample_relation -> DecodeSession -> sampler -> decode -> violation) run end to
+    end without a GPU; tests only."""
+
+    npass = 3
+    dev = torch.device("cpu")
+    w = {"decoder.emb": None, "pe1d": None}
+
+    def __init__(self, sd, pad_id):
+        self.sd, self.pad_id = sd, pad_id
+
+    def encode(self, image, retrieved, seq_const, pad_mask):
+        from oracle import ralf_oracle as O
+
+        with torch.no_grad():
+            mem = O.encode_ralf_memory(self.sd, image, {k: v.float() for k, v in retrieved.items() if torch.is_tensor(v)},
+                                       seq_const, pad_mask.bool())
+        return mem, mem.reshape(-1, mem.shape[-1])
+
+    def cross_kv(self, mem_s, kv24=False):
+        return [mem_s]
+
+    def _logits(self, tokens, memory, pad):
+        from oracle import ralf_oracle as O
+
+        with torch.no_grad():
+            return O.decoder_logits(self.sd, tokens, memory, pad)[:, -1]
+
+    def _decode_step(self, x, t, kc, vc, kvm, pad_mask, B, Mlen):
+        kc[0][:, t, 0] = x[:, 0]  # the fake embedding below is the token id itself
+        tokens = kc[0][:, :t + 1, 0].round().long()
+        return self._logits(tokens, kvm[0].view(B, Mlen, -1), pad_mask[:, :t + 1].bool())
+
+    def generate(self, mem_s, B, Mlen, token_mask, bos_id, pad_id, steps, forced=None, sampling=None, rng=None, **kw):
+        assert (sampling or {}).get("name", "deterministic") == "deterministic"
+        seq = torch.full((B, 1), bos_id)
+        memory = mem_s.view(B, Mlen, -1)
+        for t in range(steps):
+            lg = self._logits(seq, memory, seq == pad_id).clone()
+            lg[:, ~token_mask[t].bool()] = -float("inf")
+            for b in range(B):
+                f = int(forced[b, t]) if forced is not None else -1
+                if f >= 0:
+                    keep = lg[b, f].clone()
+                    lg[b] = -float("inf")
+                    lg[b, f] = keep
+            seq = torch.cat([seq, lg.argmax(dim=1, keepdim=True)], dim=1)
+        return seq[:, 1:]
+
+
+def _relation_model(fx, monkeypatch):
+    from oracle import synth
+    from ralf_b200 import engine as E
+    from ralf_b200 import generator as G
+
+    z, meta, tok, batch, table = fx
+    full = synth.synth_batch(meta["B"], meta["H"], meta["W"], 10, 16, 4, seed=meta["seed"])
+    for k in ["label", "mask", *GEO]:
+        full[k] = batch[k]
+    random.seed(meta["ctor_seed"])
+    model = G.RALF(features=None, tokenizer=tok, dataset_name="cgl", max_seq_length=10, top_k=16,
+                   auxilary_task="relation", relation_table=copy.deepcopy(table))
+    sd = helpers.synth_weights("ralf_cgl", meta["seed"])
+    model.load_state_dict(sd, strict=True)
+    fake = _OracleEngine(sd, meta["special"]["pad"])
+    monkeypatch.setattr(model, "engine", lambda: fake)
+    monkeypatch.setattr(E.ops, "embed", lambda seq, col, S, emb, scale, pe, pos0: seq[:, col:col + 1].to(torch.float32))
+    return model.eval(), full
+
+
+@pytest.mark.parametrize("mode", ["deterministic", "random"])
+def test_model_sample_relation_end_to_end_on_oracle_engine(fx, monkeypatch, mode):
+    """model.sample(cond_type="relation", use_backtrack=True) through the drop-in class with the oracle standing in for the
+    kernels: the reference's decoded layouts and violation counts (encoder memory included this time)."""
+    z, meta, tok, batch, table = fx
+    torch.set_num_threads(8)
+    model, full = _relation_model(fx, monkeypatch)
+    seed = meta["rng_seed"][mode]
+    random.seed(seed)
+    torch.manual_seed(seed)
+    cond, _ = T.get_condition(copy.deepcopy(full), "relation", tok)
+    out, vio = model.sample(cond=cond, sampling_cfg={"name": mode, "temperature": 1.0, "top_k": 5, "top_p": 0.9},
+                            cond_type="relation", return_violation=True, use_backtrack=True, return_decoded_cond=True)
+    p = f"bt_{mode}_"
+    for k in ["label", "mask", *GEO]:
+        np.testing.assert_array_equal(out[k].numpy(), z[p + f"gen_{k}"], err_msg=k)
+    assert [vio["total"], vio["viorated"]] == z[p + "violation"].tolist()
+    assert out["decoded_tokens"][0][:3] == ["bos", "relationship", "end_of_task"]
+
+
+def test_model_sample_relation_without_backtracking_on_oracle_engine(fx, monkeypatch):
+    z, meta, tok, batch, table = fx
+    torch.set_num_threads(8)
+    model, full = _relation_model(fx, monkeypatch)
+    random.seed(meta["nobt_seed"])
+    torch.manual_seed(meta["nobt_seed"])
+    cond, _ = T.get_condition(copy.deepcopy(full), "relation", tok)
+    out, vio = model.sample(cond=cond, sampling_cfg={"name": "deterministic"}, cond_type="relation",
+                            return_violation=True, use_backtrack=False)
+    for k in ["label", "mask", *GEO]:
+        np.testing.assert_array_equal(out[k].numpy(), z[f"nobt_gen_{k}"], err_msg=k)
+    assert [vio["total"], vio["viorated"]] == z["nobt_violation"].tolist()
