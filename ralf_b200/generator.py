@@ -220,6 +220,8 @@ class _B200LayoutModel(nn.Module):
                     break
             else:
                 raise FileNotFoundError(f"relation task: pass relation_table= or provide cache/{R.REFERENCE_TABLE_NAME}")
+        if isinstance(table, str):  # read once: the multitask mixture rebuilds the preprocessor at every step (:745-750)
+            table = self.relation_table = R.load_relation_table(table)
         return R.RelationPreprocessor(self.tokenizer, table)
 
     # ---- nn.Module plumbing --------------------------------------------------------------------
