@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: skip the host-buffer leg")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of CUDA graphs")
+    ap.add_argument("--decode-ways", type=int, default=1,
+                    help="cut the decode loop's batch into this many groups on parallel streams (opt-in A/B)")
     ap.add_argument("--overlap", action="store_true",
                     help="two batches in flight (OverlappedPipeline): decode of batch i under search + encode of batch i+1")
     return ap.parse_args()
@@ -154,9 +156,11 @@ def run_ours(args):
     img_h = torch.rand(B, 4, HW, HW, generator=gq).pin_memory()
     qry_h = torch.nn.functional.normalize(torch.randn(B, 512, generator=gq), dim=1).pin_memory()
     if args.overlap:
-        pipe = OverlappedPipeline(model, retr, B, HW, HW, top_k=16, micro_batch=args.micro_batch)
+        pipe = OverlappedPipeline(model, retr, B, HW, HW, top_k=16, micro_batch=args.micro_batch,
+                                  decode_ways=args.decode_ways)
     else:
-        pipe = LayoutPipeline(model, retr, B, HW, HW, top_k=16, use_graph=not args.no_graph, micro_batch=args.micro_batch)
+        pipe = LayoutPipeline(model, retr, B, HW, HW, top_k=16, use_graph=not args.no_graph, micro_batch=args.micro_batch,
+                              decode_ways=args.decode_ways)
     pipe.img.copy_(img_h)
     pipe.qry.copy_(qry_h)
     l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -269,7 +273,7 @@ def run_ours(args):
                        "gallery_dim": 512, "top_k": 16, "max_elements": args.elems, "decode_tokens": S,
                        "memory_len": M, "weights": "random-init reference architecture (seeded)",
                        "l2": "flushed between iterations (256 MiB write); gallery shard >> L2",
-                       "batches_in_flight": 2 if args.overlap else 1,
+                       "batches_in_flight": 2 if args.overlap else 1, "decode_ways": args.decode_ways,
                        "parallelism": f"dp{world} canvases, gallery row-sharded, all-gather merge" if world > 1 else "single GPU"},
             "e2e": {"value": round(world * B / (ms_e2e / args.steps / 1e3), 2), "unit": "layouts/s",
                     "h2d_bytes_per_step": int(img_h.numel() * 4 + qry_h.numel() * 4), "d2h_bytes_per_step": int(B * S * 8),

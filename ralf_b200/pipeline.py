@@ -21,11 +21,18 @@ from .retrieval import GpuRetriever
 
 class LayoutPipeline:
     def __init__(self, model, retriever: GpuRetriever, batch: int, height: int, width: int, *, top_k: int = 16,
-                 emb_dim: int = 512, use_graph: bool = True, micro_batch: int = 128) -> None:
+                 emb_dim: int = 512, use_graph: bool = True, micro_batch: int = 128, decode_ways: int = 1) -> None:
         """``micro_batch``: canvases per encode pass.  Retrieval and the decode loop run over the whole batch; the
         ResNet/encoder activations (im2col buffers, ~60 MB per canvas) only ever exist for one micro-batch, whose
-        memory K/V rows land in the batch-wide cross-attention cache."""
+        memory K/V rows land in the batch-wide cross-attention cache.
+        ``decode_ways`` (opt-in, unmeasured): the decode loop is a chain of ~70 small dependent kernels per token whose
+        grids cover a fraction of the SMs; canvases are independent, so the batch can be cut into ``decode_ways`` groups
+        whose chains run on parallel streams (parallel branches of the captured graph) and fill each other's idle SMs.
+        Results per canvas do not depend on the grouping."""
         self.model, self.retr = model, retriever
+        self.decode_ways = max(1, min(int(decode_ways), batch))
+        self._dec_streams = [torch.cuda.Stream(device=model.device) for _ in range(self.decode_ways)] \
+            if self.decode_ways > 1 else []
         self.B, self.H, self.W, self.k = batch, height, width, top_k
         self.mb = min(micro_batch, batch)
         self.dev = model.device
@@ -79,9 +86,25 @@ class LayoutPipeline:
         self.eng.cross_kv(mem_s, out=self.kv, row0=b0 * self.Mlen)
 
     def _stage_decode(self) -> None:
-        seq = self.eng.generate(None, self.B, self.Mlen, self.token_mask, self.ids["bos"], self.ids["pad"], self.S,
-                                kv=self.kv)
-        self.seq_out.copy_(seq)
+        if self.decode_ways == 1:
+            seq = self.eng.generate(None, self.B, self.Mlen, self.token_mask, self.ids["bos"], self.ids["pad"], self.S,
+                                    kv=self.kv)
+            self.seq_out.copy_(seq)
+            return
+        cur = torch.cuda.current_stream()
+        per = (self.B + self.decode_ways - 1) // self.decode_ways
+        for w, side in enumerate(self._dec_streams):
+            b0, b1 = w * per, min(self.B, (w + 1) * per)
+            if b0 >= b1:
+                break
+            side.wait_stream(cur)  # fork (inside a capture this makes `side` a branch of the same graph)
+            with torch.cuda.stream(side):
+                kv = [k[b0 * self.Mlen:b1 * self.Mlen] for k in self.kv]
+                seq = self.eng.generate(None, b1 - b0, self.Mlen, self.token_mask, self.ids["bos"], self.ids["pad"],
+                                        self.S, kv=kv)
+                self.seq_out[b0:b1].copy_(seq)
+        for side in self._dec_streams:
+            cur.wait_stream(side)  # join
 
     def _stage_main(self, idx: torch.Tensor):
         packed = self._stage_fetch(idx)

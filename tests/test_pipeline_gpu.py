@@ -123,3 +123,31 @@ def test_overlapped_pipeline_equals_sequential(cuda_device):
     again = pipe.generate_layouts(*batches[0])
     np.testing.assert_array_equal(again["seq"].numpy(), want[0]["seq"].numpy())
     np.testing.assert_array_equal(again["retrieved_idx"].numpy(), want[0]["retrieved_idx"].numpy())
+
+
+@pytest.mark.hw_pending
+def test_parallel_decode_chains_equal_single_chain(cuda_device):
+    """decode_ways > 1 (groups of canvases decoded on parallel branches of the captured graph) changes no token."""
+    from ralf_b200.pipeline import LayoutPipeline
+    from ralf_b200.retrieval import GpuRetriever
+
+    rng = np.random.default_rng(8)
+    n, B, E = 4000, 6, 10
+    G = rng.standard_normal((n, 512)).astype(np.float32)
+    gl = torch.Generator().manual_seed(9)
+    cnt = torch.randint(1, E + 1, (n,), generator=gl)
+    mask = torch.arange(E)[None] < cnt[:, None]
+    lay = {"mask": mask, "label": torch.randint(0, 4, (n, E), generator=gl) * mask}
+    for k in ["center_x", "center_y", "width", "height"]:
+        lay[k] = torch.rand(n, E, generator=gl) * mask
+    model = _model(cuda_device, seed=2)
+    retr = GpuRetriever(torch.from_numpy(G), lay, device=cuda_device)
+    img = torch.rand(B, 4, 128, 128, generator=gl)
+    q = torch.from_numpy(rng.standard_normal((B, 512)).astype(np.float32))
+    want = LayoutPipeline(model, retr, B, 128, 128, micro_batch=3).generate_layouts(img, q)
+    for ways, graph in [(2, True), (4, True), (3, False)]:  # 4 ways over 6 canvases: ragged groups (2, 2, 2, 0)
+        pipe = LayoutPipeline(model, retr, B, 128, 128, micro_batch=3, decode_ways=ways, use_graph=graph)
+        for _ in range(2):
+            got = pipe.generate_layouts(img, q)
+            np.testing.assert_array_equal(got["seq"].numpy(), want["seq"].numpy(), err_msg=f"{ways=} {graph=}")
+            np.testing.assert_array_equal(got["retrieved_idx"].numpy(), want["retrieved_idx"].numpy())
