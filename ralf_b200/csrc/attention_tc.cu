@@ -282,11 +282,255 @@ attention_tc_kernel(const float* __restrict__ q, const int ldq, const float* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Variant with TWO threads per query row (256 threads, RALF_ATTN_TC=2; built, not yet measured on hardware).
+// The kernel above is bound by its softmax: one warp per scheduler walks 256 scores per row through tcgen05.ld ->
+// exp2 -> two bf16 splits -> tcgen05.st, a serial chain the tensor pipe (4 % busy, profiles/r1_attn_tc_ncu.md) waits
+// for.  Here warps 0-3 own key columns [0, 128) and warps 4-7 columns [128, 256) of the SAME 128 rows (a warp reaches
+// the TMEM lane quadrant warp % 4, so both halves of a row live in one quadrant); row maxima and sums are combined
+// through 2 KB of shared memory.  Operand conversion (K: one row per thread; V^T, Q, output: half a row per thread) is
+// split the same way.  MMA issue, descriptors, TMEM layout and the order of the floating-point operations inside one
+// half are those of the kernel above; only the row sum is now (left half) + (right half).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+constexpr int ATC2_SMEM = ATC_SMEM + 2 * 2 * 128 * 4;  // + row max / row sum exchange, [2 halves][128 rows] each
+
+__global__ void __launch_bounds__(256, 2)
+attention_tc2_kernel(const float* __restrict__ q, const int ldq, const float* __restrict__ k,
+                     const float* __restrict__ v, const int ldk, const int Tq, const int Tk, const float scale,
+                     __nv_bfloat16* __restrict__ out_split, const long long out_plane, float* __restrict__ out_f32,
+                     const int ldo) {
+  constexpr int DH = 32;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + ATC_Q_BYTES;
+  uint8_t* sVt = sK + ATC_K_BYTES;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sVt + 2 * ATC_VT_PLANE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  float* red_max = reinterpret_cast<float*>(sVt + 2 * ATC_VT_PLANE + 64);  // [2][128]
+  float* red_sum = red_max + 256;                                          // [2][128]
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int half = warp >> 2;      // 0: key columns [0, 128), 1: [128, 256)
+  const int row = tid & 127;       // query row inside the tile = TMEM lane
+  const int h = blockIdx.x, b = blockIdx.y;
+
+  // ---- K: one row per thread -> [hi | lo] swizzled row; rows >= Tk are zero ----
+  {
+    float4 kr[8];
+    const int j = tid;
+    const float* src = k + (static_cast<long long>(b) * Tk + j) * ldk + h * DH;
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      kr[g] = (j < Tk) ? *reinterpret_cast<const float4*>(src + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 hi, lo;
+      split8(kr[2 * g], kr[2 * g + 1], hi, lo);
+      *reinterpret_cast<uint4*>(sK + j * 128 + ((g ^ (j & 7)) << 4)) = hi;
+      *reinterpret_cast<uint4*>(sK + j * 128 + (((g + 4) ^ (j & 7)) << 4)) = lo;
+    }
+  }
+  // ---- V -> V^T key blocks (both planes): key pair (2 row, 2 row + 1), d range [16 half, 16 half + 16) ----
+  {
+    float4 vr[2][4];
+    const int j = 2 * row;
+    const float* src = v + (static_cast<long long>(b) * Tk + j) * ldk + h * DH + 16 * half;
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        vr[u][g] = (j + u < Tk) ? *reinterpret_cast<const float4*>(src + static_cast<long long>(u) * ldk + 4 * g)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int kb = j >> 6, jj = j & 63;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float fa[4] = {vr[0][g].x, vr[0][g].y, vr[0][g].z, vr[0][g].w};
+      const float fc[4] = {vr[1][g].x, vr[1][g].y, vr[1][g].z, vr[1][g].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int d = 16 * half + 4 * g + e;
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(fa[e], h0, l0);
+        split_bf16(fc[e], h1, l1);
+        const int off = kb * 4096 + d * 128 + (((jj >> 3) ^ (d & 7)) << 4) + (jj & 7) * 2;
+        *reinterpret_cast<uint32_t*>(sVt + off) = pack_bf16(h0, h1);
+        *reinterpret_cast<uint32_t*>(sVt + ATC_VT_PLANE + off) = pack_bf16(l0, l1);
+      }
+    }
+  }
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tPh = tmem_base + 256, tPl = tmem_base + 384;
+  const uint32_t trow = static_cast<uint32_t>((warp & 3) * 32) << 16;  // this warp's TMEM lane quadrant
+  uint32_t phase = 0;
+  const int nks = (Tk + 15) >> 4;  // P.V k-steps that hold real keys
+  const int c_lo = 128 * half, c_hi = c_lo + 128;
+
+  for (int q0 = 0; q0 < Tq; q0 += 128) {
+    // ---- Q tile -> [hi | lo] rows: thread (row, half) converts elements [16 half, 16 half + 16) ----
+    {
+      float4 qr[4];
+      const float* src = q + (static_cast<long long>(b) * Tq + q0 + row) * ldq + h * DH + 16 * half;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        qr[g] = (q0 + row < Tq) ? *reinterpret_cast<const float4*>(src + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int gg = 0; gg < 2; ++gg) {
+        const int g = 2 * half + gg;  // 16-byte chunk of the hi half of the row; its lo twin is chunk g + 4
+        uint4 hi, lo;
+        split8(qr[2 * gg], qr[2 * gg + 1], hi, lo);
+        *reinterpret_cast<uint4*>(sQ + row * 128 + ((g ^ (row & 7)) << 4)) = hi;
+        *reinterpret_cast<uint4*>(sQ + row * 128 + (((g + 4) ^ (row & 7)) << 4)) = lo;
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      constexpr uint32_t idesc_s = make_idesc(1, 128, 256);
+      const uint64_t dq = make_sw128_kmajor_desc(smem_u32(sQ));
+      const uint64_t dk = make_sw128_kmajor_desc(smem_u32(sK));
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        mma_bf16_ss(tS, dq + 2 * s, dk + 4 + 2 * s, idesc_s, s != 0);
+        mma_bf16_ss(tS, dq + 4 + 2 * s, dk + 2 * s, idesc_s, 1);
+        mma_bf16_ss(tS, dq + 2 * s, dk + 2 * s, idesc_s, 1);
+      }
+      tc_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- softmax: thread = (query row, key half) ----
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c = c_lo; c < c_hi; c += 32) {
+      if (c >= Tk) break;
+      uint32_t sv[32];
+      tmem_ld_32x32(tS + trow + c, sv);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (c + j < Tk) ? __uint_as_float(sv[j]) : -INFINITY);
+    }
+    red_max[half * 128 + row] = mx;
+    __syncthreads();
+    mx = fmaxf(red_max[row], red_max[128 + row]);  // keys [0, 128) always hold a real key (Tk >= 64): finite
+    float lsum = 0.f;
+    const float sl2 = scale * 1.4426950408889634f, mxs = mx * sl2;
+#pragma unroll 1
+    for (int c = c_lo; c < c_hi; c += 32) {
+      uint32_t ph[16], pl[16];
+      if (c < Tk) {
+        uint32_t sv[32];
+        tmem_ld_32x32(tS + trow + c, sv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float p0 = (c + j < Tk) ? exp2f(fmaf(__uint_as_float(sv[j]), sl2, -mxs)) : 0.f;
+          const float p1 = (c + j + 1 < Tk) ? exp2f(fmaf(__uint_as_float(sv[j + 1]), sl2, -mxs)) : 0.f;
+          lsum += p0 + p1;
+          __nv_bfloat16 h0, l0, h1, l1;
+          split_bf16(p0, h0, l0);
+          split_bf16(p1, h1, l1);
+          ph[j >> 1] = pack_bf16(h0, h1);
+          pl[j >> 1] = pack_bf16(l0, l1);
+        }
+      } else {
+        if (c >= nks * 16) break;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) ph[j] = pl[j] = 0u;
+      }
+      tmem_st_32x16(tPh + trow + (c >> 1), ph);
+      tmem_st_32x16(tPl + trow + (c >> 1), pl);
+    }
+    red_sum[half * 128 + row] = lsum;
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      constexpr uint32_t idesc_o = make_idesc(1, 128, 32);
+      for (int ks = 0; ks < nks; ++ks) {
+        const uint32_t vt = smem_u32(sVt) + (ks >> 2) * 4096;
+        const uint64_t bh = make_sw128_kmajor_desc(vt) + 2 * (ks & 3);
+        const uint64_t bl = make_sw128_kmajor_desc(vt + ATC_VT_PLANE) + 2 * (ks & 3);
+        mma_bf16_ts(tS, tPh + ks * 8, bl, idesc_o, ks != 0);
+        mma_bf16_ts(tS, tPl + ks * 8, bh, idesc_o, 1);
+        mma_bf16_ts(tS, tPh + ks * 8, bh, idesc_o, 1);
+      }
+      tc_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    {
+      uint32_t ov[16];  // O columns [16 half, 16 half + 16) of this row
+      tmem_ld_32x16(tS + trow + 16 * half, ov);
+      tmem_ld_wait();
+      const int r = q0 + row;
+      if (r < Tq) {
+        const float inv = 1.f / (red_sum[row] + red_sum[128 + row]);
+        const long long orow = (static_cast<long long>(b) * Tq + r) * ldo + h * DH + 16 * half;
+        if (out_f32) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(out_f32 + orow + j) =
+                make_float4(__uint_as_float(ov[j]) * inv, __uint_as_float(ov[j + 1]) * inv,
+                            __uint_as_float(ov[j + 2]) * inv, __uint_as_float(ov[j + 3]) * inv);
+        }
+        if (out_split) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 8) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(__uint_as_float(ov[j + 2 * e]) * inv, h0, l0);
+              split_bf16(__uint_as_float(ov[j + 2 * e + 1]) * inv, h1, l1);
+              hw[e] = pack_bf16(h0, h1);
+              lw[e] = pack_bf16(l0, l1);
+            }
+            *reinterpret_cast<uint4*>(out_split + orow + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(out_split + out_plane + orow + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+        }
+      }
+    }
+    // red_max / red_sum of this tile are read above; the next tile's Q-conversion barrier orders them before reuse
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // Returns 1 when the tensor-core kernel took the call, 0 when the shape is outside its class, < 0 on error.
 int attention_tc_try(const float* q, int ldq, const float* k, const float* v, int ldk, const unsigned char* mask, int B,
                      int H, int Tq, int Tk, int head_dim, int causal, float scale, void* out_split,
                      long long out_plane, float* out_f32, int ldo, cudaStream_t st) {
-  static const bool enabled = !(getenv("RALF_ATTN_TC") && atoi(getenv("RALF_ATTN_TC")) == 0);
+  static const int variant = getenv("RALF_ATTN_TC") ? atoi(getenv("RALF_ATTN_TC")) : 1;  // 0 off, 1 default, 2 = 8-warp kernel
+  const bool enabled = variant != 0;
   if (!enabled || mask || causal || head_dim != 32 || Tk > 256 || Tk < 64 || Tq < 64) return 0;
   if ((ldq & 3) || (ldk & 3) || (ldo & 7) || (reinterpret_cast<uintptr_t>(out_split) & 15) ||
       (reinterpret_cast<uintptr_t>(out_f32) & 15) || (out_plane & 7))
@@ -299,6 +543,22 @@ int attention_tc_try(const float* q, int ldq, const float* k, const float* v, in
                                cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return set_cuda_error(e);
     attr_set = true;
+  }
+  if (variant == 2) {
+    static bool attr2_set = false;
+    if (!attr2_set) {
+      cudaError_t e = cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC2_SMEM);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+      if (e != cudaSuccess) return set_cuda_error(e);
+      attr2_set = true;
+    }
+    attention_tc2_kernel<<<dim3(H, B), 256, ATC2_SMEM, st>>>(q, ldq, k, v, ldk, Tq, Tk, scale,
+                                                             reinterpret_cast<__nv_bfloat16*>(out_split), out_plane,
+                                                             out_f32, ldo);
+    const int rc2 = set_cuda_error(cudaGetLastError());
+    return rc2 ? rc2 : 1;
   }
   attention_tc_kernel<<<dim3(H, B), 128, ATC_SMEM, st>>>(q, ldq, k, v, ldk, Tq, Tk, scale,
                                                           reinterpret_cast<__nv_bfloat16*>(out_split), out_plane,

@@ -155,3 +155,55 @@ def test_fidnet_attention_fewkeys_with_padding_matches_fp64(cuda_device, N, T, H
     ref = (torch.softmax(s, -1) @ sp(qkv[:, 2 * Dm:])).transpose(1, 2).reshape(N * T, Dm)
     err = (ops.unsplit(out).double() - ref).abs().max().item() / ref.abs().max().item()
     assert err < 2e-5, err
+
+
+@pytest.mark.hw_pending
+def test_encoder_attention_tcgen05_two_threads_per_row_variant(cuda_device):
+    """RALF_ATTN_TC=2 selects attention_tc2_kernel (256 threads: two threads per query row, key columns split in halves).
+    The selector is read once per process, so the check runs in a child process: same fp64 bar as the default kernel, and
+    bit-identical output to the default kernel wherever one half holds all the keys (Tk <= 128: the row sum has one term)."""
+    import os
+    import subprocess
+    import sys
+
+    code = r'''
+import torch, sys
+sys.path.insert(0, %r)
+from ralf_b200 import ops
+dev = torch.device("cuda:0")
+dh, H = 32, 8
+D = H * dh
+for B, Tq, Tk in [(3, 256, 256), (2, 200, 200), (5, 128, 64), (1, 300, 150), (130, 256, 256), (2, 130, 128)]:
+    g = torch.Generator(device=dev).manual_seed(B + Tq + Tk)
+    q = torch.randn(B * Tq, D, device=dev, generator=g) * 1.5
+    kv = torch.randn(B * Tk, 2 * D, device=dev, generator=g) * 1.5
+    out = ops.unsplit(ops.attention(q, kv[:, :D], kv[:, D:], B, H, Tq, Tk, dh)).double()
+    qd = q.double().view(B, Tq, H, dh).permute(0, 2, 1, 3)
+    kd = kv[:, :D].double().view(B, Tk, H, dh).permute(0, 2, 1, 3)
+    vd = kv[:, D:].double().view(B, Tk, H, dh).permute(0, 2, 1, 3)
+    ref = (torch.softmax(qd @ kd.transpose(-1, -2) * dh ** -0.5, -1) @ vd).permute(0, 2, 1, 3).reshape(B * Tq, D)
+    err = (out - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= 3e-5, (B, Tq, Tk, err)
+    torch.save(out.cpu(), sys.argv[1] + f"_{B}_{Tq}_{Tk}.pt")
+print("ok")
+''' % helpers_root()
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as tmp:
+        outs = {}
+        for variant in ("1", "2"):
+            env = dict(os.environ, RALF_ATTN_TC=variant)
+            r = subprocess.run([sys.executable, "-c", code, os.path.join(tmp, "v" + variant)], env=env, capture_output=True,
+                               text=True, timeout=600)
+            assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+            outs[variant] = {f: torch.load(os.path.join(tmp, f)) for f in os.listdir(tmp) if f.startswith("v" + variant)}
+        a, b = outs["1"]["v1_5_128_64.pt"], outs["2"]["v2_5_128_64.pt"]
+        assert torch.equal(a, b)
+        a, b = outs["1"]["v1_2_130_128.pt"], outs["2"]["v2_2_130_128.pt"]
+        assert torch.equal(a, b)
+
+
+def helpers_root():
+    from tests import helpers
+
+    return helpers.ROOT
