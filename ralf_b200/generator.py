@@ -224,6 +224,22 @@ class _B200LayoutModel(nn.Module):
             table = self.relation_table = R.load_relation_table(table)
         return R.RelationPreprocessor(self.tokenizer, table)
 
+    @property
+    def top_k(self) -> int:
+        return self._top_k
+
+    @top_k.setter
+    def top_k(self, k: int) -> None:
+        """inference.py:346 re-assigns ``model.top_k`` between runs ("dynamic top-k"): the engines that already exist
+        follow (the weights do not depend on k; retrieved inputs are cut to the first k exemplars)."""
+        self._top_k = int(k)
+        eng = getattr(self, "_engine", None)
+        if eng is not None:
+            eng.top_k = self._top_k
+        te = getattr(self, "_train_engine", None)
+        if te is not None:
+            te.infer.top_k = self._top_k
+
     # ---- nn.Module plumbing --------------------------------------------------------------------
     @property
     def device(self) -> torch.device:

@@ -131,3 +131,17 @@ def test_state_dict_contract_pku():
     np.testing.assert_array_equal(enc["mask"].numpy(), z["mask"])
     np.testing.assert_array_equal(tok.token_mask.numpy(), z["token_mask"])
     assert [tok.name_to_id("pad"), tok.name_to_id("bos"), tok.name_to_id("eos")] == z["special"].tolist()
+
+
+def test_dynamic_top_k_reaches_existing_engines():
+    """inference.py:290,346 reads and re-assigns model.top_k between runs."""
+    import types
+
+    from ralf_b200 import generator as G
+
+    m = G.RALF(features=None, tokenizer=helpers.make_tokenizer(), dataset_name="cgl", max_seq_length=10, top_k=16)
+    assert m.top_k == 16
+    m._engine = types.SimpleNamespace(top_k=16)
+    m._train_engine = types.SimpleNamespace(infer=types.SimpleNamespace(top_k=16))
+    m.top_k = 8
+    assert m.top_k == 8 and m._engine.top_k == 8 and m._train_engine.infer.top_k == 8
