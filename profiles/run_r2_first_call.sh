@@ -2,7 +2,7 @@
 # First GPU call of round 2 (run under gpurun from the repo root, ~12 min of box time):
 #   1. the hw_pending tests (written after round 1's GPU budget was spent), then the whole -m gpu suite;
 #   2. A/B bench lines for the opt-in variants that are built but unmeasured:
-#        baseline | RALF_GEMM_MINB=2 (two GEMM CTAs per SM for the short-K shapes) | RALF_ATTN_TC=2 (8-warp encoder attention) | --decode-ways 2/4 (parallel decode
+#        baseline | RALF_GEMM_MINB=2 (two GEMM CTAs per SM for the short-K shapes) | RALF_KNN_WAYS=2 (k-NN passes on parallel streams) | RALF_ATTN_TC=2 (8-warp encoder attention) | --decode-ways 2/4 (parallel decode
 #        chains inside a batch) | --overlap (two batches in flight) | RALF_GEMM_RESERVE_SMS
 # Outputs: gpurun_out/r2_*.{log,json}.  Nothing here is a bench value by itself: copy what is kept into profiles/.
 set -x
@@ -12,6 +12,7 @@ timeout 1500 python -m pytest tests -x -q -m gpu -p no:cacheprovider > gpurun_ou
 B="--steps 5 --warmup 3 --no-cpu-baseline"
 timeout 600 python bench.py $B > gpurun_out/r2_bench_base.json 2> gpurun_out/r2_bench_base.err
 RALF_GEMM_MINB=2 timeout 600 python bench.py $B > gpurun_out/r2_bench_minb2.json 2> gpurun_out/r2_bench_minb2.err
+RALF_KNN_WAYS=2 timeout 600 python bench.py $B > gpurun_out/r2_bench_knnways2.json 2> gpurun_out/r2_bench_knnways2.err
 RALF_ATTN_TC=2 timeout 600 python bench.py $B > gpurun_out/r2_bench_attn2.json 2> gpurun_out/r2_bench_attn2.err
 timeout 600 python bench.py $B --decode-ways 2 > gpurun_out/r2_bench_ways2.json 2> gpurun_out/r2_bench_ways2.err
 timeout 600 python bench.py $B --decode-ways 4 > gpurun_out/r2_bench_ways4.json 2> gpurun_out/r2_bench_ways4.err

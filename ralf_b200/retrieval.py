@@ -18,6 +18,7 @@ queries, the per-rank [Q,k] (score, global index) lists are all-gathered (NCCL) 
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -43,13 +44,40 @@ class GpuRetriever:
         if layouts is not None:
             self.table = torch.stack([layouts[k].to(self.dev, torch.float32) for k in LAYOUT_KEYS], dim=1).contiguous()
         self._ws: Optional[torch.Tensor] = None
+        # Opt-in (unmeasured): passes of 128 queries on `knn_ways` parallel streams.  A pass is pre-pass -> threshold ->
+        # scan -> re-rank; the scan runs at the HBM roofline, the three small kernels around it are latency bound
+        # (51 of the 360 us of a pass, profiles/r1_launches_l_summary.md) and can hide under another pass's scan.
+        self.knn_ways = max(1, int(os.environ.get("RALF_KNN_WAYS", "1")))
+        self._way_streams: list = []
 
     # -- search ---------------------------------------------------------------------------------
     def search_local(self, queries: torch.Tensor, k: int):
         """Top-k of this rank's shard for every query: (idx int64 [Q,k] global ids, score fp32 [Q,k])."""
         q = queries.to(self.dev, torch.float32).contiguous()
+        if self.knn_ways > 1 and q.shape[0] > 128:
+            return self._search_local_ways(q, k)
         idx, score, cert = ops.knn_topk(self.emb, q, k, index_base=self.index_base, gallery_max_norm=self.max_norm,
                                         workspace=self._ws)
+        self.last_certified = cert
+        return idx, score
+
+    def _search_local_ways(self, q: torch.Tensor, k: int):
+        """The same passes as ralf_knn_topk runs internally (128 queries each, independent of one another), issued
+        round-robin on parallel streams with a workspace each; fork / join around them, so inside a graph capture they
+        become parallel branches.  Results are identical to the single-stream call."""
+        if len(self._way_streams) < self.knn_ways:
+            self._way_streams = [torch.cuda.Stream(device=self.dev) for _ in range(self.knn_ways)]
+        cur = torch.cuda.current_stream()
+        parts = []
+        for s in self._way_streams:
+            s.wait_stream(cur)
+        for n, q0 in enumerate(range(0, q.shape[0], 128)):
+            with torch.cuda.stream(self._way_streams[n % self.knn_ways]):
+                parts.append(ops.knn_topk(self.emb, q[q0:q0 + 128], k, index_base=self.index_base,
+                                          gallery_max_norm=self.max_norm))
+        for s in self._way_streams:
+            cur.wait_stream(s)
+        idx, score, cert = (torch.cat([p[i] for p in parts]) for i in range(3))
         self.last_certified = cert
         return idx, score
 

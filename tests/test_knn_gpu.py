@@ -142,3 +142,33 @@ def test_flat_ip_index_as_hf_custom_index(cuda_device, monkeypatch):
     np.testing.assert_array_equal(i, oi)
     np.testing.assert_array_equal(s.view(np.uint32), os_.view(np.uint32))
     np.testing.assert_array_equal(index.reconstruct(123), G[123])
+
+
+@pytest.mark.hw_pending
+def test_knn_passes_on_parallel_streams_equal_single_stream(cuda_device):
+    """GpuRetriever.knn_ways > 1 (passes of 128 queries round-robin on parallel streams) returns what the single-stream
+    call returns, eagerly and as parallel branches of a captured graph."""
+    from ralf_b200.retrieval import GpuRetriever
+
+    G, Q = _data(30000, 512, 700, seed=3)
+    retr = GpuRetriever(torch.from_numpy(G), device=cuda_device)
+    q = torch.from_numpy(Q).to(cuda_device)
+    want_i, want_s = retr.search_local(q, 16)
+    for ways in (2, 3):
+        retr.knn_ways = ways
+        got_i, got_s = retr.search_local(q, 16)
+        torch.cuda.synchronize()
+        assert torch.equal(got_i, want_i) and torch.equal(got_s, want_s) and int(retr.last_certified.sum()) == 700
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        retr.search_local(q, 16)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = retr.search_local(q, 16)
+    for _ in range(2):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out[0], want_i) and torch.equal(out[1], want_s)
