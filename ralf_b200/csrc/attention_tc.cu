@@ -525,13 +525,238 @@ attention_tc2_kernel(const float* __restrict__ q, const int ldq, const float* __
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Variant for 256 < Tk <= 480 keys (RALF_ATTN_TC_BIG=1; built, not yet run on hardware): the reference's real canvases
+// are 350 x 240 -> 22 x 15 = 330 image tokens, which the kernels above hand to the CUDA-core fallback.
+// S[128, Tk] no longer leaves room for separate P planes in the 512 TMEM columns, so P is written IN PLACE: a thread
+// that has read its 32 S columns [c, c + 32) of a chunk stores the chunk's P as 16 hi columns [c, c + 16) and 16 lo
+// columns [c + 16, c + 32) over them (same lane, so no other thread or MMA is affected), and the P.V MMAs take their
+// A operand of k-step ks (keys 16 ks .. 16 ks + 15) from column 32 (ks / 2) + 8 (ks % 2) (+ 16 for lo).  O gets its own
+// columns [480, 512).  S is issued as two MMA groups (an MMA is at most 256 wide): keys [0, 256) and [256, 256 + N2).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int ATCB_MAX_KEYS = 480;
+constexpr int ATCB_K_BYTES = ATCB_MAX_KEYS * 128;
+constexpr int ATCB_VT_PLANE = 8 * 32 * 128;  // 8 key blocks of 64 keys
+constexpr int ATCB_SMEM = ATC_Q_BYTES + ATCB_K_BYTES + 2 * ATCB_VT_PLANE + 1024 + 64;
+
+__global__ void __launch_bounds__(128, 1)
+attention_tc_big_kernel(const float* __restrict__ q, const int ldq, const float* __restrict__ k,
+                        const float* __restrict__ v, const int ldk, const int Tq, const int Tk, const float scale,
+                        __nv_bfloat16* __restrict__ out_split, const long long out_plane, float* __restrict__ out_f32,
+                        const int ldo) {
+  constexpr int DH = 32;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + ATC_Q_BYTES;
+  uint8_t* sVt = sK + ATCB_K_BYTES;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sVt + 2 * ATCB_VT_PLANE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int n2 = ((Tk - 256) + 15) & ~15;  // width of the second S group (keys 256 .. 256 + n2), 16 .. 224
+  const int nks = (Tk + 15) >> 4;          // P.V k-steps that hold real keys
+  const int krows = 256 + n2;              // K rows the S MMAs read
+
+  // ---- K rows -> [hi | lo] swizzled rows, zero beyond Tk ----
+#pragma unroll 1
+  for (int j = tid; j < krows; j += 128) {
+    float4 kr[8];
+    const float* src = k + (static_cast<long long>(b) * Tk + j) * ldk + h * DH;
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      kr[g] = (j < Tk) ? *reinterpret_cast<const float4*>(src + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 hi, lo;
+      split8(kr[2 * g], kr[2 * g + 1], hi, lo);
+      *reinterpret_cast<uint4*>(sK + j * 128 + ((g ^ (j & 7)) << 4)) = hi;
+      *reinterpret_cast<uint4*>(sK + j * 128 + (((g + 4) ^ (j & 7)) << 4)) = lo;
+    }
+  }
+  // ---- V -> V^T key blocks (both planes), key pairs; zero beyond Tk up to the last k-step ----
+#pragma unroll 1
+  for (int j = 2 * tid; j < nks * 16; j += 256) {
+    float4 vr[2][8];
+    const float* src = v + (static_cast<long long>(b) * Tk + j) * ldk + h * DH;
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        vr[u][g] = (j + u < Tk) ? *reinterpret_cast<const float4*>(src + static_cast<long long>(u) * ldk + 4 * g)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int kb = j >> 6, jj = j & 63;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float fa[4] = {vr[0][g].x, vr[0][g].y, vr[0][g].z, vr[0][g].w};
+      const float fc[4] = {vr[1][g].x, vr[1][g].y, vr[1][g].z, vr[1][g].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int d = 4 * g + e;
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(fa[e], h0, l0);
+        split_bf16(fc[e], h1, l1);
+        const int off = kb * 4096 + d * 128 + (((jj >> 3) ^ (d & 7)) << 4) + (jj & 7) * 2;
+        *reinterpret_cast<uint32_t*>(sVt + off) = pack_bf16(h0, h1);
+        *reinterpret_cast<uint32_t*>(sVt + ATCB_VT_PLANE + off) = pack_bf16(l0, l1);
+      }
+    }
+  }
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tO = tmem_base + ATCB_MAX_KEYS;
+  const uint32_t trow = static_cast<uint32_t>(warp * 32) << 16;
+  uint32_t phase = 0;
+
+  for (int q0 = 0; q0 < Tq; q0 += 128) {
+    {
+      const int r = tid;
+      float4 qr[8];
+      const float* src = q + (static_cast<long long>(b) * Tq + q0 + r) * ldq + h * DH;
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        qr[g] = (q0 + r < Tq) ? *reinterpret_cast<const float4*>(src + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 hi, lo;
+        split8(qr[2 * g], qr[2 * g + 1], hi, lo);
+        *reinterpret_cast<uint4*>(sQ + r * 128 + ((g ^ (r & 7)) << 4)) = hi;
+        *reinterpret_cast<uint4*>(sQ + r * 128 + (((g + 4) ^ (r & 7)) << 4)) = lo;
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();  // (also orders the previous tile's TMEM reads before the MMAs below)
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t dq = make_sw128_kmajor_desc(smem_u32(sQ));
+      for (int grp = 0; grp < 2; ++grp) {
+        const uint32_t idesc_s = make_idesc(1, 128, grp == 0 ? 256u : static_cast<uint32_t>(n2));
+        const uint64_t dk = make_sw128_kmajor_desc(smem_u32(sK) + grp * 256 * 128);
+        const uint32_t td = tS + grp * 256;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          mma_bf16_ss(td, dq + 2 * s, dk + 4 + 2 * s, idesc_s, s != 0);
+          mma_bf16_ss(td, dq + 4 + 2 * s, dk + 2 * s, idesc_s, 1);
+          mma_bf16_ss(td, dq + 2 * s, dk + 2 * s, idesc_s, 1);
+        }
+      }
+      tc_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- softmax: thread = query row; P overwrites S chunk by chunk ----
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < Tk; c += 32) {
+      uint32_t sv[32];
+      tmem_ld_32x32(tS + trow + c, sv);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (c + j < Tk) ? __uint_as_float(sv[j]) : -INFINITY);
+    }
+    float lsum = 0.f;
+    const float sl2 = scale * 1.4426950408889634f, mxs = mx * sl2;
+#pragma unroll 1
+    for (int c = 0; c < nks * 16; c += 32) {
+      uint32_t ph[16], pl[16];
+      uint32_t sv[32];
+      tmem_ld_32x32(tS + trow + c, sv);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const float p0 = (c + j < Tk) ? exp2f(fmaf(__uint_as_float(sv[j]), sl2, -mxs)) : 0.f;
+        const float p1 = (c + j + 1 < Tk) ? exp2f(fmaf(__uint_as_float(sv[j + 1]), sl2, -mxs)) : 0.f;
+        lsum += p0 + p1;
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(p0, h0, l0);
+        split_bf16(p1, h1, l1);
+        ph[j >> 1] = pack_bf16(h0, h1);
+        pl[j >> 1] = pack_bf16(l0, l1);
+      }
+      tmem_st_32x16(tS + trow + c, ph);       // hi of keys c .. c + 31 (2 keys per column)
+      tmem_st_32x16(tS + trow + c + 16, pl);  // lo
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      constexpr uint32_t idesc_o = make_idesc(1, 128, 32);
+      for (int ks = 0; ks < nks; ++ks) {
+        const uint32_t vt = smem_u32(sVt) + (ks >> 2) * 4096;
+        const uint64_t bh = make_sw128_kmajor_desc(vt) + 2 * (ks & 3);
+        const uint64_t bl = make_sw128_kmajor_desc(vt + ATCB_VT_PLANE) + 2 * (ks & 3);
+        const uint32_t ah = tS + 32 * (ks >> 1) + 8 * (ks & 1), al = ah + 16;
+        mma_bf16_ts(tO, ah, bl, idesc_o, ks != 0);
+        mma_bf16_ts(tO, al, bh, idesc_o, 1);
+        mma_bf16_ts(tO, ah, bh, idesc_o, 1);
+      }
+      tc_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    {
+      uint32_t ov[32];
+      tmem_ld_32x32(tO + trow, ov);
+      tmem_ld_wait();
+      const int r = q0 + tid;
+      if (r < Tq) {
+        const float inv = 1.f / lsum;
+        const long long orow = (static_cast<long long>(b) * Tq + r) * ldo + h * DH;
+        if (out_f32) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(out_f32 + orow + j) =
+                make_float4(__uint_as_float(ov[j]) * inv, __uint_as_float(ov[j + 1]) * inv,
+                            __uint_as_float(ov[j + 2]) * inv, __uint_as_float(ov[j + 3]) * inv);
+        }
+        if (out_split) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(__uint_as_float(ov[j + 2 * e]) * inv, h0, l0);
+              split_bf16(__uint_as_float(ov[j + 2 * e + 1]) * inv, h1, l1);
+              hw[e] = pack_bf16(h0, h1);
+              lw[e] = pack_bf16(l0, l1);
+            }
+            *reinterpret_cast<uint4*>(out_split + orow + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(out_split + out_plane + orow + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // Returns 1 when the tensor-core kernel took the call, 0 when the shape is outside its class, < 0 on error.
 int attention_tc_try(const float* q, int ldq, const float* k, const float* v, int ldk, const unsigned char* mask, int B,
                      int H, int Tq, int Tk, int head_dim, int causal, float scale, void* out_split,
                      long long out_plane, float* out_f32, int ldo, cudaStream_t st) {
   static const int variant = getenv("RALF_ATTN_TC") ? atoi(getenv("RALF_ATTN_TC")) : 1;  // 0 off, 1 default, 2 = 8-warp kernel
   const bool enabled = variant != 0;
-  if (!enabled || mask || causal || head_dim != 32 || Tk > 256 || Tk < 64 || Tq < 64) return 0;
+  static const bool big = getenv("RALF_ATTN_TC_BIG") && atoi(getenv("RALF_ATTN_TC_BIG")) != 0;
+  const bool use_big = big && Tk > 256 && Tk <= ATCB_MAX_KEYS;
+  if (!enabled || mask || causal || head_dim != 32 || (Tk > 256 && !use_big) || Tk < 64 || Tq < 64) return 0;
   if ((ldq & 3) || (ldk & 3) || (ldo & 7) || (reinterpret_cast<uintptr_t>(out_split) & 15) ||
       (reinterpret_cast<uintptr_t>(out_f32) & 15) || (out_plane & 7))
     return 0;
@@ -543,6 +768,19 @@ int attention_tc_try(const float* q, int ldq, const float* k, const float* v, in
                                cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return set_cuda_error(e);
     attr_set = true;
+  }
+  if (use_big) {
+    static bool attrb_set = false;
+    if (!attrb_set) {
+      cudaError_t e = cudaFuncSetAttribute(attention_tc_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATCB_SMEM);
+      if (e != cudaSuccess) return set_cuda_error(e);
+      attrb_set = true;
+    }
+    attention_tc_big_kernel<<<dim3(H, B), 128, ATCB_SMEM, st>>>(q, ldq, k, v, ldk, Tq, Tk, scale,
+                                                                reinterpret_cast<__nv_bfloat16*>(out_split), out_plane,
+                                                                out_f32, ldo);
+    const int rcb = set_cuda_error(cudaGetLastError());
+    return rcb ? rcb : 1;
   }
   if (variant == 2) {
     static bool attr2_set = false;

@@ -157,23 +157,14 @@ def test_fidnet_attention_fewkeys_with_padding_matches_fp64(cuda_device, N, T, H
     assert err < 2e-5, err
 
 
-@pytest.mark.hw_pending
-def test_encoder_attention_tcgen05_two_threads_per_row_variant(cuda_device):
-    """RALF_ATTN_TC=2 selects attention_tc2_kernel (256 threads: two threads per query row, key columns split in halves).
-    The selector is read once per process, so the check runs in a child process: same fp64 bar as the default kernel, and
-    bit-identical output to the default kernel wherever one half holds all the keys (Tk <= 128: the row sum has one term)."""
-    import os
-    import subprocess
-    import sys
-
-    code = r'''
-import torch, sys
-sys.path.insert(0, %r)
+_CHILD = r'''
+import json, sys, torch
+sys.path.insert(0, sys.argv[1])
 from ralf_b200 import ops
 dev = torch.device("cuda:0")
 dh, H = 32, 8
 D = H * dh
-for B, Tq, Tk in [(3, 256, 256), (2, 200, 200), (5, 128, 64), (1, 300, 150), (130, 256, 256), (2, 130, 128)]:
+for B, Tq, Tk in json.loads(sys.argv[3]):
     g = torch.Generator(device=dev).manual_seed(B + Tq + Tk)
     q = torch.randn(B * Tq, D, device=dev, generator=g) * 1.5
     kv = torch.randn(B * Tk, 2 * D, device=dev, generator=g) * 1.5
@@ -184,26 +175,48 @@ for B, Tq, Tk in [(3, 256, 256), (2, 200, 200), (5, 128, 64), (1, 300, 150), (13
     ref = (torch.softmax(qd @ kd.transpose(-1, -2) * dh ** -0.5, -1) @ vd).permute(0, 2, 1, 3).reshape(B * Tq, D)
     err = (out - ref).abs().max().item() / ref.abs().max().item()
     assert err <= 3e-5, (B, Tq, Tk, err)
-    torch.save(out.cpu(), sys.argv[1] + f"_{B}_{Tq}_{Tk}.pt")
+    torch.save(out.cpu(), sys.argv[2] + f"_{B}_{Tq}_{Tk}.pt")
 print("ok")
-''' % helpers_root()
+'''
+
+
+def _attention_in_child(env: dict, shapes: list) -> dict:
+    """The kernel selectors (RALF_ATTN_TC, RALF_ATTN_TC_BIG) are read once per process: run the fp64 check of
+    test_encoder_attention_tcgen05_matches_fp64 in a child with `env` and hand back its outputs per shape."""
+    import json
+    import os
+    import subprocess
+    import sys
     import tempfile
 
-    with tempfile.TemporaryDirectory() as tmp:
-        outs = {}
-        for variant in ("1", "2"):
-            env = dict(os.environ, RALF_ATTN_TC=variant)
-            r = subprocess.run([sys.executable, "-c", code, os.path.join(tmp, "v" + variant)], env=env, capture_output=True,
-                               text=True, timeout=600)
-            assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
-            outs[variant] = {f: torch.load(os.path.join(tmp, f)) for f in os.listdir(tmp) if f.startswith("v" + variant)}
-        a, b = outs["1"]["v1_5_128_64.pt"], outs["2"]["v2_5_128_64.pt"]
-        assert torch.equal(a, b)
-        a, b = outs["1"]["v1_2_130_128.pt"], outs["2"]["v2_2_130_128.pt"]
-        assert torch.equal(a, b)
-
-
-def helpers_root():
     from tests import helpers
 
-    return helpers.ROOT
+    with tempfile.TemporaryDirectory() as tmp:
+        r = subprocess.run([sys.executable, "-c", _CHILD, helpers.ROOT, os.path.join(tmp, "o"), json.dumps(shapes)],
+                           env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+        return {tuple(sh): torch.load(os.path.join(tmp, "o_%d_%d_%d.pt" % tuple(sh))) for sh in shapes}
+
+
+@pytest.mark.hw_pending
+def test_encoder_attention_tcgen05_two_threads_per_row_variant(cuda_device):
+    """RALF_ATTN_TC=2 selects attention_tc2_kernel (256 threads: two threads per query row, key columns split in halves):
+    same fp64 bar as the default kernel, and bit-identical to it wherever one half holds all the keys (Tk <= 128: the
+    row sum has a single term)."""
+    shapes = [[3, 256, 256], [2, 200, 200], [5, 128, 64], [1, 300, 150], [130, 256, 256], [2, 130, 128]]
+    one = _attention_in_child({"RALF_ATTN_TC": "1"}, shapes)
+    two = _attention_in_child({"RALF_ATTN_TC": "2"}, shapes)
+    assert torch.equal(one[(5, 128, 64)], two[(5, 128, 64)]) and torch.equal(one[(2, 130, 128)], two[(2, 130, 128)])
+    assert not torch.equal(one[(130, 256, 256)], two[(130, 256, 256)])  # (left) + (right) row sums: the other kernel ran
+
+
+@pytest.mark.hw_pending
+def test_encoder_attention_tcgen05_more_than_256_keys(cuda_device):
+    """RALF_ATTN_TC_BIG=1: 256 < Tk <= 480 (the reference's real 350 x 240 canvases give 330 image tokens) on the tensor
+    cores with P written in place over S in TMEM; without the switch these shapes take the CUDA-core kernel."""
+    shapes = [[2, 330, 330], [1, 300, 257], [3, 480, 480], [2, 128, 400], [1, 200, 272], [130, 330, 330]]
+    big = _attention_in_child({"RALF_ATTN_TC_BIG": "1"}, shapes)
+    base = _attention_in_child({"RALF_ATTN_TC_BIG": "0"}, shapes)
+    assert any(not torch.equal(big[k], base[k]) for k in big)  # a different kernel produced them
+    for k in big:
+        assert (big[k] - base[k]).abs().max().item() <= 6e-5 * base[k].abs().max().item()
