@@ -151,3 +151,51 @@ def test_parallel_decode_chains_equal_single_chain(cuda_device):
             got = pipe.generate_layouts(img, q)
             np.testing.assert_array_equal(got["seq"].numpy(), want["seq"].numpy(), err_msg=f"{ways=} {graph=}")
             np.testing.assert_array_equal(got["retrieved_idx"].numpy(), want["retrieved_idx"].numpy())
+
+
+@pytest.mark.hw_pending
+def test_bench_shape_batch_invariance_and_token_validity(cuda_device):
+    """Size-independent properties at the bench's shape (256 x 256 canvases, E = 12 -> 60 tokens, micro-batches of 128):
+    (1) a canvas's tokens do not depend on what else is in the batch -- the 512-canvas graph pipeline equals the eager
+    model API run on chunks of 64; (2) every token is allowed at its position by the tokenizer's mask; (3) the retrieved
+    ids are sorted by score and their scores are the canonical dot products (spot-checked against the C oracle)."""
+    from ralf_b200.generator import ConditionalInputs
+    from ralf_b200.pipeline import LayoutPipeline
+    from ralf_b200.retrieval import GpuRetriever
+
+    B, E, n, HW = 512, 12, 200_000, 256
+    g = torch.Generator(device=cuda_device).manual_seed(1)
+    emb = torch.randn(n, 512, device=cuda_device, generator=g)
+    emb = emb / emb.norm(dim=1, keepdim=True)
+    gl = torch.Generator().manual_seed(2)
+    cnt = torch.randint(1, E + 1, (n,), generator=gl)
+    mask = torch.arange(E)[None] < cnt[:, None]
+    lay = {"mask": mask, "label": torch.randint(0, 4, (n, E), generator=gl) * mask}
+    for k in ["center_x", "center_y", "width", "height"]:
+        lay[k] = torch.rand(n, E, generator=gl) * mask
+    from ralf_b200 import generator as G
+    from oracle import synth
+
+    tok = helpers.make_tokenizer(max_seq_length=E)
+    model = G.RALF(features=None, tokenizer=tok, dataset_name="cgl", max_seq_length=E, top_k=16, auxilary_task="uncond")
+    schema = {k: {"shape": list(v.shape), "dtype": str(v.dtype).replace("torch.", "")} for k, v in model.state_dict().items()}
+    model.load_state_dict(synth.synth_state_dict(schema, seed=0), strict=True)
+    model = model.eval().to(cuda_device)
+    retr = GpuRetriever(emb, lay, device=cuda_device)
+    img = torch.rand(B, 4, HW, HW, generator=gl)
+    qry = torch.nn.functional.normalize(torch.randn(B, 512, generator=gl), dim=1)
+    out = LayoutPipeline(model, retr, B, HW, HW, micro_batch=128).generate_layouts(img, qry)
+    seq, idx = out["seq"], out["retrieved_idx"]
+    assert seq.shape == (B, tok.max_token_length)
+    allowed = tok.token_mask.bool()  # [S, V]
+    assert bool(allowed[torch.arange(seq.shape[1])[None].expand_as(seq), seq].all())
+    i2, s2 = retr.search(qry.to(cuda_device), 16)
+    assert torch.equal(i2.cpu(), idx) and bool((s2[:, :-1] >= s2[:, 1:]).all())
+    rows = [0, 255, 511]
+    oi, os_ = oracle_knn.topk(emb.cpu().numpy(), qry[rows].numpy(), 16)
+    np.testing.assert_array_equal(idx[rows].numpy(), oi)
+    np.testing.assert_array_equal(s2[rows].cpu().numpy().view(np.uint32), os_.view(np.uint32))
+    for b0 in range(0, B, 64):  # eager model API on chunks of 64: same tokens canvas for canvas
+        cond = ConditionalInputs(image=img[b0:b0 + 64].to(cuda_device), retrieved=retr.fetch(i2[b0:b0 + 64]))
+        ref = model.sample(cond=cond, cond_type="uncond", return_seq=True)
+        np.testing.assert_array_equal(seq[b0:b0 + 64].numpy(), ref["seq"].numpy(), err_msg=f"chunk at {b0}")
