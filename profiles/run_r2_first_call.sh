@@ -7,7 +7,7 @@
 # Outputs: gpurun_out/r2_*.{log,json}.  Nothing here is a bench value by itself: copy what is kept into profiles/.
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -q -m "gpu and hw_pending" -p no:cacheprovider > gpurun_out/r2_pending_tests.log 2>&1
+RALF_TEST_OPTIN=1 timeout 1500 python -m pytest tests -q -m "gpu and hw_pending" -p no:cacheprovider > gpurun_out/r2_pending_tests.log 2>&1
 timeout 1500 python -m pytest tests -x -q -m gpu -p no:cacheprovider > gpurun_out/r2_gpu_tests.log 2>&1
 B="--steps 5 --warmup 3 --no-cpu-baseline"
 timeout 600 python bench.py $B > gpurun_out/r2_bench_base.json 2> gpurun_out/r2_bench_base.err

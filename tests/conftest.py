@@ -10,12 +10,17 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
-    config.addinivalue_line("markers", "hw_pending: written after the round's GPU budget was spent, not yet run on a B200; "
-                                       "collected last so that under -x a failure here cannot mask the verified suite")
+    config.addinivalue_line("markers", "hw_pending(order=n): written after the round's GPU budget was spent, not yet run on a "
+                                       "B200; collected last (lowest order first) so that under -x a failure here cannot "
+                                       "mask the verified suite")
 
 
 def pytest_collection_modifyitems(config, items):
-    items.sort(key=lambda it: it.get_closest_marker("hw_pending") is not None)  # stable: file order kept otherwise
+    def key(it):  # stable sort: verified tests keep their file order; pending ones follow, lowest `order` (least new machinery) first
+        m = it.get_closest_marker("hw_pending")
+        return (0, 0) if m is None else (1, m.kwargs.get("order", 50))
+
+    items.sort(key=key)
 
 
 @pytest.fixture(scope="session")

@@ -114,7 +114,7 @@ def test_knn_adversarial_row_order(cuda_device):
         assert cert.cpu().numpy().all()
 
 
-@pytest.mark.hw_pending
+@pytest.mark.hw_pending(order=3)
 def test_flat_ip_index_as_hf_custom_index(cuda_device, monkeypatch):
     """FlatIPIndex behind HF datasets' FaissIndex (``custom_index=``), the reference's own route to FAISS
     (retrieval/retriever.py:79-84,200-202): neighbours and scores bit-exact against the C oracle, host arrays in/out."""
@@ -144,7 +144,7 @@ def test_flat_ip_index_as_hf_custom_index(cuda_device, monkeypatch):
     np.testing.assert_array_equal(index.reconstruct(123), G[123])
 
 
-@pytest.mark.hw_pending
+@pytest.mark.hw_pending(order=30)
 def test_knn_passes_on_parallel_streams_equal_single_stream(cuda_device):
     """GpuRetriever.knn_ways > 1 (passes of 128 queries round-robin on parallel streams) returns what the single-stream
     call returns, eagerly and as parallel branches of a captured graph."""

@@ -103,7 +103,7 @@ def test_engine_batch_matches_oracle_with_margin(cuda_device):
         assert margin < LOGIT_RTOL, f"canvas {b} diverges at step {t} with oracle margin {margin:.3e}"
 
 
-@pytest.mark.hw_pending
+@pytest.mark.hw_pending(order=2)
 def test_engine_matches_reference_golden_pku(cuda_device):
     """BASELINE configs[2] names PKU (3 labels, vocabulary 518): memory within tolerance of the reference's own output;
     token ids equal, a divergence tolerated only where the oracle's top-2 margin at that step is below the logit
