@@ -677,6 +677,59 @@ def run_coarse_saliency():
     print("coarse_saliency", out.shape)
 
 
+def run_max_length():
+    """Maximum size the reference can be built with: max_seq_length = 11 (one RelElement letter A..K per element,
+    task_preprocessor.py:64-67) -> 55 tokens, every canvas and every exemplar FULL (11 elements).  Needs a FIDNet checkpoint
+    with max_bbox = 11 (fid/model.py:131-147 loads it strictly), written into a scratch dir of its own."""
+    import copy
+
+    from image2layout.train.fid.model import FIDNetV3
+    from image2layout.train.helpers.task import get_condition
+
+    work = "/tmp/ralf_ref_work11"
+    rb.bootstrap(work)
+    torch.manual_seed(0)
+    torch.save({"state_dict": FIDNetV3(num_label=4, max_bbox=11).state_dict()},
+               os.path.join(work, "tmp/fidnet/cgl/model_best.pth.tar"))
+    ralf, tok, _ = rb.make_ralf("cgl", 11)
+    with open(os.path.join(OUT, "schema_ralf_cgl_e11.json"), "w") as f:
+        json.dump(schema_of(ralf), f)
+    sd = synth.synth_state_dict(schema_of(ralf), seed=8)
+    ralf.load_state_dict(sd, strict=True)
+    ralf.eval()
+    B, H, W, E = 2, 128, 128, 11
+    batch = synth.synth_batch(B, H, W, E, 16, tok.N_label, seed=14)
+    g = torch.Generator().manual_seed(15)
+    for tgt in (batch, batch["retrieved"]):  # fill every slot
+        tgt["mask"] = torch.ones_like(tgt["mask"])
+        tgt["label"] = torch.randint(0, tok.N_label, tgt["label"].shape, generator=g)
+        for k in ["center_x", "center_y", "width", "height"]:
+            tgt[k] = torch.rand(tgt[k].shape, generator=g)
+    out = {f"batch_{k}": batch[k].numpy() for k in ["label", "mask", "center_x", "center_y", "width", "height"]}
+    out.update({f"retrieved_{k}": batch["retrieved"][k].numpy() for k in ["label", "mask", "center_x", "center_y", "width", "height"]})
+    with torch.no_grad():
+        inputs, targets = ralf.preprocess(copy.deepcopy(batch))
+        out["seq_in"], out["targets"] = inputs["seq"].numpy(), targets["seq"].numpy()
+        logits = ralf.train_loss(copy.deepcopy(inputs), targets)[0]["logits"]
+        out["logits"] = logits.numpy()
+        cond, _ = get_condition(copy.deepcopy(batch), "uncond", tok)
+        enc_in, _ = ralf._create_encoder_inputs(cond)
+        enc_in["retrieved"] = {k: v.type_as(cond.image) for k, v in enc_in["retrieved"].items() if torch.is_tensor(v)}
+        mem = ralf._encode_into_memory(enc_in)["memory"]
+        ids = ralf.special_token_ids
+        inp = torch.full((B, 1), ids["bos"])
+        for i in range(tok.max_token_length):
+            lg = ralf.decoder(tgt=inp, tgt_key_padding_mask=(inp == ids["pad"]), is_causal=True, memory=mem)[:, i].clone()
+            lg[:, ~tok.token_mask[i]] = -float("inf")
+            inp = torch.cat([inp, lg.argmax(dim=1, keepdim=True)], dim=1)
+    np.savez_compressed(os.path.join(OUT, "ralf_cgl_e11_128.npz"), memory=mem.numpy(), gen_seq=inp[:, 1:].numpy(),
+                        seq_layout_const=enc_in["seq_layout_const"].numpy(),
+                        seq_layout_const_pad_mask=enc_in["seq_layout_const_pad_mask"].numpy(), **out,
+                        meta=np.array(json.dumps({"B": B, "H": H, "W": W, "seed": 14, "weights_seed": 8, "E": E, "K": 16,
+                                                  "dataset": "cgl", "special": {k: int(v) for k, v in ids.items()}})))
+    print("ralf_cgl_e11_128", mem.shape, inp.shape)
+
+
 def main():
     rb.bootstrap("/tmp/ralf_ref_work")
     torch.backends.mha.set_fastpath_enabled(False)
@@ -686,6 +739,9 @@ def main():
         json.dump(schema_of(ralf), f)
     if "--relation-only" in sys.argv:
         run_relation()
+        return
+    if "--max-length-only" in sys.argv:
+        run_max_length()
         return
     if "--saliency-only" in sys.argv:
         run_coarse_saliency()
@@ -701,6 +757,7 @@ def main():
         run_collate_cases()
         run_relation()
         run_coarse_saliency()
+        run_max_length()
         return
     run(ralf, tok, "ralf_cgl_256", B=2, H=256, W=256, seed=1, is_ralf=True)
     run_tasks(tok, "tasks_cgl_256", B=2, H=256, W=256, seed=1)

@@ -177,3 +177,39 @@ def test_engine_matches_oracle_at_the_bench_shape_e12(cuda_device):
         top2 = torch.topk(lg_o[b, t], 2).values
         margin = float(top2[0] - top2[1]) / float(lg_o[b, t][torch.isfinite(lg_o[b, t])].abs().max())
         assert margin < LOGIT_RTOL, f"canvas {b} diverges at step {t} with oracle margin {margin:.3e}"
+
+
+@pytest.mark.hw_pending(order=4)
+def test_engine_matches_reference_golden_at_maximum_length(cuda_device):
+    """max_seq_length = 11 (the reference's upper limit, 55 tokens), every canvas and exemplar full: memory and
+    teacher-forced logits within tolerance of the reference's own output, greedy tokens equal (first-divergence rule)."""
+    from oracle import ralf_oracle as O
+    from ralf_b200.engine import Engine
+    from tests.test_oracle_golden import _e11_inputs
+
+    z, meta, batch, sd = _e11_inputs()
+    tok = helpers.make_tokenizer(max_seq_length=11)
+    B = meta["B"]
+    sc, spm = torch.from_numpy(z["seq_layout_const"]), torch.from_numpy(z["seq_layout_const_pad_mask"])
+    eng = Engine(sd, cuda_device, is_ralf=True)
+    mem, mem_s = eng.encode(helpers.image4(batch), batch["retrieved"], sc, spm)
+    assert _relerr(mem.cpu().numpy(), z["memory"]) < LOGIT_RTOL
+    seq_in = torch.from_numpy(z["seq_in"])
+    logits = eng.decoder_logits(seq_in, seq_in == meta["special"]["pad"], mem_s, B, mem.shape[1])
+    assert _relerr(logits.cpu().numpy(), z["logits"]) < LOGIT_RTOL
+    sp = meta["special"]
+    seq = eng.generate(mem_s, B, mem.shape[1], tok.token_mask, sp["bos"], sp["pad"], tok.max_token_length).cpu()
+    ref = torch.from_numpy(z["gen_seq"])
+    if not torch.equal(seq, ref):
+        torch.set_num_threads(8)
+        with torch.no_grad():
+            _, lg_o = O.greedy_sample(sd, torch.from_numpy(z["memory"]), tok.token_mask, sp["bos"], sp["pad"],
+                                      tok.max_token_length, return_logits=True)
+        for b in range(B):
+            diff = (seq[b] != ref[b]).nonzero()
+            if len(diff) == 0:
+                continue
+            t = int(diff[0])
+            top2 = torch.topk(lg_o[b, t], 2).values
+            margin = float(top2[0] - top2[1]) / float(lg_o[b, t][torch.isfinite(lg_o[b, t])].abs().max())
+            assert margin < LOGIT_RTOL, f"canvas {b} diverges at step {t} with oracle margin {margin:.3e}"
