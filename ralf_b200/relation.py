@@ -297,7 +297,6 @@ class RelationConstraint:
             allowed = self.token_mask[slot].nonzero().flatten()
             self.start[slot] = int(allowed[0])
             assert int(allowed[-3]) + 1 - self.start[slot] == self.nbin  # the bins, then two special tokens
-        self.label_ids = set(range(tok.N_label))
         self.types: Tensor = torch.zeros(0, dtype=torch.long)
 
     # ---- parsing ------------------------------------------------------------------------------------------------
