@@ -464,3 +464,20 @@ def test_model_sample_relation_without_backtracking_on_oracle_engine(fx, monkeyp
     for k in ["label", "mask", *GEO]:
         np.testing.assert_array_equal(out[k].numpy(), z[f"nobt_gen_{k}"], err_msg=k)
     assert [vio["total"], vio["viorated"]] == z["nobt_violation"].tolist()
+
+
+def test_model_preprocess_with_the_relation_task(fx, monkeypatch):
+    """Training entry point (train.py:432) of a model built with auxilary_task="relation" (configs/ralf_cgl/relation.sh):
+    preprocess() = get_condition -> RelationPreprocessor -> tokenizer.encode, same host RNG order as the reference, so
+    under the fixture's seed it yields the fixture's constraint sequence; teacher-forcing tensors keep their contract."""
+    z, meta, tok, batch, table = fx
+    model, full = _relation_model(fx, monkeypatch)
+    seed = meta["rng_seed"]["deterministic"]
+    random.seed(seed)
+    torch.manual_seed(seed)
+    inputs, targets = model.preprocess(copy.deepcopy(full))
+    np.testing.assert_array_equal(inputs["seq_layout_const"].numpy(), z["bt_deterministic_const_seq"])
+    np.testing.assert_array_equal(inputs["seq_layout_const_pad_mask"].numpy(), z["bt_deterministic_const_pad_mask"])
+    enc = tok.encode({k: full[k] for k in ["label", "mask", *GEO]})
+    assert torch.equal(inputs["seq"], enc["seq"][:, :-1]) and torch.equal(targets["seq"], enc["seq"][:, 1:])
+    assert inputs["image"].shape[1] == 4 and set(inputs["retrieved"]) >= {"label", "mask", *GEO}
