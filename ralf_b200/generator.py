@@ -272,6 +272,19 @@ class _B200LayoutModel(nn.Module):
         ids.setdefault("mask", -1)
         return ids
 
+    def postprocess(self, outputs: dict) -> dict:
+        """BaseModel.postprocess (base_model.py:367-389): token ids (``seq``) -- or ``logits`` [B, S, V], arg-maxed under the
+        tokenizer's per-position vocabulary mask -- to the layout dict {label, mask, center_x, center_y, width, height}."""
+        if "seq" in outputs:
+            seq = outputs["seq"]
+        else:
+            logits = outputs["logits"].detach().to(torch.float32).cpu().clone()
+            if logits.size(-1) == self.tokenizer.max_token_length:  # (B, C, S) layout of the diffusion models
+                logits = logits.permute(0, 2, 1)
+            logits[:, ~self.tokenizer.token_mask.bool()] = -float("inf")
+            seq = torch.argmax(logits, dim=-1)
+        return self.tokenizer.decode(seq.cpu())
+
     def compute_stats(self) -> None:
         n = sum(p.numel() for p in self.parameters()) / 1e6
         print(f"number of parameters: {n:.2f}M")

@@ -4,6 +4,7 @@ import json
 import os
 import re
 
+import numpy as np
 import pytest
 import torch
 
@@ -112,7 +113,6 @@ def test_state_dict_contract_pku():
     """BASELINE configs[2] names the PKU dataset (3 labels -> vocabulary 518, constraint vocabulary 548): key names, order,
     shapes and dtypes of the reference class built for PKU (tests/golden/schema_ralf_pku.json, dumped from the reference),
     and the PKU tokenizer's ids / per-position mask (tests/golden/tokenizer_pku.npz)."""
-    import numpy as np
 
     from oracle import synth
     from ralf_b200 import generator as G
@@ -167,3 +167,21 @@ def test_bench_reference_arm_prints_the_contract_line():
     r = subprocess.run([sys.executable, os.path.join(helpers.ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                        capture_output=True, text=True, timeout=120, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_postprocess_decodes_sequences_and_masked_logits():
+    """BaseModel.postprocess (base_model.py:367-389)."""
+    from ralf_b200 import generator as G
+
+    tok = helpers.make_tokenizer()
+    m = G.RALF(features=None, tokenizer=tok, dataset_name="cgl", max_seq_length=10)
+    z, _ = helpers.load_golden("ralf_cgl_256")
+    seq = torch.from_numpy(z["gen_seq"])
+    out = m.postprocess({"seq": seq})
+    for k in ["label", "mask", "center_x", "center_y", "width", "height"]:
+        np.testing.assert_array_equal(out[k].numpy(), z["gen_" + k])
+    logits = torch.from_numpy(z["gen_step_logits"])  # per-step logits of the greedy loop: argmax under the mask = gen_seq
+    noisy = torch.where(torch.isfinite(logits), logits, torch.full_like(logits, 1e9))  # the mask must be re-applied here
+    out2 = m.postprocess({"logits": noisy})
+    for k in ["label", "mask", "center_x", "center_y", "width", "height"]:
+        np.testing.assert_array_equal(out2[k].numpy(), z["gen_" + k])
