@@ -293,6 +293,21 @@ class _B200LayoutModel(nn.Module):
         pass
 
     def aggregate_sampling_config(self, sampling_cfg, test_cfg=None):
+        """base_model.py:148-186 for an autoregressive class: for ``cond_type == "refinement"`` the test config's
+        ``refine_mode / refine_offset_ratio / refine_lambda`` are copied into the sampling config (the keys the reference's
+        logit-adjustment code reads; the autoregressive sampler itself ignores them)."""
+        if test_cfg is not None and _cfg_get(test_cfg, "cond_type") == "refinement":
+            assert _cfg_get(test_cfg, "refine_lambda") > 0.0
+            try:
+                from omegaconf import open_dict  # struct-mode DictConfig needs it; plain dicts do not
+            except ImportError:
+                import contextlib
+
+                open_dict = contextlib.nullcontext
+            for name in ("mode", "offset_ratio", "lambda"):
+                key = f"refine_{name}"
+                with open_dict(sampling_cfg):
+                    sampling_cfg[key] = _cfg_get(test_cfg, key)
         return sampling_cfg
 
     # ---- multitask plumbing (retrieval_augmented_autoreg.py:707-750) --------------------------------
