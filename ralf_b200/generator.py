@@ -134,6 +134,56 @@ def _register(root: nn.Module, name: str, tensor: Tensor, kind: str) -> None:
         node.register_buffer(parts[-1], tensor)
 
 
+def _initial_value(name: str, shape: tuple, shapes: dict, is_ralf: bool = True) -> Tensor:
+    """Initial value of one floating-point state-dict entry, with the distribution the reference constructor leaves it in
+    (tests/golden/init_stats.json, dumped from freshly built reference models):
+      * every matrix of the three transformers (image encoder, constraint encoder, decoder): Xavier-uniform
+        (retrieval_augmented_autoreg.py:171-176, common/common.py:69-72,233-236);
+      * decoder embedding + output projection, constraint embedding, task embedding: N(0, 0.02) (common/common.py:74-82,
+        :225-226; retrieval_augmented_autoreg.py:694);
+      * LayerNorm / BatchNorm: ones and zeros, running statistics 0 / 1; attention in/out projection biases: zeros;
+      * every other Linear / Conv2d: PyTorch's default U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and bias.
+    The Autoreg baseline class never runs its ``init_weights`` (models/autoreg.py:85-93, ``weight_init`` off): there only
+    the constraint encoder is Xavier / N(0, 0.02) (:478-488), attention input projections keep nn.MultiheadAttention's own
+    Xavier default, and the decoder embedding stays nn.Embedding's N(0, 1).
+    Drawn from the global torch generator, like the reference (train.py seeds it)."""
+    leaf = name.rsplit(".", 1)[-1]
+    if leaf == "num_batches_tracked":
+        return torch.zeros(shape, dtype=torch.long)
+    if leaf == "running_var":
+        return torch.ones(shape)
+    if leaf == "running_mean" or leaf == "in_proj_bias" or name.endswith("out_proj.bias"):
+        return torch.zeros(shape)
+    small_normal = ("user_const_encoder.emb.weight", "task_emb.weight") + \
+        (("decoder.emb.weight", "decoder.head.1.weight") if is_ralf else ())
+    if name in small_normal:
+        return torch.randn(shape) * 0.02
+    if name == "decoder.emb.weight":
+        return torch.randn(shape)
+    if len(shape) == 1:
+        if leaf == "weight":
+            return torch.ones(shape)  # normalisation gains
+        sibling = shapes.get(name[:-len("bias")] + "weight")
+        if leaf != "bias" or sibling is None or len(sibling) == 1:
+            return torch.zeros(shape)  # normalisation shifts
+        fan_in = 1
+        for d_ in sibling[1:]:
+            fan_in *= d_
+        return (torch.rand(shape) * 2 - 1) * fan_in ** -0.5
+    fan_in = 1
+    for d_ in shape[1:]:
+        fan_in *= d_
+    xavier = ("transformer_encoder.", "decoder.transformer.", "user_const_encoder.encoder.") if is_ralf \
+        else ("user_const_encoder.encoder.",)
+    if len(shape) == 2 and (name.startswith(xavier) or leaf == "in_proj_weight"):
+        bound = (6.0 / (fan_in + shape[0])) ** 0.5
+    elif leaf == "weight" and name.endswith("emb_label.weight"):
+        return torch.randn(shape)  # nn.Embedding default (frozen FIDNet; replaced by its checkpoint)
+    else:
+        bound = fan_in ** -0.5
+    return (torch.rand(shape) * 2 - 1) * bound
+
+
 def _sine_pe(max_len=5000, d=256):
     from .engine import _sine_pe_1d
 
@@ -150,7 +200,7 @@ class _B200LayoutModel(nn.Module):
                  db_dataset: Any = None, d_model: int = 256, top_k: int = 16, retrieval_backbone: str = "saliency",
                  random_retrieval: bool = False, saliency_k: Any = 8, auxilary_task: Optional[str] = "uncond",
                  use_multitask: bool = False, use_flag_embedding: bool = True, precision: str = "bf16x3",
-                 relation_table: Any = None, **kwargs: Any) -> None:
+                 relation_table: Any = None, pretrained: bool = True, **kwargs: Any) -> None:
         super().__init__()
         if d_model != 256:
             raise NotImplementedError("the B200 kernels are specialised for d_model = 256 (reference default)")
@@ -170,8 +220,9 @@ class _B200LayoutModel(nn.Module):
         self.precision = precision
         self.relation_table = relation_table  # dict / path; None -> the reference's cache locations, read on first use
         self.preprocessor = self._make_preprocessor(auxilary_task)
-        g = torch.Generator().manual_seed(0)
-        for entry in param_schema(self.tokenizer.N_label, self.tokenizer.N_total, self.preprocessor.N_total, self.IS_RALF):
+        schema = param_schema(self.tokenizer.N_label, self.tokenizer.N_total, self.preprocessor.N_total, self.IS_RALF)
+        shapes = {entry[0]: entry[1] for entry in schema}
+        for entry in schema:
             name, shape = entry[0], entry[1]
             kind = entry[2] if len(entry) > 2 else "param"
             if kind == "pe":
@@ -180,16 +231,11 @@ class _B200LayoutModel(nn.Module):
                 t = torch.ones(shape, dtype=torch.long) if name == "flag_user_const" else torch.zeros(shape, dtype=torch.long)
             elif kind == "bool":
                 t = torch.zeros(shape, dtype=torch.bool)
-            elif name.endswith("running_var") or (len(shape) == 1 and name.endswith(".weight")):
-                t = torch.ones(shape)
-            elif len(shape) <= 1:
-                t = torch.zeros(shape)
-            else:  # placeholder init; real runs load a checkpoint (inference.py:319) or train from the reference init
-                fan_in = 1
-                for d_ in shape[1:]:
-                    fan_in *= d_
-                t = torch.randn(shape, generator=g) * (0.02 if "emb" in name else fan_in ** -0.5)
+            else:
+                t = _initial_value(name, shape, shapes, self.IS_RALF)
             _register(self, name, t, kind)
+        if pretrained:
+            self._load_pretrained_files()
         self._engine: Optional[Engine] = None
         self._train_engine = None
 
@@ -201,6 +247,52 @@ class _B200LayoutModel(nn.Module):
         assert tok.geo_quantization == "linear" and not tok.is_loc_vocab_shared, "only the linear tokenizer is mirrored"
         return LayoutSequenceTokenizer(list(tok._label_feature.names), tok.max_seq_length, tok.N_bbox_per_var,
                                        list(tok.var_order), list(tok.special_tokens))
+
+    def _load_pretrained_files(self) -> None:
+        """What the reference constructors read from disk, when the files are there (they are overwritten by a later
+        ``load_state_dict`` of a trained checkpoint; a from-scratch training run starts from them):
+        the ImageNet ResNet50 ``resnet50_a1_0-14fe96d1.pth`` (cwd, else ./cache/PRECOMPUTED_WEIGHT_DIR; common/image.py:36-48),
+        whose stem gets a 4th input channel = the mean of the three (:70-78), and the frozen layout encoder
+        ``tmp/fidnet/<dataset>/model_best.pth.tar`` (else ./cache/PRECOMPUTED_WEIGHT_DIR/fidnet/...; fid/model.py:131-169,
+        "pku" -> "pku10").  The reference asserts that they exist; here a missing file leaves the initial values in place."""
+        import logging
+        import os
+
+        log = logging.getLogger(__name__)
+        own = dict(self.named_parameters())
+        own.update(dict(self.named_buffers()))
+
+        def first(*paths):
+            return next((p for p in paths if os.path.exists(p)), None)
+
+        def copy_in(prefix: str, sd: dict) -> int:
+            n = 0
+            with torch.no_grad():
+                for k, v in sd.items():
+                    dst = own.get(prefix + k)
+                    if dst is not None and torch.is_tensor(v) and tuple(dst.shape) == tuple(v.shape):
+                        dst.copy_(v)
+                        n += 1
+            return n
+
+        weight_dir = os.path.join(".", "cache", "PRECOMPUTED_WEIGHT_DIR")
+        path = first("resnet50_a1_0-14fe96d1.pth", os.path.join(weight_dir, "resnet50_a1_0-14fe96d1.pth"))
+        if path is None:
+            log.info("resnet50_a1_0-14fe96d1.pth not found: the ResNet50 trunk keeps its initial values")
+        else:
+            sd = dict(torch.load(path, map_location="cpu", weights_only=True))
+            w = sd["conv1.weight"]
+            sd["conv1.weight"] = torch.cat([w, w.mean(dim=1, keepdim=True)], dim=1)
+            log.info("ResNet50 trunk: %d tensors from %s", copy_in("encoder.extractor.body.", sd), path)
+        if self.IS_RALF:
+            ds_name = "pku10" if self.dataset_name == "pku" else self.dataset_name
+            path = first(os.path.join("tmp", "fidnet", ds_name, "model_best.pth.tar"),
+                         os.path.join(weight_dir, "fidnet", ds_name, "model_best.pth.tar"))
+            if path is None:
+                log.info("FIDNetV3 checkpoint for %r not found: the layout encoder keeps its initial values", ds_name)
+            else:
+                sd = torch.load(path, map_location="cpu", weights_only=True)["state_dict"]
+                log.info("FIDNetV3 layout encoder: %d tensors from %s", copy_in("layout_encoer.", sd), path)
 
     def _make_preprocessor(self, task: Optional[str]) -> TaskPreprocessor:
         """PREPROCESSOR[task](tokenizer=...) (task_preprocessor.py:593-602).  The relation task reads its relationship

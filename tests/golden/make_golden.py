@@ -730,6 +730,27 @@ def run_max_length():
     print("ralf_cgl_e11_128", mem.shape, inp.shape)
 
 
+def run_init_stats():
+    """Freshly constructed reference models (before any weights are loaded over them): per state-dict key the mean / std /
+    min / max / numel of the initial values, for both classes.  Pins the initial distributions a from-scratch training run
+    starts from (xavier for the transformers, N(0, 0.02) for the decoder embedding / head, PyTorch defaults elsewhere;
+    ResNet50 + FIDNet come from the checkpoint files the constructors read)."""
+    out = {}
+    for name, make in [("ralf_cgl", lambda: rb.make_ralf("cgl")), ("autoreg_cgl", lambda: rb.make_autoreg("cgl"))]:
+        torch.manual_seed(1234)
+        model = make()[0]
+        stats = {}
+        for k, v in model.state_dict().items():
+            if not v.is_floating_point() or k.endswith(".pe"):
+                continue
+            v = v.double()
+            stats[k] = [float(v.mean()), float(v.std()) if v.numel() > 1 else 0.0, float(v.min()), float(v.max()), v.numel()]
+        out[name] = stats
+    with open(os.path.join(OUT, "init_stats.json"), "w") as f:
+        json.dump(out, f)
+    print("init_stats", {k: len(v) for k, v in out.items()})
+
+
 def main():
     rb.bootstrap("/tmp/ralf_ref_work")
     torch.backends.mha.set_fastpath_enabled(False)
@@ -739,6 +760,9 @@ def main():
         json.dump(schema_of(ralf), f)
     if "--relation-only" in sys.argv:
         run_relation()
+        return
+    if "--init-stats-only" in sys.argv:
+        run_init_stats()
         return
     if "--max-length-only" in sys.argv:
         run_max_length()
@@ -758,6 +782,7 @@ def main():
         run_relation()
         run_coarse_saliency()
         run_max_length()
+        run_init_stats()
         return
     run(ralf, tok, "ralf_cgl_256", B=2, H=256, W=256, seed=1, is_ralf=True)
     run_tasks(tok, "tasks_cgl_256", B=2, H=256, W=256, seed=1)

@@ -185,3 +185,81 @@ def test_postprocess_decodes_sequences_and_masked_logits():
     out2 = m.postprocess({"logits": noisy})
     for k in ["label", "mask", "center_x", "center_y", "width", "height"]:
         np.testing.assert_array_equal(out2[k].numpy(), z["gen_" + k])
+
+
+@pytest.mark.parametrize("cls_name,stats_key", [("RALF", "ralf_cgl"), ("ConcateAuxilaryTaskAutoreg", "autoreg_cgl")])
+def test_initial_values_follow_the_reference_distributions(cls_name, stats_key):
+    """A from-scratch training run must start where the reference's does: per state-dict entry, the freshly constructed
+    drop-in class against the statistics of the freshly constructed reference class (tests/golden/init_stats.json).
+    The ResNet50 trunk and the FIDNet layout encoder come from checkpoint files in both (next test)."""
+    from ralf_b200 import generator as G
+
+    with open(os.path.join(helpers.GOLDEN, "init_stats.json")) as f:
+        ref = json.load(f)[stats_key]
+    torch.manual_seed(99)
+    m = getattr(G, cls_name)(features=None, tokenizer=helpers.make_tokenizer(), dataset_name="cgl", max_seq_length=10)
+    checked = 0
+    for k, v in m.state_dict().items():
+        if k not in ref or k.startswith(("encoder.extractor.body.", "layout_encoer.")):
+            continue
+        mean, std, lo, hi, numel = ref[k]
+        v = v.double()
+        assert v.numel() == numel, k
+        if std == 0.0 and numel > 1:  # constants: LayerNorm gains / shifts, attention biases
+            assert float(v.min()) == lo and float(v.max()) == hi, k
+        elif numel >= 4096:
+            assert abs(float(v.std()) / std - 1) < 0.03, (k, float(v.std()), std)
+            assert abs(float(v.mean())) < 0.05 * std, k
+            if hi < 4 * std:  # a uniform distribution: the bounds agree too
+                assert abs(float(v.max()) / hi - 1) < 0.02 and abs(float(v.min()) / lo - 1) < 0.02, k
+        else:  # small tensors (biases): inside the reference's support, spread of the right order
+            bound = max(abs(lo), abs(hi))
+            assert float(v.abs().max()) <= bound * 1.6 + 1e-12, k
+            if numel >= 64:
+                assert 0.6 < float(v.std()) / std < 1.6, (k, float(v.std()), std)
+        checked += 1
+    assert checked > 150
+    # drawn from the global generator, like the reference: another seed, another model; same seed, same model
+    torch.manual_seed(99)
+    m2 = getattr(G, cls_name)(features=None, tokenizer=helpers.make_tokenizer(), dataset_name="cgl", max_seq_length=10)
+    assert torch.equal(m.state_dict()["decoder.emb.weight"], m2.state_dict()["decoder.emb.weight"])
+    m3 = getattr(G, cls_name)(features=None, tokenizer=helpers.make_tokenizer(), dataset_name="cgl", max_seq_length=10)
+    assert not torch.equal(m.state_dict()["decoder.emb.weight"], m3.state_dict()["decoder.emb.weight"])
+
+
+def test_constructor_reads_the_reference_weight_files(tmp_path, monkeypatch):
+    """common/image.py:36-48,70-78 and fid/model.py:131-169: ImageNet ResNet50 (4th stem channel = mean of the three) and
+    the frozen FIDNetV3 checkpoint, from the locations the reference looks in ("pku" -> "pku10")."""
+    from ralf_b200 import generator as G
+
+    g = torch.Generator().manual_seed(3)
+    probe = G.RALF(features=None, tokenizer=helpers.make_tokenizer("pku"), dataset_name="pku", max_seq_length=10)
+    own = probe.state_dict()
+    resnet = {k[len("encoder.extractor.body."):]: torch.randn(v.shape, generator=g) if v.is_floating_point() else v.clone()
+              for k, v in own.items() if k.startswith("encoder.extractor.body.")}
+    resnet["conv1.weight"] = torch.randn(64, 3, 7, 7, generator=g)
+    resnet["fc.weight"], resnet["fc.bias"] = torch.randn(1000, 2048, generator=g), torch.randn(1000, generator=g)
+    fid = {k[len("layout_encoer."):]: torch.randn(v.shape, generator=g) if v.is_floating_point() else v.clone()
+           for k, v in own.items() if k.startswith("layout_encoer.")}
+    fid["pos_token"] = torch.randn(10, 1, 256, generator=g)  # parts of the checkpoint the feature extractor drops
+    fid["fc_out_disc.weight"] = torch.randn(1, 256, generator=g)
+    os.makedirs(tmp_path / "cache" / "PRECOMPUTED_WEIGHT_DIR" / "fidnet" / "pku10")
+    torch.save(resnet, tmp_path / "cache" / "PRECOMPUTED_WEIGHT_DIR" / "resnet50_a1_0-14fe96d1.pth")
+    torch.save({"state_dict": fid, "epoch": 7}, tmp_path / "cache" / "PRECOMPUTED_WEIGHT_DIR" / "fidnet" / "pku10" / "model_best.pth.tar")
+    monkeypatch.chdir(tmp_path)
+    m = G.RALF(features=None, tokenizer=helpers.make_tokenizer("pku"), dataset_name="pku", max_seq_length=10)
+    sd = m.state_dict()
+    w = sd["encoder.extractor.body.conv1.weight"]
+    assert torch.equal(w[:, :3], resnet["conv1.weight"]) and torch.allclose(w[:, 3], resnet["conv1.weight"].mean(dim=1))
+    for k, v in resnet.items():
+        if k not in ("conv1.weight", "fc.weight", "fc.bias"):
+            assert torch.equal(sd["encoder.extractor.body." + k], v), k
+    for k, v in fid.items():
+        if k not in ("pos_token", "fc_out_disc.weight"):
+            assert torch.equal(sd["layout_encoer." + k], v), k
+    assert not any(p.requires_grad for n, p in m.named_parameters() if n.startswith("layout_encoer."))
+    # pretrained=False and the Autoreg class (no layout encoder) leave / skip as expected
+    m0 = G.RALF(features=None, tokenizer=helpers.make_tokenizer("pku"), dataset_name="pku", max_seq_length=10, pretrained=False)
+    assert not torch.equal(m0.state_dict()["encoder.extractor.body.layer1.0.conv1.weight"], resnet["layer1.0.conv1.weight"])
+    ar = G.ConcateAuxilaryTaskAutoreg(features=None, tokenizer=helpers.make_tokenizer("pku"), dataset_name="pku")
+    assert torch.equal(ar.state_dict()["encoder.extractor.body.layer1.0.conv1.weight"], resnet["layer1.0.conv1.weight"])
