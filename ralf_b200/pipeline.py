@@ -11,12 +11,30 @@ lookup replaced by the live k-NN search the north star asks for.
 """
 from __future__ import annotations
 
+import contextlib
+import os
 from typing import Optional
 
 import torch
 
 from .generator import ConditionalInputs
 from .retrieval import GpuRetriever
+
+_NVTX = os.environ.get("RALF_NVTX", "0") != "0"
+
+
+@contextlib.contextmanager
+def _stage(name: str):
+    """NVTX range around a pipeline stage (RALF_NVTX=1; shows up as search / fetch / encode[i] / decode in a timeline of
+    the eager path or of the capture -- host-side markers, nothing is added to the graphs)."""
+    if not _NVTX:
+        yield
+        return
+    torch.cuda.nvtx.range_push("ralf." + name)
+    try:
+        yield
+    finally:
+        torch.cuda.nvtx.range_pop()
 
 
 class LayoutPipeline:
@@ -66,26 +84,33 @@ class LayoutPipeline:
 
     # ---- stages --------------------------------------------------------------------------------
     def _stage_search(self):
-        idx, score = self.retr.search_local(self.q_all, self.k)
+        with _stage("search"):
+            idx, score = self.retr.search_local(self.q_all, self.k)
         return idx, score
 
     def _stage_fetch(self, idx: torch.Tensor):
         """idx: global top-k of this rank's canvases [B, k] -> packed exemplar layouts [B, k, 6, E]."""
-        self.idx_out.copy_(idx)
-        return self.retr.fetch(idx)["packed"]
+        with _stage("fetch"):
+            self.idx_out.copy_(idx)
+            return self.retr.fetch(idx)["packed"]
 
     def _stage_encode(self, packed: torch.Tensor, b0: int) -> None:
         """One encoder micro-batch (canvases b0 .. b0+mb): memory -> rows of the batch-wide cross-attention K/V cache."""
         b1 = min(self.B, b0 + self.mb)
-        mem, mem_s = self.eng.encode(self.img[b0:b1], packed[b0:b1], self.const_seq[b0:b1], self.const_pad[b0:b1])
-        self.Mlen = mem.shape[1]
-        if self.kv is None:
-            from .engine import KV24
+        with _stage(f"encode[{b0 // self.mb}]"):
+            mem, mem_s = self.eng.encode(self.img[b0:b1], packed[b0:b1], self.const_seq[b0:b1], self.const_pad[b0:b1])
+            self.Mlen = mem.shape[1]
+            if self.kv is None:
+                from .engine import KV24
 
-            self.kv = self.eng.alloc_cross_kv(self.B * self.Mlen, kv24=KV24 and self.eng.npass == 3)
-        self.eng.cross_kv(mem_s, out=self.kv, row0=b0 * self.Mlen)
+                self.kv = self.eng.alloc_cross_kv(self.B * self.Mlen, kv24=KV24 and self.eng.npass == 3)
+            self.eng.cross_kv(mem_s, out=self.kv, row0=b0 * self.Mlen)
 
     def _stage_decode(self) -> None:
+        with _stage("decode"):
+            self._decode()
+
+    def _decode(self) -> None:
         if self.decode_ways == 1:
             seq = self.eng.generate(None, self.B, self.Mlen, self.token_mask, self.ids["bos"], self.ids["pad"], self.S,
                                     kv=self.kv)
@@ -93,18 +118,20 @@ class LayoutPipeline:
             return
         cur = torch.cuda.current_stream()
         per = (self.B + self.decode_ways - 1) // self.decode_ways
+        forked = []
         for w, side in enumerate(self._dec_streams):
             b0, b1 = w * per, min(self.B, (w + 1) * per)
             if b0 >= b1:
                 break
             side.wait_stream(cur)  # fork (inside a capture this makes `side` a branch of the same graph)
+            forked.append(side)
             with torch.cuda.stream(side):
                 kv = [k[b0 * self.Mlen:b1 * self.Mlen] for k in self.kv]
                 seq = self.eng.generate(None, b1 - b0, self.Mlen, self.token_mask, self.ids["bos"], self.ids["pad"],
                                         self.S, kv=kv)
                 self.seq_out[b0:b1].copy_(seq)
-        for side in self._dec_streams:
-            cur.wait_stream(side)  # join
+        for side in forked:  # join -- only the branches that exist (a capture must not wait on a stream outside it)
+            cur.wait_stream(side)
 
     def _stage_main(self, idx: torch.Tensor):
         packed = self._stage_fetch(idx)
