@@ -204,6 +204,21 @@ class _B200LayoutModel(nn.Module):
         super().__init__()
         if d_model != 256:
             raise NotImplementedError("the B200 kernels are specialised for d_model = 256 (reference default)")
+        # Constructor options of the reference (retrieval_augmented_autoreg.py:61-80,636-650) that change the architecture:
+        # only their shipped values are built; anything else fails here instead of being silently ignored.
+        shipped = {"use_reference_image": False, "layout_backbone": "feature_extractor", "freeze_layout_encoder": True,
+                   "decoder_d_model": 256, "encoder_pos_emb": "sine", "decoder_pos_emb": "layout",
+                   "global_task_embedding": False, "shared_embedding": False, "decoder_num_layers": 6, "RELATION_SIZE": 10}
+        if not use_flag_embedding:
+            raise NotImplementedError("use_flag_embedding=False: only the shipped configuration (True) is built")
+        for key, value in shipped.items():
+            if key in kwargs and kwargs[key] != value:
+                raise NotImplementedError(f"{key}={kwargs[key]!r}: only the shipped configuration ({value!r}) is built")
+        if saliency_k == "dynamic":
+            raise NotImplementedError('saliency_k="dynamic" (hybrid retrieval embedding) is not built')
+        unknown = set(kwargs) - set(shipped) - {"weight_init"}
+        if unknown:
+            raise TypeError(f"unexpected constructor arguments: {sorted(unknown)}")
         assert auxilary_task in T.COND_TYPES, f"{auxilary_task=} must be one of {T.COND_TYPES}"
         self.features = features
         self.tokenizer = self._host_tokenizer(tokenizer)

@@ -263,3 +263,20 @@ def test_constructor_reads_the_reference_weight_files(tmp_path, monkeypatch):
     assert not torch.equal(m0.state_dict()["encoder.extractor.body.layer1.0.conv1.weight"], resnet["layer1.0.conv1.weight"])
     ar = G.ConcateAuxilaryTaskAutoreg(features=None, tokenizer=helpers.make_tokenizer("pku"), dataset_name="pku")
     assert torch.equal(ar.state_dict()["encoder.extractor.body.layer1.0.conv1.weight"], resnet["layer1.0.conv1.weight"])
+
+
+def test_constructor_rejects_configurations_that_are_not_built():
+    """Reference constructor options that change the architecture are refused, never silently ignored."""
+    from ralf_b200 import generator as G
+
+    tok = helpers.make_tokenizer()
+    ok = dict(features=None, tokenizer=tok, dataset_name="cgl", max_seq_length=10, db_dataset=None, weight_init=True,
+              use_reference_image=False, layout_backbone="feature_extractor", freeze_layout_encoder=True, decoder_d_model=256,
+              shared_embedding=False, global_task_embedding=False)
+    G.RALF(**ok)
+    for bad in [{"use_reference_image": True}, {"saliency_k": "dynamic"}, {"decoder_d_model": 512}, {"d_model": 128},
+                {"global_task_embedding": True}, {"shared_embedding": True}, {"use_flag_embedding": False}]:
+        with pytest.raises(NotImplementedError):
+            G.RALF(**{**ok, **bad})
+    with pytest.raises(TypeError):
+        G.RALF(**ok, no_such_option=1)
