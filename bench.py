@@ -393,9 +393,39 @@ def cpu_baseline(args, budget_canvases: int = CPU_SAMPLE_CANVASES):
         O.greedy_sample(sd, mem, tok.token_mask, 517, 516, tok.max_token_length)
     t_model = time.time() - t0
     total = t_knn + t_model
-    return {"value": round(budget_canvases / total, 3), "unit": "layouts/s", "cores": cores, "kind": "port",
-            "sample": f"{budget_canvases} canvases {args.hw}x{args.hw}: k-NN over {rows} rows scaled to {args.gallery} "
-                      f"({t_knn:.2f}s) + oracle encode + no-KV-cache greedy decode of {tok.max_token_length} tokens ({t_model:.2f}s)"}
+    out = {"value": round(budget_canvases / total, 3), "unit": "layouts/s", "cores": cores, "kind": "port",
+           "sample": f"{budget_canvases} canvases {args.hw}x{args.hw}: k-NN over {rows} rows scaled to {args.gallery} "
+                     f"({t_knn:.2f}s) + oracle encode + no-KV-cache greedy decode of {tok.max_token_length} tokens ({t_model:.2f}s)"}
+    try:  # BASELINE configs[0], the reference's own CPU case: Autoreg baseline, unconstrained, batch 1, 350 x 240 canvas
+        out["config0_autoreg_b1_350x240"] = _cpu_autoreg_b1()
+    except Exception as e:  # a reported extra, never a reason to lose the bench line
+        out["config0_autoreg_b1_350x240"] = {"error": repr(e)[:200]}
+    return out
+
+
+def _cpu_autoreg_b1(repeats: int = 3):
+    from oracle import ralf_oracle as O
+    from oracle import synth
+    from ralf_b200 import generator as G
+    from tests import helpers
+
+    tok = helpers.make_tokenizer()
+    model = G.ConcateAuxilaryTaskAutoreg(features=None, tokenizer=tok, auxilary_task="uncond", pretrained=False)
+    sd = synth_weights_for(model)
+    const = model.preprocessor(G.ConditionalInputs(image=torch.zeros(1, 4, 8, 8)))
+    b = synth.synth_batch(1, 350, 240, 10, 1, 4, seed=2)
+    img = torch.cat([b["image"], b["saliency"]], 1)
+    ids = model.special_token_ids
+    times = []
+    with torch.no_grad():
+        for _ in range(repeats + 1):
+            t0 = time.time()
+            mem = O.encode_autoreg_memory(sd, img, const["seq"], const["pad_mask"])
+            O.greedy_sample(sd, mem, tok.token_mask, ids["bos"], ids["pad"], tok.max_token_length)
+            times.append(time.time() - t0)
+    t = sorted(times[1:])[len(times[1:]) // 2]  # median after one warm-up
+    return {"value": round(1.0 / t, 3), "unit": "layouts/s", "s_per_layout": round(t, 3),
+            "sample": f"median of {repeats} runs after 1 warm-up, {tok.max_token_length} greedy tokens without KV cache"}
 
 
 def run_reference(args):
