@@ -728,6 +728,7 @@ def run_max_length():
                         meta=np.array(json.dumps({"B": B, "H": H, "W": W, "seed": 14, "weights_seed": 8, "E": E, "K": 16,
                                                   "dataset": "cgl", "special": {k: int(v) for k, v in ids.items()}})))
     print("ralf_cgl_e11_128", mem.shape, inp.shape)
+    rb.bootstrap("/tmp/ralf_ref_work")  # back to the scratch dir whose FIDNet checkpoint has max_bbox = 10
 
 
 def run_init_stats():
