@@ -180,12 +180,6 @@ print("ok")
 '''
 
 
-# New tcgen05 kernels behind opt-in switches: a first run belongs in a bounded, deliberate GPU call (profiles/
-# run_r2_first_call.sh sets RALF_TEST_OPTIN=1), not in the unattended suite -- a wrong barrier there is a hang, not a failure.
-_optin = pytest.mark.skipif(not __import__("os").environ.get("RALF_TEST_OPTIN"),
-                            reason="opt-in kernels: set RALF_TEST_OPTIN=1 (see profiles/run_r2_first_call.sh)")
-
-
 def _attention_in_child(env: dict, shapes: list) -> dict:
     """The kernel selectors (RALF_ATTN_TC, RALF_ATTN_TC_BIG) are read once per process: run the fp64 check of
     test_encoder_attention_tcgen05_matches_fp64 in a child with `env` and hand back its outputs per shape."""
@@ -204,8 +198,7 @@ def _attention_in_child(env: dict, shapes: list) -> dict:
         return {tuple(sh): torch.load(os.path.join(tmp, "o_%d_%d_%d.pt" % tuple(sh))) for sh in shapes}
 
 
-@_optin
-@pytest.mark.hw_pending(order=40)
+@pytest.mark.hw_pending(order=40, optin=True)
 def test_encoder_attention_tcgen05_two_threads_per_row_variant(cuda_device):
     """RALF_ATTN_TC=2 selects attention_tc2_kernel (256 threads: two threads per query row, key columns split in halves):
     same fp64 bar as the default kernel, and bit-identical to it wherever one half holds all the keys (Tk <= 128: the
@@ -217,8 +210,7 @@ def test_encoder_attention_tcgen05_two_threads_per_row_variant(cuda_device):
     assert not torch.equal(one[(130, 256, 256)], two[(130, 256, 256)])  # (left) + (right) row sums: the other kernel ran
 
 
-@_optin
-@pytest.mark.hw_pending(order=41)
+@pytest.mark.hw_pending(order=41, optin=True)
 def test_encoder_attention_tcgen05_more_than_256_keys(cuda_device):
     """RALF_ATTN_TC_BIG=1: 256 < Tk <= 480 (the reference's real 350 x 240 canvases give 330 image tokens) on the tensor
     cores with P written in place over S in TMEM; without the switch these shapes take the CUDA-core kernel."""

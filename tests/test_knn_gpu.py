@@ -144,7 +144,7 @@ def test_flat_ip_index_as_hf_custom_index(cuda_device, monkeypatch):
     np.testing.assert_array_equal(index.reconstruct(123), G[123])
 
 
-@pytest.mark.hw_pending(order=30)
+@pytest.mark.hw_pending(order=30, optin=True)
 def test_knn_passes_on_parallel_streams_equal_single_stream(cuda_device):
     """GpuRetriever.knn_ways > 1 (passes of 128 queries round-robin on parallel streams) returns what the single-stream
     call returns, eagerly and as parallel branches of a captured graph."""

@@ -81,7 +81,7 @@ def test_graph_pipeline_equals_eager_and_oracle(cuda_device):
     np.testing.assert_array_equal(out["seq"].numpy(), out2["seq"].numpy())
 
 
-@pytest.mark.hw_pending(order=32)
+@pytest.mark.hw_pending(order=32, optin=True)
 def test_overlapped_pipeline_equals_sequential(cuda_device):
     """Two batches in flight (decode of batch i under search + encode of batch i+1, separate graph pools, two K/V
     slots) give, batch for batch, the tokens and retrieved indices of the one-batch-at-a-time pipeline."""
@@ -125,7 +125,7 @@ def test_overlapped_pipeline_equals_sequential(cuda_device):
     np.testing.assert_array_equal(again["retrieved_idx"].numpy(), want[0]["retrieved_idx"].numpy())
 
 
-@pytest.mark.hw_pending(order=31)
+@pytest.mark.hw_pending(order=31, optin=True)
 def test_parallel_decode_chains_equal_single_chain(cuda_device):
     """decode_ways > 1 (groups of canvases decoded on parallel branches of the captured graph) changes no token."""
     from ralf_b200.pipeline import LayoutPipeline
@@ -153,7 +153,7 @@ def test_parallel_decode_chains_equal_single_chain(cuda_device):
             np.testing.assert_array_equal(got["retrieved_idx"].numpy(), want["retrieved_idx"].numpy())
 
 
-@pytest.mark.hw_pending(order=15)
+@pytest.mark.hw_pending(order=15, optin=True)
 def test_bench_shape_batch_invariance_and_token_validity(cuda_device):
     """Size-independent properties at the bench's shape (256 x 256 canvases, E = 12 -> 60 tokens, micro-batches of 128):
     (1) a canvas's tokens do not depend on what else is in the batch -- the 512-canvas graph pipeline equals the eager
