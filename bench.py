@@ -274,6 +274,7 @@ def run_ours(args):
                        "memory_len": M, "weights": "random-init reference architecture (seeded)",
                        "l2": "flushed between iterations (256 MiB write); gallery shard >> L2",
                        "batches_in_flight": 2 if args.overlap else 1, "decode_ways": args.decode_ways,
+                       "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("RALF_")},  # A/B knobs set
                        "parallelism": f"dp{world} canvases, gallery row-sharded, all-gather merge" if world > 1 else "single GPU"},
             "e2e": {"value": round(world * B / (ms_e2e / args.steps / 1e3), 2), "unit": "layouts/s",
                     "h2d_bytes_per_step": int(img_h.numel() * 4 + qry_h.numel() * 4), "d2h_bytes_per_step": int(B * S * 8),
