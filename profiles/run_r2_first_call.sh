@@ -12,6 +12,7 @@ timeout 1500 python -m pytest tests -x -q -m gpu -p no:cacheprovider > gpurun_ou
 B="--steps 5 --warmup 3 --no-cpu-baseline"
 timeout 600 python bench.py $B > gpurun_out/r2_bench_base.json 2> gpurun_out/r2_bench_base.err
 RALF_GEMM_MINB=2 timeout 600 python bench.py $B > gpurun_out/r2_bench_minb2.json 2> gpurun_out/r2_bench_minb2.err
+RALF_SAMPLE_GRAPH=1 timeout 600 python bench.py $B > gpurun_out/r2_bench_samplegraph.json 2> gpurun_out/r2_bench_samplegraph.err  # moves e2e_model_api only
 RALF_KNN_WAYS=2 timeout 600 python bench.py $B > gpurun_out/r2_bench_knnways2.json 2> gpurun_out/r2_bench_knnways2.err
 RALF_ATTN_TC=2 timeout 600 python bench.py $B > gpurun_out/r2_bench_attn2.json 2> gpurun_out/r2_bench_attn2.err
 timeout 600 python bench.py $B --decode-ways 2 > gpurun_out/r2_bench_ways2.json 2> gpurun_out/r2_bench_ways2.err
@@ -24,7 +25,8 @@ for f in gpurun_out/r2_bench_*.json; do python - "$f" <<'PY'
 import json, sys
 try:
     d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-    print(sys.argv[1], d["value"], d["unit"], "ms/step", d["ms_per_step"], "e2e", d["e2e"]["value"], "knn frac", d["roofline"]["frac"])
+    print(sys.argv[1], d["value"], d["unit"], "ms/step", d["ms_per_step"], "e2e", d["e2e"]["value"], "knn frac", d["roofline"]["frac"],
+          "model api", d.get("e2e_model_api", {}).get("value"))
 except Exception as e:
     print(sys.argv[1], "no line:", e)
 PY

@@ -528,6 +528,38 @@ class Engine:
         out = seq[:, 1:]
         return (out, torch.stack(all_logits, 1)) if return_logits else out
 
+    def generate_graphed(self, mem_s: torch.Tensor, B: int, Mlen: int, token_mask: torch.Tensor, bos_id: int, pad_id: int,
+                         steps: int) -> torch.Tensor:
+        """Plain greedy ``generate`` replayed from a CUDA graph cached per (B, Mlen, steps).
+
+        Through the model-class API (``model.sample`` called batch after batch by inference.py) the decode loop is ~4 k
+        launches issued from Python, i.e. host-bound for the batch sizes the reference's loaders use; the loop only
+        depends on the memory K/V cache, so it is captured once per shape over a static cache that ``cross_kv`` then fills
+        in place.  Opt-in (``RALF_SAMPLE_GRAPH=1``) until it has run on hardware; at most 4 shapes are kept."""
+        cache = self.__dict__.setdefault("_gen_graphs", {})
+        key = (B, Mlen, steps, bos_id, pad_id)
+        entry = cache.get(key)
+        if entry is None:
+            if len(cache) >= 4:
+                cache.pop(next(iter(cache)))
+            kv = self.alloc_cross_kv(B * Mlen, kv24=KV24 and self.npass == 3)
+            self.cross_kv(mem_s, out=kv)
+            tm = token_mask.to(self.dev).to(torch.uint8).contiguous()
+            side = torch.cuda.Stream(device=self.dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):  # warm-up outside the capture (allocator, kernel attributes)
+                self.generate(None, B, Mlen, tm, bos_id, pad_id, steps, kv=kv)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.generate(None, B, Mlen, tm, bos_id, pad_id, steps, kv=kv)
+            entry = cache[key] = (kv, graph, out, tm)
+        else:
+            self.cross_kv(mem_s, out=entry[0])
+        entry[1].replay()
+        return entry[2].clone()
+
 
 class DecodeSession:
     """KV-cached next-token logits for ONE canvas with rewind, for samplers that backtrack on the host

@@ -25,6 +25,9 @@ from .engine import Engine
 from .task import ConditionalInputs, TaskPreprocessor, get_condition  # noqa: F401  (re-exported: reference import sites)
 from .tokenizer import LayoutSequenceTokenizer
 
+# RALF_SAMPLE_GRAPH=1: model.sample()'s plain greedy decode loop is replayed from a per-shape CUDA graph (opt-in, unmeasured)
+_SAMPLE_GRAPH = __import__("os").environ.get("RALF_SAMPLE_GRAPH", "0") != "0"
+
 UnconditionalPreprocessor = TaskPreprocessor  # task=None/"uncond" (task_preprocessor.py:354-384)
 
 
@@ -552,8 +555,11 @@ class _B200LayoutModel(nn.Module):
         eng = self.engine()
         mem, mem_s = eng.encode(image, getattr(cond, "retrieved", None) if self.IS_RALF else None, const["seq"],
                                 const["pad_mask"])
-        seq = eng.generate(mem_s, B, mem.shape[1], self.tokenizer.token_mask, ids["bos"], ids["pad"], steps,
-                           forced=forced, sampling=sampling, rng=generator)
+        if _SAMPLE_GRAPH and forced is None and name == "deterministic":
+            seq = eng.generate_graphed(mem_s, B, mem.shape[1], self.tokenizer.token_mask, ids["bos"], ids["pad"], steps)
+        else:
+            seq = eng.generate(mem_s, B, mem.shape[1], self.tokenizer.token_mask, ids["bos"], ids["pad"], steps,
+                               forced=forced, sampling=sampling, rng=generator)
         seq = seq.cpu()
         out = self.tokenizer.decode(seq)  # BaseModel.postprocess (base_model.py:367-389)
         if return_seq:

@@ -199,3 +199,24 @@ def test_bench_shape_batch_invariance_and_token_validity(cuda_device):
         cond = ConditionalInputs(image=img[b0:b0 + 64].to(cuda_device), retrieved=retr.fetch(i2[b0:b0 + 64]))
         ref = model.sample(cond=cond, cond_type="uncond", return_seq=True)
         np.testing.assert_array_equal(seq[b0:b0 + 64].numpy(), ref["seq"].numpy(), err_msg=f"chunk at {b0}")
+
+
+@pytest.mark.hw_pending(order=33, optin=True)
+def test_model_sample_with_cached_decode_graph_equals_eager(cuda_device, monkeypatch):
+    """RALF_SAMPLE_GRAPH=1: model.sample()'s greedy decode loop replayed from a per-shape CUDA graph gives the eager loop's
+    tokens, call after call (fresh inputs into the static K/V cache) and across shapes (one graph per shape)."""
+    from oracle import synth
+    from ralf_b200 import generator as G
+
+    model = _model(cuda_device, seed=2)
+    conds = []
+    for seed, B, hw in [(41, 3, 128), (42, 3, 128), (43, 2, 128), (44, 3, 96), (45, 3, 128)]:
+        batch = synth.synth_batch(B, hw, hw, 10, 16, 4, seed=seed)
+        conds.append(G.get_condition(batch, "uncond", model.tokenizer)[0].to(cuda_device))
+    want = [model.sample(cond=c, cond_type="uncond", return_seq=True)["seq"] for c in conds]
+    monkeypatch.setattr(G, "_SAMPLE_GRAPH", True)
+    for _ in range(2):
+        got = [model.sample(cond=c, cond_type="uncond", return_seq=True)["seq"] for c in conds]
+        for w, g in zip(want, got):
+            np.testing.assert_array_equal(g.numpy(), w.numpy())
+    assert len(model.engine()._gen_graphs) == 3  # (3, 128), (2, 128), (3, 96): one graph per shape
