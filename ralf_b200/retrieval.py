@@ -233,3 +233,114 @@ def coarse_saliency(saliency: torch.Tensor, size: tuple = (16, 16)) -> torch.Ten
     cols = torch.div(torch.arange(size[1], device=saliency.device) * W, size[1], rounding_mode="floor")
     thumb = saliency[:, rows][:, :, cols].to(torch.float32)
     return (2.0 * thumb.clamp(0.0, 1.0) - 1.0).reshape(B, -1)
+
+
+class Retriever:
+    """``image2layout.train.models.retrieval.retriever.Retriever`` (retriever.py:24-229): the reference's non-learnable
+    generator ("copy the layout of the nearest database canvas") and the builder of its retrieval cache tables -- the class
+    SURVEY.md 8 row a1 names.  Same constructor / ``sample`` / ``preprocess_retrieval_cache`` surface, with the FAISS index
+    replaced by a device-resident gallery + ``ralf_knn_topk`` and the per-sample python loops by batched calls.
+
+    Features: ``retrieval_backbone="saliency"`` (and ``"random"``, which the reference maps onto it) computes the weight-free
+    ``coarse_saliency`` features here.  The deep backbones (dreamsim / clip / vgg) are third-party pretrained embedders that
+    are out of scope: pass their outputs as ``embeddings`` [N, d] (database order) and an ``embed_fn`` that
+    maps a batch of images [B, 3, H, W] to [B, d]."""
+
+    output_keys = ["label", "mask", "center_x", "center_y", "width", "height"]
+
+    def __init__(self, features, db_dataset, max_seq_length: int, top_k: int = 1, dataset_name: str = "pku",
+                 retrieval_backbone: str = "saliency", saliency_k=None, embeddings=None, embed_fn=None, device=None,
+                 **kwargs) -> None:
+        from .data import LayoutTable
+
+        self.features, self.db_dataset, self.max_seq_length = features, db_dataset, max_seq_length
+        self.top_k, self.dataset_name, self.retrieval_backbone = top_k, dataset_name, retrieval_backbone
+        self.index_name = "search_feat"
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else "cuda"
+        self.device = torch.device(device)
+        self.embed_fn = embed_fn
+        backbone = "saliency" if retrieval_backbone == "random" else retrieval_backbone
+        if "merge" in backbone or "concat" in backbone:
+            raise NotImplementedError(f"{retrieval_backbone=}: merged retrieval tables are built offline in the reference")
+        rows = [db_dataset[i] for i in range(len(db_dataset))]
+        if embeddings is not None:
+            vectors = torch.as_tensor(embeddings, dtype=torch.float32)
+        elif backbone == "saliency":
+            vectors = torch.cat([coarse_saliency(torch.as_tensor(r["saliency"])[None]) for r in rows])
+        else:
+            raise NotImplementedError(f"{retrieval_backbone=}: pass embeddings= and embed_fn= (pretrained embedders are out of scope)")
+        assert vectors.shape[0] == len(rows), f"{vectors.shape[0]} feature rows for {len(rows)} database rows"
+        self.layouts = LayoutTable.from_rows(rows, max_seq_length, device=self.device)
+        self.retr = GpuRetriever(vectors.to(self.device), device=self.device)
+        self.db_ids = [r.get("id", i) for i, r in enumerate(rows)]
+        self.table_paired_id_idx = {self._id(i): n for n, i in enumerate(self.db_ids)}
+
+    def _id(self, data_id):
+        return int(data_id) if "pku" in self.dataset_name else data_id  # retriever.py:176-178
+
+    def eval(self):
+        return self
+
+    def to(self, device):
+        return self
+
+    def parameters(self):
+        return iter(())
+
+    def get_query(self, image=None, saliency=None) -> torch.Tensor:
+        """FeatureExtracterBackbone.get_query (retrieval/image.py:132-139), batched: [B, d] on the device."""
+        if self.retrieval_backbone in ("saliency", "random"):
+            return coarse_saliency(saliency.to(self.device))
+        assert self.embed_fn is not None, "deep retrieval backbones need embed_fn="
+        return torch.as_tensor(self.embed_fn(image), dtype=torch.float32).to(self.device)
+
+    @torch.no_grad()
+    def sample(self, cond, batch_size=1, sampling_cfg=None, **kwargs):
+        """retriever.py:91-132: the layout of the nearest database canvas for every canvas of ``cond``; ``random`` queries
+        with the saliency map of a random database row instead (one ``np.random.randint`` per canvas, as there)."""
+        import numpy as np
+
+        image = cond.image
+        B = image.size(0)
+        if self.retrieval_backbone == "random":
+            picks = [int(np.random.randint(0, len(self.db_dataset))) for _ in range(B)]
+            sal = torch.stack([torch.as_tensor(self.db_dataset[i]["saliency"]) for i in picks])
+            query = self.get_query(saliency=sal)
+        else:
+            query = self.get_query(image=image[:, :-1], saliency=image[:, -1:])
+        idx, _ = self.retr.search(query, 1, certify=True)
+        got = self.layouts.gather(idx)
+        out = {k: got[k][:, 0].cpu() for k in self.output_keys}
+        return out, {"total": 1, "viorated": 0}
+
+    def preprocess_retrieval_cache(self, split: str, dataset, top_k: int, run_on_local: bool = True,
+                                   save_scores: bool = False, root: str = "cache", queries=None, batch: int = 1024):
+        """retriever.py:134-229: ``dict[data_id -> list[database index]]`` of the ``top_k`` (+1, minus the query itself on the
+        train split) nearest database rows of every row of ``dataset``, saved under the reference's file names.
+        ``queries`` [len(dataset), d] skips the feature extraction (deep backbones)."""
+        from .data import cache_table_path, paired_table_path, save_cache_table
+
+        os.makedirs(root, exist_ok=True)
+        torch.save(dict(self.table_paired_id_idx), paired_table_path(self.dataset_name, self.retrieval_backbone, root))
+        table, scores = {}, {}
+        for s in range(0, len(dataset), batch):
+            rows = [dataset[i] for i in range(s, min(len(dataset), s + batch))]
+            if queries is not None:
+                q = torch.as_tensor(queries[s:s + len(rows)], dtype=torch.float32).to(self.device)
+            elif self.retrieval_backbone in ("saliency", "random"):
+                q = self.get_query(saliency=torch.stack([torch.as_tensor(r["saliency"]) for r in rows]))
+            else:
+                q = self.get_query(image=torch.stack([torch.as_tensor(r["image"]) for r in rows]))
+            idx, score = self.retr.search(q, top_k + 1, certify=True)
+            idx, score = idx.cpu().tolist(), score.cpu().tolist()
+            for r, i_row, s_row in zip(rows, idx, score):
+                if split == "train":  # the first hit is the query itself
+                    i_row, s_row = i_row[1:], s_row[1:]
+                table[self._id(r["id"])] = i_row
+                scores[self._id(r["id"])] = s_row
+        path = cache_table_path(self.dataset_name, split, self.retrieval_backbone, top_k, root)
+        save_cache_table(table, path)
+        if save_scores:
+            torch.save(scores, path.replace("indexes", "scores"))
+        return table

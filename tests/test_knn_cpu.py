@@ -1,4 +1,6 @@
 """CPU: the C k-NN oracle (canonical fp32 dot, (score desc, idx asc)) against a float64 ranking."""
+import os
+
 import numpy as np
 import pytest
 
@@ -109,3 +111,57 @@ def test_coarse_saliency_matches_reference():
     x = torch.rand(3, 1, 256, 256)
     want = 2 * torch.nn.functional.interpolate(x, size=(16, 16)).clamp(0, 1).flatten(1) - 1
     assert torch.equal(coarse_saliency(x), want)
+
+
+def test_retriever_class_sample_and_cache_tables(monkeypatch, tmp_path):
+    """Drop-in for the reference's Retriever (retrieval/retriever.py:24-229), host logic with the kernels replaced by the
+    oracle: saliency features of the database, sample() = the nearest canvas's layout, preprocess_retrieval_cache() = the
+    reference's table format and file names (self dropped on the train split)."""
+    import torch
+
+    from ralf_b200 import data as D
+    from ralf_b200 import ops
+    from ralf_b200.generator import ConditionalInputs
+    from ralf_b200.retrieval import Retriever, coarse_saliency
+
+    def oracle_knn_topk(gallery, queries, k, *, index_base=0, gallery_max_norm=0.0, exact=False, workspace=None):
+        i, s = oracle_knn.topk(gallery.numpy(), queries.numpy(), k)
+        return torch.from_numpy(i) + index_base, torch.from_numpy(s), torch.ones(queries.shape[0], dtype=torch.int32)
+
+    monkeypatch.setattr(ops, "knn_topk", oracle_knn_topk)
+    monkeypatch.setattr(ops, "gather_layouts", lambda packed, idx: packed[idx])
+    g = torch.Generator().manual_seed(4)
+    n, E = 40, 10
+    db = []
+    for i in range(n):
+        m = int(torch.randint(1, 8, (1,), generator=g))
+        db.append({"id": str(1000 + i), "saliency": torch.rand(1, 64, 48, generator=g), "image": torch.rand(3, 64, 48, generator=g),
+                   "label": torch.randint(0, 3, (m,), generator=g).tolist(),
+                   **{k: torch.rand(m, generator=g).tolist() for k in ["center_x", "center_y", "width", "height"]}})
+    r = Retriever(features=None, db_dataset=db, max_seq_length=E, top_k=1, dataset_name="pku", retrieval_backbone="saliency",
+                  device="cpu")
+    feats = coarse_saliency(torch.stack([x["saliency"] for x in db]))
+    assert torch.equal(r.retr.emb, feats) and r.table_paired_id_idx[1003] == 3  # "pku" ids are ints in the tables
+    # sample(): every database canvas retrieves itself
+    rows = [5, 17, 33]
+    image = torch.stack([torch.cat([db[i]["image"], db[i]["saliency"]]) for i in rows])
+    out, vio = r.sample(ConditionalInputs(image=image))
+    assert vio == {"total": 1, "viorated": 0} and set(out) == set(Retriever.output_keys)
+    for b, i in enumerate(rows):
+        m = len(db[i]["label"])
+        assert out["mask"][b].tolist() == [True] * m + [False] * (E - m)
+        assert out["label"][b][:m].tolist() == db[i]["label"]
+        np.testing.assert_allclose(out["width"][b][:m].numpy(), np.array(db[i]["width"], dtype=np.float32))
+    # cache tables: reference file names, self dropped on train, kept (top_k + 1 entries) elsewhere
+    table = r.preprocess_retrieval_cache("train", db, top_k=8, root=str(tmp_path), save_scores=True)
+    sims = feats.numpy() @ feats.numpy().T
+    for i in (0, 9, 39):
+        order = np.argsort(-sims[i], kind="stable")
+        assert order[0] == i and table[1000 + i] == order[1:9].tolist()
+    path = D.cache_table_path("pku", "train", "saliency", 8, root=str(tmp_path))
+    assert D.load_cache_table(path, top_k=4)[1005] == table[1005][:4]
+    assert os.path.exists(path.replace("indexes", "scores")) and os.path.exists(D.paired_table_path("pku", "saliency", str(tmp_path)))
+    val = r.preprocess_retrieval_cache("val", db[:5], top_k=8, root=str(tmp_path))
+    assert len(val[1002]) == 9 and val[1002][0] == 2
+    with pytest.raises(NotImplementedError):
+        Retriever(features=None, db_dataset=db, max_seq_length=E, retrieval_backbone="dreamsim", device="cpu")
