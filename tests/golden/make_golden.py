@@ -752,6 +752,35 @@ def run_init_stats():
     print("init_stats", {k: len(v) for k, v in out.items()})
 
 
+def run_reference_gradients(ralf, tok):
+    """Backward of the reference's own train_loss on the golden batch (eval mode: dropout off, BatchNorm on its running
+    statistics -- the deterministic setting): per-parameter gradient L2 norms, the small gradient tensors in full.  Pins the
+    oracle's backward (torch.autograd over oracle/ralf_oracle.py, which the GPU gradient tests compare against) to the
+    reference itself."""
+    import copy
+
+    sd = synth.synth_state_dict(schema_of(ralf), seed=1)
+    ralf.load_state_dict(sd, strict=True)
+    ralf.eval()
+    batch = synth.synth_batch(2, 256, 256, 10, 16, tok.N_label, seed=1)  # the ralf_cgl_256 golden batch
+    inputs, targets = ralf.preprocess(copy.deepcopy(batch))
+    ralf.zero_grad()
+    _, losses = ralf.train_loss(inputs, targets)
+    losses["nll_loss"].backward()
+    out = {"nll_loss": losses["nll_loss"].detach().numpy()}
+    names, norms = [], []
+    for n, p in ralf.named_parameters():
+        if p.grad is None:
+            continue
+        names.append(n)
+        norms.append(float(p.grad.double().norm()))
+        if p.numel() <= 1024:
+            out["grad__" + n] = p.grad.numpy()
+    out["names"], out["norms"] = np.array(names), np.array(norms)
+    np.savez_compressed(os.path.join(OUT, "grads_ralf_cgl_256.npz"), **out)
+    print("grads_ralf_cgl_256", len(names), "parameters with gradients, total norm", float(np.sqrt((np.array(norms) ** 2).sum())))
+
+
 def main():
     rb.bootstrap("/tmp/ralf_ref_work")
     torch.backends.mha.set_fastpath_enabled(False)
@@ -761,6 +790,9 @@ def main():
         json.dump(schema_of(ralf), f)
     if "--relation-only" in sys.argv:
         run_relation()
+        return
+    if "--grads-only" in sys.argv:
+        run_reference_gradients(ralf, tok)
         return
     if "--init-stats-only" in sys.argv:
         run_init_stats()
@@ -784,6 +816,7 @@ def main():
         run_coarse_saliency()
         run_max_length()
         run_init_stats()
+        run_reference_gradients(rb.make_ralf("cgl")[0], tok)
         return
     run(ralf, tok, "ralf_cgl_256", B=2, H=256, W=256, seed=1, is_ralf=True)
     run_tasks(tok, "tasks_cgl_256", B=2, H=256, W=256, seed=1)

@@ -46,7 +46,7 @@ def test_adamw_clip_matches_torch(cuda_device):
             assert (ps.p(n) - r.data).abs().max().item() <= 1e-6
 
 
-def _oracle_loss_and_grads(sd0, batch, inputs, targets, pad_id, train_trunk, dtype, is_ralf=True):
+def _oracle_loss_and_grads(sd0, batch, inputs, targets, pad_id, train_trunk, dtype, is_ralf=True, bn_train=None):
     """torch.autograd over the CPU oracle in `dtype` (float64 = ground truth); model.train() semantics for BatchNorm
     when the trunk trains, dropout off, FIDNet frozen (evaluated in fp32 like the product does)."""
     from oracle import ralf_oracle as O
@@ -60,7 +60,7 @@ def _oracle_loss_and_grads(sd0, batch, inputs, targets, pad_id, train_trunk, dty
             leaves[k] = v
     orig_pos = O.pos_emb_2d
     O.pos_emb_2d = lambda h, w, d=256: orig_pos(h, w, d).to(dtype)
-    O.BN_TRAIN = train_trunk
+    O.BN_TRAIN = train_trunk if bn_train is None else bn_train  # reference fixture: trunk trainable, BatchNorm in eval mode
     try:
         if is_ralf:
             with torch.no_grad():
