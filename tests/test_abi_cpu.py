@@ -280,3 +280,41 @@ def test_constructor_rejects_configurations_that_are_not_built():
             G.RALF(**{**ok, **bad})
     with pytest.raises(TypeError):
         G.RALF(**ok, no_such_option=1)
+
+
+def test_knn_entry_points_validate_before_touching_the_device():
+    """Error behaviour of the C ABI (include/ralf_b200.h: RalfStatus): bad arguments come back as negative status codes
+    from the argument checks, before any CUDA call -- so this runs without a GPU.  NULL -> RALF_ERR_NULL (-3), shapes ->
+    RALF_ERR_SHAPE (-1), row pitch -> RALF_ERR_ALIGN (-2), small workspace -> RALF_ERR_WORKSPACE (-7)."""
+    import ctypes as C
+
+    from ralf_b200 import _lib
+
+    L = _lib.lib()
+    assert L.ralf_version() >= 100
+    L.ralf_knn_workspace_bytes.restype = C.c_size_t
+    ws = L.ralf_knn_workspace_bytes(1_000_000, 512, 128, 16)
+    assert 0 < ws < (1 << 30) and L.ralf_knn_workspace_bytes(1_000_000, 512, 128, 33) >= ws
+    buf = (C.c_float * 64)()
+    p = C.cast(buf, C.c_void_p)
+    z = C.c_float(0.0)
+    for fn, extra in ((L.ralf_knn_topk, True), (L.ralf_knn_topk_exact, False)):
+        def call(g, n, d, q, nq, k, oi, os_, w, wb):
+            if extra:
+                return fn(g, n, d, q, nq, k, 0, z, oi, os_, None, w, wb, None)
+            return fn(g, n, d, q, nq, k, 0, oi, os_, w, wb, None)
+
+        assert call(None, 10, 512, p, 1, 16, p, p, p, ws) == -3
+        assert call(p, 10, 512, p, 1, 16, None, p, p, ws) == -3
+        assert call(p, 0, 512, p, 1, 16, p, p, p, ws) == -1
+        assert call(p, 10, 512, p, 0, 16, p, p, p, ws) == -1
+        assert call(p, 10, 512, p, 1, 64, p, p, p, ws) == -1        # k beyond the 48 the candidate filter keeps
+        assert call(p, 10, 512, p, 1, 16, p, p, p, 8) == -7
+        assert call(p, 10, 512, p, 1, 16, p, p, None, ws) == -7
+    assert L.ralf_knn_topk(p, 10, 510, p, 1, 16, 0, z, p, p, None, p, ws, None) == -2  # TMA needs 16-byte rows
+    assert L.ralf_knn_merge(None, p, 2, 1, 16, p, p, None) == -3
+    assert L.ralf_knn_merge(p, p, 0, 1, 16, p, p, None) == -1
+    if not torch.cuda.is_available():  # no device: a status code and a message, not a crash
+        assert L.ralf_check_device(0) < 0
+        L.ralf_last_cuda_error.restype = C.c_char_p
+        assert len(L.ralf_last_cuda_error()) > 0
