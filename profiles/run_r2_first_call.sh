@@ -12,6 +12,8 @@ timeout 1500 python -m pytest tests -x -q -m gpu -p no:cacheprovider > gpurun_ou
 B="--steps 5 --warmup 3 --no-cpu-baseline"
 timeout 600 python bench.py $B > gpurun_out/r2_bench_base.json 2> gpurun_out/r2_bench_base.err
 RALF_GEMM_MINB=2 timeout 600 python bench.py $B > gpurun_out/r2_bench_minb2.json 2> gpurun_out/r2_bench_minb2.err
+timeout 600 python bench.py $B --micro-batch 256 > gpurun_out/r2_bench_mb256.json 2> gpurun_out/r2_bench_mb256.err
+timeout 600 python bench.py $B --micro-batch 64 > gpurun_out/r2_bench_mb64.json 2> gpurun_out/r2_bench_mb64.err
 RALF_SAMPLE_GRAPH=1 timeout 600 python bench.py $B > gpurun_out/r2_bench_samplegraph.json 2> gpurun_out/r2_bench_samplegraph.err  # moves e2e_model_api only
 RALF_KNN_WAYS=2 timeout 600 python bench.py $B > gpurun_out/r2_bench_knnways2.json 2> gpurun_out/r2_bench_knnways2.err
 RALF_ATTN_TC=2 timeout 600 python bench.py $B > gpurun_out/r2_bench_attn2.json 2> gpurun_out/r2_bench_attn2.err
