@@ -1,5 +1,5 @@
 #!/bin/bash
-# First GPU call of round 2 (run under gpurun from the repo root, ~12 min of box time):
+# First GPU call of round 2 (run under gpurun from the repo root, ~25 min of box time: 12 bench lines + the tests; trim the list if the budget is tight):
 #   1. the hw_pending tests (written after round 1's GPU budget was spent), then the whole -m gpu suite;
 #   2. A/B bench lines for the opt-in variants that are built but unmeasured:
 #        baseline | RALF_GEMM_MINB=2 (two GEMM CTAs per SM for the short-K shapes) | RALF_KNN_WAYS=2 (k-NN passes on parallel streams) | RALF_ATTN_TC=2 (8-warp encoder attention) | --decode-ways 2/4 (parallel decode
