@@ -391,7 +391,7 @@ def secondary_rooflines(model, B, dev):
 CPU_SAMPLE_CANVASES = 8  # per bounded sample: large enough for the host BLAS / conv kernels to reach their batch efficiency
 
 
-def cpu_baseline(args, budget_canvases: int = CPU_SAMPLE_CANVASES):
+def cpu_baseline(args, budget_canvases: int = CPU_SAMPLE_CANVASES, extras: bool = True):
     """The reference algorithm's CPU restatement (oracle/, kind "port") on the host cores, bounded sample:
     `budget_canvases` canvases through retrieve (numpy fp32 G@q + top-k over a 100k-row slice, scaled) ->
     encode -> greedy decode WITHOUT KV cache (as the reference does)."""
@@ -432,11 +432,43 @@ def cpu_baseline(args, budget_canvases: int = CPU_SAMPLE_CANVASES):
     out = {"value": round(budget_canvases / total, 3), "unit": "layouts/s", "cores": cores, "kind": "port",
            "sample": f"{budget_canvases} canvases {args.hw}x{args.hw}: k-NN over {rows} rows scaled to {args.gallery} "
                      f"({t_knn:.2f}s) + oracle encode + no-KV-cache greedy decode of {tok.max_token_length} tokens ({t_model:.2f}s)"}
-    try:  # BASELINE configs[0], the reference's own CPU case: Autoreg baseline, unconstrained, batch 1, 350 x 240 canvas
-        out["config0_autoreg_b1_350x240"] = _cpu_autoreg_b1()
-    except Exception as e:  # a reported extra, never a reason to lose the bench line
-        out["config0_autoreg_b1_350x240"] = {"error": repr(e)[:200]}
+    if extras:
+        for key, fn in (("config0_autoreg_b1_350x240", _cpu_autoreg_b1), ("config1_train_step", _cpu_train_step)):
+            try:  # reported extras, never a reason to lose the bench line
+                out[key] = fn()
+            except Exception as e:
+                out[key] = {"error": repr(e)[:200]}
     return out
+
+
+def _cpu_train_step(batch: int = 8, hw: int = 256, repeats: int = 2):
+    """BASELINE configs[1] on the host cores: the reference training step -- teacher-forced forward,
+    label-smoothed CE, backward through every trainable parameter (BatchNorm on batch statistics), clip, AdamW -- as torch
+    autograd over the oracle in fp32, dropout off; bounded sample of `batch` canvases."""
+    from oracle import synth
+    from ralf_b200 import generator as G
+    from tests import helpers
+    from tests.test_train_gpu import _oracle_loss_and_grads
+
+    tok = helpers.make_tokenizer()
+    model = G.RALF(features=None, tokenizer=tok, dataset_name="cgl", max_seq_length=10, top_k=16, pretrained=False)
+    sd = synth_weights_for(model)
+    b = synth.synth_batch(batch, hw, hw, 10, 16, 4, seed=3)
+    inputs, targets = model.preprocess({k: (dict(v) if isinstance(v, dict) else v) for k, v in b.items()})
+    pad = tok.name_to_id("pad")
+    times = []
+    for _ in range(repeats + 1):
+        t0 = time.time()
+        _, grads = _oracle_loss_and_grads(sd, b, inputs, targets, pad, True, torch.float32)
+        params = [torch.nn.Parameter(sd[k].clone()) for k in grads]
+        for p_, k in zip(params, grads):
+            p_.grad = grads[k].to(torch.float32)
+        torch.nn.utils.clip_grad_norm_(params, 0.1)
+        torch.optim.AdamW(params, lr=1e-4, weight_decay=1e-4).step()
+        times.append(time.time() - t0)
+    t = sorted(times[1:])[len(times[1:]) // 2]
+    return {"value": round(batch / t, 3), "unit": "samples/s", "s_per_step": round(t, 3), "batch": batch,
+            "canvas": f"{hw}x{hw}x4", "sample": f"median of {repeats} steps after 1 warm-up; forward + backward + clip + AdamW, fp32"}
 
 
 def _cpu_autoreg_b1(repeats: int = 3):
@@ -469,8 +501,9 @@ def run_reference(args):
     if rank != 0:
         return
     vals = []
-    for i in range(args.warmup + args.steps):
-        cb = cpu_baseline(args, budget_canvases=CPU_SAMPLE_CANVASES)
+    n_runs = args.warmup + args.steps
+    for i in range(n_runs):
+        cb = cpu_baseline(args, budget_canvases=CPU_SAMPLE_CANVASES, extras=(i == n_runs - 1))  # extras once, on the line's sample
         if i >= args.warmup:
             vals.append(cb)
     v = sum(c["value"] for c in vals) / len(vals)
