@@ -433,11 +433,33 @@ def cpu_baseline(args, budget_canvases: int = CPU_SAMPLE_CANVASES, extras: bool 
            "sample": f"{budget_canvases} canvases {args.hw}x{args.hw}: k-NN over {rows} rows scaled to {args.gallery} "
                      f"({t_knn:.2f}s) + oracle encode + no-KV-cache greedy decode of {tok.max_token_length} tokens ({t_model:.2f}s)"}
     if extras:
-        for key, fn in (("config0_autoreg_b1_350x240", _cpu_autoreg_b1), ("config1_train_step", _cpu_train_step)):
+        for key, fn in (("config0_autoreg_b1_350x240", _cpu_autoreg_b1), ("config1_train_step", _cpu_train_step),
+                        ("config3_knn_100k", _cpu_knn)):
             try:  # reported extras, never a reason to lose the bench line
                 out[key] = fn()
             except Exception as e:
                 out[key] = {"error": repr(e)[:200]}
+    return out
+
+
+def _cpu_knn(rows: int = 100_000, d: int = 512, k: int = 16):
+    """BASELINE configs[3] on the host cores: exact inner-product top-16 as numpy fp32 ``G @ q`` +
+    partial sort over a 100 k x 512 gallery, Q = 1 / 32 / 128; effective GB/s = gallery bytes / time per pass."""
+    import numpy as np
+
+    rng = np.random.default_rng(0)
+    G = rng.standard_normal((rows, d)).astype(np.float32)
+    out = {"gallery": f"{rows}x{d} fp32", "top_k": k}
+    for q in (1, 32, 128):
+        Q = rng.standard_normal((q, d)).astype(np.float32)
+        best = float("inf")
+        for _ in range(3):
+            t0 = time.time()
+            s = G @ Q.T
+            idx = np.argpartition(-s, k, axis=0)[:k]
+            np.take_along_axis(s, idx, axis=0).argsort(axis=0)
+            best = min(best, time.time() - t0)
+        out[f"q{q}"] = {"queries_per_s": round(q / best, 1), "effective_gbs": round(rows * d * 4 / best / 1e9, 2)}
     return out
 
 
