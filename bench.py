@@ -294,6 +294,7 @@ def run_ours(args):
                          "frac": round(knn_bytes / (knn_ms / 1e3) / 1e9 / hbm_peak, 4),
                          "traffic": knn_traffic if (knn_traffic and n_local == 1_000_000) else None,
                          "algorithmic_bytes_per_launch": int(knn_bytes), "ms_per_launch": round(knn_ms, 4),
+                         "share_of_step": round(knn_passes * knn_ms / step_ms, 4),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "timed_with": "the previous batch's decode loop running on its own stream (--overlap): shared HBM"
                                        if args.overlap else "nothing else on the device"},
@@ -305,6 +306,7 @@ def run_ours(args):
         for o in other or []:  # the two kernels that dominate the step's time, timed alone right after the timed region
             pk = hbm_peak if o["bound"] == "hbm" else peaks.get("bf16_tflops", 1590.0)
             o["peak"], o["frac"] = pk, round(o["achieved"] / pk, 4)
+            o["share_of_step"] = round(o["ms_per_launch"] * o["launches_per_step"] / step_ms, 4)  # timed alone vs the step
         line["roofline_other"] = other
         if api is not None:
             line["e2e_model_api"] = api
