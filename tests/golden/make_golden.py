@@ -618,6 +618,47 @@ def run_relation(name="relation_cgl_128", B=3, H=128, W=128, seed=5):
                 sweep_sample.append(B + trial)  # B + trial: crafted constraint list `trial`
                 toks.append(t)
     out["craft_count"] = np.array(n_craft)
+    # live cross-check (build container only, nothing stored): the product's RelationConstraint.mask against the reference
+    # on many more crafted constraint lists / prefixes than the fixture carries
+    from ralf_b200 import relation as PR
+    from ralf_b200.tokenizer import LayoutSequenceTokenizer as HostTok
+
+    host_tok = HostTok(rb.LABELS["cgl"], 10)
+    random.seed(300)
+    mine_pre = PR.RelationPreprocessor(host_tok, {k: [[x if isinstance(x, str) else getattr(PR, type(x).__name__)(int(x))
+                                                         for x in r] for r in rows] for k, rows in table.items()})
+    mine = PR.RelationConstraint(mine_pre)
+    to_mine = lambda cons: [[(PR.CANVAS, PR.RelLoc(int(t))) if k == "canvas" else
+                             ((PR.RelSize if int(k) < 4 else PR.RelLoc)(int(k)), int(t)) for k, t in c] for c in cons]
+    live = 0
+    for trial in range(600):
+        b = trial % B
+        fn.prepare(const["seq"][b])
+        mine.types = fn.type_constraint_token_id.clone()
+        types = fn.type_constraint_token_id.tolist()
+        cons = [[] for _ in types]
+        for e in range(len(types)):
+            for _ in range(int(torch.randint(0, 5, (1,), generator=g))):
+                if e == 0 or int(torch.randint(0, 4, (1,), generator=g)) == 0:
+                    cons[e].append(("canvas", canvas_kinds[int(torch.randint(0, 3, (1,), generator=g))]))
+                else:
+                    cons[e].append((kinds[int(torch.randint(0, len(kinds), (1,), generator=g))],
+                                    int(torch.randint(0, e, (1,), generator=g))))
+        mc = to_mine(cons)
+        toks = [ids["bos"]]
+        scale = [128, 64, 32, 8][trial % 4]
+        for e, lab in enumerate(types):
+            w, h = torch.randint(0, scale, (2,), generator=g).tolist()
+            cx, cy = torch.randint(0, 128, (2,), generator=g).tolist()
+            for t in [lab, fn.width_start_idx + w, fn.height_start_idx + h, fn.center_x_start_idx + cx,
+                      fn.center_y_start_idx + cy]:
+                m, back = fn(torch.tensor([toks]), cons)
+                m2, back2 = mine.mask(toks, mc)
+                assert torch.equal(m, m2) and back == back2, (trial, toks, cons)
+                live += 1
+                toks.append(t)
+    out["live_checked_calls"] = np.array(live)
+    print(name, "live cross-check of RelationConstraint.mask against the reference:", live, "calls, no mismatch")
     pref = np.full((len(sweep_pref), tok.max_token_length + 2), -1, dtype=np.int64)
     for i, c in enumerate(sweep_pref):
         pref[i, :len(c)] = c
