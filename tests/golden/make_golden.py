@@ -679,6 +679,60 @@ def run_relation(name="relation_cgl_128", B=3, H=128, W=128, seed=5):
         torch.manual_seed(431)
         out[f"draw_{mode}"] = np.array([int(ref_sample(rows[i:i + 1].clone(), cfg, temperature=1.5 if i % 2 else None))
                                         for i in range(rows.size(0))], dtype=np.int64)
+    # (b-live) cross-check of the whole backtracking sampler on further seeds (nothing stored): product host code
+    # (get_condition -> RelationPreprocessor -> prepare -> sample_with_backtracking, oracle decoder on the reference's memory)
+    # against the reference's sample_relation under the same `random` / torch seeds
+    from oracle import ralf_oracle as O
+    from ralf_b200 import task as PT
+
+    sd_live = synth.synth_state_dict(schema_of(model), seed=seed)
+    pairs = 0
+    for live_seed in range(500, 504):
+        for mode in ("deterministic", "random"):
+            cfg = rb.DictConfig(name=mode, temperature=1.0, top_k=5, top_p=0.9)
+            random.seed(live_seed)
+            torch.manual_seed(live_seed)
+            cond, _ = get_condition(copy.deepcopy(batch), "relation", tok)
+            grabbed = {}
+            mem0 = model._encode_into_memory
+
+            def mem_spy2(x):
+                r = mem0(x)
+                grabbed["memory"] = r["memory"].clone()
+                return r
+
+            model._encode_into_memory = mem_spy2
+            try:
+                with torch.no_grad():
+                    res, vio = model.sample(cond=cond, sampling_cfg=cfg, cond_type="relation", return_violation=True,
+                                            use_backtrack=True)
+            finally:
+                model._encode_into_memory = mem0
+            random.seed(live_seed)
+            torch.manual_seed(live_seed)
+            cond2, _ = PT.get_condition(copy.deepcopy(batch), "relation", host_tok)
+            const2 = mine_pre(cond2)
+            forced = PT.forced_token_table("relation", cond2.seq, ids["pad"], ids["eos"], tok.max_token_length)
+            rows2, prepared2 = [], []
+            for b in range(B):
+                cons2 = mine.prepare(const2["seq"][b])
+                mem_b = grabbed["memory"][b:b + 1]
+
+                def logits_of(prefix, mem_b=mem_b):
+                    tgt = torch.tensor([prefix])
+                    with torch.no_grad():
+                        return O.decoder_logits(sd_live, tgt, mem_b, tgt == ids["pad"])[0, -1]
+
+                rows2.append(PR.sample_with_backtracking(logits_of, mine, cons2, forced[b], bos_id=ids["bos"], eos_id=ids["eos"],
+                                                         max_token_length=tok.max_token_length, sampling_cfg=dict(cfg)))
+                prepared2.append(cons2)
+            out2 = host_tok.decode(PR.pad_like_reference(rows2, tok.max_token_length))
+            for k in ["label", "mask", "center_x", "center_y", "width", "height"]:
+                assert torch.equal(out2[k], res[k]), (live_seed, mode, k)
+            assert PR.violation_count(out2, prepared2) == vio, (live_seed, mode)
+            pairs += 1
+    out["live_checked_sampler_runs"] = np.array(pairs)
+    print(name, "live cross-check of the backtracking sampler against the reference:", pairs, "seed x mode runs, no mismatch")
     # (c) without backtracking: batched decode under the label restriction only (:218-325)
     random.seed(410)
     torch.manual_seed(410)
