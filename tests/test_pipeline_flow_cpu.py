@@ -196,3 +196,55 @@ def test_overlapped_pipeline_flow(fakes):
     # the blocking interface of the parent still works (submit + wait)
     out = pipe.generate_layouts(img, q)
     assert out["seq"].shape == (B, 50)
+
+
+def test_knn_ways_flow_equals_single_stream(fakes, monkeypatch):
+    """GpuRetriever.knn_ways > 1: passes of 128 queries round-robin over the side streams, all of them forked from and
+    joined into the caller's stream, results concatenated in query order = the single-stream result (oracle as kernel)."""
+    import numpy as np
+
+    from ralf_b200 import ops
+    from ralf_b200.retrieval import GpuRetriever
+    from tests import oracle_knn
+
+    def oracle_knn_topk(gallery, queries, k, *, index_base=0, gallery_max_norm=0.0, exact=False, workspace=None):
+        LOG.append(("knn", queries.shape[0], CUR[-1].name))
+        i, s = oracle_knn.topk(gallery.numpy(), queries.numpy(), k)
+        return torch.from_numpy(i) + index_base, torch.from_numpy(s), torch.ones(queries.shape[0], dtype=torch.int32)
+
+    monkeypatch.setattr(ops, "knn_topk", oracle_knn_topk)
+    rng = np.random.default_rng(1)
+    retr = GpuRetriever(torch.from_numpy(rng.standard_normal((3000, 64)).astype(np.float32)), device="cpu", index_base=100)
+    q = torch.from_numpy(rng.standard_normal((300, 64)).astype(np.float32))
+    want_i, want_s = retr.search_local(q, 16)
+    retr.knn_ways = 2
+    LOG.clear()
+    got_i, got_s = retr.search_local(q, 16)
+    assert torch.equal(got_i, want_i) and torch.equal(got_s, want_s) and int(retr.last_certified.sum()) == 300
+    calls = [e for e in LOG if e[0] == "knn"]
+    assert [e[1] for e in calls] == [128, 128, 44] and calls[0][2] == calls[2][2] != calls[1][2] and "main" not in {e[2] for e in calls}
+    forks = {e[1] for e in LOG if e[0] == "wait_stream" and e[2] == "main"}
+    joins = {e[2] for e in LOG if e[0] == "wait_stream" and e[1] == "main"}
+    assert forks == joins == {s.name for s in retr._way_streams}
+    retr.search_local(q[:100], 16)  # a single pass stays on the caller's stream
+    assert LOG[-1] == ("knn", 100, "main")
+
+
+def test_generate_graphed_cache_flow(fakes):
+    """Engine.generate_graphed: one capture per (B, Mlen, steps) shape, later calls only refill the static K/V cache and
+    replay; at most 4 shapes are kept."""
+    from ralf_b200.engine import Engine
+
+    class Self(FakeEngine):
+        generate_graphed = Engine.generate_graphed
+
+    eng = Self()
+    tm = torch.ones(50, 519, dtype=torch.uint8)
+    for _ in range(3):
+        out = eng.generate_graphed(torch.zeros(2, 3 * 7, 256), 3, 7, tm, 517, 516, 50)
+        assert out.shape == (3, 50)
+    assert len([e for e in LOG if e[0] == "capture"]) == 1 and len([e for e in LOG if e[0] == "replay"]) == 3
+    assert len([e for e in LOG if e[0] == "cross_kv"]) == 3  # filled in place before every replay
+    for B in (1, 2, 4, 5):
+        eng.generate_graphed(torch.zeros(2, B * 7, 256), B, 7, tm, 517, 516, 50)
+    assert len(eng._gen_graphs) == 4 and (3, 7, 50, 517, 516) not in eng._gen_graphs  # the oldest shape was dropped
