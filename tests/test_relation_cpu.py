@@ -481,3 +481,40 @@ def test_model_preprocess_with_the_relation_task(fx, monkeypatch):
     enc = tok.encode({k: full[k] for k in ["label", "mask", *GEO]})
     assert torch.equal(inputs["seq"], enc["seq"][:, :-1]) and torch.equal(targets["seq"], enc["seq"][:, 1:])
     assert inputs["image"].shape[1] == 4 and set(inputs["retrieved"]) >= {"label", "mask", *GEO}
+
+
+def test_bench_model_api_leg_runs_on_the_oracle_engine(monkeypatch):
+    """bench.py's e2e_model_api leg (search -> fetch -> model.sample through the reference scripts' call sequence) end to end
+    on the CPU with the oracle standing in for the kernels: the code path itself, not a number."""
+    import bench
+    from oracle import synth
+    from ralf_b200 import engine as E
+    from ralf_b200 import generator as G
+    from ralf_b200 import ops
+    from ralf_b200.retrieval import GpuRetriever
+    from tests import oracle_knn
+
+    def oracle_knn_topk(gallery, queries, k, *, index_base=0, gallery_max_norm=0.0, exact=False, workspace=None):
+        i, s = oracle_knn.topk(gallery.numpy(), queries.numpy(), k)
+        return torch.from_numpy(i) + index_base, torch.from_numpy(s), torch.ones(queries.shape[0], dtype=torch.int32)
+
+    monkeypatch.setattr(ops, "knn_topk", oracle_knn_topk)
+    monkeypatch.setattr(ops, "gather_layouts", lambda packed, idx: packed[idx])
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    tok = helpers.make_tokenizer()
+    model = G.RALF(features=None, tokenizer=tok, dataset_name="cgl", max_seq_length=10, top_k=16, pretrained=False)
+    sd = helpers.synth_weights("ralf_cgl", 3)
+    model.load_state_dict(sd, strict=True)
+    monkeypatch.setattr(model, "engine", lambda: _OracleEngine(sd, tok.name_to_id("pad")))
+    g = torch.Generator().manual_seed(0)
+    n, E_ = 200, 10
+    cnt = torch.randint(1, E_ + 1, (n,), generator=g)
+    mask = torch.arange(E_)[None] < cnt[:, None]
+    lay = {"mask": mask, "label": torch.randint(0, 4, (n, E_), generator=g) * mask}
+    for k in GEO:
+        lay[k] = torch.rand(n, E_, generator=g) * mask
+    retr = GpuRetriever(torch.randn(n, 512, generator=g), lay, device="cpu")
+    torch.set_num_threads(8)
+    out = bench.model_api_e2e(model.eval(), retr, torch.rand(2, 4, 64, 64, generator=g), torch.randn(2, 512, generator=g),
+                              torch.device("cpu"), n=2, iters=1)
+    assert out["unit"] == "layouts/s" and out["value"] > 0 and out["canvases_per_call"] == 2
