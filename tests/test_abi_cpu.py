@@ -318,3 +318,43 @@ def test_knn_entry_points_validate_before_touching_the_device():
         assert L.ralf_check_device(0) < 0
         L.ralf_last_cuda_error.restype = C.c_char_p
         assert len(L.ralf_last_cuda_error()) > 0
+
+
+def test_bench_line_assembly_with_stub_measurements(capsys):
+    """The block of bench.py that turns the measurements into the contract's JSON line, executed here with stub numbers (the
+    measurements themselves need a B200): every key the driver reads is present and the arithmetic holds together."""
+    import textwrap
+    import types
+
+    import bench
+
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    a = src.index("    if rank == 0:\n        peaks = {}")
+    b = src.index("        print(json.dumps(line))") + len("        print(json.dumps(line))")
+    block = textwrap.dedent(src[a:b])
+
+    class Ev:
+        def elapsed_time(self, other):
+            return 2.9  # ms for the 8 k-NN passes of a step
+
+    sized = lambda n: types.SimpleNamespace(numel=lambda: n, shape=(1_000_000, 512))
+    ns = dict(vars(bench))
+    ns.update(rank=0, world=1, B=1024, HW=256, S=60, ms=930.0, ms_e2e=940.0, knn_ev=[(Ev(), Ev())] * 5, launches=28910,
+              args=types.SimpleNamespace(steps=5, warmup=3, precision="bf16x3", micro_batch=128, gallery=1_000_000, elems=12,
+                                         overlap=False, decode_ways=1, no_cpu_baseline=True, hw=256),
+              retr=types.SimpleNamespace(emb=sized(1)), model=types.SimpleNamespace(special_token_ids={}),
+              img_h=sized(1024 * 4 * 256 * 256), qry_h=sized(1024 * 512), clocks={"sm_mhz": 1900, "sm_max_mhz": 1965, "reasons": []},
+              other=[{"kernel": "a", "bound": "hbm", "achieved": 6250.9, "unit": "GB/s", "ms_per_launch": 0.1342, "launches_per_step": 360},
+                     {"kernel": "b", "bound": "tensor", "achieved": 1273.4, "unit": "TFLOP/s", "ms_per_launch": 0.0911, "launches_per_step": 48}],
+              api={"value": 900.0, "unit": "layouts/s"})
+    exec(block, ns)
+    d = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    for key in ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"]:
+        assert key in d, key
+    assert d["value"] == round(1024 / 0.186, 2) and d["ms_per_step"] == 186.0 and d["vs_baseline"] is None and d["n_gpus"] == 1
+    assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and d["e2e"]["h2d_bytes_per_step"] == 1075838976
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3 and 0 < r["share_of_step"] < 0.05
+    assert "workload" in d["config"] and "model" not in d["config"] and d["gpu_launches"] == 28910
+    assert [o["share_of_step"] for o in d["roofline_other"]] == [round(0.1342 * 360 / 186.0, 4), round(0.0911 * 48 / 186.0, 4)]
