@@ -518,3 +518,46 @@ def test_bench_model_api_leg_runs_on_the_oracle_engine(monkeypatch):
     out = bench.model_api_e2e(model.eval(), retr, torch.rand(2, 4, 64, 64, generator=g), torch.randn(2, 512, generator=g),
                               torch.device("cpu"), n=2, iters=1)
     assert out["unit"] == "layouts/s" and out["value"] > 0 and out["canvases_per_call"] == 2
+
+
+def test_sample_graph_switch_only_takes_plain_greedy(monkeypatch):
+    """RALF_SAMPLE_GRAPH routes model.sample() through Engine.generate_graphed for unconstrained greedy decoding only;
+    constrained tasks (forced-token table) and stochastic samplers keep the eager loop."""
+    from oracle import synth
+    from ralf_b200 import generator as G
+
+    calls = []
+
+    class Eng(_OracleEngine):
+        def generate_graphed(self, mem_s, B, Mlen, token_mask, bos_id, pad_id, steps):
+            calls.append("graphed")
+            return _OracleEngine.generate(self, mem_s, B, Mlen, token_mask, bos_id, pad_id, steps)
+
+        def generate(self, *a, **k):
+            calls.append("eager")
+            k.pop("sampling", None)
+            return _OracleEngine.generate(self, *a, **k)
+
+    tok = helpers.make_tokenizer()
+    model = G.RALF(features=None, tokenizer=tok, dataset_name="cgl", max_seq_length=10, top_k=16, pretrained=False,
+                   use_multitask=True)
+    sd = helpers.synth_weights("ralf_cgl", 3)
+    model.load_state_dict(sd, strict=True)
+    eng = Eng(sd, tok.name_to_id("pad"))
+    monkeypatch.setattr(model, "engine", lambda: eng)
+    monkeypatch.setattr(G, "_SAMPLE_GRAPH", True)
+    torch.set_num_threads(8)
+    batch = synth.synth_batch(2, 64, 64, 10, 16, 4, seed=8)
+    cond, _ = T.get_condition(copy.deepcopy(batch), "uncond", tok)
+    plain = model.eval().sample(cond=cond, cond_type="uncond", return_seq=True)
+    assert calls == ["graphed"]
+    monkeypatch.setattr(G, "_SAMPLE_GRAPH", False)
+    calls.clear()
+    eager = model.sample(cond=cond, cond_type="uncond", return_seq=True)
+    assert calls == ["eager"] and torch.equal(plain["seq"], eager["seq"])
+    monkeypatch.setattr(G, "_SAMPLE_GRAPH", True)
+    calls.clear()
+    torch.manual_seed(0)
+    cond_c, _ = T.get_condition(copy.deepcopy(batch), "c", tok)
+    model.sample(cond=cond_c, cond_type="c")
+    assert calls == ["eager"]  # a forced-token table: not the plain loop
