@@ -157,3 +157,35 @@ def test_violation_counts_match_reference_on_corrupted_outputs(seed):
         vio = T.calculate_violation(task, cond, torch.from_numpy(z[f"{seed}_{task}_seq"]), tok)
         assert [vio["total"], vio["viorated"]] == z[f"{seed}_{task}_violation"].tolist(), (seed, task)
         assert vio["viorated"] > 0
+
+
+@pytest.mark.parametrize("task", ["c", "cwh", "partial", "refinement"])
+def test_model_sample_constrained_tasks_end_to_end_on_oracle_engine(task, monkeypatch):
+    """The drop-in class's sample() for the constrained tasks, wired end to end on the CPU with the oracle standing in for
+    the kernels (tests/test_relation_cpu.py:_OracleEngine): get_condition -> task preprocessor -> forced-token table ->
+    encode -> restricted greedy decode -> tokenizer.decode -> violation count = the reference's sample() golden."""
+    import copy
+
+    from ralf_b200 import engine as E
+    from ralf_b200 import generator as G
+    from ralf_b200 import task as T
+    from tests.test_relation_cpu import _OracleEngine
+
+    z, meta = helpers.load_golden("tasks_cgl_256")
+    tok = helpers.make_tokenizer()
+    model = G.RALF(features=None, tokenizer=tok, dataset_name="cgl", max_seq_length=10, top_k=16, auxilary_task="uncond",
+                   use_multitask=True, pretrained=False)
+    sd = helpers.synth_weights("ralf_cgl", meta["seed"])
+    model.load_state_dict(sd, strict=True)
+    monkeypatch.setattr(model, "engine", lambda: _OracleEngine(sd, tok.name_to_id("pad")))
+    monkeypatch.setattr(E.ops, "embed", lambda seq, col, S, emb, scale, pe, pos0: seq[:, col:col + 1].to(torch.float32))
+    torch.set_num_threads(8)
+    batch = helpers.synth_batch({**meta, "E": 10, "K": 16})
+    torch.manual_seed(meta["rng_seed"][task])
+    cond, _ = T.get_condition(copy.deepcopy(batch), task, tok)
+    out, vio = model.eval().sample(cond=cond, sampling_cfg={"name": "deterministic"}, cond_type=task, return_violation=True,
+                                   return_seq=True)
+    np.testing.assert_array_equal(out["seq"].numpy(), z[f"{task}_gen_seq"])
+    for k in ["label", "mask", "center_x", "center_y", "width", "height"]:
+        np.testing.assert_array_equal(out[k].numpy(), z[f"{task}_gen_{k}"])
+    assert [vio["total"], vio["viorated"]] == z[f"{task}_violation"].tolist()
