@@ -151,7 +151,8 @@ def describe_relationships(batch: dict, label_names: Sequence[str]) -> dict:
                 loc_rows.append([*tag[i], loc_relation(box[i], box[j]), *tag[j]])
                 size_rows.append([*tag[i], size_relation(box[i], box[j]), *tag[j]])
             canvas_rows.append([*tag[i], canvas_relation(box[i]), CANVAS, "pad"])
-        table[batch["id"][b]] = loc_rows + size_rows + canvas_rows
+        key = batch["id"][b]
+        table[key.item() if torch.is_tensor(key) else key] = loc_rows + size_rows + canvas_rows
     return table
 
 
