@@ -137,7 +137,7 @@ def _register(root: nn.Module, name: str, tensor: Tensor, kind: str) -> None:
         node.register_buffer(parts[-1], tensor)
 
 
-def _initial_value(name: str, shape: tuple, shapes: dict, is_ralf: bool = True) -> Tensor:
+def _initial_value(name: str, shape: tuple, shapes: dict, weight_init: bool = True) -> Tensor:
     """Initial value of one floating-point state-dict entry, with the distribution the reference constructor leaves it in
     (tests/golden/init_stats.json, dumped from freshly built reference models):
       * every matrix of the three transformers (image encoder, constraint encoder, decoder): Xavier-uniform
@@ -146,7 +146,8 @@ def _initial_value(name: str, shape: tuple, shapes: dict, is_ralf: bool = True) 
         :225-226; retrieval_augmented_autoreg.py:694);
       * LayerNorm / BatchNorm: ones and zeros, running statistics 0 / 1; attention in/out projection biases: zeros;
       * every other Linear / Conv2d: PyTorch's default U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and bias.
-    The Autoreg baseline class never runs its ``init_weights`` (models/autoreg.py:85-93, ``weight_init`` off): there only
+    ``weight_init`` is the reference's constructor flag: on by default for the RALF class, off for the Autoreg baseline
+    (models/autoreg.py:39,85-93), which therefore never runs ``init_weights``: there only
     the constraint encoder is Xavier / N(0, 0.02) (:478-488), attention input projections keep nn.MultiheadAttention's own
     Xavier default, and the decoder embedding stays nn.Embedding's N(0, 1).
     Drawn from the global torch generator, like the reference (train.py seeds it)."""
@@ -158,7 +159,7 @@ def _initial_value(name: str, shape: tuple, shapes: dict, is_ralf: bool = True) 
     if leaf == "running_mean" or leaf == "in_proj_bias" or name.endswith("out_proj.bias"):
         return torch.zeros(shape)
     small_normal = ("user_const_encoder.emb.weight", "task_emb.weight") + \
-        (("decoder.emb.weight", "decoder.head.1.weight") if is_ralf else ())
+        (("decoder.emb.weight", "decoder.head.1.weight") if weight_init else ())
     if name in small_normal:
         return torch.randn(shape) * 0.02
     if name == "decoder.emb.weight":
@@ -176,7 +177,7 @@ def _initial_value(name: str, shape: tuple, shapes: dict, is_ralf: bool = True) 
     fan_in = 1
     for d_ in shape[1:]:
         fan_in *= d_
-    xavier = ("transformer_encoder.", "decoder.transformer.", "user_const_encoder.encoder.") if is_ralf \
+    xavier = ("transformer_encoder.", "decoder.transformer.", "user_const_encoder.encoder.") if weight_init \
         else ("user_const_encoder.encoder.",)
     if len(shape) == 2 and (name.startswith(xavier) or leaf == "in_proj_weight"):
         bound = (6.0 / (fan_in + shape[0])) ** 0.5
@@ -250,7 +251,7 @@ class _B200LayoutModel(nn.Module):
             elif kind == "bool":
                 t = torch.zeros(shape, dtype=torch.bool)
             else:
-                t = _initial_value(name, shape, shapes, self.IS_RALF)
+                t = _initial_value(name, shape, shapes, bool(kwargs.get("weight_init", self.IS_RALF)))
             _register(self, name, t, kind)
         if pretrained:
             self._load_pretrained_files()
