@@ -67,6 +67,14 @@ int ralf_knn_topk(const float* gallery, int n, int d, const float* queries, int 
 int ralf_knn_topk_exact(const float* gallery, int n, int d, const float* queries, int q, int k,
                         long long index_base, long long* out_idx, float* out_score,
                         void* workspace, size_t workspace_bytes, void* stream);
+/* Device-side exactness guarantee (no host round trip; safe inside a CUDA graph): every query with certified[q] == 0
+ * after ralf_knn_topk is re-run through the exact scan and its rows of out_idx / out_score are overwritten;
+ * certified[q] becomes 2.  With nothing to fix the three launches return after one load each.  Replaces the
+ * "IndexFlat is exact" property of the reference's FAISS index (retrieval/retriever.py:79-84,200-202) for inputs the
+ * TF32 bound cannot certify (e.g. more than C near-duplicate rows around the cut).  Same workspace as ralf_knn_topk. */
+int ralf_knn_fixup_exact(const float* gallery, int n, int d, const float* queries, int q, int k,
+                         long long index_base, int* certified, long long* out_idx, float* out_score,
+                         void* workspace, size_t workspace_bytes, void* stream);
 /* Merge `parts` per-shard result lists ([parts, q, k] scores / indices, e.g. after an NCCL
  * all-gather) into the global top-k with the same ordering rule. */
 int ralf_knn_merge(const float* part_score, const long long* part_idx, int parts, int q, int k,

@@ -61,6 +61,10 @@ def lib() -> C.CDLL:
             C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_longlong,
             C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
         ]
+        L.ralf_knn_fixup_exact.argtypes = [
+            C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_longlong,
+            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+        ]
         L.ralf_knn_merge.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_void_p]
         L.ralf_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]

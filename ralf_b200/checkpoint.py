@@ -40,7 +40,7 @@ def load_model(model: torch.nn.Module, ckpt_dir: str, device, best_or_final: str
 def save_train_state(engine, path: str, *, epoch: int = 0, best_val_loss: float = float("inf")) -> None:
     """AdamW state of a :class:`ralf_b200.train.TrainEngine` keyed by parameter name (layout-independent)."""
     ps = engine.ps
-    state = {"step_count": engine.step_count, "seed": engine.seed, "dropout": engine.dropout, "epoch": epoch,
+    state = {"step_count": engine.step_count, "base_seed": engine.base_seed, "dropout": engine.dropout, "epoch": epoch,
              "best_val_loss": best_val_loss, "exp_avg": {}, "exp_avg_sq": {}}
     for name, (off, cnt, shape) in ps.offsets.items():
         state["exp_avg"][name] = ps.flat_m[off:off + cnt].view(shape).cpu().clone()
@@ -61,7 +61,9 @@ def load_train_state(engine, path: str) -> dict:
         ps.flat_m[off:off + cnt].copy_(state["exp_avg"][name].reshape(-1))
         ps.flat_v[off:off + cnt].copy_(state["exp_avg_sq"][name].reshape(-1))
     engine.step_count = int(state["step_count"])
-    engine.seed = int(state["seed"])
+    if "base_seed" in state:  # the per-rank dropout stream is re-derived from the base seed and THIS engine's rank
+        engine.base_seed = int(state["base_seed"])
+    engine._weights_changed()
     return {k: state[k] for k in ("epoch", "best_val_loss", "step_count")}
 
 

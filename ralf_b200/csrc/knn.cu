@@ -441,18 +441,17 @@ knn_threshold_kernel(const float* __restrict__ tmax, const int sample_tiles, flo
 
 // Step 4.  One CTA (256 threads) per query.  `parts` candidate lists of C keys each (0 = empty slot).
 template <int C>
-__global__ void __launch_bounds__(256)
-knn_rerank_kernel(const uint64_t* __restrict__ cand, const int parts, const float* __restrict__ gallery,
-                  const float* __restrict__ queries, const int n, const int d, const int k,
-                  const long long index_base, const float gmax_norm, const float* __restrict__ thr_init,
-                  long long* __restrict__ out_idx, float* __restrict__ out_score, int* __restrict__ certified) {
+__device__ __forceinline__ void
+knn_rerank_body(const int q, const uint64_t* __restrict__ cand, const int parts, const float* __restrict__ gallery,
+                const float* __restrict__ queries, const int n, const int d, const int k,
+                const long long index_base, const float gmax_norm, const float* __restrict__ thr_init,
+                long long* __restrict__ out_idx, float* __restrict__ out_score, int* __restrict__ certified) {
   __shared__ uint64_t sel[C];
   __shared__ uint64_t scratch[8 * C];
   __shared__ float exact[C];
   __shared__ uint64_t fin[C];
   __shared__ int frank[C];
   __shared__ float qnorm2_s[8];
-  const int q = blockIdx.x;
   const int qtile = q >> 7, ql = q & 127;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint64_t* src = cand + (static_cast<size_t>(qtile) * parts * 128 + ql) * C;
@@ -533,15 +532,78 @@ knn_rerank_kernel(const uint64_t* __restrict__ cand, const int parts, const floa
   }
 }
 
+template <int C>
+__global__ void __launch_bounds__(256)
+knn_rerank_kernel(const uint64_t* __restrict__ cand, const int parts, const float* __restrict__ gallery,
+                  const float* __restrict__ queries, const int n, const int d, const int k,
+                  const long long index_base, const float gmax_norm, const float* __restrict__ thr_init,
+                  long long* __restrict__ out_idx, float* __restrict__ out_score, int* __restrict__ certified) {
+  knn_rerank_body<C>(blockIdx.x, cand, parts, gallery, queries, n, d, k, index_base, gmax_norm, thr_init, out_idx,
+                     out_score, certified);
+}
+
+// Exact fix-up of the queries phase 1 could not certify (ralf_knn_fixup_exact), entirely on the device:
+//   knn_collect_uncertified_kernel  compacts {q : certified[q] == 0} into qlist / qcount;
+//   knn_exact_scan_kernel           (qlist form) scans the gallery with the canonical dot for the listed queries only;
+//   knn_rerank_listed_kernel        orders their candidates, overwrites their result rows and marks them certified = 2.
+// With nothing to fix (the usual case) the three launches exit after one load each.
+__global__ void __launch_bounds__(1024)
+knn_collect_uncertified_kernel(const int* __restrict__ certified, const int q, int* __restrict__ qlist,
+                               int* __restrict__ qcount) {
+  __shared__ int warp_tot[32];
+  __shared__ int base_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base_s = 0;
+  __syncthreads();
+  for (int q0 = 0; q0 < q; q0 += 1024) {  // ascending order: the list (and with it every later launch) is deterministic
+    const int i = q0 + threadIdx.x;
+    const bool bad = i < q && certified[i] == 0;
+    const unsigned m = __ballot_sync(0xffffffffu, bad);
+    if (lane == 0) warp_tot[warp] = __popc(m);
+    __syncthreads();
+    int off = base_s;
+    for (int w = 0; w < warp; ++w) off += warp_tot[w];
+    if (bad) qlist[off + __popc(m & ((1u << lane) - 1u))] = i;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w = 0; w < 32; ++w) t += warp_tot[w];
+      base_s += t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *qcount = base_s;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256)
+knn_rerank_listed_kernel(const int* __restrict__ qlist, const int* __restrict__ qcount,
+                         const uint64_t* __restrict__ cand, const int parts, const float* __restrict__ gallery,
+                         const float* __restrict__ queries, const int n, const int d, const int k,
+                         const long long index_base, long long* __restrict__ out_idx, float* __restrict__ out_score,
+                         int* __restrict__ certified) {
+  const int cnt = *qcount;
+  for (int qi = blockIdx.x; qi < cnt; qi += gridDim.x) {  // CTA-uniform trip count
+    const int q = qlist[qi];
+    knn_rerank_body<C>(q, cand, parts, gallery, queries, n, d, k, index_base, 0.f, nullptr, out_idx, out_score,
+                       nullptr);
+    __syncthreads();
+    if (threadIdx.x == 0) certified[q] = 2;  // exact by construction
+  }
+}
+
 // Exact CUDA-core scan (fallback + independent check).  grid = (slices, q); block = 256 (8 warps);
 // each warp scores rows with the canonical dot and keeps a sorted top-C list (lane 0 inserts).
 template <int C>
 __global__ void __launch_bounds__(256)
 knn_exact_scan_kernel(const float* __restrict__ gallery, const float* __restrict__ queries, const int n,
-                      const int d, uint64_t* __restrict__ cand) {
+                      const int d, uint64_t* __restrict__ cand, const int* __restrict__ qlist,
+                      const int* __restrict__ qcount) {
   __shared__ uint64_t lists[8][C];
-  const int q = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cnt = qlist ? *qcount : gridDim.y;
+  for (int qi = blockIdx.y; qi < cnt; qi += gridDim.y) {
+  const int q = qlist ? qlist[qi] : qi;
   const float* qv = queries + static_cast<size_t>(q) * d;
   const long long r0 = (static_cast<long long>(blockIdx.x) * n) / gridDim.x;
   const long long r1 = (static_cast<long long>(blockIdx.x + 1) * n) / gridDim.x;
@@ -574,6 +636,8 @@ knn_exact_scan_kernel(const float* __restrict__ gallery, const float* __restrict
   const int part = blockIdx.x * 8 + warp;
   uint64_t* out = cand + ((static_cast<size_t>(qtile) * parts + part) * 128 + ql) * C;
   for (int e = lane; e < C; e += 32) out[e] = lst[e];
+  __syncwarp();
+  }
 }
 
 __global__ void knn_merge_kernel(const float* __restrict__ ps, const long long* __restrict__ pi, const int parts,
@@ -631,13 +695,17 @@ static size_t knn_cand_bytes(int n, int q, int C) {
 }
 
 // workspace = [candidate lists][pre-pass group maxima: qtiles x 128 tiles x 8 groups x 128 lanes f32][thresholds]
+//             [fix-up query list: q + 1 ints (count last)]
+static size_t knn_front_bytes(int n, int q, int C) {
+  const size_t qtiles = (q + 127) / 128;
+  return knn_cand_bytes(n, q, C) + qtiles * KNN_SAMPLE_TILES * KNN_GROUPS * 128 * sizeof(float) +
+         qtiles * 128 * sizeof(float);
+}
 extern "C" size_t ralf_knn_workspace_bytes(int n, int d, int q, int k) {
   (void)d;
   const int C = knn_c_for_k(k);
   if (C == 0 || n <= 0 || q <= 0) return 0;
-  const size_t qtiles = (q + 127) / 128;
-  return knn_cand_bytes(n, q, C) + qtiles * KNN_SAMPLE_TILES * KNN_GROUPS * 128 * sizeof(float) +
-         qtiles * 128 * sizeof(float);
+  return knn_front_bytes(n, q, C) + (static_cast<size_t>(q) + 1) * sizeof(int);
 }
 
 template <int C>
@@ -713,7 +781,7 @@ static int knn_exact_impl(const float* gallery, int n, int d, const float* queri
                           cudaStream_t st) {
   const int parts = knn_exact_slices(C) * 8;
   dim3 grid(knn_exact_slices(C), q);
-  knn_exact_scan_kernel<C><<<grid, 256, 0, st>>>(gallery, queries, n, d, cand);
+  knn_exact_scan_kernel<C><<<grid, 256, 0, st>>>(gallery, queries, n, d, cand, nullptr, nullptr);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error(e);
   knn_rerank_kernel<C><<<q, 256, 0, st>>>(cand, parts, gallery, queries, n, d, k, index_base, 0.f, nullptr, out_idx,
@@ -733,6 +801,38 @@ extern "C" int ralf_knn_topk_exact(const float* gallery, int n, int d, const flo
   uint64_t* cand = reinterpret_cast<uint64_t*>(workspace);
   if (C == 32) return knn_exact_impl<32>(gallery, n, d, queries, q, k, index_base, out_idx, out_score, cand, st);
   return knn_exact_impl<64>(gallery, n, d, queries, q, k, index_base, out_idx, out_score, cand, st);
+}
+
+template <int C>
+static int knn_fixup_impl(const float* gallery, int n, int d, const float* queries, int q, int k,
+                          long long index_base, int* certified, long long* out_idx, float* out_score,
+                          void* workspace, cudaStream_t st) {
+  uint64_t* cand = reinterpret_cast<uint64_t*>(workspace);
+  int* qlist = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + knn_front_bytes(n, q, C));
+  int* qcount = qlist + q;
+  knn_collect_uncertified_kernel<<<1, 1024, 0, st>>>(certified, q, qlist, qcount);
+  const int slices = knn_exact_slices(C);
+  const int gy = q < 32 ? q : 32;
+  knn_exact_scan_kernel<C><<<dim3(slices, gy), 256, 0, st>>>(gallery, queries, n, d, cand, qlist, qcount);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e);
+  knn_rerank_listed_kernel<C><<<q < 128 ? q : 128, 256, 0, st>>>(qlist, qcount, cand, slices * 8, gallery, queries, n, d,
+                                                                k, index_base, out_idx, out_score, certified);
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_knn_fixup_exact(const float* gallery, int n, int d, const float* queries, int q, int k,
+                                    long long index_base, int* certified, long long* out_idx, float* out_score,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  if (!gallery || !queries || !out_idx || !out_score || !certified) return RALF_ERR_NULL;
+  if (n <= 0 || q <= 0 || d <= 0 || k <= 0) return RALF_ERR_SHAPE;
+  const int C = knn_c_for_k(k);
+  if (C == 0) return RALF_ERR_SHAPE;
+  if (!workspace || workspace_bytes < ralf_knn_workspace_bytes(n, d, q, k)) return RALF_ERR_WORKSPACE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (C == 32)
+    return knn_fixup_impl<32>(gallery, n, d, queries, q, k, index_base, certified, out_idx, out_score, workspace, st);
+  return knn_fixup_impl<64>(gallery, n, d, queries, q, k, index_base, certified, out_idx, out_score, workspace, st);
 }
 
 extern "C" int ralf_knn_merge(const float* part_score, const long long* part_idx, int parts, int q, int k,

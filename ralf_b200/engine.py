@@ -535,7 +535,8 @@ class Engine:
         Through the model-class API (``model.sample`` called batch after batch by inference.py) the decode loop is ~4 k
         launches issued from Python, i.e. host-bound for the batch sizes the reference's loaders use; the loop only
         depends on the memory K/V cache, so it is captured once per shape over a static cache that ``cross_kv`` then fills
-        in place.  Opt-in (``RALF_SAMPLE_GRAPH=1``) until it has run on hardware; at most 4 shapes are kept."""
+        in place.  Default of ``model.sample()`` for plain greedy decoding (``RALF_SAMPLE_GRAPH=0`` switches it off); at most
+        4 shapes are kept."""
         cache = self.__dict__.setdefault("_gen_graphs", {})
         key = (B, Mlen, steps, bos_id, pad_id)
         entry = cache.get(key)

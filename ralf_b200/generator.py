@@ -25,8 +25,9 @@ from .engine import Engine
 from .task import ConditionalInputs, TaskPreprocessor, get_condition  # noqa: F401  (re-exported: reference import sites)
 from .tokenizer import LayoutSequenceTokenizer
 
-# RALF_SAMPLE_GRAPH=1: model.sample()'s plain greedy decode loop is replayed from a per-shape CUDA graph (opt-in, unmeasured)
-_SAMPLE_GRAPH = __import__("os").environ.get("RALF_SAMPLE_GRAPH", "0") != "0"
+# model.sample()'s plain greedy decode loop is replayed from a per-shape CUDA graph (measured on B200: 2471 vs 1632 layouts/s
+# through the drop-in API at batch 128, profiles/r2_ab_call1.md); RALF_SAMPLE_GRAPH=0 restores the eager loop for A/B runs.
+_SAMPLE_GRAPH = __import__("os").environ.get("RALF_SAMPLE_GRAPH", "1") != "0"
 
 UnconditionalPreprocessor = TaskPreprocessor  # task=None/"uncond" (task_preprocessor.py:354-384)
 

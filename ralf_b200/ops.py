@@ -13,7 +13,7 @@ ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2}
 
 # Number of OUR kernels launched through the C ABI (bench.py reports the delta over the timed region).
 _LAUNCHES = 0
-_KERNELS_PER_CALL = {"ralf_knn_topk": 4, "ralf_knn_topk_exact": 2, "ralf_knn_merge": 2, "ralf_ce_label_smooth": 2}
+_KERNELS_PER_CALL = {"ralf_knn_topk": 4, "ralf_knn_topk_exact": 2, "ralf_knn_fixup_exact": 3, "ralf_knn_merge": 2, "ralf_ce_label_smooth": 2}
 
 
 def launch_count() -> int:
@@ -190,8 +190,13 @@ def knn_topk(
     gallery_max_norm: float = 0.0,
     exact: bool = False,
     workspace: Optional[torch.Tensor] = None,
+    fixup: bool = True,
 ) -> tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
-    """Top-k maximum inner product (ralf_knn_topk).  Returns (idx int64 [q,k], score fp32 [q,k], certified)."""
+    """Top-k maximum inner product (ralf_knn_topk).  Returns (idx int64 [q,k], score fp32 [q,k], certified).
+    ``fixup`` (default): queries the TF32 bound cannot certify are re-run through the exact scan on the device
+    (ralf_knn_fixup_exact, no host sync, capturable) -- the result is the exact top-k unconditionally and
+    ``certified`` is 1 (proved by the bound) or 2 (exact scan) for every query.  ``fixup=False`` returns the raw
+    phase-1/2 result with certified in {0, 1} (tests of the certificate itself)."""
     assert gallery.is_cuda and queries.is_cuda and gallery.dtype == torch.float32 and queries.dtype == torch.float32
     gallery, queries = gallery.contiguous(), queries.contiguous()
     n, d = gallery.shape
@@ -213,6 +218,10 @@ def knn_topk(
                           workspace.data_ptr(), ws_bytes, _stream()), "ralf_knn_topk")
     global _LAUNCHES
     _LAUNCHES += 4 * ((q + 127) // 128 - 1)  # one pass of 4 kernels per 128 queries
+    if fixup:
+        check(L.ralf_knn_fixup_exact(gallery.data_ptr(), n, d, queries.data_ptr(), q, k, index_base, cert.data_ptr(),
+                                     idx.data_ptr(), score.data_ptr(), workspace.data_ptr(), ws_bytes, _stream()),
+              "ralf_knn_fixup_exact")
     return idx, score, cert
 
 

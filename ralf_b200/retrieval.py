@@ -52,7 +52,10 @@ class GpuRetriever:
 
     # -- search ---------------------------------------------------------------------------------
     def search_local(self, queries: torch.Tensor, k: int):
-        """Top-k of this rank's shard for every query: (idx int64 [Q,k] global ids, score fp32 [Q,k])."""
+        """Top-k of this rank's shard for every query: (idx int64 [Q,k] global ids, score fp32 [Q,k]).
+        Exact unconditionally: queries the TF32 bound cannot certify are re-run through the exact scan on the device
+        (``ops.knn_topk(fixup=True)``: no host sync, so it is part of the captured search graph); afterwards
+        ``last_certified`` is 1 (bound) or 2 (exact scan) for every query."""
         q = queries.to(self.dev, torch.float32).contiguous()
         if self.knn_ways > 1 and q.shape[0] > 128:
             return self._search_local_ways(q, k)
@@ -81,16 +84,10 @@ class GpuRetriever:
         self.last_certified = cert
         return idx, score
 
-    def search(self, queries: torch.Tensor, k: int, *, certify: bool = False):
-        """Global top-k.  With ``certify`` uncertified queries (TF32 bound inconclusive: near-duplicate
-        clusters wider than the candidate list) are re-run through the exact CUDA-core kernel."""
+    def search(self, queries: torch.Tensor, k: int, *, certify: bool = True):
+        """Global top-k (exact: see ``search_local``; ``certify`` is kept for callers of the round-1 signature and no
+        longer selects anything -- the device-side fix-up always runs)."""
         idx, score = self.search_local(queries, k)
-        if certify:
-            bad = (self.last_certified == 0).nonzero().flatten()
-            if bad.numel():  # host sync only on this opt-in path
-                q = queries.to(self.dev, torch.float32)[bad].contiguous()
-                ei, es, _ = ops.knn_topk(self.emb, q, k, index_base=self.index_base, exact=True)
-                idx[bad], score[bad] = ei, es
         if self.world > 1:
             idx, score = exchange_and_merge(idx, score, self.world, self.pg, ops.knn_merge)
         return idx, score

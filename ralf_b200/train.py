@@ -59,12 +59,18 @@ class _TapeLoss(torch.autograd.Function):
 class TrainEngine:
     limits = ("frozen FIDNetV3 evaluated without dropout",)
 
+    @property
+    def seed(self) -> int:
+        """Per-rank dropout seed: every rank draws its own masks from one base seed."""
+        return (self.base_seed * 0x9E3779B97F4A7C15 + self.rank * 0xD1B54A32D192ED03) & (2 ** 64 - 1)
+
     def __init__(self, model, *, lr: float = 1e-4, weight_decay: float = 1e-4, body_lr_scale: float = 0.1,
                  max_grad_norm: float = 0.1, world_size: int = 1, process_group=None, train_trunk: bool = True,
                  dropout: float = 0.1, seed: int = 0, rank: int = 0) -> None:
         self.model = model
         self.dropout = float(dropout)
-        self.seed = (int(seed) * 0x9E3779B97F4A7C15 + int(rank) * 0xD1B54A32D192ED03) & (2 ** 64 - 1)
+        self.rank = int(rank)
+        self.base_seed = int(seed)  # what checkpoints store; the per-rank stream is derived from it
         self.dev = model.device
         self.lr, self.wd, self.body_scale, self.max_norm = lr, weight_decay, body_lr_scale, max_grad_norm
         self.world, self.pg = world_size, process_group
@@ -97,6 +103,7 @@ class TrainEngine:
         self._dyn = torch.ones(3, dtype=torch.float32, device=self.dev)
         self._seed_host = torch.zeros(64, dtype=torch.int64).pin_memory()
         self._seed_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self._slot_done: list = [None] * 64  # event after the async copies out of ring slot i: waited on before rewriting it
         self._graph = None
         self.refresh_operands()
 
@@ -344,6 +351,7 @@ class TrainEngine:
         """Per-step scalars of the optimiser go through device memory (a captured step must not bake them in)."""
         self.step_count += 1
         t = self.step_count
+        self._wait_slot(t % 64)
         slot = self._dyn_host[t % 64]
         slot[0] = 1.0 if lr is None else lr / self.lr  # scheduler (MultiStepLR) scales every group alike
         slot[1] = 1.0 - 0.9 ** t
@@ -351,15 +359,28 @@ class TrainEngine:
         self._dyn.copy_(slot, non_blocking=True)
         self._set_step_seed()
 
+    def _wait_slot(self, i: int) -> None:
+        """The host may run more than 64 steps ahead of the device (train_step_graph never syncs): before a pinned ring
+        slot is rewritten, wait until the copies that read it 64 steps ago have executed."""
+        ev = self._slot_done[i]
+        if ev is not None:
+            ev.synchronize()
+
     def _set_step_seed(self) -> None:
         """Dropout seed of step ``step_count`` (SplitMix64 of base seed + step) -> device memory (graph-replay safe)."""
         z = (self.seed + 0x9E3779B97F4A7C15 * self.step_count) & (2 ** 64 - 1)
         z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & (2 ** 64 - 1)
         z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & (2 ** 64 - 1)
         z ^= z >> 31
-        slot = self._seed_host[self.step_count % 64:self.step_count % 64 + 1]
+        i = self.step_count % 64
+        self._wait_slot(i)
+        slot = self._seed_host[i:i + 1]
         slot[0] = z - 2 ** 64 if z >= 2 ** 63 else z
         self._seed_dev.copy_(slot, non_blocking=True)
+        if self._seed_dev.is_cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            self._slot_done[i] = ev
 
     def _step_body(self, inputs: dict, targets: dict) -> torch.Tensor:
         ps = self.ps
@@ -377,10 +398,18 @@ class TrainEngine:
         self.last_grad_norm = norm
         return loss
 
+    def _weights_changed(self) -> None:
+        """The master weights were updated in place: the model's cached inference Engine (split-bf16 GEMM operands and
+        folded BatchNorm made from the OLD weights, next to live views of the new biases / norms) is stale -- drop it, so
+        the next evaluate() / sample() / forward() in eval mode re-prepares it (generator.engine())."""
+        self.model._engine = None
+
     def train_step(self, inputs: dict, targets: dict, lr: Optional[float] = None) -> torch.Tensor:
         """One optimisation step (train.py:440-454), eager launches.  Returns the loss (device scalar; no host sync)."""
         self._set_step_scalars(lr)
-        return self._step_body(inputs, targets)
+        loss = self._step_body(inputs, targets)
+        self._weights_changed()
+        return loss
 
     # ------------------------------------------------------------------------------------------
     # CUDA-graph replay of the whole step (fixed batch shape): ~1.9 k kernel launches become one graph launch
@@ -393,7 +422,9 @@ class TrainEngine:
         def static(v):
             if torch.is_tensor(v):
                 return v.to(dev).clone()
-            return {k: static(x) for k, x in v.items()}
+            if isinstance(v, dict):
+                return {k: static(x) for k, x in v.items()}
+            return v  # non-tensor entries (e.g. the reference's retrieved["index"] lists) are not inputs of the kernels
 
         self._g_in, self._g_tg = static(inputs), static(targets)
         side = torch.cuda.Stream(device=dev)
@@ -409,15 +440,27 @@ class TrainEngine:
     def train_step_graph(self, inputs: dict, targets: dict, lr: Optional[float] = None) -> torch.Tensor:
         assert getattr(self, "_graph", None) is not None, "call capture(inputs, targets) first"
 
+        def same_shape(dst, src) -> bool:
+            if torch.is_tensor(dst):
+                return torch.is_tensor(src) and tuple(src.shape) == tuple(dst.shape)
+            if isinstance(dst, dict):
+                return isinstance(src, dict) and all(k in src and same_shape(dst[k], src[k]) for k in dst)
+            return True
+
         def fill(dst, src):
             if torch.is_tensor(dst):
                 dst.copy_(src, non_blocking=True)
-            else:
+            elif isinstance(dst, dict):
                 for k in dst:
                     fill(dst[k], src[k])
 
+        if not (same_shape(self._g_in, inputs) and same_shape(self._g_tg, targets)):
+            # a captured graph bakes the batch shape in (seq_layout_const varies per batch for the constrained tasks and
+            # under use_multitask): such a batch takes the eager step -- same kernels, same result, only the launches differ
+            return self.train_step(inputs, targets, lr)
         fill(self._g_in, inputs)
         fill(self._g_tg, targets)
         self._set_step_scalars(lr)
         self._graph.replay()
+        self._weights_changed()
         return self._g_loss

@@ -198,7 +198,6 @@ def _attention_in_child(env: dict, shapes: list) -> dict:
         return {tuple(sh): torch.load(os.path.join(tmp, "o_%d_%d_%d.pt" % tuple(sh))) for sh in shapes}
 
 
-@pytest.mark.hw_pending(order=40, optin=True)
 def test_encoder_attention_tcgen05_two_threads_per_row_variant(cuda_device):
     """RALF_ATTN_TC=2 selects attention_tc2_kernel (256 threads: two threads per query row, key columns split in halves):
     same fp64 bar as the default kernel, and bit-identical to it wherever one half holds all the keys (Tk <= 128: the
@@ -210,7 +209,6 @@ def test_encoder_attention_tcgen05_two_threads_per_row_variant(cuda_device):
     assert not torch.equal(one[(130, 256, 256)], two[(130, 256, 256)])  # (left) + (right) row sums: the other kernel ran
 
 
-@pytest.mark.hw_pending(order=41, optin=True)
 def test_encoder_attention_tcgen05_more_than_256_keys(cuda_device):
     """RALF_ATTN_TC_BIG=1: 256 < Tk <= 480 (the reference's real 350 x 240 canvases give 330 image tokens) on the tensor
     cores with P written in place over S in TMEM; without the switch these shapes take the CUDA-core kernel."""

@@ -145,7 +145,6 @@ def test_train_step_with_dropout_gradient_matches_finite_difference(cuda_device)
     assert abs(float(l_other) - float(loss0)) > 1e-5
 
 
-@pytest.mark.hw_pending(order=1)
 def test_device_mask_equals_cpu_restatement(cuda_device):
     """The mask the kernels derive on the device equals oracle/dropout_oracle.py (itself checked on the CPU against the
     host compilation of the same __host__ __device__ functions, tests/test_dropout_rng_cpu.py)."""

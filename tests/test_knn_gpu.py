@@ -54,13 +54,96 @@ def test_knn_ties_and_duplicates(cuda_device):
     Q[0] = G[7]                # query hits the duplicate cluster
     oi, os_ = oracle_knn.topk(G, Q, 16)
     gi, gs, cert = ops.knn_topk(torch.from_numpy(G).to(cuda_device), torch.from_numpy(Q).to(cuda_device), 16,
-                                gallery_max_norm=1.0001)
+                                gallery_max_norm=1.0001, fixup=False)
     np.testing.assert_array_equal(gi.cpu().numpy(), oi)
     # 41 equal scores straddle the candidate cut, so the TF32 bound cannot certify query 0 ...
     assert cert.cpu().numpy()[0] == 0 and cert.cpu().numpy()[1:].all()
     # ... and the exact kernel is the certified fallback
     ei, es, _ = ops.knn_topk(torch.from_numpy(G).to(cuda_device), torch.from_numpy(Q).to(cuda_device), 16, exact=True)
     np.testing.assert_array_equal(ei.cpu().numpy(), oi)
+
+
+def _near_duplicate_cluster(n, q, seed, width=200, eps=2e-4):
+    """A gallery with `width` near-copies of one row (perturbations far below the TF32 resolution 2^-11, far above
+    fp32's) and queries aimed at it: TF32 scores of the cluster are indistinguishable, so which 32 of them reach the
+    candidate list is arbitrary, while the exact ranking inside the cluster is well defined."""
+    rng = np.random.default_rng(seed)
+    G, Q = _data(n, 512, q, seed)
+    rows = rng.choice(n, width, replace=False)
+    G[rows] = G[rows[0]] + eps * rng.standard_normal((width, 512)).astype(np.float32) / np.sqrt(512)
+    Q[0] = G[rows[0]]
+    if q > 2:
+        Q[q // 2] = G[rows[1]] / np.linalg.norm(G[rows[1]])
+    return G, Q, rows
+
+
+def test_knn_uncertified_queries_are_fixed_on_the_device(cuda_device):
+    """ralf_knn_fixup_exact: near-duplicate cluster wider than the candidate list.  Without the fix-up phase 1/2 returns a
+    wrong top-16 for the cluster queries (and says so: certified == 0); with it (the default, what LayoutPipeline and
+    GpuRetriever use) the result equals the oracle bit for bit, certified == 2 for exactly those queries, no host sync
+    (the call is captured into a CUDA graph and replayed)."""
+    from ralf_b200 import ops
+
+    G, Q, _ = _near_duplicate_cluster(20000, 6, seed=13)
+    oi, os_ = oracle_knn.topk(G, Q, 16)
+    Gd, Qd = torch.from_numpy(G).to(cuda_device), torch.from_numpy(Q).to(cuda_device)
+    ri, rs, rc = ops.knn_topk(Gd, Qd, 16, gallery_max_norm=1.01, fixup=False)
+    rc = rc.cpu().numpy()
+    assert rc[0] == 0 and rc[3] == 0, "the cluster queries must be flagged"
+    bad = [j for j in range(6) if not np.array_equal(ri[j].cpu().numpy(), oi[j])]
+    assert set(bad) <= {0, 3} and all(rc[j] == 0 for j in bad), "a wrong row that is not flagged would be a certificate bug"
+    gi, gs, gc = ops.knn_topk(Gd, Qd, 16, gallery_max_norm=1.01)
+    np.testing.assert_array_equal(gi.cpu().numpy(), oi)
+    np.testing.assert_array_equal(gs.cpu().numpy().view(np.uint32), os_.view(np.uint32))
+    gc = gc.cpu().numpy()
+    assert gc[0] == 2 and gc[3] == 2 and (gc[[1, 2, 4, 5]] == 1).all()
+    # capturable: no host round trip anywhere in the call
+    ws = torch.empty(ops._lib.lib().ralf_knn_workspace_bytes(20000, 512, 6, 16), dtype=torch.uint8, device=cuda_device)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ops.knn_topk(Gd, Qd, 16, gallery_max_norm=1.01, workspace=ws)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        ci, cs, cc = ops.knn_topk(Gd, Qd, 16, gallery_max_norm=1.01, workspace=ws)
+    ci.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(ci.cpu().numpy(), oi)
+    np.testing.assert_array_equal(cs.cpu().numpy().view(np.uint32), os_.view(np.uint32))
+
+
+@pytest.mark.parametrize("n,q", [(100_000, 1), (100_000, 32), (100_000, 128), (1_000_000, 1), (1_000_000, 32),
+                                 (1_000_000, 128)])
+def test_knn_matches_oracle_at_baseline_sizes(cuda_device, n, q):
+    """BASELINE configs[3] sizes (gallery 100 k / 1 M x 512, Q in {1, 32, 128}) against the C oracle: indices and score
+    bits.  Plus the closest available stand-in for FAISS (not installable here, parity unpinned): torch.topk over the
+    fp32 matmul G @ q on the host -- a different summation order, so positions may only differ where the oracle's
+    neighbouring scores are closer than the summation-order error (first-divergence-margin rule)."""
+    from ralf_b200 import ops
+
+    g = torch.Generator().manual_seed(n + q)
+    G = torch.randn(n, 512, generator=g)
+    G /= G.norm(dim=1, keepdim=True)
+    Q = torch.randn(q, 512, generator=g)
+    Q /= Q.norm(dim=1, keepdim=True)
+    oi, os_ = oracle_knn.topk(G.numpy(), Q.numpy(), 16)
+    gi, gs, cert = ops.knn_topk(G.to(cuda_device), Q.to(cuda_device), 16, gallery_max_norm=1.0001)
+    np.testing.assert_array_equal(gi.cpu().numpy(), oi)
+    np.testing.assert_array_equal(gs.cpu().numpy().view(np.uint32), os_.view(np.uint32))
+    assert (cert > 0).all()
+    ts, ti = torch.topk(Q @ G.T, 17, dim=1)  # fp32 BLAS: what IndexFlat's sgemm path computes, another summation order
+    ti, ts = ti.numpy(), ts.numpy()
+    err = 512 * 2.0 ** -24  # |sum-order error| of a 512-term fp32 dot of unit vectors (loose bound)
+    for j in range(q):
+        for r in range(16):
+            if ti[j, r] != oi[j, r]:
+                gap = min(abs(os_[j, r] - os_[j, r - 1]) if r else 1.0, abs(os_[j, r] - os_[j, r + 1]) if r < 15 else
+                          abs(os_[j, 15] - ts[j, 16]))
+                assert gap <= 2 * err, f"query {j} rank {r}: BLAS ranking differs with a score gap of {gap}"
+        np.testing.assert_allclose(ts[j, :16], os_[j], rtol=0, atol=2 * err)
 
 
 def test_knn_sharded_merge_equals_unsharded(cuda_device):
@@ -114,7 +197,6 @@ def test_knn_adversarial_row_order(cuda_device):
         assert cert.cpu().numpy().all()
 
 
-@pytest.mark.hw_pending(order=3)
 def test_flat_ip_index_as_hf_custom_index(cuda_device, monkeypatch):
     """FlatIPIndex behind HF datasets' FaissIndex (``custom_index=``), the reference's own route to FAISS
     (retrieval/retriever.py:79-84,200-202): neighbours and scores bit-exact against the C oracle, host arrays in/out."""
@@ -144,7 +226,6 @@ def test_flat_ip_index_as_hf_custom_index(cuda_device, monkeypatch):
     np.testing.assert_array_equal(index.reconstruct(123), G[123])
 
 
-@pytest.mark.hw_pending(order=30, optin=True)
 def test_knn_passes_on_parallel_streams_equal_single_stream(cuda_device):
     """GpuRetriever.knn_ways > 1 (passes of 128 queries round-robin on parallel streams) returns what the single-stream
     call returns, eagerly and as parallel branches of a captured graph."""

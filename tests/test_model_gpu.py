@@ -103,7 +103,6 @@ def test_engine_batch_matches_oracle_with_margin(cuda_device):
         assert margin < LOGIT_RTOL, f"canvas {b} diverges at step {t} with oracle margin {margin:.3e}"
 
 
-@pytest.mark.hw_pending(order=2)
 def test_engine_matches_reference_golden_pku(cuda_device):
     """BASELINE configs[2] names PKU (3 labels, vocabulary 518): memory within tolerance of the reference's own output;
     token ids equal, a divergence tolerated only where the oracle's top-2 margin at that step is below the logit
@@ -140,7 +139,6 @@ def test_engine_matches_reference_golden_pku(cuda_device):
             assert margin < LOGIT_RTOL, f"canvas {b} diverges at step {t} with oracle margin {margin:.3e}"
 
 
-@pytest.mark.hw_pending(order=5)
 def test_engine_matches_oracle_at_the_bench_shape_e12(cuda_device):
     """The bench decodes max_seq_length = 12 (60 tokens), one element more than the reference can be built with (its
     constraint vocabulary has 11 element letters), so this shape is pinned to the oracle: memory within tolerance,
@@ -179,7 +177,6 @@ def test_engine_matches_oracle_at_the_bench_shape_e12(cuda_device):
         assert margin < LOGIT_RTOL, f"canvas {b} diverges at step {t} with oracle margin {margin:.3e}"
 
 
-@pytest.mark.hw_pending(order=4)
 def test_engine_matches_reference_golden_at_maximum_length(cuda_device):
     """max_seq_length = 11 (the reference's upper limit, 55 tokens), every canvas and exemplar full: memory and
     teacher-forced logits within tolerance of the reference's own output, greedy tokens equal (first-divergence rule)."""

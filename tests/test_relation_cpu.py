@@ -395,6 +395,9 @@ class _OracleEngine:
         tokens = kc[0][:, :t + 1, 0].round().long()
         return self._logits(tokens, kvm[0].view(B, Mlen, -1), pad_mask[:, :t + 1].bool())
 
+    def generate_graphed(self, mem_s, B, Mlen, token_mask, bos_id, pad_id, steps):
+        return self.generate(mem_s, B, Mlen, token_mask, bos_id, pad_id, steps)  # no graphs on the CPU: same loop
+
     def generate(self, mem_s, B, Mlen, token_mask, bos_id, pad_id, steps, forced=None, sampling=None, rng=None, **kw):
         assert (sampling or {}).get("name", "deterministic") == "deterministic"
         seq = torch.full((B, 1), bos_id)

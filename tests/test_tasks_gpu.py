@@ -175,7 +175,6 @@ def _relation_setup(dev):
     return model.eval().to(dev), tok, batch, z, meta
 
 
-@pytest.mark.hw_pending(order=10, optin=True)
 def test_decode_session_rewinds_match_oracle(cuda_device):
     """DecodeSession (KV cache kept across rewinds) against the cache-free oracle decoder on the prefixes the reference's
     backtracking sampler actually visited, rewinds included."""
@@ -211,7 +210,6 @@ def test_decode_session_rewinds_match_oracle(cuda_device):
     assert checked >= 3 * B
 
 
-@pytest.mark.hw_pending(order=11, optin=True)
 @pytest.mark.parametrize("mode", ["deterministic", "random"])
 def test_relation_backtracking_matches_reference_golden(cuda_device, mode):
     """model.sample(cond_type="relation") end to end under the recorded seeds: decoded layouts and the violation count of
@@ -234,7 +232,6 @@ def test_relation_backtracking_matches_reference_golden(cuda_device, mode):
     assert [vio["total"], vio["viorated"]] == z[p + "violation"].tolist()
 
 
-@pytest.mark.hw_pending(order=12)
 def test_relation_without_backtracking_matches_reference_golden(cuda_device):
     """use_backtrack=False: the batched device decode under the label restriction (:244-300), relations scored afterwards."""
     import random

@@ -148,7 +148,6 @@ def test_training_gradients_match_oracle(cuda_device, train_trunk):
     assert med_ours <= 2e-3 and med_ours <= max(4 * med_t32, 2e-4)
 
 
-@pytest.mark.hw_pending(order=20, optin=True)
 def test_autoreg_baseline_training_gradients_match_oracle(cuda_device):
     """The Autoreg baseline class (BASELINE configs[0]'s model; configs/autoreg_*/*.sh train it) through the same tape:
     loss and every parameter gradient vs the float64 oracle, bar as in test_training_gradients_match_oracle; then two
