@@ -283,8 +283,9 @@ int ralf_axpy(float* a, const float* b, float alpha, long long total, void* stre
 /* dst[r,:] (+)= scale * src[map(r),:] -- backward of ralf_rows_affine / concatenations. */
 int ralf_rows_gather(const float* src, long long src_ld, int M, int D, float scale, int rows_per_group,
                      int group_stride, int group_offset, float* dst, int accumulate, void* stream);
+/* V = rows of the embedding table.  Deterministic (gather per vocabulary row, no atomics). */
 int ralf_embed_bwd(const long long* tok, long long tok_ld, int tok_col, int B, int S, const float* dy, int D,
-                   float scale, float* demb, void* stream);
+                   float scale, float* demb, int V, void* stream);
 /* torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW over flat buffers (train.py:450-454). */
 int ralf_grad_norm(const float* grads, long long n, float* workspace /* 1024 floats */, float* out_norm, void* stream);
 int ralf_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
@@ -308,8 +309,10 @@ int ralf_bn_bwd_apply(const float* dy, const float* z, const float* mean, const 
 /* Backward data movement of the convolutions / pooling / FPN upsample. */
 int ralf_col2im(const float* dcol, int B, int H, int W, int C, int KH, int KW, int stride, int pad, float* dx,
                 int accumulate, void* stream);
+/* Deterministic (first-maximum tap recorded per output in `workspace`, B*Ho*Wo*C bytes; gather per input pixel); dx is
+ * written completely. */
 int ralf_maxpool3x3s2_bwd(const void* x_split, long long x_plane, const float* dy, int B, int H, int W, int C,
-                          float* dx_zeroed, void* stream);
+                          float* dx, void* workspace, void* stream);
 int ralf_upsample_nearest_bwd(const float* dbig, long long ld_big, int B, int h5, int w5, int h4, int w4, int C,
                               float* dsmall, void* stream);
 /* nn.Conv2d weight [N, C, T] <-> GEMM layout [N, T*C] (split, plus transposed copy) and gradient back. */

@@ -111,7 +111,7 @@ def lib() -> C.CDLL:
         L.ralf_gelu_bwd.argtypes = [vp, vp, ll, vp]
         L.ralf_axpy.argtypes = [vp, vp, f, ll, vp]
         L.ralf_rows_gather.argtypes = [vp, ll, i, i, f, i, i, i, vp, i, vp]
-        L.ralf_embed_bwd.argtypes = [vp, ll, i, i, i, vp, i, f, vp, vp]
+        L.ralf_embed_bwd.argtypes = [vp, ll, i, i, i, vp, i, f, vp, i, vp]
         L.ralf_grad_norm.argtypes = [vp, ll, vp, vp, vp]
         L.ralf_adamw_step.argtypes = [vp, vp, vp, vp, ll, vp, f, f, f, f, f, f, i, vp]
         L.ralf_adamw_step_dyn.argtypes = [vp, vp, vp, vp, ll, vp, f, f, f, f, f, f, vp, vp]
@@ -119,7 +119,7 @@ def lib() -> C.CDLL:
         L.ralf_bn_apply.argtypes = [vp, vp, vp, vp, vp, vp, ll, i, i, i, vp, ll, vp, vp]
         L.ralf_bn_bwd_apply.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, vp, vp]
         L.ralf_col2im.argtypes = [vp, i, i, i, i, i, i, i, i, vp, i, vp]
-        L.ralf_maxpool3x3s2_bwd.argtypes = [vp, ll, vp, i, i, i, i, vp, vp]
+        L.ralf_maxpool3x3s2_bwd.argtypes = [vp, ll, vp, i, i, i, i, vp, vp, vp]
         L.ralf_upsample_nearest_bwd.argtypes = [vp, ll, i, i, i, i, i, i, vp, vp]
         L.ralf_conv_weight_to_gemm.argtypes = [vp, i, i, i, i, vp, ll, vp, ll, i, vp]
         L.ralf_conv_grad_from_gemm.argtypes = [vp, i, i, i, i, vp, vp]

@@ -368,7 +368,7 @@ def embed(tape: Tape, ps: ParamStore, tok: torch.Tensor, S: int, emb_name: str, 
         if y.grad is None:
             return
         check(_L().ralf_embed_bwd(tok.data_ptr(), tok.stride(0), 0, tok.shape[0], S, y.grad.data_ptr(), emb.shape[1], scale,
-                                  ps.g(emb_name).data_ptr(), _stream()), "ralf_embed_bwd")
+                                  ps.g(emb_name).data_ptr(), emb.shape[0], _stream()), "ralf_embed_bwd")
         y.grad = None
 
     tape.record(bwd)

@@ -149,9 +149,11 @@ __global__ void col2im_kernel(const float* __restrict__ dcol, int B, int H, int 
   }
 }
 
-// max-pool 3x3/s2/p1 backward (scatter, first maximum wins like torch): dx must be zero-initialised.
-__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long x_plane, const float* __restrict__ dy,
-                                   int B, int H, int W, int C, int Ho, int Wo, float* __restrict__ dx) {
+// max-pool 3x3/s2/p1 backward, deterministic (no atomics): (1) per output element the tap (kh*3+kw) of its FIRST maximum --
+// torch's rule -- as a byte; (2) gather: every input pixel sums dy over the <= 4 windows whose recorded tap points at it, in a
+// fixed order.  dx is written completely (no zero-initialisation needed).
+__global__ void maxpool_bwd_arg_kernel(const __nv_bfloat16* __restrict__ x, long long x_plane, int B, int H, int W, int C,
+                                       int Ho, int Wo, uint8_t* __restrict__ tap) {
   const long long total = static_cast<long long>(B) * Ho * Wo * C;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -161,7 +163,7 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, long lon
     const int oy = static_cast<int>((pix / Wo) % Ho);
     const int b = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
     float best = -INFINITY;
-    long long arg = -1;
+    int arg = 255;
     for (int kh = 0; kh < 3; ++kh) {
       const int iy = oy * 2 - 1 + kh;
       if (iy < 0 || iy >= H) continue;
@@ -170,10 +172,38 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, long lon
         if (ix < 0 || ix >= W) continue;
         const long long src = ((static_cast<long long>(b) * H + iy) * W + ix) * C + c;
         const float v = c_load_split(x, x_plane, src);
-        if (v > best) { best = v; arg = src; }
+        if (v > best) { best = v; arg = kh * 3 + kw; }
       }
     }
-    if (arg >= 0) atomicAdd(&dx[arg], dy[i]);
+    tap[i] = static_cast<uint8_t>(arg);
+  }
+}
+__global__ void maxpool_bwd_gather_kernel(const uint8_t* __restrict__ tap, const float* __restrict__ dy, int B, int H, int W,
+                                          int C, int Ho, int Wo, float* __restrict__ dx) {
+  const long long total = static_cast<long long>(B) * H * W * C;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const long long pix = i / C;
+    const int ix = static_cast<int>(pix % W);
+    const int iy = static_cast<int>((pix / W) % H);
+    const int b = static_cast<int>(pix / (static_cast<long long>(W) * H));
+    float acc = 0.f;
+    for (int kh = 0; kh < 3; ++kh) {  // iy = 2*oy - 1 + kh
+      const int ty = iy + 1 - kh;
+      if (ty < 0 || (ty & 1)) continue;
+      const int oy = ty >> 1;
+      if (oy >= Ho) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        const int tx = ix + 1 - kw;
+        if (tx < 0 || (tx & 1)) continue;
+        const int ox = tx >> 1;
+        if (ox >= Wo) continue;
+        const long long o = ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * C + c;
+        if (tap[o] == kh * 3 + kw) acc += dy[o];
+      }
+    }
+    dx[i] = acc;
   }
 }
 
@@ -293,12 +323,15 @@ extern "C" int ralf_col2im(const float* dcol, int B, int H, int W, int C, int KH
 }
 
 extern "C" int ralf_maxpool3x3s2_bwd(const void* x_split, long long x_plane, const float* dy, int B, int H, int W, int C,
-                                     float* dx_zeroed, void* stream) {
-  if (!x_split || !dy || !dx_zeroed) return RALF_ERR_NULL;
+                                     float* dx, void* workspace /* B*Ho*Wo*C bytes */, void* stream) {
+  if (!x_split || !dy || !dx || !workspace) return RALF_ERR_NULL;
   if (B <= 0 || H <= 0 || W <= 0 || C <= 0) return RALF_ERR_SHAPE;
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long long total = static_cast<long long>(B) * Ho * Wo * C;
-  maxpool_bwd_kernel<<<c_grid_for(total, 256), 256, 0, ST(stream)>>>(CBF(x_split), x_plane, dy, B, H, W, C, Ho, Wo, dx_zeroed);
+  uint8_t* tap = reinterpret_cast<uint8_t*>(workspace);
+  maxpool_bwd_arg_kernel<<<c_grid_for(total, 256), 256, 0, ST(stream)>>>(CBF(x_split), x_plane, B, H, W, C, Ho, Wo, tap);
+  maxpool_bwd_gather_kernel<<<c_grid_for(static_cast<long long>(B) * H * W * C, 256), 256, 0, ST(stream)>>>(tap, dy, B, H, W, C,
+                                                                                                           Ho, Wo, dx);
   return set_cuda_error(cudaGetLastError());
 }
 

@@ -87,13 +87,11 @@ __global__ void colsum_kernel(const float* __restrict__ in, long long ld, int M,
 __global__ void ln_bwd_kernel(const float* __restrict__ x, long long x_ld, const float* __restrict__ dy,
                               const float* __restrict__ gamma, float eps, int M, int D, const float* __restrict__ add_to,
                               float* __restrict__ dx, float* __restrict__ part) {
-  extern __shared__ float sh[];  // [2][D] block partials
-  float* sg = sh;
-  float* sb = sh + D;
-  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
+  extern __shared__ float sh[];  // [warps][2][D] per-warp partials (deterministic: no atomics, fixed reduction order)
   const int warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per = D >> 5;
+  float pg[32], pb[32];
+  for (int i = 0; i < per; ++i) { pg[i] = 0.f; pb[i] = 0.f; }
   for (int row = blockIdx.x * warps + wid; row < M; row += gridDim.x * warps) {
     const float* xr = x + static_cast<long long>(row) * x_ld;
     const float* dyr = dy + static_cast<long long>(row) * D;
@@ -109,8 +107,8 @@ __global__ void ln_bwd_kernel(const float* __restrict__ x, long long x_ld, const
       const int c = lane + 32 * i;
       const float xh = (xv[i] - mean) * rstd;
       const float d = dyr[c];
-      atomicAdd(&sg[c], d * xh);
-      atomicAdd(&sb[c], d);
+      pg[i] += d * xh;
+      pb[i] += d;
       gv[i] = d * gamma[c];
       xv[i] = xh;
       s1 += gv[i];
@@ -126,8 +124,16 @@ __global__ void ln_bwd_kernel(const float* __restrict__ x, long long x_ld, const
       dx[off] = v;
     }
   }
+  for (int i = 0; i < per; ++i) {
+    sh[(wid * 2 + 0) * D + lane + 32 * i] = pg[i];
+    sh[(wid * 2 + 1) * D + lane + 32 * i] = pb[i];
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) part[static_cast<long long>(blockIdx.x) * 2 * D + i] = sh[i];
+  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < warps; ++w) s += sh[w * 2 * D + i];
+    part[static_cast<long long>(blockIdx.x) * 2 * D + i] = s;
+  }
 }
 __global__ void ln_bwd_reduce_kernel(const float* __restrict__ part, int nblocks, int D, float* __restrict__ dgamma,
                                      float* __restrict__ dbeta) {
@@ -480,16 +486,22 @@ __global__ void rows_gather_kernel(const float* __restrict__ src, long long src_
     dst[i] = accumulate ? dst[i] + v : v;
   }
 }
-// Embedding backward: demb[tok[r], :] += scale * dy[r, :]   (atomic scatter-add)
+// Embedding backward: demb[tok[r], :] += scale * dy[r, :].  Deterministic gather form (no atomics): one block per vocabulary
+// row t, thread per column; the block walks the B*S token ids (broadcast loads) and accumulates the matching dy rows in order.
 __global__ void embed_bwd_kernel(const long long* __restrict__ tok, long long tok_ld, int tok_col, int Bn, int S,
                                  const float* __restrict__ dy, int D, float scale, float* __restrict__ demb) {
-  const long long total = static_cast<long long>(Bn) * S * D;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % D);
-    const long long r = i / D;
-    const long long t = tok[(r / S) * tok_ld + tok_col + (r % S)];
-    atomicAdd(&demb[t * D + c], scale * dy[i]);
+  const long long t = blockIdx.x;
+  const int rows = Bn * S;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float acc = 0.f;
+    bool any = false;
+    for (int r = 0; r < rows; ++r) {
+      if (tok[(r / S) * tok_ld + tok_col + (r % S)] == t) {
+        acc += dy[static_cast<long long>(r) * D + c];
+        any = true;
+      }
+    }
+    if (any) demb[t * D + c] += scale * acc;
   }
 }
 
@@ -539,7 +551,7 @@ extern "C" int ralf_layernorm_bwd(const float* x, long long x_ld, const float* d
   int nblocks = (M + 7) / 8;
   const int cap = num_sms() * 4;
   if (nblocks > cap) nblocks = cap;
-  ln_bwd_kernel<<<nblocks, 256, 2 * D * sizeof(float), ST(stream)>>>(x, x_ld, dy, gamma, eps, M, D, add_to, dx, workspace);
+  ln_bwd_kernel<<<nblocks, 256, 8 * 2 * D * sizeof(float), ST(stream)>>>(x, x_ld, dy, gamma, eps, M, D, add_to, dx, workspace);
   ln_bwd_reduce_kernel<<<(2 * D + 255) / 256, 256, 0, ST(stream)>>>(workspace, nblocks, D, dgamma, dbeta);
   return set_cuda_error(cudaGetLastError());
 }
@@ -718,10 +730,9 @@ extern "C" int ralf_rows_gather(const float* src, long long src_ld, int M, int D
   return set_cuda_error(cudaGetLastError());
 }
 extern "C" int ralf_embed_bwd(const long long* tok, long long tok_ld, int tok_col, int B, int S, const float* dy, int D,
-                              float scale, float* demb, void* stream) {
+                              float scale, float* demb, int V, void* stream) {
   if (!tok || !dy || !demb) return RALF_ERR_NULL;
-  if (B <= 0 || S <= 0 || D <= 0) return RALF_ERR_SHAPE;
-  embed_bwd_kernel<<<t_grid_for(static_cast<long long>(B) * S * D, 256), 256, 0, ST(stream)>>>(tok, tok_ld, tok_col, B, S, dy,
-                                                                                             D, scale, demb);
+  if (B <= 0 || S <= 0 || D <= 0 || V <= 0) return RALF_ERR_SHAPE;
+  embed_bwd_kernel<<<V, D < 256 ? D : 256, 0, ST(stream)>>>(tok, tok_ld, tok_col, B, S, dy, D, scale, demb);
   return set_cuda_error(cudaGetLastError());
 }

@@ -183,9 +183,10 @@ class Trunk:
         def pool_bwd() -> None:
             if pool.grad is None:
                 return
-            dx = torch.zeros((M, 64), dtype=torch.float32, device=dev)
+            dx = torch.empty((M, 64), dtype=torch.float32, device=dev)
+            taps = torch.empty(pool.grad.numel(), dtype=torch.uint8, device=dev)
             check(_L().ralf_maxpool3x3s2_bwd(s0.data_ptr(), s0.stride(0), pool.grad.data_ptr(), B, H, W, 64, dx.data_ptr(),
-                                             _stream()), "ralf_maxpool3x3s2_bwd")
+                                             taps.data_ptr(), _stream()), "ralf_maxpool3x3s2_bwd")
             ag.accumulate(stem, dx)
             pool.grad = None
 

@@ -239,8 +239,10 @@ def test_pool_upsample_embed_backward(cuda_device):
     yt = F.max_pool2d(xq, 3, 2, 1)
     dy = torch.randn(yt.shape, generator=g).to(cuda_device)
     yt.backward(dy)
-    dx = torch.zeros(B * H * W, C, device=cuda_device)
-    check(_L().ralf_maxpool3x3s2_bwd(xs.data_ptr(), xs.stride(0), nhwc(dy).data_ptr(), B, H, W, C, dx.data_ptr(), _stream()), "mp")
+    dx = torch.full((B * H * W, C), float("nan"), device=cuda_device)  # written completely: no zero-initialisation needed
+    taps = torch.empty(dy.numel(), dtype=torch.uint8, device=cuda_device)
+    check(_L().ralf_maxpool3x3s2_bwd(xs.data_ptr(), xs.stride(0), nhwc(dy).data_ptr(), B, H, W, C, dx.data_ptr(),
+                                     taps.data_ptr(), _stream()), "mp")
     assert _rel(dx, nhwc(xq.grad)) < 1e-5
     # nearest upsample backward (11x8 -> 22x15 like the 350x240 canvas, and 8x8 -> 16x16)
     for (h5, w5, h4, w4) in [(11, 8, 22, 15), (8, 8, 16, 16)]:

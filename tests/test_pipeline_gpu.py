@@ -198,6 +198,34 @@ def test_bench_shape_batch_invariance_and_token_validity(cuda_device):
         np.testing.assert_array_equal(seq[b0:b0 + 64].numpy(), ref["seq"].numpy(), err_msg=f"chunk at {b0}")
 
 
+def test_pipeline_retrieval_is_exact_on_near_duplicate_clusters(cuda_device):
+    """The product path (LayoutPipeline's captured search graph) returns the oracle's top-16 even where the TF32 bound
+    cannot certify (200 near-copies of one gallery row, queries aimed at them): the exact fix-up runs inside the graph,
+    and last_certified shows it did (2 for the cluster queries, 1 elsewhere)."""
+    from ralf_b200.pipeline import LayoutPipeline
+    from ralf_b200.retrieval import GpuRetriever
+    from tests.test_knn_gpu import _near_duplicate_cluster
+
+    n, B, E = 20000, 4, 10
+    G, Q, _ = _near_duplicate_cluster(n, B, seed=31)
+    gl = torch.Generator().manual_seed(6)
+    cnt = torch.randint(1, E + 1, (n,), generator=gl)
+    mask = torch.arange(E)[None] < cnt[:, None]
+    lay = {"mask": mask, "label": torch.randint(0, 4, (n, E), generator=gl) * mask}
+    for k in ["center_x", "center_y", "width", "height"]:
+        lay[k] = torch.rand(n, E, generator=gl) * mask
+    model = _model(cuda_device, seed=2)
+    retr = GpuRetriever(torch.from_numpy(G), lay, device=cuda_device)
+    pipe = LayoutPipeline(model, retr, B, 64, 64)
+    img = torch.rand(B, 4, 64, 64, generator=gl)
+    oi, _ = oracle_knn.topk(G, Q, 16)
+    for _ in range(2):  # replayed graph
+        out = pipe.generate_layouts(img, torch.from_numpy(Q))
+        np.testing.assert_array_equal(out["retrieved_idx"].numpy(), oi)
+    cert = retr.last_certified.cpu().numpy()
+    assert cert[0] == 2 and cert[2] == 2 and cert[1] == 1 and cert[3] == 1, cert
+
+
 def test_model_sample_with_cached_decode_graph_equals_eager(cuda_device, monkeypatch):
     """RALF_SAMPLE_GRAPH=1: model.sample()'s greedy decode loop replayed from a per-shape CUDA graph gives the eager loop's
     tokens, call after call (fresh inputs into the static K/V cache) and across shapes (one graph per shape)."""
