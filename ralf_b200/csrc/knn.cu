@@ -137,6 +137,8 @@ template <int C>
 __device__ __forceinline__ void knn_compact_round(uint64_t* lists, const int lane, int& cnt, float& thr, int& sorted,
                                                   const int min_len) {
   using Cfg = KnnCfg<C>;
+  __syncwarp();  // the owners' appends (plain shared-memory stores) must be visible to the lanes that sort their lists
+                 // (compute-sanitizer racecheck flagged the read below against the append in knn_scan_kernel)
 #pragma unroll 1
   for (int ql = 0; ql < 32; ++ql) {
     const int n = __shfl_sync(0xffffffffu, cnt, ql);

@@ -105,7 +105,75 @@ class TrainEngine:
         self._seed_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self._slot_done: list = [None] * 64  # event after the async copies out of ring slot i: waited on before rewriting it
         self._graph = None
+        self._buckets = self._grad_buckets()
+        self._bucket_done: set = set()
+        self._comm_stream = torch.cuda.Stream(device=self.dev) if (world_size > 1 and self.dev.type == "cuda") else None
+        self.overlap_comm = True   # False: one blocking all-reduce of the flat buffer after the backward (A/B, bench)
+        self.skip_comm = False     # bench only: time the step without its all-reduce
         self.refresh_operands()
+
+    # ------------------------------------------------------------------------------------------
+    # data-parallel gradient all-reduce, bucketed in backward-completion order and overlapped with the rest of the
+    # backward (decoder / encoders / FPN -> ResNet layer4 -> layer3 -> layer2 -> layer1 + stem); the
+    # reference's DDPWrapper was meant to do this through torch's reducer (helpers/distrubuted.py:10-31).
+    # ------------------------------------------------------------------------------------------
+    def _grad_buckets(self) -> dict:
+        """tag -> [(lo, hi)] element ranges of the flat gradient buffer.  Parameters are laid out group by group (body
+        decay | body no-decay | rest decay | rest no-decay), names sorted inside a group, so every bucket is at most two
+        contiguous ranges."""
+        ps = self.ps
+        body = "encoder.extractor.body."
+
+        def ranges(pred):
+            out = []
+            for n, (off, cnt, _) in ps.offsets.items():  # insertion order = buffer order
+                if not pred(n):
+                    continue
+                end = off + (cnt + 3) // 4 * 4
+                if out and out[-1][1] == off:
+                    out[-1][1] = end
+                else:
+                    out.append([off, end])
+            return [tuple(r) for r in out]
+
+        b = {"rest": ranges(lambda n: not n.startswith(body))}
+        for li in (4, 3, 2):
+            b[f"layer{li}"] = ranges(lambda n, li=li: n.startswith(f"{body}layer{li}."))
+        b["tail"] = ranges(lambda n: n.startswith(body) and not any(n.startswith(f"{body}layer{li}.") for li in (2, 3, 4)))
+        return {k: v for k, v in b.items() if v}
+
+    def _allreduce_ranges(self, rs) -> None:
+        import torch.distributed as dist
+
+        for lo, hi in rs:
+            dist.all_reduce(self.ps.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+
+    def _mark(self, tag: str) -> None:
+        """Backward reached the point where bucket ``tag`` is complete: all-reduce it on the communication stream."""
+        if self.world <= 1 or self.skip_comm or not self.overlap_comm or tag in self._bucket_done or tag not in self._buckets:
+            return
+        self._bucket_done.add(tag)
+        cur = torch.cuda.current_stream()
+        self._comm_stream.wait_stream(cur)  # the bucket's gradients are produced on the compute stream
+        with torch.cuda.stream(self._comm_stream):
+            self._allreduce_ranges(self._buckets[tag])
+
+    def _finish_allreduce(self) -> None:
+        """After the backward: reduce whatever no marker has sent yet, join the communication stream, average."""
+        if self.world <= 1 or self.skip_comm:
+            return
+        ps = self.ps
+        if not self.overlap_comm:
+            self._allreduce_ranges([(0, ps.total)])
+        else:
+            cur = torch.cuda.current_stream()
+            rest = [r for tag, rs in self._buckets.items() if tag not in self._bucket_done for r in rs]
+            self._comm_stream.wait_stream(cur)
+            with torch.cuda.stream(self._comm_stream):
+                self._allreduce_ranges(rest)
+            cur.wait_stream(self._comm_stream)
+            self._bucket_done.clear()
+        ps.flat_g.mul_(1.0 / self.world)
 
     def refresh_operands(self) -> None:
         self.ps.refresh_operands()
@@ -180,7 +248,7 @@ class TrainEngine:
         K = self.model.top_k
         # ---- ResNet50-FPN trunk: on the tape (BatchNorm batch statistics), or frozen through the inference kernels ----
         if self.trunk is not None:
-            x, h, w = self.trunk.forward(tape, image, self.infer.pos2d)
+            x, h, w = self.trunk.forward(tape, image, self.infer.pos2d, mark=self._mark)
         else:
             tokens, h, w = self.infer.resnet_fpn(image)
             x = Node(B * h * w, D, tokens, None, need_grad=False)
@@ -302,11 +370,7 @@ class TrainEngine:
 
     def _publish_grads(self, scale: Optional[torch.Tensor]) -> None:
         ps = self.ps
-        if self.world > 1:
-            import torch.distributed as dist
-
-            dist.all_reduce(ps.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
-            ps.flat_g.mul_(1.0 / self.world)
+        self._finish_allreduce()
         if scale is not None:
             ps.flat_g.mul_(scale)
         for n, p in self._named:
@@ -387,11 +451,7 @@ class TrainEngine:
         ps.flat_g.zero_()
         loss, tape, _ = self.forward_loss(inputs, targets)
         tape.backward()
-        if self.world > 1:
-            import torch.distributed as dist
-
-            dist.all_reduce(ps.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
-            ps.flat_g.mul_(1.0 / self.world)
+        self._finish_allreduce()
         norm = ag.grad_norm(ps.flat_g)
         ag.adamw_step(ps, self.group_cfg, 0, self.max_norm, norm, dyn=self._dyn)
         self.refresh_operands()

@@ -143,9 +143,14 @@ class Trunk:
             x.grad = dx
 
     # ---- whole trunk ---------------------------------------------------------------------------
-    def forward(self, tape: Tape, image: torch.Tensor, pos2d_fn) -> tuple[Node, int, int]:
-        """image fp32 [B,4,H,W] -> tokens Node (fp32 [B*h*w, 256], 2-D sine PE added), h, w."""
+    def forward(self, tape: Tape, image: torch.Tensor, pos2d_fn, mark=None) -> tuple[Node, int, int]:
+        """image fp32 [B,4,H,W] -> tokens Node (fp32 [B*h*w, 256], 2-D sine PE added), h, w.
+        ``mark(tag)``: called DURING BACKWARD when the gradients of a parameter bucket are complete ("rest": everything
+        outside the ResNet body, i.e. when the body's backward is about to start; "layer4" / "layer3" / "layer2": that
+        stage's parameters) -- the data-parallel trainer starts the bucket's all-reduce there, under the remaining backward."""
         ps, dev = self.ps, self.dev
+        if mark is None:
+            mark = lambda tag: None
         B = image.shape[0]
         col0, H, W = ops.stem_im2col(image.contiguous())
         stem_name = BODY + ".conv1"
@@ -205,6 +210,9 @@ class Trunk:
                     idt = x
                 x, geom = self.conv_bn(tape, t2, g2, p + ".conv3", p + ".bn3", 1, 1, 0, True, res=idt)
             feats[li] = (x, geom)
+            if li < 4:  # backward reaches this point when stage li+1 is done
+                tape.record(lambda tag=f"layer{li + 1}": mark(tag))
+        tape.record(lambda: mark("rest"))  # backward: FPN + everything downstream is done, the body's backward starts
         # ---- FPN (image.py:99-111) ----
         (l3, (_, h4, w4)), (l4, (_, h5, w5)) = feats[3], feats[4]
         c4 = ag.linear(tape, ps, l3, EXT + ".fpn_conv11_4", EXT + ".fpn_conv11_4.bias")
