@@ -155,7 +155,7 @@ def encode_image(sd, image):
     """encoder -> pos_emb_2d -> transformer_encoder (retrieval_augmented_autoreg.py:967-971)."""
     f = resnet_fpn(sd, image)
     B, C, h, w = f.shape
-    x = f.flatten(2).transpose(1, 2) + pos_emb_2d(h, w, C)[None]
+    x = f.flatten(2).transpose(1, 2) + pos_emb_2d(h, w, C)[None].to(f.device)
     for i in range(NUM_LAYERS):
         x = _enc_layer_prenorm(sd, f"transformer_encoder.layers.{i}", x)
     return x
@@ -171,7 +171,7 @@ def fidnet_features(sd, lay, p="layout_encoer"):
     x = torch.relu(_lin(sd, p + ".enc_fc_in", h))
     N = x.shape[0]
     x = torch.cat([sd[p + ".enc_transformer.token"].reshape(1, 1, -1).expand(N, 1, -1), x], dim=1)
-    pad = torch.cat([torch.zeros(N, 1, dtype=torch.bool), ~lay["mask"].bool()], dim=1)
+    pad = torch.cat([torch.zeros(N, 1, dtype=torch.bool, device=x.device), ~lay["mask"].bool()], dim=1)
     for i in range(4):
         x = _enc_layer_postnorm(sd, f"{p}.enc_transformer.core.layers.{i}", x, 4, key_padding_mask=pad)
     return x[:, 0]
@@ -241,7 +241,7 @@ def decoder_logits(sd, tgt, memory, tgt_key_padding_mask, p="decoder"):
     """BaseDecoder.forward with is_causal=True (common/common.py:84-135)."""
     h = _pe1d(sd, p + ".pos_emb", sd[p + ".emb.weight"][tgt])
     S = h.shape[1]
-    causal = torch.triu(torch.full((S, S), float("-inf")), diagonal=1)
+    causal = torch.triu(torch.full((S, S), float("-inf"), device=h.device, dtype=h.dtype), diagonal=1)
     for i in range(NUM_LAYERS):
         h = _dec_layer_prenorm(sd, f"{p}.transformer.layers.{i}", h, memory, causal, tgt_key_padding_mask)
     return F.linear(_ln(sd, p + ".head.0", h), sd[p + ".head.1.weight"])
@@ -251,7 +251,7 @@ def greedy_sample(sd, memory, token_mask, bos_id, pad_id, max_token_length, retu
     """BaseRetrievalAugmentedAutoreg.sample greedy loop, cond_type uncond
     (retrieval_augmented_autoreg.py:244-300; helpers/sampling.py:24-25).  Returns seq without BOS."""
     B = memory.shape[0]
-    inp = torch.full((B, 1), bos_id, dtype=torch.long)
+    inp = torch.full((B, 1), bos_id, dtype=torch.long, device=memory.device)
     step_logits = []
     for i in range(max_token_length):
         logits = decoder_logits(sd, inp, memory, inp == pad_id)[:, i].clone()
