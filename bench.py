@@ -9,7 +9,7 @@ One "step" = one batch of synthetic canvases through the whole path, per GPU:
 Workload (BASELINE.json configs[4]: batched inference of 1024 canvases, which fits one GPU; per-GPU work is fixed as
 N grows, so scaling is weak): 1024 canvases/GPU/step, 256x256x4 synthetic canvases, k = 16, gallery 1M x 512 fp32
 sharded over the ranks, E = 12 elements -> S = 60 tokens (<= 64).  Inside a step retrieval runs in passes of 128
-queries (each pass streams the gallery shard once), the encoder in micro-batches of 128 canvases, the KV-cached decode
+queries (each pass streams the gallery shard once), the encoder in micro-batches of 256 canvases, the KV-cached decode
 loop over all 1024 canvases at once.
 Random-init weights of the reference architecture (no checkpoints offline), synthetic data.
 
@@ -44,7 +44,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="canvases per GPU per step")
-    ap.add_argument("--micro-batch", type=int, default=128, help="canvases per encoder pass inside a step")
+    ap.add_argument("--micro-batch", type=int, default=256, help="canvases per encoder pass inside a step "
+                    "(256: measured 182.4 vs 187.2 ms/step at 128, profiles/r2_ab_call1.md)")
     ap.add_argument("--gallery", type=int, default=1_000_000, help="total gallery rows (sharded over ranks)")
     ap.add_argument("--hw", type=int, default=256)
     ap.add_argument("--elems", type=int, default=12)

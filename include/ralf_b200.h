@@ -142,6 +142,40 @@ int ralf_stem_gemm(const RalfGemmArgs* args, int B, int Ho, int Wo, void* stream
 int ralf_gemm_ln(const float* x, int ldx, const float* gamma, const float* beta, float eps,
                  const RalfGemmArgs* args, void* stream);
 
+/* Fused decode-step chain (csrc/decode_chain.cu): up to 4 row-local stages
+ *     [LayerNorm | split rows from global | previous stage's output]  ->  Linear (W split bf16 [2, n_out, k_in], bf16x3)
+ *     -> + bias -> ReLU -> + residual row -> {new residual row, global fp32, next stage's operand}
+ * for the single new token of each of B canvases, in ONE kernel: a CTA owns 16 canvases, streams the chain's weights
+ * through a TMA ring and keeps the residual row / FFN hidden layer in shared memory.  Replaces the per-op launches of
+ * one pre-LN decoder layer step (common/common.py:26-41,84-135; retrieval_augmented_autoreg.py:271-297):
+ *   LN1 -> in_proj                                   (1 stage)
+ *   out_proj + x -> LN2 -> cross-attention query     (2 stages)
+ *   out_proj + x -> LN3 -> linear1 -> ReLU -> linear2 + x  [-> next layer's LN1 -> in_proj | final LN -> LM head]
+ * x: residual rows fp32 [B, 256] (row stride ldx), read once at the start (needed by LayerNorm / add_x stages).
+ * k_in is 256 (LayerNorm / split-row inputs) or 1024 (operand = previous stage's n_out = 1024 with out_operand). */
+typedef struct RalfChainStage {
+  const void* W;      /* split bf16 [2, n_out, k_in], K contiguous, row stride ldw */
+  long long w_plane;
+  int ldw;
+  int n_out;
+  int k_in;
+  int in_mode;        /* 0: previous stage's out_operand, 1: LayerNorm(residual row; gamma, beta, eps), 2: in_split rows */
+  const float* gamma;
+  const float* beta;
+  float eps;
+  const void* in_split; /* split bf16 [2, B, 256] (e.g. an attention output) */
+  long long in_plane;
+  int in_ld;
+  const float* bias;  /* [n_out] or null */
+  int act;            /* 0 none, 1 ReLU */
+  int add_x;          /* + residual row (n_out == 256) */
+  int to_x;           /* the result becomes the residual row (n_out == 256) */
+  int out_operand;    /* the result (split) is the next stage's operand; n_out == 1024 */
+  float* out_f32;     /* global fp32 [B, out_ld] or null */
+  int out_ld;
+} RalfChainStage;
+int ralf_decode_chain(const float* x, int ldx, int B, const RalfChainStage* stages, int n_stages, void* stream);
+
 
 /* ---------------------------------------------------------------------------------------------
  * K3. Non-GEMM ops of the forward / generate path (fp32 CUDA-core kernels, csrc/nn_kernels.cu).

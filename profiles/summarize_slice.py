@@ -16,7 +16,8 @@ def main(path):
         name = re.sub(r"\(.*", "", row["Kernel Name"]).replace("void ", "")
         order.append((name, v))
     # the decode slice starts with LayerNorm -> QKV GEMM -> self-attention (append) of layer 0
-    dec_start = next(i for i, (n, _) in enumerate(order) if "attention_decode" in n) - 2
+    first_attn = next(i for i, (n, _) in enumerate(order) if "attention_decode" in n)
+    dec_start = first_attn - (1 if "decode_chain" in order[first_attn - 1][0] else 2)  # fused: one chain launch before it
     enc, dec = order[:dec_start], order[dec_start:]
     agg = collections.defaultdict(lambda: [0, 0.0])
     for n, v in enc:

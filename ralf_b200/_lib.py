@@ -38,6 +38,16 @@ class GemmArgs(C.Structure):
     ]
 
 
+class ChainStage(C.Structure):
+    _fields_ = [
+        ("W", C.c_void_p), ("w_plane", C.c_longlong), ("ldw", C.c_int), ("n_out", C.c_int), ("k_in", C.c_int),
+        ("in_mode", C.c_int), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float),
+        ("in_split", C.c_void_p), ("in_plane", C.c_longlong), ("in_ld", C.c_int),
+        ("bias", C.c_void_p), ("act", C.c_int), ("add_x", C.c_int), ("to_x", C.c_int), ("out_operand", C.c_int),
+        ("out_f32", C.c_void_p), ("out_ld", C.c_int),
+    ]
+
+
 _lib = None
 
 
@@ -74,6 +84,7 @@ def lib() -> C.CDLL:
         L.ralf_stem_gemm.argtypes = [C.POINTER(GemmArgs)] + [C.c_int] * 3 + [C.c_void_p]
         L.ralf_stem_s2d.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]
         L.ralf_gemm_ln.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.POINTER(GemmArgs), C.c_void_p]
+        L.ralf_decode_chain.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(ChainStage), C.c_int, C.c_void_p]
         L.ralf_check_device.argtypes = [C.c_int]
         vp, i, ll, f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
         L.ralf_layernorm.argtypes = [vp, ll, vp, vp, f, i, i, vp, vp, ll, vp]

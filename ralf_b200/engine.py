@@ -33,6 +33,13 @@ D = 256
 FUSE_LN = os.environ.get("RALF_FUSE_LN", "0") != "0"
 # Decoder cross-attention K/V cache of the greedy loop in the 24-bit format (3 bytes per value); RALF_KV24=0 keeps fp32.
 KV24 = os.environ.get("RALF_KV24", "1") != "0"
+# Fused decode-step chains (ralf_decode_chain, csrc/decode_chain.cu): the row-local ops of a decoder-layer step in 3 kernels
+# (LN1+in_proj | out_proj+LN2+cross-q | out_proj+LN3+FFN [+ next layer's LN1+in_proj / final LN + LM head]) instead of 9.
+# Bit-identical to the per-op launches (RALF_CHAIN_ACC=1) but measured SLOWER on B200 (191.8 vs 184.1 ms per 1024-canvas
+# step, profiles/r2_decode_chain.md): a CTA that owns 16 canvases must stream ALL of the layer's weights through its own
+# tensor core, and an SS-mode tcgen05.mma at N = 16 costs ~92 cycles whatever N is (operand fetch of the 128-row weight
+# tile), so the chain is MMA-issue bound at ~0.6 us per 32 KB weight tile.  Opt-in (RALF_DECODE_CHAIN=1) for A/B runs.
+DECODE_CHAIN = os.environ.get("RALF_DECODE_CHAIN", "0") != "0"
 # 3x3 stride-1 convolutions as implicit GEMMs (ralf_conv_gemm); RALF_IMPLICIT_CONV=0 restores im2col + GEMM for A/B runs.
 IMPLICIT_CONV = os.environ.get("RALF_IMPLICIT_CONV", "1") != "0"
 
@@ -458,6 +465,8 @@ class Engine:
         """One KV-cached pass of the 6 decoder layers + head over the token embeddings ``x`` [B, 256] at position ``t``
         (updates ``x`` and rows ``t`` of the self-attention caches in place) -> logits [B, V]."""
         kv24 = kvm[0].dtype == torch.uint8
+        if DECODE_CHAIN and self.npass == 3:
+            return self._decode_step_chained(x, t, kc, vc, kvm, pad_mask, B, Mlen)
         for i in range(NLAYER):
             p = f"decoder.transformer.layers.{i}"
             # every LayerNorm of the step is folded into the GEMM that consumes it (ralf_gemm_ln)
@@ -473,6 +482,44 @@ class Engine:
             _, f = self._gemm_ln(x, p + ".norm3", p + ".linear1", act="relu", want_f32=False, want_split=True)
             self._gemm(f, p + ".linear2", res=x, out_f32=x)
         logits, _ = self._gemm_ln(x, "decoder.head.0", "decoder.head.1")
+        return logits
+
+    def _decode_step_chained(self, x: torch.Tensor, t: int, kc: list, vc: list, kvm: list, pad_mask: torch.Tensor, B: int,
+                             Mlen: int) -> torch.Tensor:
+        """``_decode_step`` with the row-local ops of every layer fused (ops.decode_chain): per layer
+        [LN1 + in_proj] -> self-attention (KV append) -> [out_proj + x, LN2, cross-q] -> cross-attention over the memory
+        cache -> [out_proj + x, LN3, linear1, ReLU, linear2 + x, and the NEXT layer's LN1 + in_proj or the final LN + LM
+        head]: 4 launches per layer instead of 11, the residual row and the FFN hidden layer never leave the SM."""
+        w, dev = self.w, self.dev
+        kv24 = kvm[0].dtype == torch.uint8
+        L = "decoder.transformer.layers."
+        cs = ops.chain_stage
+
+        def ln(name):
+            return (w[name + ".g"], w[name + ".beta"])
+
+        qkv = torch.empty((B, 3 * D), dtype=torch.float32, device=dev)
+        q = torch.empty((B, D), dtype=torch.float32, device=dev)
+        logits = torch.empty((B, self.vocab), dtype=torch.float32, device=dev)
+        ops.decode_chain(x, B, [cs(w[L + "0.qkv.w"], bias=w[L + "0.qkv.b"], ln=ln(L + "0.norm1"), out_f32=qkv)])
+        for i in range(NLAYER):
+            p = L + str(i)
+            a = ops.attention_decode_append(qkv, kc[i], vc[i], t, B, NHEAD, 32, mask=pad_mask)
+            ops.decode_chain(x, B, [cs(w[p + ".o.w"], bias=w[p + ".o.b"], in_split=a, add_x=True, to_x=True, out_f32=x),
+                                    cs(w[p + ".cq.w"], bias=w[p + ".cq.b"], ln=ln(p + ".norm2"), out_f32=q)])
+            if kv24:
+                a = ops.attention_decode_kv24(q, kvm[i], Mlen, Mlen, B, NHEAD)
+            else:
+                a = ops.attention_decode(q, kvm[i][:, :D], kvm[i][:, D:], Mlen, Mlen, B, NHEAD, 32)
+            stages = [cs(w[p + ".co.w"], bias=w[p + ".co.b"], in_split=a, add_x=True, to_x=True),
+                      cs(w[p + ".linear1.w"], bias=w[p + ".linear1.b"], ln=ln(p + ".norm3"), act="relu", out_operand=True),
+                      cs(w[p + ".linear2.w"], bias=w[p + ".linear2.b"], add_x=True, to_x=True, out_f32=x)]
+            if i + 1 < NLAYER:
+                n = L + str(i + 1)
+                stages.append(cs(w[n + ".qkv.w"], bias=w[n + ".qkv.b"], ln=ln(n + ".norm1"), out_f32=qkv))
+            else:
+                stages.append(cs(w["decoder.head.1.w"], ln=ln("decoder.head.0"), out_f32=logits))
+            ops.decode_chain(x, B, stages)
         return logits
 
     def generate(self, mem_s: Optional[torch.Tensor], B: int, Mlen: int, token_mask: torch.Tensor, bos_id: int,

@@ -181,6 +181,36 @@ def gemm_ln(
     return out_f32, out_split
 
 
+def chain_stage(w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, ln: Optional[tuple] = None,
+                in_split: Optional[torch.Tensor] = None, act: Optional[str] = None, add_x: bool = False, to_x: bool = False,
+                out_operand: bool = False, out_f32: Optional[torch.Tensor] = None, eps: float = 1e-5) -> "_lib.ChainStage":
+    """One stage of ``decode_chain``.  w: split bf16 [2, n_out, k_in].  Input: ``ln=(gamma, beta)`` = LayerNorm of the
+    residual row, ``in_split`` = split rows [2, B, 256] from global memory, neither = the previous stage's operand output."""
+    st = _lib.ChainStage()
+    assert w.dim() == 3 and w.shape[0] == 2 and w.dtype == torch.bfloat16 and w.stride(2) == 1
+    st.W, st.w_plane, st.ldw, st.n_out, st.k_in = w.data_ptr(), w.stride(0), w.stride(1), w.shape[1], w.shape[2]
+    st.in_mode = 1 if ln is not None else (2 if in_split is not None else 0)
+    st.gamma, st.beta, st.eps = (_ptr(ln[0]), _ptr(ln[1]), eps) if ln is not None else (None, None, eps)
+    if in_split is not None:
+        assert in_split.dtype == torch.bfloat16 and in_split.shape[0] == 2 and in_split.stride(2) == 1
+        st.in_split, st.in_plane, st.in_ld = in_split.data_ptr(), in_split.stride(0), in_split.stride(1)
+    st.bias = _ptr(bias)
+    st.act = ACT[act]
+    st.add_x, st.to_x, st.out_operand = int(add_x), int(to_x), int(out_operand)
+    if out_f32 is not None:
+        assert out_f32.dtype == torch.float32 and out_f32.stride(-1) == 1
+        st.out_f32, st.out_ld = out_f32.data_ptr(), out_f32.stride(0)
+    st._keep = (w, bias, ln, in_split, out_f32)  # keep the tensors alive until the call
+    return st
+
+
+def decode_chain(x: Optional[torch.Tensor], B: int, stages: list) -> None:
+    """ralf_decode_chain: the row-local stages of a decoder-layer step for the B new tokens in one kernel."""
+    arr = (_lib.ChainStage * len(stages))(*stages)
+    check(_lib.lib().ralf_decode_chain(_ptr(x), x.stride(0) if x is not None else 0, B, arr, len(stages), _stream()),
+          "ralf_decode_chain")
+
+
 def knn_topk(
     gallery: torch.Tensor,
     queries: torch.Tensor,

@@ -210,3 +210,34 @@ def test_engine_matches_reference_golden_at_maximum_length(cuda_device):
             top2 = torch.topk(lg_o[b, t], 2).values
             margin = float(top2[0] - top2[1]) / float(lg_o[b, t][torch.isfinite(lg_o[b, t])].abs().max())
             assert margin < LOGIT_RTOL, f"canvas {b} diverges at step {t} with oracle margin {margin:.3e}"
+
+
+@pytest.mark.parametrize("B,Mlen", [(3, 40), (16, 532), (37, 532)])
+def test_fused_decode_chain_equals_per_op_decode(cuda_device, monkeypatch, B, Mlen):
+    """ralf_decode_chain (the row-local ops of a decoder-layer step fused into 3 kernels per layer, csrc/decode_chain.cu)
+    against the per-op launches it replaces, over a whole greedy loop from a random memory: same LayerNorm arithmetic and
+    the same products; by default also the same MMA order (bit-identical, measured 0.0); with RALF_CHAIN_ACC=3 (one
+    accumulator per bf16x3 pass, summed in the epilogue) the fp32 summation order differs: step logits agree to <= 1e-5 of
+    scale (measured 3.6e-6 .. 5.5e-6) and the token ids are identical.  B covers a partial 16-canvas tile, one full
+    tile and two full + one partial."""
+    from ralf_b200 import engine as E
+
+    eng = _engine("ralf_cgl", 7, True, cuda_device)
+    tok = helpers.make_tokenizer()
+    g = torch.Generator().manual_seed(100 + B)
+    mem = torch.randn(B * Mlen, 256, generator=g).to(cuda_device)
+    from ralf_b200 import ops
+
+    mem_s = ops.split_bf16(mem)
+    outs = {}
+    for chain in (False, True):
+        monkeypatch.setattr(E, "DECODE_CHAIN", chain)
+        seq, lg = eng.generate(mem_s, B, Mlen, tok.token_mask, 517, 516, tok.max_token_length, return_logits=True)
+        torch.cuda.synchronize()
+        outs[chain] = (seq.cpu().numpy(), lg.cpu().numpy())
+    np.testing.assert_array_equal(outs[True][0], outs[False][0])
+    a, b = outs[True][1], outs[False][1]
+    assert np.isfinite(a).all()
+    err = np.abs(a - b).max() / np.abs(b).max()
+    assert err <= 1e-5, err
+    print(f"B={B}: fused-vs-per-op step logits {err:.2e}")
