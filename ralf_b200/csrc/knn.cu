@@ -685,9 +685,14 @@ static int knn_exact_slices(int C) { return C <= 32 ? 64 : 32; }
 
 using namespace ralf;
 
+// Pre-pass sample: 1/16 of the gallery tiles, at least 16 (128 group maxima per query >= C for both list sizes... C = 64
+// needs 8 tiles) and at most KNN_SAMPLE_TILES; every tile when the gallery has fewer than 16.
 static int knn_sample_tiles(int n) {
   const int tiles = (n + 255) / 256;
-  return tiles < KNN_SAMPLE_TILES ? tiles : KNN_SAMPLE_TILES;
+  int ns = tiles / 16;
+  if (ns < 16) ns = 16;
+  if (ns > KNN_SAMPLE_TILES) ns = KNN_SAMPLE_TILES;
+  return tiles < ns ? tiles : ns;
 }
 static size_t knn_cand_bytes(int n, int q, int C) {
   const size_t qtiles = (q + 127) / 128;
@@ -728,34 +733,33 @@ static int knn_topk_impl(const float* gallery, int n, int d, const float* querie
     if (e != cudaSuccess) return set_cuda_error(e);
     attr_set = true;
   }
-  // Queries go through in passes of 128 (one query tile): every pass streams the gallery once and stays in the
-  // HBM-bound regime the kernel is built for (beyond ~280 queries per pass the TF32 MMAs, not HBM, set the time --
-  // SURVEY.md 8d).  The workspace is reused by the passes (stream order).
+  // All query tiles (128 queries each) go out in ONE launch per phase (blockIdx.y = query tile): a query tile still
+  // streams the gallery once and stays in the HBM-bound regime the kernel is built for (beyond ~280 queries per gallery
+  // pass the TF32 MMAs, not HBM, set the time -- SURVEY.md 8d), but the pre-pass / threshold / re-rank launches and the
+  // scan's launch gaps and tails are paid once per call instead of once per 128 queries (round 1: 4 launches per tile;
+  // at an 8-way shard the fixed ~55 us per tile outweighed the 39 us of HBM time).  CTAs are scheduled x
+  // fastest, so query tile y+1 starts in the SMs tile y's tail leaves idle.
   uint64_t* cand = reinterpret_cast<uint64_t*>(workspace);
   float* tmax = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + knn_cand_bytes(n, q, C));
-  float* thr = tmax + static_cast<size_t>((q + 127) / 128) * KNN_SAMPLE_TILES * KNN_GROUPS * 128;
+  const int qtiles = (q + 127) / 128;
+  float* thr = tmax + static_cast<size_t>(qtiles) * KNN_SAMPLE_TILES * KNN_GROUPS * 128;
   static const int debug_mode = getenv("RALF_KNN_DEBUG") ? atoi(getenv("RALF_KNN_DEBUG")) : 0;
   const int ns = knn_sample_tiles(n);
   const int gx = knn_grid_x(n);
-  for (int q0 = 0; q0 < q; q0 += 128) {
-    const int qn = q - q0 < 128 ? q - q0 : 128;
-    CUtensorMap tq;
-    rc = make_kmajor_tmap(&tq, queries + static_cast<size_t>(q0) * d, 4, d, qn, 1, d, 0, 128);
-    if (rc) return rc;
-    knn_scan_kernel<C, true><<<dim3(ns, 1), 192, Cfg::SMEM_BYTES, st>>>(tq, tg, n, d, qn, nullptr, nullptr, tmax,
-                                                                        debug_mode);
-    knn_threshold_kernel<C><<<128, 256, 0, st>>>(tmax, ns, thr);
-    knn_scan_kernel<C, false><<<dim3(gx, 1), 192, Cfg::SMEM_BYTES, st>>>(tq, tg, n, d, qn, cand, thr, nullptr,
-                                                                         debug_mode);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return set_cuda_error(e);
-    knn_rerank_kernel<C><<<qn, 256, 0, st>>>(cand, gx, gallery, queries + static_cast<size_t>(q0) * d, n, d, k,
-                                             index_base, gmax, thr, out_idx + static_cast<size_t>(q0) * k,
-                                             out_score + static_cast<size_t>(q0) * k,
-                                             certified ? certified + q0 : nullptr);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return set_cuda_error(e);
-  }
+  CUtensorMap tq;
+  rc = make_kmajor_tmap(&tq, queries, 4, d, q, 1, d, 0, 128);
+  if (rc) return rc;
+  knn_scan_kernel<C, true><<<dim3(ns, qtiles), 192, Cfg::SMEM_BYTES, st>>>(tq, tg, n, d, q, nullptr, nullptr, tmax,
+                                                                          debug_mode);
+  knn_threshold_kernel<C><<<qtiles * 128, 256, 0, st>>>(tmax, ns, thr);
+  knn_scan_kernel<C, false><<<dim3(gx, qtiles), 192, Cfg::SMEM_BYTES, st>>>(tq, tg, n, d, q, cand, thr, nullptr,
+                                                                           debug_mode);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e);
+  knn_rerank_kernel<C><<<q, 256, 0, st>>>(cand, gx, gallery, queries, n, d, k, index_base, gmax, thr, out_idx, out_score,
+                                          certified);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e);
   return 0;
 }
 

@@ -246,8 +246,6 @@ def knn_topk(
     check(L.ralf_knn_topk(gallery.data_ptr(), n, d, queries.data_ptr(), q, k, index_base,
                           float(gallery_max_norm), idx.data_ptr(), score.data_ptr(), cert.data_ptr(),
                           workspace.data_ptr(), ws_bytes, _stream()), "ralf_knn_topk")
-    global _LAUNCHES
-    _LAUNCHES += 4 * ((q + 127) // 128 - 1)  # one pass of 4 kernels per 128 queries
     if fixup:
         check(L.ralf_knn_fixup_exact(gallery.data_ptr(), n, d, queries.data_ptr(), q, k, index_base, cert.data_ptr(),
                                      idx.data_ptr(), score.data_ptr(), workspace.data_ptr(), ws_bytes, _stream()),
