@@ -257,6 +257,7 @@ def run_ours(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        kv24_traffic = 837863168 + 3597056 if B == 1024 else None  # dram read + write per launch, ncu capture L (B = 1024, M = 532)
         knn_traffic = None
         try:  # dram__bytes_read.sum + dram__bytes_write.sum of one k-NN pass (ncu --set full; profiles/r1_knn_pass_f_ncu.md)
             knn_traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_knn_pass_f_ncu.json")))["traffic_bytes_per_pass"]
@@ -292,18 +293,19 @@ def run_ours(args):
                     "ms_per_step": round(ms_e2e / args.steps, 3)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "k-NN pass over the gallery shard per tile of 128 queries: whole search (knn_scan_kernel<32,pre> + "
-                                   "knn_threshold_kernel + knn_scan_kernel<32> (TF32 tcgen05 scan + fused top-C filter) + "
-                                   "knn_rerank_kernel<32> + exact fix-up launches) / query tiles",
-                         "bound": "hbm", "launches_per_step": knn_passes,
-                         "achieved": round(knn_bytes / (knn_ms / 1e3) / 1e9, 1), "peak": hbm_peak, "unit": "GB/s",
-                         "frac": round(knn_bytes / (knn_ms / 1e3) / 1e9 / hbm_peak, 4),
-                         "traffic": knn_traffic if (knn_traffic and n_local == 1_000_000) else None,
-                         "algorithmic_bytes_per_launch": int(knn_bytes), "ms_per_launch": round(knn_ms, 4),
-                         "share_of_step": round(knn_passes * knn_ms / step_ms, 4),
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                         "timed_with": "the previous batch's decode loop running on its own stream (--overlap): shared HBM"
-                                       if args.overlap else "nothing else on the device"},
+            "roofline_knn": {"kernel": "k-NN pass over the gallery shard per tile of 128 queries: whole search (knn_scan_kernel<32,pre> + "
+                                       "knn_threshold_kernel + knn_scan_kernel<32> (TF32 tcgen05 scan + fused top-C filter) + "
+                                       "knn_rerank_kernel<32> + exact fix-up launches) / query tiles",
+                             "bound": "hbm", "launches_per_step": knn_passes,
+                             "achieved": round(knn_bytes / (knn_ms / 1e3) / 1e9, 1), "peak": hbm_peak, "unit": "GB/s",
+                             "frac": round(knn_bytes / (knn_ms / 1e3) / 1e9 / hbm_peak, 4),
+                             "traffic": knn_traffic if (knn_traffic and n_local == 1_000_000) else None,
+                             "algorithmic_bytes_per_launch": int(knn_bytes), "ms_per_launch": round(knn_ms, 4),
+                             "share_of_step": round(knn_passes * knn_ms / step_ms, 4),
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                             "timed_with": "CUDA events around the search graph INSIDE the timed region (every step); "
+                                           + ("the previous batch's decode loop running on its own stream (--overlap): shared HBM"
+                                              if args.overlap else "nothing else on the device")},
             "model_flops": {"algorithmic_gflop_per_layout": round(flops_layout / 1e9, 2),
                             "achieved_tflops": round(flops_layout * value / 1e12 / world, 2),
                             "bf16_peak_tflops": peaks.get("bf16_tflops_sustained"),
@@ -313,7 +315,21 @@ def run_ours(args):
             pk = hbm_peak if o["bound"] == "hbm" else peaks.get("bf16_tflops", 1590.0)
             o["peak"], o["frac"] = pk, round(o["achieved"] / pk, 4)
             o["share_of_step"] = round(o["ms_per_launch"] * o["launches_per_step"] / step_ms, 4)  # timed alone vs the step
-        line["roofline_other"] = other
+            o["peak_source"] = "MEASURED_PEAKS.json (burst figure: kernel timed alone)" if peaks else "fallback"
+        # `roofline` = the DOMINANT single kernel of the step: the decode-step cross-attention stream over the 24-bit memory
+        # K/V cache (one shape, 6 layers x 60 tokens = 360 launches, ~26 % of the step; the tensor-core GEMM family is a
+        # third of the step but is ~40 different shapes -- its representative is in roofline_other).  The k-NN search, the
+        # other half of BASELINE.json's metric ("k-NN GB/s vs HBM peak"), is `roofline_knn`, timed live every step.
+        dom = next((o for o in (other or []) if o["bound"] == "hbm"), None)
+        if dom is not None:
+            dom = dict(dom)
+            dom["traffic"] = kv24_traffic  # ncu --set full capture of the same kernel / shape (profiles/r1_kv24_l_ncu.md)
+            dom["timed_with"] = ("20 back-to-back launches right after the timed region on a synthetic cache of the step's shape "
+                                 "(operands 837 MB >> L2), CUDA events on the launching stream; inside the region the kernel "
+                                 "lives in a CUDA graph where events cannot bracket it -- its in-step share is confirmed by the "
+                                 "ncu launch list (profiles/r2_launches_*_summary.md)")
+            line["roofline"] = dom
+        line["roofline_other"] = [o for o in (other or []) if o["bound"] != "hbm"]
         if api is not None:
             line["e2e_model_api"] = api
     else:
@@ -568,7 +584,7 @@ def run_extras(args, rank, world, dev, model, retr, pipe, line):
             ex[key]["wall_s"] = round(time.time() - t0, 1)
         torch.cuda.synchronize()
 
-    hbm_peak = (line or {}).get("roofline", {}).get("peak", 6551.0)
+    hbm_peak = (line or {}).get("roofline_knn", {}).get("peak", 6551.0)
     guarded("knn_sweep", lambda: extra_knn_sweep(rank, world, dev, retr, hbm_peak), True)
     if world > 1:
         guarded("strong_scaled_1024_total", lambda: extra_strong(args, rank, world, dev, model, retr), True)

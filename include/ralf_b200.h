@@ -273,8 +273,25 @@ int ralf_kv_append(const float* qkv, int B, int D, float* kcache, float* vcache,
 int ralf_transpose_to_split(const float* in_f32, const void* in_split, long long in_plane, long long ld_in, int R,
                             int C, void* out, long long out_plane, long long ld_out, void* stream);
 int ralf_to_split(const float* in, long long total, void* out, long long out_plane, void* stream);
+/* Multi-tensor weight refresh after an optimiser step: every task turns an fp32 weight [R, C] into the split GEMM operand
+ * W [2, R, w_ld] and its transpose W^T [2, C, wt_ld] (dgrad operand).  `tasks_dev` is a DEVICE array sorted by tile0
+ * (tile0 = running sum of ceil(R/32)*ceil(C/32)); one launch of total_tiles CTAs. */
+typedef struct RalfRefreshTask {
+  const float* src;
+  long long ld_in;
+  int R, C;
+  void* w;
+  long long w_plane, w_ld;
+  void* wt;
+  long long wt_plane, wt_ld;
+  int tile0;
+  int tiles_x;
+} RalfRefreshTask;
+int ralf_refresh_operands(const RalfRefreshTask* tasks_dev, int ntasks, int total_tiles, void* stream);
 /* out[c] (+)= sum_r in[r, c]  (bias gradients; deterministic order). */
-int ralf_colsum(const float* in, long long ld, int M, int C, float* out, int accumulate, void* stream);
+/* workspace: ralf_colsum_workspace_bytes(M, C) bytes (0 = small M: single pass) or null; both paths are deterministic. */
+size_t ralf_colsum_workspace_bytes(int M, int C);
+int ralf_colsum(const float* in, long long ld, int M, int C, float* out, int accumulate, float* workspace, void* stream);
 /* nn.LayerNorm backward; dx = add_to + dLN; workspace = 2*D*min(ceil(M/8), 4*SMs) floats. */
 int ralf_layernorm_bwd(const float* x, long long x_ld, const float* dy, const float* gamma, float eps, int M, int D,
                        const float* add_to, float* dx, float* dgamma, float* dbeta, float* workspace, void* stream);

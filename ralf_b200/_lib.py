@@ -38,6 +38,13 @@ class GemmArgs(C.Structure):
     ]
 
 
+class RefreshTask(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("ld_in", C.c_longlong), ("R", C.c_int), ("C", C.c_int),
+                ("w", C.c_void_p), ("w_plane", C.c_longlong), ("w_ld", C.c_longlong),
+                ("wt", C.c_void_p), ("wt_plane", C.c_longlong), ("wt_ld", C.c_longlong),
+                ("tile0", C.c_int), ("tiles_x", C.c_int)]
+
+
 class ChainStage(C.Structure):
     _fields_ = [
         ("W", C.c_void_p), ("w_plane", C.c_longlong), ("ldw", C.c_int), ("n_out", C.c_int), ("k_in", C.c_int),
@@ -107,7 +114,10 @@ def lib() -> C.CDLL:
         L.ralf_fid_embed_packed.argtypes = [vp, i, i, i, vp, vp, vp, i, vp, ll, vp, vp]
         L.ralf_transpose_to_split.argtypes = [vp, vp, ll, ll, i, i, vp, ll, ll, vp]
         L.ralf_to_split.argtypes = [vp, ll, vp, ll, vp]
-        L.ralf_colsum.argtypes = [vp, ll, i, i, vp, i, vp]
+        L.ralf_refresh_operands.argtypes = [vp, i, i, vp]
+        L.ralf_colsum.argtypes = [vp, ll, i, i, vp, i, vp, vp]
+        L.ralf_colsum_workspace_bytes.restype = C.c_size_t
+        L.ralf_colsum_workspace_bytes.argtypes = [i, i]
         L.ralf_layernorm_bwd.argtypes = [vp, ll, vp, vp, f, i, i, vp, vp, vp, vp, vp, vp]
         L.ralf_attention_bwd.argtypes = [vp, i, vp, vp, i, vp, i, i, i, i, i, i, f, vp, ll, vp, i, vp, vp, vp, i, vp, vp, i, vp]
         u32 = C.c_uint

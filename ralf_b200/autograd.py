@@ -90,7 +90,10 @@ def transpose_to_split(x_f32: Optional[torch.Tensor] = None, x_split: Optional[t
 
 
 def colsum(x: torch.Tensor, out: torch.Tensor, accumulate: bool = False) -> None:
-    check(_L().ralf_colsum(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], out.data_ptr(), int(accumulate), _stream()),
+    M, Cn = x.shape
+    nb = _L().ralf_colsum_workspace_bytes(M, Cn)
+    ws = torch.empty(nb // 4, dtype=torch.float32, device=x.device) if nb else None
+    check(_L().ralf_colsum(x.data_ptr(), x.stride(0), M, Cn, out.data_ptr(), int(accumulate), _ptr(ws), _stream()),
           "ralf_colsum")
 
 
@@ -158,11 +161,35 @@ class ParamStore:
         return t.reshape(t.shape[0], -1)[r0:r0 + rows]
 
     def refresh_operands(self) -> None:
-        """master fp32 weights -> split W [2,N,K] and W^T [2,K,N] for every registered GEMM weight."""
+        """master fp32 weights -> split W [2,N,K] and W^T [2,K,N] for every registered GEMM weight.  The first call
+        allocates the operand buffers weight by weight; later calls (one per optimiser step) are ONE multi-tensor launch
+        over a device-resident task table (the buffers and the master weights keep their addresses)."""
+        if getattr(self, "_refresh_table", None) is not None and self._refresh_names == list(self.gemm_weights):
+            tab, n, tiles = self._refresh_table
+            check(_L().ralf_refresh_operands(tab.data_ptr(), n, tiles, _stream()), "ralf_refresh_operands")
+            return
         for name in self.gemm_weights:
             w = self.weight_view(name)
             self.w[name] = to_split(w, out=self.w.get(name))
             self.wT[name] = transpose_to_split(x_f32=w, out=self.wT.get(name))
+        import ctypes as C
+
+        tasks, tile0 = [], 0
+        for name in self.gemm_weights:
+            w, ws, wt = self.weight_view(name), self.w[name], self.wT[name]
+            t = _lib.RefreshTask()
+            t.src, t.ld_in, t.R, t.C = w.data_ptr(), w.stride(0), w.shape[0], w.shape[1]
+            t.w, t.w_plane, t.w_ld = ws.data_ptr(), ws.stride(0), ws.stride(1)
+            t.wt, t.wt_plane, t.wt_ld = wt.data_ptr(), wt.stride(0), wt.stride(1)
+            t.tiles_x = (t.C + 31) // 32
+            t.tile0 = tile0
+            tile0 += t.tiles_x * ((t.R + 31) // 32)
+            tasks.append(t)
+        if tasks:
+            arr = (_lib.RefreshTask * len(tasks))(*tasks)
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            self._refresh_table = (host.to(self.flat_p.device), len(tasks), tile0)
+            self._refresh_names = list(self.gemm_weights)
 
 
 # ---- ops --------------------------------------------------------------------------------------------

@@ -52,6 +52,47 @@ __global__ void transpose_to_split_kernel(const float* __restrict__ in_f32, cons
   }
 }
 
+// Multi-tensor weight refresh (after every optimiser step): for each task, fp32 W [R, C] (row stride ld_in) ->
+// split W [2, R, w_ld] AND split W^T [2, C, wt_ld] in one pass over 32x32 tiles.  One launch for all ~140 GEMM weights of
+// the model instead of two launches per weight (274 of the 2330 kernels of a training step).
+struct RefreshTask {
+  const float* src;
+  long long ld_in;
+  int R, C;
+  __nv_bfloat16* w;
+  long long w_plane, w_ld;
+  __nv_bfloat16* wt;
+  long long wt_plane, wt_ld;
+  int tile0;    // first global tile index of this task
+  int tiles_x;  // ceil(C / 32)
+};
+__global__ void refresh_operands_kernel(const RefreshTask* __restrict__ tasks, int ntasks) {
+  __shared__ float tile[32][33];
+  const int g = blockIdx.x;
+  int lo = 0, hi = ntasks - 1;
+  while (lo < hi) {  // last task with tile0 <= g
+    const int mid = (lo + hi + 1) >> 1;
+    if (tasks[mid].tile0 <= g) lo = mid; else hi = mid - 1;
+  }
+  const RefreshTask t = tasks[lo];
+  const int local = g - t.tile0;
+  const int c0 = (local % t.tiles_x) * 32, r0 = (local / t.tiles_x) * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (r < t.R && c < t.C) {
+      v = t.src[static_cast<long long>(r) * t.ld_in + c];
+      t_store_split(t.w, t.w_plane, static_cast<long long>(r) * t.w_ld + c, v);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < t.C && r < t.R) t_store_split(t.wt, t.wt_plane, static_cast<long long>(c) * t.wt_ld + r, tile[threadIdx.x][i]);
+  }
+}
+
 // fp32 [M, C] -> split [M, C] (same layout): GEMM A operand from an fp32 gradient.
 __global__ void to_split_kernel(const float* __restrict__ in, long long total, __nv_bfloat16* __restrict__ out,
                                 long long plane) {
@@ -528,6 +569,14 @@ extern "C" int ralf_transpose_to_split(const float* in_f32, const void* in_split
   return set_cuda_error(cudaGetLastError());
 }
 
+static_assert(sizeof(RefreshTask) == sizeof(RalfRefreshTask), "RalfRefreshTask layout");
+extern "C" int ralf_refresh_operands(const RalfRefreshTask* tasks_dev, int ntasks, int total_tiles, void* stream) {
+  if (!tasks_dev) return RALF_ERR_NULL;
+  if (ntasks <= 0 || total_tiles <= 0) return RALF_ERR_SHAPE;
+  refresh_operands_kernel<<<total_tiles, dim3(32, 8), 0, ST(stream)>>>(reinterpret_cast<const RefreshTask*>(tasks_dev), ntasks);
+  return set_cuda_error(cudaGetLastError());
+}
+
 extern "C" int ralf_to_split(const float* in, long long total, void* out, long long out_plane, void* stream) {
   if (!in || !out) return RALF_ERR_NULL;
   if (total <= 0) return RALF_ERR_SHAPE;
@@ -535,10 +584,50 @@ extern "C" int ralf_to_split(const float* in, long long total, void* out, long l
   return set_cuda_error(cudaGetLastError());
 }
 
-extern "C" int ralf_colsum(const float* in, long long ld, int M, int C, float* out, int accumulate, void* stream) {
+// Tall matrices (M = batch x tokens or batch x pixels): the single-pass kernel above has only C/32 CTAs (57 us per call,
+// 11 % of the round-2 training step, profiles/r2_train_slice_summary.md).  Two deterministic passes instead: slabs of
+// 512 rows reduced by (C/32 x slabs) CTAs into the workspace, then summed in slab order.
+__global__ void colsum_slab_kernel(const float* __restrict__ in, long long ld, int M, int C, int rows_per_slab,
+                                   float* __restrict__ part) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int r_lo = blockIdx.y * rows_per_slab, r_hi = min(M, r_lo + rows_per_slab);
+  float acc = 0.f;
+  if (c < C)
+    for (int r = r_lo + threadIdx.y; r < r_hi; r += 8) acc += in[static_cast<long long>(r) * ld + c];
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+    part[static_cast<long long>(blockIdx.y) * C + c] = s;
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, int nslabs, int C, float* __restrict__ out, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int b = 0; b < nslabs; ++b) s += part[static_cast<long long>(b) * C + c];
+  out[c] = accumulate ? out[c] + s : s;
+}
+constexpr int COLSUM_SLAB = 512;
+
+extern "C" size_t ralf_colsum_workspace_bytes(int M, int C) {
+  if (M <= 2 * COLSUM_SLAB || C <= 0) return 0;
+  return static_cast<size_t>((M + COLSUM_SLAB - 1) / COLSUM_SLAB) * C * sizeof(float);
+}
+extern "C" int ralf_colsum(const float* in, long long ld, int M, int C, float* out, int accumulate, float* workspace,
+                           void* stream) {
   if (!in || !out) return RALF_ERR_NULL;
   if (M <= 0 || C <= 0) return RALF_ERR_SHAPE;
-  colsum_kernel<<<(C + 31) / 32, dim3(32, 8), 0, ST(stream)>>>(in, ld, M, C, out, accumulate);
+  if (workspace && M > 2 * COLSUM_SLAB) {
+    const int nslabs = (M + COLSUM_SLAB - 1) / COLSUM_SLAB;
+    colsum_slab_kernel<<<dim3((C + 31) / 32, nslabs), dim3(32, 8), 0, ST(stream)>>>(in, ld, M, C, COLSUM_SLAB, workspace);
+    colsum_final_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(workspace, nslabs, C, out, accumulate);
+  } else {
+    colsum_kernel<<<(C + 31) / 32, dim3(32, 8), 0, ST(stream)>>>(in, ld, M, C, out, accumulate);
+  }
   return set_cuda_error(cudaGetLastError());
 }
 
