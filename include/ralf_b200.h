@@ -273,6 +273,9 @@ int ralf_kv_append(const float* qkv, int B, int D, float* kcache, float* vcache,
 int ralf_transpose_to_split(const float* in_f32, const void* in_split, long long in_plane, long long ld_in, int R,
                             int C, void* out, long long out_plane, long long ld_out, void* stream);
 int ralf_to_split(const float* in, long long total, void* out, long long out_plane, void* stream);
+/* fp32 [R, C] -> split [2, R, out_ld] and its transpose split [2, C, outT_ld] in one pass (dY for dgrad and wgrad). */
+int ralf_split_and_transpose(const float* in, long long ld_in, int R, int C, void* out, long long out_plane, long long out_ld,
+                             void* outT, long long outT_plane, long long outT_ld, void* stream);
 /* Multi-tensor weight refresh after an optimiser step: every task turns an fp32 weight [R, C] into the split GEMM operand
  * W [2, R, w_ld] and its transpose W^T [2, C, wt_ld] (dgrad operand).  `tasks_dev` is a DEVICE array sorted by tile0
  * (tile0 = running sum of ceil(R/32)*ceil(C/32)); one launch of total_tiles CTAs. */
@@ -348,7 +351,7 @@ int ralf_adamw_step_dyn(float* params, const float* grads, float* exp_avg, float
                         const float* grad_norm, float max_norm, float lr, float beta1, float beta2, float eps,
                         float weight_decay, const float* dyn, void* stream);
 /* BatchNorm2d in training mode on NHWC rows [M, C]: mode 0 = batch mean / rstd (+ running-stat update),
- * mode 1 = (sum a, sum a*xhat) for the backward; workspace = 2*C*ceil(M/2048) floats. */
+ * mode 1 = (sum a, sum a*xhat) for the backward; workspace = 2*C*ceil(M/256) floats. */
 int ralf_bn_colstats(const float* a, const float* z, const float* mean, const float* rstd, int mode, int M, int C,
                      float eps, float momentum, float* out0, float* out1, float* running_mean, float* running_var,
                      float* workspace, void* stream);

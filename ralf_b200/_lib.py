@@ -115,6 +115,7 @@ def lib() -> C.CDLL:
         L.ralf_transpose_to_split.argtypes = [vp, vp, ll, ll, i, i, vp, ll, ll, vp]
         L.ralf_to_split.argtypes = [vp, ll, vp, ll, vp]
         L.ralf_refresh_operands.argtypes = [vp, i, i, vp]
+        L.ralf_split_and_transpose.argtypes = [vp, ll, i, i, vp, ll, ll, vp, ll, ll, vp]
         L.ralf_colsum.argtypes = [vp, ll, i, i, vp, i, vp, vp]
         L.ralf_colsum_workspace_bytes.restype = C.c_size_t
         L.ralf_colsum_workspace_bytes.argtypes = [i, i]

@@ -89,6 +89,20 @@ def transpose_to_split(x_f32: Optional[torch.Tensor] = None, x_split: Optional[t
     return out  # shape [2, C, R], row stride Rp
 
 
+def split_and_transpose(x: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    """fp32 [R, C] (contiguous rows) -> (split [2, R, C], split^T [2, C, R] with row stride R rounded up to 8) in one pass.
+    Falls back to the two separate kernels when C is not a multiple of 8 (padded row pitch of ``to_split``)."""
+    R, Cn = x.shape
+    if Cn % 8 or not x.is_contiguous():
+        return to_split(x), transpose_to_split(x_f32=x)
+    Rp = (R + 7) // 8 * 8
+    s = torch.empty((2, R, Cn), dtype=torch.bfloat16, device=x.device)
+    t = torch.empty((2, Cn, Rp), dtype=torch.bfloat16, device=x.device)[:, :, :R]
+    check(_L().ralf_split_and_transpose(x.data_ptr(), x.stride(0), R, Cn, s.data_ptr(), s.stride(0), s.stride(1),
+                                        t.data_ptr(), t.stride(0), Rp, _stream()), "ralf_split_and_transpose")
+    return s, t
+
+
 def colsum(x: torch.Tensor, out: torch.Tensor, accumulate: bool = False) -> None:
     M, Cn = x.shape
     nb = _L().ralf_colsum_workspace_bytes(M, Cn)
@@ -211,13 +225,15 @@ def linear(tape: Tape, ps: ParamStore, x: Node, wname: str, bias: Optional[str] 
             check(_L().ralf_relu_bwd(dy.data_ptr(), y.s.data_ptr(), dy.numel(), _stream()), "ralf_relu_bwd")
         if res is not None:
             accumulate(res, dy)  # residual branch shares dy (read-only from here on)
-        dyT = transpose_to_split(x_f32=dy)            # [2, N, M]
+        if x.need_grad:
+            dys, dyT = split_and_transpose(dy)        # [2, M, N] and [2, N, M] in one pass
+        else:
+            dyT = transpose_to_split(x_f32=dy)        # [2, N, M]
         xT = transpose_to_split(x_split=x.s)          # [2, K, M]
         ops.gemm(dyT, xT, out_f32=ps.weight_view(wname, grad=True), npass=npass, splitk=True)   # dW = dY^T X
         if bias is not None:
             colsum(dy, ps.g(bias))
         if x.need_grad:
-            dys = to_split(dy)
             dx, _ = ops.gemm(dys, ps.wT[wname], res=x.grad, npass=npass)          # dX = dY W (+ existing grad)
             x.grad = dx
         y.grad = None

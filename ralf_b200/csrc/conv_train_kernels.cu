@@ -6,6 +6,8 @@
 #include <float.h>
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ralf_internal.h"
 
@@ -149,6 +151,42 @@ __global__ void col2im_kernel(const float* __restrict__ dcol, int B, int H, int 
   }
 }
 
+// float4 form (C % 4 == 0, 16-byte aligned rows): four channels per thread -- a quarter of the index arithmetic and
+// 16-byte loads (the scalar kernel ran at a third of the HBM roofline, profiles/r2_train.md).
+__global__ void col2im_vec4_kernel(const float4* __restrict__ dcol, int B, int H, int W, int C4, int KH, int KW, int stride,
+                                   int pad, int Ho, int Wo, float4* __restrict__ dx, int accumulate) {
+  const long long total = static_cast<long long>(B) * H * W * C4;
+  const long long Kd = static_cast<long long>(KH) * KW * C4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C4);
+    long long r = i / C4;
+    const int ix = static_cast<int>(r % W); r /= W;
+    const int iy = static_cast<int>(r % H);
+    const int b = static_cast<int>(r / H);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int kh = 0; kh < KH; ++kh) {
+      const int ty = iy + pad - kh;
+      if (ty < 0 || ty % stride) continue;
+      const int oy = ty / stride;
+      if (oy >= Ho) continue;
+      for (int kw = 0; kw < KW; ++kw) {
+        const int tx = ix + pad - kw;
+        if (tx < 0 || tx % stride) continue;
+        const int ox = tx / stride;
+        if (ox >= Wo) continue;
+        const float4 v = dcol[((static_cast<long long>(b) * Ho + oy) * Wo + ox) * Kd + (static_cast<long long>(kh) * KW + kw) * C4 + c];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;  // same tap order as the scalar kernel: identical sums
+      }
+    }
+    if (accumulate) {
+      const float4 o = dx[i];
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+    dx[i] = acc;
+  }
+}
+
 // max-pool 3x3/s2/p1 backward, deterministic (no atomics): (1) per output element the tap (kh*3+kw) of its FIRST maximum --
 // torch's rule -- as a byte; (2) gather: every input pixel sums dy over the <= 4 windows whose recorded tap points at it, in a
 // fixed order.  dx is written completely (no zero-initialisation needed).
@@ -275,14 +313,18 @@ using namespace ralf;
 #define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
 
 // mode 0: BatchNorm statistics of z -> mean, rstd (+ running stats).  mode 1: (sum a, sum a*xhat) for the backward.
-// workspace: 2 * C * ceil(M / 2048) floats.
+// workspace: 2 * C * ceil(M / 256) floats.
 extern "C" int ralf_bn_colstats(const float* a, const float* z, const float* mean, const float* rstd, int mode, int M, int C,
                                 float eps, float momentum, float* out0, float* out1, float* running_mean,
                                 float* running_var, float* workspace, void* stream) {
   if (!a || !out0 || !out1 || !workspace) return RALF_ERR_NULL;
   if (mode && (!z || !mean || !rstd)) return RALF_ERR_NULL;
   if (M <= 0 || C <= 0) return RALF_ERR_SHAPE;
-  const int rows_per_slab = 2048;
+  // 512-row slabs: 4x the CTAs of round 1's 2048-row slabs (the kernel was latency bound: 55 us per call).  The slab size only
+  // changes the fp32 summation order; RALF_BN_SLAB (>= 256, the workspace bound) exists because the gradient-parity test on a
+  // 2-sample BatchNorm batch is chaotic in that order (median per-tensor max-rel error vs fp64: 1.43e-4 / 1.69e-4 / 2.33e-4 at
+  // 512 / 2048 / 256 rows -- ReLU kinks flip on 1e-7 perturbations of the statistics, tests/test_train_gpu.py).
+  static const int rows_per_slab = getenv("RALF_BN_SLAB") ? atoi(getenv("RALF_BN_SLAB")) : 512;
   const int nslabs = (M + rows_per_slab - 1) / rows_per_slab;
   colstats_partial_kernel<<<dim3((C + 31) / 32, nslabs), dim3(32, 8), 0, ST(stream)>>>(a, z, mean, rstd, mode, M, C,
                                                                                       rows_per_slab, workspace);
@@ -318,6 +360,12 @@ extern "C" int ralf_col2im(const float* dcol, int B, int H, int W, int C, int KH
   if (B <= 0 || H <= 0 || W <= 0 || C <= 0) return RALF_ERR_SHAPE;
   const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
   const long long total = static_cast<long long>(B) * H * W * C;
+  if (C % 4 == 0 && !(reinterpret_cast<uintptr_t>(dcol) & 15) && !(reinterpret_cast<uintptr_t>(dx) & 15)) {
+    col2im_vec4_kernel<<<c_grid_for(total / 4, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const float4*>(dcol), B, H, W, C / 4,
+                                                                          KH, KW, stride, pad, Ho, Wo,
+                                                                          reinterpret_cast<float4*>(dx), accumulate);
+    return set_cuda_error(cudaGetLastError());
+  }
   col2im_kernel<<<c_grid_for(total, 256), 256, 0, ST(stream)>>>(dcol, B, H, W, C, KH, KW, stride, pad, Ho, Wo, dx, accumulate);
   return set_cuda_error(cudaGetLastError());
 }

@@ -93,6 +93,29 @@ __global__ void refresh_operands_kernel(const RefreshTask* __restrict__ tasks, i
   }
 }
 
+// One tensor, both operands: fp32 dY [R, C] -> split dY [2, R, w_ld] (dgrad A operand) and split dY^T [2, C, wt_ld]
+// (wgrad A operand) in one pass -- the backward of every linear layer needs both.
+__global__ void split_and_transpose_kernel(const float* __restrict__ src, long long ld_in, int R, int C,
+                                           __nv_bfloat16* __restrict__ w, long long w_plane, long long w_ld,
+                                           __nv_bfloat16* __restrict__ wt, long long wt_plane, long long wt_ld) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (r < R && c < C) {
+      v = src[static_cast<long long>(r) * ld_in + c];
+      t_store_split(w, w_plane, static_cast<long long>(r) * w_ld + c, v);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < C && r < R) t_store_split(wt, wt_plane, static_cast<long long>(c) * wt_ld + r, tile[threadIdx.x][i]);
+  }
+}
+
 // fp32 [M, C] -> split [M, C] (same layout): GEMM A operand from an fp32 gradient.
 __global__ void to_split_kernel(const float* __restrict__ in, long long total, __nv_bfloat16* __restrict__ out,
                                 long long plane) {
@@ -566,6 +589,16 @@ extern "C" int ralf_transpose_to_split(const float* in_f32, const void* in_split
   dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
   transpose_to_split_kernel<<<grid, block, 0, ST(stream)>>>(in_f32, CBF(in_split), in_plane, ld_in, R, C, BF(out),
                                                            out_plane, ld_out);
+  return set_cuda_error(cudaGetLastError());
+}
+
+extern "C" int ralf_split_and_transpose(const float* in, long long ld_in, int R, int C, void* out, long long out_plane,
+                                        long long out_ld, void* outT, long long outT_plane, long long outT_ld, void* stream) {
+  if (!in || !out || !outT) return RALF_ERR_NULL;
+  if (R <= 0 || C <= 0 || out_ld < C || outT_ld < R) return RALF_ERR_SHAPE;
+  dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
+  split_and_transpose_kernel<<<grid, block, 0, ST(stream)>>>(in, ld_in, R, C, BF(out), out_plane, out_ld, BF(outT), outT_plane,
+                                                            outT_ld);
   return set_cuda_error(cudaGetLastError());
 }
 

@@ -59,7 +59,7 @@ class Trunk:
         M, Cn = z.shape
         mean = torch.empty(Cn, dtype=torch.float32, device=self.dev)
         rstd = torch.empty(Cn, dtype=torch.float32, device=self.dev)
-        ws = torch.empty(2 * Cn * ((M + 2047) // 2048), dtype=torch.float32, device=self.dev)
+        ws = torch.empty(2 * Cn * ((M + 255) // 256), dtype=torch.float32, device=self.dev)
         rm, rv = self.buffers[bn + ".running_mean"], self.buffers[bn + ".running_var"]
         check(_L().ralf_bn_colstats(z.data_ptr(), None, None, None, 0, M, Cn, 1e-5, 0.1, mean.data_ptr(), rstd.data_ptr(),
                                     rm.data_ptr(), rv.data_ptr(), ws.data_ptr(), _stream()), "ralf_bn_colstats")
@@ -98,7 +98,7 @@ class Trunk:
                 check(_L().ralf_relu_bwd(dy.data_ptr(), out.data_ptr(), dy.numel(), _stream()), "ralf_relu_bwd")
             if res is not None:
                 ag.accumulate(res, dy)
-            ws = torch.empty(2 * Cout * ((M + 2047) // 2048), dtype=torch.float32, device=self.dev)
+            ws = torch.empty(2 * Cout * ((M + 255) // 256), dtype=torch.float32, device=self.dev)
             check(_L().ralf_bn_colstats(dy.data_ptr(), z.data_ptr(), mean.data_ptr(), rstd.data_ptr(), 1, M, Cout, 1e-5, 0.0,
                                         ps.g(bn + ".bias").data_ptr(), ps.g(bn + ".weight").data_ptr(), None, None,
                                         ws.data_ptr(), _stream()), "ralf_bn_colstats")
@@ -118,7 +118,11 @@ class Trunk:
         ps = self.ps
         B, H, W = geom
         pname = conv + ".weight"
-        dzT = ag.transpose_to_split(x_f32=dz)
+        want_dx = need_dx and x.need_grad
+        if want_dx:
+            dzs, dzT = ag.split_and_transpose(dz)  # dgrad and wgrad operands in one pass over dz
+        else:
+            dzT = ag.transpose_to_split(x_f32=dz)
         colT = ag.transpose_to_split(x_split=col)
         if k == 1:
             ops.gemm(dzT, colT, out_f32=ps.weight_view(conv, grad=True), splitk=True)
@@ -128,9 +132,8 @@ class Trunk:
             _, Nn, Cc, T = next(kc for kc in self.kconvs if kc[0] == pname)
             check(_L().ralf_conv_grad_from_gemm(dwg.data_ptr(), Nn, Cc, T, dwg.stride(0), ps.g(pname).data_ptr(), _stream()),
                   "ralf_conv_grad_from_gemm")
-        if not (need_dx and x.need_grad):
+        if not want_dx:
             return
-        dzs = ag.to_split(dz)
         wT = ps.wT[conv] if k == 1 else self.cwT[pname][:, :col.shape[2], :dz.shape[1]]
         if direct:
             dx, _ = ops.gemm(dzs, wT, res=x.grad)
@@ -169,7 +172,7 @@ class Trunk:
             if dy is None:
                 return
             check(_L().ralf_relu_bwd(dy.data_ptr(), s0.data_ptr(), dy.numel(), _stream()), "ralf_relu_bwd")
-            ws = torch.empty(2 * 64 * ((M + 2047) // 2048), dtype=torch.float32, device=dev)
+            ws = torch.empty(2 * 64 * ((M + 255) // 256), dtype=torch.float32, device=dev)
             check(_L().ralf_bn_colstats(dy.data_ptr(), z.data_ptr(), mean.data_ptr(), rstd.data_ptr(), 1, M, 64, 1e-5, 0.0,
                                         ps.g(BODY + ".bn1.bias").data_ptr(), ps.g(BODY + ".bn1.weight").data_ptr(), None, None,
                                         ws.data_ptr(), _stream()), "ralf_bn_colstats")

@@ -109,7 +109,9 @@ def test_training_gradients_match_oracle(cuda_device, train_trunk):
     2-sample batch) on individual tensors for this very input (measured).  The bar is therefore:
     loss 1e-5; global gradient norm 1e-3; per-tensor relative L2 error <= the same bound the fp32 oracle meets
     against fp64 (3e-2) and a median per-tensor max-rel error <= 2e-3 -- and we must not be worse than the fp32
-    oracle itself on the median."""
+    oracle itself on the median.  (The median is chaotic in the fp32 summation ORDER of the BatchNorm statistics on this
+    2-sample batch: 1.43e-4 / 1.69e-4 / 2.33e-4 for 512- / 2048- / 256-row partial sums, measured in round 2; the
+    library's default is the 512-row order.)"""
     from oracle import synth
     from ralf_b200.train import TrainEngine
 
