@@ -274,6 +274,154 @@ attention_fewkeys_kernel(const float* __restrict__ q, int ldq, const float* __re
 }
 
 // ------------------------------------------------------------------------------------------------
+// Few-keys attention, second version: K/V of a CTA's groups staged ONCE in shared memory.
+// The kernel above reads every K/V element with a dependent, warp-broadcast __ldg per float4 at ~170 registers per
+// thread (one CTA per SM): 157 us per FIDNetV3 layer and 184 us for the fusion Attention at 128 canvases against HBM
+// floors of 11 / 16 us (profiles/r2_launches_f_chain_on_summary.md) -- latency bound.  Here a CTA owns G "groups" (a group
+// = one K/V set: a layout sequence of FIDNetV3, or a canvas for the fusion Attention) x a tile of QT queries per group:
+//   1. K and V rows of the G groups -> shared memory [g][h][j][64 + 4] with coalesced float4 loads (all 256 threads);
+//   2. thread = (g, h, query): the same arithmetic, in the same order, as attention_fewkeys_kernel (bit-identical
+//      results), operands from shared memory (lanes of a (g, h) share the address: broadcast);
+//   3. the output tile is staged in shared memory and stored as whole rows.
+// QP = lanes reserved per (g, h) (16 for the short sequences, 32 for image tokens); NT = query tiles per CTA (the fusion
+// Attention reuses a canvas's K/V for 4 tiles of 32 queries).
+// ------------------------------------------------------------------------------------------------
+template <int H, int QP>
+__global__ void __launch_bounds__(256, 1)
+attention_kvsmem_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, const float* __restrict__ v,
+                        int ldk, const unsigned char* __restrict__ mask, int B, int Tq, int Tk, float scale,
+                        __nv_bfloat16* __restrict__ out_split, long long out_plane, float* __restrict__ out_f32, int ldo,
+                        int NT) {
+  constexpr int DH = 64, PITCH = DH + 4;
+  constexpr int G = 256 / (H * QP);        // groups per CTA
+  constexpr int OP = H * DH + 4;           // staged output row pitch
+  extern __shared__ __align__(16) float sm[];
+  float* ks = sm;                                     // [G][H][Tk][PITCH]
+  float* vs = ks + G * H * kFewKeysMax * PITCH;
+  float* stage = vs + G * H * kFewKeysMax * PITCH;    // [G][QP][OP]
+  unsigned char* ms = reinterpret_cast<unsigned char*>(stage + G * QP * OP);  // [G][16]
+  const int tid = threadIdx.x;
+  const int g0 = blockIdx.y * G;
+  // ---- 1. stage K / V (and the key-padding mask) of the CTA's groups
+  const int row_f4 = H * DH / 4;  // float4 per K (or V) row
+  for (int i = tid; i < G * Tk * row_f4; i += 256) {
+    const int c4 = i % row_f4, r = i / row_f4;
+    const int j = r % Tk, g = r / Tk;
+    if (g0 + g >= B) continue;
+    const long long off = (static_cast<long long>(g0 + g) * Tk + j) * ldk + c4 * 4;
+    const float4 fk = *reinterpret_cast<const float4*>(k + off);
+    const float4 fv = *reinterpret_cast<const float4*>(v + off);
+    const int h = (c4 * 4) / DH, d = (c4 * 4) % DH;
+    const int so = ((g * H + h) * kFewKeysMax + j) * PITCH + d;
+    *reinterpret_cast<float4*>(ks + so) = fk;
+    *reinterpret_cast<float4*>(vs + so) = fv;
+  }
+  if (tid < G * kFewKeysMax) {
+    const int g = tid / kFewKeysMax, j = tid % kFewKeysMax;
+    ms[tid] = (mask && g0 + g < B && j < Tk) ? mask[static_cast<long long>(g0 + g) * Tk + j] : 0;
+  }
+  __syncthreads();
+  const int tl = tid % QP, gh = tid / QP;
+  const int h = gh % H, g = gh / H;
+  const bool group_ok = g0 + g < B;
+  for (int nt = 0; nt < NT; ++nt) {
+    const int t0 = (blockIdx.x * NT + nt) * QP;
+    if (t0 >= Tq) break;  // CTA-uniform
+    const int t = t0 + tl;
+    const bool active = group_ok && t < Tq;
+    float qr[DH], o[DH], sc[kFewKeysMax];
+    if (active) {
+      const float* qp = q + (static_cast<long long>(g0 + g) * Tq + t) * ldq + h * DH;
+#pragma unroll
+      for (int i = 0; i < DH; i += 4) {
+        const float4 f = *reinterpret_cast<const float4*>(qp + i);
+        qr[i] = f.x * scale; qr[i + 1] = f.y * scale; qr[i + 2] = f.z * scale; qr[i + 3] = f.w * scale;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < DH; ++i) qr[i] = 0.f;
+    }
+    const float* kb = ks + (g * H + h) * kFewKeysMax * PITCH;
+    const float* vb = vs + (g * H + h) * kFewKeysMax * PITCH;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kFewKeysMax; ++j) {
+      float acc = 0.f;
+      if (j < Tk) {
+#pragma unroll
+        for (int i = 0; i < DH; i += 4) {
+          const float4 f = *reinterpret_cast<const float4*>(kb + j * PITCH + i);
+          acc = fmaf(qr[i], f.x, acc); acc = fmaf(qr[i + 1], f.y, acc);
+          acc = fmaf(qr[i + 2], f.z, acc); acc = fmaf(qr[i + 3], f.w, acc);
+        }
+        if (ms[g * kFewKeysMax + j]) acc = -INFINITY;
+        mx = fmaxf(mx, acc);
+      }
+      sc[j] = acc;
+    }
+    float l = 0.f;
+#pragma unroll
+    for (int i = 0; i < DH; ++i) o[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < kFewKeysMax; ++j) {
+      if (j < Tk) {
+        const float p = __expf(sc[j] - mx);
+        l += p;
+#pragma unroll
+        for (int i = 0; i < DH; i += 4) {
+          const float4 f = *reinterpret_cast<const float4*>(vb + j * PITCH + i);
+          o[i] = fmaf(p, f.x, o[i]); o[i + 1] = fmaf(p, f.y, o[i + 1]);
+          o[i + 2] = fmaf(p, f.z, o[i + 2]); o[i + 3] = fmaf(p, f.w, o[i + 3]);
+        }
+      }
+    }
+    const float inv = 1.f / l;
+    float* mine = stage + (g * QP + tl) * OP + h * DH;
+#pragma unroll
+    for (int i = 0; i < DH; i += 4)
+      *reinterpret_cast<float4*>(mine + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+    __syncthreads();
+    // ---- 3. whole output rows: row (g, tl) = H*64 contiguous floats
+    for (int i = tid; i < G * QP * row_f4; i += 256) {
+      const int c4 = i % row_f4, r = i / row_f4;
+      const int rl = r % QP, rg = r / QP;
+      if (g0 + rg >= B || t0 + rl >= Tq) continue;
+      const float4 f = *reinterpret_cast<const float4*>(stage + (rg * QP + rl) * OP + c4 * 4);
+      const long long off = (static_cast<long long>(g0 + rg) * Tq + t0 + rl) * ldo + c4 * 4;
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + off) = f;
+      if (out_split) {
+        __align__(8) __nv_bfloat16 hi[4];
+        __align__(8) __nv_bfloat16 lo[4];
+        split_bf16(f.x, hi[0], lo[0]); split_bf16(f.y, hi[1], lo[1]);
+        split_bf16(f.z, hi[2], lo[2]); split_bf16(f.w, hi[3], lo[3]);
+        *reinterpret_cast<uint2*>(out_split + off) = *reinterpret_cast<const uint2*>(hi);
+        *reinterpret_cast<uint2*>(out_split + out_plane + off) = *reinterpret_cast<const uint2*>(lo);
+      }
+    }
+    __syncthreads();  // the stage is rewritten by the next query tile
+  }
+}
+template <int H, int QP>
+static int launch_kvsmem(const float* q, int ldq, const float* k, const float* v, int ldk, const unsigned char* mask, int B,
+                         int Tq, int Tk, float scale, void* out_split, long long out_plane, float* out_f32, int ldo,
+                         cudaStream_t st) {
+  constexpr int G = 256 / (H * QP);
+  constexpr int SMEM = (2 * G * H * kFewKeysMax * 68 + G * QP * (H * 64 + 4)) * 4 + G * kFewKeysMax;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kvsmem_kernel<H, QP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return set_cuda_error(e);
+    attr_set = true;
+  }
+  const int tiles = (Tq + QP - 1) / QP;
+  const int NT = tiles >= 4 ? 4 : tiles;  // query tiles per CTA (K/V staged once for all of them)
+  dim3 grid((tiles + NT - 1) / NT, (B + G - 1) / G);
+  attention_kvsmem_kernel<H, QP><<<grid, 256, SMEM, st>>>(q, ldq, k, v, ldk, mask, B, Tq, Tk, scale,
+                                                         reinterpret_cast<__nv_bfloat16*>(out_split), out_plane, out_f32, ldo, NT);
+  return set_cuda_error(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
 // Single-query attention against a K/V cache (greedy decode).  One warp per (batch, head).
 //   q: [B, ldq] fp32 (+ h*DH);  K/V row j of batch b: base + (b*kv_bstride + j)*ldk + h*DH
 //   mask: uint8 [B, mask_ld] or null; Tk keys.  Output: split bf16 [2, B, H*DH].
@@ -1148,7 +1296,26 @@ static int attention_impl(const float* q, int ldq, const float* k, const float* 
     if (tc != 0) return tc < 0 ? tc : 0;
   }
   // few keys, wide heads (fusion Attention over the 16 retrieved layouts): tile kernel with coalesced stores
-  static const bool fewkeys_on = !(getenv("RALF_ATTN_FEWKEYS") && atoi(getenv("RALF_ATTN_FEWKEYS")) == 0);
+  // RALF_ATTN_FEWKEYS: 2 (default) = K/V staged in shared memory (attention_kvsmem_kernel), 1 = the round-1 tile kernel
+  // (broadcast __ldg), 0 = generic kernel.  1 and 2 give bit-identical results.
+  static const int fewkeys_mode = getenv("RALF_ATTN_FEWKEYS") ? atoi(getenv("RALF_ATTN_FEWKEYS")) : 2;
+  const bool fewkeys_on = fewkeys_mode != 0;
+  if (fewkeys_mode == 2 && !da.thresh24 && head_dim == 64 && Tk <= kFewKeysMax && (H == 8 || H == 4) && !causal &&
+      (ldo & 3) == 0 && (out_plane & 3) == 0 && (reinterpret_cast<uintptr_t>(k) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(v) & 15) == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0) {
+    if (H == 8) {
+      if (Tq > 16)
+        return launch_kvsmem<8, 32>(q, ldq, k, v, ldk, key_padding_mask, B, Tq, Tk, scale, out_split, out_plane, out_f32, ldo,
+                                    ST(stream));
+      return launch_kvsmem<8, 16>(q, ldq, k, v, ldk, key_padding_mask, B, Tq, Tk, scale, out_split, out_plane, out_f32, ldo,
+                                  ST(stream));
+    }
+    if (Tq > 16)
+      return launch_kvsmem<4, 32>(q, ldq, k, v, ldk, key_padding_mask, B, Tq, Tk, scale, out_split, out_plane, out_f32, ldo,
+                                  ST(stream));
+    return launch_kvsmem<4, 16>(q, ldq, k, v, ldk, key_padding_mask, B, Tq, Tk, scale, out_split, out_plane, out_f32, ldo,
+                                ST(stream));
+  }
   if (fewkeys_on && !da.thresh24 && head_dim == 64 && Tk <= kFewKeysMax && H <= 8 && !causal &&
       (ldo & 3) == 0 && (out_plane & 3) == 0) {
     static bool attr_set = false;

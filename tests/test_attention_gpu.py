@@ -218,3 +218,52 @@ def test_encoder_attention_tcgen05_more_than_256_keys(cuda_device):
     assert any(not torch.equal(big[k], base[k]) for k in big)  # a different kernel produced them
     for k in big:
         assert (big[k] - base[k]).abs().max().item() <= 6e-5 * base[k].abs().max().item()
+
+
+_CHILD_FEWKEYS = r'''
+import json, sys, torch
+sys.path.insert(0, sys.argv[1])
+from ralf_b200 import ops
+dev = torch.device("cuda:0")
+for kind, B, Tq, Tk, H in json.loads(sys.argv[3]):
+    Dm = H * 64
+    g = torch.Generator(device=dev).manual_seed(B + Tq + Tk + H)
+    if kind == "fid":   # fused QKV of B sequences of Tq tokens, key-padding mask
+        qkv = torch.randn(B * Tq, 3 * Dm, device=dev, generator=g)
+        nv = torch.randint(1, Tq + 1, (B,), device=dev, generator=g)
+        pad = (torch.arange(Tq, device=dev)[None] >= nv[:, None]).to(torch.uint8).contiguous()
+        out = ops.attention(qkv[:, :Dm], qkv[:, Dm:2 * Dm], qkv[:, 2 * Dm:], B, H, Tq, Tq, 64, mask=pad)
+    else:               # image tokens over the retrieved layouts
+        q = torch.randn(B * Tq, Dm, device=dev, generator=g)
+        kv = torch.randn(B * Tk, 2 * Dm, device=dev, generator=g)
+        out = ops.attention(q, kv[:, :Dm], kv[:, Dm:], B, H, Tq, Tk, 64)
+    torch.cuda.synchronize()
+    torch.save(out.cpu(), sys.argv[2] + f"_{kind}_{B}_{Tq}_{Tk}_{H}.pt")
+print("ok")
+'''
+
+
+def test_fewkeys_attention_smem_kernel_is_bit_identical_to_the_tile_kernel(cuda_device):
+    """attention_kvsmem_kernel (RALF_ATTN_FEWKEYS=2, default: K/V of a CTA's groups staged once in shared memory) does the
+    arithmetic of attention_fewkeys_kernel (=1) in the same order: outputs equal bit for bit on the FIDNetV3 and fusion
+    Attention shape classes, partial groups / tiles included (the fp64 bars are test_fusion_... / test_fidnet_... above,
+    which run the default kernel)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import tempfile
+
+    from tests import helpers
+
+    shapes = [["fid", 2080, 11, 11, 4], ["fid", 7, 16, 16, 4], ["fid", 1, 13, 13, 4], ["fus", 130, 256, 16, 8],
+              ["fus", 2, 330, 16, 8], ["fus", 5, 100, 7, 8], ["fus", 1, 31, 1, 4], ["fus", 3, 9, 16, 8]]
+    outs = {}
+    for mode in ("1", "2"):
+        with tempfile.TemporaryDirectory() as tmp:
+            r = subprocess.run([sys.executable, "-c", _CHILD_FEWKEYS, helpers.ROOT, os.path.join(tmp, "o"), json.dumps(shapes)],
+                               env=dict(os.environ, RALF_ATTN_FEWKEYS=mode), capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+            outs[mode] = [torch.load(os.path.join(tmp, "o_%s_%d_%d_%d_%d.pt" % tuple(sh))) for sh in shapes]
+    for sh, a, b in zip(shapes, outs["1"], outs["2"]):
+        assert torch.equal(a, b), sh
