@@ -257,7 +257,9 @@ def run_ours(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        kv24_traffic = 837863168 + 3597056 if B == 1024 else None  # dram read + write per launch, ncu capture L (B = 1024, M = 532)
+        from ralf_b200.engine import KVFMT as _kvfmt
+        # dram read + write per launch of the dominant kernel from its ncu --set full capture (B = 1024, M = 532)
+        kv24_traffic = {24: 837863168 + 3597056, 16: 593771776 + 6663424}.get(_kvfmt) if B == 1024 else None
         knn_traffic = None
         try:  # dram__bytes_read.sum + dram__bytes_write.sum of one k-NN pass (ncu --set full; profiles/r1_knn_pass_f_ncu.md)
             knn_traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_knn_pass_f_ncu.json")))["traffic_bytes_per_pass"]
@@ -323,7 +325,7 @@ def run_ours(args):
         dom = next((o for o in (other or []) if o["bound"] == "hbm"), None)
         if dom is not None:
             dom = dict(dom)
-            dom["traffic"] = kv24_traffic  # ncu --set full capture of the same kernel / shape (profiles/r1_kv24_l_ncu.md)
+            dom["traffic"] = kv24_traffic  # ncu --set full capture of the same kernel / shape (profiles/r2_kv16_ncu.md, r1_kv24_l_ncu.md)
             dom["timed_with"] = ("20 back-to-back launches right after the timed region on a synthetic cache of the step's shape "
                                  "(operands 837 MB >> L2), CUDA events on the launching stream; inside the region the kernel "
                                  "lives in a CUDA graph where events cannot bracket it -- its in-step share is confirmed by the "
@@ -631,10 +633,16 @@ def secondary_rooflines(model, B, dev):
         bound; achieved counts the 3 bf16 passes of the fp32-faithful product (3 * 2 * M * N * K)."""
     from ralf_b200 import ops
 
+    from ralf_b200.engine import KVFMT
+
     out = []
     M = 532
-    kv = torch.randint(0, 255, (B * M, 1536), dtype=torch.uint8, device=dev)
-    kv[:, 1::2][:, :512] &= 0x3F  # keep the synthetic hi halves finite (exponent byte < 0x7f)
+    row = ops.KV_ROW_BYTES[KVFMT]
+    kv = torch.randint(0, 255, (B * M, row), dtype=torch.uint8, device=dev)
+    if KVFMT == 24:
+        kv[:, 1::2][:, :512] &= 0x3F  # keep the synthetic hi halves finite (exponent byte < 0x7f)
+    else:
+        kv[:, 1024:] = torch.full((B * M, 16), 1e-3, device=dev).view(torch.uint8).view(B * M, 64)  # finite scales
     q = torch.randn(B, 256, device=dev)
     o = torch.empty(2, B, 256, dtype=torch.bfloat16, device=dev)
 
@@ -650,8 +658,9 @@ def secondary_rooflines(model, B, dev):
         return e0.elapsed_time(e1) / n
 
     ms = t(lambda: ops.attention_decode_kv24(q, kv, M, M, B, 8, out=o))
-    byt = B * M * 1536 + B * 256 * 4 + B * 256 * 4
-    out.append({"kernel": "attention_decode_kv24_kernel (decode-step cross-attention over the 24-bit memory K/V cache)",
+    byt = B * M * row + B * 256 * 4 + B * 256 * 4
+    out.append({"kernel": f"attention_decode_kv{KVFMT}_kernel (decode-step cross-attention over the {KVFMT}-bit memory K/V cache, "
+                          f"{row} bytes per memory token)",
                 "bound": "hbm", "achieved": round(byt / ms / 1e6, 1), "unit": "GB/s", "ms_per_launch": round(ms, 4),
                 "algorithmic_bytes_per_launch": byt, "launches_per_step": 360})
     del kv

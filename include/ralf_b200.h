@@ -117,6 +117,12 @@ typedef struct RalfGemmArgs {
                        * is the fp32 result rounded to 24 bits, hi = bits 31..16, lo = bits 15..8 (16-bit mantissa,
                        * the accuracy class of the bf16x3 product that made it) -- 3 instead of 4 bytes per element on
                        * the stream the decode loop is bound by */
+  int out_kv_fmt;     /* 0 / 24: the 24-bit format above.  16: rows of 1088 bytes
+                       * [K 256 x u16 | V 256 x u16 | K scale 8 x f32 | V scale 8 x f32]: per (row, head) the 32 values are
+                       * stored as offset-binary 16-bit integers q + 32768, q = rint(x * 32767 / amax), next to the scale
+                       * amax / 32767 -- 2.125 bytes per element; error 2^-16 of the head's largest value (measured on the
+                       * reference goldens: step logits within 8e-5 of scale, token ids identical;
+                       * profiles/r2_precision_study.json) */
   void* splitk_ws;    /* optional workspace: lets a plain fp32-output GEMM with few M x N tiles and a long K (weight
                        * gradients: K = all rows of the batch) run split-K (k slices -> partials -> deterministic sum) */
   size_t splitk_ws_bytes; /* >= ralf_gemm_splitk_workspace_bytes(M, N, K) */
@@ -202,6 +208,9 @@ int ralf_attention_decode(const float* q, int ldq, const float* k, const float* 
 /* ralf_attention_decode over a 24-bit K/V cache written by ralf_gemm(out_kv24): rows (b*kv_bstride + j) of 1536 bytes,
  * 8 heads x 32, no mask (memory cross-attention of the decode loop). */
 int ralf_attention_decode_kv24(const float* q, int ldq, const void* kv24, long long kv_bstride, int Tk, int B, int H,
+                               float scale, void* out_split, long long out_plane, int ldo, void* stream);
+/* The same over the 16-bit per-head-scaled cache (ralf_gemm out_kv24 with out_kv_fmt = 16, rows of 1088 bytes). */
+int ralf_attention_decode_kv16(const float* q, int ldq, const void* kv16, long long kv_bstride, int Tk, int B, int H,
                                float scale, void* out_split, long long out_plane, int ldo, void* stream);
 /* Self-attention decode step with the cache append fused in: qkv [B, 3*H*head_dim] (this step's fused
  * projection), K/V caches [B, S, H*head_dim]; writes row `pos` of both caches, then attends over keys 0..pos. */

@@ -33,7 +33,7 @@ class GemmArgs(C.Structure):
         ("out_f32", C.c_void_p), ("out_split", C.c_void_p), ("out_plane", C.c_longlong),
         ("out_split_lo", C.c_int), ("out_ld", C.c_int), ("out_col0", C.c_int),
         ("rows_per_group", C.c_int), ("group_stride", C.c_int), ("group_offset", C.c_int),
-        ("out_kv24", C.c_void_p),
+        ("out_kv24", C.c_void_p), ("out_kv_fmt", C.c_int),
         ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_size_t),
     ]
 
@@ -98,6 +98,7 @@ def lib() -> C.CDLL:
         L.ralf_attention.argtypes = [vp, i, vp, vp, i, vp, i, i, i, i, i, i, f, vp, ll, vp, i, vp]
         L.ralf_attention_decode.argtypes = [vp, i, vp, vp, ll, i, vp, i, i, i, i, i, f, vp, ll, i, vp]
         L.ralf_attention_decode_kv24.argtypes = [vp, i, vp, ll, i, i, i, f, vp, ll, i, vp]
+        L.ralf_attention_decode_kv16.argtypes = [vp, i, vp, ll, i, i, i, f, vp, ll, i, vp]
         L.ralf_attention_decode_append.argtypes = [vp, i, vp, vp, i, i, vp, i, i, i, i, f, vp, ll, i, vp]
         L.ralf_stem_im2col.argtypes = [vp, i, i, i, i, vp, ll, vp]
         L.ralf_im2col.argtypes = [vp, ll, i, i, i, i, i, i, i, i, vp, ll, vp]

@@ -45,7 +45,8 @@ struct GemmEpi {
   int vec_ok;                                      // all strides/offsets allow 16-byte accesses
   int split_lo;                                    // write the lo plane too
   uint8_t* out_kv24;                               // 24-bit K/V cache rows (see ralf_b200.h) or null
-  long long kv24_ld;                               // bytes per cache row (1536)
+  long long kv24_ld;                               // bytes per cache row (1536, or 1088 for the 16-bit format)
+  int kv_fmt;                                      // 24: 24-bit float; 16: 16-bit integers + fp32 scale per (row, head)
 };
 
 // Implicit-GEMM convolution (stride 1, "same" padding): the A operand is never materialised.  k-block kb maps to
@@ -268,7 +269,27 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpi& ep, const uint
                                  __float_as_uint(x[4 * j + 3]));
           epi_row_to_global<8>(stg, lane, mine, gaddr(ep.out_f32 + f32_off + out_row * ep.out_ld + ep.out_col0 + nbase));
         }
-        if (ep.out_kv24) {
+        if (ep.out_kv24 && ep.kv_fmt == 16) {
+          // this 32-column chunk is one head of K or V: offset-binary 16-bit integers + one fp32 scale (ralf_b200.h)
+          float amax = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) amax = fmaxf(amax, fabsf(x[j]));
+          const float inv = amax > 0.f ? 32767.f / amax : 0.f;
+          uint4 mq[4];
+          uint32_t qw[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const uint32_t q0 = static_cast<uint32_t>(__float2int_rn(x[j] * inv) + 32768);
+            const uint32_t q1 = static_cast<uint32_t>(__float2int_rn(x[j + 1] * inv) + 32768);
+            qw[j >> 1] = (q0 & 0xffffu) | (q1 << 16);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mq[j] = make_uint4(qw[4 * j], qw[4 * j + 1], qw[4 * j + 2], qw[4 * j + 3]);
+          const int part = nbase >> 8, cc = nbase & 255;  // K (0) or V (1) half of the 512 columns
+          uint8_t* row = ep.out_kv24 + out_row * ep.kv24_ld;
+          epi_row_to_global<4>(stg, lane, mq, gaddr(row + part * 512 + cc * 2));
+          if (row_ok) *reinterpret_cast<float*>(row + 1024 + part * 32 + (cc >> 5) * 4) = amax * (1.f / 32767.f);
+        } else if (ep.out_kv24) {
           // fp32 rounded to 24 bits: bf16-sized top half (2 B) + one extra mantissa byte -- 3 bytes per value
           uint4 mh[4], ml[2];
           uint32_t hw[16], lb[8];
@@ -879,7 +900,8 @@ static int gemm_dispatch(const RalfGemmArgs* a, const CUtensorMap& ta, int bn, c
   ep.post_relu = a->post_relu;
   ep.split_lo = a->out_split_lo;
   ep.out_kv24 = reinterpret_cast<uint8_t*>(a->out_kv24);
-  ep.kv24_ld = 1536;
+  ep.kv_fmt = a->out_kv_fmt == 16 ? 16 : 24;
+  ep.kv24_ld = ep.kv_fmt == 16 ? 1088 : 1536;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   ep.vec_ok = (a->out_ld % 8 == 0) && (a->out_col0 % 8 == 0) && al16(a->out_f32) && al16(a->out_split) &&
               (a->out_plane % 8 == 0) && al16(a->bias) && al16(a->res) && al16(a->res_split) &&
@@ -1075,6 +1097,7 @@ extern "C" int ralf_gemm_ln(const float* x, int ldx, const float* gamma, const f
   ep.split_lo = a->out_split_lo;
   ep.out_kv24 = nullptr;
   ep.kv24_ld = 0;
+  ep.kv_fmt = 24;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   ep.vec_ok = (a->out_ld % 8 == 0) && (a->out_col0 % 8 == 0) && al16(a->out_f32) && al16(a->out_split) &&
               (a->out_plane % 8 == 0) && al16(a->bias) && al16(a->res) && al16(a->res_split) &&

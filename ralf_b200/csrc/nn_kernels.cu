@@ -720,6 +720,98 @@ attention_decode_kv24_kernel(const float* __restrict__ q, int ldq, const uint8_t
   }
 }
 
+// The same single-pass cross-attention over the 16-bit per-head-scaled K/V cache (ralf_gemm out_kv24, out_kv_fmt = 16):
+// a cache row is 1088 bytes [K 256 x u16 | V 256 x u16 | K scale 8 x f32 | V scale 8 x f32], a value is
+// (u16 - 32768) * scale[head].  29 % fewer bytes than the 24-bit rows on the stream that bounds the decode loop.
+// u16 -> float without a conversion instruction: 0x4B000000 | u16 is the float 2^23 + u16, minus (2^23 + 32768).
+__device__ __forceinline__ float4 kv16_unpack(const uint2 w) {
+  constexpr float BIAS = 8388608.f + 32768.f;
+  float4 f;
+  f.x = __uint_as_float(0x4B000000u | (w.x & 0xffffu)) - BIAS;
+  f.y = __uint_as_float(__byte_perm(w.x, 0x4B000000u, 0x7632)) - BIAS;
+  f.z = __uint_as_float(0x4B000000u | (w.y & 0xffffu)) - BIAS;
+  f.w = __uint_as_float(__byte_perm(w.y, 0x4B000000u, 0x7632)) - BIAS;
+  return f;
+}
+
+__global__ void __launch_bounds__(256)
+attention_decode_kv16_kernel(const float* __restrict__ q, int ldq, const uint8_t* __restrict__ kv, long long kv_bstride,
+                             int Tk, int H, float scale, __nv_bfloat16* __restrict__ out_split, long long out_plane,
+                             int ldo) {
+  constexpr int DH = 32, CPL = 8, KPI = 4, UN = 8, ROW = 1088;
+  pdl_trigger();
+  pdl_wait();
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x;
+  if (h >= H) return;
+  const int kk = lane / CPL, c = lane % CPL;
+  float4 q4 = *reinterpret_cast<const float4*>(q + static_cast<long long>(b) * ldq + h * DH + 4 * c);
+  q4.x *= scale; q4.y *= scale; q4.z *= scale; q4.w *= scale;
+  const uint8_t* base = kv + static_cast<long long>(b) * kv_bstride * ROW;
+  const int o_k = h * 64 + c * 8, o_v = 512 + h * 64 + c * 8, o_ks = 1024 + h * 4, o_vs = 1056 + h * 4;
+  float m = -INFINITY, l = 0.f;
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+  for (int j0 = 0; j0 < Tk; j0 += 32) {
+    uint2 kw[UN], vw[UN];
+    float ksc[UN], vsc[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int j = j0 + u * KPI + kk;
+      kw[u] = vw[u] = make_uint2(0x80008000u, 0x80008000u);  // offset-binary zero
+      ksc[u] = vsc[u] = 0.f;
+      if (j < Tk) {
+        const uint8_t* r = base + static_cast<long long>(j) * ROW;
+        kw[u] = __ldcs(reinterpret_cast<const uint2*>(r + o_k));
+        vw[u] = __ldcs(reinterpret_cast<const uint2*>(r + o_v));
+        ksc[u] = __ldcs(reinterpret_cast<const float*>(r + o_ks));
+        vsc[u] = __ldcs(reinterpret_cast<const float*>(r + o_vs));
+      }
+    }
+    float s[UN];
+    float bm = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const float4 kf = kv16_unpack(kw[u]);
+      float d = q4.x * kf.x + q4.y * kf.y + q4.z * kf.z + q4.w * kf.w;
+#pragma unroll
+      for (int off = CPL >> 1; off >= 1; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+      s[u] = (j0 + u * KPI + kk < Tk) ? d * ksc[u] : -INFINITY;
+      bm = fmaxf(bm, s[u]);
+    }
+#pragma unroll
+    for (int off = CPL; off < 32; off <<= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, off));
+    const float m_new = fmaxf(m, bm);
+    const float corr = __expf(m - m_new);
+    l *= corr;
+    o.x *= corr; o.y *= corr; o.z *= corr; o.w *= corr;
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const float p = __expf(s[u] - m_new);
+      const float4 vf = kv16_unpack(vw[u]);
+      const float pv = p * vsc[u];
+      l += p;
+      o.x = fmaf(pv, vf.x, o.x); o.y = fmaf(pv, vf.y, o.y);
+      o.z = fmaf(pv, vf.z, o.z); o.w = fmaf(pv, vf.w, o.w);
+    }
+    m = m_new;
+  }
+#pragma unroll
+  for (int off = CPL; off < 32; off <<= 1) {
+    o.x += __shfl_xor_sync(0xffffffffu, o.x, off); o.y += __shfl_xor_sync(0xffffffffu, o.y, off);
+    o.z += __shfl_xor_sync(0xffffffffu, o.z, off); o.w += __shfl_xor_sync(0xffffffffu, o.w, off);
+    l += __shfl_xor_sync(0xffffffffu, l, off);
+  }
+  if (kk == 0) {
+    const float inv = 1.f / l;
+    const long long off0 = static_cast<long long>(b) * ldo + h * DH + 4 * c;
+    store_split(out_split, out_plane, off0 + 0, o.x * inv);
+    store_split(out_split, out_plane, off0 + 1, o.y * inv);
+    store_split(out_split, out_plane, off0 + 2, o.z * inv);
+    store_split(out_split, out_plane, off0 + 3, o.w * inv);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // ResNet stem im2col: image fp32 NCHW [B, 4, H, W] -> split rows [B*Ho*Wo, KP] with k = (kh*7+kw)*4+c
 // for the 7x7 / stride 2 / pad 3 convolution (common/image.py:69-77), zero padded to KP columns.
@@ -1413,6 +1505,18 @@ extern "C" int ralf_attention_decode_kv24(const float* q, int ldq, const void* k
   if ((ldq & 3) || (reinterpret_cast<uintptr_t>(kv24) & 15)) return RALF_ERR_ALIGN;
   const cudaError_t e = launch_pdl(attention_decode_kv24_kernel, dim3(B), dim3(32 * H), 0, ST(stream), q, ldq,
                                    reinterpret_cast<const uint8_t*>(kv24), kv_bstride, Tk, H, scale, BF(out_split),
+                                   out_plane, ldo);
+  return set_cuda_error(e != cudaSuccess ? e : cudaGetLastError());
+}
+
+extern "C" int ralf_attention_decode_kv16(const float* q, int ldq, const void* kv16, long long kv_bstride, int Tk, int B,
+                                          int H, float scale, void* out_split, long long out_plane, int ldo,
+                                          void* stream) {
+  if (!q || !kv16 || !out_split) return RALF_ERR_NULL;
+  if (B <= 0 || H != 8 || Tk <= 0) return RALF_ERR_SHAPE;  // row format: 8 heads x 32 (d_model 256)
+  if ((ldq & 3) || (reinterpret_cast<uintptr_t>(kv16) & 15)) return RALF_ERR_ALIGN;
+  const cudaError_t e = launch_pdl(attention_decode_kv16_kernel, dim3(B), dim3(32 * H), 0, ST(stream), q, ldq,
+                                   reinterpret_cast<const uint8_t*>(kv16), kv_bstride, Tk, H, scale, BF(out_split),
                                    out_plane, ldo);
   return set_cuda_error(e != cudaSuccess ? e : cudaGetLastError());
 }

@@ -33,6 +33,11 @@ D = 256
 FUSE_LN = os.environ.get("RALF_FUSE_LN", "0") != "0"
 # Decoder cross-attention K/V cache of the greedy loop in the 24-bit format (3 bytes per value); RALF_KV24=0 keeps fp32.
 KV24 = os.environ.get("RALF_KV24", "1") != "0"
+# Format of that cache: 16 (default) = 16-bit integers with one fp32 scale per (memory token, head), 2.125 bytes per value;
+# 24 = the round-1 24-bit float format (3 bytes).  The decode loop is bound by this stream: 1088 instead of 1536 bytes per
+# memory token and layer.  Accuracy on the reference goldens (profiles/r2_precision_study.json): step logits within 8e-5 of
+# scale (24-bit: 2.5e-5; bf16 would be 5e-3, over the 1e-3 bar), token ids identical.
+KVFMT = 24 if os.environ.get("RALF_KVFMT", "16") == "24" else 16
 # Fused decode-step chains (ralf_decode_chain, csrc/decode_chain.cu): the row-local ops of a decoder-layer step in 3 kernels
 # (LN1+in_proj | out_proj+LN2+cross-q | out_proj+LN3+FFN [+ next layer's LN1+in_proj / final LN + LM head]) instead of 9.
 # Bit-identical to the per-op launches (RALF_CHAIN_ACC=1) but measured SLOWER on B200 (191.8 vs 184.1 ms per 1024-canvas
@@ -418,7 +423,7 @@ class Engine:
         [rows, 1536] rows in the 24-bit format of include/ralf_b200.h (3 bytes per value: the greedy decode loop is bound
         by this stream)."""
         if kv24:
-            return [torch.empty((rows, 1536), dtype=torch.uint8, device=self.dev) for _ in range(NLAYER)]
+            return [torch.empty((rows, ops.KV_ROW_BYTES[KVFMT]), dtype=torch.uint8, device=self.dev) for _ in range(NLAYER)]
         return [torch.empty((rows, 2 * D), dtype=torch.float32, device=self.dev) for _ in range(NLAYER)]
 
     def cross_kv(self, mem_s: torch.Tensor, out: Optional[list] = None, row0: int = 0, kv24: bool = False) -> list:

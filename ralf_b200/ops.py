@@ -133,9 +133,10 @@ def gemm(
             g.splitk_ws, g.splitk_ws_bytes = ws.data_ptr(), nbytes
             global _LAUNCHES
             _LAUNCHES += 1
-    if out_kv24 is not None:  # uint8 [M, 1536] rows of the 24-bit K/V cache (N = 512)
-        assert out_kv24.dtype == torch.uint8 and out_kv24.shape[-1] == 1536 and out_kv24.is_contiguous() and N == 512
+    if out_kv24 is not None:  # uint8 rows of the quantised K/V cache (N = 512): 1536 B = 24-bit, 1088 B = 16-bit + scales
+        assert out_kv24.dtype == torch.uint8 and out_kv24.shape[-1] in KV_ROW_BYTES.values() and out_kv24.is_contiguous() and N == 512
         g.out_kv24 = out_kv24.data_ptr()
+        g.out_kv_fmt = 16 if out_kv24.shape[-1] == KV_ROW_BYTES[16] else 24
         if out_f32 is None and out_split is None:
             g.out_ld = 512  # unused, keeps the alignment checks trivially true
     if stem is not None:
@@ -317,15 +318,21 @@ def attention_decode(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, kv_bstri
     return out
 
 
+KV_ROW_BYTES = {24: 1536, 16: 1088}  # bytes per memory token of the quantised cross-attention K/V cache
+
+
 def attention_decode_kv24(q: torch.Tensor, kv24: torch.Tensor, kv_bstride: int, Tk: int, B: int, H: int, *,
                           out: Optional[torch.Tensor] = None):
-    """Decode-step cross-attention over the 24-bit K/V cache (uint8 [rows, 1536]); returns split [2, B, 256]."""
-    assert kv24.dtype == torch.uint8 and kv24.shape[-1] == 1536 and H == 8
+    """Decode-step cross-attention over the quantised K/V cache (uint8 [rows, 1536]: 24-bit format; [rows, 1088]: 16-bit
+    per-head-scaled format); returns split [2, B, 256]."""
+    assert kv24.dtype == torch.uint8 and kv24.shape[-1] in KV_ROW_BYTES.values() and H == 8
     if out is None:
         out = _split_out(B, H * 32, q.device)
-    check(_lib.lib().ralf_attention_decode_kv24(q.data_ptr(), q.stride(0), kv24.data_ptr(), kv_bstride, Tk, B, H,
-                                                32 ** -0.5, out.data_ptr(), out.stride(0), H * 32, _stream()),
-          "ralf_attention_decode_kv24")
+    L = _lib.lib()
+    fn, name = ((L.ralf_attention_decode_kv16, "ralf_attention_decode_kv16") if kv24.shape[-1] == KV_ROW_BYTES[16]
+                else (L.ralf_attention_decode_kv24, "ralf_attention_decode_kv24"))
+    check(fn(q.data_ptr(), q.stride(0), kv24.data_ptr(), kv_bstride, Tk, B, H, 32 ** -0.5, out.data_ptr(), out.stride(0),
+             H * 32, _stream()), name)
     return out
 
 

@@ -356,7 +356,7 @@ def test_bench_line_assembly_with_stub_measurements():
     assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and d["e2e"]["h2d_bytes_per_step"] == 1075838976
     r = d["roofline"]  # the dominant kernel: the decode cross-attention stream (HBM bound), with the ncu traffic figure
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3
-    assert r["share_of_step"] == round(0.1342 * 360 / 186.0, 4) and r["traffic"] == 837863168 + 3597056
+    assert r["share_of_step"] == round(0.1342 * 360 / 186.0, 4) and r["traffic"] == 593771776 + 6663424
     k = d["roofline_knn"]  # the k-NN half of the metric, timed live
     assert k["bound"] == "hbm" and abs(k["frac"] - k["achieved"] / k["peak"]) < 1e-3 and 0 < k["share_of_step"] < 0.05
     assert "workload" in d["config"] and "model" not in d["config"] and d["gpu_launches"] == 28910

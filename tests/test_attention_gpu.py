@@ -119,6 +119,40 @@ def test_kv24_cache_gemm_and_cross_attention(cuda_device, B, Tk):
     assert (out - ref).abs().max().item() <= 2e-5 * ref.abs().max().item() + 1e-6
 
 
+@pytest.mark.parametrize("B,Tk", [(3, 532), (130, 334), (2, 40)])
+def test_kv16_cache_gemm_and_cross_attention(cuda_device, B, Tk):
+    """16-bit per-head-scaled K/V cache (ralf_gemm out_kv_fmt = 16, the default of the decode loop): every stored value
+    is the offset-binary 16-bit integer rint(x * 32767 / amax) + 32768 of the GEMM's fp32 result x, amax = the largest
+    magnitude of its (row, head); the stored scale is amax / 32767; and the kv16 decode kernel equals float64 attention
+    over the DEQUANTISED values.  Also bounds the format's own error: |dequant - x| <= amax / 65534 (half a step)."""
+    from ralf_b200 import ops
+
+    H, dh, D = 8, 32, 256
+    g = torch.Generator(device=cuda_device).manual_seed(B + Tk)
+    mem = ops.split_bf16(torch.randn(B * Tk, D, device=cuda_device, generator=g))
+    w = ops.split_bf16(torch.randn(2 * D, D, device=cuda_device, generator=g) / 16)
+    bias = torch.randn(2 * D, device=cuda_device, generator=g)
+    ref32, _ = ops.gemm(mem, w, bias=bias)
+    kv16 = torch.empty(B * Tk, ops.KV_ROW_BYTES[16], dtype=torch.uint8, device=cuda_device)
+    ops.gemm(mem, w, bias=bias, want_f32=False, out_kv24=kv16)
+    qv = (kv16[:, :1024].contiguous().view(torch.int16).to(torch.int32) & 0xFFFF) - 32768      # [rows, 512]: K | V
+    sc = kv16[:, 1024:].contiguous().view(torch.float32)                                         # [rows, 16]: K heads | V heads
+    x = ref32.view(B * Tk, 16, 32)
+    amax = x.abs().amax(dim=-1)
+    assert torch.equal(sc, amax * (1.0 / 32767.0))
+    want_q = torch.round(x * (32767.0 / amax)[..., None]).to(torch.int32).view(B * Tk, 512)
+    assert (qv - want_q).abs().max().item() <= 1  # rint of a product rounded in fp32: at most one step apart, almost always 0
+    assert (qv != want_q).float().mean().item() < 1e-3
+    deq = (qv.view(B * Tk, 16, 32).float() * sc[..., None]).view(B * Tk, 512)
+    assert ((deq - ref32).abs() <= (amax / 65534.0 * 1.01 + 1e-12)[..., None].expand(-1, -1, 32).reshape(B * Tk, 512)).all()
+    q = torch.randn(B, D, device=cuda_device, generator=g) * 2
+    out = ops.unsplit(ops.attention_decode_kv24(q, kv16, Tk, Tk, B, H)).double()
+    ref = _ref_decode(q, deq[:, :D], deq[:, D:], B, H, dh, Tk)
+    assert (out - ref).abs().max().item() <= 2e-5 * ref.abs().max().item() + 1e-6
+    full = _ref_decode(q, ref32[:, :D], ref32[:, D:], B, H, dh, Tk)  # vs attention over the unquantised fp32 K/V
+    assert (out - full).abs().max().item() <= 2e-4 * full.abs().max().item()
+
+
 @pytest.mark.parametrize("B,Tq,Tk,H", [(3, 256, 16, 8), (2, 330, 16, 8), (5, 100, 7, 8), (130, 256, 16, 8), (1, 31, 1, 4)])
 def test_fusion_attention_fewkeys_matches_fp64(cuda_device, B, Tq, Tk, H):
     """Fusion Attention shape class (common/attention.py:49-71: 8 heads x 64, image tokens over the 16 retrieved layouts):
