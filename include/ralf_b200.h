@@ -118,7 +118,7 @@ typedef struct RalfGemmArgs {
                        * the accuracy class of the bf16x3 product that made it) -- 3 instead of 4 bytes per element on
                        * the stream the decode loop is bound by */
   int out_kv_fmt;     /* 0 / 24: the 24-bit format above.  16: rows of 1088 bytes
-                       * [K 256 x u16 | V 256 x u16 | K scale 8 x f32 | V scale 8 x f32]: per (row, head) the 32 values are
+                       * [K 256 x u16 | V 256 x u16 | 8 x (K scale, V scale) f32]: per (row, head) the 32 values are
                        * stored as offset-binary 16-bit integers q + 32768, q = rint(x * 32767 / amax), next to the scale
                        * amax / 32767 -- 2.125 bytes per element; error 2^-16 of the head's largest value (measured on the
                        * reference goldens: step logits within 8e-5 of scale, token ids identical;

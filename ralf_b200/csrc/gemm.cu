@@ -288,7 +288,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpi& ep, const uint
           const int part = nbase >> 8, cc = nbase & 255;  // K (0) or V (1) half of the 512 columns
           uint8_t* row = ep.out_kv24 + out_row * ep.kv24_ld;
           epi_row_to_global<4>(stg, lane, mq, gaddr(row + part * 512 + cc * 2));
-          if (row_ok) *reinterpret_cast<float*>(row + 1024 + part * 32 + (cc >> 5) * 4) = amax * (1.f / 32767.f);
+          if (row_ok) *reinterpret_cast<float*>(row + 1024 + (cc >> 5) * 8 + part * 4) = amax * (1.f / 32767.f);
         } else if (ep.out_kv24) {
           // fp32 rounded to 24 bits: bf16-sized top half (2 B) + one extra mantissa byte -- 3 bytes per value
           uint4 mh[4], ml[2];

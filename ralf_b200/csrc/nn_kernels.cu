@@ -721,8 +721,8 @@ attention_decode_kv24_kernel(const float* __restrict__ q, int ldq, const uint8_t
 }
 
 // The same single-pass cross-attention over the 16-bit per-head-scaled K/V cache (ralf_gemm out_kv24, out_kv_fmt = 16):
-// a cache row is 1088 bytes [K 256 x u16 | V 256 x u16 | K scale 8 x f32 | V scale 8 x f32], a value is
-// (u16 - 32768) * scale[head].  29 % fewer bytes than the 24-bit rows on the stream that bounds the decode loop.
+// a cache row is 1088 bytes [K 256 x u16 | V 256 x u16 | 8 x (K scale, V scale) f32 pairs], a value is
+// (u16 - 32768) * scale[head] (the two scales of a head sit together: one 8-byte load per key and lane).  29 % fewer bytes than the 24-bit rows on the stream that bounds the decode loop.
 // u16 -> float without a conversion instruction: 0x4B000000 | u16 is the float 2^23 + u16, minus (2^23 + 32768).
 __device__ __forceinline__ float4 kv16_unpack(const uint2 w) {
   constexpr float BIAS = 8388608.f + 32768.f;
@@ -748,7 +748,7 @@ attention_decode_kv16_kernel(const float* __restrict__ q, int ldq, const uint8_t
   float4 q4 = *reinterpret_cast<const float4*>(q + static_cast<long long>(b) * ldq + h * DH + 4 * c);
   q4.x *= scale; q4.y *= scale; q4.z *= scale; q4.w *= scale;
   const uint8_t* base = kv + static_cast<long long>(b) * kv_bstride * ROW;
-  const int o_k = h * 64 + c * 8, o_v = 512 + h * 64 + c * 8, o_ks = 1024 + h * 4, o_vs = 1056 + h * 4;
+  const int o_k = h * 64 + c * 8, o_v = 512 + h * 64 + c * 8, o_s = 1024 + h * 8;
   float m = -INFINITY, l = 0.f;
   float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
@@ -764,8 +764,9 @@ attention_decode_kv16_kernel(const float* __restrict__ q, int ldq, const uint8_t
         const uint8_t* r = base + static_cast<long long>(j) * ROW;
         kw[u] = __ldcs(reinterpret_cast<const uint2*>(r + o_k));
         vw[u] = __ldcs(reinterpret_cast<const uint2*>(r + o_v));
-        ksc[u] = __ldcs(reinterpret_cast<const float*>(r + o_ks));
-        vsc[u] = __ldcs(reinterpret_cast<const float*>(r + o_vs));
+        const float2 sc2 = __ldcs(reinterpret_cast<const float2*>(r + o_s));
+        ksc[u] = sc2.x;
+        vsc[u] = sc2.y;
       }
     }
     float s[UN];

@@ -136,7 +136,8 @@ def test_kv16_cache_gemm_and_cross_attention(cuda_device, B, Tk):
     kv16 = torch.empty(B * Tk, ops.KV_ROW_BYTES[16], dtype=torch.uint8, device=cuda_device)
     ops.gemm(mem, w, bias=bias, want_f32=False, out_kv24=kv16)
     qv = (kv16[:, :1024].contiguous().view(torch.int16).to(torch.int32) & 0xFFFF) - 32768      # [rows, 512]: K | V
-    sc = kv16[:, 1024:].contiguous().view(torch.float32)                                         # [rows, 16]: K heads | V heads
+    sc = kv16[:, 1024:].contiguous().view(torch.float32).view(-1, 8, 2)                          # [rows, head, (K, V)]
+    sc = torch.cat([sc[:, :, 0], sc[:, :, 1]], dim=1).contiguous()                               # [rows, 16]: K heads | V heads
     x = ref32.view(B * Tk, 16, 32)
     amax = x.abs().amax(dim=-1)
     assert torch.equal(sc, amax * (1.0 / 32767.0))
