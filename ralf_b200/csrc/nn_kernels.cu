@@ -1516,6 +1516,9 @@ extern "C" int ralf_attention_decode_kv16(const float* q, int ldq, const void* k
   if (!q || !kv16 || !out_split) return RALF_ERR_NULL;
   if (B <= 0 || H != 8 || Tk <= 0) return RALF_ERR_SHAPE;  // row format: 8 heads x 32 (d_model 256)
   if ((ldq & 3) || (reinterpret_cast<uintptr_t>(kv16) & 15)) return RALF_ERR_ALIGN;
+  // (A lane-per-key variant -- whole 64-byte head rows per lane, no shuffles, private online softmax -- was measured in
+  // round 2: 0.155 ms against 0.105 ms for this one; 32 different rows per load instruction cost more L1 wavefronts than
+  // the shuffles it saved.  Removed; profiles/r2_kv16_ncu.md.)
   const cudaError_t e = launch_pdl(attention_decode_kv16_kernel, dim3(B), dim3(32 * H), 0, ST(stream), q, ldq,
                                    reinterpret_cast<const uint8_t*>(kv16), kv_bstride, Tk, H, scale, BF(out_split),
                                    out_plane, ldo);

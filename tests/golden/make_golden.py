@@ -94,6 +94,60 @@ def run(model, tok, name, B, H, W, seed, is_ralf):
     print(name, {k: getattr(v, "shape", None) for k, v in out.items()})
 
 
+def run_b32(model, tok, name="ralf_cgl_b32_128", B=32, H=128, W=128, seed=17, full=4):
+    """SURVEY.md 8c asks for goldens at B in {1, 2, 32}: a 32-canvas batch through the UNMODIFIED reference (preprocess ->
+    memory -> teacher-forced logits -> sample()).  To keep the fixture small, memory / logits are stored in full for the
+    first `full` canvases only; for every canvas the greedy token ids, the decoded layout, and per (canvas, position)
+    summaries of the logits (max, log-sum-exp, arg-max) and per-row norms of the memory are stored."""
+    import copy
+
+    torch.manual_seed(0)
+    sd = synth.synth_state_dict(schema_of(model), seed=seed)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    batch = synth.synth_batch(B, H, W, 10, 16, tok.N_label, seed=seed)
+    out = {}
+    with torch.no_grad():
+        inputs, targets = model.preprocess(copy.deepcopy(batch))
+        out["seq_in"], out["targets"] = inputs["seq"].numpy(), targets["seq"].numpy()
+        out["tgt_key_padding_mask"] = inputs["tgt_key_padding_mask"].numpy()
+        out["seq_layout_const"] = inputs["seq_layout_const"].numpy()
+        out["seq_layout_const_pad_mask"] = inputs["seq_layout_const_pad_mask"].numpy()
+        mem = model._encode_into_memory(copy.deepcopy(inputs))["memory"]
+        out["memory_head"] = mem[:full].numpy()
+        out["memory_row_norm"] = mem.norm(dim=-1).numpy()
+        outputs, losses = model.train_loss(copy.deepcopy(inputs), targets)
+        lg = outputs["logits"]
+        out["logits_head"] = lg[:full].numpy()
+        out["logits_max"], out["logits_lse"] = lg.max(-1).values.numpy(), torch.logsumexp(lg, -1).numpy()
+        out["logits_argmax"] = lg.argmax(-1).numpy()
+        out["nll_loss"] = losses["nll_loss"].numpy()
+        from image2layout.train.helpers.task import get_condition
+
+        cond, _ = get_condition(copy.deepcopy(batch), "uncond", tok)
+        res = model.sample(cond=cond, sampling_cfg=rb.DictConfig(name="deterministic"), cond_type="uncond",
+                           return_violation=False)
+        for k in ["label", "mask", "center_x", "center_y", "width", "height"]:
+            out["gen_" + k] = res[k].numpy()
+        # raw greedy token ids, replaying the loop of retrieval_augmented_autoreg.py:271-297 (as run() does)
+        enc_in, _ = model._create_encoder_inputs(cond)
+        enc_in["retrieved"] = {k: v.type_as(cond.image) for k, v in enc_in["retrieved"].items() if torch.is_tensor(v)}
+        memory = model._encode_into_memory(enc_in)
+        ids = model.special_token_ids
+        inp = torch.full((B, 1), ids["bos"])
+        for i in range(tok.max_token_length):
+            lgi = model.decoder(tgt=inp, tgt_key_padding_mask=(inp == ids["pad"]), is_causal=True, **memory)[:, i].clone()
+            lgi[:, ~tok.token_mask[i]] = -float("inf")
+            inp = torch.cat([inp, lgi.argmax(dim=1, keepdim=True)], dim=1)
+        out["gen_seq"] = inp[:, 1:].numpy()
+        dec = tok.decode(inp[:, 1:])
+        assert all(torch.equal(dec[k], res[k]) for k in ["label", "mask"]), "sample() and replay disagree"
+    out["meta"] = np.array(json.dumps({"B": B, "H": H, "W": W, "seed": seed, "E": 10, "K": 16, "dataset": "cgl", "full": full,
+                                       "special": {k: int(v) for k, v in ids.items()}}))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, {k: getattr(v, "shape", None) for k, v in out.items()})
+
+
 TASKS = ["c", "cwh", "partial", "refinement"]
 
 
@@ -895,6 +949,9 @@ def main():
     if "--max-length-only" in sys.argv:
         run_max_length()
         return
+    if "--b32-only" in sys.argv:
+        run_b32(ralf, tok)
+        return
     if "--saliency-only" in sys.argv:
         run_coarse_saliency()
         return
@@ -921,6 +978,7 @@ def main():
     with open(os.path.join(OUT, "schema_autoreg_cgl.json"), "w") as f:
         json.dump(schema_of(ar), f)
     run(ar, tok2, "autoreg_cgl_350x240", B=1, H=350, W=240, seed=3, is_ralf=False)
+    run_b32(rb.make_ralf("cgl")[0], tok)
 
 
 if __name__ == "__main__":

@@ -241,3 +241,31 @@ def test_fused_decode_chain_equals_per_op_decode(cuda_device, monkeypatch, B, Ml
     err = np.abs(a - b).max() / np.abs(b).max()
     assert err <= 1e-5, err
     print(f"B={B}: fused-vs-per-op step logits {err:.2e}")
+
+
+def test_engine_matches_reference_golden_at_batch_32(cuda_device):
+    """B = 32 golden of the UNMODIFIED reference (fixture layout: test_oracle_golden.py): memory and logits of
+    the first 4 canvases within 1e-3 of scale, logit summaries of all 32 within 1e-3, greedy token ids and decoded layouts
+    of all 32 bit-exact."""
+    z, meta = helpers.load_golden("ralf_cgl_b32_128")
+    eng = _engine("ralf_cgl", meta["seed"], True, cuda_device)
+    batch = helpers.synth_batch(meta)
+    tok = helpers.make_tokenizer()
+    B, full = meta["B"], meta["full"]
+    mem, mem_s = eng.encode(helpers.image4(batch), batch["retrieved"], torch.from_numpy(z["seq_layout_const"]),
+                            torch.from_numpy(z["seq_layout_const_pad_mask"]))
+    assert _relerr(mem[:full].cpu().numpy(), z["memory_head"]) < LOGIT_RTOL
+    assert _relerr(mem.norm(dim=-1).cpu().numpy(), z["memory_row_norm"]) < LOGIT_RTOL
+    Mlen = mem.shape[1]
+    lg = eng.decoder_logits(torch.from_numpy(z["seq_in"]), torch.from_numpy(z["tgt_key_padding_mask"]), mem_s, B, Mlen)
+    assert _relerr(lg[:full].cpu().numpy(), z["logits_head"]) < LOGIT_RTOL
+    scale = np.abs(z["logits_head"]).max()
+    assert np.abs(lg.max(-1).values.cpu().numpy() - z["logits_max"]).max() <= LOGIT_RTOL * scale
+    assert np.abs(torch.logsumexp(lg, -1).cpu().numpy() - z["logits_lse"]).max() <= LOGIT_RTOL * np.abs(z["logits_lse"]).max()
+    sp = meta["special"]
+    seq = eng.generate(mem_s, B, Mlen, tok.token_mask, sp["bos"], sp["pad"], tok.max_token_length)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(seq.cpu().numpy(), z["gen_seq"])
+    dec = tok.decode(seq.cpu())
+    for k in ["label", "mask", "center_x", "center_y", "width", "height"]:
+        np.testing.assert_array_equal(dec[k].numpy(), z["gen_" + k])
