@@ -142,8 +142,8 @@ int ralf_conv_gemm(const RalfGemmArgs* args, int B, int H, int W, int C, int KH,
  * k = kh'*64 + kw'*16 + (dy*2+dx)*4 + c, args->M = B*Ho*Wo (Ho = H/2, Wo = W/2 <= 128), args->K = 256. */
 int ralf_stem_s2d(const float* img, int B, int H, int W, void* out, long long out_plane, void* stream);
 int ralf_stem_gemm(const RalfGemmArgs* args, int B, int Ho, int Wo, void* stream);
-/* D = LayerNorm(x)[M,256] . W^T with the LayerNorm computed inside the GEMM (decode path: M <= 128, K = 256,
- * npass = 3).  x fp32 [M, 256] (row stride ldx); `args` supplies W and the epilogue (its A fields are ignored).
+/* D = LayerNorm(x)[M,256] . W^T with the LayerNorm computed inside the GEMM (decode path: K = 256,
+ * npass = 3; every (n-tile, 128-row tile) CTA normalises its rows).  x fp32 [M, 256] (row stride ldx); `args` supplies W and the epilogue (its A fields are ignored).
  * Replaces nn.LayerNorm + nn.Linear pairs of the pre-LN decoder layer / LM head (common/common.py:26-41). */
 int ralf_gemm_ln(const float* x, int ldx, const float* gamma, const float* beta, float eps,
                  const RalfGemmArgs* args, void* stream);

@@ -27,8 +27,9 @@ from . import ops
 NHEAD = 8
 NLAYER = 6
 D = 256
-# LayerNorm folded into the consuming decode GEMM (ralf_gemm_ln) is OFF by default: measured on B200 (profiles/r1_notes.md) the
-# in-kernel row normalisation costs more than the separate 4 us LayerNorm launch it removes (1698 vs 2162 layouts/s).
+# LayerNorm folded into the consuming decode GEMM (ralf_gemm_ln) is OFF by default: measured on B200 the in-kernel row
+# normalisation costs more than the separate 5 us LayerNorm launch it removes (round 1, B <= 128: 1698 vs 2162 layouts/s;
+# round 2, generalised to the bench batch of 1024: 188.2 vs 168.5 ms per step).
 # RALF_FUSE_LN=1 switches it on for A/B runs.
 FUSE_LN = os.environ.get("RALF_FUSE_LN", "0") != "0"
 # Decoder cross-attention K/V cache of the greedy loop in the 24-bit format (3 bytes per value); RALF_KV24=0 keeps fp32.
@@ -227,7 +228,7 @@ class Engine:
 
     def _gemm_ln(self, x, ln_name, name, **kw):
         """LayerNorm fused into the consuming GEMM (M <= 128 rows: the decode path); falls back to two kernels above."""
-        if x.shape[0] > 128 or self.npass != 3 or not FUSE_LN:
+        if self.npass != 3 or not FUSE_LN:
             _, h = self._ln(x, ln_name)
             return self._gemm(h, name, **kw)
         return ops.gemm_ln(x, self.w[ln_name + ".g"], self.w[ln_name + ".beta"], self.w[name + ".w"],

@@ -162,3 +162,22 @@ def test_gemm_splitk_matches_fp64(cuda_device, M, N, K):
     out2 = torch.empty_like(out)
     ops.gemm(a, w, out_f32=out2[:, :N], splitk=True)
     assert torch.equal(out[:, :N], out2[:, :N])  # deterministic
+
+
+@pytest.mark.parametrize("M,N,act", [(5, 256, None), (128, 768, None), (300, 1024, "relu"), (1024, 768, None), (1030, 519, None)])
+def test_gemm_with_fused_layernorm_matches_fp64(cuda_device, M, N, act):
+    """ralf_gemm_ln (LayerNorm computed inside the GEMM's A-operand prologue, one CTA per n-tile x 128-row tile; opt-in for
+    the decode chain via RALF_FUSE_LN=1) against float64 LayerNorm + Linear, including partial row tiles and a ragged N."""
+    from ralf_b200 import ops
+
+    g = torch.Generator(device=cuda_device).manual_seed(M + N)
+    x = torch.randn(M, 256, device=cuda_device, generator=g) * 3 + 0.5
+    gamma = torch.randn(256, device=cuda_device, generator=g)
+    beta = torch.randn(256, device=cuda_device, generator=g)
+    w = torch.randn(N, 256, device=cuda_device, generator=g) / 16
+    bias = torch.randn(N, device=cuda_device, generator=g)
+    out, _ = ops.gemm_ln(x, gamma, beta, ops.split_bf16(w), bias=bias, act=act)
+    ref = torch.nn.functional.layer_norm(x.double(), (256,), gamma.double(), beta.double(), 1e-5) @ w.double().T + bias.double()
+    if act == "relu":
+        ref = ref.relu()
+    assert (out.double() - ref).abs().max().item() <= 3e-5 * ref.abs().max().item()
