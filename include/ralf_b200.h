@@ -320,16 +320,17 @@ int ralf_dropout(const float* in_f32, const void* in_split, long long in_plane, 
 int ralf_dropout_mask(const unsigned long long* seed, unsigned int site, float p, long long total, unsigned char* out,
                       void* stream);
 /* ralf_attention with dropout on the attention probabilities: O = (softmax(S) o M / (1-p)) V; mask element index
- * ((b*H + h)*Tq + t)*Tk + j.  Always the CUDA-core kernel. */
+ * ((b*H + h)*Tq + t)*Tk + j.  Always the CUDA-core kernel.  lse_out (optional, p > 0 only): B*H*Tq floats, the row
+ * log-sum-exp, which ralf_attention_bwd_dropout(lse_given = 1) then reads from lse_ws instead of recomputing it. */
 int ralf_attention_dropout(const float* q, int ldq, const float* k, const float* v, int ldk,
                            const unsigned char* key_padding_mask, int B, int H, int Tq, int Tk, int head_dim, int causal,
                            float scale, void* out_split, long long out_plane, float* out_f32, int ldo,
-                           const unsigned long long* seed, unsigned int site, float p, void* stream);
+                           const unsigned long long* seed, unsigned int site, float p, float* lse_out, void* stream);
 int ralf_attention_bwd_dropout(const float* q, int ldq, const float* k, const float* v, int ldk,
                                const unsigned char* key_padding_mask, int B, int H, int Tq, int Tk, int head_dim,
                                int causal, float scale, const void* o_split, long long o_plane, const float* dO, int ldo,
                                float* lse_ws, float* delta_ws, float* dq, int lddq, float* dk, float* dv, int lddk,
-                               const unsigned long long* seed, unsigned int site, float p, void* stream);
+                               const unsigned long long* seed, unsigned int site, float p, int lse_given, void* stream);
 /* Backward of ralf_attention (same addressing); lse_ws / delta_ws: B*H*Tq floats each. */
 int ralf_attention_bwd(const float* q, int ldq, const float* k, const float* v, int ldk,
                        const unsigned char* key_padding_mask, int B, int H, int Tq, int Tk, int head_dim, int causal,

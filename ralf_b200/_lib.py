@@ -124,8 +124,8 @@ def lib() -> C.CDLL:
         L.ralf_attention_bwd.argtypes = [vp, i, vp, vp, i, vp, i, i, i, i, i, i, f, vp, ll, vp, i, vp, vp, vp, i, vp, vp, i, vp]
         u32 = C.c_uint
         L.ralf_attention_bwd_dropout.argtypes = [vp, i, vp, vp, i, vp, i, i, i, i, i, i, f, vp, ll, vp, i, vp, vp, vp, i, vp, vp,
-                                                 i, vp, u32, f, vp]
-        L.ralf_attention_dropout.argtypes = [vp, i, vp, vp, i, vp, i, i, i, i, i, i, f, vp, ll, vp, i, vp, u32, f, vp]
+                                                 i, vp, u32, f, i, vp]
+        L.ralf_attention_dropout.argtypes = [vp, i, vp, vp, i, vp, i, i, i, i, i, i, f, vp, ll, vp, i, vp, u32, f, vp, vp]
         L.ralf_dropout.argtypes = [vp, vp, ll, vp, ll, vp, u32, f, vp, vp, ll, vp]
         L.ralf_dropout_mask.argtypes = [vp, u32, f, ll, vp, vp]
         L.ralf_ce_label_smooth_bwd.argtypes = [vp, i, vp, i, i, f, ll, vp, f, vp, i, vp]

@@ -332,9 +332,14 @@ def linear_res(tape: Tape, ps: ParamStore, x: Node, wname: str, bias: Optional[s
     return dropout_add(tape, linear(tape, ps, x, wname, bias), res)
 
 
-def _attention_bwd(q, ldq, k, v, ldk, mask, B, H, Tq, Tk, dh, causal, o_split, dO, dq, lddq, dk, dv, lddk, dropout=None):
+def _attention_bwd(q, ldq, k, v, ldk, mask, B, H, Tq, Tk, dh, causal, o_split, dO, dq, lddq, dk, dv, lddk, dropout=None,
+                   lse=None):
+    """``lse``: the row log-sum-exp saved by the forward kernel (training with dropout): the dQ kernel then sweeps the keys
+    once instead of twice."""
     dev = dO.device
-    lse = torch.empty(B * H * Tq, dtype=torch.float32, device=dev)
+    lse_given = lse is not None
+    if lse is None:
+        lse = torch.empty(B * H * Tq, dtype=torch.float32, device=dev)
     delta = torch.empty(B * H * Tq, dtype=torch.float32, device=dev)
     if dropout is not None:
         seed, site, p = dropout
@@ -342,7 +347,7 @@ def _attention_bwd(q, ldq, k, v, ldk, mask, B, H, Tq, Tk, dh, causal, o_split, d
                                               dh, int(causal), dh ** -0.5, o_split.data_ptr(), o_split.stride(0),
                                               dO.data_ptr(), dO.stride(0), lse.data_ptr(), delta.data_ptr(), dq.data_ptr(),
                                               lddq, dk.data_ptr(), dv.data_ptr(), lddk, seed.data_ptr(), site, p,
-                                              _stream()), "ralf_attention_bwd_dropout")
+                                              int(lse_given), _stream()), "ralf_attention_bwd_dropout")
         return
     check(_L().ralf_attention_bwd(q.data_ptr(), ldq, k.data_ptr(), v.data_ptr(), ldk, _ptr(mask), B, H, Tq, Tk, dh,
                                   int(causal), dh ** -0.5, o_split.data_ptr(), o_split.stride(0), dO.data_ptr(),
@@ -357,8 +362,9 @@ def self_attention(tape: Tape, qkv: Node, B: int, T: int, H: int, dh: int, *, ma
     x = qkv.f32
     dr = tape.drop
     dropout = (dr.seed, dr.next_site(), dr.p) if dr is not None else None  # attention-probability dropout
+    lse = torch.empty(B * H * T, dtype=torch.float32, device=x.device) if (dropout is not None and dropout[2] > 0) else None
     out = ops.attention(x[:, :Dm], x[:, Dm:2 * Dm], x[:, 2 * Dm:], B, H, T, T, dh, mask=mask, causal=causal,
-                        dropout=dropout)
+                        dropout=dropout, lse_out=lse)
     y = Node(qkv.M, Dm, None, out)
 
     def bwd() -> None:
@@ -366,7 +372,7 @@ def self_attention(tape: Tape, qkv: Node, B: int, T: int, H: int, dh: int, *, ma
             return
         d = torch.empty_like(x)
         _attention_bwd(x[:, :Dm], x.stride(0), x[:, Dm:2 * Dm], x[:, 2 * Dm:], x.stride(0), mask, B, H, T, T, dh, causal,
-                       out, y.grad, d[:, :Dm], d.stride(0), d[:, Dm:2 * Dm], d[:, 2 * Dm:], d.stride(0), dropout=dropout)
+                       out, y.grad, d[:, :Dm], d.stride(0), d[:, Dm:2 * Dm], d[:, 2 * Dm:], d.stride(0), dropout=dropout, lse=lse)
         accumulate(qkv, d)
         y.grad = None
 
@@ -382,7 +388,8 @@ def cross_attention(tape: Tape, q: Node, kv: Node, kcol: int, vcol: int, B: int,
     kk, vv = kv.f32[:, kcol:kcol + Dm], kv.f32[:, vcol:vcol + Dm]
     dr = tape.drop if use_dropout else None
     dropout = (dr.seed, dr.next_site(), dr.p) if dr is not None else None
-    out = ops.attention(q.f32, kk, vv, B, H, Tq, Tk, dh, dropout=dropout)
+    lse = torch.empty(B * H * Tq, dtype=torch.float32, device=q.f32.device) if (dropout is not None and dropout[2] > 0) else None
+    out = ops.attention(q.f32, kk, vv, B, H, Tq, Tk, dh, dropout=dropout, lse_out=lse)
     y = Node(q.M, Dm, None, out)
 
     def bwd() -> None:
@@ -392,7 +399,7 @@ def cross_attention(tape: Tape, q: Node, kv: Node, kcol: int, vcol: int, B: int,
         dq = torch.empty_like(q.f32)
         g = torch.empty_like(kv.f32)
         _attention_bwd(q.f32, q.f32.stride(0), kk, vv, kv.f32.stride(0), None, B, H, Tq, Tk, dh, False, out, y.grad, dq,
-                       dq.stride(0), g[:, kcol:kcol + Dm], g[:, vcol:vcol + Dm], g.stride(0), dropout=dropout)
+                       dq.stride(0), g[:, kcol:kcol + Dm], g[:, vcol:vcol + Dm], g.stride(0), dropout=dropout, lse=lse)
         accumulate(kv, g)
         accumulate(q, dq)
         y.grad = None

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(128)
 attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, const float* __restrict__ v,
                  int ldk, const unsigned char* __restrict__ mask, int Tq, int Tk, int causal, float scale,
                  __nv_bfloat16* __restrict__ out_split, long long out_plane, float* __restrict__ out_f32, int ldo,
-                 DropArgs da) {
+                 DropArgs da, float* __restrict__ lse_out) {
   constexpr int KT = 64;
   __shared__ __align__(16) float ks[KT][DH];
   __shared__ __align__(16) float vs[KT][DH];
@@ -172,6 +172,8 @@ attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__
     }
   }
   if (!active) return;
+  // training: the log-sum-exp of the row, so that the backward (attn_bwd_dq_kernel) need not sweep the keys twice
+  if (lse_out) lse_out[(static_cast<long long>(b) * gridDim.y + h) * Tq + t] = mrun + __logf(lrun);
   const float inv = 1.f / lrun;
   const long long orow = (static_cast<long long>(b) * Tq + t) * ldo + h * DH;
 #pragma unroll
@@ -1378,7 +1380,7 @@ extern "C" int ralf_layernorm(const float* x, long long in_ld, const float* gamm
 static int attention_impl(const float* q, int ldq, const float* k, const float* v, int ldk,
                           const unsigned char* key_padding_mask, int B, int H, int Tq, int Tk, int head_dim, int causal,
                           float scale, void* out_split, long long out_plane, float* out_f32, int ldo, DropArgs da,
-                          void* stream) {
+                          void* stream, float* lse_out = nullptr) {
   if (!q || !k || !v) return RALF_ERR_NULL;
   if (B <= 0 || H <= 0 || Tq <= 0 || Tk <= 0 || (head_dim != 32 && head_dim != 64)) return RALF_ERR_SHAPE;
   if ((ldq & 3) || (ldk & 3)) return RALF_ERR_ALIGN;
@@ -1427,10 +1429,10 @@ static int attention_impl(const float* q, int ldq, const float* k, const float* 
   dim3 grid((Tq + threads - 1) / threads, H, B);
   if (head_dim == 32)
     attention_kernel<32><<<grid, threads, 0, ST(stream)>>>(q, ldq, k, v, ldk, key_padding_mask, Tq, Tk, causal, scale,
-                                                          BF(out_split), out_plane, out_f32, ldo, da);
+                                                          BF(out_split), out_plane, out_f32, ldo, da, lse_out);
   else
     attention_kernel<64><<<grid, threads, 0, ST(stream)>>>(q, ldq, k, v, ldk, key_padding_mask, Tq, Tk, causal, scale,
-                                                          BF(out_split), out_plane, out_f32, ldo, da);
+                                                          BF(out_split), out_plane, out_f32, ldo, da, lse_out);
   return set_cuda_error(cudaGetLastError());
 }
 
@@ -1445,11 +1447,13 @@ extern "C" int ralf_attention(const float* q, int ldq, const float* k, const flo
 extern "C" int ralf_attention_dropout(const float* q, int ldq, const float* k, const float* v, int ldk,
                                       const unsigned char* key_padding_mask, int B, int H, int Tq, int Tk, int head_dim,
                                       int causal, float scale, void* out_split, long long out_plane, float* out_f32,
-                                      int ldo, const unsigned long long* seed, unsigned int site, float p, void* stream) {
+                                      int ldo, const unsigned long long* seed, unsigned int site, float p, float* lse_out,
+                                      void* stream) {
   if (!seed) return RALF_ERR_NULL;
   if (!(p >= 0.f && p < 1.f)) return RALF_ERR_SHAPE;
+  if (lse_out && !(p > 0.f)) return RALF_ERR_SHAPE;  // p = 0 may take a kernel that does not produce the log-sum-exp
   return attention_impl(q, ldq, k, v, ldk, key_padding_mask, B, H, Tq, Tk, head_dim, causal, scale, out_split, out_plane,
-                        out_f32, ldo, make_drop_args(seed, site, p), stream);
+                        out_f32, ldo, make_drop_args(seed, site, p), stream, lse_out);
 }
 
 static int attention_decode_impl(const float* q, int ldq, const float* k, const float* v, long long kv_bstride, int ldk,

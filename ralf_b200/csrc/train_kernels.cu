@@ -220,7 +220,8 @@ __global__ void __launch_bounds__(128)
 attn_bwd_dq_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, const float* __restrict__ v, int ldk,
                    const unsigned char* __restrict__ mask, int Tq, int Tk, int causal, float scale,
                    const __nv_bfloat16* __restrict__ o_split, long long o_plane, const float* __restrict__ dO, int ldo,
-                   float* __restrict__ lse, float* __restrict__ delta, float* __restrict__ dq, int lddq, DropArgs da) {
+                   float* __restrict__ lse, float* __restrict__ delta, float* __restrict__ dq, int lddq, DropArgs da,
+                   int lse_given) {
   constexpr int KT = 64;
   __shared__ __align__(16) float ks[KT][DH];
   __shared__ __align__(16) float vs[KT][DH];
@@ -248,8 +249,11 @@ attn_bwd_dq_kernel(const float* __restrict__ q, int ldq, const float* __restrict
     delta[(static_cast<long long>(b) * H + h) * Tq + t] = dl;
   }
   const int kmax = causal ? min(Tk, (blockIdx.x + 1) * static_cast<int>(blockDim.x)) : Tk;
-  // pass 0: log-sum-exp of this query's scores (recomputed here so the forward kernel need not save it)
-  {
+  // pass 0: log-sum-exp of this query's scores -- skipped when the forward kernel saved it (lse_given: training with
+  // dropout always runs attention_kernel, which writes it; halves this kernel's sweep over the keys)
+  if (lse_given) {
+    if (active) my_lse = lse[(static_cast<long long>(b) * H + h) * Tq + t];
+  } else {
     float mrun = -INFINITY, lrun = 0.f;
     for (int j0 = 0; j0 < kmax; j0 += KT) {
       __syncthreads();
@@ -727,7 +731,7 @@ static int attention_bwd_impl(const float* q, int ldq, const float* k, const flo
                                   const unsigned char* key_padding_mask, int B, int H, int Tq, int Tk, int head_dim,
                                   int causal, float scale, const void* o_split, long long o_plane, const float* dO,
                                   int ldo, float* lse_ws, float* delta_ws, float* dq, int lddq, float* dk, float* dv,
-                                  int lddk, DropArgs da, void* stream) {
+                                  int lddk, DropArgs da, void* stream, int lse_given = 0) {
   float* lse = lse_ws;
   if (!q || !k || !v || !o_split || !dO || !lse || !delta_ws || !dq || !dk || !dv) return RALF_ERR_NULL;
   if (B <= 0 || H <= 0 || Tq <= 0 || Tk <= 0 || (head_dim != 32 && head_dim != 64)) return RALF_ERR_SHAPE;
@@ -737,12 +741,12 @@ static int attention_bwd_impl(const float* q, int ldq, const float* k, const flo
   dim3 g1((Tq + tq - 1) / tq, H, B), g2((Tk + tk - 1) / tk, H, B);
   if (head_dim == 32) {
     attn_bwd_dq_kernel<32><<<g1, tq, 0, ST(stream)>>>(q, ldq, k, v, ldk, key_padding_mask, Tq, Tk, causal, scale,
-                                                     CBF(o_split), o_plane, dO, ldo, lse, delta_ws, dq, lddq, da);
+                                                     CBF(o_split), o_plane, dO, ldo, lse, delta_ws, dq, lddq, da, lse_given);
     attn_bwd_dkv_kernel<32><<<g2, tk, 0, ST(stream)>>>(q, ldq, k, v, ldk, key_padding_mask, Tq, Tk, causal, scale, dO, ldo,
                                                       lse, delta_ws, dk, dv, lddk, da);
   } else {
     attn_bwd_dq_kernel<64><<<g1, tq, 0, ST(stream)>>>(q, ldq, k, v, ldk, key_padding_mask, Tq, Tk, causal, scale,
-                                                     CBF(o_split), o_plane, dO, ldo, lse, delta_ws, dq, lddq, da);
+                                                     CBF(o_split), o_plane, dO, ldo, lse, delta_ws, dq, lddq, da, lse_given);
     attn_bwd_dkv_kernel<64><<<g2, tk, 0, ST(stream)>>>(q, ldq, k, v, ldk, key_padding_mask, Tq, Tk, causal, scale, dO, ldo,
                                                       lse, delta_ws, dk, dv, lddk, da);
   }
@@ -763,11 +767,11 @@ extern "C" int ralf_attention_bwd_dropout(const float* q, int ldq, const float* 
                                           int head_dim, int causal, float scale, const void* o_split, long long o_plane,
                                           const float* dO, int ldo, float* lse_ws, float* delta_ws, float* dq, int lddq,
                                           float* dk, float* dv, int lddk, const unsigned long long* seed,
-                                          unsigned int site, float p, void* stream) {
+                                          unsigned int site, float p, int lse_given, void* stream) {
   if (!seed) return RALF_ERR_NULL;
   if (!(p >= 0.f && p < 1.f)) return RALF_ERR_SHAPE;
   return attention_bwd_impl(q, ldq, k, v, ldk, key_padding_mask, B, H, Tq, Tk, head_dim, causal, scale, o_split, o_plane, dO,
-                            ldo, lse_ws, delta_ws, dq, lddq, dk, dv, lddk, make_drop_args(seed, site, p), stream);
+                            ldo, lse_ws, delta_ws, dq, lddq, dk, dv, lddk, make_drop_args(seed, site, p), stream, lse_given);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -287,9 +287,10 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, rows:
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, H: int, Tq: int, Tk: int, dh: int, *,
               mask: Optional[torch.Tensor] = None, causal: bool = False, scale: Optional[float] = None,
-              dropout: Optional[tuple] = None):
+              dropout: Optional[tuple] = None, lse_out: Optional[torch.Tensor] = None):
     """q [B*Tq, >=H*dh] / k, v [B*Tk, >=H*dh] fp32 views (row stride = stride(0)); returns split [2, B*Tq, H*dh].
-    ``dropout`` = (seed int64 device tensor [1], site, p): dropout on the attention probabilities (training)."""
+    ``dropout`` = (seed int64 device tensor [1], site, p): dropout on the attention probabilities (training);
+    ``lse_out`` fp32 [B*H*Tq] (with dropout, p > 0): receives the row log-sum-exp for the backward."""
     out = _split_out(B * Tq, H * dh, q.device)
     assert k.stride(0) == v.stride(0)
     sc = scale if scale is not None else dh ** -0.5
@@ -297,7 +298,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, H: int,
         seed, site, p = dropout
         check(_lib.lib().ralf_attention_dropout(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0),
                                                 _ptr(mask), B, H, Tq, Tk, dh, int(causal), sc, out.data_ptr(),
-                                                out.stride(0), None, H * dh, seed.data_ptr(), site, p, _stream()),
+                                                out.stride(0), None, H * dh, seed.data_ptr(), site, p, _ptr(lse_out), _stream()),
               "ralf_attention_dropout")
         return out
     check(_lib.lib().ralf_attention(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), _ptr(mask),
