@@ -44,7 +44,7 @@ def main():
         a = torch.randn(2, M, K, device=dev).to(torch.bfloat16)
         w = torch.randn(2, N, K, device=dev).to(torch.bfloat16)
         bias = torch.randn(N, device=dev)
-        kw = dict(bias=bias, act=act)
+        kw = dict(bias=bias, act=act, block_n=int(os.environ.get("RALF_BENCH_BN", "0")))
         byt = 2 * M * K * 2 + 2 * N * K * 2
         if res == "split":
             kw["res_split"] = torch.randn(2, M, N, device=dev).to(torch.bfloat16)

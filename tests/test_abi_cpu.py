@@ -320,6 +320,33 @@ def test_knn_entry_points_validate_before_touching_the_device():
         assert len(L.ralf_last_cuda_error()) > 0
 
 
+def test_round2_entry_points_validate_before_touching_the_device():
+    """ralf_knn_fixup_exact / ralf_decode_chain / ralf_attention_decode_kv16: argument checks return RalfStatus codes before
+    any CUDA call (runs without a GPU)."""
+    import ctypes as C
+
+    from ralf_b200 import _lib
+
+    L = _lib.lib()
+    buf = (C.c_char * 4096)()
+    p = C.cast(buf, C.c_void_p)
+    ws = L.ralf_knn_workspace_bytes(10, 512, 1, 16)
+    assert L.ralf_knn_fixup_exact(p, 10, 512, p, 1, 16, 0, None, p, p, p, ws, None) == -3        # certified is required
+    assert L.ralf_knn_fixup_exact(p, 10, 512, p, 1, 64, 0, p, p, p, p, ws, None) == -1           # k beyond the filter's 48
+    assert L.ralf_knn_fixup_exact(p, 10, 512, p, 1, 16, 0, p, p, p, p, 8, None) == -7            # workspace too small
+    assert L.ralf_attention_decode_kv16(None, 256, p, 10, 10, 1, 8, C.c_float(1.0), p, 0, 256, None) == -3
+    assert L.ralf_attention_decode_kv16(p, 256, p, 10, 10, 1, 4, C.c_float(1.0), p, 0, 256, None) == -1   # row format: 8 heads
+    st = (_lib.ChainStage * 2)()
+    assert L.ralf_decode_chain(p, 256, 4, None, 1, None) == -3
+    assert L.ralf_decode_chain(p, 256, 4, st, 5, None) == -1                                     # at most 4 stages
+    st[0].W, st[0].ldw, st[0].n_out, st[0].k_in, st[0].in_mode = p.value, 256, 256, 512, 1       # K must be 256 or 1024
+    assert L.ralf_decode_chain(p, 256, 4, st, 1, None) == -1
+    st[0].k_in = 256                                                                             # LayerNorm input without gamma / beta
+    assert L.ralf_decode_chain(p, 256, 4, st, 1, None) == -3
+    st[0].gamma, st[0].beta, st[0].out_operand = p.value, p.value, 1                             # operand output needs n_out = 1024 and a next stage
+    assert L.ralf_decode_chain(p, 256, 4, st, 1, None) == -1
+
+
 def test_bench_line_assembly_with_stub_measurements():
     """The block of bench.py that turns the measurements into the contract's JSON line, executed here with stub numbers (the
     measurements themselves need a B200): every key the driver reads is present and the arithmetic holds together."""

@@ -115,6 +115,24 @@ def test_knn_uncertified_queries_are_fixed_on_the_device(cuda_device):
     np.testing.assert_array_equal(cs.cpu().numpy().view(np.uint32), os_.view(np.uint32))
 
 
+def test_knn_fixup_with_more_than_1024_queries(cuda_device):
+    """The uncertified-query list is built in chunks of 1024 (knn_collect_uncertified_kernel) and the exact scan / re-rank walk
+    it with grid-stride loops: 1300 queries (11 query tiles in one launch per phase), cluster queries in the first, the
+    tenth and the last tile."""
+    from ralf_b200 import ops
+
+    G, Q, rows = _near_duplicate_cluster(30000, 1300, seed=17)
+    for pos, r in ((5, rows[2]), (1100, rows[3]), (1299, rows[4])):
+        Q[pos] = G[r] / np.linalg.norm(G[r])
+    oi, os_ = oracle_knn.topk(G, Q, 16)
+    gi, gs, cert = ops.knn_topk(torch.from_numpy(G).to(cuda_device), torch.from_numpy(Q).to(cuda_device), 16,
+                                gallery_max_norm=1.01)
+    np.testing.assert_array_equal(gi.cpu().numpy(), oi)
+    np.testing.assert_array_equal(gs.cpu().numpy().view(np.uint32), os_.view(np.uint32))
+    cert = cert.cpu().numpy()
+    assert (cert > 0).all() and cert[5] == 2 and cert[1100] == 2 and cert[1299] == 2 and (cert == 2).sum() <= 8
+
+
 @pytest.mark.parametrize("n,q", [(100_000, 1), (100_000, 32), (100_000, 128), (1_000_000, 1), (1_000_000, 32),
                                  (1_000_000, 128)])
 def test_knn_matches_oracle_at_baseline_sizes(cuda_device, n, q):
