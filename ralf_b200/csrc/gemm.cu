@@ -91,6 +91,7 @@ struct GemmCfg {
     return stages * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/ + 32768 /*epilogue staging: 8 warps x 4 KB*/;
   }
   static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator buffers
+  static constexpr uint32_t TMEM_COLS_FOLD = 4 * BN < 32 ? 32 : 4 * BN;  // folded: each buffer is 2 * BN columns
 };
 
 // ---- warp-level staging: row-per-thread registers <-> coalesced global memory ------------------------------------
@@ -196,7 +197,7 @@ template <int BN>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpi& ep, const uint32_t tacc, const int quad, const int lane,
                                                    const int m0, const int n0, const int M, const int N, uint4* stg,
                                                    const int c_begin = 0, const int c_end = BN,
-                                                   const long long f32_off = 0) {
+                                                   const long long f32_off = 0, const int fold_cols = 0) {
     const int r = m0 + quad * 32 + lane;
     const bool row_ok = r < M;
     const long long out_row =
@@ -210,10 +211,18 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpi& ep, const uint
       const bool full = ep.vec_ok && (nbase + 32 <= N);  // warp-uniform
       uint32_t v[32];
       tmem_ld_32x32(tacc + (static_cast<uint32_t>(quad * 32) << 16) + c, v);
-      tmem_ld_wait();
       float x[32];
+      if (fold_cols) {  // folded bf16x3: x_hi.w_hi in column c, (x_hi.w_lo + x_lo.w_hi) in column fold_cols + c
+        uint32_t v2[32];
+        tmem_ld_32x32(tacc + (static_cast<uint32_t>(quad * 32) << 16) + fold_cols + c, v2);
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + __uint_as_float(v2[j]);
+      } else {
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+      }
       if (full) {
         if (ep.bias) {
 #pragma unroll
@@ -362,13 +371,14 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpi& ep, const uint
     }
 }
 
-// MINB = minimum resident CTAs per SM the register allocation must allow.  ptxas (12.9) gives the MINB = 1 build 165
-// registers per thread: 52.8 k per CTA, i.e. never a second CTA on an SM whatever the shared-memory ring -- the short-K,
-// epilogue-bound shapes then run 8 epilogue warps per SM at half the HBM roofline.  MINB = 2 compiles to 96 registers with
-// 40-48 bytes of spill (profiles/r1_gemm_minb2_ptxas.md) and lets cudaOccupancyMaxActiveBlocksPerMultiprocessor return 2
-// for the small rings.  Not yet measured on hardware (round-1 GPU budget was spent): opt-in, RALF_GEMM_MINB=2.
-template <int BN, int NPASS, int MINB>
-__global__ void __launch_bounds__(320, MINB)
+// FOLD (NPASS = 3, BN <= 128): two MMAs per k-step instead of three.  The W stage holds its hi rows directly followed by
+// its lo rows, so ONE descriptor with N = 2*BN multiplies x_hi with [w_hi ; w_lo]: columns [0, BN) of the accumulator
+// collect x_hi.w_hi, columns [BN, 2BN) collect x_hi.w_lo; the second MMA (N = BN) adds x_lo.w_hi into columns [BN, 2BN).
+// The epilogue adds the two halves.  Why: an SS-mode tcgen05.mma at M = 128 costs ~92 cycles however narrow N is
+// (profiles/r2_decode_chain.md), so at BN <= 128 (<= 64 cycles of math per MMA) the kernel is bound by the NUMBER of MMAs.
+// (The round-1 MINB = 2 variant -- two CTAs per SM at 96 registers -- was measured 4 % slower in round 2 and is retired.)
+template <int BN, int NPASS, int FOLD>
+__global__ void __launch_bounds__(320, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmEpi ep, const int M, const int N, const int K, const int STAGES, const ConvGeom cg,
                  const int splits, const long long split_stride) {
@@ -453,7 +463,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int kb = 0; kb < npre; ++kb) load_stage(mt, n0, kb0 + kb, kb);
     }
   }
-  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  constexpr uint32_t TCOLS = FOLD ? Cfg::TMEM_COLS_FOLD : Cfg::TMEM_COLS;
+  constexpr uint32_t ACC_COLS = FOLD ? 2 * BN : BN;  // columns per accumulator buffer
+  if (warp == 1) tmem_alloc<TCOLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -490,7 +502,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int buf = it & 1;
         mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t tacc = tmem_base + buf * BN;
+        const uint32_t tacc = tmem_base + buf * ACC_COLS;
         const int kb0 = (tile % splits) * nkb_s, kb1 = min(nkb, kb0 + nkb_s);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[s], ph);
@@ -502,7 +514,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t koff = static_cast<uint64_t>(2 * k);  // 32 bytes >> 4 per UMMA_K = 16
-            if (NPASS == 3) {
+            if (NPASS == 3 && FOLD) {
+              constexpr uint32_t idesc2 = make_idesc(1, 128, 2 * BN);
+              const uint64_t da_lo = make_sw128_kmajor_desc(a_hi + Cfg::A_BYTES);
+              mma_bf16_ss(tacc, da_hi + koff, db_hi + koff, idesc2, ((kb - kb0) | k) != 0);  // x_hi . [w_hi ; w_lo]
+              mma_bf16_ss(tacc + BN, da_lo + koff, db_hi + koff, idesc, 1);                  // + x_lo . w_hi
+            } else if (NPASS == 3) {
               const uint64_t da_lo = make_sw128_kmajor_desc(a_hi + Cfg::A_BYTES);
               const uint64_t db_lo = make_sw128_kmajor_desc(b_hi + Cfg::B_BYTES);
               mma_bf16_ss(tacc, da_hi + koff, db_lo + koff, idesc, ((kb - kb0) | k) != 0);
@@ -535,9 +552,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tile_rows(mn / tiles_n, m0, m_end);
     mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
     tc_fence_after();
-    const uint32_t tacc = tmem_base + buf * BN;
+    const uint32_t tacc = tmem_base + buf * ACC_COLS;
     gemm_epilogue_tile<BN>(ep, tacc, quad, lane, m0, n0, m_end, N, stage_all + (warp - 2) * 256, half * CH, half * CH + CH,
-                           static_cast<long long>(tile % splits) * split_stride);
+                           static_cast<long long>(tile % splits) * split_stride, FOLD ? BN : 0);
     tc_fence_before();
     mbar_arrive(&tempty_bar[buf]);
     }  // tile loop
@@ -546,7 +563,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    tmem_dealloc<TCOLS>(tmem_base);
   }
 }
 
@@ -761,17 +778,17 @@ int make_kmajor_tmap(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t
   return 0;
 }
 
-template <int BN, int NPASS, int MINB>
+template <int BN, int NPASS, int FOLD>
 static int launch_gemm_v(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi& ep, int M, int N, int K,
                          cudaStream_t st, const ConvGeom& cg, int splits, long long split_stride) {
   using Cfg = GemmCfg<BN, NPASS>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, NPASS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, NPASS, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::smem_bytes(Cfg::MAX_STAGES));
     if (e != cudaSuccess) return set_cuda_error(e);
     // several CTAs per SM only materialise when the SM is configured with the full shared-memory carve-out
-    e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, NPASS, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, NPASS, FOLD>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return set_cuda_error(e);
     attr_set = true;
@@ -795,10 +812,11 @@ static int launch_gemm_v(const CUtensorMap& ta, const CUtensorMap& tb, const Gem
   static int occ_cache[16] = {0};
   int occ = occ_cache[stages];
   if (occ == 0) {
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gemm_bf16_kernel<BN, NPASS, MINB>, 320,
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gemm_bf16_kernel<BN, NPASS, FOLD>, 320,
                                                                   Cfg::smem_bytes(stages));
     if (e != cudaSuccess) return set_cuda_error(e);
-    if (occ > static_cast<int>(512 / Cfg::TMEM_COLS)) occ = 512 / Cfg::TMEM_COLS;
+    constexpr int tcols = FOLD ? Cfg::TMEM_COLS_FOLD : Cfg::TMEM_COLS;
+    if (occ > static_cast<int>(512 / tcols)) occ = 512 / tcols;
     if (occ < 1) occ = 1;
     occ_cache[stages] = occ;
   }
@@ -810,7 +828,7 @@ static int launch_gemm_v(const CUtensorMap& ta, const CUtensorMap& tb, const Gem
   const int grid_sms = (multi_tile && reserve_sms > 0 && reserve_sms < sms) ? sms - reserve_sms : sms;
   const long long max_ctas = static_cast<long long>(grid_sms) * occ;
   dim3 grid(static_cast<unsigned>(num_tiles < max_ctas ? num_tiles : max_ctas));
-  const cudaError_t le = launch_pdl(gemm_bf16_kernel<BN, NPASS, MINB>, grid, dim3(320), Cfg::smem_bytes(stages), st, ta, tb,
+  const cudaError_t le = launch_pdl(gemm_bf16_kernel<BN, NPASS, FOLD>, grid, dim3(320), Cfg::smem_bytes(stages), st, ta, tb,
                                     ep, M, N, K, stages, cg, splits, split_stride);
   return set_cuda_error(le != cudaSuccess ? le : cudaGetLastError());
 }
@@ -818,9 +836,12 @@ static int launch_gemm_v(const CUtensorMap& ta, const CUtensorMap& tb, const Gem
 template <int BN, int NPASS>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi& ep, int M, int N, int K,
                        cudaStream_t st, const ConvGeom& cg, int splits = 1, long long split_stride = 0) {
-  static const bool minb2 = getenv("RALF_GEMM_MINB") && atoi(getenv("RALF_GEMM_MINB")) == 2;
-  if (minb2) return launch_gemm_v<BN, NPASS, 2>(ta, tb, ep, M, N, K, st, cg, splits, split_stride);
-  return launch_gemm_v<BN, NPASS, 1>(ta, tb, ep, M, N, K, st, cg, splits, split_stride);
+  // RALF_GEMM_FOLD=0 restores three MMAs per k-step (A/B runs)
+  static const bool fold = !(getenv("RALF_GEMM_FOLD") && atoi(getenv("RALF_GEMM_FOLD")) == 0);
+  if constexpr (NPASS == 3 && BN <= 128) {
+    if (fold) return launch_gemm_v<BN, NPASS, 1>(ta, tb, ep, M, N, K, st, cg, splits, split_stride);
+  }
+  return launch_gemm_v<BN, NPASS, 0>(ta, tb, ep, M, N, K, st, cg, splits, split_stride);
 }
 
 }  // namespace ralf
