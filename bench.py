@@ -354,7 +354,10 @@ def run_ours(args):
         dog = threading.Timer(args.extras_budget_s, expired)
         dog.daemon = True
         dog.start()
-        ex = run_extras(args, rank, world, dev, model, retr, pipe, line)
+        try:
+            ex = run_extras(args, rank, world, dev, model, retr, pipe, line)
+        except Exception as e:  # never a reason to lose the line
+            ex = {"error": repr(e)[:300]}
         dog.cancel()
         if line is not None:
             line["extras"] = ex
