@@ -1514,6 +1514,106 @@ extern "C" int ralf_attention_decode_kv24(const float* q, int ldq, const void* k
   return set_cuda_error(e != cudaSuccess ? e : cudaGetLastError());
 }
 
+// Four lanes per key (8 channels = one 16-byte load each for K and for V): per cache value a third of the shuffles and
+// half of the load / scale instructions of the eight-lane kernel above, 8 keys per warp-wide load, 64 keys per batch.
+__device__ __forceinline__ void kv16_unpack8(const uint4 w, float (&f)[8]) {
+  constexpr float BIAS = 8388608.f + 32768.f;
+  const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    f[2 * e] = __uint_as_float(0x4B000000u | (ww[e] & 0xffffu)) - BIAS;
+    f[2 * e + 1] = __uint_as_float(__byte_perm(ww[e], 0x4B000000u, 0x7632)) - BIAS;
+  }
+}
+__global__ void __launch_bounds__(256)
+attention_decode_kv16x4_kernel(const float* __restrict__ q, int ldq, const uint8_t* __restrict__ kv, long long kv_bstride,
+                               int Tk, int H, float scale, __nv_bfloat16* __restrict__ out_split, long long out_plane,
+                               int ldo) {
+  constexpr int DH = 32, CPL = 4, KPI = 8, UN = 8, ROW = 1088;
+  pdl_trigger();
+  pdl_wait();
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x;
+  if (h >= H) return;
+  const int kk = lane / CPL, c = lane % CPL;
+  float qr[8];
+  {
+    const float* qp = q + static_cast<long long>(b) * ldq + h * DH + 8 * c;
+    const float4 a = *reinterpret_cast<const float4*>(qp), bq = *reinterpret_cast<const float4*>(qp + 4);
+    qr[0] = a.x * scale; qr[1] = a.y * scale; qr[2] = a.z * scale; qr[3] = a.w * scale;
+    qr[4] = bq.x * scale; qr[5] = bq.y * scale; qr[6] = bq.z * scale; qr[7] = bq.w * scale;
+  }
+  const uint8_t* base = kv + static_cast<long long>(b) * kv_bstride * ROW;
+  const int o_k = h * 64 + c * 16, o_v = 512 + h * 64 + c * 16, o_s = 1024 + h * 8;
+  float m = -INFINITY, l = 0.f;
+  float o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = 0.f;
+#pragma unroll 1
+  for (int j0 = 0; j0 < Tk; j0 += KPI * UN) {
+    uint4 kw[UN], vw[UN];
+    float ksc[UN], vsc[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int j = j0 + u * KPI + kk;
+      kw[u] = vw[u] = make_uint4(0x80008000u, 0x80008000u, 0x80008000u, 0x80008000u);  // offset-binary zero
+      ksc[u] = vsc[u] = 0.f;
+      if (j < Tk) {
+        const uint8_t* r = base + static_cast<long long>(j) * ROW;
+        kw[u] = __ldcs(reinterpret_cast<const uint4*>(r + o_k));
+        vw[u] = __ldcs(reinterpret_cast<const uint4*>(r + o_v));
+        const float2 sc2 = __ldcs(reinterpret_cast<const float2*>(r + o_s));
+        ksc[u] = sc2.x;
+        vsc[u] = sc2.y;
+      }
+    }
+    float s[UN];
+    float bm = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      float kf[8];
+      kv16_unpack8(kw[u], kf);
+      float d = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d = fmaf(qr[i], kf[i], d);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      s[u] = (j0 + u * KPI + kk < Tk) ? d * ksc[u] : -INFINITY;
+      bm = fmaxf(bm, s[u]);
+    }
+#pragma unroll
+    for (int off = CPL; off < 32; off <<= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, off));
+    const float m_new = fmaxf(m, bm);
+    const float corr = __expf(m - m_new);
+    l *= corr;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] *= corr;
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const float p = __expf(s[u] - m_new);
+      float vf[8];
+      kv16_unpack8(vw[u], vf);
+      const float pv = p * vsc[u];
+      l += p;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(pv, vf[i], o[i]);
+    }
+    m = m_new;
+  }
+#pragma unroll
+  for (int off = CPL; off < 32; off <<= 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] += __shfl_xor_sync(0xffffffffu, o[i], off);
+    l += __shfl_xor_sync(0xffffffffu, l, off);
+  }
+  if (kk == 0) {
+    const float inv = 1.f / l;
+    const long long off0 = static_cast<long long>(b) * ldo + h * DH + 8 * c;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) store_split(out_split, out_plane, off0 + i, o[i] * inv);
+  }
+}
+
 extern "C" int ralf_attention_decode_kv16(const float* q, int ldq, const void* kv16, long long kv_bstride, int Tk, int B,
                                           int H, float scale, void* out_split, long long out_plane, int ldo,
                                           void* stream) {
@@ -1523,9 +1623,13 @@ extern "C" int ralf_attention_decode_kv16(const float* q, int ldq, const void* k
   // (A lane-per-key variant -- whole 64-byte head rows per lane, no shuffles, private online softmax -- was measured in
   // round 2: 0.155 ms against 0.105 ms for this one; 32 different rows per load instruction cost more L1 wavefronts than
   // the shuffles it saved.  Removed; profiles/r2_kv16_ncu.md.)
-  const cudaError_t e = launch_pdl(attention_decode_kv16_kernel, dim3(B), dim3(32 * H), 0, ST(stream), q, ldq,
-                                   reinterpret_cast<const uint8_t*>(kv16), kv_bstride, Tk, H, scale, BF(out_split),
-                                   out_plane, ldo);
+  // RALF_KV16_LANES: 4 (default) = four lanes per key, 16-byte loads; 8 = the first version (eight lanes, 8-byte loads)
+  static const int lanes = getenv("RALF_KV16_LANES") ? atoi(getenv("RALF_KV16_LANES")) : 4;
+  const cudaError_t e =
+      lanes == 8 ? launch_pdl(attention_decode_kv16_kernel, dim3(B), dim3(32 * H), 0, ST(stream), q, ldq,
+                              reinterpret_cast<const uint8_t*>(kv16), kv_bstride, Tk, H, scale, BF(out_split), out_plane, ldo)
+                 : launch_pdl(attention_decode_kv16x4_kernel, dim3(B), dim3(32 * H), 0, ST(stream), q, ldq,
+                              reinterpret_cast<const uint8_t*>(kv16), kv_bstride, Tk, H, scale, BF(out_split), out_plane, ldo);
   return set_cuda_error(e != cudaSuccess ? e : cudaGetLastError());
 }
 
