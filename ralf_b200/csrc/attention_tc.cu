@@ -526,7 +526,7 @@ attention_tc2_kernel(const float* __restrict__ q, const int ldq, const float* __
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Variant for 256 < Tk <= 480 keys (RALF_ATTN_TC_BIG=1; built, not yet run on hardware): the reference's real canvases
+// Variant for 256 < Tk <= 480 keys (default for these shapes since round 2; RALF_ATTN_TC_BIG=0 switches it off): the reference's real canvases
 // are 350 x 240 -> 22 x 15 = 330 image tokens, which the kernels above hand to the CUDA-core fallback.
 // S[128, Tk] no longer leaves room for separate P planes in the 512 TMEM columns, so P is written IN PLACE: a thread
 // that has read its 32 S columns [c, c + 32) of a chunk stores the chunk's P as 16 hi columns [c, c + 16) and 16 lo
@@ -754,7 +754,9 @@ int attention_tc_try(const float* q, int ldq, const float* k, const float* v, in
                      long long out_plane, float* out_f32, int ldo, cudaStream_t st) {
   static const int variant = getenv("RALF_ATTN_TC") ? atoi(getenv("RALF_ATTN_TC")) : 1;  // 0 off, 1 default, 2 = 8-warp kernel
   const bool enabled = variant != 0;
-  static const bool big = getenv("RALF_ATTN_TC_BIG") && atoi(getenv("RALF_ATTN_TC_BIG")) != 0;
+  // 256 < Tk <= 480 (the reference's real 350 x 240 canvases: 330 image tokens) on the tensor cores: default since round 2
+  // (verified against fp64 on hardware; encode of 128 real-size canvases 15.4 vs 18.0 ms); RALF_ATTN_TC_BIG=0 = CUDA cores
+  static const bool big = !(getenv("RALF_ATTN_TC_BIG") && atoi(getenv("RALF_ATTN_TC_BIG")) == 0);
   const bool use_big = big && Tk > 256 && Tk <= ATCB_MAX_KEYS;
   if (!enabled || mask || causal || head_dim != 32 || (Tk > 256 && !use_big) || Tk < 64 || Tq < 64) return 0;
   if ((ldq & 3) || (ldk & 3) || (ldo & 7) || (reinterpret_cast<uintptr_t>(out_split) & 15) ||

@@ -245,8 +245,8 @@ def test_encoder_attention_tcgen05_two_threads_per_row_variant(cuda_device):
 
 
 def test_encoder_attention_tcgen05_more_than_256_keys(cuda_device):
-    """RALF_ATTN_TC_BIG=1: 256 < Tk <= 480 (the reference's real 350 x 240 canvases give 330 image tokens) on the tensor
-    cores with P written in place over S in TMEM; without the switch these shapes take the CUDA-core kernel."""
+    """256 < Tk <= 480 (the reference's real 350 x 240 canvases give 330 image tokens) on the tensor cores with P written in
+    place over S in TMEM (the default since round 2); RALF_ATTN_TC_BIG=0 sends these shapes to the CUDA-core kernel."""
     shapes = [[2, 330, 330], [1, 300, 257], [3, 480, 480], [2, 128, 400], [1, 200, 272], [130, 330, 330]]
     big = _attention_in_child({"RALF_ATTN_TC_BIG": "1"}, shapes)
     base = _attention_in_child({"RALF_ATTN_TC_BIG": "0"}, shapes)
