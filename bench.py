@@ -470,6 +470,37 @@ def extra_strong(args, rank, world, dev, model, retr):
             "value": round(B * world / ms * 1e3, 1), "unit": "layouts/s", "ms_per_step": round(ms, 3)}
 
 
+def extra_real_canvas(args, rank, world, dev, retr, B: int = 512):
+    """The reference's REAL shape (hfds_builder/helpers/global_variables.py:5-6: 350 x 240 canvases -> 330 image tokens,
+    memory 680; E = 10 -> 50 tokens) through the same pipeline: B canvases per GPU per step, gallery as in the headline."""
+    from ralf_b200 import generator as G
+    from ralf_b200.pipeline import LayoutPipeline
+    from ralf_b200.retrieval import GpuRetriever
+    from ralf_b200.tokenizer import LayoutSequenceTokenizer
+
+    E = 10
+    tok = LayoutSequenceTokenizer(["logo", "text", "underlay", "embellishment"], E)
+    model = G.RALF(features=None, tokenizer=tok, dataset_name="cgl", max_seq_length=E, db_dataset=None,
+                   retrieval_backbone="dreamsim", top_k=16, saliency_k="None", auxilary_task="uncond")
+    model.load_state_dict(synth_weights_for(model), strict=True)
+    model.eval().to(dev)
+    table = retr.table[:, :, :E].contiguous()  # the headline's layout table cut to 10 elements per exemplar
+    r = GpuRetriever(retr.emb, None, device=dev, rank=rank, world_size=world, index_base=retr.index_base,
+                     process_group=retr.pg)
+    r.table = table
+    pipe = LayoutPipeline(model, r, B, 350, 240, top_k=16, micro_batch=min(args.micro_batch, B))
+    g = torch.Generator().manual_seed(23 + rank)
+    pipe.img.copy_(torch.rand(B, 4, 350, 240, generator=g))
+    pipe.qry.copy_(torch.nn.functional.normalize(torch.randn(B, 512, generator=g), dim=1))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    ms = _max_over_ranks(_events_ms(pipe.step, 3, 2), world, dev)
+    return {"config": "real canvas size 350x240 (330 image tokens, memory 680), E = 10 -> 50 tokens", "canvases_per_gpu": B,
+            "n_gpus": world, "value": round(B * world / ms * 1e3, 1), "unit": "layouts/s", "ms_per_step": round(ms, 3)}
+
+
 def extra_b1_latency(dev):
     """BASELINE configs[0] on the GPU: Autoreg baseline (no retrieval), unconstrained, batch 1, 350x240 canvas, 50 greedy
     tokens through the drop-in model.sample() (host tensors in, CPU layout dict out) -- median latency."""
@@ -594,6 +625,7 @@ def run_extras(args, rank, world, dev, model, retr, pipe, line):
     if world > 1:
         guarded("strong_scaled_1024_total", lambda: extra_strong(args, rank, world, dev, model, retr), True)
     del pipe
+    guarded("real_canvas_350x240", lambda: extra_real_canvas(args, rank, world, dev, retr), True)
     guarded("train", lambda: extra_train(args, rank, world, dev), True)
     if world == 1:
         guarded("b1_latency", lambda: extra_b1_latency(dev), False)
