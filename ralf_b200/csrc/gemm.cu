@@ -569,6 +569,269 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 
 // ------------------------------------------------------------------------------------------------
+// Short-K bottleneck-tail GEMMs (ResNet conv3 / downsample: K <= 256, N a multiple of 128, split bf16 output, optional
+// split bf16 residual + ReLU): the same producer / MMA warps as gemm_bf16_kernel<128, 3, 1>, but the EPILOGUE moves its
+// global traffic with TMA.  These GEMMs are bound by the residual read + output write (K = 64: 1.2 GB per 128 canvases
+// against 17 GFLOP x 3), and the register-staged epilogue above keeps only one 4 KB chunk of loads in flight per warp,
+// then one chunk of stores: 0.45-0.5 of the HBM peak.  Here every epilogue warp owns a ring of NBUF 4 KB chunk buffers
+// ([2 planes][32 rows][32 columns] bf16, SWIZZLE_64B = the XOR pattern of epi_swz<4>, so the row-per-thread accesses
+// are conflict free): the residual of chunk g + NBUF - 1 is fetched by cp.async.bulk.tensor while chunk g is computed
+// IN PLACE in its buffer and chunk g - 1 drains through a bulk tensor store.  Arithmetic and its order are those of
+// gemm_epilogue_tile, so the results are bit-identical to the register-staged path.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+struct TepiCfg {
+  static constexpr int BN = 128;
+  static constexpr int STAGE_BYTES = 2 * (128 * 128 + BN * 128);  // 64 KB: A hi/lo + W hi/lo of one k-block
+  static constexpr int CHUNK_BYTES = 4096;                         // [2][32][32] bf16
+  static constexpr int smem_bytes(int stages, int nbuf) {
+    return stages * STAGE_BYTES + 8 * nbuf * CHUNK_BYTES + 1024 /*align*/ + 1024 /*barriers*/;
+  }
+};
+
+template <int NBUF>
+__global__ void __launch_bounds__(320, 1)
+gemm_bf16_tepi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
+                      const float* __restrict__ bias, const int act, const int has_res, const int post_relu, const int M,
+                      const int N, const int K, const int STAGES) {
+  constexpr int BN = TepiCfg::BN;
+  constexpr int A_BYTES = 128 * 128, B_BYTES = BN * 128;
+  pdl_trigger();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
+  uint8_t* chunks = smem + STAGES * TepiCfg::STAGE_BYTES;  // 8 warps x NBUF x 4 KB, 1024-byte aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(chunks + 8 * NBUF * TepiCfg::CHUNK_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* res_bar = tempty_bar + 2;  // [8 warps][NBUF]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 8 * NBUF);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_n = N / BN;
+  const int num_tiles = ((M + 127) / 128) * tiles_n;
+  const int nkb = (K + 63) / 64;
+  auto load_stage = [&](const int mt, const int n0, const int kb, const int s) {
+    mbar_expect_tx(&full_bar[s], TepiCfg::STAGE_BYTES);
+    uint8_t* st = smem + s * TepiCfg::STAGE_BYTES;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) tma_load_3d(&tmA, &full_bar[s], st + p * A_BYTES, kb * 64, mt * 128, p);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) tma_load_3d(&tmB, &full_bar[s], st + 2 * A_BYTES + p * B_BYTES, kb * 64, n0, p);
+  };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmR);
+    tma_prefetch_desc(&tmO);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 256);
+    }
+    for (int i = 0; i < 8 * NBUF; ++i) mbar_init(&res_bar[i], 1);
+    fence_mbar_init();
+    pdl_wait();
+    const int mt = blockIdx.x / tiles_n, n0 = (blockIdx.x % tiles_n) * BN;
+    const int npre = nkb < STAGES ? nkb : STAGES;
+    for (int kb = 0; kb < npre; ++kb) load_stage(mt, n0, kb, kb);
+  }
+  constexpr uint32_t TCOLS = 4 * BN;   // two folded accumulator buffers of 2 * BN columns
+  constexpr uint32_t ACC_COLS = 2 * BN;
+  if (warp == 1) tmem_alloc<TCOLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const int npre = nkb < STAGES ? nkb : STAGES;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile / tiles_n, n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (tile == static_cast<int>(blockIdx.x) && kb < npre) {  // issued in the prologue
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+            continue;
+          }
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          load_stage(mt, n0, kb, s);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(1, 128, BN);
+      constexpr uint32_t idesc2 = make_idesc(1, 128, 2 * BN);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * ACC_COLS;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_hi = base_u32 + s * TepiCfg::STAGE_BYTES;
+          const uint32_t b_hi = a_hi + 2 * A_BYTES;
+          const uint64_t da_hi = make_sw128_kmajor_desc(a_hi);
+          const uint64_t da_lo = make_sw128_kmajor_desc(a_hi + A_BYTES);
+          const uint64_t db_hi = make_sw128_kmajor_desc(b_hi);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t koff = static_cast<uint64_t>(2 * k);
+            mma_bf16_ss(tacc, da_hi + koff, db_hi + koff, idesc2, (kb | k) != 0);  // x_hi . [w_hi ; w_lo]
+            mma_bf16_ss(tacc + BN, da_lo + koff, db_hi + koff, idesc, 1);          // + x_lo . w_hi
+          }
+          tc_commit(&empty_bar[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        tc_commit(&tfull_bar[buf]);
+      }
+    }
+  } else {
+    // Epilogue warp ew: TMEM lanes / tile rows 32 * (ew % 4) .., columns 64 * (ew / 4) .. + 64 of every tile, as two
+    // chunks of 32 columns; chunk g of this warp lives in buffer g % NBUF.
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const int half = ew >> 2;
+    uint8_t* cb = chunks + ew * NBUF * TepiCfg::CHUNK_BYTES;
+    uint64_t* rb = res_bar + ew * NBUF;
+    const int my_tiles = static_cast<int>(blockIdx.x) < num_tiles ? (num_tiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
+    const int total = 2 * my_tiles;
+    auto coords = [&](const int g, int& col, int& row) {
+      const int tile = blockIdx.x + (g >> 1) * gridDim.x;
+      col = (tile % tiles_n) * BN + half * 64 + (g & 1) * 32;
+      row = (tile / tiles_n) * 128 + quad * 32;
+    };
+    auto issue_res = [&](const int g) {  // lane 0 only
+      if (g < total) {
+        int col, row;
+        coords(g, col, row);
+        mbar_expect_tx(&rb[g % NBUF], TepiCfg::CHUNK_BYTES);
+        tma_load_3d(&tmR, &rb[g % NBUF], cb + (g % NBUF) * TepiCfg::CHUNK_BYTES, col, row, 0);
+      }
+    };
+    if (has_res && lane == 0) {
+      for (int g = 0; g < NBUF - 1; ++g) issue_res(g);
+    }
+    const int sw = (lane >> 1) & 3;  // SWIZZLE_64B: 16-byte piece j of row r sits at piece j ^ ((r >> 1) & 3)
+    for (int g = 0; g < total; ++g) {
+      const int it = g >> 1, c = g & 1, buf = it & 1;
+      int col, row;
+      coords(g, col, row);
+      if (c == 0) {
+        mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+        tc_fence_after();
+      }
+      const uint32_t tacc = tmem_base + buf * ACC_COLS + (static_cast<uint32_t>(quad * 32) << 16) + half * 64 + c * 32;
+      uint32_t v[32], v2[32];
+      tmem_ld_32x32(tacc, v);
+      tmem_ld_32x32(tacc + BN, v2);
+      tmem_ld_wait();
+      if (c == 1) {  // the accumulator buffer is drained: hand it back to the MMA warp before the memory work
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[buf]);
+      }
+      float x[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + __uint_as_float(v2[j]);
+      if (bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col + j));
+          x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
+        }
+      }
+      if (act == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+      }
+      uint4* bq = reinterpret_cast<uint4*>(cb + (g % NBUF) * TepiCfg::CHUNK_BYTES);
+      if (has_res) {
+        mbar_wait(&rb[g % NBUF], (g / NBUF) & 1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 mh = bq[lane * 4 + (j ^ sw)], ml = bq[128 + lane * 4 + (j ^ sw)];
+          const uint32_t hw[4] = {mh.x, mh.y, mh.z, mh.w};
+          const uint32_t lw[4] = {ml.x, ml.y, ml.z, ml.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            x[8 * j + 2 * q] += __uint_as_float(hw[q] << 16) + __uint_as_float(lw[q] << 16);
+            x[8 * j + 2 * q + 1] += __uint_as_float(hw[q] & 0xffff0000u) + __uint_as_float(lw[q] & 0xffff0000u);
+          }
+        }
+      } else {
+        if (lane == 0) bulk_wait_read<NBUF - 1>();  // the store that last used this buffer (chunk g - NBUF) has read it
+        __syncwarp();
+      }
+      if (post_relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          __nv_bfloat16 h0, l0, h1, l1;
+          split_bf16(x[8 * j + 2 * q], h0, l0);
+          split_bf16(x[8 * j + 2 * q + 1], h1, l1);
+          hw[q] = pack_bf16(h0, h1);
+          lw[q] = pack_bf16(l0, l1);
+        }
+        bq[lane * 4 + (j ^ sw)] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        bq[128 + lane * 4 + (j ^ sw)] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      }
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the bulk store
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&tmO, bq, col, row, 0);
+        bulk_commit();
+        if (has_res) {
+          bulk_wait_read<1>();  // chunk g - 1's store has read its buffer: refill it with the residual of g + NBUF - 1
+          issue_res(g + NBUF - 1);
+        }
+      }
+      __syncwarp();
+    }
+    if (lane == 0) bulk_wait_all();  // shared memory must outlive the stores
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TCOLS>(tmem_base);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
 // LayerNorm fused into the GEMM's A operand (decode path, K = 256 = d_model; one CTA per (n-tile, 128-row tile)).
 // Measured at the bench shape (M = 1024) in round 2: 188.2 vs 168.5 ms per step -- the serial per-thread row
 // normalisation sits on every GEMM's critical path and costs more than the 5 us LayerNorm launch it removes.  Opt-in.
@@ -868,6 +1131,57 @@ static int make_conv_tmap(CUtensorMap* out, const void* ptr, uint64_t C_, uint64
   return 0;
 }
 
+
+// Epilogue operand of gemm_bf16_tepi_kernel: split bf16 tensor [2 planes][rows, cols] (row stride ld, plane stride in
+// elements) as a 3-D map (cols, rows, plane) with boxes of 32 columns x 32 rows x both planes, SWIZZLE_64B.
+static int make_chunk_tmap(CUtensorMap* out, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld, uint64_t plane_stride) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey key{ptr, cols, rows, 2, ld, plane_stride, 32u, 32u, 0xC2u};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return 0; }
+  }
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return RALF_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15) || ((plane_stride * 2) & 15)) return RALF_ERR_ALIGN;
+  cuuint64_t gdim[3] = {cols, rows, 2};
+  cuuint64_t gstr[2] = {ld * 2, plane_stride * 2};
+  cuuint32_t box[3] = {32, 32, 2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "ralf_b200: cuTensorMapEncodeTiled (epilogue chunks) failed (%d)\n", (int)r);
+    return RALF_ERR_DRIVER;
+  }
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, *out);
+  return 0;
+}
+
+template <int NBUF>
+static int launch_tepi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const CUtensorMap& to,
+                       const float* bias, int act, int has_res, int post_relu, int M, int N, int K, int stages, cudaStream_t st) {
+  static bool attr_set = false;
+  const int smem = TepiCfg::smem_bytes(stages, NBUF);
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tepi_kernel<NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         TepiCfg::smem_bytes(NBUF == 4 ? 1 : 2, NBUF));
+    if (e != cudaSuccess) return set_cuda_error(e);
+    attr_set = true;
+  }
+  const long long num_tiles = static_cast<long long>(N / 128) * ((M + 127) / 128);
+  const int sms = num_sms();
+  dim3 grid(static_cast<unsigned>(num_tiles < sms ? num_tiles : sms));
+  const cudaError_t le = launch_pdl(gemm_bf16_tepi_kernel<NBUF>, grid, dim3(320), smem, st, ta, tb, tr, to, bias, act, has_res,
+                                    post_relu, M, N, K, stages);
+  return set_cuda_error(le != cudaSuccess ? le : cudaGetLastError());
+}
+
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int S, long long stride, int M, int N,
                                      float* __restrict__ out, int out_ld) {
   const long long total = static_cast<long long>(M) * N;
@@ -957,6 +1271,24 @@ static int gemm_dispatch(const RalfGemmArgs* a, const CUtensorMap& ta, int bn, c
                                                    a->out_f32 + a->out_col0, a->out_ld);
       return set_cuda_error(cudaGetLastError());
     }
+  }
+  // Bottleneck-tail shape class -> the TMA-epilogue kernel (RALF_GEMM_TEPI=0 keeps the register-staged epilogue: A/B runs)
+  static const bool tepi = !(getenv("RALF_GEMM_TEPI") && atoi(getenv("RALF_GEMM_TEPI")) == 0);
+  static const bool fold_on = !(getenv("RALF_GEMM_FOLD") && atoi(getenv("RALF_GEMM_FOLD")) == 0);
+  if (tepi && fold_on && bn == 128 && np == 3 && !cg.enabled && a->K <= 256 && a->N % 128 == 0 && a->M >= 128 * 148 &&
+      ep.out_split && ep.split_lo && !ep.out_f32 && !ep.out_kv24 && !ep.res && a->rows_per_group <= 0 && ep.res_row_mod <= 0 &&
+      ep.vec_ok && ep.act != 2) {
+    CUtensorMap tr, to;
+    rc = make_chunk_tmap(&to, ep.out_split + ep.out_col0, a->N, a->M, ep.out_ld, ep.out_plane);
+    if (rc) return rc;
+    tr = to;
+    if (ep.res_split) {
+      rc = make_chunk_tmap(&tr, ep.res_split, a->N, a->M, ep.res_ld, ep.res_plane);
+      if (rc) return rc;
+    }
+    const int nkb = (a->K + 63) / 64;
+    return nkb == 1 ? launch_tepi<4>(ta, tb, tr, to, ep.bias, ep.act, ep.res_split != nullptr, ep.post_relu, a->M, a->N, a->K, 1, st)
+                    : launch_tepi<3>(ta, tb, tr, to, ep.bias, ep.act, ep.res_split != nullptr, ep.post_relu, a->M, a->N, a->K, 2, st);
   }
 #define RALF_GEMM_CASE(BN_, NP_) \
   if (bn == BN_ && np == NP_) return launch_gemm<BN_, NP_>(ta, tb, ep, a->M, a->N, a->K, st, cg);

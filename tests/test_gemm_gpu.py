@@ -181,3 +181,36 @@ def test_gemm_with_fused_layernorm_matches_fp64(cuda_device, M, N, act):
     if act == "relu":
         ref = ref.relu()
     assert (out.double() - ref).abs().max().item() <= 3e-5 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("M,N,K,residual,act", [
+    (19072, 256, 64, True, None),     # ResNet layer-1 conv3: one k-block, four chunk buffers per warp
+    (19072, 256, 64, False, None),    # layer-1 downsample: no residual
+    (20000, 512, 128, True, None),    # layer-2 conv3: two ring stages, three chunk buffers; M % 128 = 32 (clipped boxes)
+    (18950, 1024, 256, True, "relu"),  # layer-3 conv3 shape with an activation; M % 32 != 0
+    (37888, 128, 64, True, None),     # two tiles per CTA and one n-tile
+])
+def test_gemm_tma_epilogue_is_bit_identical_to_register_epilogue(cuda_device, M, N, K, residual, act):
+    """Bottleneck-tail shape class (K <= 256, N % 128 == 0, M >= 148 tiles, split output): gemm_bf16_tepi_kernel moves the
+    residual and the output with bulk tensor copies.  Same MMAs, same epilogue arithmetic -> must equal the register-staged
+    kernel (forced here with block_n = 64) bit for bit, and float64 within the bf16x3 bound."""
+    from ralf_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(cuda_device)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda_device)
+    bias = torch.randn(N, generator=g).to(cuda_device)
+    res_s = ops.split_bf16(torch.randn(M, N, generator=g).to(cuda_device)) if residual else None
+    a_s, w_s = ops.split_bf16(a), ops.split_bf16(w)
+    guard = 4096
+    flat = torch.full((2 * M * N + 2 * guard,), 7.0, dtype=torch.bfloat16, device=cuda_device)  # canaries around the output
+    out_t = flat[guard:guard + 2 * M * N].view(2, M, N)
+    kw = dict(bias=bias, act=act, res_split=res_s, post_relu=residual, want_f32=False)
+    ops.gemm(a_s, w_s, out_split=out_t, **kw)
+    out_r = torch.empty(2, M, N, dtype=torch.bfloat16, device=cuda_device)
+    ops.gemm(a_s, w_s, out_split=out_r, block_n=64, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(out_t.view(torch.int16), out_r.view(torch.int16))
+    assert (flat[:guard] == 7.0).all() and (flat[-guard:] == 7.0).all()
+    ref = _ref(a, w, bias, act, ops.unsplit(res_s) if residual else None, post_relu=residual)
+    assert (ops.unsplit(out_t).double() - ref).abs().max().item() <= 4e-5 * ref.abs().max().item()
