@@ -135,6 +135,10 @@ int ralf_gemm(const RalfGemmArgs* args, void* stream);
  * box whose out-of-image part is zero-filled (= the padding); no im2col buffer exists.
  * args->W = [planes][N, KH*KW*C] with k = (kh*KW + kw)*C + c; args->M = B*H*W; args->K = KH*KW*C; C % 64 == 0. */
 int ralf_conv_gemm(const RalfGemmArgs* args, int B, int H, int W, int C, int KH, int KW, void* stream);
+/* The same with stride 1 or 2 (ResNet's stride-2 3x3 and 1x1 downsample convolutions, torchvision resnet50 via
+ * models/common/image.py:90-120): args->M = B*Ho*Wo, Ho = (H + 2*(KH/2) - KH) / stride + 1; a tap's TMA box skips every
+ * other input position through the tensor map's element strides, so no im2col rows are materialised. */
+int ralf_conv_gemm_strided(const RalfGemmArgs* args, int B, int H, int W, int C, int KH, int KW, int stride, void* stream);
 /* ResNet50 stem (7x7 / stride 2 / pad 3 on the 4-channel canvas, common/image.py:69-77) in space-to-depth form:
  * ralf_stem_s2d turns the fp32 NCHW image [B,4,H,W] (H, W even) into a zero-bordered NHWC split buffer
  * [planes][B, H/2+3, W/2+3, 16] (channel = (dy*2+dx)*4 + c); ralf_stem_gemm runs the equivalent 4x4 / stride 1

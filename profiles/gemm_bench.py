@@ -22,6 +22,11 @@ SHAPES = [  # name, M, N, K, residual ("split" | "f32" | None), out ("split" | "
     ("l3.c3  ", 32768, 1024, 256, "split", "split", None),
     ("l3.c2  ", 32768, 256, 2304, None, "split", "relu"),
     ("l4.c2  ", 8192, 512, 4608, None, "split", "relu"),
+    ("l2.c1  ", 131072, 128, 512, None, "split", "relu"),
+    ("l3.c1  ", 32768, 256, 1024, None, "split", "relu"),
+    ("l3.ds  ", 32768, 1024, 512, None, "split", None),
+    ("l4.c3  ", 8192, 2048, 512, "split", "split", None),
+    ("l4.ds  ", 8192, 2048, 1024, None, "split", None),
     ("enc.qkv", 32768, 768, 256, None, "f32", None),
     ("enc.o  ", 32768, 256, 256, "f32", "f32", None),
     ("enc.l1 ", 32768, 1024, 256, None, "split", "relu"),

@@ -49,7 +49,7 @@ struct GemmEpi {
   int kv_fmt;                                      // 24: 24-bit float; 16: 16-bit integers + fp32 scale per (row, head)
 };
 
-// Implicit-GEMM convolution (stride 1, "same" padding): the A operand is never materialised.  k-block kb maps to
+// Implicit-GEMM convolution (stride 1 or 2, padding KH / 2): the A operand is never materialised.  k-block kb maps to
 // filter tap (kh, kw) = kb / cblocks and input channels 64 * (kb % cblocks) ...; an M tile is a (Wo x BH x NB) brick
 // of output positions, loaded per tap as ONE 5-D TMA box over the NHWC activation shifted by (kh - pad, kw - pad) --
 // out-of-image coordinates are zero-filled by TMA, which is exactly the convolution's zero padding.
@@ -60,6 +60,7 @@ struct ConvGeom {
   int hblocks;        // ceil(Ho / BH)
   int cblocks;        // C / 64
   int KW, pad;
+  int stride;         // 1 or 2: input position = stride * output position + tap - pad (the tensor map's element strides)
 };
 
 __device__ __forceinline__ void tma_load_5d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2,
@@ -429,8 +430,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int kh = tap / cg.KW, kw = tap - kh * cg.KW;
 #pragma unroll
       for (int p = 0; p < P; ++p)
-        tma_load_5d(&tmA, &full_bar[s], st + p * Cfg::A_BYTES, cb * 64, kw - cg.pad, hb * cg.BH + kh - cg.pad,
-                    g * cg.NB, p);
+        tma_load_5d(&tmA, &full_bar[s], st + p * Cfg::A_BYTES, cb * 64, kw - cg.pad,
+                    hb * cg.BH * cg.stride + kh - cg.pad, g * cg.NB, p);
     } else {
 #pragma unroll
       for (int p = 0; p < P; ++p) tma_load_3d(&tmA, &full_bar[s], st + p * Cfg::A_BYTES, kb * 64, mt * 128, p);
@@ -606,7 +607,7 @@ __global__ void __launch_bounds__(320, 1)
 gemm_bf16_tepi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
                       const float* __restrict__ bias, const int act, const int has_res, const int post_relu, const int M,
-                      const int N, const int K, const int STAGES) {
+                      const int N, const int K, const int STAGES, const ConvGeom cg) {
   constexpr int BN = TepiCfg::BN;
   constexpr int A_BYTES = 128 * 128, B_BYTES = BN * 128;
   pdl_trigger();
@@ -629,8 +630,18 @@ gemm_bf16_tepi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   auto load_stage = [&](const int mt, const int n0, const int kb, const int s) {
     mbar_expect_tx(&full_bar[s], TepiCfg::STAGE_BYTES);
     uint8_t* st = smem + s * TepiCfg::STAGE_BYTES;
+    if (cg.enabled) {  // implicit convolution whose M tiles are all full: tile mt = output rows [128 mt, 128 mt + 128)
+      const int g = mt / cg.hblocks, hb = mt - g * cg.hblocks;
+      const int tap = kb / cg.cblocks, cb = kb - tap * cg.cblocks;
+      const int kh = tap / cg.KW, kw = tap - kh * cg.KW;
 #pragma unroll
-    for (int p = 0; p < 2; ++p) tma_load_3d(&tmA, &full_bar[s], st + p * A_BYTES, kb * 64, mt * 128, p);
+      for (int p = 0; p < 2; ++p)
+        tma_load_5d(&tmA, &full_bar[s], st + p * A_BYTES, cb * 64, kw - cg.pad, hb * cg.BH * cg.stride + kh - cg.pad,
+                    g * cg.NB, p);
+    } else {
+#pragma unroll
+      for (int p = 0; p < 2; ++p) tma_load_3d(&tmA, &full_bar[s], st + p * A_BYTES, kb * 64, mt * 128, p);
+    }
 #pragma unroll
     for (int p = 0; p < 2; ++p) tma_load_3d(&tmB, &full_bar[s], st + 2 * A_BYTES + p * B_BYTES, kb * 64, n0, p);
   };
@@ -1113,14 +1124,15 @@ using namespace ralf;
 
 // NHWC split activation [planes][B, H, W, C] -> 5-D tensor map (C, W, H, B, plane); box = 64 channels x Wo x BH x NB.
 static int make_conv_tmap(CUtensorMap* out, const void* ptr, uint64_t C_, uint64_t W_, uint64_t H_, uint64_t B_,
-                          uint64_t planes, uint64_t plane_stride, uint32_t bw, uint32_t bh, uint32_t nb) {
+                          uint64_t planes, uint64_t plane_stride, uint32_t bw, uint32_t bh, uint32_t nb, uint32_t stride = 1) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) return RALF_ERR_DRIVER;
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((C_ * 2) & 15) || ((plane_stride * 2) & 15)) return RALF_ERR_ALIGN;
   cuuint64_t gdim[5] = {C_, W_, H_, B_, planes};
   cuuint64_t gstr[4] = {C_ * 2, W_ * C_ * 2, H_ * W_ * C_ * 2, (planes > 1 ? plane_stride : B_ * H_ * W_ * C_) * 2};
-  cuuint32_t box[5] = {64, bw, bh, nb, 1};
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  // element strides: a box of bw * stride traversed positions loads every stride-th one = bw of them
+  cuuint32_t box[5] = {64, bw * stride, bh * stride, nb, 1};
+  cuuint32_t estr[5] = {1, stride, stride, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1165,7 +1177,8 @@ static int make_chunk_tmap(CUtensorMap* out, const void* ptr, uint64_t cols, uin
 
 template <int NBUF>
 static int launch_tepi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const CUtensorMap& to,
-                       const float* bias, int act, int has_res, int post_relu, int M, int N, int K, int stages, cudaStream_t st) {
+                       const float* bias, int act, int has_res, int post_relu, int M, int N, int K, int stages, const ConvGeom& cg,
+                       cudaStream_t st) {
   static bool attr_set = false;
   const int smem = TepiCfg::smem_bytes(stages, NBUF);
   if (!attr_set) {
@@ -1178,7 +1191,7 @@ static int launch_tepi(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   const int sms = num_sms();
   dim3 grid(static_cast<unsigned>(num_tiles < sms ? num_tiles : sms));
   const cudaError_t le = launch_pdl(gemm_bf16_tepi_kernel<NBUF>, grid, dim3(320), smem, st, ta, tb, tr, to, bias, act, has_res,
-                                    post_relu, M, N, K, stages);
+                                    post_relu, M, N, K, stages, cg);
   return set_cuda_error(le != cudaSuccess ? le : cudaGetLastError());
 }
 
@@ -1272,12 +1285,17 @@ static int gemm_dispatch(const RalfGemmArgs* a, const CUtensorMap& ta, int bn, c
       return set_cuda_error(cudaGetLastError());
     }
   }
-  // Bottleneck-tail shape class -> the TMA-epilogue kernel (RALF_GEMM_TEPI=0 keeps the register-staged epilogue: A/B runs)
+  // Bottleneck-tail shape class -> the TMA-epilogue kernel (RALF_GEMM_TEPI=0 keeps the register-staged epilogue: A/B runs;
+  // RALF_TEPI_KMAX = longest K it takes, its operand ring being two stages deep)
   static const bool tepi = !(getenv("RALF_GEMM_TEPI") && atoi(getenv("RALF_GEMM_TEPI")) == 0);
   static const bool fold_on = !(getenv("RALF_GEMM_FOLD") && atoi(getenv("RALF_GEMM_FOLD")) == 0);
-  if (tepi && fold_on && bn == 128 && np == 3 && !cg.enabled && a->K <= 256 && a->N % 128 == 0 && a->M >= 128 * 148 &&
-      ep.out_split && ep.split_lo && !ep.out_f32 && !ep.out_kv24 && !ep.res && a->rows_per_group <= 0 && ep.res_row_mod <= 0 &&
-      ep.vec_ok && ep.act != 2) {
+  static const int tepi_kmax = getenv("RALF_TEPI_KMAX") ? atoi(getenv("RALF_TEPI_KMAX")) : 256;
+  static const int tepi_k64 = getenv("RALF_TEPI_K64") ? atoi(getenv("RALF_TEPI_K64")) : 14;  // stages * 10 + chunk buffers
+  // implicit convolutions qualify when every M tile is a full, contiguous block of 128 output rows
+  const bool cg_full = !cg.enabled || (cg.Wo * cg.BH * cg.NB == 128 && cg.Ho % cg.BH == 0 && cg.B % cg.NB == 0);
+  if (tepi && fold_on && bn == 128 && np == 3 && cg_full && a->K <= tepi_kmax && a->N % 128 == 0 &&
+      static_cast<long long>((a->M + 127) / 128) * (a->N / 128) >= 2 * num_sms() && ep.out_split && ep.split_lo && !ep.out_f32 &&
+      !ep.out_kv24 && !ep.res && a->rows_per_group <= 0 && ep.res_row_mod <= 0 && ep.vec_ok && ep.act != 2) {
     CUtensorMap tr, to;
     rc = make_chunk_tmap(&to, ep.out_split + ep.out_col0, a->N, a->M, ep.out_ld, ep.out_plane);
     if (rc) return rc;
@@ -1287,8 +1305,10 @@ static int gemm_dispatch(const RalfGemmArgs* a, const CUtensorMap& ta, int bn, c
       if (rc) return rc;
     }
     const int nkb = (a->K + 63) / 64;
-    return nkb == 1 ? launch_tepi<4>(ta, tb, tr, to, ep.bias, ep.act, ep.res_split != nullptr, ep.post_relu, a->M, a->N, a->K, 1, st)
-                    : launch_tepi<3>(ta, tb, tr, to, ep.bias, ep.act, ep.res_split != nullptr, ep.post_relu, a->M, a->N, a->K, 2, st);
+    const int has_res = ep.res_split != nullptr;
+    if (nkb == 1 && tepi_k64 == 14)
+      return launch_tepi<4>(ta, tb, tr, to, ep.bias, ep.act, has_res, ep.post_relu, a->M, a->N, a->K, 1, cg, st);
+    return launch_tepi<3>(ta, tb, tr, to, ep.bias, ep.act, has_res, ep.post_relu, a->M, a->N, a->K, 2, cg, st);
   }
 #define RALF_GEMM_CASE(BN_, NP_) \
   if (bn == BN_ && np == NP_) return launch_gemm<BN_, NP_>(ta, tb, ep, a->M, a->N, a->K, st, cg);
@@ -1328,40 +1348,50 @@ extern "C" int ralf_gemm(const RalfGemmArgs* a, void* stream) {
   if (rc) return rc;
   ConvGeom cg;
   cg.enabled = 0;
-  cg.B = cg.Ho = cg.Wo = cg.BH = cg.NB = cg.hblocks = cg.cblocks = cg.KW = 1;
+  cg.B = cg.Ho = cg.Wo = cg.BH = cg.NB = cg.hblocks = cg.cblocks = cg.KW = cg.stride = 1;
   cg.pad = 0;
   return gemm_dispatch(a, ta, bn, cg, stream);
 }
 
-// Stride-1 "same" convolution as an implicit GEMM: args->A = NHWC split activation [planes][B*H*W, C] (dense rows,
-// lda == C), args->W = [planes][N, KH*KW*C] with k = (kh*KW + kw)*C + c, args->M = B*H*W, args->K = KH*KW*C.
-// The epilogue fields mean what they mean for ralf_gemm.  C % 64 == 0, W <= 128.
-extern "C" int ralf_conv_gemm(const RalfGemmArgs* a, int B, int H, int W, int C, int KH, int KW, void* stream) {
+// Convolution (stride 1 or 2, padding KH / 2) as an implicit GEMM: args->A = NHWC split activation [planes][B*H*W, C]
+// (dense rows, lda == C), args->W = [planes][N, KH*KW*C] with k = (kh*KW + kw)*C + c, args->M = B*Ho*Wo output positions
+// (Ho = (H + 2*(KH/2) - KH) / stride + 1), args->K = KH*KW*C.  The epilogue fields mean what they mean for ralf_gemm.
+// C % 64 == 0, Wo <= 128.  Stride 2 uses the tensor map's element strides: a tap's box skips every other input position.
+extern "C" int ralf_conv_gemm_strided(const RalfGemmArgs* a, int B, int H, int W, int C, int KH, int KW, int stride,
+                                      void* stream) {
   if (!a || a->M <= 0 || a->N <= 0 || a->K <= 0) return RALF_ERR_SHAPE;
   if (a->npass != 1 && a->npass != 3) return RALF_ERR_SHAPE;
   if (!a->A || !a->W) return RALF_ERR_NULL;
-  if (B <= 0 || H <= 0 || W <= 0 || W > 128 || C <= 0 || (C % 64) || KH != KW || !(KH & 1) || KH > 7) return RALF_ERR_SHAPE;
-  if (a->M != B * H * W || a->K != KH * KW * C || a->lda != C) return RALF_ERR_SHAPE;
+  if (stride != 1 && stride != 2) return RALF_ERR_SHAPE;
+  if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C % 64) || KH != KW || !(KH & 1) || KH > 7) return RALF_ERR_SHAPE;
+  const int pad = KH / 2;
+  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  if (Wo > 128 || a->M != B * Ho * Wo || a->K != KH * KW * C || a->lda != C) return RALF_ERR_SHAPE;
   if (a->ldw % 8) return RALF_ERR_ALIGN;
   const int planes = a->npass == 3 ? 2 : 1;
   ConvGeom cg;
   cg.enabled = 1;
-  cg.B = B; cg.Ho = H; cg.Wo = W;
-  cg.BH = 128 / W < H ? 128 / W : H;
-  cg.NB = cg.BH == H ? 128 / (W * H) : 1;
+  cg.B = B; cg.Ho = Ho; cg.Wo = Wo;
+  cg.BH = 128 / Wo < Ho ? 128 / Wo : Ho;
+  cg.NB = cg.BH == Ho ? 128 / (Wo * Ho) : 1;
   if (cg.NB < 1) cg.NB = 1;
   if (cg.NB > B) cg.NB = B;
-  cg.hblocks = (H + cg.BH - 1) / cg.BH;
+  cg.hblocks = (Ho + cg.BH - 1) / cg.BH;
   cg.cblocks = C / 64;
   cg.KW = KW;
-  cg.pad = KH / 2;
+  cg.pad = pad;
+  cg.stride = stride;
   const long long mt = static_cast<long long>((B + cg.NB - 1) / cg.NB) * cg.hblocks;
   const int bn = gemm_pick_bn(a, mt);
   if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return RALF_ERR_SHAPE;
   CUtensorMap ta;
-  int rc = make_conv_tmap(&ta, a->A, C, W, H, B, planes, a->a_plane, W, cg.BH, cg.NB);
+  int rc = make_conv_tmap(&ta, a->A, C, W, H, B, planes, a->a_plane, Wo, cg.BH, cg.NB, stride);
   if (rc) return rc;
   return gemm_dispatch(a, ta, bn, cg, stream);
+}
+
+extern "C" int ralf_conv_gemm(const RalfGemmArgs* a, int B, int H, int W, int C, int KH, int KW, void* stream) {
+  return ralf_conv_gemm_strided(a, B, H, W, C, KH, KW, 1, stream);
 }
 
 // ResNet stem as an implicit GEMM over the space-to-depth image of ralf_stem_s2d (nn_kernels.cu):
@@ -1386,6 +1416,7 @@ extern "C" int ralf_stem_gemm(const RalfGemmArgs* a, int B, int Ho, int Wo, void
   cg.cblocks = 1;  // k-block = kh' (tap = kb, kw = 0, channel block 0)
   cg.KW = 1;
   cg.pad = 0;
+  cg.stride = 1;
   const long long mt = static_cast<long long>(B) * cg.hblocks;
   const int bn = gemm_pick_bn(a, mt);
   if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return RALF_ERR_SHAPE;

@@ -46,8 +46,10 @@ KVFMT = 24 if os.environ.get("RALF_KVFMT", "16") == "24" else 16
 # tensor core, and an SS-mode tcgen05.mma at N = 16 costs ~92 cycles whatever N is (operand fetch of the 128-row weight
 # tile), so the chain is MMA-issue bound at ~0.6 us per 32 KB weight tile.  Opt-in (RALF_DECODE_CHAIN=1) for A/B runs.
 DECODE_CHAIN = os.environ.get("RALF_DECODE_CHAIN", "0") != "0"
-# 3x3 stride-1 convolutions as implicit GEMMs (ralf_conv_gemm); RALF_IMPLICIT_CONV=0 restores im2col + GEMM for A/B runs.
+# 3x3 convolutions as implicit GEMMs (ralf_conv_gemm_strided); RALF_IMPLICIT_CONV=0 restores im2col + GEMM for A/B runs,
+# RALF_STRIDED_CONV=0 only for the stride-2 3x3 / 1x1 convolutions (TMA boxes with element strides).
 IMPLICIT_CONV = os.environ.get("RALF_IMPLICIT_CONV", "1") != "0"
+STRIDED_CONV = os.environ.get("RALF_STRIDED_CONV", "1") != "0"
 
 
 def _sine_pe_1d(max_len: int, d_model: int) -> torch.Tensor:
@@ -257,18 +259,23 @@ class Engine:
         feats = {}
         for (p, li, stride, planes, has_ds) in self.blocks:
             _, t1 = self._gemm(x, p + ".c1", act="relu", want_f32=False, want_split=True)
-            if stride == 1 and IMPLICIT_CONV and W <= 128:  # implicit GEMM: the 3x3 taps are TMA boxes, no im2col
-                Ho, Wo = H, W
+            strided_ok = STRIDED_CONV and H % 2 == 0 and W % 2 == 0
+            if IMPLICIT_CONV and ((stride == 1 and W <= 128) or (stride == 2 and strided_ok and W <= 256)):
+                # implicit GEMM: the 3x3 taps are TMA boxes (element strides 2 for the stride-2 blocks), no im2col
+                Ho, Wo = H // stride, W // stride
                 _, t2 = self._gemm(t1, p + ".c2", act="relu", want_f32=False, want_split=True,
-                                   conv=(B, H, W, planes, 3, 3))
+                                   conv=(B, H, W, planes, 3, 3, stride))
             else:
                 a2, Ho, Wo = ops.im2col(t1, B, H, W, planes, 3, 3, stride, 1)
                 _, t2 = self._gemm(a2, p + ".c2", act="relu", want_f32=False, want_split=True)
                 del a2
             del t1
             if has_ds:
-                xs = x if stride == 1 else ops.im2col(x, B, H, W, C, 1, 1, stride, 0)[0]
-                _, idt = self._gemm(xs, p + ".ds", want_f32=False, want_split=True)
+                if stride == 2 and IMPLICIT_CONV and strided_ok and W <= 256:
+                    _, idt = self._gemm(x, p + ".ds", want_f32=False, want_split=True, conv=(B, H, W, C, 1, 1, 2))
+                else:
+                    xs = x if stride == 1 else ops.im2col(x, B, H, W, C, 1, 1, stride, 0)[0]
+                    _, idt = self._gemm(xs, p + ".ds", want_f32=False, want_split=True)
             else:
                 idt = x
             _, x = self._gemm(t2, p + ".c3", res_split=idt, post_relu=True, want_f32=False, want_split=True)

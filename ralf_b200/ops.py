@@ -79,8 +79,8 @@ def gemm(
     """D = A . W^T with the fused epilogue of ``ralf_gemm`` (include/ralf_b200.h).
 
     Outputs are allocated when not supplied ([M, N] fp32 and/or [2, M, N] split bf16).
-    ``conv = (B, H, W, C, KH, KW)``: ``a`` is the NHWC activation [2, B*H*W, C] and the call is the stride-1 "same"
-    convolution ``ralf_conv_gemm`` (implicit GEMM, K = KH*KW*C taken from ``w``).
+    ``conv = (B, H, W, C, KH, KW[, stride])``: ``a`` is the NHWC activation [2, B*H*W, C] and the call is the
+    convolution ``ralf_conv_gemm_strided`` (implicit GEMM, padding KH // 2, stride 1 or 2, K = KH*KW*C taken from ``w``).
     ``stem = (B, Ho, Wo)``: ``a`` is the space-to-depth buffer of :func:`stem_s2d` ([2, B*(Ho+3)*(Wo+3), 16]) and the
     call is ``ralf_stem_gemm`` (K = 256)."""
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 3 and w.dim() == 3
@@ -91,9 +91,11 @@ def gemm(
         assert a.shape[1] == sB * (sHo + 3) * (sWo + 3) and K == 16 and w.shape[2] == 256 and a.is_contiguous()
         M, K = sB * sHo * sWo, 256
     if conv is not None:
-        cB, cH, cW, cC, cKH, cKW = conv
+        cB, cH, cW, cC, cKH, cKW = conv[:6]
+        cS = conv[6] if len(conv) > 6 else 1
         assert M == cB * cH * cW and K == cC and a.stride(1) == cC and w.shape[2] == cKH * cKW * cC, (a.shape, w.shape)
         K = w.shape[2]
+        M = cB * ((cH + 2 * (cKH // 2) - cKH) // cS + 1) * ((cW + 2 * (cKW // 2) - cKW) // cS + 1)
     assert w.shape[2] == K, (a.shape, w.shape)
     assert a.stride(2) == 1 and w.stride(2) == 1
     if out_f32 is None and want_f32:
@@ -142,7 +144,7 @@ def gemm(
     if stem is not None:
         check(_lib.lib().ralf_stem_gemm(C.byref(g), *stem, _stream()), "ralf_stem_gemm")
     elif conv is not None:
-        check(_lib.lib().ralf_conv_gemm(C.byref(g), *conv, _stream()), "ralf_conv_gemm")
+        check(_lib.lib().ralf_conv_gemm_strided(C.byref(g), cB, cH, cW, cC, cKH, cKW, cS, _stream()), "ralf_conv_gemm_strided")
     else:
         check(_lib.lib().ralf_gemm(C.byref(g), _stream()), "ralf_gemm")
     return out_f32, out_split

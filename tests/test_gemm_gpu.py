@@ -214,3 +214,31 @@ def test_gemm_tma_epilogue_is_bit_identical_to_register_epilogue(cuda_device, M,
     assert (flat[:guard] == 7.0).all() and (flat[-guard:] == 7.0).all()
     ref = _ref(a, w, bias, act, ops.unsplit(res_s) if residual else None, post_relu=residual)
     assert (ops.unsplit(out_t).double() - ref).abs().max().item() <= 4e-5 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("B,H,W,C,N,KH", [(2, 64, 64, 128, 128, 3), (3, 32, 32, 256, 256, 3), (5, 16, 16, 512, 64, 3),
+                                          (2, 64, 64, 256, 512, 1), (3, 16, 16, 1024, 128, 1), (2, 22, 15, 256, 256, 3),
+                                          (1, 44, 30, 128, 64, 1), (160, 64, 64, 256, 512, 1)])
+def test_conv_gemm_stride2_matches_conv2d_fp64_and_im2col(cuda_device, B, H, W, C, N, KH):
+    """ResNet's stride-2 3x3 (pad 1) and 1x1 downsample convolutions as implicit GEMMs: the taps are TMA boxes with
+    element strides 2.  Against torch conv2d in float64, and bit-identical to im2col + plain GEMM (same k order, same
+    MMAs).  22x15 / 44x30: odd sizes and partial tiles; the last case is large enough for the TMA-epilogue kernel."""
+    from ralf_b200 import ops
+
+    g = torch.Generator(device=cuda_device).manual_seed(B * H + W + C + KH)
+    x = torch.randn(B, H, W, C, device=cuda_device, generator=g)
+    w = torch.randn(N, C, KH, KH, device=cuda_device, generator=g) / (C * KH * KH) ** 0.5
+    bias = torch.randn(N, device=cuda_device, generator=g)
+    xs = ops.split_bf16(x.reshape(B * H * W, C))
+    ws = ops.split_bf16(w.permute(0, 2, 3, 1).reshape(N, KH * KH * C).contiguous())
+    _, y = ops.gemm(xs, ws, bias=bias, act="relu", want_f32=False, want_split=True, conv=(B, H, W, C, KH, KH, 2))
+    cols, Ho, Wo = ops.im2col(xs, B, H, W, C, KH, KH, 2, KH // 2)
+    assert y.shape[1] == B * Ho * Wo
+    _, y2 = ops.gemm(cols, ws, bias=bias, act="relu", want_f32=False, want_split=True, block_n=64 if N % 128 else 0)
+    if N % 128 == 0:
+        assert torch.equal(y.view(torch.int16), y2.view(torch.int16))
+    ref = torch.nn.functional.conv2d(ops.unsplit(xs).view(B, H, W, C).permute(0, 3, 1, 2).double(),
+                                     ops.unsplit(ws).view(N, KH, KH, C).permute(0, 3, 1, 2).double(), bias.double(),
+                                     stride=2, padding=KH // 2).relu().permute(0, 2, 3, 1).reshape(B * Ho * Wo, N)
+    err = (ops.unsplit(y).double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= 4e-5, err
