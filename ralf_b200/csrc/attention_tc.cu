@@ -52,11 +52,7 @@ __device__ __forceinline__ void split8(const float4 a, const float4 b, uint4& hi
   uint32_t h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    __nv_bfloat16 h0, l0, h1, l1;
-    split_bf16(f[2 * i], h0, l0);
-    split_bf16(f[2 * i + 1], h1, l1);
-    h[i] = pack_bf16(h0, h1);
-    l[i] = pack_bf16(l0, l1);
+    split2_bf16(f[2 * i], f[2 * i + 1], h[i], l[i]);
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
@@ -207,11 +203,7 @@ attention_tc_kernel(const float* __restrict__ q, const int ldq, const float* __r
           const float p0 = (c + j < Tk) ? exp2f(fmaf(__uint_as_float(sv[j]), sl2, -mxs)) : 0.f;
           const float p1 = (c + j + 1 < Tk) ? exp2f(fmaf(__uint_as_float(sv[j + 1]), sl2, -mxs)) : 0.f;
           lsum += p0 + p1;
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(p0, h0, l0);
-          split_bf16(p1, h1, l1);
-          ph[j >> 1] = pack_bf16(h0, h1);
-          pl[j >> 1] = pack_bf16(l0, l1);
+          split2_bf16(p0, p1, ph[j >> 1], pl[j >> 1]);
         }
       } else {
         if (c >= nks * 16) break;  // k-steps past the last key are never issued
@@ -261,11 +253,7 @@ attention_tc_kernel(const float* __restrict__ q, const int ldq, const float* __r
             uint32_t hw[4], lw[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(__uint_as_float(ov[j + 2 * e]) * inv, h0, l0);
-              split_bf16(__uint_as_float(ov[j + 2 * e + 1]) * inv, h1, l1);
-              hw[e] = pack_bf16(h0, h1);
-              lw[e] = pack_bf16(l0, l1);
+              split2_bf16(__uint_as_float(ov[j + 2 * e]) * inv, __uint_as_float(ov[j + 2 * e + 1]) * inv, hw[e], lw[e]);
             }
             *reinterpret_cast<uint4*>(out_split + orow + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
             *reinterpret_cast<uint4*>(out_split + out_plane + orow + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
@@ -448,11 +436,7 @@ attention_tc2_kernel(const float* __restrict__ q, const int ldq, const float* __
           const float p0 = (c + j < Tk) ? exp2f(fmaf(__uint_as_float(sv[j]), sl2, -mxs)) : 0.f;
           const float p1 = (c + j + 1 < Tk) ? exp2f(fmaf(__uint_as_float(sv[j + 1]), sl2, -mxs)) : 0.f;
           lsum += p0 + p1;
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(p0, h0, l0);
-          split_bf16(p1, h1, l1);
-          ph[j >> 1] = pack_bf16(h0, h1);
-          pl[j >> 1] = pack_bf16(l0, l1);
+          split2_bf16(p0, p1, ph[j >> 1], pl[j >> 1]);
         }
       } else {
         if (c >= nks * 16) break;
@@ -503,11 +487,7 @@ attention_tc2_kernel(const float* __restrict__ q, const int ldq, const float* __
             uint32_t hw[4], lw[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(__uint_as_float(ov[j + 2 * e]) * inv, h0, l0);
-              split_bf16(__uint_as_float(ov[j + 2 * e + 1]) * inv, h1, l1);
-              hw[e] = pack_bf16(h0, h1);
-              lw[e] = pack_bf16(l0, l1);
+              split2_bf16(__uint_as_float(ov[j + 2 * e]) * inv, __uint_as_float(ov[j + 2 * e + 1]) * inv, hw[e], lw[e]);
             }
             *reinterpret_cast<uint4*>(out_split + orow + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
             *reinterpret_cast<uint4*>(out_split + out_plane + orow + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
@@ -677,11 +657,7 @@ attention_tc_big_kernel(const float* __restrict__ q, const int ldq, const float*
         const float p0 = (c + j < Tk) ? exp2f(fmaf(__uint_as_float(sv[j]), sl2, -mxs)) : 0.f;
         const float p1 = (c + j + 1 < Tk) ? exp2f(fmaf(__uint_as_float(sv[j + 1]), sl2, -mxs)) : 0.f;
         lsum += p0 + p1;
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(p0, h0, l0);
-        split_bf16(p1, h1, l1);
-        ph[j >> 1] = pack_bf16(h0, h1);
-        pl[j >> 1] = pack_bf16(l0, l1);
+        split2_bf16(p0, p1, ph[j >> 1], pl[j >> 1]);
       }
       tmem_st_32x16(tS + trow + c, ph);       // hi of keys c .. c + 31 (2 keys per column)
       tmem_st_32x16(tS + trow + c + 16, pl);  // lo
@@ -727,11 +703,7 @@ attention_tc_big_kernel(const float* __restrict__ q, const int ldq, const float*
             uint32_t hw[4], lw[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(__uint_as_float(ov[j + 2 * e]) * inv, h0, l0);
-              split_bf16(__uint_as_float(ov[j + 2 * e + 1]) * inv, h1, l1);
-              hw[e] = pack_bf16(h0, h1);
-              lw[e] = pack_bf16(l0, l1);
+              split2_bf16(__uint_as_float(ov[j + 2 * e]) * inv, __uint_as_float(ov[j + 2 * e + 1]) * inv, hw[e], lw[e]);
             }
             *reinterpret_cast<uint4*>(out_split + orow + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
             *reinterpret_cast<uint4*>(out_split + out_plane + orow + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
@@ -748,11 +720,278 @@ attention_tc_big_kernel(const float* __restrict__ q, const int ldq, const float*
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Variant with HALF the tensor memory (RALF_ATTN_TC=3, default since round 2): attention_tc_kernel allocates all 512
+// TMEM columns, so the second CTA resident on an SM blocks in tcgen05.alloc until the first one is done -- one 4-warp CTA
+// per SM then serialises operand conversion -> MMA -> softmax -> MMA with the tensor pipe 4 % busy and the issue slots
+// 19 % (profiles/r1_attn_tc_ncu.md).  Here a CTA takes 256 columns, so TWO CTAs compute on an SM at the same time and
+// fill each other's MMA round trips:
+//   * the keys are processed in two halves of 128: S_h = Q K_h^T is a 128 x 128 tile (columns [0, 128));
+//   * P_h = exp(scale (S_h - rowmax_h)) is written IN PLACE over S_h (the 32 fp32 scores of a chunk become 16 columns
+//     of hi pairs + 16 columns of lo pairs);
+//   * each half has its own accumulator O_h (columns 128 + 64 h ..), and V^T is stored [hi rows ; lo rows] per key
+//     block so that ONE MMA with N = 64 yields P_hi.V_hi | P_hi.V_lo and a second (N = 32) adds P_lo.V_hi: two MMAs per
+//     k-step instead of three (an MMA at M = 128 costs ~92 cycles however narrow N is);
+//   * the halves are combined in registers: out = (a_0 O_0 + a_1 O_1) / (a_0 l_0 + a_1 l_1), a_h = exp(scale (m_h - m)).
+// Same operand precision (split bf16, fp32 accumulation) as the kernel above; the two-half softmax differs from the
+// single-pass one by fp32 rounding only.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int ATC3_VT_BLOCK = 2 * 32 * 128;  // one 64-key block: [hi: 32 d-rows x 128 B][lo: 32 d-rows x 128 B]
+constexpr int ATC3_SMEM = ATC_Q_BYTES + ATC_K_BYTES + 4 * ATC3_VT_BLOCK + 1024 + 64;
+
+__global__ void __launch_bounds__(128, 2)
+attention_tc3_kernel(const float* __restrict__ q, const int ldq, const float* __restrict__ k,
+                     const float* __restrict__ v, const int ldk, const int Tq, const int Tk, const float scale,
+                     __nv_bfloat16* __restrict__ out_split, const long long out_plane, float* __restrict__ out_f32,
+                     const int ldo) {
+  constexpr int DH = 32;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + ATC_Q_BYTES;
+  uint8_t* sVt = sK + ATC_K_BYTES;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sVt + 4 * ATC3_VT_BLOCK);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int h = blockIdx.x, b = blockIdx.y;
+
+  {  // K rows -> [hi | lo] swizzled rows (rows >= Tk are zero)
+    float4 kr[2][8];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int j = tid + 128 * u;
+      const float* src = k + (static_cast<long long>(b) * Tk + j) * ldk + h * DH;
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        kr[u][g] = (j < Tk) ? *reinterpret_cast<const float4*>(src + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int j = tid + 128 * u;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 hi, lo;
+        split8(kr[u][2 * g], kr[u][2 * g + 1], hi, lo);
+        *reinterpret_cast<uint4*>(sK + j * 128 + ((g ^ (j & 7)) << 4)) = hi;
+        *reinterpret_cast<uint4*>(sK + j * 128 + (((g + 4) ^ (j & 7)) << 4)) = lo;
+      }
+    }
+  }
+  {  // V -> V^T key blocks, hi rows then lo rows; thread = key pair (2 tid, 2 tid + 1)
+    float4 vr[2][8];
+    const int j = 2 * tid;
+    const float* src = v + (static_cast<long long>(b) * Tk + j) * ldk + h * DH;
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        vr[u][g] = (j + u < Tk) ? *reinterpret_cast<const float4*>(src + static_cast<long long>(u) * ldk + 4 * g)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int kb = j >> 6, jj = j & 63;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float fa[4] = {vr[0][g].x, vr[0][g].y, vr[0][g].z, vr[0][g].w};
+      const float fc[4] = {vr[1][g].x, vr[1][g].y, vr[1][g].z, vr[1][g].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int d = 4 * g + e;
+        uint32_t hp, lp;
+        split2_bf16(fa[e], fc[e], hp, lp);
+        const int off = kb * ATC3_VT_BLOCK + d * 128 + (((jj >> 3) ^ (d & 7)) << 4) + (jj & 7) * 2;
+        *reinterpret_cast<uint32_t*>(sVt + off) = hp;
+        *reinterpret_cast<uint32_t*>(sVt + 4096 + off) = lp;
+      }
+    }
+  }
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base;
+  const uint32_t trow = static_cast<uint32_t>(warp * 32) << 16;  // this warp's TMEM lane quadrant
+  uint32_t phase = 0;
+  const int nhalf = Tk > 128 ? 2 : 1;
+  const float sl2 = scale * 1.4426950408889634f;
+
+  for (int q0 = 0; q0 < Tq; q0 += 128) {
+    {  // Q tile -> [hi | lo] rows (thread = row)
+      const int r = tid;
+      float4 qr[8];
+      const float* src = q + (static_cast<long long>(b) * Tq + q0 + r) * ldq + h * DH;
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        qr[g] = (q0 + r < Tq) ? *reinterpret_cast<const float4*>(src + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 hi, lo;
+        split8(qr[2 * g], qr[2 * g + 1], hi, lo);
+        *reinterpret_cast<uint4*>(sQ + r * 128 + ((g ^ (r & 7)) << 4)) = hi;
+        *reinterpret_cast<uint4*>(sQ + r * 128 + (((g + 4) ^ (r & 7)) << 4)) = lo;
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    float mh[2] = {-INFINITY, -INFINITY}, lh[2] = {0.f, 0.f};
+#pragma unroll
+    for (int kh = 0; kh < 2; ++kh) {
+      if (kh < nhalf) {
+        const int tkh = min(Tk - kh * 128, 128);   // keys of this half
+        const int nks = (tkh + 15) >> 4;           // P.V k-steps that hold real keys
+        if (tid == 0) {
+          tc_fence_after();
+          constexpr uint32_t idesc_s = make_idesc(1, 128, 128);
+          const uint64_t dq = make_sw128_kmajor_desc(smem_u32(sQ));
+          const uint64_t dk = make_sw128_kmajor_desc(smem_u32(sK) + kh * 128 * 128);
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {  // K = 32 = 2 k-steps of 16; +4 = the lo half of the row (64 B)
+            mma_bf16_ss(tS, dq + 2 * s, dk + 4 + 2 * s, idesc_s, s != 0);
+            mma_bf16_ss(tS, dq + 4 + 2 * s, dk + 2 * s, idesc_s, 1);
+            mma_bf16_ss(tS, dq + 2 * s, dk + 2 * s, idesc_s, 1);
+          }
+          tc_commit(bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 128; c += 32) {
+          if (c >= tkh) break;
+          uint32_t sv[32];
+          tmem_ld_32x32(tS + trow + c, sv);
+          tmem_ld_wait();
+          if (c + 32 <= tkh) {  // warp-uniform: only the last chunk of a ragged key count needs the per-key mask
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(sv[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (c + j < tkh) ? __uint_as_float(sv[j]) : -INFINITY);
+          }
+        }
+        float lsum = 0.f;
+        const float mxs = mx * sl2;
+#pragma unroll 1
+        for (int c = 0; c < 128; c += 32) {
+          uint32_t ph[16], pl[16];
+          if (c < tkh) {
+            uint32_t sv[32];
+            tmem_ld_32x32(tS + trow + c, sv);
+            tmem_ld_wait();
+            if (c + 32 <= tkh) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                const float p0 = ex2_ftz(fmaf(__uint_as_float(sv[j]), sl2, -mxs));
+                const float p1 = ex2_ftz(fmaf(__uint_as_float(sv[j + 1]), sl2, -mxs));
+                lsum += p0 + p1;
+                split2_bf16(p0, p1, ph[j >> 1], pl[j >> 1]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                const float p0 = (c + j < tkh) ? ex2_ftz(fmaf(__uint_as_float(sv[j]), sl2, -mxs)) : 0.f;
+                const float p1 = (c + j + 1 < tkh) ? ex2_ftz(fmaf(__uint_as_float(sv[j + 1]), sl2, -mxs)) : 0.f;
+                lsum += p0 + p1;
+                split2_bf16(p0, p1, ph[j >> 1], pl[j >> 1]);
+              }
+            }
+          } else {
+            if (c >= nks * 16) break;  // k-steps past the last key are never issued
+#pragma unroll
+            for (int j = 0; j < 16; ++j) ph[j] = pl[j] = 0u;
+          }
+          tmem_st_32x16(tS + trow + c, ph);       // in place: hi pairs over the chunk's first 16 columns,
+          tmem_st_32x16(tS + trow + c + 16, pl);  // lo pairs over the other 16
+        }
+        mh[kh] = mx;
+        lh[kh] = lsum;
+        tmem_st_wait();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+          tc_fence_after();
+          constexpr uint32_t idesc_64 = make_idesc(1, 128, 64);
+          constexpr uint32_t idesc_32 = make_idesc(1, 128, 32);
+          const uint32_t tO = tmem_base + 128 + 64 * kh;
+          for (int ks = 0; ks < nks; ++ks) {
+            const uint32_t vt = smem_u32(sVt) + (kh * 2 + (ks >> 2)) * ATC3_VT_BLOCK;
+            const uint64_t bd = make_sw128_kmajor_desc(vt) + 2 * (ks & 3);
+            const uint32_t a_hi = tS + (ks >> 1) * 32 + (ks & 1) * 8;
+            mma_bf16_ts(tO, a_hi, bd, idesc_64, ks != 0);      // [P_hi.V_hi | P_hi.V_lo]
+            mma_bf16_ts(tO + 32, a_hi + 16, bd, idesc_32, 1);  // + P_lo.V_hi
+          }
+          tc_commit(bar);
+        }
+        mbar_wait(bar, phase);  // P is consumed: the next half's S may overwrite it
+        phase ^= 1;
+        tc_fence_after();
+      }
+    }
+    {
+      const float m = fmaxf(mh[0], mh[1]);
+      const float a0 = ex2_ftz((mh[0] - m) * sl2);
+      const float a1 = nhalf > 1 ? ex2_ftz((mh[1] - m) * sl2) : 0.f;
+      const float inv = 1.f / (a0 * lh[0] + a1 * lh[1]);
+      float o[32];
+      {
+        uint32_t u0[32], u1[32];
+        tmem_ld_32x32(tmem_base + 128 + trow, u0);
+        tmem_ld_32x32(tmem_base + 160 + trow, u1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = a0 * (__uint_as_float(u0[j]) + __uint_as_float(u1[j]));
+      }
+      if (nhalf > 1) {
+        uint32_t u0[32], u1[32];
+        tmem_ld_32x32(tmem_base + 192 + trow, u0);
+        tmem_ld_32x32(tmem_base + 224 + trow, u1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = fmaf(a1, __uint_as_float(u0[j]) + __uint_as_float(u1[j]), o[j]);
+      }
+      const int r = q0 + tid;
+      if (r < Tq) {
+        const long long orow = (static_cast<long long>(b) * Tq + r) * ldo + h * DH;
+        if (out_f32) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(out_f32 + orow + j) = make_float4(o[j] * inv, o[j + 1] * inv, o[j + 2] * inv, o[j + 3] * inv);
+        }
+        if (out_split) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              split2_bf16(o[j + 2 * e] * inv, o[j + 2 * e + 1] * inv, hw[e], lw[e]);
+            }
+            *reinterpret_cast<uint4*>(out_split + orow + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(out_split + out_plane + orow + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
 // Returns 1 when the tensor-core kernel took the call, 0 when the shape is outside its class, < 0 on error.
 int attention_tc_try(const float* q, int ldq, const float* k, const float* v, int ldk, const unsigned char* mask, int B,
                      int H, int Tq, int Tk, int head_dim, int causal, float scale, void* out_split,
                      long long out_plane, float* out_f32, int ldo, cudaStream_t st) {
-  static const int variant = getenv("RALF_ATTN_TC") ? atoi(getenv("RALF_ATTN_TC")) : 1;  // 0 off, 1 default, 2 = 8-warp kernel
+  // 0 off, 1 = round-1 kernel (512 TMEM columns), 2 = 8-warp kernel, 3 = half-TMEM kernel, two computing CTAs per SM (default)
+  static const int variant = getenv("RALF_ATTN_TC") ? atoi(getenv("RALF_ATTN_TC")) : 3;
   const bool enabled = variant != 0;
   // 256 < Tk <= 480 (the reference's real 350 x 240 canvases: 330 image tokens) on the tensor cores: default since round 2
   // (verified against fp64 on hardware; encode of 128 real-size canvases 15.4 vs 18.0 ms); RALF_ATTN_TC_BIG=0 = CUDA cores
@@ -783,6 +1022,22 @@ int attention_tc_try(const float* q, int ldq, const float* k, const float* v, in
                                                                 out_f32, ldo);
     const int rcb = set_cuda_error(cudaGetLastError());
     return rcb ? rcb : 1;
+  }
+  if (variant == 3) {
+    static bool attr3_set = false;
+    if (!attr3_set) {
+      cudaError_t e = cudaFuncSetAttribute(attention_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC3_SMEM);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(attention_tc3_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+      if (e != cudaSuccess) return set_cuda_error(e);
+      attr3_set = true;
+    }
+    attention_tc3_kernel<<<dim3(H, B), 128, ATC3_SMEM, st>>>(q, ldq, k, v, ldk, Tq, Tk, scale,
+                                                             reinterpret_cast<__nv_bfloat16*>(out_split), out_plane,
+                                                             out_f32, ldo);
+    const int rc3 = set_cuda_error(cudaGetLastError());
+    return rc3 ? rc3 : 1;
   }
   if (variant == 2) {
     static bool attr2_set = false;

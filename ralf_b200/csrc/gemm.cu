@@ -331,11 +331,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpi& ep, const uint
             uint32_t hw[4], lw[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(x[8 * j + 2 * q], h0, l0);
-              split_bf16(x[8 * j + 2 * q + 1], h1, l1);
-              hw[q] = pack_bf16(h0, h1);
-              lw[q] = pack_bf16(l0, l1);
+              split2_bf16(x[8 * j + 2 * q], x[8 * j + 2 * q + 1], hw[q], lw[q]);
             }
             mh[j] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
             ml[j] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
@@ -593,29 +589,31 @@ __device__ __forceinline__ void bulk_wait_read() {
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+template <int BN_>
 struct TepiCfg {
-  static constexpr int BN = 128;
-  static constexpr int STAGE_BYTES = 2 * (128 * 128 + BN * 128);  // 64 KB: A hi/lo + W hi/lo of one k-block
+  static constexpr int BN = BN_;                                   // 128, or 64 for the 64-channel layers
+  static constexpr int STAGE_BYTES = 2 * (128 * 128 + BN * 128);  // 64 / 48 KB: A hi/lo + W hi/lo of one k-block
   static constexpr int CHUNK_BYTES = 4096;                         // [2][32][32] bf16
   static constexpr int smem_bytes(int stages, int nbuf) {
     return stages * STAGE_BYTES + 8 * nbuf * CHUNK_BYTES + 1024 /*align*/ + 1024 /*barriers*/;
   }
 };
 
-template <int NBUF>
+template <int BN, int NBUF>
 __global__ void __launch_bounds__(320, 1)
 gemm_bf16_tepi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
                       const float* __restrict__ bias, const int act, const int has_res, const int post_relu, const int M,
                       const int N, const int K, const int STAGES, const ConvGeom cg) {
-  constexpr int BN = TepiCfg::BN;
+  using TCfg = TepiCfg<BN>;
+  constexpr int CPT = BN / 64;  // 32-column chunks per tile and epilogue warp
   constexpr int A_BYTES = 128 * 128, B_BYTES = BN * 128;
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
-  uint8_t* chunks = smem + STAGES * TepiCfg::STAGE_BYTES;  // 8 warps x NBUF x 4 KB, 1024-byte aligned
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(chunks + 8 * NBUF * TepiCfg::CHUNK_BYTES);
+  uint8_t* chunks = smem + STAGES * TCfg::STAGE_BYTES;  // 8 warps x NBUF x 4 KB, 1024-byte aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(chunks + 8 * NBUF * TCfg::CHUNK_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -628,8 +626,8 @@ gemm_bf16_tepi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const int num_tiles = ((M + 127) / 128) * tiles_n;
   const int nkb = (K + 63) / 64;
   auto load_stage = [&](const int mt, const int n0, const int kb, const int s) {
-    mbar_expect_tx(&full_bar[s], TepiCfg::STAGE_BYTES);
-    uint8_t* st = smem + s * TepiCfg::STAGE_BYTES;
+    mbar_expect_tx(&full_bar[s], TCfg::STAGE_BYTES);
+    uint8_t* st = smem + s * TCfg::STAGE_BYTES;
     if (cg.enabled) {  // implicit convolution whose M tiles are all full: tile mt = output rows [128 mt, 128 mt + 128)
       const int g = mt / cg.hblocks, hb = mt - g * cg.hblocks;
       const int tap = kb / cg.cblocks, cb = kb - tap * cg.cblocks;
@@ -708,7 +706,7 @@ gemm_bf16_tepi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t a_hi = base_u32 + s * TepiCfg::STAGE_BYTES;
+          const uint32_t a_hi = base_u32 + s * TCfg::STAGE_BYTES;
           const uint32_t b_hi = a_hi + 2 * A_BYTES;
           const uint64_t da_hi = make_sw128_kmajor_desc(a_hi);
           const uint64_t da_lo = make_sw128_kmajor_desc(a_hi + A_BYTES);
@@ -726,46 +724,55 @@ gemm_bf16_tepi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
     }
   } else {
-    // Epilogue warp ew: TMEM lanes / tile rows 32 * (ew % 4) .., columns 64 * (ew / 4) .. + 64 of every tile, as two
-    // chunks of 32 columns; chunk g of this warp lives in buffer g % NBUF.
+    // Epilogue warp ew: TMEM lanes / tile rows 32 * (ew % 4) .., columns (BN / 2) * (ew / 4) .. + BN / 2 of every tile,
+    // as CPT chunks of 32 columns; chunk g of this warp lives in buffer g % NBUF.  Tile coordinates advance by the
+    // grid stride without divisions (they would cost more than the chunk's arithmetic).
     const int ew = warp - 2;
     const int quad = warp & 3;
     const int half = ew >> 2;
-    uint8_t* cb = chunks + ew * NBUF * TepiCfg::CHUNK_BYTES;
+    uint8_t* cb = chunks + ew * NBUF * TCfg::CHUNK_BYTES;
     uint64_t* rb = res_bar + ew * NBUF;
     const int my_tiles = static_cast<int>(blockIdx.x) < num_tiles ? (num_tiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
-    const int total = 2 * my_tiles;
-    auto coords = [&](const int g, int& col, int& row) {
-      const int tile = blockIdx.x + (g >> 1) * gridDim.x;
-      col = (tile % tiles_n) * BN + half * 64 + (g & 1) * 32;
-      row = (tile / tiles_n) * 128 + quad * 32;
-    };
-    auto issue_res = [&](const int g) {  // lane 0 only
-      if (g < total) {
-        int col, row;
-        coords(g, col, row);
-        mbar_expect_tx(&rb[g % NBUF], TepiCfg::CHUNK_BYTES);
-        tma_load_3d(&tmR, &rb[g % NBUF], cb + (g % NBUF) * TepiCfg::CHUNK_BYTES, col, row, 0);
+    const int total = CPT * my_tiles;
+    const int step_m = static_cast<int>(gridDim.x) / tiles_n, step_n = static_cast<int>(gridDim.x) % tiles_n;
+    struct Pos { int mt, nt, c; };
+    auto advance = [&](Pos& p) {  // next chunk of this warp
+      if (++p.c == CPT) {
+        p.c = 0;
+        p.mt += step_m;
+        p.nt += step_n;
+        if (p.nt >= tiles_n) { p.nt -= tiles_n; ++p.mt; }
       }
     };
+    Pos cur{static_cast<int>(blockIdx.x) / tiles_n, static_cast<int>(blockIdx.x) % tiles_n, 0};
+    Pos pre = cur;  // position of the next residual chunk to request (lane 0)
+    int gpre = 0;
+    auto issue_res = [&]() {  // lane 0 only: request chunk gpre
+      if (gpre < total) {
+        mbar_expect_tx(&rb[gpre % NBUF], TCfg::CHUNK_BYTES);
+        tma_load_3d(&tmR, &rb[gpre % NBUF], cb + (gpre % NBUF) * TCfg::CHUNK_BYTES, pre.nt * BN + half * (BN / 2) + pre.c * 32,
+                    pre.mt * 128 + quad * 32, 0);
+        advance(pre);
+      }
+      ++gpre;
+    };
     if (has_res && lane == 0) {
-      for (int g = 0; g < NBUF - 1; ++g) issue_res(g);
+      for (int g = 0; g < NBUF - 1; ++g) issue_res();
     }
     const int sw = (lane >> 1) & 3;  // SWIZZLE_64B: 16-byte piece j of row r sits at piece j ^ ((r >> 1) & 3)
-    for (int g = 0; g < total; ++g) {
-      const int it = g >> 1, c = g & 1, buf = it & 1;
-      int col, row;
-      coords(g, col, row);
+    for (int g = 0; g < total; ++g, advance(cur)) {
+      const int it = g / CPT, c = g % CPT, buf = it & 1;
+      const int col = cur.nt * BN + half * (BN / 2) + c * 32, row = cur.mt * 128 + quad * 32;
       if (c == 0) {
         mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
         tc_fence_after();
       }
-      const uint32_t tacc = tmem_base + buf * ACC_COLS + (static_cast<uint32_t>(quad * 32) << 16) + half * 64 + c * 32;
+      const uint32_t tacc = tmem_base + buf * ACC_COLS + (static_cast<uint32_t>(quad * 32) << 16) + half * (BN / 2) + c * 32;
       uint32_t v[32], v2[32];
       tmem_ld_32x32(tacc, v);
       tmem_ld_32x32(tacc + BN, v2);
       tmem_ld_wait();
-      if (c == 1) {  // the accumulator buffer is drained: hand it back to the MMA warp before the memory work
+      if (c == CPT - 1) {  // the accumulator buffer is drained: hand it back to the MMA warp before the memory work
         tc_fence_before();
         mbar_arrive(&tempty_bar[buf]);
       }
@@ -783,7 +790,7 @@ gemm_bf16_tepi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
       }
-      uint4* bq = reinterpret_cast<uint4*>(cb + (g % NBUF) * TepiCfg::CHUNK_BYTES);
+      uint4* bq = reinterpret_cast<uint4*>(cb + (g % NBUF) * TCfg::CHUNK_BYTES);
       if (has_res) {
         mbar_wait(&rb[g % NBUF], (g / NBUF) & 1);
 #pragma unroll
@@ -810,11 +817,7 @@ gemm_bf16_tepi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         uint32_t hw[4], lw[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(x[8 * j + 2 * q], h0, l0);
-          split_bf16(x[8 * j + 2 * q + 1], h1, l1);
-          hw[q] = pack_bf16(h0, h1);
-          lw[q] = pack_bf16(l0, l1);
+          split2_bf16(x[8 * j + 2 * q], x[8 * j + 2 * q + 1], hw[q], lw[q]);
         }
         bq[lane * 4 + (j ^ sw)] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
         bq[128 + lane * 4 + (j ^ sw)] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
@@ -826,7 +829,7 @@ gemm_bf16_tepi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         bulk_commit();
         if (has_res) {
           bulk_wait_read<1>();  // chunk g - 1's store has read its buffer: refill it with the residual of g + NBUF - 1
-          issue_res(g + NBUF - 1);
+          issue_res();
         }
       }
       __syncwarp();
@@ -949,11 +952,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmB, const float* __restrict_
         const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
         for (int i = 0; i < 8; i += 2) {
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16((v[i] - mean) * rstd * g[i] + bt[i], h0, l0);
-          split_bf16((v[i + 1] - mean) * rstd * g[i + 1] + bt[i + 1], h1, l1);
-          hw[i >> 1] = pack_bf16(h0, h1);
-          lw[i >> 1] = pack_bf16(l0, l1);
+          split2_bf16((v[i] - mean) * rstd * g[i] + bt[i], (v[i + 1] - mean) * rstd * g[i + 1] + bt[i + 1], hw[i >> 1], lw[i >> 1]);
         }
       }
       const int kb = ch32 >> 3, chunk = ch32 & 7;
@@ -1175,22 +1174,23 @@ static int make_chunk_tmap(CUtensorMap* out, const void* ptr, uint64_t cols, uin
   return 0;
 }
 
-template <int NBUF>
+template <int BN, int NBUF>
 static int launch_tepi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const CUtensorMap& to,
                        const float* bias, int act, int has_res, int post_relu, int M, int N, int K, int stages, const ConvGeom& cg,
                        cudaStream_t st) {
-  static bool attr_set = false;
-  const int smem = TepiCfg::smem_bytes(stages, NBUF);
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tepi_kernel<NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         TepiCfg::smem_bytes(NBUF == 4 ? 1 : 2, NBUF));
+  static int attr_bytes = 0;
+  const int smem = TepiCfg<BN>::smem_bytes(stages, NBUF);
+  if (smem > 232448) return RALF_ERR_SHAPE;
+  if (smem > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tepi_kernel<BN, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_cuda_error(e);
-    attr_set = true;
+    attr_bytes = smem;
   }
-  const long long num_tiles = static_cast<long long>(N / 128) * ((M + 127) / 128);
+  const long long tiles_m = cg.enabled ? static_cast<long long>(cg.B / cg.NB) * cg.hblocks : (M + 127) / 128;
+  const long long num_tiles = static_cast<long long>(N / BN) * tiles_m;
   const int sms = num_sms();
   dim3 grid(static_cast<unsigned>(num_tiles < sms ? num_tiles : sms));
-  const cudaError_t le = launch_pdl(gemm_bf16_tepi_kernel<NBUF>, grid, dim3(320), smem, st, ta, tb, tr, to, bias, act, has_res,
+  const cudaError_t le = launch_pdl(gemm_bf16_tepi_kernel<BN, NBUF>, grid, dim3(320), smem, st, ta, tb, tr, to, bias, act, has_res,
                                     post_relu, M, N, K, stages, cg);
   return set_cuda_error(le != cudaSuccess ? le : cudaGetLastError());
 }
@@ -1293,8 +1293,11 @@ static int gemm_dispatch(const RalfGemmArgs* a, const CUtensorMap& ta, int bn, c
   static const int tepi_k64 = getenv("RALF_TEPI_K64") ? atoi(getenv("RALF_TEPI_K64")) : 14;  // stages * 10 + chunk buffers
   // implicit convolutions qualify when every M tile is a full, contiguous block of 128 output rows
   const bool cg_full = !cg.enabled || (cg.Wo * cg.BH * cg.NB == 128 && cg.Ho % cg.BH == 0 && cg.B % cg.NB == 0);
-  if (tepi && fold_on && bn == 128 && np == 3 && cg_full && a->K <= tepi_kmax && a->N % 128 == 0 &&
-      static_cast<long long>((a->M + 127) / 128) * (a->N / 128) >= 2 * num_sms() && ep.out_split && ep.split_lo && !ep.out_f32 &&
+  static const bool tepi64 = !(getenv("RALF_TEPI_BN64") && atoi(getenv("RALF_TEPI_BN64")) == 0);
+  const long long tepi_tiles = (cg.enabled ? static_cast<long long>(cg.B / (cg.NB > 0 ? cg.NB : 1)) * cg.hblocks : (a->M + 127) / 128) *
+                               (a->N / bn);
+  if (tepi && fold_on && (bn == 128 || (bn == 64 && tepi64)) && np == 3 && cg_full && a->N % bn == 0 &&
+      (bn == 64 || a->K <= tepi_kmax) && tepi_tiles >= 2 * num_sms() && ep.out_split && ep.split_lo && !ep.out_f32 &&
       !ep.out_kv24 && !ep.res && a->rows_per_group <= 0 && ep.res_row_mod <= 0 && ep.vec_ok && ep.act != 2) {
     CUtensorMap tr, to;
     rc = make_chunk_tmap(&to, ep.out_split + ep.out_col0, a->N, a->M, ep.out_ld, ep.out_plane);
@@ -1306,9 +1309,16 @@ static int gemm_dispatch(const RalfGemmArgs* a, const CUtensorMap& ta, int bn, c
     }
     const int nkb = (a->K + 63) / 64;
     const int has_res = ep.res_split != nullptr;
-    if (nkb == 1 && tepi_k64 == 14)
-      return launch_tepi<4>(ta, tb, tr, to, ep.bias, ep.act, has_res, ep.post_relu, a->M, a->N, a->K, 1, cg, st);
-    return launch_tepi<3>(ta, tb, tr, to, ep.bias, ep.act, has_res, ep.post_relu, a->M, a->N, a->K, 2, cg, st);
+#define RALF_TEPI(BN_, NBUF_, STAGES_) \
+  return launch_tepi<BN_, NBUF_>(ta, tb, tr, to, ep.bias, ep.act, has_res, ep.post_relu, a->M, a->N, a->K, STAGES_, cg, st)
+    if (bn == 128) {
+      if (nkb == 1 && tepi_k64 == 14) RALF_TEPI(128, 4, 1);
+      RALF_TEPI(128, 3, 2);
+    }
+    // BN = 64 (stem, layer-1 conv1 / conv2): 48 KB stages; without a residual two chunk buffers per warp are enough
+    if (nkb <= 2 || has_res) RALF_TEPI(64, 3, 2);
+    RALF_TEPI(64, 2, 3);
+#undef RALF_TEPI
   }
 #define RALF_GEMM_CASE(BN_, NP_) \
   if (bn == BN_ && np == NP_) return launch_gemm<BN_, NP_>(ta, tb, ep, a->M, a->N, a->K, st, cg);
