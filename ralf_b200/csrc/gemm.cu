@@ -591,7 +591,7 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 
 template <int BN_>
 struct TepiCfg {
-  static constexpr int BN = BN_;                                   // 128, or 64 for the 64-channel layers
+  static constexpr int BN = BN_;                                   // 128 (64 was measured for the 64-channel layers: no gain)
   static constexpr int STAGE_BYTES = 2 * (128 * 128 + BN * 128);  // 64 / 48 KB: A hi/lo + W hi/lo of one k-block
   static constexpr int CHUNK_BYTES = 4096;                         // [2][32][32] bf16
   static constexpr int smem_bytes(int stages, int nbuf) {
@@ -1293,12 +1293,14 @@ static int gemm_dispatch(const RalfGemmArgs* a, const CUtensorMap& ta, int bn, c
   static const int tepi_k64 = getenv("RALF_TEPI_K64") ? atoi(getenv("RALF_TEPI_K64")) : 14;  // stages * 10 + chunk buffers
   // implicit convolutions qualify when every M tile is a full, contiguous block of 128 output rows
   const bool cg_full = !cg.enabled || (cg.Wo * cg.BH * cg.NB == 128 && cg.Ho % cg.BH == 0 && cg.B % cg.NB == 0);
-  static const bool tepi64 = !(getenv("RALF_TEPI_BN64") && atoi(getenv("RALF_TEPI_BN64")) == 0);
+  // (A BN = 64 flavour for the 64-channel layers -- stem, layer-1 conv1 / conv2 -- was measured: stem 300.0 vs 300.0 us,
+  // conv2 140.3 vs 140.3 us.  Those layers are bound by the tensor core's shared-memory operand reads -- 14 KB per k-step
+  // for 128 x 64 outputs --, not by their epilogue; ncu: tensor pipe 32-40 %, DRAM 20-25 %.  Not instantiated.)
   const long long tepi_tiles = (cg.enabled ? static_cast<long long>(cg.B / (cg.NB > 0 ? cg.NB : 1)) * cg.hblocks : (a->M + 127) / 128) *
-                               (a->N / bn);
-  if (tepi && fold_on && (bn == 128 || (bn == 64 && tepi64)) && np == 3 && cg_full && a->N % bn == 0 &&
-      (bn == 64 || a->K <= tepi_kmax) && tepi_tiles >= 2 * num_sms() && ep.out_split && ep.split_lo && !ep.out_f32 &&
-      !ep.out_kv24 && !ep.res && a->rows_per_group <= 0 && ep.res_row_mod <= 0 && ep.vec_ok && ep.act != 2) {
+                               (a->N / 128);
+  if (tepi && fold_on && bn == 128 && np == 3 && cg_full && a->N % 128 == 0 && a->K <= tepi_kmax &&
+      tepi_tiles >= 2 * num_sms() && ep.out_split && ep.split_lo && !ep.out_f32 && !ep.out_kv24 && !ep.res &&
+      a->rows_per_group <= 0 && ep.res_row_mod <= 0 && ep.vec_ok && ep.act != 2) {
     CUtensorMap tr, to;
     rc = make_chunk_tmap(&to, ep.out_split + ep.out_col0, a->N, a->M, ep.out_ld, ep.out_plane);
     if (rc) return rc;
@@ -1309,16 +1311,9 @@ static int gemm_dispatch(const RalfGemmArgs* a, const CUtensorMap& ta, int bn, c
     }
     const int nkb = (a->K + 63) / 64;
     const int has_res = ep.res_split != nullptr;
-#define RALF_TEPI(BN_, NBUF_, STAGES_) \
-  return launch_tepi<BN_, NBUF_>(ta, tb, tr, to, ep.bias, ep.act, has_res, ep.post_relu, a->M, a->N, a->K, STAGES_, cg, st)
-    if (bn == 128) {
-      if (nkb == 1 && tepi_k64 == 14) RALF_TEPI(128, 4, 1);
-      RALF_TEPI(128, 3, 2);
-    }
-    // BN = 64 (stem, layer-1 conv1 / conv2): 48 KB stages; without a residual two chunk buffers per warp are enough
-    if (nkb <= 2 || has_res) RALF_TEPI(64, 3, 2);
-    RALF_TEPI(64, 2, 3);
-#undef RALF_TEPI
+    if (nkb == 1 && tepi_k64 == 14)
+      return launch_tepi<128, 4>(ta, tb, tr, to, ep.bias, ep.act, has_res, ep.post_relu, a->M, a->N, a->K, 1, cg, st);
+    return launch_tepi<128, 3>(ta, tb, tr, to, ep.bias, ep.act, has_res, ep.post_relu, a->M, a->N, a->K, 2, cg, st);
   }
 #define RALF_GEMM_CASE(BN_, NP_) \
   if (bn == BN_ && np == NP_) return launch_gemm<BN_, NP_>(ta, tb, ep, a->M, a->N, a->K, st, cg);

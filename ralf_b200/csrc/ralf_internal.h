@@ -13,8 +13,9 @@ int set_cuda_error(cudaError_t e);
 int make_kmajor_tmap(CUtensorMap* out, const void* ptr, int elem_bytes, uint64_t K, uint64_t rows,
                      uint64_t planes, uint64_t ld, uint64_t plane_stride, uint32_t box_rows);
 int num_sms();
-// RALF_PDL=1 turns programmatic dependent launch on (A/B runs); default off, see runtime.cu.
-bool pdl_enabled();
+// Programmatic dependent launch mode (RALF_PDL): 0 off, 1 every launch, 2 only single-wave grids (<= #SMs CTAs: the
+// latency-bound kernels of the decode loop); see runtime.cu.
+int pdl_mode();
 
 // kernel<<<grid, block, smem, st>>>(args...) with the programmatic-stream-serialization attribute (see common.cuh).
 template <typename... KArgs, typename... Args>
@@ -29,7 +30,8 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  const int mode = pdl_mode();
+  cfg.numAttrs = (mode == 1 || (mode == 2 && static_cast<long long>(grid.x) * grid.y * grid.z <= num_sms())) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 // attention_tc.cu: tcgen05 attention for (head_dim 32, no mask, 64 <= Tk <= 256); 1 = launched, 0 = not applicable.

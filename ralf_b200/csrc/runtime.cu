@@ -25,13 +25,15 @@ int num_sms() {
   return sms;
 }
 
-bool pdl_enabled() {
+int pdl_mode() {
   // Opt-in (RALF_PDL=1).  Measured on B200 (capture N, 1024-canvas step under CUDA graphs): 201.2 ms with programmatic
   // edges vs 186.3 ms without -- dependents that become resident early hold shared memory / TMEM next to the still
   // running producer and cost more than the ~2 us of prologue they hide; the graph-replayed training step also drifted
   // 1.5e-4 from the eager one.  Off by default; the kernels keep their (then no-op) griddepcontrol instructions.
-  static const bool on = getenv("RALF_PDL") && atoi(getenv("RALF_PDL")) != 0;
-  return on;
+  // RALF_PDL=2 (round 2): only for grids of at most one CTA per SM -- the decode loop's kernels, whose dependents find
+  // idle SMs to become resident on.
+  static const int mode = getenv("RALF_PDL") ? atoi(getenv("RALF_PDL")) : 0;
+  return mode;
 }
 }  // namespace ralf
 

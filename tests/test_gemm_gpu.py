@@ -242,37 +242,3 @@ def test_conv_gemm_stride2_matches_conv2d_fp64_and_im2col(cuda_device, B, H, W, 
                                      stride=2, padding=KH // 2).relu().permute(0, 2, 3, 1).reshape(B * Ho * Wo, N)
     err = (ops.unsplit(y).double() - ref).abs().max().item() / ref.abs().max().item()
     assert err <= 4e-5, err
-
-
-def test_gemm_tma_epilogue_64_channel_layers_bit_identical(cuda_device):
-    """BN = 64 flavour of the TMA-epilogue kernel (ResNet stem, layer-1 conv1 / conv2: 64 output channels, split output
-    only): plain GEMM, 3x3 implicit convolution and the space-to-depth stem must equal the register-staged kernel
-    (block_n = 32) bit for bit."""
-    from ralf_b200 import ops
-
-    g = torch.Generator(device=cuda_device).manual_seed(11)
-    bias = torch.randn(64, device=cuda_device, generator=g)
-    # layer-1 conv1 shape class: K = 256 -> 4 k-blocks (three ring stages, two chunk buffers); K = 128 -> (2, 3)
-    for M, K in ((40000, 256), (38000, 128)):
-        a = ops.split_bf16(torch.randn(M, K, device=cuda_device, generator=g))
-        w = ops.split_bf16(torch.randn(64, K, device=cuda_device, generator=g) / K ** 0.5)
-        _, y = ops.gemm(a, w, bias=bias, act="relu", want_f32=False, want_split=True)
-        _, y2 = ops.gemm(a, w, bias=bias, act="relu", want_f32=False, want_split=True, block_n=32)
-        assert torch.equal(y.view(torch.int16), y2.view(torch.int16))
-        ref = _ref(ops.unsplit(a), ops.unsplit(w), bias, "relu")
-        assert (ops.unsplit(y).double() - ref).abs().max().item() <= 4e-5 * ref.abs().max().item()
-    # layer-1 conv2: 3x3 on 64 x 64 x 64, ten canvases = 320 full tiles
-    B, H, W, C = 10, 64, 64, 64
-    x = ops.split_bf16(torch.randn(B * H * W, C, device=cuda_device, generator=g))
-    w = ops.split_bf16(torch.randn(64, 9 * C, device=cuda_device, generator=g) / 24.0)
-    _, y = ops.gemm(x, w, bias=bias, act="relu", want_f32=False, want_split=True, conv=(B, H, W, C, 3, 3))
-    _, y2 = ops.gemm(x, w, bias=bias, act="relu", want_f32=False, want_split=True, conv=(B, H, W, C, 3, 3), block_n=32)
-    assert torch.equal(y.view(torch.int16), y2.view(torch.int16))
-    # stem: three 256 x 256 canvases = 384 full tiles
-    img = torch.rand(3, 4, 256, 256, device=cuda_device, generator=g)
-    ws = ops.split_bf16(torch.randn(64, 256, device=cuda_device, generator=g) / 16.0)
-    a, Ho, Wo = ops.stem_s2d(img)
-    _, y = ops.gemm(a, ws, bias=bias, act="relu", stem=(3, Ho, Wo), want_f32=False, want_split=True)
-    _, y2 = ops.gemm(a, ws, bias=bias, act="relu", stem=(3, Ho, Wo), want_f32=False, want_split=True, block_n=32)
-    assert torch.equal(y.view(torch.int16), y2.view(torch.int16))
-    assert ops.unsplit(y).abs().max().item() > 0
