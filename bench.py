@@ -331,7 +331,7 @@ def run_ours(args):
                                  "lives in a CUDA graph where events cannot bracket it -- its in-step share is confirmed by the "
                                  "ncu launch list (profiles/r2_launches_*_summary.md)")
             line["roofline"] = dom
-        line["roofline_other"] = [o for o in (other or []) if o["bound"] != "hbm"]
+        line["roofline_other"] = [o for o in (other or [])[1:]] if dom is not None else list(other or [])
         if api is not None:
             line["e2e_model_api"] = api
     else:
@@ -661,7 +661,8 @@ def model_api_e2e(model, retr, img_h, qry_h, dev, n: int = 128, iters: int = 3):
 
 
 def secondary_rooflines(model, B, dev):
-    """The step's two dominant kernels timed alone (CUDA events, 20 launches each, operands >> L2):
+    """Dominant kernels of the step timed alone (CUDA events, 20 launches each, operands >> L2); the first entry becomes
+    `roofline`, the rest `roofline_other`:
     (1) memory cross-attention of one decode step over the layer-major 24-bit K/V cache of B canvases -- HBM bound,
         algorithmic bytes = B * M * 1536 (every K and V row read once, 3 bytes per value) + q / out rows;
     (2) a ResNet layer-3 3x3 convolution as implicit GEMM (micro-batch 128: M = 32768, N = 256, K = 2304) -- tensor
@@ -708,6 +709,20 @@ def secondary_rooflines(model, B, dev):
     out.append({"kernel": "gemm_bf16_kernel<128,3> as implicit-GEMM 3x3 convolution (ResNet layer3 conv2, 128 canvases)",
                 "bound": "tensor", "achieved": round(fl / ms / 1e9, 1), "unit": "TFLOP/s", "ms_per_launch": round(ms, 4),
                 "flops_per_launch_3pass": fl, "launches_per_step": 48})
+    del x, w, y
+    # (3) the ResNet layer-1 bottleneck tail (1x1 conv3 + identity + ReLU: M = 128 * 64 * 64, N = 256, K = 64) through the
+    #     TMA-epilogue GEMM -- HBM bound: A + split residual + split output, every byte once
+    Mc, Nc, Kc = 128 * 64 * 64, 256, 64
+    a = torch.randn(2, Mc, Kc, device=dev).to(torch.bfloat16)
+    w = torch.randn(2, Nc, Kc, device=dev).to(torch.bfloat16)
+    res = torch.randn(2, Mc, Nc, device=dev).to(torch.bfloat16)
+    y = torch.empty(2, Mc, Nc, dtype=torch.bfloat16, device=dev)
+    bias = torch.randn(Nc, device=dev)
+    ms = t(lambda: ops.gemm(a, w, bias=bias, res_split=res, post_relu=True, out_split=y, want_f32=False))
+    byt = a.numel() * 2 + w.numel() * 2 + res.numel() * 2 + y.numel() * 2
+    out.append({"kernel": "gemm_bf16_tepi_kernel<128,4> (ResNet layer1 conv3 + identity + ReLU, 128 canvases; TMA epilogue)",
+                "bound": "hbm", "achieved": round(byt / ms / 1e6, 1), "unit": "GB/s", "ms_per_launch": round(ms, 4),
+                "algorithmic_bytes_per_launch": byt, "launches_per_step": 24})
     return out
 
 

@@ -372,7 +372,8 @@ def test_bench_line_assembly_with_stub_measurements():
               retr=types.SimpleNamespace(emb=sized(1)), model=types.SimpleNamespace(special_token_ids={}),
               img_h=sized(1024 * 4 * 256 * 256), qry_h=sized(1024 * 512), clocks={"sm_mhz": 1900, "sm_max_mhz": 1965, "reasons": []},
               other=[{"kernel": "a", "bound": "hbm", "achieved": 6250.9, "unit": "GB/s", "ms_per_launch": 0.1342, "launches_per_step": 360},
-                     {"kernel": "b", "bound": "tensor", "achieved": 1273.4, "unit": "TFLOP/s", "ms_per_launch": 0.0911, "launches_per_step": 48}],
+                     {"kernel": "b", "bound": "tensor", "achieved": 1273.4, "unit": "TFLOP/s", "ms_per_launch": 0.0911, "launches_per_step": 48},
+                     {"kernel": "c", "bound": "hbm", "achieved": 6050.0, "unit": "GB/s", "ms_per_launch": 0.2, "launches_per_step": 24}],
               api={"value": 900.0, "unit": "layouts/s"})
     exec(block, ns)
     d = json.loads(json.dumps(ns["line"]))  # what emit() prints
@@ -387,4 +388,5 @@ def test_bench_line_assembly_with_stub_measurements():
     k = d["roofline_knn"]  # the k-NN half of the metric, timed live
     assert k["bound"] == "hbm" and abs(k["frac"] - k["achieved"] / k["peak"]) < 1e-3 and 0 < k["share_of_step"] < 0.05
     assert "workload" in d["config"] and "model" not in d["config"] and d["gpu_launches"] == 28910
-    assert [o["share_of_step"] for o in d["roofline_other"]] == [round(0.0911 * 48 / 186.0, 4)]
+    assert [o["share_of_step"] for o in d["roofline_other"]] == [round(0.0911 * 48 / 186.0, 4), round(0.2 * 24 / 186.0, 4)]
+    assert [o["kernel"] for o in d["roofline_other"]] == ["b", "c"] and abs(d["roofline_other"][1]["frac"] - 6050.0 / r["peak"]) < 1e-3
