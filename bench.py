@@ -243,6 +243,19 @@ def run_ours(args):
         finish()
         ms_e2e = timed(lambda: step_e2e(), args.steps, record=None)
 
+    # phase split of one more step (after the timed region; CUDA events between the graph replays of the pipeline)
+    phases = None
+    if not args.no_graph and not args.overlap:
+        try:
+            marks = []
+            l2_flush.zero_()
+            pipe.step(phase_events=marks)
+            torch.cuda.synchronize()
+            phases = {b[0] + "_ms": round(a[1].elapsed_time(b[1]), 3) for a, b in zip(marks[:-1], marks[1:])}
+            phases["note"] = ("one extra step after the timed region: search (+ all-gather merge at N > 1), exemplar fetch, "
+                              "encode (ResNet-FPN + encoders + memory K/V, all micro-batches), decode (the 60-token greedy loop)")
+        except Exception as e:  # a reported extra
+            phases = {"error": repr(e)[:200]}
     other = secondary_rooflines(model, B, dev) if rank == 0 else None
     api = None
     if rank == 0 and world == 1 and not args.skip_e2e:
@@ -334,6 +347,8 @@ def run_ours(args):
         line["roofline_other"] = [o for o in (other or [])[1:]] if dom is not None else list(other or [])
         if api is not None:
             line["e2e_model_api"] = api
+        if phases is not None:
+            line["phases"] = phases
     else:
         line = None
     # ---- reported extras: the other BASELINE configs on the same box, same run (never a reason to lose the line) ----

@@ -134,6 +134,14 @@ int ralf_gemm(const RalfGemmArgs* args, void* stream);
  * [planes][B*H*W, C] itself, each k-block of the main loop is one (filter tap, 64-channel slice) fetched by a 5-D TMA
  * box whose out-of-image part is zero-filled (= the padding); no im2col buffer exists.
  * args->W = [planes][N, KH*KW*C] with k = (kh*KW + kw)*C + c; args->M = B*H*W; args->K = KH*KW*C; C % 64 == 0. */
+/* Decode-loop residual GEMM with the FOLLOWING LayerNorm fused in (nn.TransformerDecoderLayer, norm_first:
+ * x = x + sublayer(..); h = norm(x), models/common/common.py:84-135): x_new = A . W^T + bias + res -> out_f32 (may alias
+ * res), LayerNorm(x_new; gamma, beta, eps) -> ln_split as split bf16 rows [2][M, 256].  N must be 256, K % 64 == 0,
+ * npass 3; args supplies A, W, bias, res / res_ld, out_f32 / out_ld, every other epilogue field unset.  The eight
+ * 32-column tiles of a row block run as one thread-block cluster and exchange row statistics through distributed shared
+ * memory. */
+int ralf_gemm_res_ln(const RalfGemmArgs* args, const float* gamma, const float* beta, float eps, void* ln_split,
+                     long long ln_plane, void* stream);
 int ralf_conv_gemm(const RalfGemmArgs* args, int B, int H, int W, int C, int KH, int KW, void* stream);
 /* The same with stride 1 or 2 (ResNet's stride-2 3x3 and 1x1 downsample convolutions, torchvision resnet50 via
  * models/common/image.py:90-120): args->M = B*Ho*Wo, Ho = (H + 2*(KH/2) - KH) / stride + 1; a tap's TMA box skips every

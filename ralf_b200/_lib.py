@@ -88,6 +88,7 @@ def lib() -> C.CDLL:
         L.ralf_gemm_splitk_workspace_bytes.restype = C.c_size_t
         L.ralf_gemm_splitk_workspace_bytes.argtypes = [C.c_int] * 3
         L.ralf_conv_gemm.argtypes = [C.POINTER(GemmArgs)] + [C.c_int] * 6 + [C.c_void_p]
+        L.ralf_gemm_res_ln.argtypes = [C.POINTER(GemmArgs), C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_longlong, C.c_void_p]
         L.ralf_conv_gemm_strided.argtypes = [C.POINTER(GemmArgs)] + [C.c_int] * 7 + [C.c_void_p]
         L.ralf_stem_gemm.argtypes = [C.POINTER(GemmArgs)] + [C.c_int] * 3 + [C.c_void_p]
         L.ralf_stem_s2d.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]

@@ -846,6 +846,206 @@ gemm_bf16_tepi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
 
 // ------------------------------------------------------------------------------------------------
+// Decode-loop residual GEMM with the FOLLOWING LayerNorm in its epilogue (round 2): x_new = A . W^T + bias + x (N = 256 =
+// d_model) and h = LayerNorm(x_new) as split operand rows for the next GEMM.  A full row spans the eight 32-column
+// n-tiles, which keep running on eight different SMs (a single CTA per row block would serialise the MMAs, see
+// decode_chain.cu); the eight CTAs form a THREAD-BLOCK CLUSTER and exchange their per-row partial sums through
+// distributed shared memory: sum -> cluster barrier -> mean; centred sum of squares -> cluster barrier -> rstd (the
+// two-pass form of layernorm_kernel; partials are added in rank order, so every CTA computes the same statistics).
+// One tile per CTA, grid = (8, M tiles), cluster = (8, 1, 1).  Replaces 18 of the 19 LayerNorm launches of a decode step.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem_f32(const float* local_ptr, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_ptr)), "r"(rank));
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+constexpr int RLN_STAGE_BYTES = 2 * (128 * 128 + 32 * 128);  // 40 KB: A hi/lo (128 rows) + W hi/lo (32 rows) of one k-block
+constexpr int RLN_STAGES = 4;
+constexpr int RLN_SMEM = RLN_STAGES * RLN_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * 128 * 4 /*row partials*/;
+
+__global__ void __launch_bounds__(192, 1)
+gemm_resln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const float* __restrict__ bias, const float* res, const int res_ld, float* out_f32, const int out_ld,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, const float eps,
+                  __nv_bfloat16* __restrict__ ln_split, const long long ln_plane, const int M, const int K) {
+  constexpr int BN = 32, A_BYTES = 128 * 128, B_BYTES = BN * 128;
+  pdl_trigger();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base_u32 - smem_u32(smem_raw));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + RLN_STAGES * RLN_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + RLN_STAGES;
+  uint64_t* tfull_bar = empty_bar + RLN_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+  float* part1 = reinterpret_cast<float*>(smem + RLN_STAGES * RLN_STAGE_BYTES + 256);  // [128] row sums of this n-tile
+  float* part2 = part1 + 128;                                                            // [128] centred sums of squares
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * 128;
+  const int nkb = (K + 63) / 64;
+
+  auto load_stage = [&](const int kb, const int s) {
+    mbar_expect_tx(&full_bar[s], RLN_STAGE_BYTES);
+    uint8_t* st = smem + s * RLN_STAGE_BYTES;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) tma_load_3d(&tmA, &full_bar[s], st + p * A_BYTES, kb * 64, m0, p);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) tma_load_3d(&tmB, &full_bar[s], st + 2 * A_BYTES + p * B_BYTES, kb * 64, n0, p);
+  };
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < RLN_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_mbar_init();
+    pdl_wait();
+    const int npre = nkb < RLN_STAGES ? nkb : RLN_STAGES;
+    for (int kb = 0; kb < npre; ++kb) load_stage(kb, kb);
+  }
+  if (warp == 1) tmem_alloc<64>(tmem_slot);  // one folded accumulator: 2 * BN columns
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        if (kb >= RLN_STAGES) {  // the first ring was issued in the prologue
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          load_stage(kb, s);
+        }
+        if (++s == RLN_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(1, 128, BN);
+      constexpr uint32_t idesc2 = make_idesc(1, 128, 2 * BN);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_hi = base_u32 + s * RLN_STAGE_BYTES;
+        const uint64_t da_hi = make_sw128_kmajor_desc(a_hi);
+        const uint64_t da_lo = make_sw128_kmajor_desc(a_hi + A_BYTES);
+        const uint64_t db_hi = make_sw128_kmajor_desc(a_hi + 2 * A_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t koff = static_cast<uint64_t>(2 * k);
+          mma_bf16_ss(tmem_base, da_hi + koff, db_hi + koff, idesc2, (kb | k) != 0);  // x_hi . [w_hi ; w_lo]
+          mma_bf16_ss(tmem_base + BN, da_lo + koff, db_hi + koff, idesc, 1);          // + x_lo . w_hi
+        }
+        tc_commit(&empty_bar[s]);
+        if (++s == RLN_STAGES) { s = 0; ph ^= 1; }
+      }
+      tc_commit(tfull_bar);
+    }
+    __syncwarp();
+  }
+  // ---- epilogue: warps 2-5, thread = row (TMEM lane quadrant warp % 4); the other warps only join the cluster barriers ----
+  const bool epi = warp >= 2;
+  const int quad = warp & 3;
+  const int rl = quad * 32 + lane;  // row within the tile
+  const int r = m0 + rl;
+  const bool row_ok = epi && r < M;
+  float x[32];
+  if (epi) {
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    uint32_t v[32], v2[32];
+    const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    tmem_ld_32x32(tacc, v);
+    tmem_ld_32x32(tacc + BN, v2);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + __uint_as_float(v2[j]);
+    if (bias) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0 + j));
+        x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
+      }
+    }
+    float s = 0.f;
+    if (row_ok) {
+      const float* rr = res + static_cast<long long>(r) * res_ld + n0;
+      float* oo = out_f32 + static_cast<long long>(r) * out_ld + n0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(rr + j);
+        x[j] += t.x; x[j + 1] += t.y; x[j + 2] += t.z; x[j + 3] += t.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(oo + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) s += x[j];
+    }
+    part1[rl] = s;
+  }
+  cluster_sync_all();
+  float mean = 0.f;
+  if (epi) {
+    float t = 0.f;
+#pragma unroll
+    for (uint32_t rk = 0; rk < 8; ++rk) t += ld_dsmem_f32(part1 + rl, rk);
+    mean = t * (1.f / 256.f);
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float d = x[j] - mean;
+      sq = fmaf(d, d, sq);
+    }
+    part2[rl] = row_ok ? sq : 0.f;
+  }
+  cluster_sync_all();
+  if (epi) {
+    float t = 0.f;
+#pragma unroll
+    for (uint32_t rk = 0; rk < 8; ++rk) t += ld_dsmem_f32(part2 + rl, rk);
+    const float rstd = rsqrtf(t * (1.f / 256.f) + eps);
+    if (row_ok) {
+      uint32_t hw[16], lw[16];
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + n0 + j));
+        const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + n0 + j));
+        const float y0 = (x[j] - mean) * rstd * g.x + bt.x, y1 = (x[j + 1] - mean) * rstd * g.y + bt.y;
+        const float y2 = (x[j + 2] - mean) * rstd * g.z + bt.z, y3 = (x[j + 3] - mean) * rstd * g.w + bt.w;
+        split2_bf16(y0, y1, hw[j >> 1], lw[j >> 1]);
+        split2_bf16(y2, y3, hw[(j >> 1) + 1], lw[(j >> 1) + 1]);
+      }
+      __nv_bfloat16* oh = ln_split + static_cast<long long>(r) * 256 + n0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        *reinterpret_cast<uint4*>(oh + 8 * j) = make_uint4(hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
+        *reinterpret_cast<uint4*>(oh + ln_plane + 8 * j) = make_uint4(lw[4 * j], lw[4 * j + 1], lw[4 * j + 2], lw[4 * j + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();  // no CTA of the cluster leaves while its partials may still be read
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<64>(tmem_base);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
 // LayerNorm fused into the GEMM's A operand (decode path, K = 256 = d_model; one CTA per (n-tile, 128-row tile)).
 // Measured at the bench shape (M = 1024) in round 2: 188.2 vs 168.5 ms per step -- the serial per-thread row
 // normalisation sits on every GEMM's critical path and costs more than the 5 us LayerNorm launch it removes.  Opt-in.
@@ -1443,6 +1643,49 @@ extern "C" int ralf_stem_gemm(const RalfGemmArgs* a, int B, int Ho, int Wo, void
     return RALF_ERR_DRIVER;
   }
   return gemm_dispatch(a, ta, bn, cg, stream);
+}
+
+
+// x_new = A . W^T + bias + res -> out_f32 (may alias res), LayerNorm(x_new; gamma, beta) -> ln_split ([2][M, 256] split rows,
+// plane stride ln_plane elements).  N = 256, K a multiple of 64, bf16x3.  `a` supplies A, W, bias, res / res_ld,
+// out_f32 / out_ld (its other epilogue fields must be unset).  Cluster kernel: gemm_resln_kernel.
+extern "C" int ralf_gemm_res_ln(const RalfGemmArgs* a, const float* gamma, const float* beta, float eps, void* ln_split,
+                                long long ln_plane, void* stream) {
+  if (!a || !a->A || !a->W || !a->res || !a->out_f32 || !gamma || !beta || !ln_split) return RALF_ERR_NULL;
+  if (a->M <= 0 || a->N != 256 || a->K <= 0 || (a->K % 64) || a->npass != 3) return RALF_ERR_SHAPE;
+  if (a->res_split || a->out_split || a->out_kv24 || a->act || a->post_relu || a->rows_per_group > 0 || a->res_row_mod > 0 ||
+      a->out_col0)
+    return RALF_ERR_SHAPE;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if ((a->lda % 8) || (a->ldw % 8) || (a->res_ld % 4) || (a->out_ld % 4) || (ln_plane % 8) || !al16(a->res) || !al16(a->out_f32) ||
+      !al16(a->bias) || !al16(gamma) || !al16(beta) || !al16(ln_split))
+    return RALF_ERR_ALIGN;
+  CUtensorMap ta, tb;
+  int rc = make_kmajor_tmap(&ta, a->A, 2, a->K, a->M, 2, a->lda, a->a_plane, 128);
+  if (rc) return rc;
+  rc = make_kmajor_tmap(&tb, a->W, 2, a->K, a->N, 2, a->ldw, a->w_plane, 32);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_resln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RLN_SMEM);
+    if (e != cudaSuccess) return set_cuda_error(e);
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(8, (a->M + 127) / 128);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = RLN_SMEM;
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 8;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_resln_kernel, ta, tb, a->bias, a->res, a->res_ld, a->out_f32, a->out_ld,
+                                            gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(ln_split), ln_plane, a->M, a->K);
+  return set_cuda_error(le != cudaSuccess ? le : cudaGetLastError());
 }
 
 template <int BN>

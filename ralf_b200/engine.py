@@ -50,6 +50,12 @@ DECODE_CHAIN = os.environ.get("RALF_DECODE_CHAIN", "0") != "0"
 # RALF_STRIDED_CONV=0 only for the stride-2 3x3 / 1x1 convolutions (TMA boxes with element strides).
 IMPLICIT_CONV = os.environ.get("RALF_IMPLICIT_CONV", "1") != "0"
 STRIDED_CONV = os.environ.get("RALF_STRIDED_CONV", "1") != "0"
+# Decode loop: LayerNorm in the epilogue of the residual GEMM in front of it (thread-block cluster of the row's eight
+# n-tiles, statistics through distributed shared memory).  Built and measured in round 2 (profiles/resln_bench.py, graph
+# replay of a dependent chain at M = 1024): GEMM 6.35 us, GEMM + LayerNorm launch 8.44 us, fused cluster kernel 8.31 us --
+# the two cluster barriers + the guarded exit cost what the 2.1 us LayerNorm launch costs; step 147.9-148.5 vs 147.0-148.4
+# ms with 1080 launches fewer.  Opt-in (RALF_DECODE_RESLN=1); tokens stay bit-exact on every golden with it on.
+DECODE_RESLN = os.environ.get("RALF_DECODE_RESLN", "0") != "0"
 
 
 def _sine_pe_1d(max_len: int, d_model: int) -> torch.Tensor:
@@ -480,6 +486,8 @@ class Engine:
         kv24 = kvm[0].dtype == torch.uint8
         if DECODE_CHAIN and self.npass == 3:
             return self._decode_step_chained(x, t, kc, vc, kvm, pad_mask, B, Mlen)
+        if DECODE_RESLN and self.npass == 3 and not FUSE_LN:
+            return self._decode_step_resln(x, t, kc, vc, kvm, pad_mask, B, Mlen)
         for i in range(NLAYER):
             p = f"decoder.transformer.layers.{i}"
             # every LayerNorm of the step is folded into the GEMM that consumes it (ralf_gemm_ln)
@@ -495,6 +503,35 @@ class Engine:
             _, f = self._gemm_ln(x, p + ".norm3", p + ".linear1", act="relu", want_f32=False, want_split=True)
             self._gemm(f, p + ".linear2", res=x, out_f32=x)
         logits, _ = self._gemm_ln(x, "decoder.head.0", "decoder.head.1")
+        return logits
+
+    def _decode_step_resln(self, x: torch.Tensor, t: int, kc: list, vc: list, kvm: list, pad_mask: torch.Tensor, B: int,
+                           Mlen: int) -> torch.Tensor:
+        """``_decode_step`` with every LayerNorm but the first computed in the epilogue of the residual GEMM in front of
+        it (ops.gemm_res_ln: out-projections and linear2 write the new residual row AND its normalised split operand):
+        8 launches per layer instead of 11."""
+        w = self.w
+        kv24 = kvm[0].dtype == torch.uint8
+        L = "decoder.transformer.layers."
+
+        def res_ln(a, name, ln_name):
+            return ops.gemm_res_ln(a, w[name + ".w"], x, w[ln_name + ".g"], w[ln_name + ".beta"], bias=w.get(name + ".b"))[1]
+
+        _, h = self._ln(x, L + "0.norm1")
+        for i in range(NLAYER):
+            p = L + str(i)
+            qkv, _ = self._gemm(h, p + ".qkv")
+            a = ops.attention_decode_append(qkv, kc[i], vc[i], t, B, NHEAD, 32, mask=pad_mask)
+            h = res_ln(a, p + ".o", p + ".norm2")
+            q, _ = self._gemm(h, p + ".cq")
+            if kv24:
+                a = ops.attention_decode_kv24(q, kvm[i], Mlen, Mlen, B, NHEAD)
+            else:
+                a = ops.attention_decode(q, kvm[i][:, :D], kvm[i][:, D:], Mlen, Mlen, B, NHEAD, 32)
+            h = res_ln(a, p + ".co", p + ".norm3")
+            _, f = self._gemm(h, p + ".linear1", act="relu", want_f32=False, want_split=True)
+            h = res_ln(f, p + ".linear2", (L + str(i + 1) + ".norm1") if i + 1 < NLAYER else "decoder.head.0")
+        logits, _ = self._gemm(h, "decoder.head.1")
         return logits
 
     def _decode_step_chained(self, x: torch.Tensor, t: int, kc: list, vc: list, kvm: list, pad_mask: torch.Tensor, B: int,

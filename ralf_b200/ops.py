@@ -184,6 +184,31 @@ def gemm_ln(
     return out_f32, out_split
 
 
+def gemm_res_ln(a: torch.Tensor, w: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *,
+                bias: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None,
+                ln_split: Optional[torch.Tensor] = None, eps: float = 1e-5) -> tuple[torch.Tensor, torch.Tensor]:
+    """x_new = a . w^T + bias + x and h = LayerNorm(x_new) in one launch (``ralf_gemm_res_ln``; decode loop).
+    a: split bf16 [2, M, K]; w: split bf16 [2, 256, K]; x: fp32 [M, 256] (``out_f32`` defaults to updating it in place).
+    Returns (x_new fp32 [M, 256], h split bf16 [2, M, 256])."""
+    M, K = a.shape[1], a.shape[2]
+    assert w.shape[1] == 256 and w.shape[2] == K and x.shape == (M, 256) and x.dtype == torch.float32 and x.stride(1) == 1
+    if out_f32 is None:
+        out_f32 = x
+    if ln_split is None:
+        ln_split = torch.empty((2, M, 256), dtype=torch.bfloat16, device=a.device)
+    assert ln_split.stride(1) == 256 and ln_split.stride(2) == 1
+    g = GemmArgs()
+    g.A, g.a_plane, g.lda = a.data_ptr(), a.stride(0), a.stride(1)
+    g.W, g.w_plane, g.ldw = w.data_ptr(), w.stride(0), w.stride(1)
+    g.M, g.N, g.K, g.npass = M, 256, K, 3
+    g.bias = _ptr(bias)
+    g.res, g.res_ld = x.data_ptr(), x.stride(0)
+    g.out_f32, g.out_ld = out_f32.data_ptr(), out_f32.stride(0)
+    check(_lib.lib().ralf_gemm_res_ln(C.byref(g), gamma.data_ptr(), beta.data_ptr(), eps, ln_split.data_ptr(), ln_split.stride(0),
+                                      _stream()), "ralf_gemm_res_ln")
+    return out_f32, ln_split
+
+
 def chain_stage(w: torch.Tensor, *, bias: Optional[torch.Tensor] = None, ln: Optional[tuple] = None,
                 in_split: Optional[torch.Tensor] = None, act: Optional[str] = None, add_x: bool = False, to_x: bool = False,
                 out_operand: bool = False, out_f32: Optional[torch.Tensor] = None, eps: float = 1e-5) -> "_lib.ChainStage":

@@ -193,9 +193,20 @@ class LayoutPipeline:
         torch.cuda.synchronize()
 
     # ---- run -----------------------------------------------------------------------------------
-    def step(self, events: Optional[list] = None, copy_events: Optional[list] = None) -> torch.Tensor:
+    def step(self, events: Optional[list] = None, copy_events: Optional[list] = None,
+             phase_events: Optional[list] = None) -> torch.Tensor:
         """One pass over the static inputs (self.img, self.qry already filled).  Returns token ids [B, S] (device).
-        ``events``: optional list that receives a (start, end) CUDA-event pair around the k-NN phase."""
+        ``events``: optional list that receives a (start, end) CUDA-event pair around the k-NN phase.
+        ``phase_events`` (graph path): receives (name, event) marks -- start, search, fetch, encode, decode -- so a caller
+        can read the phase split of a step with CUDA events."""
+
+        def mark(name):
+            if phase_events is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                phase_events.append((name, ev))
+
+        mark("start")
         if self.world > 1:
             import torch.distributed as dist
 
@@ -219,12 +230,16 @@ class LayoutPipeline:
             events.append((e0, e1))
         if self.world > 1:
             self._my_idx.copy_(self._merge(*self._local))
+        mark("search")
         self.g_fetch.replay()
+        mark("fetch")
         for i, g in enumerate(self.g_enc):
             if copy_events is not None:  # micro-batch i's canvases must have landed
                 torch.cuda.current_stream().wait_event(copy_events[i])
             g.replay()
+        mark("encode")
         self.g_dec.replay()
+        mark("decode")
         return self.seq_out
 
     def __call__(self, image: torch.Tensor, query: torch.Tensor) -> torch.Tensor:

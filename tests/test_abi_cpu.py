@@ -374,7 +374,7 @@ def test_bench_line_assembly_with_stub_measurements():
               other=[{"kernel": "a", "bound": "hbm", "achieved": 6250.9, "unit": "GB/s", "ms_per_launch": 0.1342, "launches_per_step": 360},
                      {"kernel": "b", "bound": "tensor", "achieved": 1273.4, "unit": "TFLOP/s", "ms_per_launch": 0.0911, "launches_per_step": 48},
                      {"kernel": "c", "bound": "hbm", "achieved": 6050.0, "unit": "GB/s", "ms_per_launch": 0.2, "launches_per_step": 24}],
-              api={"value": 900.0, "unit": "layouts/s"})
+              api={"value": 900.0, "unit": "layouts/s"}, phases={"search_ms": 2.9, "encode_ms": 84.0, "decode_ms": 62.0})
     exec(block, ns)
     d = json.loads(json.dumps(ns["line"]))  # what emit() prints
     for key in ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
@@ -388,5 +388,6 @@ def test_bench_line_assembly_with_stub_measurements():
     k = d["roofline_knn"]  # the k-NN half of the metric, timed live
     assert k["bound"] == "hbm" and abs(k["frac"] - k["achieved"] / k["peak"]) < 1e-3 and 0 < k["share_of_step"] < 0.05
     assert "workload" in d["config"] and "model" not in d["config"] and d["gpu_launches"] == 28910
+    assert d["phases"]["decode_ms"] == 62.0
     assert [o["share_of_step"] for o in d["roofline_other"]] == [round(0.0911 * 48 / 186.0, 4), round(0.2 * 24 / 186.0, 4)]
     assert [o["kernel"] for o in d["roofline_other"]] == ["b", "c"] and abs(d["roofline_other"][1]["frac"] - 6050.0 / r["peak"]) < 1e-3

@@ -242,3 +242,32 @@ def test_conv_gemm_stride2_matches_conv2d_fp64_and_im2col(cuda_device, B, H, W, 
                                      stride=2, padding=KH // 2).relu().permute(0, 2, 3, 1).reshape(B * Ho * Wo, N)
     err = (ops.unsplit(y).double() - ref).abs().max().item() / ref.abs().max().item()
     assert err <= 4e-5, err
+
+
+@pytest.mark.parametrize("M,K", [(1024, 256), (1024, 1024), (1, 256), (300, 1024), (129, 256)])
+def test_gemm_residual_layernorm_cluster_kernel(cuda_device, M, K):
+    """ralf_gemm_res_ln (decode loop): x_new = a . w^T + bias + x must equal the plain residual GEMM bit for bit, and its
+    LayerNorm output (row statistics exchanged between the eight n-tile CTAs of a cluster through distributed shared
+    memory) must equal float64 LayerNorm of x_new to split-operand precision and the stand-alone LayerNorm kernel to fp32
+    rounding.  M = 1 is the DecodeSession shape, 300 / 129 leave partial row tiles."""
+    from ralf_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(M + K)
+    a = ops.split_bf16(torch.randn(M, K, generator=g).to(cuda_device))
+    w = ops.split_bf16((torch.randn(256, K, generator=g) / K ** 0.5).to(cuda_device))
+    bias = torch.randn(256, generator=g).to(cuda_device)
+    x = (torch.randn(M, 256, generator=g) * 2 + 0.5).to(cuda_device)
+    gamma = torch.randn(256, generator=g).to(cuda_device)
+    beta = torch.randn(256, generator=g).to(cuda_device)
+    want_x, _ = ops.gemm(a, w, bias=bias, res=x, block_n=32)
+    _, want_h = ops.layernorm(want_x, gamma, beta)
+    xin = x.clone()
+    guard = torch.full((2, M + 8, 256), 3.0, dtype=torch.bfloat16, device=cuda_device)
+    got_x, got_h = ops.gemm_res_ln(a, w, xin, gamma, beta, bias=bias, ln_split=guard[:, :M])
+    torch.cuda.synchronize()
+    assert got_x.data_ptr() == xin.data_ptr() and torch.equal(got_x, want_x)   # in place, bit-identical to the per-op GEMM
+    assert (guard[:, M:] == 3.0).all()
+    ref = torch.nn.functional.layer_norm(want_x.double(), (256,), gamma.double(), beta.double(), 1e-5)
+    assert (ops.unsplit(got_h).double() - ref).abs().max().item() <= 2e-4
+    # against the stand-alone kernel: one step of the split representation (2^-17 of the magnitude) at most
+    assert (ops.unsplit(got_h) - ops.unsplit(want_h)).abs().max().item() <= 2e-5 * ops.unsplit(want_h).abs().max().item()

@@ -243,6 +243,32 @@ def test_fused_decode_chain_equals_per_op_decode(cuda_device, monkeypatch, B, Ml
     print(f"B={B}: fused-vs-per-op step logits {err:.2e}")
 
 
+@pytest.mark.parametrize("B,Mlen", [(3, 40), (37, 532), (130, 64)])
+def test_decode_with_layernorm_in_the_residual_gemm_equals_per_op_decode(cuda_device, monkeypatch, B, Mlen):
+    """RALF_DECODE_RESLN (opt-in): the decode step with every LayerNorm but the first computed in the epilogue of the residual
+    GEMM in front of it (ralf_gemm_res_ln, cluster kernel) against the per-op launches, over a whole greedy loop: same
+    products and residual adds (bit-identical x), LayerNorm statistics summed in a different order -> step logits within
+    1e-5 of scale and identical token ids.  130 canvases: two row tiles, the second partial."""
+    from ralf_b200 import engine as E
+    from ralf_b200 import ops
+
+    eng = _engine("ralf_cgl", 7, True, cuda_device)
+    tok = helpers.make_tokenizer()
+    g = torch.Generator().manual_seed(200 + B)
+    mem_s = ops.split_bf16(torch.randn(B * Mlen, 256, generator=g).to(cuda_device))
+    outs = {}
+    for fused in (False, True):
+        monkeypatch.setattr(E, "DECODE_RESLN", fused)
+        seq, lg = eng.generate(mem_s, B, Mlen, tok.token_mask, 517, 516, tok.max_token_length, return_logits=True)
+        torch.cuda.synchronize()
+        outs[fused] = (seq.cpu().numpy(), lg.cpu().numpy())
+    np.testing.assert_array_equal(outs[True][0], outs[False][0])
+    a, b = outs[True][1], outs[False][1]
+    assert np.isfinite(a).all()
+    err = np.abs(a - b).max() / np.abs(b).max()
+    assert err <= 1e-5, err
+
+
 def test_engine_matches_reference_golden_at_batch_32(cuda_device):
     """B = 32 golden of the UNMODIFIED reference (fixture layout: test_oracle_golden.py): memory and logits of
     the first 4 canvases within 1e-3 of scale, logit summaries of all 32 within 1e-3, greedy token ids and decoded layouts
