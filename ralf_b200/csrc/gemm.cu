@@ -582,6 +582,12 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
                "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
@@ -599,7 +605,7 @@ struct TepiCfg {
   }
 };
 
-template <int BN, int NBUF>
+template <int BN, int NBUF, int F32>
 __global__ void __launch_bounds__(320, 1)
 gemm_bf16_tepi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
@@ -750,8 +756,12 @@ gemm_bf16_tepi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     auto issue_res = [&]() {  // lane 0 only: request chunk gpre
       if (gpre < total) {
         mbar_expect_tx(&rb[gpre % NBUF], TCfg::CHUNK_BYTES);
-        tma_load_3d(&tmR, &rb[gpre % NBUF], cb + (gpre % NBUF) * TCfg::CHUNK_BYTES, pre.nt * BN + half * (BN / 2) + pre.c * 32,
-                    pre.mt * 128 + quad * 32, 0);
+        if constexpr (F32)
+          tma_load_2d(&tmR, &rb[gpre % NBUF], cb + (gpre % NBUF) * TCfg::CHUNK_BYTES, pre.nt * BN + half * (BN / 2) + pre.c * 32,
+                      pre.mt * 128 + quad * 32);
+        else
+          tma_load_3d(&tmR, &rb[gpre % NBUF], cb + (gpre % NBUF) * TCfg::CHUNK_BYTES, pre.nt * BN + half * (BN / 2) + pre.c * 32,
+                      pre.mt * 128 + quad * 32, 0);
         advance(pre);
       }
       ++gpre;
@@ -759,7 +769,9 @@ gemm_bf16_tepi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (has_res && lane == 0) {
       for (int g = 0; g < NBUF - 1; ++g) issue_res();
     }
-    const int sw = (lane >> 1) & 3;  // SWIZZLE_64B: 16-byte piece j of row r sits at piece j ^ ((r >> 1) & 3)
+    // SWIZZLE_64B (split bf16 chunk, 64-byte rows): 16-byte piece j of row r sits at piece j ^ ((r >> 1) & 3);
+    // SWIZZLE_128B (fp32 chunk, 128-byte rows): at piece j ^ (r & 7)
+    const int sw = F32 ? (lane & 7) : ((lane >> 1) & 3);
     for (int g = 0; g < total; ++g, advance(cur)) {
       const int it = g / CPT, c = g % CPT, buf = it & 1;
       const int col = cur.nt * BN + half * (BN / 2) + c * 32, row = cur.mt * 128 + quad * 32;
@@ -791,7 +803,15 @@ gemm_bf16_tepi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
       }
       uint4* bq = reinterpret_cast<uint4*>(cb + (g % NBUF) * TCfg::CHUNK_BYTES);
-      if (has_res) {
+      if (has_res && F32) {
+        mbar_wait(&rb[g % NBUF], (g / NBUF) & 1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 t = bq[lane * 8 + (j ^ sw)];
+          x[4 * j] += __uint_as_float(t.x); x[4 * j + 1] += __uint_as_float(t.y);
+          x[4 * j + 2] += __uint_as_float(t.z); x[4 * j + 3] += __uint_as_float(t.w);
+        }
+      } else if (has_res) {
         mbar_wait(&rb[g % NBUF], (g / NBUF) & 1);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -812,20 +832,28 @@ gemm_bf16_tepi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
       }
+      if constexpr (F32) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t hw[4], lw[4];
+        for (int j = 0; j < 8; ++j)
+          bq[lane * 8 + (j ^ sw)] = make_uint4(__float_as_uint(x[4 * j]), __float_as_uint(x[4 * j + 1]), __float_as_uint(x[4 * j + 2]),
+                                               __float_as_uint(x[4 * j + 3]));
+      } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          split2_bf16(x[8 * j + 2 * q], x[8 * j + 2 * q + 1], hw[q], lw[q]);
+        for (int j = 0; j < 4; ++j) {
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            split2_bf16(x[8 * j + 2 * q], x[8 * j + 2 * q + 1], hw[q], lw[q]);
+          }
+          bq[lane * 4 + (j ^ sw)] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          bq[128 + lane * 4 + (j ^ sw)] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
-        bq[lane * 4 + (j ^ sw)] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        bq[128 + lane * 4 + (j ^ sw)] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
       }
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the bulk store
       __syncwarp();
       if (lane == 0) {
-        tma_store_3d(&tmO, bq, col, row, 0);
+        if constexpr (F32) tma_store_2d(&tmO, bq, col, row);
+        else tma_store_3d(&tmO, bq, col, row, 0);
         bulk_commit();
         if (has_res) {
           bulk_wait_read<1>();  // chunk g - 1's store has read its buffer: refill it with the residual of g + NBUF - 1
@@ -1374,7 +1402,37 @@ static int make_chunk_tmap(CUtensorMap* out, const void* ptr, uint64_t cols, uin
   return 0;
 }
 
-template <int BN, int NBUF>
+// fp32 flavour: [rows, cols] fp32 (row stride ld elements) as a 2-D map with 32 x 32 boxes (128-byte rows), SWIZZLE_128B.
+static int make_chunk_tmap_f32(CUtensorMap* out, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey key{ptr, cols, rows, 1, ld, 0, 32u, 32u, 0xC4u};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return 0; }
+  }
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return RALF_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 4) & 15)) return RALF_ERR_ALIGN;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "ralf_b200: cuTensorMapEncodeTiled (fp32 epilogue chunks) failed (%d)\n", (int)r);
+    return RALF_ERR_DRIVER;
+  }
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, *out);
+  return 0;
+}
+
+template <int BN, int NBUF, int F32 = 0>
 static int launch_tepi(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const CUtensorMap& to,
                        const float* bias, int act, int has_res, int post_relu, int M, int N, int K, int stages, const ConvGeom& cg,
                        cudaStream_t st) {
@@ -1382,7 +1440,7 @@ static int launch_tepi(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   const int smem = TepiCfg<BN>::smem_bytes(stages, NBUF);
   if (smem > 232448) return RALF_ERR_SHAPE;
   if (smem > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tepi_kernel<BN, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tepi_kernel<BN, NBUF, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_cuda_error(e);
     attr_bytes = smem;
   }
@@ -1390,7 +1448,7 @@ static int launch_tepi(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   const long long num_tiles = static_cast<long long>(N / BN) * tiles_m;
   const int sms = num_sms();
   dim3 grid(static_cast<unsigned>(num_tiles < sms ? num_tiles : sms));
-  const cudaError_t le = launch_pdl(gemm_bf16_tepi_kernel<BN, NBUF>, grid, dim3(320), smem, st, ta, tb, tr, to, bias, act, has_res,
+  const cudaError_t le = launch_pdl(gemm_bf16_tepi_kernel<BN, NBUF, F32>, grid, dim3(320), smem, st, ta, tb, tr, to, bias, act, has_res,
                                     post_relu, M, N, K, stages, cg);
   return set_cuda_error(le != cudaSuccess ? le : cudaGetLastError());
 }
@@ -1514,6 +1572,25 @@ static int gemm_dispatch(const RalfGemmArgs* a, const CUtensorMap& ta, int bn, c
     if (nkb == 1 && tepi_k64 == 14)
       return launch_tepi<128, 4>(ta, tb, tr, to, ep.bias, ep.act, has_res, ep.post_relu, a->M, a->N, a->K, 1, cg, st);
     return launch_tepi<128, 3>(ta, tb, tr, to, ep.bias, ep.act, has_res, ep.post_relu, a->M, a->N, a->K, 2, cg, st);
+  }
+  // fp32 flavour of the same kernel: fp32 output (+ optional fp32 residual), no split output (transformer encoder qkv / out-proj,
+  // FIDNetV3 layers); RALF_GEMM_TEPI_F32=0 switches it off
+  static const bool tepi_f32 = !(getenv("RALF_GEMM_TEPI_F32") && atoi(getenv("RALF_GEMM_TEPI_F32")) == 0);
+  if (tepi && tepi_f32 && fold_on && bn == 128 && np == 3 && !cg.enabled && a->N % 128 == 0 && a->K <= tepi_kmax &&
+      tepi_tiles >= 2 * num_sms() && ep.out_f32 && !ep.out_split && !ep.out_kv24 && !ep.res_split && a->rows_per_group <= 0 &&
+      ep.res_row_mod <= 0 && ep.vec_ok && ep.act != 2 && !a->splitk_ws) {
+    CUtensorMap tr, to;
+    rc = make_chunk_tmap_f32(&to, ep.out_f32 + ep.out_col0, a->N, a->M, ep.out_ld);
+    if (rc) return rc;
+    tr = to;
+    if (ep.res) {
+      rc = make_chunk_tmap_f32(&tr, ep.res, a->N, a->M, ep.res_ld);
+      if (rc) return rc;
+    }
+    const int nkb = (a->K + 63) / 64;
+    const int has_res = ep.res != nullptr;
+    if (nkb == 1) return launch_tepi<128, 4, 1>(ta, tb, tr, to, ep.bias, ep.act, has_res, ep.post_relu, a->M, a->N, a->K, 1, cg, st);
+    return launch_tepi<128, 3, 1>(ta, tb, tr, to, ep.bias, ep.act, has_res, ep.post_relu, a->M, a->N, a->K, 2, cg, st);
   }
 #define RALF_GEMM_CASE(BN_, NP_) \
   if (bn == BN_ && np == NP_) return launch_gemm<BN_, NP_>(ta, tb, ep, a->M, a->N, a->K, st, cg);

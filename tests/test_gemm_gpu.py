@@ -271,3 +271,32 @@ def test_gemm_residual_layernorm_cluster_kernel(cuda_device, M, K):
     assert (ops.unsplit(got_h).double() - ref).abs().max().item() <= 2e-4
     # against the stand-alone kernel: one step of the split representation (2^-17 of the magnitude) at most
     assert (ops.unsplit(got_h) - ops.unsplit(want_h)).abs().max().item() <= 2e-5 * ops.unsplit(want_h).abs().max().item()
+
+
+@pytest.mark.parametrize("M,N,K,residual,act,inplace", [
+    (32768, 768, 256, False, None, False),   # image-encoder qkv
+    (20000, 256, 256, True, None, True),     # out-projection + residual, written over the residual (M % 128 = 32)
+    (22528, 256, 64, True, "relu", False),   # one k-block: four chunk buffers
+    (19000, 384, 128, False, "relu", False),
+])
+def test_gemm_tma_epilogue_fp32_output_is_bit_identical(cuda_device, M, N, K, residual, act, inplace):
+    """fp32 flavour of the TMA-epilogue kernel (fp32 output, optional fp32 residual; 32 x 32 fp32 chunks, SWIZZLE_128B) against
+    the register-staged kernel (block_n = 64), bit for bit; canaries around the output."""
+    from ralf_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a_s = ops.split_bf16(torch.randn(M, K, generator=g).to(cuda_device))
+    w_s = ops.split_bf16((torch.randn(N, K, generator=g) / K ** 0.5).to(cuda_device))
+    bias = torch.randn(N, generator=g).to(cuda_device)
+    res = torch.randn(M, N, generator=g).to(cuda_device) if residual else None
+    want, _ = ops.gemm(a_s, w_s, bias=bias, act=act, res=res, block_n=64)
+    guard = 4096
+    flat = torch.full((M * N + 2 * guard,), 7.0, device=cuda_device)
+    out = flat[guard:guard + M * N].view(M, N)
+    if inplace:
+        out.copy_(res)
+        res = out
+    ops.gemm(a_s, w_s, bias=bias, act=act, res=res, out_f32=out)
+    torch.cuda.synchronize()
+    assert torch.equal(out, want)
+    assert (flat[:guard] == 7.0).all() and (flat[-guard:] == 7.0).all()
