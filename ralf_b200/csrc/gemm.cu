@@ -575,6 +575,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // are conflict free): the residual of chunk g + NBUF - 1 is fetched by cp.async.bulk.tensor while chunk g is computed
 // IN PLACE in its buffer and chunk g - 1 drains through a bulk tensor store.  Arithmetic and its order are those of
 // gemm_epilogue_tile, so the results are bit-identical to the register-staged path.
+// F32 = 1: the same pipeline for fp32-output GEMMs with an optional fp32 residual (transformer out-projections / qkv):
+// a chunk is [32 rows][32 columns] fp32 = 128-byte rows, SWIZZLE_128B (piece j of row r at j ^ (r & 7)), 2-D tensor maps.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
