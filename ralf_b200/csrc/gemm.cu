@@ -1551,6 +1551,11 @@ static int gemm_dispatch(const RalfGemmArgs* a, const CUtensorMap& ta, int bn, c
   static const bool fold_on = !(getenv("RALF_GEMM_FOLD") && atoi(getenv("RALF_GEMM_FOLD")) == 0);
   static const int tepi_kmax = getenv("RALF_TEPI_KMAX") ? atoi(getenv("RALF_TEPI_KMAX")) : 256;
   static const int tepi_k64 = getenv("RALF_TEPI_K64") ? atoi(getenv("RALF_TEPI_K64")) : 14;  // stages * 10 + chunk buffers
+  // Without a residual one chunk buffer per warp is enough, which leaves room for a THREE-stage operand ring
+  // (RALF_TEPI_DEEP=0: keep two stages + three buffers); RALF_TEPI_KMAX_NORES = longest K of that variant.
+  static const bool tepi_deep = !(getenv("RALF_TEPI_DEEP") && atoi(getenv("RALF_TEPI_DEEP")) == 0);
+  static const int tepi_kmax_nores = getenv("RALF_TEPI_KMAX_NORES") ? atoi(getenv("RALF_TEPI_KMAX_NORES")) : 256;
+  const int tepi_klim = (tepi_deep && !a->res && !a->res_split && tepi_kmax_nores > tepi_kmax) ? tepi_kmax_nores : tepi_kmax;
   // implicit convolutions qualify when every M tile is a full, contiguous block of 128 output rows
   const bool cg_full = !cg.enabled || (cg.Wo * cg.BH * cg.NB == 128 && cg.Ho % cg.BH == 0 && cg.B % cg.NB == 0);
   // (A BN = 64 flavour for the 64-channel layers -- stem, layer-1 conv1 / conv2 -- was measured: stem 300.0 vs 300.0 us,
@@ -1558,7 +1563,7 @@ static int gemm_dispatch(const RalfGemmArgs* a, const CUtensorMap& ta, int bn, c
   // for 128 x 64 outputs --, not by their epilogue; ncu: tensor pipe 32-40 %, DRAM 20-25 %.  Not instantiated.)
   const long long tepi_tiles = (cg.enabled ? static_cast<long long>(cg.B / (cg.NB > 0 ? cg.NB : 1)) * cg.hblocks : (a->M + 127) / 128) *
                                (a->N / 128);
-  if (tepi && fold_on && bn == 128 && np == 3 && cg_full && a->N % 128 == 0 && a->K <= tepi_kmax &&
+  if (tepi && fold_on && bn == 128 && np == 3 && cg_full && a->N % 128 == 0 && a->K <= tepi_klim &&
       tepi_tiles >= 2 * num_sms() && ep.out_split && ep.split_lo && !ep.out_f32 && !ep.out_kv24 && !ep.res &&
       a->rows_per_group <= 0 && ep.res_row_mod <= 0 && ep.vec_ok && ep.act != 2) {
     CUtensorMap tr, to;
@@ -1573,12 +1578,14 @@ static int gemm_dispatch(const RalfGemmArgs* a, const CUtensorMap& ta, int bn, c
     const int has_res = ep.res_split != nullptr;
     if (nkb == 1 && tepi_k64 == 14)
       return launch_tepi<128, 4>(ta, tb, tr, to, ep.bias, ep.act, has_res, ep.post_relu, a->M, a->N, a->K, 1, cg, st);
+    if (!has_res && tepi_deep && nkb >= 3)
+      return launch_tepi<128, 1>(ta, tb, tr, to, ep.bias, ep.act, 0, ep.post_relu, a->M, a->N, a->K, 3, cg, st);
     return launch_tepi<128, 3>(ta, tb, tr, to, ep.bias, ep.act, has_res, ep.post_relu, a->M, a->N, a->K, 2, cg, st);
   }
   // fp32 flavour of the same kernel: fp32 output (+ optional fp32 residual), no split output (transformer encoder qkv / out-proj,
   // FIDNetV3 layers); RALF_GEMM_TEPI_F32=0 switches it off
   static const bool tepi_f32 = !(getenv("RALF_GEMM_TEPI_F32") && atoi(getenv("RALF_GEMM_TEPI_F32")) == 0);
-  if (tepi && tepi_f32 && fold_on && bn == 128 && np == 3 && !cg.enabled && a->N % 128 == 0 && a->K <= tepi_kmax &&
+  if (tepi && tepi_f32 && fold_on && bn == 128 && np == 3 && !cg.enabled && a->N % 128 == 0 && a->K <= tepi_klim &&
       tepi_tiles >= 2 * num_sms() && ep.out_f32 && !ep.out_split && !ep.out_kv24 && !ep.res_split && a->rows_per_group <= 0 &&
       ep.res_row_mod <= 0 && ep.vec_ok && ep.act != 2 && !a->splitk_ws) {
     CUtensorMap tr, to;
@@ -1592,6 +1599,8 @@ static int gemm_dispatch(const RalfGemmArgs* a, const CUtensorMap& ta, int bn, c
     const int nkb = (a->K + 63) / 64;
     const int has_res = ep.res != nullptr;
     if (nkb == 1) return launch_tepi<128, 4, 1>(ta, tb, tr, to, ep.bias, ep.act, has_res, ep.post_relu, a->M, a->N, a->K, 1, cg, st);
+    if (!has_res && tepi_deep && nkb >= 3)
+      return launch_tepi<128, 1, 1>(ta, tb, tr, to, ep.bias, ep.act, 0, ep.post_relu, a->M, a->N, a->K, 3, cg, st);
     return launch_tepi<128, 3, 1>(ta, tb, tr, to, ep.bias, ep.act, has_res, ep.post_relu, a->M, a->N, a->K, 2, cg, st);
   }
 #define RALF_GEMM_CASE(BN_, NP_) \

@@ -189,6 +189,8 @@ def test_gemm_with_fused_layernorm_matches_fp64(cuda_device, M, N, act):
     (20000, 512, 128, True, None),    # layer-2 conv3: two ring stages, three chunk buffers; M % 128 = 32 (clipped boxes)
     (18950, 1024, 256, True, "relu"),  # layer-3 conv3 shape with an activation; M % 32 != 0
     (37888, 128, 64, True, None),     # two tiles per CTA and one n-tile
+    (20000, 256, 256, False, "relu"),  # no residual, K >= 192: three operand stages, ONE chunk buffer per warp
+    (19500, 384, 512, False, None),   # the same variant at K = 512 (taken only with RALF_TEPI_KMAX_NORES >= 512)
 ])
 def test_gemm_tma_epilogue_is_bit_identical_to_register_epilogue(cuda_device, M, N, K, residual, act):
     """Bottleneck-tail shape class (K <= 256, N % 128 == 0, M >= 148 tiles, split output): gemm_bf16_tepi_kernel moves the
