@@ -288,14 +288,14 @@ attention_fewkeys_kernel(const float* __restrict__ q, int ldq, const float* __re
 // QP = lanes reserved per (g, h) (16 for the short sequences, 32 for image tokens); NT = query tiles per CTA (the fusion
 // Attention reuses a canvas's K/V for 4 tiles of 32 queries).
 // ------------------------------------------------------------------------------------------------
-template <int H, int QP>
-__global__ void __launch_bounds__(256, 1)
+template <int H, int QP, int NTH>
+__global__ void __launch_bounds__(NTH, 256 / NTH)
 attention_kvsmem_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, const float* __restrict__ v,
                         int ldk, const unsigned char* __restrict__ mask, int B, int Tq, int Tk, float scale,
                         __nv_bfloat16* __restrict__ out_split, long long out_plane, float* __restrict__ out_f32, int ldo,
                         int NT) {
   constexpr int DH = 64, PITCH = DH + 4;
-  constexpr int G = 256 / (H * QP);        // groups per CTA
+  constexpr int G = NTH / (H * QP);        // groups per CTA
   constexpr int OP = H * DH + 4;           // staged output row pitch
   extern __shared__ __align__(16) float sm[];
   float* ks = sm;                                     // [G][H][Tk][PITCH]
@@ -305,18 +305,42 @@ attention_kvsmem_kernel(const float* __restrict__ q, int ldq, const float* __res
   const int tid = threadIdx.x;
   const int g0 = blockIdx.y * G;
   // ---- 1. stage K / V (and the key-padding mask) of the CTA's groups
-  const int row_f4 = H * DH / 4;  // float4 per K (or V) row
-  for (int i = tid; i < G * Tk * row_f4; i += 256) {
-    const int c4 = i % row_f4, r = i / row_f4;
-    const int j = r % Tk, g = r / Tk;
-    if (g0 + g >= B) continue;
-    const long long off = (static_cast<long long>(g0 + g) * Tk + j) * ldk + c4 * 4;
-    const float4 fk = *reinterpret_cast<const float4*>(k + off);
-    const float4 fv = *reinterpret_cast<const float4*>(v + off);
+  constexpr int row_f4 = H * DH / 4;  // float4 per K (or V) row
+  {
+    // thread = (row within a pass, float4 of the row); up to 8 rows of K and V are REQUESTED before the first is stored (the
+    // first version issued one dependent load pair per iteration: 13 global round trips per CTA, which was its run time)
+    constexpr int RPP = NTH / row_f4;  // rows per pass
+    constexpr int UNR = 8;
+    const int c4 = tid % row_f4, r0 = tid / row_f4;
     const int h = (c4 * 4) / DH, d = (c4 * 4) % DH;
-    const int so = ((g * H + h) * kFewKeysMax + j) * PITCH + d;
-    *reinterpret_cast<float4*>(ks + so) = fk;
-    *reinterpret_cast<float4*>(vs + so) = fv;
+    const int R = G * Tk;
+#pragma unroll 1
+    for (int rb = 0; rb < R; rb += RPP * UNR) {
+      float4 fk[UNR], fv[UNR];
+      int so[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int r = rb + u * RPP + r0;
+        int g = 0;  // r / Tk without a division: G <= 4
+#pragma unroll
+        for (int gg = 1; gg < G; ++gg) g += (r >= gg * Tk) ? 1 : 0;
+        const int j = r - g * Tk;
+        so[u] = -1;
+        if (r < R && g0 + g < B) {
+          const long long off = (static_cast<long long>(g0 + g) * Tk + j) * ldk + c4 * 4;
+          fk[u] = *reinterpret_cast<const float4*>(k + off);
+          fv[u] = *reinterpret_cast<const float4*>(v + off);
+          so[u] = ((g * H + h) * kFewKeysMax + j) * PITCH + d;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (so[u] >= 0) {
+          *reinterpret_cast<float4*>(ks + so[u]) = fk[u];
+          *reinterpret_cast<float4*>(vs + so[u]) = fv[u];
+        }
+      }
+    }
   }
   if (tid < G * kFewKeysMax) {
     const int g = tid / kFewKeysMax, j = tid % kFewKeysMax;
@@ -384,7 +408,7 @@ attention_kvsmem_kernel(const float* __restrict__ q, int ldq, const float* __res
       *reinterpret_cast<float4*>(mine + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
     __syncthreads();
     // ---- 3. whole output rows: row (g, tl) = H*64 contiguous floats
-    for (int i = tid; i < G * QP * row_f4; i += 256) {
+    for (int i = tid; i < G * QP * row_f4; i += NTH) {
       const int c4 = i % row_f4, r = i / row_f4;
       const int rl = r % QP, rg = r / QP;
       if (g0 + rg >= B || t0 + rl >= Tq) continue;
@@ -403,24 +427,42 @@ attention_kvsmem_kernel(const float* __restrict__ q, int ldq, const float* __res
     __syncthreads();  // the stage is rewritten by the next query tile
   }
 }
-template <int H, int QP>
-static int launch_kvsmem(const float* q, int ldq, const float* k, const float* v, int ldk, const unsigned char* mask, int B,
-                         int Tq, int Tk, float scale, void* out_split, long long out_plane, float* out_f32, int ldo,
-                         cudaStream_t st) {
-  constexpr int G = 256 / (H * QP);
+template <int H, int QP, int NTH>
+static int launch_kvsmem_n(const float* q, int ldq, const float* k, const float* v, int ldk, const unsigned char* mask, int B,
+                           int Tq, int Tk, float scale, void* out_split, long long out_plane, float* out_f32, int ldo,
+                           cudaStream_t st) {
+  constexpr int G = NTH / (H * QP);
   constexpr int SMEM = (2 * G * H * kFewKeysMax * 68 + G * QP * (H * 64 + 4)) * 4 + G * kFewKeysMax;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kvsmem_kernel<H, QP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attention_kvsmem_kernel<H, QP, NTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_kvsmem_kernel<H, QP, NTH>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                               cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return set_cuda_error(e);
     attr_set = true;
   }
   const int tiles = (Tq + QP - 1) / QP;
   const int NT = tiles >= 4 ? 4 : tiles;  // query tiles per CTA (K/V staged once for all of them)
   dim3 grid((tiles + NT - 1) / NT, (B + G - 1) / G);
-  attention_kvsmem_kernel<H, QP><<<grid, 256, SMEM, st>>>(q, ldq, k, v, ldk, mask, B, Tq, Tk, scale,
-                                                         reinterpret_cast<__nv_bfloat16*>(out_split), out_plane, out_f32, ldo, NT);
+  attention_kvsmem_kernel<H, QP, NTH><<<grid, NTH, SMEM, st>>>(q, ldq, k, v, ldk, mask, B, Tq, Tk, scale,
+                                                              reinterpret_cast<__nv_bfloat16*>(out_split), out_plane, out_f32,
+                                                              ldo, NT);
   return set_cuda_error(cudaGetLastError());
+}
+// RALF_KVSMEM_THREADS: 128 (default where two groups fit a CTA: FIDNetV3's 4 heads x 16 query lanes -- 70 KB of shared memory,
+// three CTAs per SM overlap each other's load -> compute -> store phases) or 256 (round-2 first version, one CTA per SM).
+// Same arithmetic per thread either way.
+template <int H, int QP>
+static int launch_kvsmem(const float* q, int ldq, const float* k, const float* v, int ldk, const unsigned char* mask, int B,
+                         int Tq, int Tk, float scale, void* out_split, long long out_plane, float* out_f32, int ldo,
+                         cudaStream_t st) {
+  static const int nth = getenv("RALF_KVSMEM_THREADS") ? atoi(getenv("RALF_KVSMEM_THREADS")) : 128;
+  if constexpr (H * QP <= 128) {
+    if (nth == 128)
+      return launch_kvsmem_n<H, QP, 128>(q, ldq, k, v, ldk, mask, B, Tq, Tk, scale, out_split, out_plane, out_f32, ldo, st);
+  }
+  return launch_kvsmem_n<H, QP, 256>(q, ldq, k, v, ldk, mask, B, Tq, Tk, scale, out_split, out_plane, out_f32, ldo, st);
 }
 
 // ------------------------------------------------------------------------------------------------
