@@ -347,6 +347,43 @@ def test_round2_entry_points_validate_before_touching_the_device():
     assert L.ralf_decode_chain(p, 256, 4, st, 1, None) == -1
 
 
+def test_late_round2_entry_points_validate_before_touching_the_device():
+    """ralf_conv_gemm_strided / ralf_gemm_res_ln: shape, null and alignment checks return RalfStatus codes before any CUDA
+    call (runs without a GPU)."""
+    import ctypes as C
+
+    from ralf_b200 import _lib
+
+    L = _lib.lib()
+    buf = (C.c_char * 4096)()
+    p = (C.addressof(buf) + 255) & ~255  # 256-byte aligned scratch address (never dereferenced)
+    g = _lib.GemmArgs()
+    g.A, g.W, g.lda, g.ldw, g.npass = p, p, 64, 576, 3
+    g.M, g.N, g.K = 2 * 32 * 32, 64, 9 * 64
+    assert L.ralf_conv_gemm_strided(C.byref(g), 2, 64, 64, 64, 3, 3, 3, None) == -1          # stride 1 or 2 only
+    assert L.ralf_conv_gemm_strided(C.byref(g), 2, 64, 64, 64, 3, 3, 1, None) == -1          # M must be B * Ho * Wo of THAT stride
+    g.M = 2 * 32 * 31
+    assert L.ralf_conv_gemm_strided(C.byref(g), 2, 64, 64, 64, 3, 3, 2, None) == -1
+    g.A = None
+    g.M = 2 * 32 * 32
+    assert L.ralf_conv_gemm_strided(C.byref(g), 2, 64, 64, 64, 3, 3, 2, None) == -3
+    r = _lib.GemmArgs()
+    r.A, r.W, r.lda, r.ldw, r.npass, r.M, r.N, r.K = p, p, 256, 256, 3, 8, 256, 256
+    r.res, r.res_ld, r.out_f32, r.out_ld = p, 256, p, 256
+    f = C.c_float(1e-5)
+    assert L.ralf_gemm_res_ln(C.byref(r), None, p, f, p, 8 * 256, None) == -3                  # gamma / beta / ln_split are required
+    r.N = 512
+    assert L.ralf_gemm_res_ln(C.byref(r), p, p, f, p, 8 * 256, None) == -1                     # the LayerNorm row is d_model = 256
+    r.N, r.K = 256, 200
+    assert L.ralf_gemm_res_ln(C.byref(r), p, p, f, p, 8 * 256, None) == -1                     # K in whole k-blocks
+    r.K, r.act = 256, 1
+    assert L.ralf_gemm_res_ln(C.byref(r), p, p, f, p, 8 * 256, None) == -1                     # no activation in this epilogue
+    r.act, r.res_ld = 0, 255
+    assert L.ralf_gemm_res_ln(C.byref(r), p, p, f, p, 8 * 256, None) == -2                     # rows must allow 16-byte accesses
+    r.res_ld, r.res = 256, None
+    assert L.ralf_gemm_res_ln(C.byref(r), p, p, f, p, 8 * 256, None) == -3
+
+
 def test_bench_line_assembly_with_stub_measurements():
     """The block of bench.py that turns the measurements into the contract's JSON line, executed here with stub numbers (the
     measurements themselves need a B200): every key the driver reads is present and the arithmetic holds together."""
